@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- BIGSI search hot path on B200 (BASELINE.json configs[1], weak-scaled by column shard).
+
+Workload (config.workload): synthetic m=25 000 000, h=3, k=31 index with 50 000 sample columns
+PER GPU resident in HBM (156.8 GB/GPU); one STEP = one 10 000-k-mer query run through the hot
+path: canonical+murmur3 hash kernel -> fused gather-AND-popcount kernel -> merge -> threshold at
+min_kmers = U (an exact query through the count path).  64 distinct queries rotate so that
+consecutive steps never touch the same rows (187.5 MB of rows per step > 126 MB L2).
+
+Metric: k-mer row-AND lookups/s, one lookup = gather h rows of one 50 000-column shard and AND
+them (18 750 algorithmic bytes).  At N GPUs every rank looks the same k-mers up in its own
+column shard (rank 0 broadcasts the row ids, hits are all-gathered), so the whole-job value is
+N * U * steps / time.
+
+`--impl reference` times the CPU oracle port of the reference's algorithm (oracle/, OpenMP on all
+host cores) on the same workload; see DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K, H = 31, 3
+METRIC = "kmer_row_and_lookups_per_sec"
+UNIT = "lookups/s (1 lookup = h=3 row gather+AND over one 50 000-column shard = 18 750 B)"
+N_DISTINCT = 64
+HIT_CAP = 1024
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--m", type=int, default=25_000_000, help="Bloom filter size (rows); default = BASELINE")
+    ap.add_argument("--cols", type=int, default=50_000, help="sample columns per GPU")
+    ap.add_argument("--kmers", type=int, default=10_000, help="unique k-mers per query")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prewarm", type=int, default=300, help="untimed steps before the warm-up (clock ramp)")
+    return ap.parse_args()
+
+
+def planted_columns(n_shards, cols):
+    """Per shard: 3 all-ones columns and 4 graded columns, as GLOBAL column ids."""
+    pc, pt = [], []
+    for g in range(n_shards):
+        base = g * cols
+        for c in (0, 1, cols - 1):
+            pc.append(base + c)
+            pt.append(0xFFFFFFFF)
+        for c, d in ((cols // 2, 0.95), (7, 0.6), (cols // 4 + 1, 0.41), (2 * cols // 3, 0.3)):
+            pc.append(base + c)
+            pt.append(int(d * 2 ** 32))
+    return pc, pt
+
+
+def make_queries(n, u):
+    """n distinct queries of u unique random 31-mers (seed q+1): uint8 [n, u, K]."""
+    out = np.empty((n, u, K), dtype=np.uint8)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for q in range(n):
+        rng = np.random.default_rng(q + 1)
+        arr = acgt[rng.integers(0, 4, size=(u, K))]
+        assert len(np.unique(arr, axis=0)) == u  # set(kmers) semantics: all unique already
+        out[q] = arr
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, device_index, period=0.004):
+        super().__init__(daemon=True)
+        self.period = period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        return {
+            "sm_mhz": float(np.median(self.samples)) if self.samples else None,
+            "sm_max_mhz": float(self.max_mhz) if self.max_mhz else None,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU oracle leg (cpu_baseline and --impl reference)
+# ---------------------------------------------------------------------------------------------
+class CpuArm:
+    """The oracle port of the reference's algorithm on the same synthetic workload.  Rows the
+    queries touch are regenerated from the synthetic index's pure function BEFORE timing (the
+    reference's in-memory store would hold them already)."""
+
+    def __init__(self, args, n_queries):
+        from oracle import oracle as O
+
+        self.O = O
+        self.cores = O.lib().oracle_num_threads()
+        pc, pt = planted_columns(1, args.cols)
+        self.spec = O.SynthSpec(0, 1, pc, pt)
+        self.m, self.cols, self.u = args.m, args.cols, args.kmers
+        self.queries = make_queries(n_queries, args.kmers)
+        self.stores = []
+        for q in range(n_queries):
+            r = O.hash_kmers(self.queries[q], K, H, self.m)
+            uniq, inv = np.unique(r.reshape(-1), return_inverse=True)
+            store = self.spec.rows(uniq, 0, self.cols)
+            self.stores.append((store, np.ascontiguousarray(inv.reshape(r.shape), dtype=np.int64), uniq))
+
+    def step(self, q):
+        """hash + per-k-mer AND + per-column count + threshold (graph/index.py:62-80, graph/bigsi.py:35-44,211-242)."""
+        O = self.O
+        store, slot, uniq = self.stores[q]
+        r = O.hash_kmers(self.queries[q], K, H, self.m)  # canonical + murmur3, as the reference does per query
+        # row ids -> slots of the in-memory store (the reference's dict lookup by row key)
+        slot2 = np.searchsorted(uniq, r.reshape(-1)).reshape(r.shape).astype(np.int64)
+        cnt = O.counts_from_rows(store, slot2, self.cols)
+        return np.nonzero(cnt >= self.u)[0]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    nq = max(1, min(8, args.steps + args.warmup))
+    arm = CpuArm(args, nq)
+    for i in range(args.warmup):
+        arm.step(i % nq)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        hits = arm.step((args.warmup + i) % nq)
+    dt = time.perf_counter() - t0
+    assert len(hits) >= 3
+    value = args.kmers * args.steps / dt
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port",
+                         "sample": "every step = one full %d-k-mer query on one %d-column shard (rows it touches "
+                                   "pre-generated in host RAM, %d distinct queries rotating)" % (args.kmers, args.cols, nq)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": "BASELINE configs[1]: synthetic m=%d h=%d k=%d, N=%d columns per GPU (x%d GPUs, column-sharded), "
+                    "one %d-k-mer exact query (min_kmers=U) per step through hash + fused gather-AND-popcount + merge + "
+                    "threshold" % (args.m, H, K, args.cols, n_gpus, args.kmers),
+        "m": args.m, "h": H, "k": K, "cols_per_gpu": args.cols, "kmers_per_query": args.kmers,
+        "distinct_queries": N_DISTINCT,
+        "l2_policy": "inputs larger than L2: each step gathers %.1f MB of distinct rows, %d distinct queries rotate"
+                     % (args.kmers * H * math.ceil(args.cols / 8) / 1e6, N_DISTINCT),
+        "matrix_density": 0.5,
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import bigsi_b200
+    from bigsi_b200.sharded import DeviceShard, ShardedSearcher, unpack_hits
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU oracle")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    U, cols = args.kmers, args.cols
+    pc, pt = planted_columns(world, cols)
+    index = bigsi_b200.DeviceIndex(args.m, cols, col_offset=rank * cols, device=local_rank)
+    t0 = time.perf_counter()
+    index.fill_synthetic(0, 1, pc, pt)
+    fill_s = time.perf_counter() - t0
+    shard = DeviceShard(index, K, H, cap=HIT_CAP)
+    searcher = ShardedSearcher(shard, dist if world > 1 else None, world, rank)
+
+    queries = make_queries(N_DISTINCT, U)
+    d_queries = torch.from_numpy(queries).to(dev)  # resident k-mer bytes (value arm)
+    h_queries = torch.from_numpy(queries).pin_memory()  # pinned host copy (e2e arm)
+    d_qoff = torch.tensor([0, U], dtype=torch.int64, device=dev)
+    d_min = torch.tensor([U], dtype=torch.int32, device=dev)
+    h_min = np.array([U], dtype=np.uint32)
+    h_qoff = np.array([0, U], dtype=np.int64)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def dev_step(i):
+        return searcher.search_step(d_queries[i % N_DISTINCT], d_qoff, d_min, 1, U)
+
+    # ---- correctness gate on the first query (planted all-ones columns must be the exact hits)
+    g = dev_step(0)
+    torch.cuda.synchronize()
+    n, hc, hv = unpack_hits(g.cpu().numpy(), 1, HIT_CAP)
+    for r in range(world):
+        got = sorted(hc[r, 0, : int(n[r, 0])].tolist())
+        assert got == [0, 1, cols - 1], "rank %d: unexpected exact hits %r" % (r, got[:10])
+
+    # ---- pre-warm (clocks), then W warm-up steps, then K timed steps: device-resident inputs
+    for i in range(args.prewarm):
+        dev_step(i)
+    barrier()
+    for i in range(args.warmup):
+        dev_step(i)
+    barrier()
+    launches0 = index.info()["kernel_launches"]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        dev_step(args.warmup + i)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = index.info()["kernel_launches"] - launches0
+    launches += args.steps * (2 if rank == 0 else 1)  # hash (rank 0) + threshold kernels are handle-less
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * U * args.steps / (ms_max * 1e-3)
+
+    # ---- roofline pass: same K steps with the fused kernel bracketed by CUDA events on its stream
+    index.set_option("timing", 1)
+    for i in range(args.steps):
+        dev_step(args.warmup + i)
+    barrier()
+    fused_ms, merge_ms, n_timed = index.timing_collect()
+    index.set_option("timing", 0)
+    info = index.info()
+    fused_avg_ms = fused_ms / max(n_timed, 1)
+    merge_avg_ms = merge_ms / max(n_timed, 1)
+    algo_bytes = info["last_algorithmic_bytes"]
+    achieved = algo_bytes / (fused_avg_ms * 1e-3) / 1e9
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as f:
+            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "fused_query_dram_bytes.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- e2e arm: the C-ABI host call (N=1) / pinned host -> device -> exchange -> host (N>1)
+    def e2e_step(i):
+        q = i % N_DISTINCT
+        if world == 1:
+            return index.search_kmers_hits(h_queries[q].numpy(), K, H, h_min, q_offsets=h_qoff, cap=HIT_CAP)[0]
+        d_k = h_queries[q].to(dev, non_blocking=True) if rank == 0 else d_queries[q]
+        g = searcher.search_step(d_k, d_qoff, d_min, 1, U)
+        return g.cpu() if rank == 0 else None
+
+    for i in range(max(args.warmup, 3)):
+        e2e_step(i)
+    barrier()
+    e2e_steps = min(args.steps, 500)
+    w0 = time.perf_counter()
+    for i in range(e2e_steps):
+        res = e2e_step(args.warmup + i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0  # host calls synchronise every step, so wall clock == device time + host overhead
+    barrier()
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * U * e2e_steps / float(te.item())
+    n_hits = 3
+    h2d = U * K + 16 + 4
+    d2h = 8 + n_hits * 8 if world == 1 else world * (2 + 2 * HIT_CAP) * 4
+
+    # ---- AND-mode (exact_filter) kernel, for context
+    d_rows0 = shard.hash(d_queries[0])
+    d_and = torch.empty((1, (cols + 7) // 8 + 16), dtype=torch.uint8, device=dev)
+    index.set_option("timing", 1)
+    for i in range(20):
+        r = shard.hash(d_queries[i % N_DISTINCT])
+        index.query_dev(1, r.data_ptr(), d_qoff.data_ptr(), 1, U, H, d_and.data_ptr(), d_and.shape[1],
+                        torch.cuda.current_stream().cuda_stream, U)
+    torch.cuda.synchronize()
+    and_ms, and_merge_ms, and_n = index.timing_collect()
+    index.set_option("timing", 0)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = run_cpu_baseline(args)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitwise (LOP3) / u32 counts", "data": "synthetic",
+            "config": workload_config(args, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": 1e3 * float(te.item()) / e2e_steps,
+                    "path": "bigsi_b200_search_kmers_hits (C ABI, pinned host buffers)" if world == 1 else
+                            "pinned host k-mers -> H2D -> hash -> NCCL broadcast -> fused query -> threshold -> NCCL all-gather -> D2H"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "fused_query<COUNTS,h=3>", "kernel_ms": fused_avg_ms,
+                         "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
+                         "frac_of_8TBps_nominal": achieved / 8000.0, "merge_kernel_ms": merge_avg_ms,
+                         "launches_timed": int(n_timed)},
+            "and_mode": {"kernel_ms": and_ms / max(and_n, 1), "achieved_GBps": algo_bytes / (and_ms / max(and_n, 1) * 1e-3) / 1e9,
+                         "merge_kernel_ms": and_merge_ms / max(and_n, 1)},
+            "launch_geometry": {kk: info[kk] for kk in ("last_grid", "last_block", "last_smem_bytes", "last_tile_bytes",
+                                                        "last_n_tiles", "last_kmers_per_stage", "last_n_stages",
+                                                        "last_n_slices")},
+            "index": {"matrix_bytes": info["matrix_bytes"], "row_pitch_bytes": info["row_pitch_bytes"], "fill_seconds": fill_s},
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    index.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_cpu_baseline(args):
+    """Bounded sample of the same workload on the host cores (oracle port, all threads)."""
+    nq = 4
+    arm = CpuArm(args, nq)
+    arm.step(0)
+    t0 = time.perf_counter()
+    done = 0
+    while True:
+        arm.step(done % nq)
+        done += 1
+        dt = time.perf_counter() - t0
+        if dt >= args.cpu_seconds or done >= 2000:
+            break
+    return {"value": args.kmers * done / dt, "unit": UNIT, "cores": arm.cores, "kind": "port",
+            "sample": "%d full %d-k-mer queries (%d distinct, rotating) on one %d-column shard in %.1f s; rows "
+                      "pre-generated in host RAM; hash + AND + per-column count + threshold, OpenMP"
+                      % (done, args.kmers, nq, args.cols, dt)}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

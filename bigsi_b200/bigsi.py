@@ -1,0 +1,302 @@
+"""BIGSI: drop-in for the reference's public class on the search path.
+
+Mirrors bigsi/graph/bigsi.py:129-275 (constructor from a config dict, classmethods bloom/build,
+insert, search, lookup, delete, result dict layout) while the data plane is the HBM-resident
+DeviceIndex + the fused CUDA kernel:
+
+  reference                                              here
+  ------------------------------------------------------ -------------------------------------------
+  get_storage(config) (storage/__init__.py:18-19)        process-resident store keyed by config
+  KmerSignatureIndex.lookup (graph/index.py:42-80)       bigsi_b200_lookup_kmers (hash + gather-AND)
+  exact_filter (graph/bigsi.py:192-205)                  bigsi_b200_search_kmers  MODE_AND
+  inexact_filter (graph/bigsi.py:211-230)                bigsi_b200_search_kmers_hits (counts + threshold)
+
+The reference constructs BIGSI(config) per request/worker (bigsi/__main__.py:204,76); the GPU
+index is therefore cached per process, keyed by the storage name, and never re-uploaded per call.
+"""
+import logging
+import math
+
+import numpy as np
+
+from . import bits as _bits
+from ._lib import MODE_AND, MODE_COUNTS
+from .bloom import BloomFilter
+from .index import DeviceIndex, hash_kmers, kmers_to_array
+from .metadata import DELETION_SPECIAL_SAMPLE_NAME, SampleMetadata
+from .utils import convert_query_kmers, seq_to_kmers, unique_kmers
+
+logger = logging.getLogger(__name__)
+
+DEFAULT_CONFIG = {  # bigsi/constants.py:13-19 with the HBM engine in place of a KV backend
+    "h": 3,
+    "k": 31,
+    "m": 25 * 10 ** 6,
+    "storage-engine": "b200",
+    "storage-config": {"filename": "bigsi-b200-default", "device": 0},
+}
+DEFAULT_NPROC = 4
+MIN_UNIQUE_KMERS_IN_QUERY = 0
+
+_STORES = {}  # storage name -> _Store (the process-resident replacement of the KV store)
+
+
+class _Store:
+    """What the reference keeps in its KV store: the bit matrix, ksi:* and metadata:* keys."""
+
+    def __init__(self, index, m, h, k):
+        self.index = index
+        self.bloomfilter_size = m
+        self.num_hashes = h
+        self.kmer_size = k
+        self.meta = {}
+
+    def close(self):
+        self.index.close()
+
+
+def _store_name(config):
+    sc = config.get("storage-config", {}) or {}
+    return str(sc.get("filename", sc.get("name", "bigsi-b200-default")))
+
+
+def _device(config):
+    return int((config.get("storage-config", {}) or {}).get("device", 0))
+
+
+def validate_build_params(bloomfilters, samples):
+    if not len(bloomfilters) == len(samples):
+        raise ValueError("There must be the same number of bloomfilters and sample names")
+
+
+class BigsiQueryResult:
+    """bigsi/graph/bigsi.py:91-126."""
+
+    PERCENT_KMERS_FOUND_KEY = "percent_kmers_found"
+    NUM_KMERS_KEY = "num_kmers"
+    NUM_KMERS_FOUND_KEY = "num_kmers_found"
+    SAMPLE_KEY = "sample_name"
+
+    def __init__(self, colour, sample_name, num_kmers_found, num_kmers):
+        self.colour = colour
+        self.sample_name = sample_name
+        self.num_kmers_found = num_kmers_found
+        self.num_kmers = num_kmers
+        self.percent_kmers_found = round(100 * float(num_kmers_found) / num_kmers, 2)
+        self.score = None
+
+    def todict(self):
+        outd = {
+            self.PERCENT_KMERS_FOUND_KEY: self.percent_kmers_found,
+            self.NUM_KMERS_KEY: self.num_kmers,
+            self.NUM_KMERS_FOUND_KEY: self.num_kmers_found,
+            self.SAMPLE_KEY: self.sample_name,
+        }
+        if self.score:
+            outd.update(self.score)
+        return outd
+
+    def __eq__(self, ob):
+        return self.todict() == ob.todict()
+
+    def add_score(self, score):
+        self.score = score
+
+
+class BIGSI(SampleMetadata):
+    def __init__(self, config=None):
+        if config is None:
+            config = DEFAULT_CONFIG
+        self.config = config
+        name = _store_name(config)
+        if name not in _STORES:
+            # the reference raises KeyError from storage.get_integer on an empty store
+            # (graph/index.py:24, matrix/bitmatrix.py:16-17)
+            raise KeyError("no index has been built for storage '%s'" % name)
+        self._store = _STORES[name]
+        SampleMetadata.__init__(self, self._store.meta)
+        self.min_unique_kmers_in_query = MIN_UNIQUE_KMERS_IN_QUERY
+
+    # -- properties ------------------------------------------------------------
+    @property
+    def index(self):
+        return self._store.index
+
+    @property
+    def kmer_size(self):
+        return self.config["k"]
+
+    @property
+    def nproc(self):
+        return self.config.get("nproc", DEFAULT_NPROC)
+
+    @property
+    def bloomfilter_size(self):
+        return self._store.bloomfilter_size
+
+    @property
+    def num_hashes(self):
+        return self._store.num_hashes
+
+    # -- build path ------------------------------------------------------------
+    @classmethod
+    def bloom(cls, config, kmers):
+        """graph/bigsi.py:150-155: canonical k-mers -> Bloom filter bitarray (hashing on the GPU)."""
+        kmers = convert_query_kmers(kmers)
+        bloomfilter = BloomFilter(m=config["m"], h=config["h"], device=_device(config))
+        bloomfilter.update(kmers)
+        return bloomfilter.bitarray
+
+    @classmethod
+    def build(cls, config, bloomfilters, samples):
+        """graph/bigsi.py:157-172: N Bloom filters become the N columns of the m x N matrix."""
+        validate_build_params(bloomfilters, samples)
+        m, h, k = config["m"], config["h"], config["k"]
+        name = _store_name(config)
+        if name in _STORES:
+            _STORES.pop(name).close()
+        n = len(bloomfilters)
+        sc = config.get("storage-config", {}) or {}
+        capacity = int(sc.get("col_capacity", 0)) or max(n, 1)
+        index = DeviceIndex(m, n, col_capacity=capacity, col_offset=0, device=_device(config))
+        store = _Store(index, m, h, k)
+        try:
+            SampleMetadata(store.meta).add_samples(samples)
+            packed = []
+            for bf in bloomfilters:
+                if isinstance(bf, BloomFilter):
+                    bf = bf.bitarray
+                p = _bits.to_packed(bf, m)
+                if p.size * 8 < m:
+                    raise ValueError("bloom filter shorter than m=%d bits" % m)
+                packed.append(p[: (m + 7) // 8])
+            # matrix/transpose.py:33-43: N filters of m bits -> m rows of N bits, in row chunks
+            if n:
+                rows_per_chunk = max(1, (1 << 26) // max(n, 1))
+                for r0 in range(0, m, rows_per_chunk):
+                    r1 = min(m, r0 + rows_per_chunk)
+                    b0, b1 = r0 // 8, (r1 + 7) // 8
+                    X = np.stack([np.unpackbits(p[b0:b1])[r0 - b0 * 8 : r1 - b0 * 8] for p in packed], axis=1)
+                    index.upload_rows(r0, np.packbits(X, axis=1))
+        except Exception:
+            store.close()
+            raise
+        _STORES[name] = store
+        return cls(config)
+
+    def insert(self, bloomfilter, sample):
+        """graph/bigsi.py:244-247 -> matrix/bitmatrix.py:67-75 (column = new count - 1)."""
+        logger.warning("Build and merge is preferable to insert in most cases")
+        colour = self.add_sample(sample)
+        self.insert_bloom(bloomfilter, colour - 1)
+
+    def insert_bloom(self, bloomfilter, column_index):
+        if isinstance(bloomfilter, BloomFilter):
+            bloomfilter = bloomfilter.bitarray
+        m = self.bloomfilter_size
+        p = _bits.to_packed(bloomfilter, m)
+        nbits = _bits.nbits_of(bloomfilter)
+        nbits = m if nbits is None else min(nbits, m)
+        info = self.index.info()
+        if column_index >= info["col_capacity"]:
+            self._grow(max(column_index + 1, 2 * info["col_capacity"]))
+        self.index.set_column(column_index, p, nbits)
+
+    def _grow(self, new_capacity):
+        """Re-pitch the matrix when an insert exceeds the column capacity (host round trip)."""
+        old = self.index
+        info = old.info()
+        new = DeviceIndex(info["num_rows"], info["num_cols"], col_capacity=new_capacity,
+                          col_offset=info["col_offset"], device=info["device"])
+        step = max(1, (1 << 26) // max(info["row_bytes"], 1))
+        for r0 in range(0, info["num_rows"], step):
+            n = min(step, info["num_rows"] - r0)
+            new.upload_rows(r0, old.download_rows(r0, n))
+        self._store.index = new
+        old.close()
+
+    def delete(self):
+        """graph/bigsi.py:249-250: storage.delete_all()."""
+        name = _store_name(self.config)
+        st = _STORES.pop(name, None)
+        if st is not None:
+            st.close()
+
+    def merge(self, bigsi):
+        raise NotImplementedError("merge is an offline maintenance path outside the GPU search scope (DESIGN.md)")
+
+    # -- query path ------------------------------------------------------------
+    def seq_to_kmers(self, seq):
+        return seq_to_kmers(seq, self.kmer_size)
+
+    def lookup(self, kmers, remove_trailing_zeros=True):
+        """graph/index.py:42-49: {raw k-mer: bitarray of the samples that contain it}."""
+        if isinstance(kmers, str):
+            kmers = [kmers]
+        uk = unique_kmers(kmers)
+        if not uk:
+            return {}
+        klen = len(uk[0])
+        n = self.index.num_cols
+        packed = self.index.lookup_kmers(kmers_to_array(uk, klen), klen, self.num_hashes)
+        nbits = n if remove_trailing_zeros else 8 * ((n + 7) // 8)
+        return {km: _bits.from_packed(packed[i], nbits) for i, km in enumerate(uk)}
+
+    def search(self, seq, threshold=1.0, score=False):
+        """graph/bigsi.py:174-190."""
+        self.__validate_search_query(seq)
+        assert threshold <= 1
+        kmers = list(self.seq_to_kmers(seq))
+        uk = unique_kmers(kmers)
+        num_kmers = len(uk)
+        if num_kmers == 0:
+            # the reference reduces over an empty list of per-k-mer vectors (utils/fncts.py:24-25)
+            raise TypeError("reduce() of empty iterable with no initial value")
+        min_kmers = math.ceil(num_kmers * threshold)
+        arr = kmers_to_array(uk, self.kmer_size)
+        if threshold == 1.0:
+            results = self.exact_filter(arr, num_kmers)
+        else:
+            results = self.inexact_filter(arr, num_kmers, min_kmers)
+        if score:
+            self.score(kmers, uk, results)
+        return [r.todict() for r in results if not r.sample_name == DELETION_SPECIAL_SAMPLE_NAME]
+
+    def exact_filter(self, kmer_array, num_kmers):
+        """graph/bigsi.py:192-205: colours whose column is set for every k-mer, ascending."""
+        n = self.num_samples
+        presence = self.index.search_kmers(kmer_array, self.kmer_size, self.num_hashes, mode=MODE_AND)[0]
+        colours = np.nonzero(np.unpackbits(presence)[:n])[0].tolist()
+        names = self.colours_to_samples(colours)
+        return [BigsiQueryResult(colour=c, sample_name=names[c], num_kmers=num_kmers, num_kmers_found=num_kmers)
+                for c in colours]
+
+    def inexact_filter(self, kmer_array, num_kmers, min_kmers):
+        """graph/bigsi.py:211-230: per-sample k-mer counts >= min_kmers, stable sort by count desc."""
+        n = self.num_samples
+        if min_kmers <= 0:
+            counts = self.index.search_kmers(kmer_array, self.kmer_size, self.num_hashes, mode=MODE_COUNTS)[0][:n]
+            colours, found = np.arange(n), counts
+        else:
+            colours, found, total = self.index.search_kmers_hits(kmer_array, self.kmer_size, self.num_hashes,
+                                                                 [min(min_kmers, 0xFFFFFFFF)])[0]
+            keep = colours < n
+            colours, found = colours[keep], found[keep]
+        order = np.argsort(-found.astype(np.int64), kind="stable")  # ties stay in ascending colour
+        return [BigsiQueryResult(colour=int(colours[i]), sample_name=self.colour_to_sample(int(colours[i])),
+                                 num_kmers_found=int(found[i]), num_kmers=num_kmers) for i in order]
+
+    def score(self, kmers, unique, results):
+        raise NotImplementedError("score=True (Scorer post-processing) is listed under 'next' in DESIGN.md")
+
+    def __validate_search_query(self, seq):
+        kmers = set()
+        for k in self.seq_to_kmers(seq):
+            kmers.add(k)
+            if len(kmers) > self.min_unique_kmers_in_query:
+                return True
+        logger.warning(
+            "Query string should contain at least %i unique kmers. Your query contained %i unique kmers, and as a "
+            "result the false discovery rate may be high. In future this will become an error."
+            % (self.min_unique_kmers_in_query, len(kmers))
+        )

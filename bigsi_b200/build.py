@@ -1,0 +1,58 @@
+"""Builds bigsi_b200/libbigsi_b200.so (hand-written sm_100a CUDA + the C ABI) with nvcc, in-tree.
+
+The library is the product: there is no CPU or PyTorch fallback.  `python -m bigsi_b200.build`
+or `__graft_entry__.build()` compile it; importing `bigsi_b200` never compiles anything.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libbigsi_b200.so")
+SOURCES = ["capi.cu", "query_kernels.cu", "aux_kernels.cu"]
+HEADERS = ["ptx.cuh", "query.cuh", os.path.join("..", "..", "include", "bigsi_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O3,-Wall",
+    "--shared",
+]
+
+
+def find_nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+
+
+def is_stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False, extra_flags=()):
+    """Compile the library if any source is newer than it.  Returns the .so path."""
+    if not force and not is_stale():
+        return LIB_PATH
+    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra_flags)
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout)
+        raise RuntimeError("nvcc failed building libbigsi_b200.so")
+    if verbose:
+        print(res.stdout)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,302 @@
+// Helper kernels around the fused query kernel: k-mer hashing, per-k-mer lookup vectors,
+// threshold/compaction, column insert and the synthetic index generator.
+#include "ptx.cuh"
+#include "query.cuh"
+
+namespace bigsi {
+
+// ------------------------------------------------------------------------------------------
+// K1: canonical k-mer + MurmurHash3_x86_32, seeds 0..h-1, signed, floor-mod m.
+// Replaces convert_query_kmer/canonical (bigsi/utils/fncts.py:38-54) and _hash/generate_hashes
+// (bigsi/bloom/bloomfilter.py:5-13; third-party mmh3 2.5.1 = MurmurHash3_x86_32).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t comp_base(uint32_t b)
+{
+    // only A<->T and C<->G are complemented (utils/fncts.py:12); anything else passes through
+    return b == 'A' ? 'T' : b == 'T' ? 'A' : b == 'C' ? 'G' : b == 'G' ? 'C' : b;
+}
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
+
+__global__ void __launch_bounds__(128) hash_kmers_kernel(const uint8_t *__restrict__ kmers, uint64_t n, int k, int h,
+                                                         uint64_t m, int canonical, int32_t *__restrict__ rows_out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *s = kmers + i * (uint64_t)k;
+    // orientation: forward unless the reverse complement is lexicographically smaller
+    bool fwd = true;
+    if (canonical) {
+        for (int j = 0; j < k; ++j) {
+            const uint32_t a = s[j], b = comp_base(s[k - 1 - j]);
+            if (a != b) {
+                fwd = a < b;
+                break;
+            }
+        }
+    }
+    auto byte_at = [&](int j) -> uint32_t { return fwd ? (uint32_t)s[j] : comp_base(s[k - 1 - j]); };
+    const int nblocks = k >> 2;
+    for (int seed = 0; seed < h; ++seed) {
+        uint32_t h1 = (uint32_t)seed;
+        for (int b = 0; b < nblocks; ++b) {
+            uint32_t k1 = byte_at(4 * b) | (byte_at(4 * b + 1) << 8) | (byte_at(4 * b + 2) << 16) |
+                          (byte_at(4 * b + 3) << 24);
+            k1 *= 0xcc9e2d51u;
+            k1 = rotl32(k1, 15);
+            k1 *= 0x1b873593u;
+            h1 ^= k1;
+            h1 = rotl32(h1, 13);
+            h1 = h1 * 5u + 0xe6546b64u;
+        }
+        uint32_t k1 = 0;
+        const int t = 4 * nblocks;
+        switch (k & 3) {
+        case 3: k1 ^= byte_at(t + 2) << 16;  // fallthrough
+        case 2: k1 ^= byte_at(t + 1) << 8;   // fallthrough
+        case 1:
+            k1 ^= byte_at(t);
+            k1 *= 0xcc9e2d51u;
+            k1 = rotl32(k1, 15);
+            k1 *= 0x1b873593u;
+            h1 ^= k1;
+        }
+        h1 ^= (uint32_t)k;
+        h1 ^= h1 >> 16;
+        h1 *= 0x85ebca6bu;
+        h1 ^= h1 >> 13;
+        h1 *= 0xc2b2ae35u;
+        h1 ^= h1 >> 16;
+        long long r = (long long)(int32_t)h1 % (long long)m;  // Python floor-mod of the SIGNED hash
+        if (r < 0) r += (long long)m;
+        rows_out[i * (uint64_t)h + seed] = (int32_t)r;
+    }
+}
+
+cudaError_t launch_hash_kmers(const char *d_kmers, uint64_t n, int k, int h, uint64_t m, int canonical,
+                              int32_t *d_rows_out, cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    const uint64_t blocks = (n + 127) / 128;
+    hash_kmers_kernel<<<(unsigned)blocks, 128, 0, stream>>>(reinterpret_cast<const uint8_t *>(d_kmers), n, k, h, m,
+                                                            canonical, d_rows_out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: per-k-mer AND vectors (KmerSignatureIndex.lookup, bigsi/graph/index.py:42-49,75-80).
+// One thread per (k-mer, 16-byte unit); output keeps the reference's MSB-first bytes.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lookup_kernel(const uint8_t *__restrict__ matrix, uint64_t pitch,
+                                                     uint32_t row_bytes, uint32_t units, const int32_t *__restrict__ rows,
+                                                     uint64_t n_kmers, int h, uint8_t *__restrict__ out,
+                                                     uint64_t out_stride)
+{
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t km = tid / units;
+    const uint32_t u = (uint32_t)(tid % units);
+    if (km >= n_kmers) return;
+    uint4 acc = make_uint4(~0u, ~0u, ~0u, ~0u);
+    for (int j = 0; j < h; ++j) {
+        const uint4 v = ldg128_stream(matrix + (uint64_t)(uint32_t)__ldg(rows + km * h + j) * pitch + u * 16);
+        acc.x &= v.x; acc.y &= v.y; acc.z &= v.z; acc.w &= v.w;
+    }
+    uint8_t *dst = out + km * out_stride + u * 16;
+    const uint32_t remain = row_bytes - u * 16;
+    if (remain >= 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        *reinterpret_cast<uint4 *>(dst) = acc;
+    } else {
+        const uint32_t w[4] = {acc.x, acc.y, acc.z, acc.w};
+        for (uint32_t b = 0; b < min(remain, 16u); ++b) dst[b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+    }
+}
+
+cudaError_t launch_lookup(const uint8_t *matrix, uint64_t pitch, uint32_t row_bytes, const int32_t *d_rows,
+                          uint64_t n_kmers, int h, uint8_t *d_out, uint64_t out_stride, cudaStream_t stream)
+{
+    if (n_kmers == 0 || row_bytes == 0) return cudaSuccess;
+    const uint32_t units = (row_bytes + 15) / 16;
+    const uint64_t threads = n_kmers * units;
+    const uint64_t blocks = (threads + 255) / 256;
+    if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    lookup_kernel<<<(unsigned)blocks, 256, 0, stream>>>(matrix, pitch, row_bytes, units, d_rows, n_kmers, h, d_out,
+                                                        out_stride);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// counts >= min_kmers -> compact (colour, count) pairs (bigsi/graph/bigsi.py:241-242).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) threshold_kernel(const uint32_t *__restrict__ counts, uint64_t counts_stride,
+                                                        uint32_t num_cols, const uint32_t *__restrict__ min_kmers,
+                                                        int32_t *__restrict__ cols_out, uint32_t *__restrict__ counts_out,
+                                                        uint64_t cap, unsigned long long *__restrict__ n_out)
+{
+    __shared__ uint32_t warp_cnt[8];
+    __shared__ unsigned long long block_base;
+    const uint32_t q = blockIdx.y;
+    const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t thr = __ldg(min_kmers + q);
+    uint32_t c = 0;
+    bool hit = false;
+    if (col < num_cols) {
+        c = __ldg(counts + (uint64_t)q * counts_stride + col);
+        hit = c >= thr;
+    }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) warp_cnt[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t t = warp_cnt[w];
+            warp_cnt[w] = tot;
+            tot += t;
+        }
+        block_base = tot ? atomicAdd(n_out + q, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    if (hit) {
+        const uint64_t pos = block_base + warp_cnt[warp] + __popc(ballot & ((1u << lane) - 1));
+        if (pos < cap) {
+            cols_out[(uint64_t)q * cap + pos] = (int32_t)col;
+            counts_out[(uint64_t)q * cap + pos] = c;
+        }
+    }
+}
+
+cudaError_t launch_threshold(const uint32_t *d_counts, uint64_t counts_stride, uint64_t n_queries, uint64_t num_cols,
+                             const uint32_t *d_min_kmers, int32_t *d_cols_out, uint32_t *d_counts_out, uint64_t cap,
+                             unsigned long long *d_n_out, cudaStream_t stream)
+{
+    if (n_queries == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(d_n_out, 0, n_queries * sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    if (num_cols == 0) return cudaSuccess;
+    if (n_queries > 65535) return cudaErrorInvalidConfiguration;
+    dim3 grid((unsigned)((num_cols + 255) / 256), (unsigned)n_queries);
+    threshold_kernel<<<grid, 256, 0, stream>>>(d_counts, counts_stride, (uint32_t)num_cols, d_min_kmers, d_cols_out,
+                                               d_counts_out, cap, d_n_out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: insert_column (bigsi/matrix/bitmatrix.py:67-75 -> storage/base.py:111-122): one thread per row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) set_column_kernel(uint8_t *__restrict__ matrix, uint64_t pitch, uint64_t num_rows,
+                                                         uint64_t col, const uint8_t *__restrict__ bloom, uint64_t n_bits)
+{
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= num_rows) return;
+    const uint32_t bit = r < n_bits ? (bloom[r >> 3] >> (7 - (r & 7))) & 1u : 0u;
+    uint8_t *p = matrix + r * pitch + (col >> 3);
+    const uint8_t mask = (uint8_t)(0x80u >> (col & 7));
+    const uint8_t v = *p;
+    *p = bit ? (uint8_t)(v | mask) : (uint8_t)(v & ~mask);
+}
+
+cudaError_t launch_set_column(uint8_t *matrix, uint64_t pitch, uint64_t num_rows, uint64_t col, const uint8_t *d_bloom,
+                              uint64_t n_bits, cudaStream_t stream)
+{
+    if (num_rows == 0) return cudaSuccess;
+    const uint64_t blocks = (num_rows + 255) / 256;
+    set_column_kernel<<<(unsigned)blocks, 256, 0, stream>>>(matrix, pitch, num_rows, col, d_bloom, n_bits);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K7: synthetic index, a pure function of (seed, row, GLOBAL column).  Same arithmetic as
+// oracle/bigsi_oracle.c oracle_synth_row (the spec is in DESIGN.md "Synthetic index").
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z)
+{
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t synth_row_key(uint64_t seed, uint64_t row)
+{
+    return mix64(seed ^ (row * 0xd1b54a32d192ed03ull));
+}
+__device__ __forceinline__ uint64_t synth_word(uint64_t rk, uint64_t W, int and_draws)
+{
+    uint64_t w = ~0ull;
+    for (int i = 0; i < and_draws; ++i) w &= mix64(rk + (W * 4 + (uint64_t)i) * 0x9e3779b97f4a7c15ull);
+    return w;
+}
+__device__ __forceinline__ uint32_t synth_plant_u32(uint64_t rk, uint64_t col)
+{
+    return (uint32_t)(mix64(rk ^ (col * 0xc2b2ae3d27d4eb4full + 0x165667b19e3779f9ull)) >> 32);
+}
+
+// one thread per (row, 8 local bytes); the whole pitch is written (padding = 0)
+__global__ void __launch_bounds__(256) fill_synthetic_kernel(uint8_t *__restrict__ matrix, uint64_t pitch,
+                                                             uint64_t num_rows, uint64_t num_cols, uint64_t col_offset,
+                                                             uint64_t seed, int and_draws)
+{
+    const uint32_t wpr = (uint32_t)(pitch >> 3);  // 8-byte words per row
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t row = tid / wpr;
+    const uint32_t j = (uint32_t)(tid % wpr);
+    if (row >= num_rows) return;
+    const uint64_t rk = synth_row_key(seed, row);
+    const uint64_t gb = (col_offset >> 3) + (uint64_t)j * 8;  // global byte of local byte 8j
+    const uint64_t W = gb >> 3;
+    const uint32_t sh = (uint32_t)(gb & 7) * 8;
+    uint64_t v = synth_word(rk, W, and_draws) >> sh;
+    if (sh) v |= synth_word(rk, W + 1, and_draws) << (64 - sh);
+    // zero the columns >= num_cols: local byte b holds columns 8b..8b+7, MSB first
+    const uint64_t first_col = (uint64_t)j * 64;
+    if (first_col >= num_cols) {
+        v = 0;
+    } else if (first_col + 64 > num_cols) {
+        const uint32_t keep = (uint32_t)(num_cols - first_col);  // 1..63 valid columns
+        const uint32_t full_bytes = keep >> 3, rem = keep & 7;
+        uint64_t mask = full_bytes ? (~0ull >> (64 - 8 * full_bytes)) : 0ull;
+        if (rem) mask |= (uint64_t)(0xff00u >> rem & 0xffu) << (8 * full_bytes);
+        v &= mask;
+    }
+    *reinterpret_cast<uint64_t *>(matrix + row * pitch + (uint64_t)j * 8) = v;
+}
+
+// planted columns: one thread per row walks the (short) planted list, so there are no races
+__global__ void __launch_bounds__(256) plant_columns_kernel(uint8_t *__restrict__ matrix, uint64_t pitch,
+                                                            uint64_t num_rows, uint64_t num_cols, uint64_t col_offset,
+                                                            uint64_t seed, const uint64_t *__restrict__ planted_cols,
+                                                            const uint32_t *__restrict__ planted_thr, int n_planted)
+{
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= num_rows) return;
+    const uint64_t rk = synth_row_key(seed, row);
+    uint8_t *base = matrix + row * pitch;
+    for (int p = 0; p < n_planted; ++p) {
+        const uint64_t c = planted_cols[p];
+        if (c < col_offset || c >= col_offset + num_cols) continue;
+        const uint64_t lc = c - col_offset;
+        const uint8_t mask = (uint8_t)(0x80u >> (lc & 7));
+        const uint32_t thr = planted_thr[p];
+        const bool bit = thr == 0xffffffffu ? true : synth_plant_u32(rk, c) < thr;
+        const uint8_t v = base[lc >> 3];
+        base[lc >> 3] = bit ? (uint8_t)(v | mask) : (uint8_t)(v & ~mask);
+    }
+}
+
+cudaError_t launch_fill_synthetic(uint8_t *matrix, uint64_t pitch, uint64_t num_rows, uint64_t num_cols,
+                                  uint64_t col_offset, uint64_t seed, int and_draws, const uint64_t *d_planted_cols,
+                                  const uint32_t *d_planted_thr, int n_planted, cudaStream_t stream)
+{
+    if (num_rows == 0) return cudaSuccess;
+    const uint64_t threads = num_rows * (pitch >> 3);
+    const uint64_t blocks = (threads + 255) / 256;
+    if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    fill_synthetic_kernel<<<(unsigned)blocks, 256, 0, stream>>>(matrix, pitch, num_rows, num_cols, col_offset, seed,
+                                                                and_draws);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || n_planted == 0) return e;
+    plant_columns_kernel<<<(unsigned)((num_rows + 255) / 256), 256, 0, stream>>>(
+        matrix, pitch, num_rows, num_cols, col_offset, seed, d_planted_cols, d_planted_thr, n_planted);
+    return cudaGetLastError();
+}
+
+}  // namespace bigsi

@@ -1,0 +1,829 @@
+// C ABI of libbigsi_b200.so (include/bigsi_b200.h): index lifecycle, launch planning and the
+// host-buffer entry points.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bigsi_b200.h"
+#include "query.cuh"
+
+using namespace bigsi;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char *what)
+{
+    const int code = e == cudaErrorMemoryAllocation
+                         ? BIGSI_B200_ERR_OOM
+                         : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? BIGSI_B200_ERR_NO_DEVICE
+                                                                                        : BIGSI_B200_ERR_CUDA;
+    (void)cudaGetLastError();  // clear the sticky-free error state
+    return fail(code, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+#define CK(expr)                                          \
+    do {                                                  \
+        cudaError_t _e = (expr);                          \
+        if (_e != cudaSuccess) return fail_cuda(_e, #expr); \
+    } while (0)
+
+uint32_t bits_of(uint64_t v)
+{
+    uint32_t b = 0;
+    while (v) {
+        ++b;
+        v >>= 1;
+    }
+    return b;
+}
+uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+struct DevBuf {
+    void *p = nullptr;
+    uint64_t cap = 0;
+    cudaError_t reserve(uint64_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) {
+            cudaError_t e = cudaFree(p);
+            p = nullptr;
+            cap = 0;
+            if (e != cudaSuccess) return e;
+        }
+        const uint64_t want = round_up(bytes + bytes / 4, 256);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            e = cudaMalloc(&p, round_up(bytes, 256));
+            if (e != cudaSuccess) return e;
+            cap = round_up(bytes, 256);
+            return cudaSuccess;
+        }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int dev)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+struct TimedLaunch {
+    cudaEvent_t e0, e1, e2;
+};
+
+}  // namespace
+
+struct bigsi_b200_index {
+    int device = 0;
+    int sm_count = 0;
+    uint64_t num_rows = 0, num_cols = 0, col_capacity = 0, col_offset = 0, pitch = 0;
+    uint8_t *matrix = nullptr;
+    cudaStream_t stream = nullptr;
+    // options
+    int64_t opt_tile_bytes = 0, opt_grid = 0, opt_kmers_per_stage = 0, opt_n_stages = 0, opt_ctas_per_sm = 0;
+    bool timing = false;
+    // scratch
+    DevBuf partial, d_kmers, d_rows, d_qoff, d_out, d_min, d_hit_cols, d_hit_counts, d_nhits, d_bloom, d_planted;
+    // timing
+    std::vector<TimedLaunch> timed_free, timed_used;
+    // statistics
+    bigsi_b200_info stats{};
+    uint64_t kernel_launches = 0;
+};
+
+namespace {
+
+bool g_kernels_ready = false;
+
+int ensure_kernels()
+{
+    if (g_kernels_ready) return 0;
+    CK(query_kernels_init());
+    g_kernels_ready = true;
+    return 0;
+}
+
+// Launch plan of one query batch (DESIGN.md "Launch planning").
+int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t total_kmers, uint64_t max_query_kmers,
+               int h, QueryParams &p, int &grid)
+{
+    if (h < 1 || h > kMaxH) return fail(BIGSI_B200_ERR_INVALID, "h=%d out of range [1,%d]", h, kMaxH);
+    if (n_queries > 0xffffffffull) return fail(BIGSI_B200_ERR_INVALID, "too many queries");
+    memset(&p, 0, sizeof p);
+    const uint64_t row_bytes = (ix->num_cols + 7) / 8;
+    p.matrix = ix->matrix;
+    p.pitch = ix->pitch;
+    p.n_queries = (uint32_t)n_queries;
+    p.h = (uint32_t)h;
+    p.total_kmers = total_kmers;
+    p.num_cols = (uint32_t)ix->num_cols;
+    p.row_bytes16 = (uint32_t)round_up(row_bytes ? row_bytes : 1, 16);
+
+    // column tile: as wide as the consumer warps allow, but >= 3 one-k-mer stages must fit in smem
+    uint64_t max_tile = (uint64_t)(kSmemBudget - kSmemHeaderBytes) / (3ull * h) / 16 * 16;
+    if (max_tile > (uint64_t)kMaxTileBytes) max_tile = kMaxTileBytes;
+    if (max_tile < 16) return fail(BIGSI_B200_ERR_INVALID, "h=%d too large for the shared-memory ring", h);
+    uint64_t tile = 0;
+    if (ix->opt_tile_bytes > 0) {
+        tile = round_up((uint64_t)ix->opt_tile_bytes, 16);
+        if (tile > max_tile) tile = max_tile;
+    } else {
+        const uint64_t nt = (p.row_bytes16 + max_tile - 1) / max_tile;
+        tile = (p.row_bytes16 + nt - 1) / nt;
+        const uint64_t t128 = round_up(tile, 128);
+        tile = t128 <= max_tile ? t128 : round_up(tile, 16);
+    }
+    if (tile > p.row_bytes16) tile = p.row_bytes16;
+    p.tile_bytes = (uint32_t)tile;
+    p.n_tiles = (uint32_t)((p.row_bytes16 + tile - 1) / tile);
+
+    // ring geometry
+    const uint64_t kmer_bytes = (uint64_t)h * tile;
+    uint32_t G = 1;
+    if (ix->opt_kmers_per_stage > 0) {
+        G = (uint32_t)ix->opt_kmers_per_stage;
+    } else {
+        for (uint32_t g = 8; g > 1; g >>= 1)
+            if (g * kmer_bytes <= 16384) {
+                G = g;
+                break;
+            }
+    }
+    while (G > 1 && 3ull * G * kmer_bytes > (uint64_t)(kSmemBudget - kSmemHeaderBytes)) G >>= 1;
+    uint64_t stages = (uint64_t)(kSmemBudget - kSmemHeaderBytes) / (G * kmer_bytes);
+    if (stages > (uint64_t)kMaxStages) stages = kMaxStages;
+    if (ix->opt_n_stages > 0 && (uint64_t)ix->opt_n_stages < stages) stages = (uint64_t)ix->opt_n_stages;
+    if (stages < 2) return fail(BIGSI_B200_ERR_INVALID, "ring does not fit (h=%d tile=%llu)", h, (unsigned long long)tile);
+    p.kmers_per_stage = G;
+    p.n_stages = (uint32_t)stages;
+
+    // slices
+    p.total_items = (uint64_t)p.n_tiles * total_kmers;
+    const uint64_t ctas =
+        ix->opt_grid > 0 ? (uint64_t)ix->opt_grid
+                         : (uint64_t)ix->sm_count * (uint64_t)(ix->opt_ctas_per_sm > 0 ? ix->opt_ctas_per_sm : 1);
+    if (p.total_items == 0) {
+        p.items_per_slice = 1;
+        p.n_slices = 0;
+        p.slices_per_cta = 1;
+        grid = 0;
+    } else {
+        const uint64_t spc = (p.total_items + ctas * kMaxSliceItems - 1) / (ctas * kMaxSliceItems);
+        uint64_t ips = (p.total_items + ctas * spc - 1) / (ctas * spc);
+        if (ips > kMaxSliceItems) ips = kMaxSliceItems;
+        if (ips < 1) ips = 1;
+        const uint64_t n_slices = (p.total_items + ips - 1) / ips;
+        if (n_slices > 0xffffffffull) return fail(BIGSI_B200_ERR_INVALID, "query batch too large");
+        p.items_per_slice = (uint32_t)ips;
+        p.n_slices = (uint32_t)n_slices;
+        p.slices_per_cta = (uint32_t)((n_slices + ctas - 1) / ctas);
+        grid = (int)((n_slices + p.slices_per_cta - 1) / p.slices_per_cta);
+    }
+    const uint64_t longest = max_query_kmers ? (max_query_kmers < total_kmers ? max_query_kmers : total_kmers) : total_kmers;
+    if (mode == BIGSI_B200_MODE_COUNTS && longest > 0xffffffffull)
+        return fail(BIGSI_B200_ERR_INVALID, "a query longer than 2^32-1 k-mers does not fit uint32 counts");
+    p.total_planes = mode == BIGSI_B200_MODE_COUNTS ? (bits_of(longest) ? bits_of(longest) : 1) : 1;
+    const uint64_t seg_max = longest < p.items_per_slice ? longest : p.items_per_slice;
+    p.planes_per_slot = mode == BIGSI_B200_MODE_COUNTS ? (bits_of(seg_max) ? bits_of(seg_max) : 1) : 1;
+    return 0;
+}
+
+int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const int64_t *d_qoff, uint64_t n_queries,
+              uint64_t total_kmers, uint64_t max_query_kmers, int h, void *d_out, uint64_t out_stride,
+              cudaStream_t stream)
+{
+    if (mode != BIGSI_B200_MODE_COUNTS && mode != BIGSI_B200_MODE_AND)
+        return fail(BIGSI_B200_ERR_INVALID, "unknown query mode %d", mode);
+    if (n_queries == 0) return 0;
+    const uint64_t row_bytes = (ix->num_cols + 7) / 8;
+    if (mode == BIGSI_B200_MODE_COUNTS ? out_stride < ix->num_cols : out_stride < row_bytes)
+        return fail(BIGSI_B200_ERR_INVALID, "out_stride %llu too small", (unsigned long long)out_stride);
+    if (ix->num_cols == 0) return 0;
+    if (int rc = ensure_kernels()) return rc;
+    QueryParams p;
+    int grid = 0;
+    if (int rc = plan_query(ix, mode, n_queries, total_kmers, max_query_kmers, h, p, grid)) return rc;
+    p.rows = d_rows;
+    p.qoff = d_qoff;
+    p.out = d_out;
+    p.out_stride = out_stride;
+    const uint64_t need = query_partial_bytes(p);
+    if (need > ix->partial.cap) {
+        CK(cudaStreamSynchronize(stream));
+        cudaError_t e = ix->partial.reserve(need);
+        if (e != cudaSuccess) return fail_cuda(e, "partial-plane workspace");
+    }
+    p.partial = static_cast<uint8_t *>(ix->partial.p);
+
+    TimedLaunch tl{};
+    if (ix->timing) {
+        if (ix->timed_free.empty()) {
+            CK(cudaEventCreate(&tl.e0));
+            CK(cudaEventCreate(&tl.e1));
+            CK(cudaEventCreate(&tl.e2));
+        } else {
+            tl = ix->timed_free.back();
+            ix->timed_free.pop_back();
+        }
+        CK(cudaEventRecord(tl.e0, stream));
+    }
+    if (grid > 0) {
+        CK(launch_query(p, mode, grid, stream));
+        ix->kernel_launches++;
+    }
+    if (ix->timing) CK(cudaEventRecord(tl.e1, stream));
+    CK(launch_merge(p, mode, stream));
+    ix->kernel_launches++;
+    if (ix->timing) {
+        CK(cudaEventRecord(tl.e2, stream));
+        ix->timed_used.push_back(tl);
+    }
+
+    bigsi_b200_info &s = ix->stats;
+    s.last_kmers = total_kmers;
+    s.last_algorithmic_bytes = total_kmers * (uint64_t)h * row_bytes;
+    s.last_grid = (uint32_t)grid;
+    s.last_block = query_block_threads(p);
+    s.last_smem_bytes = query_smem_bytes(p);
+    s.last_tile_bytes = p.tile_bytes;
+    s.last_n_tiles = p.n_tiles;
+    s.last_kmers_per_stage = p.kmers_per_stage;
+    s.last_n_stages = p.n_stages;
+    s.last_n_slices = p.n_slices;
+    return 0;
+}
+
+int check_index(const bigsi_b200_index *ix)
+{
+    if (!ix) return fail(BIGSI_B200_ERR_INVALID, "null index handle");
+    return 0;
+}
+
+// q_offsets sanity on the host (host-buffer entry points only)
+int check_offsets(const int64_t *qoff, uint64_t n_queries, uint64_t *total_out, uint64_t *longest_out)
+{
+    if (n_queries == 0) {
+        *total_out = 0;
+        *longest_out = 0;
+        return 0;
+    }
+    if (!qoff) return fail(BIGSI_B200_ERR_INVALID, "null q_offsets");
+    if (qoff[0] != 0) return fail(BIGSI_B200_ERR_INVALID, "q_offsets[0] must be 0");
+    uint64_t longest = 0;
+    for (uint64_t q = 0; q < n_queries; ++q) {
+        if (qoff[q + 1] < qoff[q]) return fail(BIGSI_B200_ERR_INVALID, "q_offsets must be non-decreasing");
+        const uint64_t len = (uint64_t)(qoff[q + 1] - qoff[q]);
+        if (len > longest) longest = len;
+    }
+    *total_out = (uint64_t)qoff[n_queries];
+    *longest_out = longest;
+    return 0;
+}
+
+}  // namespace
+
+// ============================================================================================
+// library
+// ============================================================================================
+extern "C" {
+
+int bigsi_b200_abi_version(void) { return BIGSI_B200_ABI_VERSION; }
+const char *bigsi_b200_last_error(void) { return g_err.c_str(); }
+
+int bigsi_b200_device_count(int *count_out)
+{
+    if (!count_out) return fail(BIGSI_B200_ERR_INVALID, "null count_out");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count_out = 0;
+        return fail_cuda(e, "cudaGetDeviceCount");
+    }
+    *count_out = n;
+    return 0;
+}
+
+int bigsi_b200_host_alloc(uint64_t bytes, void **ptr_out)
+{
+    if (!ptr_out) return fail(BIGSI_B200_ERR_INVALID, "null ptr_out");
+    *ptr_out = nullptr;
+    cudaError_t e = cudaHostAlloc(ptr_out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaHostAlloc");
+    return 0;
+}
+int bigsi_b200_host_free(void *ptr)
+{
+    if (!ptr) return 0;
+    CK(cudaFreeHost(ptr));
+    return 0;
+}
+
+// ============================================================================================
+// index lifecycle
+// ============================================================================================
+int bigsi_b200_index_create(int device, uint64_t num_rows, uint64_t num_cols, uint64_t col_capacity,
+                            uint64_t col_offset, bigsi_b200_index **index_out)
+{
+    if (!index_out) return fail(BIGSI_B200_ERR_INVALID, "null index_out");
+    *index_out = nullptr;
+    if (num_rows == 0 || num_rows > 0x7fffffffull)
+        return fail(BIGSI_B200_ERR_INVALID, "num_rows must be in [1, 2^31-1] (row ids are int32)");
+    if (col_capacity < num_cols) col_capacity = num_cols;
+    if (col_capacity == 0) col_capacity = 1;
+    if (col_capacity > 0xffffffffull - 1024) return fail(BIGSI_B200_ERR_INVALID, "too many columns for one shard");
+    if (col_offset % 8) return fail(BIGSI_B200_ERR_INVALID, "col_offset must be a multiple of 8");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
+    if (n == 0) return fail(BIGSI_B200_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= n) return fail(BIGSI_B200_ERR_INVALID, "device %d out of range (have %d)", device, n);
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(BIGSI_B200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    bigsi_b200_index *ix = new bigsi_b200_index();
+    ix->device = device;
+    ix->sm_count = prop.multiProcessorCount;
+    ix->num_rows = num_rows;
+    ix->num_cols = num_cols;
+    ix->pitch = round_up((col_capacity + 7) / 8, 128);
+    ix->col_capacity = ix->pitch * 8;
+    ix->col_offset = col_offset;
+    const uint64_t bytes = ix->num_rows * ix->pitch;
+    e = cudaMalloc(reinterpret_cast<void **>(&ix->matrix), bytes);
+    if (e != cudaSuccess) {
+        delete ix;
+        return fail_cuda(e, "cudaMalloc(matrix)");
+    }
+    e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ix->matrix, 0, bytes, ix->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+    if (e != cudaSuccess) {
+        cudaFree(ix->matrix);
+        if (ix->stream) cudaStreamDestroy(ix->stream);
+        delete ix;
+        return fail_cuda(e, "index initialisation");
+    }
+    *index_out = ix;
+    return 0;
+}
+
+int bigsi_b200_index_destroy(bigsi_b200_index *ix)
+{
+    if (!ix) return 0;
+    DeviceGuard guard(ix->device);
+    cudaDeviceSynchronize();
+    for (auto &t : ix->timed_free) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
+    for (auto &t : ix->timed_used) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
+    DevBuf *bufs[] = {&ix->partial, &ix->d_kmers, &ix->d_rows, &ix->d_qoff, &ix->d_out, &ix->d_min,
+                      &ix->d_hit_cols, &ix->d_hit_counts, &ix->d_nhits, &ix->d_bloom, &ix->d_planted};
+    for (DevBuf *b : bufs) b->release();
+    if (ix->matrix) cudaFree(ix->matrix);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+    return 0;
+}
+
+int bigsi_b200_index_get_info(const bigsi_b200_index *ix, bigsi_b200_info *out)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (!out) return fail(BIGSI_B200_ERR_INVALID, "null info_out");
+    *out = ix->stats;
+    out->num_rows = ix->num_rows;
+    out->num_cols = ix->num_cols;
+    out->col_capacity = ix->col_capacity;
+    out->col_offset = ix->col_offset;
+    out->row_bytes = (ix->num_cols + 7) / 8;
+    out->row_pitch_bytes = ix->pitch;
+    out->matrix_bytes = ix->num_rows * ix->pitch;
+    out->device = ix->device;
+    out->sm_count = ix->sm_count;
+    out->kernel_launches = ix->kernel_launches;
+    out->scratch_bytes = ix->partial.cap;
+    return 0;
+}
+
+int bigsi_b200_index_set_option(bigsi_b200_index *ix, const char *key, int64_t value)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (!key) return fail(BIGSI_B200_ERR_INVALID, "null option key");
+    if (value < 0) return fail(BIGSI_B200_ERR_INVALID, "option %s: negative value", key);
+    if (!strcmp(key, "tile_bytes")) ix->opt_tile_bytes = value;
+    else if (!strcmp(key, "grid")) ix->opt_grid = value;
+    else if (!strcmp(key, "kmers_per_stage")) ix->opt_kmers_per_stage = value;
+    else if (!strcmp(key, "n_stages")) ix->opt_n_stages = value;
+    else if (!strcmp(key, "ctas_per_sm")) ix->opt_ctas_per_sm = value;
+    else if (!strcmp(key, "timing")) ix->timing = value != 0;
+    else return fail(BIGSI_B200_ERR_INVALID, "unknown option '%s'", key);
+    return 0;
+}
+
+int bigsi_b200_index_timing_collect(bigsi_b200_index *ix, double *fused_ms_out, double *merge_ms_out, uint64_t *n_out)
+{
+    if (int rc = check_index(ix)) return rc;
+    DeviceGuard guard(ix->device);
+    double fused = 0, merge = 0;
+    uint64_t n = 0;
+    for (auto &t : ix->timed_used) {
+        CK(cudaEventSynchronize(t.e2));
+        float a = 0, b = 0;
+        CK(cudaEventElapsedTime(&a, t.e0, t.e1));
+        CK(cudaEventElapsedTime(&b, t.e1, t.e2));
+        fused += a;
+        merge += b;
+        ++n;
+        ix->timed_free.push_back(t);
+    }
+    ix->timed_used.clear();
+    if (fused_ms_out) *fused_ms_out = fused;
+    if (merge_ms_out) *merge_ms_out = merge;
+    if (n_out) *n_out = n;
+    return 0;
+}
+
+int bigsi_b200_index_upload_rows(bigsi_b200_index *ix, uint64_t row0, uint64_t n_rows, const uint8_t *rows,
+                                 uint64_t src_stride, uint64_t src_byte_offset)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (n_rows == 0) return 0;
+    if (!rows) return fail(BIGSI_B200_ERR_INVALID, "null rows");
+    if (row0 + n_rows > ix->num_rows) return fail(BIGSI_B200_ERR_RANGE, "rows [%llu,%llu) exceed m=%llu",
+                                                   (unsigned long long)row0, (unsigned long long)(row0 + n_rows),
+                                                   (unsigned long long)ix->num_rows);
+    const uint64_t row_bytes = (ix->num_cols + 7) / 8;
+    if (row_bytes == 0) return 0;
+    if (src_stride < row_bytes) return fail(BIGSI_B200_ERR_INVALID, "src_stride smaller than the row");
+    DeviceGuard guard(ix->device);
+    CK(cudaMemcpy2DAsync(ix->matrix + row0 * ix->pitch, ix->pitch, rows + src_byte_offset, src_stride, row_bytes, n_rows,
+                         cudaMemcpyHostToDevice, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    // a partial last byte may carry columns >= num_cols of a wider source row: keep padding zero
+    if (ix->num_cols & 7) {
+        // handled on the host side of the plugin (rows are uploaded at their own width); enforce here
+        // by re-masking the last byte of every uploaded row.
+        const uint8_t mask = (uint8_t)(0xff00u >> (ix->num_cols & 7));
+        std::vector<uint8_t> last(n_rows);
+        for (uint64_t i = 0; i < n_rows; ++i) last[i] = rows[src_byte_offset + i * src_stride + row_bytes - 1] & mask;
+        CK(cudaMemcpy2DAsync(ix->matrix + row0 * ix->pitch + row_bytes - 1, ix->pitch, last.data(), 1, 1, n_rows,
+                             cudaMemcpyHostToDevice, ix->stream));
+        CK(cudaStreamSynchronize(ix->stream));
+    }
+    return 0;
+}
+
+int bigsi_b200_index_download_rows(const bigsi_b200_index *ix, uint64_t row0, uint64_t n_rows, uint8_t *out,
+                                   uint64_t dst_stride)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (n_rows == 0) return 0;
+    if (!out) return fail(BIGSI_B200_ERR_INVALID, "null out");
+    if (row0 + n_rows > ix->num_rows) return fail(BIGSI_B200_ERR_RANGE, "rows out of range");
+    const uint64_t row_bytes = (ix->num_cols + 7) / 8;
+    if (row_bytes == 0) return 0;
+    if (dst_stride < row_bytes) return fail(BIGSI_B200_ERR_INVALID, "dst_stride smaller than the row");
+    DeviceGuard guard(ix->device);
+    CK(cudaMemcpy2DAsync(out, dst_stride, ix->matrix + row0 * ix->pitch, ix->pitch, row_bytes, n_rows,
+                         cudaMemcpyDeviceToHost, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    return 0;
+}
+
+int bigsi_b200_index_set_column(bigsi_b200_index *ix, uint64_t col, const uint8_t *bloom, uint64_t n_bits)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (!bloom && n_bits) return fail(BIGSI_B200_ERR_INVALID, "null bloom filter");
+    if (n_bits > ix->num_rows) return fail(BIGSI_B200_ERR_RANGE, "bloom filter longer than m");
+    if (col > ix->num_cols) return fail(BIGSI_B200_ERR_RANGE, "column %llu beyond num_cols=%llu",
+                                        (unsigned long long)col, (unsigned long long)ix->num_cols);
+    if (col >= ix->col_capacity) return fail(BIGSI_B200_ERR_RANGE, "column capacity %llu exhausted",
+                                             (unsigned long long)ix->col_capacity);
+    DeviceGuard guard(ix->device);
+    const uint64_t nbytes = (n_bits + 7) / 8;
+    cudaError_t e = ix->d_bloom.reserve(nbytes ? nbytes : 1);
+    if (e != cudaSuccess) return fail_cuda(e, "bloom staging");
+    if (nbytes) CK(cudaMemcpyAsync(ix->d_bloom.p, bloom, nbytes, cudaMemcpyHostToDevice, ix->stream));
+    CK(launch_set_column(ix->matrix, ix->pitch, ix->num_rows, col, static_cast<const uint8_t *>(ix->d_bloom.p), n_bits,
+                         ix->stream));
+    ix->kernel_launches++;
+    CK(cudaStreamSynchronize(ix->stream));
+    if (col == ix->num_cols) ix->num_cols++;
+    return 0;
+}
+
+int bigsi_b200_index_fill_synthetic(bigsi_b200_index *ix, uint64_t seed, int and_draws, const uint64_t *planted_cols,
+                                    const uint32_t *planted_thr, int n_planted)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (and_draws < 0 || and_draws > 8) return fail(BIGSI_B200_ERR_INVALID, "and_draws must be in [0,8]");
+    if (n_planted < 0 || (n_planted && (!planted_cols || !planted_thr)))
+        return fail(BIGSI_B200_ERR_INVALID, "bad planted-column list");
+    DeviceGuard guard(ix->device);
+    const uint64_t pc_bytes = round_up((uint64_t)n_planted * 8, 256);
+    uint64_t *d_cols = nullptr;
+    uint32_t *d_thr = nullptr;
+    if (n_planted) {
+        cudaError_t e = ix->d_planted.reserve(pc_bytes + (uint64_t)n_planted * 4);
+        if (e != cudaSuccess) return fail_cuda(e, "planted staging");
+        d_cols = static_cast<uint64_t *>(ix->d_planted.p);
+        d_thr = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ix->d_planted.p) + pc_bytes);
+        CK(cudaMemcpyAsync(d_cols, planted_cols, (uint64_t)n_planted * 8, cudaMemcpyHostToDevice, ix->stream));
+        CK(cudaMemcpyAsync(d_thr, planted_thr, (uint64_t)n_planted * 4, cudaMemcpyHostToDevice, ix->stream));
+    }
+    CK(launch_fill_synthetic(ix->matrix, ix->pitch, ix->num_rows, ix->num_cols, ix->col_offset, seed, and_draws, d_cols,
+                             d_thr, n_planted, ix->stream));
+    ix->kernel_launches += n_planted ? 2 : 1;
+    CK(cudaStreamSynchronize(ix->stream));
+    return 0;
+}
+
+// ============================================================================================
+// hashing
+// ============================================================================================
+int bigsi_b200_hash_kmers_dev(const char *d_kmers, uint64_t n, int k, int h, uint64_t m, int canonical,
+                              int32_t *d_rows_out, void *stream)
+{
+    if (k < 1) return fail(BIGSI_B200_ERR_INVALID, "k must be >= 1");
+    if (h < 1) return fail(BIGSI_B200_ERR_INVALID, "h must be >= 1");
+    if (m == 0 || m > 0x7fffffffull) return fail(BIGSI_B200_ERR_INVALID, "m must be in [1, 2^31-1]");
+    if (n == 0) return 0;
+    if (!d_kmers || !d_rows_out) return fail(BIGSI_B200_ERR_INVALID, "null device pointer");
+    if ((n + 127) / 128 > 0x7fffffffull) return fail(BIGSI_B200_ERR_INVALID, "too many k-mers");
+    CK(launch_hash_kmers(d_kmers, n, k, h, m, canonical, d_rows_out, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int bigsi_b200_hash_kmers(int device, const char *kmers, uint64_t n, int k, int h, uint64_t m, int canonical,
+                          int32_t *rows_out)
+{
+    if (k < 1 || h < 1) return fail(BIGSI_B200_ERR_INVALID, "k and h must be >= 1");
+    if (n == 0) return 0;
+    if (!kmers || !rows_out) return fail(BIGSI_B200_ERR_INVALID, "null pointer");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
+    if (ndev == 0) return fail(BIGSI_B200_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return fail(BIGSI_B200_ERR_INVALID, "device out of range");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
+    char *d_k = nullptr;
+    int32_t *d_r = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void **>(&d_k), n * (uint64_t)k));
+    e = cudaMalloc(reinterpret_cast<void **>(&d_r), n * (uint64_t)h * 4);
+    if (e != cudaSuccess) {
+        cudaFree(d_k);
+        return fail_cuda(e, "cudaMalloc");
+    }
+    int rc = 0;
+    e = cudaMemcpy(d_k, kmers, n * (uint64_t)k, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = bigsi_b200_hash_kmers_dev(d_k, n, k, h, m, canonical, d_r, nullptr);
+        if (rc == 0) e = cudaMemcpy(rows_out, d_r, n * (uint64_t)h * 4, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_k);
+    cudaFree(d_r);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail_cuda(e, "hash_kmers copy");
+    return 0;
+}
+
+// ============================================================================================
+// device-pointer query entry points
+// ============================================================================================
+int bigsi_b200_query_dev(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const int64_t *d_q_offsets,
+                         uint64_t n_queries, uint64_t total_kmers, uint64_t max_query_kmers, int h, void *d_out,
+                         uint64_t out_stride, void *stream)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (n_queries && (!d_q_offsets || !d_out)) return fail(BIGSI_B200_ERR_INVALID, "null device pointer");
+    if (total_kmers && !d_rows) return fail(BIGSI_B200_ERR_INVALID, "null d_rows");
+    DeviceGuard guard(ix->device);
+    return run_query(ix, mode, d_rows, d_q_offsets, n_queries, total_kmers, max_query_kmers, h, d_out, out_stride,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int bigsi_b200_lookup_dev(bigsi_b200_index *ix, const int32_t *d_rows, uint64_t n_kmers, int h, uint8_t *d_out,
+                          uint64_t out_stride, void *stream)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (h < 1) return fail(BIGSI_B200_ERR_INVALID, "h must be >= 1");
+    const uint64_t row_bytes = (ix->num_cols + 7) / 8;
+    if (out_stride < row_bytes) return fail(BIGSI_B200_ERR_INVALID, "out_stride too small");
+    if (n_kmers == 0 || row_bytes == 0) return 0;
+    if (!d_rows || !d_out) return fail(BIGSI_B200_ERR_INVALID, "null device pointer");
+    DeviceGuard guard(ix->device);
+    CK(launch_lookup(ix->matrix, ix->pitch, (uint32_t)row_bytes, d_rows, n_kmers, h, d_out, out_stride,
+                     static_cast<cudaStream_t>(stream)));
+    ix->kernel_launches++;
+    return 0;
+}
+
+int bigsi_b200_threshold_dev(const uint32_t *d_counts, uint64_t counts_stride, uint64_t n_queries, uint64_t num_cols,
+                             const uint32_t *d_min_kmers, int32_t *d_cols_out, uint32_t *d_counts_out, uint64_t cap,
+                             uint64_t *d_n_out, void *stream)
+{
+    if (n_queries == 0) return 0;
+    if (!d_counts || !d_min_kmers || !d_n_out || (cap && (!d_cols_out || !d_counts_out)))
+        return fail(BIGSI_B200_ERR_INVALID, "null device pointer");
+    if (num_cols > 0xffffffffull) return fail(BIGSI_B200_ERR_INVALID, "too many columns");
+    // grid.y carries the query index: batches beyond 65535 queries are split here
+    for (uint64_t q0 = 0; q0 < n_queries; q0 += 65535) {
+        const uint64_t nq = n_queries - q0 < 65535 ? n_queries - q0 : 65535;
+        CK(launch_threshold(d_counts + q0 * counts_stride, counts_stride, nq, num_cols, d_min_kmers + q0,
+                            d_cols_out + q0 * cap, d_counts_out + q0 * cap, cap,
+                            reinterpret_cast<unsigned long long *>(d_n_out) + q0, static_cast<cudaStream_t>(stream)));
+    }
+    return 0;
+}
+
+// ============================================================================================
+// host-buffer entry points
+// ============================================================================================
+static int search_common(bigsi_b200_index *ix, int mode, const char *kmers, const int32_t *rows, const int64_t *qoff,
+                         uint64_t n_queries, int k, int h, uint64_t *total_out, uint64_t *longest_out,
+                         uint64_t out_stride)
+{
+    // stages inputs, hashes if needed and runs the query into ix->d_out (device); no D2H here
+    uint64_t total = 0, longest = 0;
+    if (int rc = check_offsets(qoff, n_queries, &total, &longest)) return rc;
+    *total_out = total;
+    *longest_out = longest;
+    if (h < 1) return fail(BIGSI_B200_ERR_INVALID, "h must be >= 1");
+    if (total && !kmers && !rows) return fail(BIGSI_B200_ERR_INVALID, "null query input");
+    cudaError_t e;
+    if ((e = ix->d_qoff.reserve((n_queries + 1) * 8)) != cudaSuccess) return fail_cuda(e, "staging");
+    if ((e = ix->d_rows.reserve(total * (uint64_t)h * 4 + 4)) != cudaSuccess) return fail_cuda(e, "staging");
+    const uint64_t out_bytes = n_queries * out_stride * (mode == BIGSI_B200_MODE_COUNTS ? 4 : 1);
+    if ((e = ix->d_out.reserve(out_bytes + 16)) != cudaSuccess) return fail_cuda(e, "staging");
+    CK(cudaMemcpyAsync(ix->d_qoff.p, qoff, (n_queries + 1) * 8, cudaMemcpyHostToDevice, ix->stream));
+    if (total) {
+        if (kmers) {
+            if (k < 1) return fail(BIGSI_B200_ERR_INVALID, "k must be >= 1");
+            if ((e = ix->d_kmers.reserve(total * (uint64_t)k)) != cudaSuccess) return fail_cuda(e, "staging");
+            CK(cudaMemcpyAsync(ix->d_kmers.p, kmers, total * (uint64_t)k, cudaMemcpyHostToDevice, ix->stream));
+            if (int rc = bigsi_b200_hash_kmers_dev(static_cast<const char *>(ix->d_kmers.p), total, k, h, ix->num_rows, 1,
+                                                   static_cast<int32_t *>(ix->d_rows.p), ix->stream))
+                return rc;
+            ix->kernel_launches++;
+        } else {
+            for (uint64_t i = 0; i < total * (uint64_t)h; ++i)
+                if (rows[i] < 0 || (uint64_t)rows[i] >= ix->num_rows)
+                    return fail(BIGSI_B200_ERR_RANGE, "row id %d out of range at %llu", rows[i], (unsigned long long)i);
+            CK(cudaMemcpyAsync(ix->d_rows.p, rows, total * (uint64_t)h * 4, cudaMemcpyHostToDevice, ix->stream));
+        }
+    }
+    return run_query(ix, mode, static_cast<const int32_t *>(ix->d_rows.p), static_cast<const int64_t *>(ix->d_qoff.p),
+                     n_queries, total, longest, h, ix->d_out.p, out_stride, ix->stream);
+}
+
+static int search_full(bigsi_b200_index *ix, int mode, const char *kmers, const int32_t *rows, const int64_t *qoff,
+                       uint64_t n_queries, int k, int h, void *out, uint64_t out_stride)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (n_queries == 0) return 0;
+    if (!out) return fail(BIGSI_B200_ERR_INVALID, "null out");
+    if (mode != BIGSI_B200_MODE_COUNTS && mode != BIGSI_B200_MODE_AND)
+        return fail(BIGSI_B200_ERR_INVALID, "unknown query mode %d", mode);
+    DeviceGuard guard(ix->device);
+    uint64_t total = 0, longest = 0;
+    if (int rc = search_common(ix, mode, kmers, rows, qoff, n_queries, k, h, &total, &longest, out_stride)) return rc;
+    const uint64_t width = mode == BIGSI_B200_MODE_COUNTS ? ix->num_cols * 4 : (ix->num_cols + 7) / 8;
+    const uint64_t stride_b = out_stride * (mode == BIGSI_B200_MODE_COUNTS ? 4 : 1);
+    if (width)
+        CK(cudaMemcpy2DAsync(out, stride_b, ix->d_out.p, stride_b, width, n_queries, cudaMemcpyDeviceToHost, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    return 0;
+}
+
+int bigsi_b200_search_kmers(bigsi_b200_index *ix, int mode, const char *kmers, const int64_t *q_offsets,
+                            uint64_t n_queries, int k, int h, void *out, uint64_t out_stride)
+{
+    return search_full(ix, mode, kmers, nullptr, q_offsets, n_queries, k, h, out, out_stride);
+}
+
+int bigsi_b200_search_rows(bigsi_b200_index *ix, int mode, const int32_t *rows, const int64_t *q_offsets,
+                           uint64_t n_queries, int h, void *out, uint64_t out_stride)
+{
+    return search_full(ix, mode, nullptr, rows, q_offsets, n_queries, 0, h, out, out_stride);
+}
+
+int bigsi_b200_search_kmers_hits(bigsi_b200_index *ix, const char *kmers, const int64_t *q_offsets, uint64_t n_queries,
+                                 int k, int h, const uint32_t *min_kmers, int32_t *cols_out, uint32_t *counts_out,
+                                 uint64_t cap, uint64_t *n_out)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (n_queries == 0) return 0;
+    if (!min_kmers || !n_out || (cap && (!cols_out || !counts_out))) return fail(BIGSI_B200_ERR_INVALID, "null pointer");
+    DeviceGuard guard(ix->device);
+    uint64_t total = 0, longest = 0;
+    const uint64_t stride = round_up(ix->num_cols ? ix->num_cols : 1, 4);
+    if (int rc = search_common(ix, BIGSI_B200_MODE_COUNTS, kmers, nullptr, q_offsets, n_queries, k, h, &total, &longest,
+                               stride))
+        return rc;
+    cudaError_t e;
+    if ((e = ix->d_min.reserve(n_queries * 4)) != cudaSuccess) return fail_cuda(e, "staging");
+    if ((e = ix->d_nhits.reserve(n_queries * 8)) != cudaSuccess) return fail_cuda(e, "staging");
+    if ((e = ix->d_hit_cols.reserve(n_queries * cap * 4 + 4)) != cudaSuccess) return fail_cuda(e, "staging");
+    if ((e = ix->d_hit_counts.reserve(n_queries * cap * 4 + 4)) != cudaSuccess) return fail_cuda(e, "staging");
+    CK(cudaMemcpyAsync(ix->d_min.p, min_kmers, n_queries * 4, cudaMemcpyHostToDevice, ix->stream));
+    if (ix->num_cols == 0) {
+        CK(cudaStreamSynchronize(ix->stream));
+        for (uint64_t q = 0; q < n_queries; ++q) n_out[q] = 0;
+        return 0;
+    }
+    if (int rc = bigsi_b200_threshold_dev(static_cast<const uint32_t *>(ix->d_out.p), stride, n_queries, ix->num_cols,
+                                          static_cast<const uint32_t *>(ix->d_min.p),
+                                          static_cast<int32_t *>(ix->d_hit_cols.p),
+                                          static_cast<uint32_t *>(ix->d_hit_counts.p), cap,
+                                          static_cast<uint64_t *>(ix->d_nhits.p), ix->stream))
+        return rc;
+    ix->kernel_launches++;
+    CK(cudaMemcpyAsync(n_out, ix->d_nhits.p, n_queries * 8, cudaMemcpyDeviceToHost, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    // second leg: only the hit lists that are populated
+    if (n_queries == 1) {
+        const uint64_t n = n_out[0] < cap ? n_out[0] : cap;
+        if (n) {
+            CK(cudaMemcpyAsync(cols_out, ix->d_hit_cols.p, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+            CK(cudaMemcpyAsync(counts_out, ix->d_hit_counts.p, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+            CK(cudaStreamSynchronize(ix->stream));
+        }
+    } else if (cap) {
+        uint64_t max_n = 0;
+        for (uint64_t q = 0; q < n_queries; ++q) {
+            const uint64_t n = n_out[q] < cap ? n_out[q] : cap;
+            if (n > max_n) max_n = n;
+        }
+        if (max_n) {
+            CK(cudaMemcpy2DAsync(cols_out, cap * 4, ix->d_hit_cols.p, cap * 4, max_n * 4, n_queries,
+                                 cudaMemcpyDeviceToHost, ix->stream));
+            CK(cudaMemcpy2DAsync(counts_out, cap * 4, ix->d_hit_counts.p, cap * 4, max_n * 4, n_queries,
+                                 cudaMemcpyDeviceToHost, ix->stream));
+            CK(cudaStreamSynchronize(ix->stream));
+        }
+    }
+    return 0;
+}
+
+int bigsi_b200_lookup_kmers(bigsi_b200_index *ix, const char *kmers, uint64_t n, int k, int h, uint8_t *out,
+                            uint64_t out_stride)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (n == 0) return 0;
+    if (!kmers || !out) return fail(BIGSI_B200_ERR_INVALID, "null pointer");
+    if (k < 1 || h < 1) return fail(BIGSI_B200_ERR_INVALID, "k and h must be >= 1");
+    const uint64_t row_bytes = (ix->num_cols + 7) / 8;
+    if (out_stride < row_bytes) return fail(BIGSI_B200_ERR_INVALID, "out_stride too small");
+    if (row_bytes == 0) return 0;
+    DeviceGuard guard(ix->device);
+    cudaError_t e;
+    const uint64_t dstride = round_up(row_bytes, 16);
+    if ((e = ix->d_kmers.reserve(n * (uint64_t)k)) != cudaSuccess) return fail_cuda(e, "staging");
+    if ((e = ix->d_rows.reserve(n * (uint64_t)h * 4)) != cudaSuccess) return fail_cuda(e, "staging");
+    if ((e = ix->d_out.reserve(n * dstride)) != cudaSuccess) return fail_cuda(e, "staging");
+    CK(cudaMemcpyAsync(ix->d_kmers.p, kmers, n * (uint64_t)k, cudaMemcpyHostToDevice, ix->stream));
+    if (int rc = bigsi_b200_hash_kmers_dev(static_cast<const char *>(ix->d_kmers.p), n, k, h, ix->num_rows, 1,
+                                           static_cast<int32_t *>(ix->d_rows.p), ix->stream))
+        return rc;
+    ix->kernel_launches++;
+    if (int rc = bigsi_b200_lookup_dev(ix, static_cast<const int32_t *>(ix->d_rows.p), n, h,
+                                       static_cast<uint8_t *>(ix->d_out.p), dstride, ix->stream))
+        return rc;
+    CK(cudaMemcpy2DAsync(out, out_stride, ix->d_out.p, dstride, row_bytes, n, cudaMemcpyDeviceToHost, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+// Launch interface of the fused gather-AND-{count|AND} kernel and its merge kernel
+// (query_kernels.cu) and of the small helper kernels (aux_kernels.cu).
+// See DESIGN.md "Kernels" for the work decomposition.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bigsi {
+
+constexpr int kMaxConsumerWarps = 13;                           // 416 consumer threads, one 16-byte unit each
+constexpr int kMaxBlockThreads = (kMaxConsumerWarps + 1) * 32;  // + one TMA producer warp
+constexpr int kMaxTileBytes = kMaxConsumerWarps * 32 * 16;      // 6656 B = 53 248 sample columns per tile
+constexpr int kMaxStages = 32;
+constexpr int kSmemHeaderBytes = 1024;                          // mbarriers
+constexpr int kSmemBudget = 227 * 1024;
+constexpr uint32_t kMaxSliceItems = 65535;                      // a segment's count fits 16 bit planes
+constexpr int kSegPlanes = 16;
+constexpr int kMaxH = 1024;
+
+enum { kModeCounts = 0, kModeAnd = 1 };
+
+// Work space of one launch: items = (column tile, global k-mer index), k-mer fastest.  It is cut
+// into n_slices equal slices of items_per_slice (<= 65535); CTA b owns the contiguous slices
+// [b*slices_per_cta, (b+1)*slices_per_cta); a slice is cut into SEGMENTS at (tile, query)
+// boundaries.  A segment accumulates in registers and is written once, as bit planes, to partial
+// slot  slice + tile*n_queries + query  (unique per segment, monotone in item order).
+struct QueryParams {
+    const uint8_t *matrix;    // m rows x pitch bytes, MSB-first sample columns
+    uint64_t pitch;           // multiple of 128
+    const int32_t *rows;      // [total_kmers * h] row ids
+    const int64_t *qoff;      // [n_queries + 1] k-mer offsets
+    uint32_t n_queries;
+    uint32_t h;
+    uint64_t total_kmers;
+    uint32_t num_cols;        // valid columns of this shard
+    uint32_t row_bytes16;     // ceil(num_cols/8) rounded up to 16 (padding bits are zero in HBM)
+    uint32_t tile_bytes;      // column-tile width in bytes, multiple of 16, <= kMaxTileBytes
+    uint32_t n_tiles;         // ceil(row_bytes16 / tile_bytes)
+    uint32_t kmers_per_stage; // G: k-mers staged per ring slot
+    uint32_t n_stages;        // ring depth
+    uint64_t total_items;     // n_tiles * total_kmers
+    uint32_t items_per_slice; // <= kMaxSliceItems
+    uint32_t n_slices;
+    uint32_t slices_per_cta;
+    uint8_t *partial;         // [n_slots][planes_per_slot][tile_bytes]
+    uint32_t planes_per_slot; // COUNTS: bits(min(items_per_slice, longest query)); AND: 1
+    uint32_t total_planes;    // bits(longest query) <= 32 (merge accumulator width)
+    void *out;                // COUNTS: uint32 [n_queries][out_stride]; AND: uint8 [n_queries][out_stride]
+    uint64_t out_stride;      // elements (COUNTS) or bytes (AND)
+};
+
+inline uint32_t query_consumer_warps(const QueryParams &p) { return (p.tile_bytes + 511) / 512; }
+inline uint32_t query_block_threads(const QueryParams &p) { return (query_consumer_warps(p) + 1) * 32; }
+inline uint32_t query_smem_bytes(const QueryParams &p)
+{
+    return kSmemHeaderBytes + p.n_stages * p.kmers_per_stage * p.h * p.tile_bytes;
+}
+inline uint64_t query_n_slots(const QueryParams &p)
+{
+    return (uint64_t)p.n_slices + (uint64_t)p.n_tiles * p.n_queries;
+}
+inline uint64_t query_partial_bytes(const QueryParams &p)
+{
+    return query_n_slots(p) * p.planes_per_slot * p.tile_bytes;
+}
+
+// Stage 1: gather + AND + vertical count, per-segment bit planes -> p.partial.
+cudaError_t launch_query(const QueryParams &p, int mode, int grid, cudaStream_t stream);
+// Stage 2: sum (or AND) the partial planes of every (query, column), expand to integers -> p.out.
+cudaError_t launch_merge(const QueryParams &p, int mode, cudaStream_t stream);
+cudaError_t query_kernels_init();  // opt-in to large dynamic shared memory
+
+// ---- helper kernels (aux_kernels.cu) -------------------------------------------------------
+cudaError_t launch_hash_kmers(const char *d_kmers, uint64_t n, int k, int h, uint64_t m, int canonical,
+                              int32_t *d_rows_out, cudaStream_t stream);
+cudaError_t launch_lookup(const uint8_t *matrix, uint64_t pitch, uint32_t row_bytes, const int32_t *d_rows,
+                          uint64_t n_kmers, int h, uint8_t *d_out, uint64_t out_stride, cudaStream_t stream);
+cudaError_t launch_threshold(const uint32_t *d_counts, uint64_t counts_stride, uint64_t n_queries,
+                             uint64_t num_cols, const uint32_t *d_min_kmers, int32_t *d_cols_out,
+                             uint32_t *d_counts_out, uint64_t cap, unsigned long long *d_n_out,
+                             cudaStream_t stream);
+cudaError_t launch_set_column(uint8_t *matrix, uint64_t pitch, uint64_t num_rows, uint64_t col,
+                              const uint8_t *d_bloom, uint64_t n_bits, cudaStream_t stream);
+cudaError_t launch_fill_synthetic(uint8_t *matrix, uint64_t pitch, uint64_t num_rows, uint64_t num_cols,
+                                  uint64_t col_offset, uint64_t seed, int and_draws,
+                                  const uint64_t *d_planted_cols, const uint32_t *d_planted_thr, int n_planted,
+                                  cudaStream_t stream);
+
+}  // namespace bigsi

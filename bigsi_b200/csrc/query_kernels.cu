@@ -1,0 +1,534 @@
+// Fused gather-AND-{popcount|AND} kernel and its merge kernel for sm_100a.
+//
+// Replaces, for a whole batch of queries in one launch, the reference's
+//   BitMatrix.get_rows            (bigsi/matrix/bitmatrix.py:30-37, storage/base.py:106-109)
+//   per-k-mer bitwise_and         (bigsi/graph/index.py:75-80, utils/fncts.py:24-25)
+//   exact_filter AND over k-mers  (bigsi/graph/bigsi.py:192-195)
+//   unpack_and_sum column counts  (bigsi/graph/bigsi.py:35-44, 211-219)
+//
+// Work space: items = (column tile, global k-mer index), k-mer fastest.  Every CTA owns an equal,
+// contiguous run of slices of it; a slice is cut into SEGMENTS at (tile, query) boundaries; one
+// segment accumulates in registers and is written once, as bit planes, to its partial slot.
+//
+// Stage 1 (fused_query): persistent, warp specialised, one CTA per SM.  The last warp is the
+// producer: each lane issues one 1-D bulk async copy (cp.async.bulk, SASS UBLKCP) of one row
+// segment (tile_bytes of one gathered row) into a shared-memory ring slot; slot = G k-mers x h
+// rows, completion counted in bytes on an mbarrier.  The other warps are consumers: thread t owns
+// the 16-byte unit t of the tile (128 sample columns), reads the h row segments of each staged
+// k-mer as conflict-free LDS.128, ANDs them (LOP3) and feeds the 128-bit vector into a bit-sliced
+// carry-save counter (Harley-Seal: ones/twos/fours + ripple planes => up to 16-bit vertical
+// counters), so the kernel stays HBM-bound instead of ALU-bound.
+//
+// Stage 2 (merge): per (query, tile, column chunk) adds the bit-sliced partial counters of all
+// segments with ripple-carry full adders (2 LOP3 per plane), tree-reduces across thread groups in
+// shared memory and expands the planes to uint32 counts once (or ANDs the presence planes).
+#include "ptx.cuh"
+#include "query.cuh"
+
+namespace bigsi {
+
+struct W4 {
+    uint32_t v[4];
+};
+__device__ __forceinline__ W4 to_w4(const uint4 &a) { return W4{{a.x, a.y, a.z, a.w}}; }
+
+// ------------------------------------------------------------------------------------------
+// segment iteration (identical on producer and consumer side)
+// ------------------------------------------------------------------------------------------
+struct Seg {
+    uint64_t kg0;  // first global k-mer index
+    uint32_t nk;   // k-mers in this segment (<= items_per_slice)
+    uint32_t tile;
+    uint32_t q;
+    uint32_t slice;
+};
+
+struct SegIter {
+    uint64_t p, end, total;
+    const int64_t *qoff;
+    uint32_t nq, ips, q, tile;
+    bool have_tile;
+
+    __device__ SegIter(const QueryParams &P, uint64_t b, uint64_t e)
+        : p(b), end(e), total(P.total_kmers), qoff(P.qoff), nq(P.n_queries), ips(P.items_per_slice), q(0),
+          tile(0), have_tile(false)
+    {
+    }
+    __device__ uint32_t find_query(uint64_t kg) const
+    {
+        // q with qoff[q] <= kg < qoff[q+1]  (skips empty queries)
+        uint32_t lo = 0, hi = nq;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if ((uint64_t)__ldg(qoff + mid) <= kg) lo = mid; else hi = mid;
+        }
+        return lo;
+    }
+    __device__ bool next(Seg &s)
+    {
+        if (p >= end) return false;
+        const uint32_t t = (uint32_t)(p / total);
+        const uint64_t kg = p - (uint64_t)t * total;
+        if (!have_tile || t != tile) {
+            tile = t;
+            have_tile = true;
+            q = find_query(kg);
+        } else {
+            while (kg >= (uint64_t)__ldg(qoff + q + 1)) ++q;
+        }
+        uint64_t lim = (uint64_t)__ldg(qoff + q + 1) - kg;  // to the end of the query (<= end of tile)
+        if (end - p < lim) lim = end - p;
+        const uint64_t sl = p / ips;
+        const uint64_t to_slice_end = (sl + 1) * ips - p;
+        if (to_slice_end < lim) lim = to_slice_end;
+        s.kg0 = kg;
+        s.nk = (uint32_t)lim;
+        s.tile = t;
+        s.q = q;
+        s.slice = (uint32_t)sl;
+        p += lim;
+        return true;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// bit-sliced vertical counter: 128 columns x 16 bits per thread
+// ------------------------------------------------------------------------------------------
+constexpr int kHiPlanes = kSegPlanes - 3;  // planes of weight 8 .. 2^15
+
+struct VCounter {
+    W4 ones, twos, fours;  // accumulators of weight 1, 2, 4
+    W4 p0, p1, p2;         // pending operands waiting for a partner at each level
+    W4 hi[kHiPlanes];
+    uint32_t n;            // inputs so far (uniform across the CTA)
+
+    __device__ __forceinline__ void reset()
+    {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ones.v[j] = twos.v[j] = fours.v[j] = 0;
+            p0.v[j] = p1.v[j] = p2.v[j] = 0;
+#pragma unroll
+            for (int b = 0; b < kHiPlanes; ++b) hi[b].v[j] = 0;
+        }
+        n = 0;
+    }
+    // acc <- acc ^ a ^ b ; carry <- maj(acc_old, a, b)
+    static __device__ __forceinline__ void csa(W4 &carry, W4 &acc, const W4 &a, const W4 &b)
+    {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t o = acc.v[j];
+            acc.v[j] = xor3(o, a.v[j], b.v[j]);
+            carry.v[j] = maj3(o, a.v[j], b.v[j]);
+        }
+    }
+    // nhi = number of live hi planes for this segment (uniform)
+    __device__ __forceinline__ void add(const W4 &x, uint32_t nhi)
+    {
+        const uint32_t i = n++;
+        if (!(i & 1)) { p0 = x; return; }
+        W4 c1;
+        csa(c1, ones, p0, x);
+        if (!(i & 2)) { p1 = c1; return; }
+        W4 c2;
+        csa(c2, twos, p1, c1);
+        if (!(i & 4)) { p2 = c2; return; }
+        W4 c;
+        csa(c, fours, p2, c2);
+#pragma unroll
+        for (int b = 0; b < kHiPlanes; ++b) {
+            if (b < (int)nhi) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t o = hi[b].v[j];
+                    hi[b].v[j] = o ^ c.v[j];
+                    c.v[j] = o & c.v[j];
+                }
+            }
+        }
+    }
+    // fold pending operands: pad the input stream with zero vectors to a multiple of 8
+    __device__ __forceinline__ void finish(uint32_t nhi)
+    {
+        const W4 z = {{0, 0, 0, 0}};
+        while (n & 7) add(z, nhi);
+    }
+};
+
+__device__ __forceinline__ void stg128(void *p, const W4 &x)
+{
+    *reinterpret_cast<uint4 *>(p) = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+}
+
+// write the live planes of one segment to its partial slot (plane-major, tile_bytes per plane)
+__device__ __forceinline__ void flush_planes(const VCounter &c, uint32_t nplanes, uint8_t *slot_unit,
+                                             uint32_t plane_stride)
+{
+    stg128(slot_unit, c.ones);
+    if (nplanes > 1) stg128(slot_unit + plane_stride, c.twos);
+    if (nplanes > 2) stg128(slot_unit + 2 * (size_t)plane_stride, c.fours);
+#pragma unroll
+    for (int b = 0; b < kHiPlanes; ++b)
+        if (b + 3 < (int)nplanes) stg128(slot_unit + (size_t)(b + 3) * plane_stride, c.hi[b]);
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 1: producer warp
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_producer(const QueryParams &P, uint8_t *ring, uint64_t *full, uint64_t *empty,
+                                             uint64_t begin, uint64_t end)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t h = P.h;
+    const uint32_t G = P.kmers_per_stage;
+    const uint32_t seg_stride = P.tile_bytes;
+    const uint32_t stage_bytes = G * h * seg_stride;
+    const uint64_t policy = policy_evict_first();
+    const uint64_t total = P.total_kmers;
+    const uint64_t n_copies = (end - begin) * h;  // row copies this CTA issues, in item order
+    uint32_t stage = 0, parity = 0;
+
+    // Row ids are read through a two-deep window of 32 consecutive copy slots per warp register,
+    // so the ids of the next >= 32 copies are always in registers before their ring slot frees up.
+    auto load_id = [&](uint64_t c) -> int32_t {
+        if (c >= n_copies) return 0;
+        const uint64_t item = begin + c / h;
+        const uint32_t j = (uint32_t)(c % h);
+        const uint64_t kg = item % total;
+        return __ldg(P.rows + kg * h + j);
+    };
+    uint64_t win_base = 0;
+    int32_t cur = load_id(lane), nxt = load_id(32 + lane);
+    uint64_t c0 = 0;  // copy index of the first row of the current ring slot
+
+    SegIter it(P, begin, end);
+    Seg s;
+    while (it.next(s)) {
+        const uint32_t tb0 = s.tile * P.tile_bytes;
+        const uint32_t tw = min(P.tile_bytes, P.row_bytes16 - tb0);
+        const uint8_t *src0 = P.matrix + tb0;
+        for (uint32_t k0 = 0; k0 < s.nk; k0 += G) {
+            const uint32_t n_rows = min(G, s.nk - k0) * h;
+            uint8_t *dst0 = ring + (size_t)stage * stage_bytes;
+            mbar_wait(&empty[stage], parity ^ 1);  // slot drained by all consumer warps
+            if (lane == 0) mbar_arrive_expect_tx(&full[stage], n_rows * tw);
+            __syncwarp();
+            for (uint32_t i0 = 0; i0 < n_rows; i0 += 32) {
+                const uint64_t cb = c0 + i0;
+                while (cb >= win_base + 32) {
+                    cur = nxt;
+                    win_base += 32;
+                    nxt = load_id(win_base + 32 + lane);
+                }
+                const uint32_t off = (uint32_t)(cb - win_base) + lane;  // 0..62
+                const int32_t r0 = __shfl_sync(0xffffffffu, cur, off & 31);
+                const int32_t r1 = __shfl_sync(0xffffffffu, nxt, off & 31);
+                const int32_t row = off < 32 ? r0 : r1;
+                const uint32_t i = i0 + lane;
+                if (i < n_rows)
+                    bulk_g2s_hint(dst0 + (size_t)i * seg_stride, src0 + (uint64_t)(uint32_t)row * P.pitch, tw,
+                                  &full[stage], policy);
+            }
+            c0 += n_rows;
+            if (++stage == P.n_stages) {
+                stage = 0;
+                parity ^= 1;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 1: consumer warps
+// ------------------------------------------------------------------------------------------
+template <int MODE, int HC>
+__device__ __forceinline__ void tma_consumer(const QueryParams &P, const uint8_t *ring, uint64_t *full,
+                                             uint64_t *empty, uint64_t begin, uint64_t end)
+{
+    const uint32_t unit = threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t h = HC ? HC : P.h;
+    const uint32_t G = P.kmers_per_stage;
+    const uint32_t seg_stride = P.tile_bytes;
+    const uint32_t stage_bytes = G * h * seg_stride;
+    uint32_t stage = 0, parity = 0;
+
+    VCounter ctr;
+    W4 acc;
+    SegIter it(P, begin, end);
+    Seg s;
+    while (it.next(s)) {
+        const uint32_t tb0 = s.tile * P.tile_bytes;
+        const uint32_t tw = min(P.tile_bytes, P.row_bytes16 - tb0);
+        const bool active = unit * 16 < tw;
+        const uint32_t nplanes = 32 - __clz(s.nk);
+        const uint32_t nhi = nplanes > 3 ? nplanes - 3 : 0;
+        if (MODE == kModeCounts) ctr.reset();
+        else acc = W4{{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}};
+
+        for (uint32_t k0 = 0; k0 < s.nk; k0 += G) {
+            const uint32_t gn = min(G, s.nk - k0);
+            mbar_wait(&full[stage], parity);  // all row segments of this slot have landed
+            if (active) {
+                const uint8_t *base = ring + (size_t)stage * stage_bytes + unit * 16;
+                for (uint32_t g = 0; g < gn; ++g) {
+                    const uint8_t *b = base + g * h * seg_stride;
+                    W4 x = to_w4(lds128(b));
+                    if (HC == 3) {
+                        const W4 y = to_w4(lds128(b + seg_stride));
+                        const W4 z = to_w4(lds128(b + 2 * seg_stride));
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) x.v[j] = and3(x.v[j], y.v[j], z.v[j]);
+                    } else {
+                        for (uint32_t r = 1; r < h; ++r) {
+                            const W4 y = to_w4(lds128(b + r * seg_stride));
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) x.v[j] &= y.v[j];
+                        }
+                    }
+                    if (MODE == kModeCounts) {
+                        ctr.add(x, nhi);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc.v[j] &= x.v[j];
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);  // this warp is done reading the slot
+            if (++stage == P.n_stages) {
+                stage = 0;
+                parity ^= 1;
+            }
+        }
+        if (active) {
+            const uint64_t slot = (uint64_t)s.slice + (uint64_t)s.tile * P.n_queries + s.q;
+            uint8_t *dst = P.partial + slot * P.planes_per_slot * P.tile_bytes + unit * 16;
+            if (MODE == kModeCounts) {
+                ctr.finish(nhi);
+                flush_planes(ctr, nplanes, dst, P.tile_bytes);
+            } else {
+                stg128(dst, acc);
+            }
+        }
+    }
+}
+
+template <int MODE, int HC>
+__global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_constant__ QueryParams P)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *empty = full + kMaxStages;
+    uint8_t *ring = smem + kSmemHeaderBytes;
+    const uint32_t consumer_warps = (blockDim.x >> 5) - 1;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < P.n_stages; ++s) {
+            mbar_init(&full[s], 1);                // one arrive.expect_tx by the producer + tx bytes
+            mbar_init(&empty[s], consumer_warps);  // one arrive per consumer warp
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const uint64_t span = (uint64_t)P.slices_per_cta * P.items_per_slice;
+    const uint64_t begin = (uint64_t)blockIdx.x * span;
+    uint64_t end = begin + span;
+    if (end > P.total_items) end = P.total_items;
+    if (begin >= end) return;
+
+    if ((threadIdx.x >> 5) == consumer_warps)
+        tma_producer(P, ring, full, empty, begin, end);
+    else
+        tma_consumer<MODE, HC>(P, ring, full, empty, begin, end);
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 2: merge.  Block = 256 threads = WPB words x NG slot groups; one block per
+// (query, tile, chunk of WPB 32-bit words).
+// ------------------------------------------------------------------------------------------
+constexpr int kMergeThreads = 256;
+constexpr int kMaxTotalPlanes = 32;
+
+template <int MODE, int NG>
+__global__ void __launch_bounds__(kMergeThreads) merge_kernel(const __grid_constant__ QueryParams P)
+{
+    constexpr int WPB = kMergeThreads / NG;                   // words per block
+    constexpr int NP = MODE == kModeCounts ? kMaxTotalPlanes : 1;
+    __shared__ uint32_t sm[(NG > 1 ? NG / 2 : 1) * NP * WPB];  // [group][plane][word]
+
+    const uint32_t chunk_bytes = WPB * 4;
+    const uint32_t cpt = (P.tile_bytes + chunk_bytes - 1) / chunk_bytes;
+    const uint64_t bid = blockIdx.x;
+    const uint32_t chunk = (uint32_t)(bid % cpt);
+    const uint64_t tq = bid / cpt;
+    const uint32_t t = (uint32_t)(tq % P.n_tiles);
+    const uint32_t q = (uint32_t)(tq / P.n_tiles);
+    const uint32_t tb0 = t * P.tile_bytes;
+    const uint32_t tw = min(P.tile_bytes, P.row_bytes16 - tb0);
+    const uint32_t cb = chunk * chunk_bytes;
+    if (cb >= tw) return;
+
+    const uint32_t w = threadIdx.x % WPB;
+    const uint32_t g = threadIdx.x / WPB;
+    const bool valid = cb + w * 4 < tw;
+    const uint32_t TP = MODE == kModeCounts ? P.total_planes : 1;
+
+    uint32_t acc[NP];
+#pragma unroll
+    for (int b = 0; b < NP; ++b) acc[b] = MODE == kModeCounts ? 0u : 0xffffffffu;
+
+    const uint64_t k0 = (uint64_t)__ldg(P.qoff + q), k1 = (uint64_t)__ldg(P.qoff + q + 1);
+    if (k1 > k0 && valid) {
+        const uint64_t I0 = (uint64_t)t * P.total_kmers + k0, I1 = (uint64_t)t * P.total_kmers + k1;
+        const uint64_t ips = P.items_per_slice;
+        const uint64_t s_first = I0 / ips, s_last = (I1 - 1) / ips;
+        for (uint64_t s = s_first + g; s <= s_last; s += NG) {
+            const uint64_t slot = s + (uint64_t)t * P.n_queries + q;
+            const uint8_t *src = P.partial + slot * P.planes_per_slot * P.tile_bytes + cb + w * 4;
+            if (MODE == kModeCounts) {
+                const uint64_t lo = max(I0, s * ips), hi = min(I1, (s + 1) * ips);
+                const uint32_t ps = 32 - __clz((uint32_t)(hi - lo));  // planes this segment wrote
+                uint32_t x[kSegPlanes];
+#pragma unroll
+                for (int b = 0; b < kSegPlanes; ++b)
+                    x[b] = b < (int)ps ? *reinterpret_cast<const uint32_t *>(src + (size_t)b * P.tile_bytes) : 0u;
+                uint32_t carry = 0;
+#pragma unroll
+                for (int b = 0; b < NP; ++b) {
+                    if (b < (int)TP) {
+                        const uint32_t xb = b < kSegPlanes ? x[b < kSegPlanes ? b : 0] : 0u;
+                        const uint32_t o = acc[b];
+                        acc[b] = xor3(o, xb, carry);
+                        carry = maj3(o, xb, carry);
+                    }
+                }
+            } else {
+                acc[0] &= *reinterpret_cast<const uint32_t *>(src);
+            }
+        }
+    }
+
+    // tree reduction over the NG slot groups
+    if (NG > 1) {
+#pragma unroll
+        for (int stride = NG / 2; stride >= 1; stride >>= 1) {
+            if ((int)g >= stride && (int)g < 2 * stride) {
+#pragma unroll
+                for (int b = 0; b < NP; ++b)
+                    if (b < (int)TP) sm[((g - stride) * NP + b) * WPB + w] = acc[b];
+            }
+            __syncthreads();
+            if ((int)g < stride) {
+                if (MODE == kModeCounts) {
+                    uint32_t carry = 0;
+#pragma unroll
+                    for (int b = 0; b < NP; ++b) {
+                        if (b < (int)TP) {
+                            const uint32_t xb = sm[(g * NP + b) * WPB + w];
+                            const uint32_t o = acc[b];
+                            acc[b] = xor3(o, xb, carry);
+                            carry = maj3(o, xb, carry);
+                        }
+                    }
+                } else {
+                    acc[0] &= sm[g * WPB + w];
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // group 0 publishes the merged planes; every thread then expands columns
+    if (g == 0) {
+#pragma unroll
+        for (int b = 0; b < NP; ++b)
+            if (b < (int)TP) sm[b * WPB + w] = valid ? acc[b] : 0u;
+    }
+    __syncthreads();
+
+    if (MODE == kModeCounts) {
+        uint32_t *out = reinterpret_cast<uint32_t *>(P.out) + (uint64_t)q * P.out_stride;
+        const uint32_t col_base = (tb0 + cb) * 8;
+        // bit i of a little-endian 32-bit word of MSB-first bytes is column (i ^ 7) of that word
+        const uint32_t ncols_here = min((uint32_t)WPB * 32u, (tw - cb) * 8u);  // never past this tile
+        for (uint32_t c = threadIdx.x; c < ncols_here; c += kMergeThreads) {
+            const uint32_t col = col_base + c;
+            if (col >= P.num_cols) break;
+            const uint32_t word = c >> 5, bit = (c & 31) ^ 7;
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int b = 0; b < NP; ++b)
+                if (b < (int)TP) cnt |= ((sm[b * WPB + word] >> bit) & 1u) << b;
+            out[col] = cnt;
+        }
+    } else {
+        uint8_t *out = reinterpret_cast<uint8_t *>(P.out) + (uint64_t)q * P.out_stride;
+        const uint32_t row_bytes = (P.num_cols + 7) >> 3;
+        const uint32_t nbytes_here = min((uint32_t)WPB * 4u, tw - cb);  // never past this tile
+        for (uint32_t c = threadIdx.x; c < nbytes_here; c += kMergeThreads) {
+            const uint32_t byte = tb0 + cb + c;
+            if (byte >= row_bytes) break;
+            uint32_t v = (sm[c >> 2] >> (8 * (c & 3))) & 0xffu;
+            if (byte == row_bytes - 1 && (P.num_cols & 7)) v &= 0xff00u >> (P.num_cols & 7);
+            out[byte] = (uint8_t)v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+template <int MODE, int HC>
+static cudaError_t launch_one(const QueryParams &p, int grid, cudaStream_t stream)
+{
+    fused_query<MODE, HC><<<grid, query_block_threads(p), query_smem_bytes(p), stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_query(const QueryParams &p, int mode, int grid, cudaStream_t stream)
+{
+    if (mode == kModeCounts)
+        return p.h == 3 ? launch_one<kModeCounts, 3>(p, grid, stream) : launch_one<kModeCounts, 0>(p, grid, stream);
+    return p.h == 3 ? launch_one<kModeAnd, 3>(p, grid, stream) : launch_one<kModeAnd, 0>(p, grid, stream);
+}
+
+template <int MODE>
+static cudaError_t launch_merge_mode(const QueryParams &p, cudaStream_t stream)
+{
+    // slots one (tile, query) can span: decides how many thread groups share the slot loop
+    const uint64_t longest = p.total_planes >= 32 ? 0xffffffffull : ((1ull << p.total_planes) - 1);
+    const uint64_t max_slots = longest / p.items_per_slice + 2;
+    const int ng = MODE == kModeAnd ? (max_slots <= 2 ? 1 : 8) : (max_slots <= 2 ? 1 : (max_slots <= 16 ? 8 : 32));
+    const uint32_t chunk_bytes = (kMergeThreads / ng) * 4;
+    const uint64_t cpt = (p.tile_bytes + chunk_bytes - 1) / chunk_bytes;
+    const uint64_t blocks = cpt * p.n_tiles * p.n_queries;
+    if (blocks == 0) return cudaSuccess;
+    if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    if (ng == 1) merge_kernel<MODE, 1><<<(unsigned)blocks, kMergeThreads, 0, stream>>>(p);
+    else if (ng == 8) merge_kernel<MODE, 8><<<(unsigned)blocks, kMergeThreads, 0, stream>>>(p);
+    else merge_kernel<MODE, 32><<<(unsigned)blocks, kMergeThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge(const QueryParams &p, int mode, cudaStream_t stream)
+{
+    return mode == kModeCounts ? launch_merge_mode<kModeCounts>(p, stream) : launch_merge_mode<kModeAnd>(p, stream);
+}
+
+cudaError_t query_kernels_init()
+{
+    cudaError_t e;
+#define BIGSI_SET_SMEM(K)                                                                   \
+    e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);  \
+    if (e != cudaSuccess) return e;
+    BIGSI_SET_SMEM((fused_query<kModeCounts, 3>))
+    BIGSI_SET_SMEM((fused_query<kModeCounts, 0>))
+    BIGSI_SET_SMEM((fused_query<kModeAnd, 3>))
+    BIGSI_SET_SMEM((fused_query<kModeAnd, 0>))
+#undef BIGSI_SET_SMEM
+    return cudaSuccess;
+}
+
+}  // namespace bigsi

@@ -1,0 +1,203 @@
+"""DeviceIndex: one column shard of the m x N signature matrix resident in HBM.
+
+Python face of the C ABI (include/bigsi_b200.h).  Replaces the reference's storage backends
+(bigsi/storage/*.py) plus BitMatrix (bigsi/matrix/bitmatrix.py:7-75) for the search path: rows are
+addressed by number in one packed HBM array instead of by key in a KV store.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import MODE_AND, MODE_COUNTS, check
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None and a.size else ctypes.c_void_p(0)
+
+
+def kmers_to_array(kmers, k):
+    """list of k-mer strings (all of length k, ASCII) -> uint8 [n, k]."""
+    n = len(kmers)
+    if n == 0:
+        return np.zeros((0, k), dtype=np.uint8)
+    joined = "".join(kmers).encode("utf-8")
+    if len(joined) != n * k:
+        raise ValueError("k-mers must be ASCII strings of length k=%d" % k)
+    return np.frombuffer(joined, dtype=np.uint8).reshape(n, k)
+
+
+def hash_kmers(kmers, k, h, m, canonical=True, device=0):
+    """Row ids int32 [n, h] of n k-mers (bigsi/bloom/bloomfilter.py:5-13 after
+    utils/fncts.py:47-54 when canonical) computed by the CUDA hash kernel."""
+    arr = kmers if isinstance(kmers, np.ndarray) else kmers_to_array(list(kmers), k)
+    arr = np.ascontiguousarray(arr, dtype=np.uint8)
+    out = np.empty((arr.shape[0], h), dtype=np.int32)
+    check(_lib.lib().bigsi_b200_hash_kmers(device, _ptr(arr), arr.shape[0], k, h, m, 1 if canonical else 0, _ptr(out)))
+    return out
+
+
+class DeviceIndex:
+    def __init__(self, num_rows, num_cols, col_capacity=0, col_offset=0, device=0):
+        self._h = ctypes.c_void_p(0)
+        L = _lib.lib()
+        check(L.bigsi_b200_index_create(device, num_rows, num_cols, col_capacity, col_offset, ctypes.byref(self._h)))
+        self._L = L
+
+    # -- lifecycle -----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.bigsi_b200_index_destroy(self._h)
+            self._h = ctypes.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        if not self._h.value:
+            raise ValueError("index has been destroyed")
+        return self._h
+
+    def info(self):
+        i = _lib.Info()
+        check(self._L.bigsi_b200_index_get_info(self.handle, ctypes.byref(i)))
+        return i.asdict()
+
+    @property
+    def num_rows(self):
+        return self.info()["num_rows"]
+
+    @property
+    def num_cols(self):
+        return self.info()["num_cols"]
+
+    @property
+    def row_bytes(self):
+        return self.info()["row_bytes"]
+
+    def set_option(self, key, value):
+        check(self._L.bigsi_b200_index_set_option(self.handle, key.encode(), int(value)))
+
+    def timing_collect(self):
+        """(fused_kernel_ms_sum, merge_kernel_ms_sum, n_launches) since the last collect."""
+        a, b, n = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_uint64(0)
+        check(self._L.bigsi_b200_index_timing_collect(self.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)))
+        return a.value, b.value, n.value
+
+    # -- matrix content ------------------------------------------------------
+    def upload_rows(self, row0, rows, src_byte_offset=0):
+        """rows: uint8 [n, >= row_bytes] in the reference's bitarray.tobytes() layout."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint8)
+        if rows.ndim != 2:
+            raise ValueError("rows must be 2-D (n_rows, bytes)")
+        check(self._L.bigsi_b200_index_upload_rows(self.handle, row0, rows.shape[0], _ptr(rows), rows.strides[0],
+                                                   src_byte_offset))
+
+    def download_rows(self, row0, n_rows):
+        out = np.empty((n_rows, self.row_bytes), dtype=np.uint8)
+        check(self._L.bigsi_b200_index_download_rows(self.handle, row0, n_rows, _ptr(out), out.strides[0] if n_rows else 0))
+        return out
+
+    def set_column(self, col, bloom_packed, n_bits):
+        bloom_packed = np.ascontiguousarray(bloom_packed, dtype=np.uint8)
+        if bloom_packed.size * 8 < n_bits:
+            raise ValueError("bloom filter shorter than n_bits")
+        check(self._L.bigsi_b200_index_set_column(self.handle, col, _ptr(bloom_packed), n_bits))
+
+    def fill_synthetic(self, seed=0, and_draws=1, planted_cols=(), planted_thr=()):
+        pc = np.ascontiguousarray(planted_cols, dtype=np.uint64)
+        pt = np.ascontiguousarray(planted_thr, dtype=np.uint32)
+        if pc.shape != pt.shape:
+            raise ValueError("planted_cols and planted_thr must have the same length")
+        check(self._L.bigsi_b200_index_fill_synthetic(self.handle, seed, and_draws, _ptr(pc), _ptr(pt), pc.size))
+
+    # -- queries (host buffers) ----------------------------------------------
+    @staticmethod
+    def _offsets(q_offsets, n):
+        if q_offsets is None:
+            q_offsets = [0, n]
+        q = np.ascontiguousarray(q_offsets, dtype=np.int64)
+        if q.ndim != 1 or q.size < 1 or q[0] != 0 or q[-1] != n:
+            raise ValueError("q_offsets must start at 0 and end at the number of k-mers")
+        return q
+
+    def _out(self, mode, nq):
+        nc = self.num_cols
+        if mode == MODE_COUNTS:
+            return np.zeros((nq, max(nc, 1)), dtype=np.uint32), max(nc, 1)
+        rb = max((nc + 7) // 8, 1)
+        return np.zeros((nq, rb), dtype=np.uint8), rb
+
+    def search_kmers(self, kmers, k, h, q_offsets=None, mode=MODE_COUNTS):
+        """Unique raw k-mers of a batch of queries -> uint32 counts [Q, N] or packed MSB-first
+        presence bytes [Q, ceil(N/8)]."""
+        arr = kmers if isinstance(kmers, np.ndarray) else kmers_to_array(list(kmers), k)
+        arr = np.ascontiguousarray(arr, dtype=np.uint8)
+        q = self._offsets(q_offsets, arr.shape[0])
+        out, stride = self._out(mode, q.size - 1)
+        check(self._L.bigsi_b200_search_kmers(self.handle, mode, _ptr(arr), _ptr(q), q.size - 1, k, h, _ptr(out), stride))
+        nc = self.num_cols
+        return out[:, :nc] if mode == MODE_COUNTS else out[:, : (nc + 7) // 8]
+
+    def search_rows(self, rows, h, q_offsets=None, mode=MODE_COUNTS):
+        rows = np.ascontiguousarray(rows, dtype=np.int32).reshape(-1, h)
+        q = self._offsets(q_offsets, rows.shape[0])
+        out, stride = self._out(mode, q.size - 1)
+        check(self._L.bigsi_b200_search_rows(self.handle, mode, _ptr(rows), _ptr(q), q.size - 1, h, _ptr(out), stride))
+        nc = self.num_cols
+        return out[:, :nc] if mode == MODE_COUNTS else out[:, : (nc + 7) // 8]
+
+    def search_kmers_hits(self, kmers, k, h, min_kmers, q_offsets=None, cap=None):
+        """Fused search + threshold.  Returns a list (one per query) of (colours int32, counts
+        uint32) with count >= min_kmers[q], colours ascending."""
+        arr = kmers if isinstance(kmers, np.ndarray) else kmers_to_array(list(kmers), k)
+        arr = np.ascontiguousarray(arr, dtype=np.uint8)
+        q = self._offsets(q_offsets, arr.shape[0])
+        nq = q.size - 1
+        mk = np.ascontiguousarray(np.broadcast_to(np.asarray(min_kmers, dtype=np.uint32), (nq,)))
+        nc = self.num_cols
+        cap = nc if cap is None else int(cap)
+        cols = np.empty((nq, max(cap, 1)), dtype=np.int32)
+        cnts = np.empty((nq, max(cap, 1)), dtype=np.uint32)
+        n = np.zeros(nq, dtype=np.uint64)
+        check(self._L.bigsi_b200_search_kmers_hits(self.handle, _ptr(arr), _ptr(q), nq, k, h, _ptr(mk), _ptr(cols),
+                                                   _ptr(cnts), cap, _ptr(n)))
+        res = []
+        for i in range(nq):
+            ni = int(min(n[i], cap))
+            c, v = cols[i, :ni], cnts[i, :ni]
+            order = np.argsort(c, kind="stable")
+            res.append((c[order], v[order], int(n[i])))
+        return res
+
+    def lookup_kmers(self, kmers, k, h):
+        """Per-k-mer AND vectors: uint8 [n, ceil(N/8)] (graph/index.py:42-49)."""
+        arr = kmers if isinstance(kmers, np.ndarray) else kmers_to_array(list(kmers), k)
+        arr = np.ascontiguousarray(arr, dtype=np.uint8)
+        rb = max(self.row_bytes, 1)
+        out = np.zeros((arr.shape[0], rb), dtype=np.uint8)
+        check(self._L.bigsi_b200_lookup_kmers(self.handle, _ptr(arr), arr.shape[0], k, h, _ptr(out), rb))
+        return out[:, : self.row_bytes]
+
+    # -- queries (device pointers; torch tensors or raw addresses) --------------
+    def query_dev(self, mode, d_rows, d_q_offsets, n_queries, total_kmers, h, d_out, out_stride, stream=0,
+                  max_query_kmers=0):
+        check(self._L.bigsi_b200_query_dev(self.handle, mode, d_rows, d_q_offsets, n_queries, total_kmers,
+                                           max_query_kmers, h, d_out, out_stride, stream))
+
+    def lookup_dev(self, d_rows, n_kmers, h, d_out, out_stride, stream=0):
+        check(self._L.bigsi_b200_lookup_dev(self.handle, d_rows, n_kmers, h, d_out, out_stride, stream))
+
+
+def hash_kmers_dev(d_kmers, n, k, h, m, d_rows_out, stream=0, canonical=True):
+    check(_lib.lib().bigsi_b200_hash_kmers_dev(d_kmers, n, k, h, m, 1 if canonical else 0, d_rows_out, stream))
+
+
+def threshold_dev(d_counts, counts_stride, n_queries, num_cols, d_min_kmers, d_cols_out, d_counts_out, cap, d_n_out,
+                  stream=0):
+    check(_lib.lib().bigsi_b200_threshold_dev(d_counts, counts_stride, n_queries, num_cols, d_min_kmers, d_cols_out,
+                                              d_counts_out, cap, d_n_out, stream))

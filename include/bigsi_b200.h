@@ -1,0 +1,168 @@
+/*
+ * bigsi_b200.h -- C ABI of the B200-native BIGSI query engine (libbigsi_b200.so).
+ *
+ * Drop-in boundary for the reference's search hot path (Phelimb/BIGSI v0.3.8; citations are
+ * relative to the reference tree, bigsi/...).  The m x N bit-sliced signature matrix that the
+ * reference keeps one row per key in RocksDB/BerkeleyDB/Redis (storage/base.py:86-109) lives
+ * here as ONE packed array in HBM: row r starts at r * row_pitch_bytes, bytes are exactly the
+ * reference's `bitarray.tobytes()` (column c -> byte c>>3, mask 0x80>>(c&7); storage/base.py:86-99),
+ * the pitch is padded to a multiple of 128 bytes and all padding bits are zero.
+ *
+ * Conventions: plain C types only; every function returns 0 (BIGSI_B200_OK) or a negative
+ * error code and leaves a message for bigsi_b200_last_error() (thread local); the caller owns
+ * every host buffer; `_dev` entry points take DEVICE pointers plus a cudaStream_t (passed as
+ * void*) and are stream-ordered/asynchronous, all other entry points synchronise before they
+ * return.  One index handle = one column shard on one GPU; multi-GPU deployments run one
+ * process per GPU (column sharding).  A handle owns scratch memory, so calls on
+ * one handle must not overlap (one stream / one host thread at a time).  There is NO CPU
+ * fallback: without a CUDA device every compute entry point fails with BIGSI_B200_ERR_NO_DEVICE
+ * or BIGSI_B200_ERR_CUDA.
+ */
+#ifndef BIGSI_B200_H
+#define BIGSI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BIGSI_B200_ABI_VERSION 2
+
+enum {
+    BIGSI_B200_OK = 0,
+    BIGSI_B200_ERR_INVALID = -1,   /* bad argument */
+    BIGSI_B200_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+    BIGSI_B200_ERR_OOM = -3,       /* device or pinned-host allocation failed */
+    BIGSI_B200_ERR_NO_DEVICE = -4, /* no usable CUDA device */
+    BIGSI_B200_ERR_RANGE = -5      /* row / column / capacity out of range */
+};
+
+/* query modes */
+enum {
+    BIGSI_B200_MODE_COUNTS = 0, /* per-column k-mer counts: graph/bigsi.py:35-44,211-219 (unpack_and_sum) */
+    BIGSI_B200_MODE_AND = 1     /* AND over all k-mers:     graph/bigsi.py:192-195 (exact_filter)         */
+};
+
+typedef struct bigsi_b200_index bigsi_b200_index; /* opaque */
+
+typedef struct {
+    uint64_t num_rows;        /* m  (Bloom filter size; "number_of_rows", matrix/bitmatrix.py:3)     */
+    uint64_t num_cols;        /* N of this shard ("number_of_cols", matrix/bitmatrix.py:4)            */
+    uint64_t col_capacity;    /* columns the pitch can hold (insert grows num_cols up to this)        */
+    uint64_t col_offset;      /* global colour of local column 0 (multiple of 8)                      */
+    uint64_t row_bytes;       /* ceil(num_cols / 8)                                                   */
+    uint64_t row_pitch_bytes; /* multiple of 128                                                      */
+    uint64_t matrix_bytes;    /* num_rows * row_pitch_bytes resident in HBM                           */
+    int32_t device;
+    int32_t sm_count;
+    /* statistics of the most recent query launch on this handle */
+    uint64_t last_kmers;             /* k-mer lookups in that launch                                  */
+    uint64_t last_algorithmic_bytes; /* kmers * h * row_bytes                 */
+    uint32_t last_grid, last_block, last_smem_bytes;
+    uint32_t last_tile_bytes, last_n_tiles, last_kmers_per_stage, last_n_stages, last_n_slices;
+    uint64_t kernel_launches;        /* cumulative count of kernels this handle has launched          */
+    uint64_t scratch_bytes;          /* partial-plane workspace currently allocated                   */
+} bigsi_b200_info;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int bigsi_b200_abi_version(void);
+const char *bigsi_b200_last_error(void);
+int bigsi_b200_device_count(int *count_out);
+
+/* Pinned host buffers for the host<->device legs of the host-buffer entry points. */
+int bigsi_b200_host_alloc(uint64_t bytes, void **ptr_out);
+int bigsi_b200_host_free(void *ptr);
+
+/* ---- index lifecycle (replaces get_storage()/BitMatrix.create: storage/__init__.py:18-19,
+ *      matrix/bitmatrix.py:19-25) ------------------------------------------------------------ */
+int bigsi_b200_index_create(int device, uint64_t num_rows, uint64_t num_cols, uint64_t col_capacity,
+                            uint64_t col_offset, bigsi_b200_index **index_out);
+int bigsi_b200_index_destroy(bigsi_b200_index *index); /* storage.delete_all()/close(): graph/bigsi.py:249-250 */
+int bigsi_b200_index_get_info(const bigsi_b200_index *index, bigsi_b200_info *info_out);
+
+/* Tuning / instrumentation knobs (value 0 = automatic): "tile_bytes", "grid", "kmers_per_stage",
+ * "n_stages", "ctas_per_sm"; "timing" (1 = bracket the fused kernel and the merge kernel of
+ * every query launch with CUDA events, read back with bigsi_b200_index_timing_collect). */
+int bigsi_b200_index_set_option(bigsi_b200_index *index, const char *key, int64_t value);
+/* Synchronises, sums the event-timed durations recorded since the last collect and resets them.
+ * fused_ms = fused gather-AND-count kernel, merge_ms = merge kernel, n = query launches timed. */
+int bigsi_b200_index_timing_collect(bigsi_b200_index *index, double *fused_ms_out, double *merge_ms_out,
+                                    uint64_t *n_out);
+
+/* Rows in the reference's byte layout (BitMatrix.set_rows: matrix/bitmatrix.py:42-44 ->
+ * storage/base.py:91-94).  Source row i starts at rows + i*src_stride; the shard's bytes are
+ * taken from byte offset src_byte_offset (= col_offset/8 when uploading from a full-width row). */
+int bigsi_b200_index_upload_rows(bigsi_b200_index *index, uint64_t row0, uint64_t n_rows,
+                                 const uint8_t *rows, uint64_t src_stride, uint64_t src_byte_offset);
+/* BitMatrix.get_rows (matrix/bitmatrix.py:30-37): row_bytes bytes per row into out + i*dst_stride. */
+int bigsi_b200_index_download_rows(const bigsi_b200_index *index, uint64_t row0, uint64_t n_rows,
+                                   uint8_t *out, uint64_t dst_stride);
+/* BitMatrix.insert_column (matrix/bitmatrix.py:67-75 -> storage/base.py:111-122): write Bloom
+ * filter bits (MSB-first, n_bits <= num_rows; rows >= n_bits get 0) into LOCAL column `col`;
+ * col == num_cols appends (num_cols grows by one, up to col_capacity). */
+int bigsi_b200_index_set_column(bigsi_b200_index *index, uint64_t col, const uint8_t *bloom_msb_first,
+                                uint64_t n_bits);
+/* Synthetic matrix, a pure function of (seed, row, GLOBAL column) -- DESIGN.md "Synthetic index".
+ * density = 2^-and_draws; planted columns are GLOBAL ids with a u32 threshold (0xffffffff = all ones). */
+int bigsi_b200_index_fill_synthetic(bigsi_b200_index *index, uint64_t seed, int and_draws,
+                                    const uint64_t *planted_cols, const uint32_t *planted_thr, int n_planted);
+
+/* ---- k-mer -> row ids (replaces convert_query_kmer + generate_hashes: utils/fncts.py:47-54,
+ *      bloom/bloomfilter.py:5-13, graph/index.py:62-70).  kmers = n*k raw ASCII bytes;
+ *      rows_out = n*h int32: signed MurmurHash3_x86_32 of the k bytes, seeds 0..h-1, floor-mod m.
+ *      canonical != 0 hashes min(kmer, reverse complement) (the search/bloom paths); canonical == 0
+ *      hashes the bytes as given (bare generate_hashes). */
+int bigsi_b200_hash_kmers(int device, const char *kmers, uint64_t n, int k, int h, uint64_t m,
+                          int canonical, int32_t *rows_out);
+int bigsi_b200_hash_kmers_dev(const char *d_kmers, uint64_t n, int k, int h, uint64_t m, int canonical,
+                              int32_t *d_rows_out, void *stream);
+
+/* ---- fused gather-AND-{count|AND} (replaces BitMatrix.get_rows + bitwise_and + exact_filter /
+ *      unpack_and_sum: matrix/bitmatrix.py:30-37, graph/index.py:72-80, graph/bigsi.py:35-44,192-219).
+ *      d_rows: total_kmers*h row ids; d_q_offsets: n_queries+1 k-mer offsets (q_offsets[0]=0,
+ *      q_offsets[n_queries]=total_kmers); max_query_kmers: upper bound on the longest query
+ *      (0 = unknown, total_kmers is assumed).
+ *      COUNTS: d_out = uint32 [n_queries][out_stride] (out_stride in ELEMENTS >= num_cols).
+ *      AND:    d_out = uint8  [n_queries][out_stride] (out_stride in BYTES >= row_bytes),
+ *              MSB-first presence bits; an empty query yields all-ones in the valid columns.    */
+int bigsi_b200_query_dev(bigsi_b200_index *index, int mode, const int32_t *d_rows,
+                         const int64_t *d_q_offsets, uint64_t n_queries, uint64_t total_kmers,
+                         uint64_t max_query_kmers, int h, void *d_out, uint64_t out_stride, void *stream);
+
+/* Per-k-mer AND vectors (KmerSignatureIndex.lookup: graph/index.py:42-49,75-80): d_out =
+ * uint8 [n_kmers][out_stride], out_stride >= row_bytes. */
+int bigsi_b200_lookup_dev(bigsi_b200_index *index, const int32_t *d_rows, uint64_t n_kmers, int h,
+                          uint8_t *d_out, uint64_t out_stride, void *stream);
+
+/* counts >= min_kmers (graph/bigsi.py:241-242) for a batch of queries: query q keeps the columns
+ * with d_counts[q*counts_stride + c] >= d_min_kmers[q] and stores up to `cap` (colour, count)
+ * pairs at d_cols_out/d_counts_out + q*cap (order unspecified; colours are LOCAL column ids);
+ * d_n_out[q] receives the number of hits (may exceed cap; only the first cap are stored). */
+int bigsi_b200_threshold_dev(const uint32_t *d_counts, uint64_t counts_stride, uint64_t n_queries,
+                             uint64_t num_cols, const uint32_t *d_min_kmers, int32_t *d_cols_out,
+                             uint32_t *d_counts_out, uint64_t cap, uint64_t *d_n_out, void *stream);
+
+/* ---- host-buffer calls (the reference-facing plugin path: everything below takes and returns
+ *      HOST memory; H2D/D2H copies happen inside). ------------------------------------------- */
+/* Queries given as raw k-mers (n*k ASCII, already unique per query -- graph/index.py:45). */
+int bigsi_b200_search_kmers(bigsi_b200_index *index, int mode, const char *kmers,
+                            const int64_t *q_offsets, uint64_t n_queries, int k, int h,
+                            void *out, uint64_t out_stride);
+/* Queries given as precomputed row ids. */
+int bigsi_b200_search_rows(bigsi_b200_index *index, int mode, const int32_t *rows,
+                           const int64_t *q_offsets, uint64_t n_queries, int h,
+                           void *out, uint64_t out_stride);
+/* Fused search + threshold (BIGSI.search's inexact_filter, graph/bigsi.py:211-230): raw unique
+ * k-mers in, compact (colour, count) hits out; layout as bigsi_b200_threshold_dev. */
+int bigsi_b200_search_kmers_hits(bigsi_b200_index *index, const char *kmers, const int64_t *q_offsets,
+                                 uint64_t n_queries, int k, int h, const uint32_t *min_kmers,
+                                 int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_out);
+/* lookup(): per-k-mer AND vectors to host, out = uint8 [n][out_stride]. */
+int bigsi_b200_lookup_kmers(bigsi_b200_index *index, const char *kmers, uint64_t n, int k, int h,
+                            uint8_t *out, uint64_t out_stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIGSI_B200_H */

@@ -253,6 +253,41 @@ class OracleIndex:
         return format_results(hits, U, self.samples)
 
 
+# ---------------------------------------------------------------------------
+# row-id level entry points (used to check the device kernels without hashing)
+# ---------------------------------------------------------------------------
+def counts_from_rows(store, row_ids, num_cols):
+    """store uint8 [m, row_bytes]; row_ids int [U, h] -> int32 [num_cols] (graph/bigsi.py:35-44)."""
+    store = np.ascontiguousarray(store, dtype=np.uint8)
+    slot = np.ascontiguousarray(row_ids, dtype=np.int64)
+    rb = store.shape[1]
+    out = np.zeros(rb * 8, dtype=np.int32)
+    if slot.shape[0]:
+        lib().oracle_counts(_ptr(store), store.strides[0], rb, _ptr(slot), slot.shape[0], slot.shape[1], _ptr(out))
+    return out[:num_cols]
+
+
+def presence_from_rows(store, row_ids):
+    """AND over all k-mers (graph/bigsi.py:192-195): packed uint8 [row_bytes]."""
+    store = np.ascontiguousarray(store, dtype=np.uint8)
+    slot = np.ascontiguousarray(row_ids, dtype=np.int64)
+    rb = store.shape[1]
+    out = np.empty(rb, dtype=np.uint8)
+    lib().oracle_exact(_ptr(store), store.strides[0], rb, _ptr(slot), slot.shape[0], slot.shape[1], _ptr(out))
+    return out
+
+
+def and_per_kmer_from_rows(store, row_ids):
+    """graph/index.py:75-80: uint8 [U, row_bytes]."""
+    store = np.ascontiguousarray(store, dtype=np.uint8)
+    slot = np.ascontiguousarray(row_ids, dtype=np.int64)
+    rb = store.shape[1]
+    out = np.empty((slot.shape[0], rb), dtype=np.uint8)
+    if slot.shape[0]:
+        lib().oracle_and_per_kmer(_ptr(store), store.strides[0], rb, _ptr(slot), slot.shape[0], slot.shape[1], _ptr(out))
+    return out
+
+
 def format_results(hits, num_kmers, samples):
     """graph/bigsi.py:91-126 + 186-190: dict layout, rounding, tombstone filter."""
     out = []

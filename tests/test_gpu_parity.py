@@ -1,0 +1,393 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libbigsi_b200.so), against the CPU
+oracle (oracle/) and the committed golden fixtures generated from the unmodified reference.
+Everything here is bit-exact (integer / byte work)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.golden_util import bloom_from_b64, load, rows_from_b64
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def B():
+    import bigsi_b200
+
+    assert bigsi_b200.device_count() >= 1, "no CUDA device visible to libbigsi_b200.so"
+    return bigsi_b200
+
+
+def _rand_kmers(rng, n, k, alphabet="ACGT"):
+    a = np.frombuffer(alphabet.encode(), dtype=np.uint8)
+    return a[rng.integers(0, len(a), size=(n, k))]
+
+
+def _kmer_strs(arr):
+    return [bytes(r).decode() for r in arr]
+
+
+# ---------------------------------------------------------------------------
+# hashing (K1)
+# ---------------------------------------------------------------------------
+def test_hash_kat_and_golden(B):
+    # /root/reference/bigsi/tests/bloom/test_create_bloomfilter.py:5-8
+    assert B.generate_hashes("ATT", 3, 25) == {2, 15, 17}
+    assert B.generate_hashes("ATT", 1, 25) == {15}
+    assert B.generate_hashes("ATT", 2, 50) == {15, 27}
+    g = load("hashes.json")
+    for kat in g["kat"]:
+        assert sorted(B.generate_hashes(kat["element"], kat["h"], kat["m"])) == kat["set"]
+    for c in g["cases"]:
+        got = B.hash_kmers([c["kmer"]], len(c["kmer"]), c["h"], c["m"])[0].tolist()
+        assert got == c["rows"], c
+
+
+@pytest.mark.parametrize("k", [1, 3, 4, 5, 31, 32, 33, 63])
+def test_hash_random_vs_oracle(B, k):
+    rng = np.random.default_rng(k)
+    for alphabet in ("ACGT", "ACGTNacgt-"):
+        arr = _rand_kmers(rng, 3000, k, alphabet)
+        # add reverse-complement palindromes and pairs
+        arr[1] = np.frombuffer(O.canonical(bytes(arr[0])), dtype=np.uint8)
+        for h, m in ((1, 25), (3, 25_000_000), (5, 2_147_483_647), (2, 1)):
+            assert np.array_equal(B.hash_kmers(arr, k, h, m), O.hash_kmers(arr, k, h, m))
+            nc = B.hash_kmers(arr, k, h, m, canonical=False)
+            ref = np.array([[O.lib().oracle_hash_row(bytes(r), k, s, m) for s in range(h)] for r in arr[:50]])
+            assert np.array_equal(nc[:50], ref)
+
+
+# ---------------------------------------------------------------------------
+# fused kernel vs oracle on random matrices
+# ---------------------------------------------------------------------------
+def _random_index(B, rng, m, N, density=0.5):
+    rb = (N + 7) // 8
+    rows = (rng.random((m, rb * 8)) < density)
+    rows[:, N:] = False
+    packed = np.packbits(rows, axis=1)
+    ix = B.DeviceIndex(m, N)
+    ix.upload_rows(0, packed)
+    return ix, packed
+
+
+def _check_batch(ix, packed, N, row_ids, qoff, h):
+    counts = ix.search_rows(row_ids, h, q_offsets=qoff, mode=0)
+    pres = ix.search_rows(row_ids, h, q_offsets=qoff, mode=1)
+    for q in range(len(qoff) - 1):
+        r = row_ids[qoff[q] : qoff[q + 1]]
+        exp_c = O.counts_from_rows(packed, r, N)
+        assert np.array_equal(counts[q].astype(np.int64), exp_c.astype(np.int64)), "counts q=%d" % q
+        if len(r):
+            exp_p = O.presence_from_rows(packed, r)
+        else:
+            exp_p = np.packbits(np.arange(((N + 7) // 8) * 8) < N)
+        assert np.array_equal(pres[q], exp_p), "presence q=%d" % q
+
+
+@pytest.mark.parametrize("N", [1, 7, 8, 64, 100, 127, 128, 129, 777, 4096, 5000])
+@pytest.mark.parametrize("h", [1, 3])
+def test_counts_and_presence_small(B, N, h):
+    rng = np.random.default_rng(N * 10 + h)
+    m = 5003
+    ix, packed = _random_index(B, rng, m, N, density=0.7)
+    for U in (1, 2, 7, 8, 9, 64, 1000):
+        row_ids = rng.integers(0, m, size=(U, h), dtype=np.int32)
+        _check_batch(ix, packed, N, row_ids, [0, U], h)
+    ix.close()
+
+
+@pytest.mark.parametrize("h", [2, 4, 5, 11, 40])
+def test_other_hash_counts(B, h):
+    rng = np.random.default_rng(h)
+    m, N = 2000, 1500
+    ix, packed = _random_index(B, rng, m, N, density=0.9)
+    row_ids = rng.integers(0, m, size=(333, h), dtype=np.int32)
+    row_ids[5] = row_ids[5, 0]  # duplicate hashes inside one k-mer
+    _check_batch(ix, packed, N, row_ids, [0, 333], h)
+    ix.close()
+
+
+def test_multi_tile_wide_rows(B):
+    """N > 53 248 columns -> more than one column tile per row."""
+    rng = np.random.default_rng(5)
+    m, N = 300, 120_001
+    ix, packed = _random_index(B, rng, m, N, density=0.8)
+    row_ids = rng.integers(0, m, size=(500, 3), dtype=np.int32)
+    _check_batch(ix, packed, N, row_ids, [0, 500], 3)
+    assert ix.info()["last_n_tiles"] >= 3
+    ix.close()
+
+
+def test_ragged_batch_with_empty_queries(B):
+    rng = np.random.default_rng(11)
+    m, N = 4000, 3001
+    ix, packed = _random_index(B, rng, m, N, density=0.6)
+    lens = [0, 1, 0, 0, 5, 300, 8, 0, 1024, 17, 0]
+    qoff = np.concatenate([[0], np.cumsum(lens)])
+    row_ids = rng.integers(0, m, size=(int(qoff[-1]), 3), dtype=np.int32)
+    _check_batch(ix, packed, N, row_ids, qoff, 3)
+    # many short queries (one merge slot each)
+    lens = rng.integers(0, 40, size=500)
+    qoff = np.concatenate([[0], np.cumsum(lens)])
+    row_ids = rng.integers(0, m, size=(int(qoff[-1]), 3), dtype=np.int32)
+    _check_batch(ix, packed, N, row_ids, qoff, 3)
+    ix.close()
+
+
+@pytest.mark.parametrize("opts", [
+    {"tile_bytes": 16}, {"tile_bytes": 48, "kmers_per_stage": 1}, {"tile_bytes": 512, "kmers_per_stage": 4, "n_stages": 2},
+    {"grid": 1}, {"grid": 3, "tile_bytes": 128}, {"grid": 1000}, {"kmers_per_stage": 8, "n_stages": 3},
+])
+def test_launch_geometry_overrides(B, opts):
+    rng = np.random.default_rng(3)
+    m, N = 3000, 2500
+    ix, packed = _random_index(B, rng, m, N, density=0.75)
+    for key, v in opts.items():
+        ix.set_option(key, v)
+    lens = [700, 0, 33, 1500]
+    qoff = np.concatenate([[0], np.cumsum(lens)])
+    row_ids = rng.integers(0, m, size=(int(qoff[-1]), 3), dtype=np.int32)
+    _check_batch(ix, packed, N, row_ids, qoff, 3)
+    ix.close()
+
+
+def test_long_query_multi_slice(B):
+    """More items than 65 535 per CTA: several slices per CTA and > 16 count planes."""
+    rng = np.random.default_rng(17)
+    m, N = 512, 200
+    ix, packed = _random_index(B, rng, m, N, density=0.9)
+    U = 148 * 65535 + 12345
+    row_ids = rng.integers(0, m, size=(U, 3), dtype=np.int32)
+    counts = ix.search_rows(row_ids, 3, mode=0)[0]
+    assert np.array_equal(counts.astype(np.int64), O.counts_from_rows(packed, row_ids, N).astype(np.int64))
+    assert counts.max() > 65535
+    info = ix.info()
+    assert info["last_n_slices"] > info["last_grid"]
+    pres = ix.search_rows(row_ids, 3, mode=1)[0]
+    assert np.array_equal(pres, O.presence_from_rows(packed, row_ids))
+    ix.close()
+
+
+def test_kmer_level_entry_points(B):
+    rng = np.random.default_rng(23)
+    m, N, k, h = 10_007, 1234, 31, 3
+    ix, packed = _random_index(B, rng, m, N, density=0.8)
+    oix = O.OracleIndex(k, m, h, N, rows=packed)
+    arr = _rand_kmers(rng, 400, k)
+    arr[7] = arr[3]  # a duplicate raw k-mer counts twice at this level (dedup is the caller's job)
+    kmers = _kmer_strs(arr)
+    assert np.array_equal(ix.search_kmers(arr, k, h)[0].astype(np.int64), oix.counts(kmers).astype(np.int64))
+    assert np.array_equal(ix.search_kmers(arr, k, h, mode=1)[0], oix.presence(kmers))
+    assert np.array_equal(ix.lookup_kmers(arr, k, h), oix.lookup_packed(kmers))
+    # fused threshold
+    cnt = oix.counts(kmers)
+    for thr in (1, 100, 200, 400, 401):
+        cols, vals, n = ix.search_kmers_hits(arr, k, h, [thr])[0]
+        exp = np.nonzero(cnt >= thr)[0]
+        assert n == len(exp) and np.array_equal(cols, exp) and np.array_equal(vals, cnt[exp])
+    # capacity smaller than the number of hits: count is still exact
+    cols, vals, n = ix.search_kmers_hits(arr, k, h, [1], cap=5)[0]
+    assert n == int((cnt >= 1).sum()) and len(cols) == 5 and all(cnt[c] == v for c, v in zip(cols, vals))
+    # batch of two queries with different thresholds
+    res = ix.search_kmers_hits(arr, k, h, [150, 390], q_offsets=[0, 200, 400])
+    for (cols, vals, n), sl, thr in zip(res, (slice(0, 200), slice(200, 400)), (150, 390)):
+        c = oix.counts(kmers[sl])
+        exp = np.nonzero(c >= thr)[0]
+        assert np.array_equal(cols, exp) and np.array_equal(vals, c[exp])
+    ix.close()
+
+
+def test_set_column_and_download(B):
+    rng = np.random.default_rng(29)
+    m, N = 999, 13
+    ix, packed = _random_index(B, rng, m, N, density=0.5)
+    assert np.array_equal(ix.download_rows(0, m), packed)
+    bits = np.unpackbits(packed, axis=1)[:, :N].copy()
+    # overwrite column 4, then append three columns (one crosses a byte boundary: 13 -> 16)
+    for col in (4, 13, 14, 15):
+        bloom = rng.random(m) < 0.4
+        ix.set_column(col, np.packbits(bloom), m)
+        if col < bits.shape[1]:
+            bits[:, col] = bloom
+        else:
+            bits = np.concatenate([bits, bloom[:, None]], axis=1)
+    assert ix.num_cols == 16
+    assert np.array_equal(np.unpackbits(ix.download_rows(0, m), axis=1)[:, :16], bits.astype(np.uint8))
+    ix.close()
+
+
+# ---------------------------------------------------------------------------
+# synthetic index generator (K7) vs the oracle's pure function
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("col_offset,N", [(0, 1000), (50_000, 4096), (8, 77), (1_000_000 - 8, 50_000)])
+def test_fill_synthetic_matches_oracle(B, col_offset, N):
+    m = 700
+    planted = [col_offset + 3, col_offset + N - 1, col_offset + N // 2, col_offset + N + 5, 1]
+    thr = [0xFFFFFFFF, 1 << 31, 1 << 30, 0xFFFFFFFF, 0xFFFFFFFF]
+    for and_draws in (1, 2):
+        spec = O.SynthSpec(seed=42, and_draws=and_draws, planted_cols=planted, planted_thr=thr)
+        ix = B.DeviceIndex(m, N, col_offset=col_offset)
+        ix.fill_synthetic(42, and_draws, planted, thr)
+        got = ix.download_rows(0, m)
+        exp = spec.rows(np.arange(m), col_offset, N)
+        assert np.array_equal(got, exp)
+        ix.close()
+
+
+# ---------------------------------------------------------------------------
+# reference API: golden vectors from the unmodified reference
+# ---------------------------------------------------------------------------
+def _config(case, name):
+    return {"k": case["k"], "m": case["m"], "h": case["h"], "storage-engine": "b200",
+            "storage-config": {"filename": name, "device": 0}}
+
+
+def _check_queries(bigsi, queries):
+    for q in queries:
+        if "raises" in q:
+            with pytest.raises(BaseException) as ei:
+                bigsi.search(q["seq"], q["threshold"])
+            assert type(ei.value).__name__ == q["raises"]
+        else:
+            assert bigsi.search(q["seq"], q["threshold"]) == q["result"], (q["seq"][:40], q["threshold"])
+
+
+def test_reference_golden_search_cases(B):
+    g = load("search_cases.json")
+    for ci, case in enumerate(g["cases"]):
+        k, m, h = case["k"], case["m"], case["h"]
+        cfg = _config(case, "golden-%d" % ci)
+        blooms = []
+        for seq, ref_b64 in zip(case["sample_seqs"], case["blooms_b64"]):
+            b = B.BIGSI.bloom(cfg, B.seq_to_kmers(seq, k))
+            assert np.array_equal(np.frombuffer(b.tobytes(), dtype=np.uint8), bloom_from_b64(ref_b64))
+            blooms.append(b)
+        bigsi = B.BIGSI.build(cfg, blooms, case["samples"])
+        assert np.array_equal(bigsi.index.download_rows(0, m), rows_from_b64(case["rows_b64"], m, case["row_bytes"]))
+        _check_queries(bigsi, case["queries"])
+        got = bigsi.lookup(case["lookup_in"])
+        assert {km: v.to01() for km, v in got.items()} == case["lookup"]
+        if "insert" in case:
+            ins = case["insert"]
+            bigsi.insert(B.BIGSI.bloom(cfg, B.seq_to_kmers(ins["seq"], k)), ins["sample"])
+            assert bigsi.num_samples == ins["num_samples"]
+            assert np.array_equal(bigsi.index.download_rows(0, m), rows_from_b64(ins["rows_b64"], m, ins["row_bytes"]))
+            _check_queries(B.BIGSI(cfg), ins["queries"])
+        if "delete" in case:
+            d = case["delete"]
+            bigsi.delete_sample(d["sample"])
+            _check_queries(bigsi, d["queries"])
+        bigsi.delete()
+        with pytest.raises(BaseException):
+            B.BIGSI(cfg)
+
+
+def test_reference_end_to_end_kat(B):
+    # /root/reference/bigsi/tests/graph/test_end_to_end.py:12-131 restated against this engine
+    cfg = {"k": 3, "m": 1000, "h": 3, "storage-engine": "b200", "storage-config": {"filename": "kat"}}
+    kat = load("search_cases.json")["reference_kat"]
+
+    def mk(seqs, names):
+        return B.BIGSI.build(cfg, [B.BIGSI.bloom(cfg, B.seq_to_kmers(s, 3)) for s in seqs], names)
+
+    bigsi = mk(["ATACACAAT", "ACAGAGAAC"], ["a", "b"])
+    assert bigsi.search("ATACACAAT")[0] == {"percent_kmers_found": 100, "num_kmers": 6, "num_kmers_found": 6, "sample_name": "a"}
+    assert bigsi.search("ACAGAGAAC")[0] == {"percent_kmers_found": 100, "num_kmers": 6, "num_kmers_found": 6, "sample_name": "b"}
+    assert bigsi.search("ACAGTTAAC") == []
+    _check_queries(bigsi, kat["exact"])
+    assert bigsi.kmer_size == 3 and bigsi.bloomfilter_size == 1000 and bigsi.num_hashes == 3 and bigsi.num_samples == 2
+    with pytest.raises(ValueError):
+        bigsi.insert(B.BIGSI.bloom(cfg, ["ATC"]), "a")  # duplicate sample name
+    with pytest.raises(ValueError):
+        B.BIGSI.build(cfg, [B.BIGSI.bloom(cfg, ["ATC"])], ["x", "y"])
+    bigsi = mk(["ATACACAAT", "ATACACAAC"], ["a", "b"])
+    _check_queries(bigsi, kat["inexact"])
+    assert {k: v.to01() for k, v in bigsi.lookup("AAT").items()} == kat["inexact_lookup"]
+    # test_index.py:14-44 lookups incl. canonicalisation and duplicate k-mers
+    res = bigsi.lookup(["ATA", "ATA", "TAT"])
+    assert res["ATA"] == res["TAT"] and len(res) == 2 and len(res["ATA"]) == 2
+    assert len(bigsi.lookup("ATA", remove_trailing_zeros=False)["ATA"]) == 8
+    with pytest.raises(AssertionError):
+        bigsi.search("ATACACAAT", 1.5)
+    bigsi.delete()
+
+
+def test_config1_golden(B):
+    c = load("config1.json")
+    cfg = _config(c, "config1")
+    blooms = [B.BIGSI.bloom(cfg, km) for km in c["sample_kmers"]]
+    assert [b.count() for b in blooms] == c["bloom_popcounts"]
+    bigsi = B.BIGSI.build(cfg, blooms, c["samples"])
+    assert np.array_equal(bigsi.index.download_rows(0, c["m"]), rows_from_b64(c["rows_b64"], c["m"], c["row_bytes"]))
+    _check_queries(bigsi, c["queries"])
+    bigsi.delete()
+
+
+def test_random_api_parity_vs_oracle(B):
+    """Randomised BIGSI.search vs the oracle restatement, incl. non-ACGT bases and reverse
+    complements in one query, thresholds 0..1, N not a multiple of 8."""
+    rng = np.random.default_rng(101)
+    k, m, h, n = 11, 20_011, 3, 37
+    cfg = {"k": k, "m": m, "h": h, "storage-config": {"filename": "rand-api"}}
+    genomes = ["".join(rng.choice(list("ACGT"), size=600)) for _ in range(n)]
+    for i in range(1, n, 3):  # related samples: shared prefixes
+        genomes[i] = genomes[i - 1][:400] + genomes[i][400:]
+    names = ["s%d" % i for i in range(n)]
+    blooms = [B.BIGSI.bloom(cfg, B.seq_to_kmers(g, k)) for g in genomes]
+    bigsi = B.BIGSI.build(cfg, blooms, names)
+    oblooms = [O.OracleIndex.bloom(k, m, h, [O.canonical(x) for x in O.seq_to_kmers(g, k)]) for g in genomes]
+    oix = O.OracleIndex.build(k, m, h, oblooms, names)
+    assert np.array_equal(bigsi.index.download_rows(0, m), oix.rows)
+    queries = [genomes[0][:200], genomes[1][350:450], genomes[4][100:130] + "N" + genomes[4][131:180],
+               B.reverse_comp(genomes[7][:90]) + genomes[7][:90], genomes[9][:k], "ACGT" * 20]
+    for qseq in queries:
+        for thr in (1.0, 0.9, 0.5, 0.31, 0.0):
+            assert bigsi.search(qseq, thr) == oix.search(qseq, thr), (qseq[:20], thr)
+    bigsi.delete()
+
+
+# ---------------------------------------------------------------------------
+# BASELINE config 2 at full size: m = 25 M, N = 50 000 (156.8 GB in HBM)
+# ---------------------------------------------------------------------------
+def test_full_size_config2_parity(B):
+    import torch
+
+    free, total = torch.cuda.mem_get_info(0)
+    m, N, k, h = 25_000_000, 50_000, 31, 3
+    if free < m * 6272 + (4 << 30):
+        pytest.skip("needs %.0f GB of free HBM" % (m * 6272 / 1e9))
+    planted = [0, 1, 49_999, 25_000, 7, 12_345, 33_333]
+    thr = [0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, int(0.95 * 2 ** 32), int(0.6 * 2 ** 32), int(0.41 * 2 ** 32), int(0.3 * 2 ** 32)]
+    ix = B.DeviceIndex(m, N)
+    ix.fill_synthetic(0, 1, planted, thr)
+    spec = O.SynthSpec(0, 1, planted, thr)
+    oix = O.OracleIndex(k, m, h, N, synth=spec)
+    rng = np.random.default_rng(1)
+    arr = _rand_kmers(rng, 10_000, k)
+    kmers = _kmer_strs(arr)
+    # spot-check stored rows incl. the last one
+    probe = np.array([0, 1, 12_345_678, m - 1])
+    for r in probe:
+        assert np.array_equal(ix.download_rows(int(r), 1)[0], spec.rows([r], 0, N)[0])
+    exp = oix.counts(kmers)
+    got = ix.search_kmers(arr, k, h)[0]
+    assert np.array_equal(got.astype(np.int64), exp.astype(np.int64))
+    assert got[0] == 10_000 and got[1] == 10_000 and got[49_999] == 10_000
+    assert np.array_equal(ix.search_kmers(arr, k, h, mode=1)[0], oix.presence(kmers))
+    # exact query == threshold at U; 0.4 threshold keeps the graded planted columns
+    cols, vals, n = ix.search_kmers_hits(arr, k, h, [10_000])[0]
+    assert cols.tolist() == [0, 1, 49_999]
+    mk = math.ceil(10_000 * 0.4)
+    cols, vals, n = ix.search_kmers_hits(arr, k, h, [mk])[0]
+    e = np.nonzero(exp >= mk)[0]
+    assert np.array_equal(cols, e) and np.array_equal(vals, exp[e]) and 25_000 in cols.tolist()
+    # size-independent properties: counts are additive over a split of the query ...
+    a = ix.search_kmers(arr[:3777], k, h)[0].astype(np.int64)
+    b = ix.search_kmers(arr[3777:], k, h)[0].astype(np.int64)
+    assert np.array_equal(a + b, got.astype(np.int64))
+    # ... and batched == one by one
+    both = ix.search_kmers(arr, k, h, q_offsets=[0, 3777, 10_000])
+    assert np.array_equal(both[0], a) and np.array_equal(both[1], b)
+    ix.close()
