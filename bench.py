@@ -287,7 +287,7 @@ def run_b200(args):
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     launches = index.info()["kernel_launches"] - launches0
-    launches += args.steps * (2 if rank == 0 else 1)  # hash (rank 0) + threshold kernels are handle-less
+    launches += args.steps * (1 if rank == 0 else 0)  # the hash kernel (rank 0) is handle-less
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

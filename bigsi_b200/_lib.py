@@ -61,6 +61,7 @@ SIGNATURES = {
     "bigsi_b200_index_set_option": (_int, [_vp, ctypes.c_char_p, _i64]),
     "bigsi_b200_index_timing_collect": (_int, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                                ctypes.POINTER(_u64)]),
+    "bigsi_b200_index_debug_read": (_int, [_vp, _vp, _u64]),
     "bigsi_b200_index_upload_rows": (_int, [_vp, _u64, _u64, _vp, _u64, _u64]),
     "bigsi_b200_index_download_rows": (_int, [_vp, _u64, _u64, _vp, _u64]),
     "bigsi_b200_index_set_column": (_int, [_vp, _u64, _vp, _u64]),
@@ -68,6 +69,7 @@ SIGNATURES = {
     "bigsi_b200_hash_kmers": (_int, [_int, _vp, _u64, _int, _int, _u64, _int, _vp]),
     "bigsi_b200_hash_kmers_dev": (_int, [_vp, _u64, _int, _int, _u64, _int, _vp, _vp]),
     "bigsi_b200_query_dev": (_int, [_vp, _int, _vp, _vp, _u64, _u64, _u64, _int, _vp, _u64, _vp]),
+    "bigsi_b200_query_hits_dev": (_int, [_vp, _vp, _vp, _u64, _u64, _u64, _int, _vp, _vp, _vp, _u64, _vp, _vp, _u64, _vp]),
     "bigsi_b200_lookup_dev": (_int, [_vp, _vp, _u64, _int, _vp, _u64, _vp]),
     "bigsi_b200_threshold_dev": (_int, [_vp, _u64, _u64, _u64, _vp, _vp, _vp, _u64, _vp, _vp]),
     "bigsi_b200_search_kmers": (_int, [_vp, _int, _vp, _vp, _u64, _int, _int, _vp, _u64]),

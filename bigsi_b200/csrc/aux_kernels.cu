@@ -1,5 +1,6 @@
 // Helper kernels around the fused query kernel: k-mer hashing, per-k-mer lookup vectors,
 // threshold/compaction, column insert and the synthetic index generator.
+#include "launch.cuh"
 #include "ptx.cuh"
 #include "query.cuh"
 
@@ -17,58 +18,138 @@ __device__ __forceinline__ uint32_t comp_base(uint32_t b)
 }
 __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
 
-__global__ void __launch_bounds__(128) hash_kmers_kernel(const uint8_t *__restrict__ kmers, uint64_t n, int k, int h,
-                                                         uint64_t m, int canonical, int32_t *__restrict__ rows_out)
+// Block-cooperative hashing.  (1) the block's k-mer bytes are staged in shared memory with 16-byte
+// loads; (2) one thread per k-mer decides the orientation; (3) one thread per (k-mer, 4-byte block)
+// writes the canonical bytes as little-endian words (zero padded, so the last word IS murmur's
+// tail); (4) one thread per (k-mer, seed) runs MurmurHash3_x86_32 over those words.
+constexpr int kHashThreads = 128;
+constexpr int kHashSmemBytes = 40 * 1024;
+
+__device__ __forceinline__ int32_t murmur_finish_mod(uint32_t h1, uint32_t len, uint32_t m)
 {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint8_t *s = kmers + i * (uint64_t)k;
-    // orientation: forward unless the reverse complement is lexicographically smaller
-    bool fwd = true;
-    if (canonical) {
-        for (int j = 0; j < k; ++j) {
-            const uint32_t a = s[j], b = comp_base(s[k - 1 - j]);
-            if (a != b) {
-                fwd = a < b;
-                break;
+    h1 ^= len;
+    h1 ^= h1 >> 16;
+    h1 *= 0x85ebca6bu;
+    h1 ^= h1 >> 13;
+    h1 *= 0xc2b2ae35u;
+    h1 ^= h1 >> 16;
+    // Python floor-mod of the SIGNED 32-bit hash (bloom/bloomfilter.py:5-6), in 32-bit arithmetic
+    if ((int32_t)h1 >= 0) return (int32_t)(h1 % m);
+    const uint32_t r = (0u - h1) % m;  // |s| mod m
+    return (int32_t)(r ? m - r : 0u);
+}
+__device__ __forceinline__ uint32_t murmur_block(uint32_t h1, uint32_t k1)
+{
+    k1 *= 0xcc9e2d51u;
+    k1 = rotl32(k1, 15);
+    k1 *= 0x1b873593u;
+    h1 ^= k1;
+    h1 = rotl32(h1, 13);
+    return h1 * 5u + 0xe6546b64u;
+}
+__device__ __forceinline__ uint32_t murmur_tail(uint32_t h1, uint32_t k1)
+{
+    k1 *= 0xcc9e2d51u;
+    k1 = rotl32(k1, 15);
+    k1 *= 0x1b873593u;
+    return h1 ^ k1;
+}
+
+__global__ void __launch_bounds__(kHashThreads) hash_kmers_kernel(const uint8_t *__restrict__ kmers, uint64_t n, int k,
+                                                                 int h, uint32_t m, int canonical, uint32_t kpb,
+                                                                 int use_smem, int32_t *__restrict__ rows_out)
+{
+    extern __shared__ __align__(16) uint8_t sk[];
+    grid_dependency_wait();  // the previous query's fused kernel may still be reading rows_out
+    grid_launch_dependents();
+    const uint64_t base = (uint64_t)blockIdx.x * kpb;
+    const uint32_t cnt = (uint32_t)min((uint64_t)kpb, n - base);
+    const uint8_t *g0 = kmers + base * (uint64_t)k;
+    const int nblocks = k >> 2, rem = k & 3;
+    if (use_smem) {
+        // smem layout: [raw bytes: kpb*k + 32][orientation: kpb, padded to 16][words: kpb * wstride]
+        const uint32_t wpk = (uint32_t)(k + 3) >> 2;
+        const uint32_t wstride = wpk | 1;  // odd stride: conflict-free LDS across k-mers
+        const uint32_t raw_bytes = ((kpb * (uint32_t)k + 32) + 15) & ~15u;
+        uint8_t *fwd = sk + raw_bytes;
+        uint32_t *cw = reinterpret_cast<uint32_t *>(sk + raw_bytes + ((kpb + 15) & ~15u));
+        // (1) one round trip of 16-byte loads over the enclosing aligned window; the window leaves
+        // the k-mer array only inside its first / last 16-byte line, which every CUDA allocation
+        // (>= 256-byte granular) covers
+        const uint32_t nbytes = cnt * (uint32_t)k;
+        const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15);
+        const uint4 *a0 = reinterpret_cast<const uint4 *>(g0 - skew);
+        const uint32_t nvec = (skew + nbytes + 15) >> 4;
+        uint4 *sv = reinterpret_cast<uint4 *>(sk);
+        for (uint32_t i = threadIdx.x; i < nvec; i += kHashThreads) sv[i] = __ldg(a0 + i);
+        __syncthreads();
+        const uint8_t *src = sk + skew;
+        // (2) orientation: forward unless the reverse complement is lexicographically smaller
+        for (uint32_t km = threadIdx.x; km < cnt; km += kHashThreads) {
+            const uint8_t *s = src + (size_t)km * k;
+            bool f = true;
+            if (canonical) {
+                for (int j = 0; j < k; ++j) {
+                    const uint32_t a = s[j], b = comp_base(s[k - 1 - j]);
+                    if (a != b) {
+                        f = a < b;
+                        break;
+                    }
+                }
+            }
+            fwd[km] = f ? 1 : 0;
+        }
+        __syncthreads();
+        // (3) canonical bytes as little-endian words
+        for (uint32_t i = threadIdx.x; i < cnt * wpk; i += kHashThreads) {
+            const uint32_t km = i / wpk, wi = i % wpk;
+            const uint8_t *s = src + (size_t)km * k;
+            const bool f = fwd[km] != 0;
+            uint32_t word = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = (int)wi * 4 + u;
+                if (j < k) word |= (f ? (uint32_t)s[j] : comp_base(s[k - 1 - j])) << (8 * u);
+            }
+            cw[km * wstride + wi] = word;
+        }
+        __syncthreads();
+        // (4) hash
+        for (uint32_t w = threadIdx.x; w < cnt * (uint32_t)h; w += kHashThreads) {
+            const uint32_t km = w / (uint32_t)h, seed = w % (uint32_t)h;
+            const uint32_t *wp = cw + km * wstride;
+            uint32_t h1 = seed;
+            for (int b = 0; b < nblocks; ++b) h1 = murmur_block(h1, wp[b]);
+            if (rem) h1 = murmur_tail(h1, wp[nblocks]);
+            rows_out[(base + km) * (uint64_t)h + seed] = murmur_finish_mod(h1, (uint32_t)k, m);
+        }
+        return;
+    }
+    // very long "k-mers" (k > the staging buffer): one thread per (k-mer, seed) straight from global
+    for (uint32_t w = threadIdx.x; w < cnt * (uint32_t)h; w += kHashThreads) {
+        const uint32_t km = w / (uint32_t)h, seed = w % (uint32_t)h;
+        const uint8_t *s = g0 + (size_t)km * k;
+        bool fwd = true;
+        if (canonical) {
+            for (int j = 0; j < k; ++j) {
+                const uint32_t a = s[j], b = comp_base(s[k - 1 - j]);
+                if (a != b) {
+                    fwd = a < b;
+                    break;
+                }
             }
         }
-    }
-    auto byte_at = [&](int j) -> uint32_t { return fwd ? (uint32_t)s[j] : comp_base(s[k - 1 - j]); };
-    const int nblocks = k >> 2;
-    for (int seed = 0; seed < h; ++seed) {
-        uint32_t h1 = (uint32_t)seed;
-        for (int b = 0; b < nblocks; ++b) {
-            uint32_t k1 = byte_at(4 * b) | (byte_at(4 * b + 1) << 8) | (byte_at(4 * b + 2) << 16) |
-                          (byte_at(4 * b + 3) << 24);
-            k1 *= 0xcc9e2d51u;
-            k1 = rotl32(k1, 15);
-            k1 *= 0x1b873593u;
-            h1 ^= k1;
-            h1 = rotl32(h1, 13);
-            h1 = h1 * 5u + 0xe6546b64u;
+        auto byte_at = [&](int j) -> uint32_t { return fwd ? (uint32_t)s[j] : comp_base(s[k - 1 - j]); };
+        uint32_t h1 = seed;
+        for (int b = 0; b < nblocks; ++b)
+            h1 = murmur_block(h1, byte_at(4 * b) | (byte_at(4 * b + 1) << 8) | (byte_at(4 * b + 2) << 16) |
+                                      (byte_at(4 * b + 3) << 24));
+        if (rem) {
+            uint32_t k1 = 0;
+            for (int u = 0; u < rem; ++u) k1 |= byte_at(4 * nblocks + u) << (8 * u);
+            h1 = murmur_tail(h1, k1);
         }
-        uint32_t k1 = 0;
-        const int t = 4 * nblocks;
-        switch (k & 3) {
-        case 3: k1 ^= byte_at(t + 2) << 16;  // fallthrough
-        case 2: k1 ^= byte_at(t + 1) << 8;   // fallthrough
-        case 1:
-            k1 ^= byte_at(t);
-            k1 *= 0xcc9e2d51u;
-            k1 = rotl32(k1, 15);
-            k1 *= 0x1b873593u;
-            h1 ^= k1;
-        }
-        h1 ^= (uint32_t)k;
-        h1 ^= h1 >> 16;
-        h1 *= 0x85ebca6bu;
-        h1 ^= h1 >> 13;
-        h1 *= 0xc2b2ae35u;
-        h1 ^= h1 >> 16;
-        long long r = (long long)(int32_t)h1 % (long long)m;  // Python floor-mod of the SIGNED hash
-        if (r < 0) r += (long long)m;
-        rows_out[i * (uint64_t)h + seed] = (int32_t)r;
+        rows_out[(base + km) * (uint64_t)h + seed] = murmur_finish_mod(h1, (uint32_t)k, m);
     }
 }
 
@@ -76,10 +157,22 @@ cudaError_t launch_hash_kmers(const char *d_kmers, uint64_t n, int k, int h, uin
                               int32_t *d_rows_out, cudaStream_t stream)
 {
     if (n == 0) return cudaSuccess;
-    const uint64_t blocks = (n + 127) / 128;
-    hash_kmers_kernel<<<(unsigned)blocks, 128, 0, stream>>>(reinterpret_cast<const uint8_t *>(d_kmers), n, k, h, m,
-                                                            canonical, d_rows_out);
-    return cudaGetLastError();
+    // k-mers per block: about two (k-mer, seed) items per thread, bounded by the staging buffer
+    uint32_t kpb = (uint32_t)((2 * kHashThreads + h - 1) / h);
+    const uint64_t per_kmer = (uint64_t)k + 1 + 4ull * ((((uint64_t)k + 3) >> 2) | 1);  // raw + flag + words
+    int use_smem = 1;
+    if (per_kmer + 96 > (uint64_t)kHashSmemBytes) {
+        use_smem = 0;
+    } else if ((uint64_t)kpb * per_kmer + 96 > (uint64_t)kHashSmemBytes) {
+        kpb = (uint32_t)(((uint64_t)kHashSmemBytes - 96) / per_kmer);
+    }
+    if (kpb < 1) kpb = 1;
+    const uint64_t blocks = (n + kpb - 1) / kpb;
+    if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    const size_t smem = use_smem ? (size_t)kpb * per_kmer + 96 : 0;
+    return launch_pdl(hash_kmers_kernel, dim3((unsigned)blocks), dim3(kHashThreads), smem, stream,
+                      reinterpret_cast<const uint8_t *>(d_kmers), n, k, h, (uint32_t)m, canonical, kpb, use_smem,
+                      d_rows_out);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -83,6 +83,27 @@ struct DevBuf {
     }
 };
 
+struct PinnedBuf {
+    void *p = nullptr;
+    uint64_t cap = 0;
+    cudaError_t reserve(uint64_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaHostAlloc(&p, round_up(bytes, 4096), cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = round_up(bytes, 4096);
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
 struct DeviceGuard {
     int prev = -1;
     cudaError_t err;
@@ -112,8 +133,11 @@ struct bigsi_b200_index {
     // options
     int64_t opt_tile_bytes = 0, opt_grid = 0, opt_kmers_per_stage = 0, opt_n_stages = 0, opt_ctas_per_sm = 0;
     bool timing = false;
+    int64_t opt_debug_flags = 0;
     // scratch
-    DevBuf partial, d_kmers, d_rows, d_qoff, d_out, d_min, d_hit_cols, d_hit_counts, d_nhits, d_bloom, d_planted;
+    DevBuf debug_ts;
+    DevBuf partial, d_kmers, d_rows, d_qoff, d_out, d_min, d_nhits, d_bloom, d_planted;
+    PinnedBuf h_small;
     // timing
     std::vector<TimedLaunch> timed_free, timed_used;
     // statistics
@@ -212,23 +236,38 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
     const uint64_t longest = max_query_kmers ? (max_query_kmers < total_kmers ? max_query_kmers : total_kmers) : total_kmers;
     if (mode == BIGSI_B200_MODE_COUNTS && longest > 0xffffffffull)
         return fail(BIGSI_B200_ERR_INVALID, "a query longer than 2^32-1 k-mers does not fit uint32 counts");
+    p.max_query_kmers = longest;
+    if (longest / p.items_per_slice + 2 > 65535)
+        return fail(BIGSI_B200_ERR_INVALID, "a query spans more than 65 535 slices; split the batch");
     p.total_planes = mode == BIGSI_B200_MODE_COUNTS ? (bits_of(longest) ? bits_of(longest) : 1) : 1;
     const uint64_t seg_max = longest < p.items_per_slice ? longest : p.items_per_slice;
     p.planes_per_slot = mode == BIGSI_B200_MODE_COUNTS ? (bits_of(seg_max) ? bits_of(seg_max) : 1) : 1;
     return 0;
 }
 
+struct HitsOut {
+    const uint32_t *min_kmers = nullptr;
+    int32_t *cols = nullptr;
+    uint32_t *counts = nullptr;
+    unsigned long long *n = nullptr;
+    uint64_t cap = 0;
+};
+
 int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const int64_t *d_qoff, uint64_t n_queries,
               uint64_t total_kmers, uint64_t max_query_kmers, int h, void *d_out, uint64_t out_stride,
-              cudaStream_t stream)
+              cudaStream_t stream, const HitsOut *hits = nullptr)
 {
     if (mode != BIGSI_B200_MODE_COUNTS && mode != BIGSI_B200_MODE_AND)
         return fail(BIGSI_B200_ERR_INVALID, "unknown query mode %d", mode);
     if (n_queries == 0) return 0;
     const uint64_t row_bytes = (ix->num_cols + 7) / 8;
-    if (mode == BIGSI_B200_MODE_COUNTS ? out_stride < ix->num_cols : out_stride < row_bytes)
+    if (d_out && (mode == BIGSI_B200_MODE_COUNTS ? out_stride < ix->num_cols : out_stride < row_bytes))
         return fail(BIGSI_B200_ERR_INVALID, "out_stride %llu too small", (unsigned long long)out_stride);
-    if (ix->num_cols == 0) return 0;
+    if (!d_out && !(hits && mode == BIGSI_B200_MODE_COUNTS)) return fail(BIGSI_B200_ERR_INVALID, "null output");
+    if (ix->num_cols == 0) {
+        if (hits) CK(cudaMemsetAsync(hits->n, 0, n_queries * sizeof(unsigned long long), stream));
+        return 0;
+    }
     if (int rc = ensure_kernels()) return rc;
     QueryParams p;
     int grid = 0;
@@ -237,6 +276,21 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const int64
     p.qoff = d_qoff;
     p.out = d_out;
     p.out_stride = out_stride;
+    p.debug_flags = (uint32_t)ix->opt_debug_flags;
+    if (p.debug_flags & 2u) {  // timeline stamps of the LAST launch, fetched with bigsi_b200_index_debug_read
+        cudaError_t de = ix->debug_ts.reserve((uint64_t)(grid > 0 ? grid : 1) * 64);
+        if (de != cudaSuccess) return fail_cuda(de, "debug buffer");
+        p.debug_ts = static_cast<unsigned long long *>(ix->debug_ts.p);
+    }
+    if (hits) {
+        p.min_kmers = hits->min_kmers;
+        p.hit_cols = hits->cols;
+        p.hit_counts = hits->counts;
+        p.n_hits = hits->n;
+        p.hit_cap = hits->cap;
+        // stage 1 zeroes the hit counters; without a stage-1 launch do it here
+        if (grid == 0) CK(cudaMemsetAsync(hits->n, 0, n_queries * sizeof(unsigned long long), stream));
+    }
     const uint64_t need = query_partial_bytes(p);
     if (need > ix->partial.cap) {
         CK(cudaStreamSynchronize(stream));
@@ -260,6 +314,11 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const int64
     if (grid > 0) {
         CK(launch_query(p, mode, grid, stream));
         ix->kernel_launches++;
+    }
+    if (p.debug_flags & 4u) {  // experiment: time a SECOND (warm) merge instead of the first
+        QueryParams p2 = p;
+        p2.min_kmers = nullptr;
+        CK(launch_merge(p2, mode, stream));
     }
     if (ix->timing) CK(cudaEventRecord(tl.e1, stream));
     CK(launch_merge(p, mode, stream));
@@ -408,9 +467,10 @@ int bigsi_b200_index_destroy(bigsi_b200_index *ix)
     cudaDeviceSynchronize();
     for (auto &t : ix->timed_free) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
     for (auto &t : ix->timed_used) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
-    DevBuf *bufs[] = {&ix->partial, &ix->d_kmers, &ix->d_rows, &ix->d_qoff, &ix->d_out, &ix->d_min,
-                      &ix->d_hit_cols, &ix->d_hit_counts, &ix->d_nhits, &ix->d_bloom, &ix->d_planted};
+    DevBuf *bufs[] = {&ix->debug_ts, &ix->partial, &ix->d_kmers, &ix->d_rows, &ix->d_qoff, &ix->d_out, &ix->d_min,
+                      &ix->d_nhits, &ix->d_bloom, &ix->d_planted};
     for (DevBuf *b : bufs) b->release();
+    ix->h_small.release();
     if (ix->matrix) cudaFree(ix->matrix);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
@@ -447,7 +507,20 @@ int bigsi_b200_index_set_option(bigsi_b200_index *ix, const char *key, int64_t v
     else if (!strcmp(key, "n_stages")) ix->opt_n_stages = value;
     else if (!strcmp(key, "ctas_per_sm")) ix->opt_ctas_per_sm = value;
     else if (!strcmp(key, "timing")) ix->timing = value != 0;
+    else if (!strcmp(key, "debug_flags")) ix->opt_debug_flags = value;
     else return fail(BIGSI_B200_ERR_INVALID, "unknown option '%s'", key);
+    return 0;
+}
+
+int bigsi_b200_index_debug_read(bigsi_b200_index *ix, uint64_t *out, uint64_t n_words)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (!out) return fail(BIGSI_B200_ERR_INVALID, "null out");
+    if (n_words * 8 > ix->debug_ts.cap) return fail(BIGSI_B200_ERR_RANGE, "debug buffer holds %llu bytes",
+                                                     (unsigned long long)ix->debug_ts.cap);
+    DeviceGuard guard(ix->device);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, ix->debug_ts.p, n_words * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -580,7 +653,6 @@ int bigsi_b200_hash_kmers_dev(const char *d_kmers, uint64_t n, int k, int h, uin
     if (m == 0 || m > 0x7fffffffull) return fail(BIGSI_B200_ERR_INVALID, "m must be in [1, 2^31-1]");
     if (n == 0) return 0;
     if (!d_kmers || !d_rows_out) return fail(BIGSI_B200_ERR_INVALID, "null device pointer");
-    if ((n + 127) / 128 > 0x7fffffffull) return fail(BIGSI_B200_ERR_INVALID, "too many k-mers");
     CK(launch_hash_kmers(d_kmers, n, k, h, m, canonical, d_rows_out, static_cast<cudaStream_t>(stream)));
     return 0;
 }
@@ -634,6 +706,27 @@ int bigsi_b200_query_dev(bigsi_b200_index *ix, int mode, const int32_t *d_rows, 
                      static_cast<cudaStream_t>(stream));
 }
 
+int bigsi_b200_query_hits_dev(bigsi_b200_index *ix, const int32_t *d_rows, const int64_t *d_q_offsets,
+                              uint64_t n_queries, uint64_t total_kmers, uint64_t max_query_kmers, int h,
+                              const uint32_t *d_min_kmers, int32_t *d_cols_out, uint32_t *d_counts_out, uint64_t cap,
+                              uint64_t *d_n_out, uint32_t *d_counts_full, uint64_t counts_stride, void *stream)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (n_queries == 0) return 0;
+    if (!d_q_offsets || !d_min_kmers || !d_n_out || (cap && (!d_cols_out || !d_counts_out)))
+        return fail(BIGSI_B200_ERR_INVALID, "null device pointer");
+    if (total_kmers && !d_rows) return fail(BIGSI_B200_ERR_INVALID, "null d_rows");
+    DeviceGuard guard(ix->device);
+    HitsOut ho;
+    ho.min_kmers = d_min_kmers;
+    ho.cols = d_cols_out;
+    ho.counts = d_counts_out;
+    ho.n = reinterpret_cast<unsigned long long *>(d_n_out);
+    ho.cap = cap;
+    return run_query(ix, BIGSI_B200_MODE_COUNTS, d_rows, d_q_offsets, n_queries, total_kmers, max_query_kmers, h,
+                     d_counts_full, counts_stride, static_cast<cudaStream_t>(stream), &ho);
+}
+
 int bigsi_b200_lookup_dev(bigsi_b200_index *ix, const int32_t *d_rows, uint64_t n_kmers, int h, uint8_t *d_out,
                           uint64_t out_stride, void *stream)
 {
@@ -673,7 +766,7 @@ int bigsi_b200_threshold_dev(const uint32_t *d_counts, uint64_t counts_stride, u
 // ============================================================================================
 static int search_common(bigsi_b200_index *ix, int mode, const char *kmers, const int32_t *rows, const int64_t *qoff,
                          uint64_t n_queries, int k, int h, uint64_t *total_out, uint64_t *longest_out,
-                         uint64_t out_stride)
+                         uint64_t out_stride, const HitsOut *hits = nullptr)
 {
     // stages inputs, hashes if needed and runs the query into ix->d_out (device); no D2H here
     uint64_t total = 0, longest = 0;
@@ -685,8 +778,8 @@ static int search_common(bigsi_b200_index *ix, int mode, const char *kmers, cons
     cudaError_t e;
     if ((e = ix->d_qoff.reserve((n_queries + 1) * 8)) != cudaSuccess) return fail_cuda(e, "staging");
     if ((e = ix->d_rows.reserve(total * (uint64_t)h * 4 + 4)) != cudaSuccess) return fail_cuda(e, "staging");
-    const uint64_t out_bytes = n_queries * out_stride * (mode == BIGSI_B200_MODE_COUNTS ? 4 : 1);
-    if ((e = ix->d_out.reserve(out_bytes + 16)) != cudaSuccess) return fail_cuda(e, "staging");
+    const uint64_t out_bytes = hits ? 0 : n_queries * out_stride * (mode == BIGSI_B200_MODE_COUNTS ? 4 : 1);
+    if (!hits && (e = ix->d_out.reserve(out_bytes + 16)) != cudaSuccess) return fail_cuda(e, "staging");
     CK(cudaMemcpyAsync(ix->d_qoff.p, qoff, (n_queries + 1) * 8, cudaMemcpyHostToDevice, ix->stream));
     if (total) {
         if (kmers) {
@@ -705,7 +798,7 @@ static int search_common(bigsi_b200_index *ix, int mode, const char *kmers, cons
         }
     }
     return run_query(ix, mode, static_cast<const int32_t *>(ix->d_rows.p), static_cast<const int64_t *>(ix->d_qoff.p),
-                     n_queries, total, longest, h, ix->d_out.p, out_stride, ix->stream);
+                     n_queries, total, longest, h, hits ? nullptr : ix->d_out.p, out_stride, ix->stream, hits);
 }
 
 static int search_full(bigsi_b200_index *ix, int mode, const char *kmers, const int32_t *rows, const int64_t *qoff,
@@ -747,50 +840,60 @@ int bigsi_b200_search_kmers_hits(bigsi_b200_index *ix, const char *kmers, const 
     if (n_queries == 0) return 0;
     if (!min_kmers || !n_out || (cap && (!cols_out || !counts_out))) return fail(BIGSI_B200_ERR_INVALID, "null pointer");
     DeviceGuard guard(ix->device);
-    uint64_t total = 0, longest = 0;
-    const uint64_t stride = round_up(ix->num_cols ? ix->num_cols : 1, 4);
-    if (int rc = search_common(ix, BIGSI_B200_MODE_COUNTS, kmers, nullptr, q_offsets, n_queries, k, h, &total, &longest,
-                               stride))
-        return rc;
     cudaError_t e;
+    // one device block [n_hits: Q x u64][cols: Q x cap][counts: Q x cap] so that small results come
+    // back in ONE device-to-host copy
+    const uint64_t n_bytes = n_queries * 8, list_bytes = n_queries * cap * 4;
     if ((e = ix->d_min.reserve(n_queries * 4)) != cudaSuccess) return fail_cuda(e, "staging");
-    if ((e = ix->d_nhits.reserve(n_queries * 8)) != cudaSuccess) return fail_cuda(e, "staging");
-    if ((e = ix->d_hit_cols.reserve(n_queries * cap * 4 + 4)) != cudaSuccess) return fail_cuda(e, "staging");
-    if ((e = ix->d_hit_counts.reserve(n_queries * cap * 4 + 4)) != cudaSuccess) return fail_cuda(e, "staging");
+    if ((e = ix->d_nhits.reserve(n_bytes + 2 * list_bytes + 16)) != cudaSuccess) return fail_cuda(e, "staging");
+    uint8_t *blk = static_cast<uint8_t *>(ix->d_nhits.p);
+    HitsOut ho;
+    ho.min_kmers = static_cast<const uint32_t *>(ix->d_min.p);
+    ho.n = reinterpret_cast<unsigned long long *>(blk);
+    ho.cols = reinterpret_cast<int32_t *>(blk + n_bytes);
+    ho.counts = reinterpret_cast<uint32_t *>(blk + n_bytes + list_bytes);
+    ho.cap = cap;
     CK(cudaMemcpyAsync(ix->d_min.p, min_kmers, n_queries * 4, cudaMemcpyHostToDevice, ix->stream));
-    if (ix->num_cols == 0) {
-        CK(cudaStreamSynchronize(ix->stream));
-        for (uint64_t q = 0; q < n_queries; ++q) n_out[q] = 0;
-        return 0;
-    }
-    if (int rc = bigsi_b200_threshold_dev(static_cast<const uint32_t *>(ix->d_out.p), stride, n_queries, ix->num_cols,
-                                          static_cast<const uint32_t *>(ix->d_min.p),
-                                          static_cast<int32_t *>(ix->d_hit_cols.p),
-                                          static_cast<uint32_t *>(ix->d_hit_counts.p), cap,
-                                          static_cast<uint64_t *>(ix->d_nhits.p), ix->stream))
+    uint64_t total = 0, longest = 0;
+    if (int rc = search_common(ix, BIGSI_B200_MODE_COUNTS, kmers, nullptr, q_offsets, n_queries, k, h, &total, &longest, 0,
+                               &ho))
         return rc;
-    ix->kernel_launches++;
-    CK(cudaMemcpyAsync(n_out, ix->d_nhits.p, n_queries * 8, cudaMemcpyDeviceToHost, ix->stream));
-    CK(cudaStreamSynchronize(ix->stream));
-    // second leg: only the hit lists that are populated
+    // Single query (the BIGSI.search case): speculatively fetch the count and the first hits in one copy.
+    const uint64_t spec = cap < 64 ? cap : 64;
     if (n_queries == 1) {
+        if ((e = ix->h_small.reserve(8 + 2 * spec * 4)) != cudaSuccess) return fail_cuda(e, "pinned staging");
+        uint8_t *hs = static_cast<uint8_t *>(ix->h_small.p);
+        CK(cudaMemcpyAsync(hs, blk, 8, cudaMemcpyDeviceToHost, ix->stream));
+        if (spec) {
+            CK(cudaMemcpyAsync(hs + 8, ho.cols, spec * 4, cudaMemcpyDeviceToHost, ix->stream));
+            CK(cudaMemcpyAsync(hs + 8 + spec * 4, ho.counts, spec * 4, cudaMemcpyDeviceToHost, ix->stream));
+        }
+        CK(cudaStreamSynchronize(ix->stream));
+        memcpy(n_out, hs, 8);
         const uint64_t n = n_out[0] < cap ? n_out[0] : cap;
-        if (n) {
-            CK(cudaMemcpyAsync(cols_out, ix->d_hit_cols.p, n * 4, cudaMemcpyDeviceToHost, ix->stream));
-            CK(cudaMemcpyAsync(counts_out, ix->d_hit_counts.p, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+        if (n <= spec) {
+            memcpy(cols_out, hs + 8, n * 4);
+            memcpy(counts_out, hs + 8 + spec * 4, n * 4);
+        } else {
+            CK(cudaMemcpyAsync(cols_out, ho.cols, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+            CK(cudaMemcpyAsync(counts_out, ho.counts, n * 4, cudaMemcpyDeviceToHost, ix->stream));
             CK(cudaStreamSynchronize(ix->stream));
         }
-    } else if (cap) {
+        return 0;
+    }
+    CK(cudaMemcpyAsync(n_out, blk, n_bytes, cudaMemcpyDeviceToHost, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    if (cap) {
         uint64_t max_n = 0;
         for (uint64_t q = 0; q < n_queries; ++q) {
             const uint64_t n = n_out[q] < cap ? n_out[q] : cap;
             if (n > max_n) max_n = n;
         }
         if (max_n) {
-            CK(cudaMemcpy2DAsync(cols_out, cap * 4, ix->d_hit_cols.p, cap * 4, max_n * 4, n_queries,
-                                 cudaMemcpyDeviceToHost, ix->stream));
-            CK(cudaMemcpy2DAsync(counts_out, cap * 4, ix->d_hit_counts.p, cap * 4, max_n * 4, n_queries,
-                                 cudaMemcpyDeviceToHost, ix->stream));
+            CK(cudaMemcpy2DAsync(cols_out, cap * 4, ho.cols, cap * 4, max_n * 4, n_queries, cudaMemcpyDeviceToHost,
+                                 ix->stream));
+            CK(cudaMemcpy2DAsync(counts_out, cap * 4, ho.counts, cap * 4, max_n * 4, n_queries, cudaMemcpyDeviceToHost,
+                                 ix->stream));
             CK(cudaStreamSynchronize(ix->stream));
         }
     }

@@ -45,8 +45,18 @@ struct QueryParams {
     uint8_t *partial;         // [n_slots][planes_per_slot][tile_bytes]
     uint32_t planes_per_slot; // COUNTS: bits(min(items_per_slice, longest query)); AND: 1
     uint32_t total_planes;    // bits(longest query) <= 32 (merge accumulator width)
-    void *out;                // COUNTS: uint32 [n_queries][out_stride]; AND: uint8 [n_queries][out_stride]
+    uint64_t max_query_kmers; // upper bound on the longest query (sizes the merge's slot loop)
+    void *out;                // COUNTS: uint32 [n_queries][out_stride]; AND: uint8 [n_queries][out_stride]; may be
+                              // null in COUNTS mode when only the thresholded hits are wanted
     uint64_t out_stride;      // elements (COUNTS) or bytes (AND)
+    // optional fused threshold (COUNTS mode): keep columns with count >= min_kmers[q]
+    const uint32_t *min_kmers;       // [n_queries] or null
+    int32_t *hit_cols;               // [n_queries][hit_cap] LOCAL column ids, order unspecified
+    uint32_t *hit_counts;            // [n_queries][hit_cap]
+    unsigned long long *n_hits;      // [n_queries] number of hits (may exceed hit_cap); zeroed by stage 1
+    uint64_t hit_cap;
+    uint32_t debug_flags;     // bit 0: consumers skip the AND/count work (pure-gather ceiling measurement)
+    unsigned long long *debug_ts;  // optional [grid][8] timeline stamps (globaltimer ns), see fused_query
 };
 
 inline uint32_t query_consumer_warps(const QueryParams &p) { return (p.tile_bytes + 511) / 512; }
@@ -61,7 +71,8 @@ inline uint64_t query_n_slots(const QueryParams &p)
 }
 inline uint64_t query_partial_bytes(const QueryParams &p)
 {
-    return query_n_slots(p) * p.planes_per_slot * p.tile_bytes;
+    // + one slot of slack: the merge reads whole 16-plane groups
+    return (query_n_slots(p) * p.planes_per_slot + kSegPlanes) * p.tile_bytes;
 }
 
 // Stage 1: gather + AND + vertical count, per-segment bit planes -> p.partial.

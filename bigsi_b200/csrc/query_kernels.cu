@@ -19,13 +19,26 @@
 // carry-save counter (Harley-Seal: ones/twos/fours + ripple planes => up to 16-bit vertical
 // counters), so the kernel stays HBM-bound instead of ALU-bound.
 //
-// Stage 2 (merge): per (query, tile, column chunk) adds the bit-sliced partial counters of all
-// segments with ripple-carry full adders (2 LOP3 per plane), tree-reduces across thread groups in
-// shared memory and expands the planes to uint32 counts once (or ANDs the presence planes).
+// Stage 2 (merge_kernels.cu): per (query, tile, column chunk) counts the partial planes of all
+// segments vertically once more and expands them to uint32 counts (or ANDs the presence planes).
+#include "launch.cuh"
 #include "ptx.cuh"
 #include "query.cuh"
 
 namespace bigsi {
+
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// timeline slots per CTA: 0 entry, 1 producer first issue, 2 first slot landed, 3 last slot consumed,
+// 4 after flush, 5 producer last issue
+#define BIGSI_TS(slot)                                                            \
+    do {                                                                          \
+        if (P.debug_ts) P.debug_ts[(size_t)blockIdx.x * 8 + (slot)] = gtime();    \
+    } while (0)
 
 struct W4 {
     uint32_t v[4];
@@ -54,6 +67,11 @@ struct SegIter {
           tile(0), have_tile(false)
     {
     }
+    // end offset of query q; a single query ends at total_kmers by contract (no global load)
+    __device__ __forceinline__ uint64_t qend(uint32_t qq) const
+    {
+        return nq == 1 ? total : (uint64_t)__ldg(qoff + qq + 1);
+    }
     __device__ uint32_t find_query(uint64_t kg) const
     {
         // q with qoff[q] <= kg < qoff[q+1]  (skips empty queries)
@@ -74,9 +92,9 @@ struct SegIter {
             have_tile = true;
             q = find_query(kg);
         } else {
-            while (kg >= (uint64_t)__ldg(qoff + q + 1)) ++q;
+            while (kg >= qend(q)) ++q;
         }
-        uint64_t lim = (uint64_t)__ldg(qoff + q + 1) - kg;  // to the end of the query (<= end of tile)
+        uint64_t lim = qend(q) - kg;  // to the end of the query (<= end of tile)
         if (end - p < lim) lim = end - p;
         const uint64_t sl = p / ips;
         const uint64_t to_slice_end = (sl + 1) * ips - p;
@@ -161,16 +179,17 @@ __device__ __forceinline__ void stg128(void *p, const W4 &x)
     *reinterpret_cast<uint4 *>(p) = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
 }
 
-// write the live planes of one segment to its partial slot (plane-major, tile_bytes per plane)
-__device__ __forceinline__ void flush_planes(const VCounter &c, uint32_t nplanes, uint8_t *slot_unit,
-                                             uint32_t plane_stride)
+// write the planes of one segment to its partial slot (plane-major, tile_bytes per plane).  All
+// planes_per_slot planes are written (planes the segment cannot reach are zero in the counter), so
+// the merge loads them without looking at segment lengths.
+__device__ __forceinline__ void flush_planes(const VCounter &c, uint32_t pps, uint8_t *slot_unit, uint32_t plane_stride)
 {
     stg128(slot_unit, c.ones);
-    if (nplanes > 1) stg128(slot_unit + plane_stride, c.twos);
-    if (nplanes > 2) stg128(slot_unit + 2 * (size_t)plane_stride, c.fours);
+    if (pps > 1) stg128(slot_unit + plane_stride, c.twos);
+    if (pps > 2) stg128(slot_unit + 2 * (size_t)plane_stride, c.fours);
 #pragma unroll
     for (int b = 0; b < kHiPlanes; ++b)
-        if (b + 3 < (int)nplanes) stg128(slot_unit + (size_t)(b + 3) * plane_stride, c.hi[b]);
+        if (b + 3 < (int)pps) stg128(slot_unit + (size_t)(b + 3) * plane_stride, c.hi[b]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -204,10 +223,13 @@ __device__ __forceinline__ void tma_producer(const QueryParams &P, uint8_t *ring
 
     SegIter it(P, begin, end);
     Seg s;
+    bool first = true;
     while (it.next(s)) {
         const uint32_t tb0 = s.tile * P.tile_bytes;
         const uint32_t tw = min(P.tile_bytes, P.row_bytes16 - tb0);
         const uint8_t *src0 = P.matrix + tb0;
+        if (first && lane == 0) BIGSI_TS(1);
+        first = false;
         for (uint32_t k0 = 0; k0 < s.nk; k0 += G) {
             const uint32_t n_rows = min(G, s.nk - k0) * h;
             uint8_t *dst0 = ring + (size_t)stage * stage_bytes;
@@ -237,6 +259,7 @@ __device__ __forceinline__ void tma_producer(const QueryParams &P, uint8_t *ring
             }
         }
     }
+    if (lane == 0) BIGSI_TS(5);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -258,6 +281,7 @@ __device__ __forceinline__ void tma_consumer(const QueryParams &P, const uint8_t
     W4 acc;
     SegIter it(P, begin, end);
     Seg s;
+    bool first_slot = true;
     while (it.next(s)) {
         const uint32_t tb0 = s.tile * P.tile_bytes;
         const uint32_t tw = min(P.tile_bytes, P.row_bytes16 - tb0);
@@ -270,7 +294,9 @@ __device__ __forceinline__ void tma_consumer(const QueryParams &P, const uint8_t
         for (uint32_t k0 = 0; k0 < s.nk; k0 += G) {
             const uint32_t gn = min(G, s.nk - k0);
             mbar_wait(&full[stage], parity);  // all row segments of this slot have landed
-            if (active) {
+            if (first_slot && threadIdx.x == 0) BIGSI_TS(2);
+            first_slot = false;
+            if (active && !(P.debug_flags & 1u)) {
                 const uint8_t *base = ring + (size_t)stage * stage_bytes + unit * 16;
                 for (uint32_t g = 0; g < gn; ++g) {
                     const uint8_t *b = base + g * h * seg_stride;
@@ -302,16 +328,18 @@ __device__ __forceinline__ void tma_consumer(const QueryParams &P, const uint8_t
                 parity ^= 1;
             }
         }
+        if (threadIdx.x == 0) BIGSI_TS(3);
         if (active) {
             const uint64_t slot = (uint64_t)s.slice + (uint64_t)s.tile * P.n_queries + s.q;
             uint8_t *dst = P.partial + slot * P.planes_per_slot * P.tile_bytes + unit * 16;
             if (MODE == kModeCounts) {
                 ctr.finish(nhi);
-                flush_planes(ctr, nplanes, dst, P.tile_bytes);
+                flush_planes(ctr, P.planes_per_slot, dst, P.tile_bytes);
             } else {
                 stg128(dst, acc);
             }
         }
+        if (threadIdx.x == 0) BIGSI_TS(4);
     }
 }
 
@@ -325,6 +353,7 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
     const uint32_t consumer_warps = (blockDim.x >> 5) - 1;
 
     if (threadIdx.x == 0) {
+        BIGSI_TS(0);
         for (uint32_t s = 0; s < P.n_stages; ++s) {
             mbar_init(&full[s], 1);                // one arrive.expect_tx by the producer + tx bytes
             mbar_init(&empty[s], consumer_warps);  // one arrive per consumer warp
@@ -332,6 +361,14 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
         fence_barrier_init();
     }
     __syncthreads();
+    // PDL: everything above overlapped the previous kernel's tail; from here on we read what it
+    // produced (row ids) and overwrite what the previous query's merge may still read (partials)
+    grid_launch_dependents();
+    grid_dependency_wait();
+
+    if (P.n_hits != nullptr)  // hit counters of the fused threshold (stage 2 adds to them)
+        for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < P.n_queries; q += gridDim.x * blockDim.x)
+            P.n_hits[q] = 0ull;
 
     const uint64_t span = (uint64_t)P.slices_per_cta * P.items_per_slice;
     const uint64_t begin = (uint64_t)blockIdx.x * span;
@@ -346,145 +383,12 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 2: merge.  Block = 256 threads = WPB words x NG slot groups; one block per
-// (query, tile, chunk of WPB 32-bit words).
-// ------------------------------------------------------------------------------------------
-constexpr int kMergeThreads = 256;
-constexpr int kMaxTotalPlanes = 32;
-
-template <int MODE, int NG>
-__global__ void __launch_bounds__(kMergeThreads) merge_kernel(const __grid_constant__ QueryParams P)
-{
-    constexpr int WPB = kMergeThreads / NG;                   // words per block
-    constexpr int NP = MODE == kModeCounts ? kMaxTotalPlanes : 1;
-    __shared__ uint32_t sm[(NG > 1 ? NG / 2 : 1) * NP * WPB];  // [group][plane][word]
-
-    const uint32_t chunk_bytes = WPB * 4;
-    const uint32_t cpt = (P.tile_bytes + chunk_bytes - 1) / chunk_bytes;
-    const uint64_t bid = blockIdx.x;
-    const uint32_t chunk = (uint32_t)(bid % cpt);
-    const uint64_t tq = bid / cpt;
-    const uint32_t t = (uint32_t)(tq % P.n_tiles);
-    const uint32_t q = (uint32_t)(tq / P.n_tiles);
-    const uint32_t tb0 = t * P.tile_bytes;
-    const uint32_t tw = min(P.tile_bytes, P.row_bytes16 - tb0);
-    const uint32_t cb = chunk * chunk_bytes;
-    if (cb >= tw) return;
-
-    const uint32_t w = threadIdx.x % WPB;
-    const uint32_t g = threadIdx.x / WPB;
-    const bool valid = cb + w * 4 < tw;
-    const uint32_t TP = MODE == kModeCounts ? P.total_planes : 1;
-
-    uint32_t acc[NP];
-#pragma unroll
-    for (int b = 0; b < NP; ++b) acc[b] = MODE == kModeCounts ? 0u : 0xffffffffu;
-
-    const uint64_t k0 = (uint64_t)__ldg(P.qoff + q), k1 = (uint64_t)__ldg(P.qoff + q + 1);
-    if (k1 > k0 && valid) {
-        const uint64_t I0 = (uint64_t)t * P.total_kmers + k0, I1 = (uint64_t)t * P.total_kmers + k1;
-        const uint64_t ips = P.items_per_slice;
-        const uint64_t s_first = I0 / ips, s_last = (I1 - 1) / ips;
-        for (uint64_t s = s_first + g; s <= s_last; s += NG) {
-            const uint64_t slot = s + (uint64_t)t * P.n_queries + q;
-            const uint8_t *src = P.partial + slot * P.planes_per_slot * P.tile_bytes + cb + w * 4;
-            if (MODE == kModeCounts) {
-                const uint64_t lo = max(I0, s * ips), hi = min(I1, (s + 1) * ips);
-                const uint32_t ps = 32 - __clz((uint32_t)(hi - lo));  // planes this segment wrote
-                uint32_t x[kSegPlanes];
-#pragma unroll
-                for (int b = 0; b < kSegPlanes; ++b)
-                    x[b] = b < (int)ps ? *reinterpret_cast<const uint32_t *>(src + (size_t)b * P.tile_bytes) : 0u;
-                uint32_t carry = 0;
-#pragma unroll
-                for (int b = 0; b < NP; ++b) {
-                    if (b < (int)TP) {
-                        const uint32_t xb = b < kSegPlanes ? x[b < kSegPlanes ? b : 0] : 0u;
-                        const uint32_t o = acc[b];
-                        acc[b] = xor3(o, xb, carry);
-                        carry = maj3(o, xb, carry);
-                    }
-                }
-            } else {
-                acc[0] &= *reinterpret_cast<const uint32_t *>(src);
-            }
-        }
-    }
-
-    // tree reduction over the NG slot groups
-    if (NG > 1) {
-#pragma unroll
-        for (int stride = NG / 2; stride >= 1; stride >>= 1) {
-            if ((int)g >= stride && (int)g < 2 * stride) {
-#pragma unroll
-                for (int b = 0; b < NP; ++b)
-                    if (b < (int)TP) sm[((g - stride) * NP + b) * WPB + w] = acc[b];
-            }
-            __syncthreads();
-            if ((int)g < stride) {
-                if (MODE == kModeCounts) {
-                    uint32_t carry = 0;
-#pragma unroll
-                    for (int b = 0; b < NP; ++b) {
-                        if (b < (int)TP) {
-                            const uint32_t xb = sm[(g * NP + b) * WPB + w];
-                            const uint32_t o = acc[b];
-                            acc[b] = xor3(o, xb, carry);
-                            carry = maj3(o, xb, carry);
-                        }
-                    }
-                } else {
-                    acc[0] &= sm[g * WPB + w];
-                }
-            }
-            __syncthreads();
-        }
-    }
-    // group 0 publishes the merged planes; every thread then expands columns
-    if (g == 0) {
-#pragma unroll
-        for (int b = 0; b < NP; ++b)
-            if (b < (int)TP) sm[b * WPB + w] = valid ? acc[b] : 0u;
-    }
-    __syncthreads();
-
-    if (MODE == kModeCounts) {
-        uint32_t *out = reinterpret_cast<uint32_t *>(P.out) + (uint64_t)q * P.out_stride;
-        const uint32_t col_base = (tb0 + cb) * 8;
-        // bit i of a little-endian 32-bit word of MSB-first bytes is column (i ^ 7) of that word
-        const uint32_t ncols_here = min((uint32_t)WPB * 32u, (tw - cb) * 8u);  // never past this tile
-        for (uint32_t c = threadIdx.x; c < ncols_here; c += kMergeThreads) {
-            const uint32_t col = col_base + c;
-            if (col >= P.num_cols) break;
-            const uint32_t word = c >> 5, bit = (c & 31) ^ 7;
-            uint32_t cnt = 0;
-#pragma unroll
-            for (int b = 0; b < NP; ++b)
-                if (b < (int)TP) cnt |= ((sm[b * WPB + word] >> bit) & 1u) << b;
-            out[col] = cnt;
-        }
-    } else {
-        uint8_t *out = reinterpret_cast<uint8_t *>(P.out) + (uint64_t)q * P.out_stride;
-        const uint32_t row_bytes = (P.num_cols + 7) >> 3;
-        const uint32_t nbytes_here = min((uint32_t)WPB * 4u, tw - cb);  // never past this tile
-        for (uint32_t c = threadIdx.x; c < nbytes_here; c += kMergeThreads) {
-            const uint32_t byte = tb0 + cb + c;
-            if (byte >= row_bytes) break;
-            uint32_t v = (sm[c >> 2] >> (8 * (c & 3))) & 0xffu;
-            if (byte == row_bytes - 1 && (P.num_cols & 7)) v &= 0xff00u >> (P.num_cols & 7);
-            out[byte] = (uint8_t)v;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 template <int MODE, int HC>
 static cudaError_t launch_one(const QueryParams &p, int grid, cudaStream_t stream)
 {
-    fused_query<MODE, HC><<<grid, query_block_threads(p), query_smem_bytes(p), stream>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(fused_query<MODE, HC>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream, p);
 }
 
 cudaError_t launch_query(const QueryParams &p, int mode, int grid, cudaStream_t stream)
@@ -492,29 +396,6 @@ cudaError_t launch_query(const QueryParams &p, int mode, int grid, cudaStream_t 
     if (mode == kModeCounts)
         return p.h == 3 ? launch_one<kModeCounts, 3>(p, grid, stream) : launch_one<kModeCounts, 0>(p, grid, stream);
     return p.h == 3 ? launch_one<kModeAnd, 3>(p, grid, stream) : launch_one<kModeAnd, 0>(p, grid, stream);
-}
-
-template <int MODE>
-static cudaError_t launch_merge_mode(const QueryParams &p, cudaStream_t stream)
-{
-    // slots one (tile, query) can span: decides how many thread groups share the slot loop
-    const uint64_t longest = p.total_planes >= 32 ? 0xffffffffull : ((1ull << p.total_planes) - 1);
-    const uint64_t max_slots = longest / p.items_per_slice + 2;
-    const int ng = MODE == kModeAnd ? (max_slots <= 2 ? 1 : 8) : (max_slots <= 2 ? 1 : (max_slots <= 16 ? 8 : 32));
-    const uint32_t chunk_bytes = (kMergeThreads / ng) * 4;
-    const uint64_t cpt = (p.tile_bytes + chunk_bytes - 1) / chunk_bytes;
-    const uint64_t blocks = cpt * p.n_tiles * p.n_queries;
-    if (blocks == 0) return cudaSuccess;
-    if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    if (ng == 1) merge_kernel<MODE, 1><<<(unsigned)blocks, kMergeThreads, 0, stream>>>(p);
-    else if (ng == 8) merge_kernel<MODE, 8><<<(unsigned)blocks, kMergeThreads, 0, stream>>>(p);
-    else merge_kernel<MODE, 32><<<(unsigned)blocks, kMergeThreads, 0, stream>>>(p);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_merge(const QueryParams &p, int mode, cudaStream_t stream)
-{
-    return mode == kModeCounts ? launch_merge_mode<kModeCounts>(p, stream) : launch_merge_mode<kModeAnd>(p, stream);
 }
 
 cudaError_t query_kernels_init()

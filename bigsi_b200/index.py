@@ -189,6 +189,12 @@ class DeviceIndex:
         check(self._L.bigsi_b200_query_dev(self.handle, mode, d_rows, d_q_offsets, n_queries, total_kmers,
                                            max_query_kmers, h, d_out, out_stride, stream))
 
+    def query_hits_dev(self, d_rows, d_q_offsets, n_queries, total_kmers, h, d_min_kmers, d_cols_out, d_counts_out,
+                       cap, d_n_out, stream=0, max_query_kmers=0, d_counts_full=0, counts_stride=0):
+        check(self._L.bigsi_b200_query_hits_dev(self.handle, d_rows, d_q_offsets, n_queries, total_kmers,
+                                                max_query_kmers, h, d_min_kmers, d_cols_out, d_counts_out, cap,
+                                                d_n_out, d_counts_full, counts_stride, stream))
+
     def lookup_dev(self, d_rows, n_kmers, h, d_out, out_stride, stream=0):
         check(self._L.bigsi_b200_lookup_dev(self.handle, d_rows, n_kmers, h, d_out, out_stride, stream))
 

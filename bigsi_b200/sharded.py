@@ -96,6 +96,19 @@ class DeviceShard:
         return buf
 
 
+    def search_hits(self, rows, q_offsets, n_queries, min_kmers, max_query_kmers=0):
+        """Fused gather-AND-count + threshold (one C-ABI call, two kernels): same packed layout as
+        hits(); the full count vectors are never written."""
+        t = self.torch
+        buf = t.empty((n_queries * (2 + 2 * self.cap),), dtype=t.int32, device=self.device)
+        base = buf.data_ptr()
+        self.index.query_hits_dev(rows.data_ptr(), q_offsets.data_ptr(), n_queries, rows.shape[0], self.h,
+                                  min_kmers.data_ptr(), base + 8 * n_queries,
+                                  base + 8 * n_queries + 4 * n_queries * self.cap, self.cap, base, self._stream(),
+                                  max_query_kmers)
+        return buf
+
+
 def unpack_hits(buf, n_queries, cap):
     """Inverse of DeviceShard.hits' packing for a [G, Q*(2+2*cap)] (or 1-D) int32 array on the host."""
     a = np.asarray(buf).reshape(-1, n_queries * (2 + 2 * cap))
@@ -129,8 +142,7 @@ class ShardedSearcher:
             rows = t.empty((U, sh.h), dtype=t.int32, device=sh.device)
         if self.dist is not None:
             self.dist.broadcast(rows, src=0)  # exchange 1: row ids
-        counts = sh.counts(rows, q_offsets, n_queries, max_query_kmers)
-        packed = sh.hits(counts, min_kmers)
+        packed = sh.search_hits(rows, q_offsets, n_queries, min_kmers, max_query_kmers)
         if self.dist is None:
             return packed[None]
         gathered = t.empty((self.world_size, packed.shape[0]), dtype=packed.dtype, device=sh.device)

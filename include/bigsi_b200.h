@@ -82,13 +82,17 @@ int bigsi_b200_index_destroy(bigsi_b200_index *index); /* storage.delete_all()/c
 int bigsi_b200_index_get_info(const bigsi_b200_index *index, bigsi_b200_info *info_out);
 
 /* Tuning / instrumentation knobs (value 0 = automatic): "tile_bytes", "grid", "kmers_per_stage",
- * "n_stages", "ctas_per_sm"; "timing" (1 = bracket the fused kernel and the merge kernel of
+ * "n_stages", "ctas_per_sm", "debug_flags"; "timing" (1 = bracket the fused kernel and the merge kernel of
  * every query launch with CUDA events, read back with bigsi_b200_index_timing_collect). */
 int bigsi_b200_index_set_option(bigsi_b200_index *index, const char *key, int64_t value);
 /* Synchronises, sums the event-timed durations recorded since the last collect and resets them.
  * fused_ms = fused gather-AND-count kernel, merge_ms = merge kernel, n = query launches timed. */
 int bigsi_b200_index_timing_collect(bigsi_b200_index *index, double *fused_ms_out, double *merge_ms_out,
                                     uint64_t *n_out);
+
+/* Debug aid: with option "debug_flags" bit 1 set, every CTA of the fused kernel records 8 uint64
+ * globaltimer stamps (ns) of its last launch; this copies the first n_words of them to the host. */
+int bigsi_b200_index_debug_read(bigsi_b200_index *index, uint64_t *out, uint64_t n_words);
 
 /* Rows in the reference's byte layout (BitMatrix.set_rows: matrix/bitmatrix.py:42-44 ->
  * storage/base.py:91-94).  Source row i starts at rows + i*src_stride; the shard's bytes are
@@ -129,6 +133,16 @@ int bigsi_b200_hash_kmers_dev(const char *d_kmers, uint64_t n, int k, int h, uin
 int bigsi_b200_query_dev(bigsi_b200_index *index, int mode, const int32_t *d_rows,
                          const int64_t *d_q_offsets, uint64_t n_queries, uint64_t total_kmers,
                          uint64_t max_query_kmers, int h, void *d_out, uint64_t out_stride, void *stream);
+
+/* Same gather-AND-count with the threshold fused into the merge kernel (graph/bigsi.py:211-230,241-242):
+ * query q keeps the columns whose count >= d_min_kmers[q]; hits are laid out as in
+ * bigsi_b200_threshold_dev.  d_counts_full may be NULL (hits only) or receive the full uint32 counts
+ * [n_queries][counts_stride] as well. */
+int bigsi_b200_query_hits_dev(bigsi_b200_index *index, const int32_t *d_rows, const int64_t *d_q_offsets,
+                              uint64_t n_queries, uint64_t total_kmers, uint64_t max_query_kmers, int h,
+                              const uint32_t *d_min_kmers, int32_t *d_cols_out, uint32_t *d_counts_out,
+                              uint64_t cap, uint64_t *d_n_out, uint32_t *d_counts_full, uint64_t counts_stride,
+                              void *stream);
 
 /* Per-k-mer AND vectors (KmerSignatureIndex.lookup: graph/index.py:42-49,75-80): d_out =
  * uint8 [n_kmers][out_stride], out_stride >= row_bytes. */

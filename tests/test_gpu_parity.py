@@ -391,3 +391,51 @@ def test_full_size_config2_parity(B):
     both = ix.search_kmers(arr, k, h, q_offsets=[0, 3777, 10_000])
     assert np.array_equal(both[0], a) and np.array_equal(both[1], b)
     ix.close()
+
+
+# ---------------------------------------------------------------------------
+# device-pointer entry points on torch tensors (the multi-GPU plumbing path)
+# ---------------------------------------------------------------------------
+def test_device_pointer_path_fused_threshold(B):
+    import torch
+
+    from bigsi_b200.sharded import DeviceShard, ShardedSearcher, unpack_hits
+
+    rng = np.random.default_rng(31)
+    m, N, k, h = 30_011, 9000, 31, 3
+    ix, packed = _random_index(B, rng, m, N, density=0.85)
+    oix = O.OracleIndex(k, m, h, N, rows=packed)
+    shard = DeviceShard(ix, k, h, cap=512)
+    lens = [300, 0, 1, 900]
+    qoff = np.concatenate([[0], np.cumsum(lens)])
+    arr = _rand_kmers(rng, int(qoff[-1]), k)
+    kmers = _kmer_strs(arr)
+    mins = np.array([150, 1, 1, 520], dtype=np.int32)
+    dev = shard.device
+    d_k = torch.from_numpy(arr).to(dev)
+    d_q = torch.from_numpy(qoff.astype(np.int64)).to(dev)
+    d_min = torch.from_numpy(mins).to(dev)
+    rows = shard.hash(d_k)
+    assert np.array_equal(rows.cpu().numpy(), O.hash_kmers(arr, k, h, m))
+    # unfused: counts then threshold
+    counts = shard.counts(rows, d_q, 4, max(lens))
+    n1, c1, v1 = unpack_hits(shard.hits(counts, d_min).cpu().numpy(), 4, 512)
+    # fused
+    n2, c2, v2 = unpack_hits(shard.search_hits(rows, d_q, 4, d_min, max(lens)).cpu().numpy(), 4, 512)
+    g = ShardedSearcher(shard).search_step(d_k, d_q, d_min, 4, max(lens))
+    n3, c3, v3 = unpack_hits(g.cpu().numpy(), 4, 512)
+    torch.cuda.synchronize()
+    for q in range(4):
+        sl = slice(qoff[q], qoff[q + 1])
+        cnt = oix.counts(kmers[sl]) if lens[q] else np.zeros(N, dtype=np.int32)
+        assert np.array_equal(counts[q, :N].cpu().numpy().astype(np.int64), cnt.astype(np.int64))
+        exp = np.nonzero(cnt >= mins[q])[0]
+        for n, c, v in ((n1, c1, v1), (n2, c2, v2), (n3, c3, v3)):
+            assert n[0, q] == len(exp)
+            got = min(len(exp), 512)
+            order = np.argsort(c[0, q, :got])
+            if len(exp) <= 512:
+                assert np.array_equal(c[0, q, :got][order], exp) and np.array_equal(v[0, q, :got][order], cnt[exp])
+            else:
+                assert all(cnt[cc] == vv and cnt[cc] >= mins[q] for cc, vv in zip(c[0, q, :got], v[0, q, :got]))
+    ix.close()
