@@ -41,6 +41,8 @@ class Info(ctypes.Structure):
         ("last_n_slices", ctypes.c_uint32),
         ("kernel_launches", ctypes.c_uint64),
         ("scratch_bytes", ctypes.c_uint64),
+        ("last_fused", ctypes.c_uint32),
+        ("reserved", ctypes.c_uint32),
     ]
 
     def asdict(self):
@@ -70,6 +72,8 @@ SIGNATURES = {
     "bigsi_b200_hash_kmers_dev": (_int, [_vp, _u64, _int, _int, _u64, _int, _vp, _vp]),
     "bigsi_b200_query_dev": (_int, [_vp, _int, _vp, _vp, _u64, _u64, _u64, _int, _vp, _u64, _vp]),
     "bigsi_b200_query_hits_dev": (_int, [_vp, _vp, _vp, _u64, _u64, _u64, _int, _vp, _vp, _vp, _u64, _vp, _vp, _u64, _vp]),
+    "bigsi_b200_query_kmers_hits_dev": (_int, [_vp, _vp, _int, _vp, _u64, _u64, _u64, _int, _vp, _vp, _vp, _u64, _vp, _vp,
+                                               _u64, _vp]),
     "bigsi_b200_lookup_dev": (_int, [_vp, _vp, _u64, _int, _vp, _u64, _vp]),
     "bigsi_b200_threshold_dev": (_int, [_vp, _u64, _u64, _u64, _vp, _vp, _vp, _u64, _vp, _vp]),
     "bigsi_b200_search_kmers": (_int, [_vp, _int, _vp, _vp, _u64, _int, _int, _vp, _u64]),

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libbigsi_b200.so")
 SOURCES = ["capi.cu", "query_kernels.cu", "merge_kernels.cu", "aux_kernels.cu"]
-HEADERS = ["ptx.cuh", "query.cuh", "launch.cuh", os.path.join("..", "..", "include", "bigsi_b200.h")]
+HEADERS = ["ptx.cuh", "query.cuh", "launch.cuh", "hash.cuh", "merge.cuh", os.path.join("..", "..", "include", "bigsi_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1,5 +1,6 @@
 // Helper kernels around the fused query kernel: k-mer hashing, per-k-mer lookup vectors,
 // threshold/compaction, column insert and the synthetic index generator.
+#include "hash.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
 #include "query.cuh"
@@ -7,53 +8,10 @@
 namespace bigsi {
 
 // ------------------------------------------------------------------------------------------
-// K1: canonical k-mer + MurmurHash3_x86_32, seeds 0..h-1, signed, floor-mod m.
-// Replaces convert_query_kmer/canonical (bigsi/utils/fncts.py:38-54) and _hash/generate_hashes
-// (bigsi/bloom/bloomfilter.py:5-13; third-party mmh3 2.5.1 = MurmurHash3_x86_32).
+// K1: canonical k-mer + MurmurHash3_x86_32 (device code in hash.cuh), one block per group of k-mers.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t comp_base(uint32_t b)
-{
-    // only A<->T and C<->G are complemented (utils/fncts.py:12); anything else passes through
-    return b == 'A' ? 'T' : b == 'T' ? 'A' : b == 'C' ? 'G' : b == 'G' ? 'C' : b;
-}
-__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
-
-// Block-cooperative hashing.  (1) the block's k-mer bytes are staged in shared memory with 16-byte
-// loads; (2) one thread per k-mer decides the orientation; (3) one thread per (k-mer, 4-byte block)
-// writes the canonical bytes as little-endian words (zero padded, so the last word IS murmur's
-// tail); (4) one thread per (k-mer, seed) runs MurmurHash3_x86_32 over those words.
 constexpr int kHashThreads = 128;
 constexpr int kHashSmemBytes = 40 * 1024;
-
-__device__ __forceinline__ int32_t murmur_finish_mod(uint32_t h1, uint32_t len, uint32_t m)
-{
-    h1 ^= len;
-    h1 ^= h1 >> 16;
-    h1 *= 0x85ebca6bu;
-    h1 ^= h1 >> 13;
-    h1 *= 0xc2b2ae35u;
-    h1 ^= h1 >> 16;
-    // Python floor-mod of the SIGNED 32-bit hash (bloom/bloomfilter.py:5-6), in 32-bit arithmetic
-    if ((int32_t)h1 >= 0) return (int32_t)(h1 % m);
-    const uint32_t r = (0u - h1) % m;  // |s| mod m
-    return (int32_t)(r ? m - r : 0u);
-}
-__device__ __forceinline__ uint32_t murmur_block(uint32_t h1, uint32_t k1)
-{
-    k1 *= 0xcc9e2d51u;
-    k1 = rotl32(k1, 15);
-    k1 *= 0x1b873593u;
-    h1 ^= k1;
-    h1 = rotl32(h1, 13);
-    return h1 * 5u + 0xe6546b64u;
-}
-__device__ __forceinline__ uint32_t murmur_tail(uint32_t h1, uint32_t k1)
-{
-    k1 *= 0xcc9e2d51u;
-    k1 = rotl32(k1, 15);
-    k1 *= 0x1b873593u;
-    return h1 ^ k1;
-}
 
 __global__ void __launch_bounds__(kHashThreads) hash_kmers_kernel(const uint8_t *__restrict__ kmers, uint64_t n, int k,
                                                                  int h, uint32_t m, int canonical, uint32_t kpb,
@@ -67,62 +25,7 @@ __global__ void __launch_bounds__(kHashThreads) hash_kmers_kernel(const uint8_t 
     const uint8_t *g0 = kmers + base * (uint64_t)k;
     const int nblocks = k >> 2, rem = k & 3;
     if (use_smem) {
-        // smem layout: [raw bytes: kpb*k + 32][orientation: kpb, padded to 16][words: kpb * wstride]
-        const uint32_t wpk = (uint32_t)(k + 3) >> 2;
-        const uint32_t wstride = wpk | 1;  // odd stride: conflict-free LDS across k-mers
-        const uint32_t raw_bytes = ((kpb * (uint32_t)k + 32) + 15) & ~15u;
-        uint8_t *fwd = sk + raw_bytes;
-        uint32_t *cw = reinterpret_cast<uint32_t *>(sk + raw_bytes + ((kpb + 15) & ~15u));
-        // (1) one round trip of 16-byte loads over the enclosing aligned window; the window leaves
-        // the k-mer array only inside its first / last 16-byte line, which every CUDA allocation
-        // (>= 256-byte granular) covers
-        const uint32_t nbytes = cnt * (uint32_t)k;
-        const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15);
-        const uint4 *a0 = reinterpret_cast<const uint4 *>(g0 - skew);
-        const uint32_t nvec = (skew + nbytes + 15) >> 4;
-        uint4 *sv = reinterpret_cast<uint4 *>(sk);
-        for (uint32_t i = threadIdx.x; i < nvec; i += kHashThreads) sv[i] = __ldg(a0 + i);
-        __syncthreads();
-        const uint8_t *src = sk + skew;
-        // (2) orientation: forward unless the reverse complement is lexicographically smaller
-        for (uint32_t km = threadIdx.x; km < cnt; km += kHashThreads) {
-            const uint8_t *s = src + (size_t)km * k;
-            bool f = true;
-            if (canonical) {
-                for (int j = 0; j < k; ++j) {
-                    const uint32_t a = s[j], b = comp_base(s[k - 1 - j]);
-                    if (a != b) {
-                        f = a < b;
-                        break;
-                    }
-                }
-            }
-            fwd[km] = f ? 1 : 0;
-        }
-        __syncthreads();
-        // (3) canonical bytes as little-endian words
-        for (uint32_t i = threadIdx.x; i < cnt * wpk; i += kHashThreads) {
-            const uint32_t km = i / wpk, wi = i % wpk;
-            const uint8_t *s = src + (size_t)km * k;
-            const bool f = fwd[km] != 0;
-            uint32_t word = 0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = (int)wi * 4 + u;
-                if (j < k) word |= (f ? (uint32_t)s[j] : comp_base(s[k - 1 - j])) << (8 * u);
-            }
-            cw[km * wstride + wi] = word;
-        }
-        __syncthreads();
-        // (4) hash
-        for (uint32_t w = threadIdx.x; w < cnt * (uint32_t)h; w += kHashThreads) {
-            const uint32_t km = w / (uint32_t)h, seed = w % (uint32_t)h;
-            const uint32_t *wp = cw + km * wstride;
-            uint32_t h1 = seed;
-            for (int b = 0; b < nblocks; ++b) h1 = murmur_block(h1, wp[b]);
-            if (rem) h1 = murmur_tail(h1, wp[nblocks]);
-            rows_out[(base + km) * (uint64_t)h + seed] = murmur_finish_mod(h1, (uint32_t)k, m);
-        }
+        hash_kmers_cooperative(g0, cnt, k, h, m, canonical, sk, rows_out + base * (uint64_t)h);
         return;
     }
     // very long "k-mers" (k > the staging buffer): one thread per (k-mer, seed) straight from global
@@ -159,7 +62,7 @@ cudaError_t launch_hash_kmers(const char *d_kmers, uint64_t n, int k, int h, uin
     if (n == 0) return cudaSuccess;
     // k-mers per block: about two (k-mer, seed) items per thread, bounded by the staging buffer
     uint32_t kpb = (uint32_t)((2 * kHashThreads + h - 1) / h);
-    const uint64_t per_kmer = (uint64_t)k + 1 + 4ull * ((((uint64_t)k + 3) >> 2) | 1);  // raw + flag + words
+    const uint64_t per_kmer = prehash_bytes_per_kmer((uint32_t)k);  // raw + flag + words
     int use_smem = 1;
     if (per_kmer + 96 > (uint64_t)kHashSmemBytes) {
         use_smem = 0;

@@ -7,6 +7,8 @@
 #include <vector>
 
 #include "../../include/bigsi_b200.h"
+#include "hash.cuh"
+#include "merge.cuh"
 #include "query.cuh"
 
 using namespace bigsi;
@@ -134,6 +136,9 @@ struct bigsi_b200_index {
     int64_t opt_tile_bytes = 0, opt_grid = 0, opt_kmers_per_stage = 0, opt_n_stages = 0, opt_ctas_per_sm = 0;
     bool timing = false;
     int64_t opt_debug_flags = 0;
+    int64_t opt_prehash = 1, opt_fuse_merge = 1;  // in-kernel hashing / in-kernel merge (1 = when possible)
+    DevBuf d_barrier;                             // grid-barrier arrival counter of the fused kernel
+    uint64_t barrier_target = 0;
     // scratch
     DevBuf debug_ts;
     DevBuf partial, d_kmers, d_rows, d_qoff, d_out, d_min, d_nhits, d_bloom, d_planted;
@@ -157,24 +162,27 @@ int ensure_kernels()
     return 0;
 }
 
-// Launch plan of one query batch (DESIGN.md "Launch planning").
+// Launch plan of one query batch (DESIGN.md "Launch planning").  `have_kmers`: the caller holds
+// raw k-mers (length k), so the kernel may hash them itself when the geometry allows.
 int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t total_kmers, uint64_t max_query_kmers,
-               int h, QueryParams &p, int &grid)
+               int h, bool have_kmers, int k, QueryParams &p, int &grid)
 {
     if (h < 1 || h > kMaxH) return fail(BIGSI_B200_ERR_INVALID, "h=%d out of range [1,%d]", h, kMaxH);
     if (n_queries > 0xffffffffull) return fail(BIGSI_B200_ERR_INVALID, "too many queries");
     memset(&p, 0, sizeof p);
     const uint64_t row_bytes = (ix->num_cols + 7) / 8;
+    const uint64_t smem_avail = (uint64_t)(kSmemBudget - kSmemHeaderBytes);
     p.matrix = ix->matrix;
     p.pitch = ix->pitch;
     p.n_queries = (uint32_t)n_queries;
     p.h = (uint32_t)h;
     p.total_kmers = total_kmers;
     p.num_cols = (uint32_t)ix->num_cols;
+    p.num_rows = (uint32_t)ix->num_rows;
     p.row_bytes16 = (uint32_t)round_up(row_bytes ? row_bytes : 1, 16);
 
     // column tile: as wide as the consumer warps allow, but >= 3 one-k-mer stages must fit in smem
-    uint64_t max_tile = (uint64_t)(kSmemBudget - kSmemHeaderBytes) / (3ull * h) / 16 * 16;
+    uint64_t max_tile = smem_avail / (3ull * h) / 16 * 16;
     if (max_tile > (uint64_t)kMaxTileBytes) max_tile = kMaxTileBytes;
     if (max_tile < 16) return fail(BIGSI_B200_ERR_INVALID, "h=%d too large for the shared-memory ring", h);
     uint64_t tile = 0;
@@ -190,26 +198,6 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
     if (tile > p.row_bytes16) tile = p.row_bytes16;
     p.tile_bytes = (uint32_t)tile;
     p.n_tiles = (uint32_t)((p.row_bytes16 + tile - 1) / tile);
-
-    // ring geometry
-    const uint64_t kmer_bytes = (uint64_t)h * tile;
-    uint32_t G = 1;
-    if (ix->opt_kmers_per_stage > 0) {
-        G = (uint32_t)ix->opt_kmers_per_stage;
-    } else {
-        for (uint32_t g = 8; g > 1; g >>= 1)
-            if (g * kmer_bytes <= 16384) {
-                G = g;
-                break;
-            }
-    }
-    while (G > 1 && 3ull * G * kmer_bytes > (uint64_t)(kSmemBudget - kSmemHeaderBytes)) G >>= 1;
-    uint64_t stages = (uint64_t)(kSmemBudget - kSmemHeaderBytes) / (G * kmer_bytes);
-    if (stages > (uint64_t)kMaxStages) stages = kMaxStages;
-    if (ix->opt_n_stages > 0 && (uint64_t)ix->opt_n_stages < stages) stages = (uint64_t)ix->opt_n_stages;
-    if (stages < 2) return fail(BIGSI_B200_ERR_INVALID, "ring does not fit (h=%d tile=%llu)", h, (unsigned long long)tile);
-    p.kmers_per_stage = G;
-    p.n_stages = (uint32_t)stages;
 
     // slices
     p.total_items = (uint64_t)p.n_tiles * total_kmers;
@@ -242,6 +230,52 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
     p.total_planes = mode == BIGSI_B200_MODE_COUNTS ? (bits_of(longest) ? bits_of(longest) : 1) : 1;
     const uint64_t seg_max = longest < p.items_per_slice ? longest : p.items_per_slice;
     p.planes_per_slot = mode == BIGSI_B200_MODE_COUNTS ? (bits_of(seg_max) ? bits_of(seg_max) : 1) : 1;
+
+    // in-kernel hashing: every CTA hashes its own contiguous k-mers in the prologue (one tile, one
+    // slice per CTA, and the id table + staging scratch must fit beside a useful ring)
+    p.prehash = 0;
+    p.ids_bytes = 0;
+    if (have_kmers && grid > 0 && ix->opt_prehash != 0 && p.n_tiles == 1 && p.slices_per_cta == 1 && k >= 1) {
+        const uint64_t ids_bytes = round_up((uint64_t)p.items_per_slice * h * 4, 128);
+        const uint64_t scratch = hash_scratch_bytes(p.items_per_slice, (uint32_t)k);
+        if (ids_bytes <= 16384 && ids_bytes + scratch <= smem_avail && ids_bytes + 3ull * h * tile <= smem_avail) {
+            p.prehash = 1;
+            p.ids_bytes = (uint32_t)ids_bytes;
+            p.k = (uint32_t)k;
+        }
+    }
+
+    // ring geometry
+    const uint64_t ring_avail = smem_avail - p.ids_bytes;
+    const uint64_t kmer_bytes = (uint64_t)h * tile;
+    uint32_t G = 1;
+    if (ix->opt_kmers_per_stage > 0) {
+        G = (uint32_t)ix->opt_kmers_per_stage;
+    } else {
+        for (uint32_t g = 8; g > 1; g >>= 1)
+            if (g * kmer_bytes <= 16384) {
+                G = g;
+                break;
+            }
+    }
+    while (G > 1 && 3ull * G * kmer_bytes > ring_avail) G >>= 1;
+    uint64_t stages = ring_avail / (G * kmer_bytes);
+    if (stages > (uint64_t)kMaxStages) stages = kMaxStages;
+    if (ix->opt_n_stages > 0 && (uint64_t)ix->opt_n_stages < stages) stages = (uint64_t)ix->opt_n_stages;
+    if (stages < 2) return fail(BIGSI_B200_ERR_INVALID, "ring does not fit (h=%d tile=%llu)", h, (unsigned long long)tile);
+    p.kmers_per_stage = G;
+    p.n_stages = (uint32_t)stages;
+
+    // in-kernel merge: needs every CTA resident at once (one CTA per SM, grid <= SM count)
+    p.fuse_merge = 0;
+    if (ix->opt_fuse_merge != 0 && grid > 0 && grid <= ix->sm_count) {
+        p.fuse_merge = 1;
+        const MergePlan m = plan_merge(p, mode, query_block_threads(p));
+        p.merge_ng = (uint32_t)m.ng;
+        p.merge_gpi = m.gpi;
+        p.merge_items = m.n_items;
+        if (kSmemHeaderBytes + p.ids_bytes + (uint64_t)kMergeScratchBytes > (uint64_t)kSmemBudget) p.fuse_merge = 0;
+    }
     return 0;
 }
 
@@ -253,9 +287,11 @@ struct HitsOut {
     uint64_t cap = 0;
 };
 
-int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const int64_t *d_qoff, uint64_t n_queries,
-              uint64_t total_kmers, uint64_t max_query_kmers, int h, void *d_out, uint64_t out_stride,
-              cudaStream_t stream, const HitsOut *hits = nullptr)
+// One query batch on `stream`.  Exactly one of d_rows / d_kmers is given; with k-mers the kernel
+// hashes them itself when the plan allows, otherwise the hash kernel runs first into scratch rows.
+int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char *d_kmers, int k, const int64_t *d_qoff,
+              uint64_t n_queries, uint64_t total_kmers, uint64_t max_query_kmers, int h, void *d_out,
+              uint64_t out_stride, cudaStream_t stream, const HitsOut *hits = nullptr)
 {
     if (mode != BIGSI_B200_MODE_COUNTS && mode != BIGSI_B200_MODE_AND)
         return fail(BIGSI_B200_ERR_INVALID, "unknown query mode %d", mode);
@@ -264,6 +300,7 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const int64
     if (d_out && (mode == BIGSI_B200_MODE_COUNTS ? out_stride < ix->num_cols : out_stride < row_bytes))
         return fail(BIGSI_B200_ERR_INVALID, "out_stride %llu too small", (unsigned long long)out_stride);
     if (!d_out && !(hits && mode == BIGSI_B200_MODE_COUNTS)) return fail(BIGSI_B200_ERR_INVALID, "null output");
+    if (d_kmers && k < 1) return fail(BIGSI_B200_ERR_INVALID, "k must be >= 1");
     if (ix->num_cols == 0) {
         if (hits) CK(cudaMemsetAsync(hits->n, 0, n_queries * sizeof(unsigned long long), stream));
         return 0;
@@ -271,7 +308,19 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const int64
     if (int rc = ensure_kernels()) return rc;
     QueryParams p;
     int grid = 0;
-    if (int rc = plan_query(ix, mode, n_queries, total_kmers, max_query_kmers, h, p, grid)) return rc;
+    if (int rc = plan_query(ix, mode, n_queries, total_kmers, max_query_kmers, h, d_kmers != nullptr, k, p, grid)) return rc;
+    if (d_kmers && p.prehash) {
+        p.kmers = reinterpret_cast<const uint8_t *>(d_kmers);
+    } else if (d_kmers && total_kmers) {
+        if (total_kmers * (uint64_t)h * 4 > ix->d_rows.cap) {
+            CK(cudaStreamSynchronize(stream));
+            cudaError_t e = ix->d_rows.reserve(total_kmers * (uint64_t)h * 4);
+            if (e != cudaSuccess) return fail_cuda(e, "row-id workspace");
+        }
+        CK(launch_hash_kmers(d_kmers, total_kmers, k, h, ix->num_rows, 1, static_cast<int32_t *>(ix->d_rows.p), stream));
+        ix->kernel_launches++;
+        d_rows = static_cast<const int32_t *>(ix->d_rows.p);
+    }
     p.rows = d_rows;
     p.qoff = d_qoff;
     p.out = d_out;
@@ -298,6 +347,11 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const int64
         if (e != cudaSuccess) return fail_cuda(e, "partial-plane workspace");
     }
     p.partial = static_cast<uint8_t *>(ix->partial.p);
+    if (p.fuse_merge) {
+        p.barrier = static_cast<unsigned long long *>(ix->d_barrier.p);
+        ix->barrier_target += (uint64_t)grid;
+        p.barrier_target = ix->barrier_target;
+    }
 
     TimedLaunch tl{};
     if (ix->timing) {
@@ -312,17 +366,18 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const int64
         CK(cudaEventRecord(tl.e0, stream));
     }
     if (grid > 0) {
-        CK(launch_query(p, mode, grid, stream));
+        cudaError_t e = launch_query(p, mode, grid, stream);
+        if (e != cudaSuccess) {
+            if (p.fuse_merge) ix->barrier_target -= (uint64_t)grid;  // nothing arrived
+            return fail_cuda(e, "fused_query launch");
+        }
         ix->kernel_launches++;
     }
-    if (p.debug_flags & 4u) {  // experiment: time a SECOND (warm) merge instead of the first
-        QueryParams p2 = p;
-        p2.min_kmers = nullptr;
-        CK(launch_merge(p2, mode, stream));
-    }
     if (ix->timing) CK(cudaEventRecord(tl.e1, stream));
-    CK(launch_merge(p, mode, stream));
-    ix->kernel_launches++;
+    if (!p.fuse_merge) {
+        CK(launch_merge(p, mode, stream));
+        ix->kernel_launches++;
+    }
     if (ix->timing) {
         CK(cudaEventRecord(tl.e2, stream));
         ix->timed_used.push_back(tl);
@@ -339,6 +394,7 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const int64
     s.last_kmers_per_stage = p.kmers_per_stage;
     s.last_n_stages = p.n_stages;
     s.last_n_slices = p.n_slices;
+    s.last_fused = (p.fuse_merge ? 1u : 0u) | (p.prehash ? 2u : 0u);
     return 0;
 }
 
@@ -448,10 +504,13 @@ int bigsi_b200_index_create(int device, uint64_t num_rows, uint64_t num_cols, ui
         return fail_cuda(e, "cudaMalloc(matrix)");
     }
     e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = ix->d_barrier.reserve(256);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ix->d_barrier.p, 0, 256, ix->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(ix->matrix, 0, bytes, ix->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
     if (e != cudaSuccess) {
         cudaFree(ix->matrix);
+        ix->d_barrier.release();
         if (ix->stream) cudaStreamDestroy(ix->stream);
         delete ix;
         return fail_cuda(e, "index initialisation");
@@ -467,7 +526,7 @@ int bigsi_b200_index_destroy(bigsi_b200_index *ix)
     cudaDeviceSynchronize();
     for (auto &t : ix->timed_free) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
     for (auto &t : ix->timed_used) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
-    DevBuf *bufs[] = {&ix->debug_ts, &ix->partial, &ix->d_kmers, &ix->d_rows, &ix->d_qoff, &ix->d_out, &ix->d_min,
+    DevBuf *bufs[] = {&ix->d_barrier, &ix->debug_ts, &ix->partial, &ix->d_kmers, &ix->d_rows, &ix->d_qoff, &ix->d_out, &ix->d_min,
                       &ix->d_nhits, &ix->d_bloom, &ix->d_planted};
     for (DevBuf *b : bufs) b->release();
     ix->h_small.release();
@@ -508,6 +567,8 @@ int bigsi_b200_index_set_option(bigsi_b200_index *ix, const char *key, int64_t v
     else if (!strcmp(key, "ctas_per_sm")) ix->opt_ctas_per_sm = value;
     else if (!strcmp(key, "timing")) ix->timing = value != 0;
     else if (!strcmp(key, "debug_flags")) ix->opt_debug_flags = value;
+    else if (!strcmp(key, "prehash")) ix->opt_prehash = value;
+    else if (!strcmp(key, "fuse_merge")) ix->opt_fuse_merge = value;
     else return fail(BIGSI_B200_ERR_INVALID, "unknown option '%s'", key);
     return 0;
 }
@@ -702,8 +763,8 @@ int bigsi_b200_query_dev(bigsi_b200_index *ix, int mode, const int32_t *d_rows, 
     if (n_queries && (!d_q_offsets || !d_out)) return fail(BIGSI_B200_ERR_INVALID, "null device pointer");
     if (total_kmers && !d_rows) return fail(BIGSI_B200_ERR_INVALID, "null d_rows");
     DeviceGuard guard(ix->device);
-    return run_query(ix, mode, d_rows, d_q_offsets, n_queries, total_kmers, max_query_kmers, h, d_out, out_stride,
-                     static_cast<cudaStream_t>(stream));
+    return run_query(ix, mode, d_rows, nullptr, 0, d_q_offsets, n_queries, total_kmers, max_query_kmers, h, d_out,
+                     out_stride, static_cast<cudaStream_t>(stream));
 }
 
 int bigsi_b200_query_hits_dev(bigsi_b200_index *ix, const int32_t *d_rows, const int64_t *d_q_offsets,
@@ -723,8 +784,31 @@ int bigsi_b200_query_hits_dev(bigsi_b200_index *ix, const int32_t *d_rows, const
     ho.counts = d_counts_out;
     ho.n = reinterpret_cast<unsigned long long *>(d_n_out);
     ho.cap = cap;
-    return run_query(ix, BIGSI_B200_MODE_COUNTS, d_rows, d_q_offsets, n_queries, total_kmers, max_query_kmers, h,
-                     d_counts_full, counts_stride, static_cast<cudaStream_t>(stream), &ho);
+    return run_query(ix, BIGSI_B200_MODE_COUNTS, d_rows, nullptr, 0, d_q_offsets, n_queries, total_kmers, max_query_kmers,
+                     h, d_counts_full, counts_stride, static_cast<cudaStream_t>(stream), &ho);
+}
+
+int bigsi_b200_query_kmers_hits_dev(bigsi_b200_index *ix, const char *d_kmers, int k, const int64_t *d_q_offsets,
+                                    uint64_t n_queries, uint64_t total_kmers, uint64_t max_query_kmers, int h,
+                                    const uint32_t *d_min_kmers, int32_t *d_cols_out, uint32_t *d_counts_out,
+                                    uint64_t cap, uint64_t *d_n_out, uint32_t *d_counts_full, uint64_t counts_stride,
+                                    void *stream)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (n_queries == 0) return 0;
+    if (!d_q_offsets || !d_min_kmers || !d_n_out || (cap && (!d_cols_out || !d_counts_out)))
+        return fail(BIGSI_B200_ERR_INVALID, "null device pointer");
+    if (total_kmers && !d_kmers) return fail(BIGSI_B200_ERR_INVALID, "null d_kmers");
+    DeviceGuard guard(ix->device);
+    HitsOut ho;
+    ho.min_kmers = d_min_kmers;
+    ho.cols = d_cols_out;
+    ho.counts = d_counts_out;
+    ho.n = reinterpret_cast<unsigned long long *>(d_n_out);
+    ho.cap = cap;
+    return run_query(ix, BIGSI_B200_MODE_COUNTS, nullptr, total_kmers ? d_kmers : nullptr, k, d_q_offsets, n_queries,
+                     total_kmers, max_query_kmers, h, d_counts_full, counts_stride, static_cast<cudaStream_t>(stream),
+                     &ho);
 }
 
 int bigsi_b200_lookup_dev(bigsi_b200_index *ix, const int32_t *d_rows, uint64_t n_kmers, int h, uint8_t *d_out,
@@ -777,28 +861,29 @@ static int search_common(bigsi_b200_index *ix, int mode, const char *kmers, cons
     if (total && !kmers && !rows) return fail(BIGSI_B200_ERR_INVALID, "null query input");
     cudaError_t e;
     if ((e = ix->d_qoff.reserve((n_queries + 1) * 8)) != cudaSuccess) return fail_cuda(e, "staging");
-    if ((e = ix->d_rows.reserve(total * (uint64_t)h * 4 + 4)) != cudaSuccess) return fail_cuda(e, "staging");
     const uint64_t out_bytes = hits ? 0 : n_queries * out_stride * (mode == BIGSI_B200_MODE_COUNTS ? 4 : 1);
     if (!hits && (e = ix->d_out.reserve(out_bytes + 16)) != cudaSuccess) return fail_cuda(e, "staging");
     CK(cudaMemcpyAsync(ix->d_qoff.p, qoff, (n_queries + 1) * 8, cudaMemcpyHostToDevice, ix->stream));
+    const char *d_kmers = nullptr;
+    const int32_t *d_rows = nullptr;
     if (total) {
         if (kmers) {
             if (k < 1) return fail(BIGSI_B200_ERR_INVALID, "k must be >= 1");
-            if ((e = ix->d_kmers.reserve(total * (uint64_t)k)) != cudaSuccess) return fail_cuda(e, "staging");
+            if ((e = ix->d_kmers.reserve(total * (uint64_t)k + 32)) != cudaSuccess) return fail_cuda(e, "staging");
+            if ((e = ix->d_rows.reserve(total * (uint64_t)h * 4 + 4)) != cudaSuccess) return fail_cuda(e, "staging");
             CK(cudaMemcpyAsync(ix->d_kmers.p, kmers, total * (uint64_t)k, cudaMemcpyHostToDevice, ix->stream));
-            if (int rc = bigsi_b200_hash_kmers_dev(static_cast<const char *>(ix->d_kmers.p), total, k, h, ix->num_rows, 1,
-                                                   static_cast<int32_t *>(ix->d_rows.p), ix->stream))
-                return rc;
-            ix->kernel_launches++;
+            d_kmers = static_cast<const char *>(ix->d_kmers.p);  // hashed in-kernel when the plan allows
         } else {
             for (uint64_t i = 0; i < total * (uint64_t)h; ++i)
                 if (rows[i] < 0 || (uint64_t)rows[i] >= ix->num_rows)
                     return fail(BIGSI_B200_ERR_RANGE, "row id %d out of range at %llu", rows[i], (unsigned long long)i);
+            if ((e = ix->d_rows.reserve(total * (uint64_t)h * 4 + 4)) != cudaSuccess) return fail_cuda(e, "staging");
             CK(cudaMemcpyAsync(ix->d_rows.p, rows, total * (uint64_t)h * 4, cudaMemcpyHostToDevice, ix->stream));
+            d_rows = static_cast<const int32_t *>(ix->d_rows.p);
         }
     }
-    return run_query(ix, mode, static_cast<const int32_t *>(ix->d_rows.p), static_cast<const int64_t *>(ix->d_qoff.p),
-                     n_queries, total, longest, h, hits ? nullptr : ix->d_out.p, out_stride, ix->stream, hits);
+    return run_query(ix, mode, d_rows, d_kmers, k, static_cast<const int64_t *>(ix->d_qoff.p), n_queries, total, longest, h,
+                     hits ? nullptr : ix->d_out.p, out_stride, ix->stream, hits);
 }
 
 static int search_full(bigsi_b200_index *ix, int mode, const char *kmers, const int32_t *rows, const int64_t *qoff,

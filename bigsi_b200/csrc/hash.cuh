@@ -1,0 +1,118 @@
+// Canonical k-mer + MurmurHash3_x86_32 device code shared by the stand-alone hash kernel
+// (aux_kernels.cu) and by the prologue of the fused query kernel (query_kernels.cu).
+// Replaces convert_query_kmer/canonical (bigsi/utils/fncts.py:38-54) and _hash/generate_hashes
+// (bigsi/bloom/bloomfilter.py:5-13; third-party mmh3 2.5.1 = MurmurHash3_x86_32): seeds 0..h-1,
+// SIGNED 32-bit result, Python floor-mod m.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bigsi {
+
+__device__ __forceinline__ uint32_t comp_base(uint32_t b)
+{
+    // only A<->T and C<->G are complemented (utils/fncts.py:12); anything else passes through
+    return b == 'A' ? 'T' : b == 'T' ? 'A' : b == 'C' ? 'G' : b == 'G' ? 'C' : b;
+}
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
+
+__device__ __forceinline__ int32_t murmur_finish_mod(uint32_t h1, uint32_t len, uint32_t m)
+{
+    h1 ^= len;
+    h1 ^= h1 >> 16;
+    h1 *= 0x85ebca6bu;
+    h1 ^= h1 >> 13;
+    h1 *= 0xc2b2ae35u;
+    h1 ^= h1 >> 16;
+    // Python floor-mod of the SIGNED 32-bit hash (bloom/bloomfilter.py:5-6), in 32-bit arithmetic
+    if ((int32_t)h1 >= 0) return (int32_t)(h1 % m);
+    const uint32_t r = (0u - h1) % m;  // |s| mod m
+    return (int32_t)(r ? m - r : 0u);
+}
+__device__ __forceinline__ uint32_t murmur_block(uint32_t h1, uint32_t k1)
+{
+    k1 *= 0xcc9e2d51u;
+    k1 = rotl32(k1, 15);
+    k1 *= 0x1b873593u;
+    h1 ^= k1;
+    h1 = rotl32(h1, 13);
+    return h1 * 5u + 0xe6546b64u;
+}
+__device__ __forceinline__ uint32_t murmur_tail(uint32_t h1, uint32_t k1)
+{
+    k1 *= 0xcc9e2d51u;
+    k1 = rotl32(k1, 15);
+    k1 *= 0x1b873593u;
+    return h1 ^ k1;
+}
+
+// shared-memory scratch hash_kmers_cooperative needs for cnt k-mers of length k
+__host__ __device__ inline uint64_t hash_scratch_bytes(uint64_t cnt, uint32_t k)
+{
+    return cnt * ((uint64_t)k + 1 + 4ull * ((((uint64_t)k + 3) >> 2) | 1)) + 96;
+}
+
+// Block-cooperative hashing of cnt CONTIGUOUS k-mers starting at g0 (every thread of the CTA must
+// call it; contains __syncthreads).  (1) the bytes are staged in shared memory with one round trip
+// of 16-byte loads over the enclosing aligned window (the window leaves the k-mer array only
+// inside its first / last 16-byte line, which every CUDA allocation covers); (2) one thread per
+// k-mer decides the orientation; (3) one thread per (k-mer, 4-byte block) writes the canonical
+// bytes as little-endian words (zero padded, so the last word IS murmur's tail); (4) one thread per
+// (k-mer, seed) runs MurmurHash3 over those words and stores ids[km * h + seed].
+__device__ __forceinline__ void hash_kmers_cooperative(const uint8_t *g0, uint32_t cnt, int k, int h, uint32_t m,
+                                                       int canonical, uint8_t *scratch, int32_t *ids)
+{
+    const uint32_t nthreads = blockDim.x;
+    const int nblocks = k >> 2, rem = k & 3;
+    const uint32_t wpk = (uint32_t)(k + 3) >> 2;
+    const uint32_t wstride = wpk | 1;  // odd stride: conflict-free LDS across k-mers
+    const uint32_t raw_bytes = ((cnt * (uint32_t)k + 32) + 15) & ~15u;
+    uint8_t *fwd = scratch + raw_bytes;
+    uint32_t *cw = reinterpret_cast<uint32_t *>(scratch + raw_bytes + ((cnt + 15) & ~15u));
+    const uint32_t nbytes = cnt * (uint32_t)k;
+    const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15);
+    const uint4 *a0 = reinterpret_cast<const uint4 *>(g0 - skew);
+    const uint32_t nvec = (skew + nbytes + 15) >> 4;
+    uint4 *sv = reinterpret_cast<uint4 *>(scratch);
+    for (uint32_t i = threadIdx.x; i < nvec; i += nthreads) sv[i] = __ldg(a0 + i);
+    __syncthreads();
+    const uint8_t *src = scratch + skew;
+    for (uint32_t km = threadIdx.x; km < cnt; km += nthreads) {
+        const uint8_t *s = src + (size_t)km * k;
+        bool f = true;  // forward unless the reverse complement is lexicographically smaller
+        if (canonical) {
+            for (int j = 0; j < k; ++j) {
+                const uint32_t a = s[j], b = comp_base(s[k - 1 - j]);
+                if (a != b) {
+                    f = a < b;
+                    break;
+                }
+            }
+        }
+        fwd[km] = f ? 1 : 0;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < cnt * wpk; i += nthreads) {
+        const uint32_t km = i / wpk, wi = i % wpk;
+        const uint8_t *s = src + (size_t)km * k;
+        const bool f = fwd[km] != 0;
+        uint32_t word = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = (int)wi * 4 + u;
+            if (j < k) word |= (f ? (uint32_t)s[j] : comp_base(s[k - 1 - j])) << (8 * u);
+        }
+        cw[km * wstride + wi] = word;
+    }
+    __syncthreads();
+    for (uint32_t w = threadIdx.x; w < cnt * (uint32_t)h; w += nthreads) {
+        const uint32_t km = w / (uint32_t)h, seed = w % (uint32_t)h;
+        const uint32_t *wp = cw + km * wstride;
+        uint32_t h1 = seed;
+        for (int b = 0; b < nblocks; ++b) h1 = murmur_block(h1, wp[b]);
+        if (rem) h1 = murmur_tail(h1, wp[nblocks]);
+        ids[w] = murmur_finish_mod(h1, (uint32_t)k, m);
+    }
+}
+
+}  // namespace bigsi

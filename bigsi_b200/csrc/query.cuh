@@ -55,15 +55,32 @@ struct QueryParams {
     uint32_t *hit_counts;            // [n_queries][hit_cap]
     unsigned long long *n_hits;      // [n_queries] number of hits (may exceed hit_cap); zeroed by stage 1
     uint64_t hit_cap;
+    // optional in-kernel hashing: the CTA hashes its own (contiguous) k-mers in the prologue instead
+    // of reading row ids (needs n_tiles == 1 and slices_per_cta == 1)
+    const uint8_t *kmers;     // [total_kmers * k] raw ASCII k-mers, or null (then `rows` is used)
+    uint32_t k;
+    uint32_t num_rows;        // m
+    uint32_t prehash;         // 1: hash in the prologue into the shared-memory id table
+    uint32_t ids_bytes;       // size of that table (between the mbarriers and the ring)
+    // optional in-kernel merge: stage 2 runs inside stage 1 after a grid-wide barrier
+    uint32_t fuse_merge;
+    uint32_t merge_ng, merge_gpi;
+    uint64_t merge_items;
+    unsigned long long *barrier;        // monotonic arrival counter shared by all launches of a handle
+    unsigned long long barrier_target;  // value the counter reaches when every CTA of THIS launch arrived
     uint32_t debug_flags;     // bit 0: consumers skip the AND/count work (pure-gather ceiling measurement)
     unsigned long long *debug_ts;  // optional [grid][8] timeline stamps (globaltimer ns), see fused_query
 };
 
 inline uint32_t query_consumer_warps(const QueryParams &p) { return (p.tile_bytes + 511) / 512; }
 inline uint32_t query_block_threads(const QueryParams &p) { return (query_consumer_warps(p) + 1) * 32; }
+constexpr int kMergeScratchBytes = 16 * 16 * 32 * 4 + 256;  // == kMergeSmemBytes (merge.cuh)
+inline uint32_t query_ring_bytes(const QueryParams &p) { return p.n_stages * p.kmers_per_stage * p.h * p.tile_bytes; }
 inline uint32_t query_smem_bytes(const QueryParams &p)
 {
-    return kSmemHeaderBytes + p.n_stages * p.kmers_per_stage * p.h * p.tile_bytes;
+    uint32_t ring = query_ring_bytes(p);
+    if (p.fuse_merge && ring < (uint32_t)kMergeScratchBytes) ring = kMergeScratchBytes;  // the merge phase reuses the ring
+    return kSmemHeaderBytes + p.ids_bytes + ring;
 }
 inline uint64_t query_n_slots(const QueryParams &p)
 {
@@ -77,6 +94,8 @@ inline uint64_t query_partial_bytes(const QueryParams &p)
 
 // Stage 1: gather + AND + vertical count, per-segment bit planes -> p.partial.
 cudaError_t launch_query(const QueryParams &p, int mode, int grid, cudaStream_t stream);
+// shared-memory scratch the in-kernel hashing needs per k-mer (raw bytes + flag + canonical words)
+inline uint64_t prehash_bytes_per_kmer(uint32_t k) { return (uint64_t)k + 1 + 4ull * ((((uint64_t)k + 3) >> 2) | 1); }
 // Stage 2: sum (or AND) the partial planes of every (query, column), expand to integers -> p.out.
 cudaError_t launch_merge(const QueryParams &p, int mode, cudaStream_t stream);
 cudaError_t query_kernels_init();  // opt-in to large dynamic shared memory

@@ -21,7 +21,9 @@
 //
 // Stage 2 (merge_kernels.cu): per (query, tile, column chunk) counts the partial planes of all
 // segments vertically once more and expands them to uint32 counts (or ANDs the presence planes).
+#include "hash.cuh"
 #include "launch.cuh"
+#include "merge.cuh"
 #include "ptx.cuh"
 #include "query.cuh"
 
@@ -34,7 +36,7 @@ __device__ __forceinline__ unsigned long long gtime()
     return t;
 }
 // timeline slots per CTA: 0 entry, 1 producer first issue, 2 first slot landed, 3 last slot consumed,
-// 4 after flush, 5 producer last issue
+// 4 after flush, 5 producer last issue, 6 past the grid barrier, 7 merge phase done
 #define BIGSI_TS(slot)                                                            \
     do {                                                                          \
         if (P.debug_ts) P.debug_ts[(size_t)blockIdx.x * 8 + (slot)] = gtime();    \
@@ -195,8 +197,8 @@ __device__ __forceinline__ void flush_planes(const VCounter &c, uint32_t pps, ui
 // ------------------------------------------------------------------------------------------
 // stage 1: producer warp
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_producer(const QueryParams &P, uint8_t *ring, uint64_t *full, uint64_t *empty,
-                                             uint64_t begin, uint64_t end)
+__device__ __forceinline__ void tma_producer(const QueryParams &P, uint8_t *ring, const int32_t *ids, uint64_t *full,
+                                             uint64_t *empty, uint64_t begin, uint64_t end)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t h = P.h;
@@ -212,6 +214,7 @@ __device__ __forceinline__ void tma_producer(const QueryParams &P, uint8_t *ring
     // so the ids of the next >= 32 copies are always in registers before their ring slot frees up.
     auto load_id = [&](uint64_t c) -> int32_t {
         if (c >= n_copies) return 0;
+        if (P.prehash) return ids[c];  // hashed by this CTA in the prologue (shared memory)
         const uint64_t item = begin + c / h;
         const uint32_t j = (uint32_t)(c % h);
         const uint64_t kg = item % total;
@@ -343,13 +346,32 @@ __device__ __forceinline__ void tma_consumer(const QueryParams &P, const uint8_t
     }
 }
 
+// grid-wide barrier over a monotonic arrival counter (all CTAs of the launch are co-resident: the
+// kernel is launched cooperatively with at most one CTA per SM)
+__device__ __forceinline__ void grid_barrier(unsigned long long *counter, unsigned long long target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();  // publish this CTA's partial planes
+        atomicAdd(counter, 1ull);
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter) : "memory");
+            if (seen < target) __nanosleep(40);
+        } while (seen < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 template <int MODE, int HC>
 __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_constant__ QueryParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty = full + kMaxStages;
-    uint8_t *ring = smem + kSmemHeaderBytes;
+    int32_t *ids = reinterpret_cast<int32_t *>(smem + kSmemHeaderBytes);
+    uint8_t *ring = smem + kSmemHeaderBytes + P.ids_bytes;
     const uint32_t consumer_warps = (blockDim.x >> 5) - 1;
 
     if (threadIdx.x == 0) {
@@ -362,7 +384,7 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
     }
     __syncthreads();
     // PDL: everything above overlapped the previous kernel's tail; from here on we read what it
-    // produced (row ids) and overwrite what the previous query's merge may still read (partials)
+    // produced (k-mers / row ids) and overwrite what the previous query's merge may still read
     grid_launch_dependents();
     grid_dependency_wait();
 
@@ -374,12 +396,39 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
     const uint64_t begin = (uint64_t)blockIdx.x * span;
     uint64_t end = begin + span;
     if (end > P.total_items) end = P.total_items;
-    if (begin >= end) return;
+    const bool have_work = begin < end;
 
-    if ((threadIdx.x >> 5) == consumer_warps)
-        tma_producer(P, ring, full, empty, begin, end);
-    else
-        tma_consumer<MODE, HC>(P, ring, full, empty, begin, end);
+    if (P.prehash && have_work) {
+        // n_tiles == 1 and one slice per CTA: this CTA's k-mers are [begin, end), contiguous in memory.
+        // The (still empty) ring is the scratch; the ids land in their own table in front of it.
+        hash_kmers_cooperative(P.kmers + begin * P.k, (uint32_t)(end - begin), (int)P.k, (int)P.h, P.num_rows, 1, ring,
+                               ids);
+        fence_proxy_async();  // generic-proxy writes to the ring are ordered before the TMA writes
+        __syncthreads();
+    }
+
+    if (have_work) {
+        if ((threadIdx.x >> 5) == consumer_warps)
+            tma_producer(P, ring, ids, full, empty, begin, end);
+        else
+            tma_consumer<MODE, HC>(P, ring, full, empty, begin, end);
+    }
+
+    if (P.fuse_merge) {
+        // stage 2 in the same kernel: once every CTA has published its planes, the CTAs share the
+        // merge work items; the drained ring is the scratch
+        grid_barrier(P.barrier, P.barrier_target);
+        if (threadIdx.x == 0) BIGSI_TS(6);
+        for (uint64_t item = blockIdx.x; item < P.merge_items; item += gridDim.x) {
+            if (MODE == kModeCounts) {
+                if (P.merge_ng == 1) merge_counts_item<1>(P, item, P.merge_gpi, ring);
+                else merge_counts_item<4>(P, item, P.merge_gpi, ring);
+            } else {
+                merge_and_item(P, item, ring);
+            }
+        }
+        if (threadIdx.x == 0) BIGSI_TS(7);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -388,7 +437,8 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
 template <int MODE, int HC>
 static cudaError_t launch_one(const QueryParams &p, int grid, cudaStream_t stream)
 {
-    return launch_pdl(fused_query<MODE, HC>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream, p);
+    return launch_ex(fused_query<MODE, HC>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream,
+                     /*pdl=*/true, /*cooperative=*/p.fuse_merge != 0, p);
 }
 
 cudaError_t launch_query(const QueryParams &p, int mode, int grid, cudaStream_t stream)

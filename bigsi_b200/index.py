@@ -195,6 +195,12 @@ class DeviceIndex:
                                                 max_query_kmers, h, d_min_kmers, d_cols_out, d_counts_out, cap,
                                                 d_n_out, d_counts_full, counts_stride, stream))
 
+    def query_kmers_hits_dev(self, d_kmers, k, d_q_offsets, n_queries, total_kmers, h, d_min_kmers, d_cols_out,
+                             d_counts_out, cap, d_n_out, stream=0, max_query_kmers=0, d_counts_full=0, counts_stride=0):
+        check(self._L.bigsi_b200_query_kmers_hits_dev(self.handle, d_kmers, k, d_q_offsets, n_queries, total_kmers,
+                                                      max_query_kmers, h, d_min_kmers, d_cols_out, d_counts_out, cap,
+                                                      d_n_out, d_counts_full, counts_stride, stream))
+
     def lookup_dev(self, d_rows, n_kmers, h, d_out, out_stride, stream=0):
         check(self._L.bigsi_b200_lookup_dev(self.handle, d_rows, n_kmers, h, d_out, out_stride, stream))
 

@@ -4,7 +4,8 @@ The reference has no distributed path; every sample colu
 in both the AND and the count (bigsi/graph/index.py:42-80, graph/bigsi.py:192-230), so rank g
 holds all m rows of the columns [g*N/G, (g+1)*N/G) and a query needs exactly two small exchanges:
 
-  1. broadcast of the query's row ids (int32 [U*h]) from rank 0,
+  1. broadcast of the query (raw k-mer bytes uint8 [U*k]; the row ids int32 [U*h] are derived from
+     them identically on every rank, inside the query kernel) from rank 0,
   2. all-gather of the per-shard hits (count + compact (colour, count) pairs) or counts.
 
 torch.distributed is the plumbing (NCCL on the GPU box, gloo in the CPU tests); the local shard
@@ -109,6 +110,20 @@ class DeviceShard:
         return buf
 
 
+    def search_kmers_hits(self, kmers_u8, q_offsets, n_queries, min_kmers, max_query_kmers=0):
+        """The whole path in (normally) one kernel: raw k-mers uint8 [U, k] on the device ->
+        canonical + murmur3 in the kernel prologue -> gather-AND-count -> grid barrier -> merge +
+        threshold.  Same packed layout as hits()."""
+        t = self.torch
+        buf = t.empty((n_queries * (2 + 2 * self.cap),), dtype=t.int32, device=self.device)
+        base = buf.data_ptr()
+        self.index.query_kmers_hits_dev(kmers_u8.data_ptr(), self.k, q_offsets.data_ptr(), n_queries, kmers_u8.shape[0],
+                                        self.h, min_kmers.data_ptr(), base + 8 * n_queries,
+                                        base + 8 * n_queries + 4 * n_queries * self.cap, self.cap, base, self._stream(),
+                                        max_query_kmers)
+        return buf
+
+
 def unpack_hits(buf, n_queries, cap):
     """Inverse of DeviceShard.hits' packing for a [G, Q*(2+2*cap)] (or 1-D) int32 array on the host."""
     a = np.asarray(buf).reshape(-1, n_queries * (2 + 2 * cap))
@@ -135,14 +150,13 @@ class ShardedSearcher:
         int32 [G, Q*(2+2*cap)] on the device (see DeviceShard.hits / unpack_hits; LOCAL colours)."""
         t = self.torch
         sh = self.shard
-        U = kmers_u8.shape[0]
-        if self.rank == 0:
-            rows = sh.hash(kmers_u8)
-        else:
-            rows = t.empty((U, sh.h), dtype=t.int32, device=sh.device)
         if self.dist is not None:
-            self.dist.broadcast(rows, src=0)  # exchange 1: row ids
-        packed = sh.search_hits(rows, q_offsets, n_queries, min_kmers, max_query_kmers)
+            # exchange 1: the query itself (raw k-mer bytes; every rank derives the same row ids from
+            # them inside its own kernel, so the ranks stay symmetric and rank 0 runs no extra kernel)
+            if self.rank != 0:
+                kmers_u8 = t.empty_like(kmers_u8)
+            self.dist.broadcast(kmers_u8, src=0)
+        packed = sh.search_kmers_hits(kmers_u8, q_offsets, n_queries, min_kmers, max_query_kmers)
         if self.dist is None:
             return packed[None]
         gathered = t.empty((self.world_size, packed.shape[0]), dtype=packed.dtype, device=sh.device)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BIGSI_B200_ABI_VERSION 2
+#define BIGSI_B200_ABI_VERSION 3
 
 enum {
     BIGSI_B200_OK = 0,
@@ -63,6 +63,8 @@ typedef struct {
     uint32_t last_tile_bytes, last_n_tiles, last_kmers_per_stage, last_n_stages, last_n_slices;
     uint64_t kernel_launches;        /* cumulative count of kernels this handle has launched          */
     uint64_t scratch_bytes;          /* partial-plane workspace currently allocated                   */
+    uint32_t last_fused;             /* bit 0: merge ran inside the fused kernel, bit 1: k-mers hashed in it */
+    uint32_t reserved;
 } bigsi_b200_info;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -82,7 +84,8 @@ int bigsi_b200_index_destroy(bigsi_b200_index *index); /* storage.delete_all()/c
 int bigsi_b200_index_get_info(const bigsi_b200_index *index, bigsi_b200_info *info_out);
 
 /* Tuning / instrumentation knobs (value 0 = automatic): "tile_bytes", "grid", "kmers_per_stage",
- * "n_stages", "ctas_per_sm", "debug_flags"; "timing" (1 = bracket the fused kernel and the merge kernel of
+ * "n_stages", "ctas_per_sm", "debug_flags"; "prehash" / "fuse_merge" (default 1; 0 forces the
+ * separate hash / merge kernels); "timing" (1 = bracket the fused kernel and the merge kernel of
  * every query launch with CUDA events, read back with bigsi_b200_index_timing_collect). */
 int bigsi_b200_index_set_option(bigsi_b200_index *index, const char *key, int64_t value);
 /* Synchronises, sums the event-timed durations recorded since the last collect and resets them.
@@ -143,6 +146,16 @@ int bigsi_b200_query_hits_dev(bigsi_b200_index *index, const int32_t *d_rows, co
                               const uint32_t *d_min_kmers, int32_t *d_cols_out, uint32_t *d_counts_out,
                               uint64_t cap, uint64_t *d_n_out, uint32_t *d_counts_full, uint64_t counts_stride,
                               void *stream);
+
+/* The whole search path of a batch in (normally) ONE kernel: raw unique k-mers (n*k ASCII, device)
+ * are canonicalised and hashed in the kernel prologue, rows gathered/ANDed/counted, and after a
+ * grid-wide barrier the same kernel merges and thresholds.  Falls back to hash kernel + fused kernel
+ * + merge kernel when the launch geometry does not allow it.  Outputs as bigsi_b200_query_hits_dev. */
+int bigsi_b200_query_kmers_hits_dev(bigsi_b200_index *index, const char *d_kmers, int k, const int64_t *d_q_offsets,
+                                    uint64_t n_queries, uint64_t total_kmers, uint64_t max_query_kmers, int h,
+                                    const uint32_t *d_min_kmers, int32_t *d_cols_out, uint32_t *d_counts_out,
+                                    uint64_t cap, uint64_t *d_n_out, uint32_t *d_counts_full,
+                                    uint64_t counts_stride, void *stream);
 
 /* Per-k-mer AND vectors (KmerSignatureIndex.lookup: graph/index.py:42-49,75-80): d_out =
  * uint8 [n_kmers][out_stride], out_stride >= row_bytes. */

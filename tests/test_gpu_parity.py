@@ -139,6 +139,7 @@ def test_ragged_batch_with_empty_queries(B):
 @pytest.mark.parametrize("opts", [
     {"tile_bytes": 16}, {"tile_bytes": 48, "kmers_per_stage": 1}, {"tile_bytes": 512, "kmers_per_stage": 4, "n_stages": 2},
     {"grid": 1}, {"grid": 3, "tile_bytes": 128}, {"grid": 1000}, {"kmers_per_stage": 8, "n_stages": 3},
+    {"fuse_merge": 0}, {"fuse_merge": 0, "tile_bytes": 64}, {"fuse_merge": 0, "grid": 5}, {"grid": 148, "tile_bytes": 32},
 ])
 def test_launch_geometry_overrides(B, opts):
     rng = np.random.default_rng(3)
@@ -424,6 +425,15 @@ def test_device_pointer_path_fused_threshold(B):
     n2, c2, v2 = unpack_hits(shard.search_hits(rows, d_q, 4, d_min, max(lens)).cpu().numpy(), 4, 512)
     g = ShardedSearcher(shard).search_step(d_k, d_q, d_min, 4, max(lens))
     n3, c3, v3 = unpack_hits(g.cpu().numpy(), 4, 512)
+    assert ix.info()["last_fused"] & 1  # merge ran inside the fused kernel
+    # the same through the separate hash / merge kernels
+    ix.set_option("fuse_merge", 0)
+    ix.set_option("prehash", 0)
+    n4, c4, v4 = unpack_hits(shard.search_kmers_hits(d_k, d_q, 4, d_min, max(lens)).cpu().numpy(), 4, 512)
+    assert ix.info()["last_fused"] == 0
+    ix.set_option("fuse_merge", 1)
+    ix.set_option("prehash", 1)
+    assert np.array_equal(n3, n4)
     torch.cuda.synchronize()
     for q in range(4):
         sl = slice(qoff[q], qoff[q + 1])

@@ -28,25 +28,27 @@ shard = DeviceShard(ix, K, H)
 dev = shard.device
 rng = np.random.default_rng(0)
 acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
-rows = [shard.hash(torch.from_numpy(acgt[rng.integers(0, 4, size=(args.kmers, K))]).to(dev)) for _ in range(16)]
+kms = [torch.from_numpy(acgt[rng.integers(0, 4, size=(args.kmers, K))]).to(dev) for _ in range(16)]
+d_min = torch.tensor([args.kmers], dtype=torch.int32, device=dev)
 d_q = torch.tensor([0, args.kmers], dtype=torch.int64, device=dev)
 out = torch.empty((1, args.cols + 64), dtype=torch.int32, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 ix.set_option("debug_flags", args.flags)
-names = ["entry", "prod_first_issue", "first_slot_landed", "last_slot_consumed", "flushed", "prod_last_issue"]
+names = ["entry", "prod_first_issue", "first_slot_landed", "last_slot_consumed", "flushed", "prod_last_issue",
+         "past_grid_barrier", "merge_done"]
 for rep in range(6):
-    ix.query_dev(0, rows[rep].data_ptr(), d_q.data_ptr(), 1, args.kmers, H, out.data_ptr(), out.shape[1], st, args.kmers)
+    shard.search_kmers_hits(kms[rep], d_q, 1, d_min, args.kmers)
     torch.cuda.synchronize()
     grid = ix.info()["last_grid"]
     buf = np.zeros(grid * 8, dtype=np.uint64)
     _lib.check(_lib.lib().bigsi_b200_index_debug_read(ix.handle, ctypes.c_void_p(buf.ctypes.data), buf.size))
     ts = buf.reshape(grid, 8).astype(np.int64)
     t0 = ts[:, 0].min()
-    rel = (ts[:, :6] - t0) / 1e3
+    rel = (ts[:, :8] - t0) / 1e3
     if rep < 2:
         continue
     print("launch %d: grid=%d  (microseconds since the first CTA entered the kernel; min / median / max over CTAs)" % (rep, grid))
     for i, n in enumerate(names):
         col = rel[:-1, i]  # the last CTA may hold a short remainder slice
         print("  %-20s %7.2f %7.2f %7.2f" % (n, col.min(), np.median(col), col.max()))
-    print("  kernel span (first entry -> last flush): %.2f us" % rel[:, 4].max())
+    print("  kernel span (first entry -> last flush): %.2f us; -> merge done: %.2f us" % (rel[:, 4].max(), rel[:, 7].max()))
