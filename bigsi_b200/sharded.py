@@ -159,9 +159,9 @@ class ShardedSearcher:
         packed = sh.search_kmers_hits(kmers_u8, q_offsets, n_queries, min_kmers, max_query_kmers)
         if self.dist is None:
             return packed[None]
-        gathered = t.empty((self.world_size, packed.shape[0]), dtype=packed.dtype, device=sh.device)
+        gathered = t.empty((self.world_size * packed.shape[0],), dtype=packed.dtype, device=sh.device)
         self.dist.all_gather_into_tensor(gathered, packed)  # exchange 2: per-shard hits
-        return gathered
+        return gathered.view(self.world_size, packed.shape[0])
 
     def to_global(self, gathered, n_queries, col_offsets, q=0):
         """Host-side merge of one query's gathered hits into global ascending colours."""
