@@ -176,8 +176,8 @@ __device__ __forceinline__ void merge_counts_item(const QueryParams &P, uint64_t
     if (in_range) {
         // expansion: one column per thread and pass
         uint32_t *out = P.out ? reinterpret_cast<uint32_t *>(P.out) + (uint64_t)G.q * P.out_stride : nullptr;
-        const bool thresholding = P.min_kmers != nullptr;
-        const uint32_t thr = thresholding ? __ldg(P.min_kmers + G.q) : 0u;
+        const bool thresholding = P.min_kmers != nullptr || P.min_by_value;
+        const uint32_t thr = P.min_by_value ? P.min_kmers_value : (thresholding ? __ldg(P.min_kmers + G.q) : 0u);
         const uint32_t col_base = (G.tb0 + G.cb) * 8;
         const uint32_t ncols_here = min(wpi * 32u, (G.tw - G.cb) * 8u);  // never past this tile
         for (uint32_t c0 = 0; c0 < ncols_here; c0 += blockDim.x) {

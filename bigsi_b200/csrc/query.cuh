@@ -16,6 +16,7 @@ constexpr int kSmemBudget = 227 * 1024;
 constexpr uint32_t kMaxSliceItems = 65535;                      // a segment's count fits 16 bit planes
 constexpr int kSegPlanes = 16;
 constexpr int kMaxH = 1024;
+constexpr int kMaxSinks = 9;   // host + up to 8 GPUs of one box
 
 enum { kModeCounts = 0, kModeAnd = 1 };
 
@@ -68,6 +69,22 @@ struct QueryParams {
     uint64_t merge_items;
     unsigned long long *barrier;        // monotonic arrival counter shared by all launches of a handle
     unsigned long long barrier_target;  // value the counter reaches when every CTA of THIS launch arrived
+    // single-query extras ------------------------------------------------------------------------
+    uint32_t min_by_value;    // 1: threshold = min_kmers_value (no device array to read)
+    uint32_t min_kmers_value;
+    // input gate: spin until *wait_flag >= wait_value before the k-mers are read (the query may live in
+    // a peer GPU's or the host's memory and be published there by somebody else)
+    const unsigned long long *wait_flag;
+    unsigned long long wait_value;
+    // result publication: after the merge phase the LAST CTA copies the hit list of query 0 to every
+    // sink -- a block [0] = sequence flag, [1] = number of hits, then int32 cols[sink_spec], uint32
+    // counts[sink_spec] -- in this GPU's, a peer GPU's (NVLink) or the host's (mapped pinned) memory
+    uint32_t n_sinks;
+    uint32_t sink_spec;
+    unsigned long long sink_seq;
+    unsigned long long *sinks[kMaxSinks];
+    unsigned long long *done_counter;   // monotonic; the CTA that brings it to done_target is the last
+    unsigned long long done_target;
     uint32_t debug_flags;     // bit 0: consumers skip the AND/count work (pure-gather ceiling measurement)
     unsigned long long *debug_ts;  // optional [grid][8] timeline stamps (globaltimer ns), see fused_query
 };

@@ -398,6 +398,16 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
     if (end > P.total_items) end = P.total_items;
     const bool have_work = begin < end;
 
+    if (P.wait_flag != nullptr) {  // the query is published by another GPU / the host: wait for it
+        if (threadIdx.x == 0) {
+            unsigned long long seen;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(P.wait_flag) : "memory");
+            } while (seen < P.wait_value);
+        }
+        __syncthreads();
+    }
+
     if (P.prehash && have_work) {
         // n_tiles == 1 and one slice per CTA: this CTA's k-mers are [begin, end), contiguous in memory.
         // The (still empty) ring is the scratch; the ids land in their own table in front of it.
@@ -428,6 +438,38 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
             }
         }
         if (threadIdx.x == 0) BIGSI_TS(7);
+
+        if (P.n_sinks) {
+            // the last CTA to finish its merge items publishes query 0's hit list to every sink
+            __shared__ int s_last;
+            if (threadIdx.x == 0) {
+                __threadfence();
+                s_last = atomicAdd(P.done_counter, 1ull) + 1ull == P.done_target;
+            }
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                const unsigned long long n = *reinterpret_cast<volatile unsigned long long *>(P.n_hits);
+                unsigned long long m = n < P.hit_cap ? n : P.hit_cap;
+                if (m > P.sink_spec) m = P.sink_spec;
+                for (uint32_t sidx = 0; sidx < P.n_sinks; ++sidx) {
+                    int32_t *dc = reinterpret_cast<int32_t *>(P.sinks[sidx] + 2);
+                    uint32_t *dv = reinterpret_cast<uint32_t *>(dc + P.sink_spec);
+                    for (uint32_t i = threadIdx.x; i < (uint32_t)m; i += blockDim.x) {
+                        dc[i] = __ldcg(P.hit_cols + i);
+                        dv[i] = __ldcg(P.hit_counts + i);
+                    }
+                }
+                __threadfence_system();
+                __syncthreads();
+                if (threadIdx.x < P.n_sinks) {
+                    volatile unsigned long long *blk = P.sinks[threadIdx.x];
+                    blk[1] = n;
+                    __threadfence_system();
+                    blk[0] = P.sink_seq;  // the flag goes last
+                }
+            }
+        }
     }
 }
 
