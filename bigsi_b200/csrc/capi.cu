@@ -136,7 +136,9 @@ struct bigsi_b200_index {
     int64_t opt_tile_bytes = 0, opt_grid = 0, opt_kmers_per_stage = 0, opt_n_stages = 0, opt_ctas_per_sm = 0;
     bool timing = false;
     int64_t opt_debug_flags = 0;
-    int64_t opt_prehash = 1, opt_fuse_merge = 1;  // in-kernel hashing / in-kernel merge (1 = when possible)
+    int64_t opt_prehash = 1, opt_fuse_merge = 1, opt_merge_chunk_bytes = 0, opt_solo = 1, opt_pool_pct = 12;
+    DevBuf d_pool;            // pool ids / ready flags / claim counter of the solo path
+    uint64_t pool_epoch = 0;  // in-kernel hashing / in-kernel merge (1 = when possible)
     DevBuf d_barrier;                             // grid-barrier arrival counter of the fused kernel
     uint64_t barrier_target = 0;
     // scratch
@@ -232,15 +234,17 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
     p.planes_per_slot = mode == BIGSI_B200_MODE_COUNTS ? (bits_of(seg_max) ? bits_of(seg_max) : 1) : 1;
 
     // in-kernel hashing: every CTA hashes its own contiguous k-mers in the prologue (one tile, one
-    // slice per CTA, and the id table + staging scratch must fit beside a useful ring)
+    // slice per CTA, and the id table + hashing scratch must fit beside a useful ring)
     p.prehash = 0;
     p.ids_bytes = 0;
+    p.ids_table_bytes = 0;
     if (have_kmers && grid > 0 && ix->opt_prehash != 0 && p.n_tiles == 1 && p.slices_per_cta == 1 && k >= 1) {
-        const uint64_t ids_bytes = round_up((uint64_t)p.items_per_slice * h * 4, 128);
-        const uint64_t scratch = hash_scratch_bytes(p.items_per_slice, (uint32_t)k);
-        if (ids_bytes <= 16384 && ids_bytes + scratch <= smem_avail && ids_bytes + 3ull * h * tile <= smem_avail) {
+        const uint64_t table = round_up((uint64_t)p.items_per_slice * h * 4, 128);
+        const uint64_t scratch = round_up(hash_scratch_bytes(p.items_per_slice, (uint32_t)k) + 256, 128);
+        if (table <= 16384 && table + scratch + 3ull * h * tile <= smem_avail) {
             p.prehash = 1;
-            p.ids_bytes = (uint32_t)ids_bytes;
+            p.ids_table_bytes = (uint32_t)table;
+            p.ids_bytes = (uint32_t)(table + scratch);
             p.k = (uint32_t)k;
         }
     }
@@ -268,13 +272,37 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
 
     // in-kernel merge: needs every CTA resident at once (one CTA per SM, grid <= SM count)
     p.fuse_merge = 0;
-    if (ix->opt_fuse_merge != 0 && grid > 0 && grid <= ix->sm_count) {
+    if (ix->opt_fuse_merge != 0 && grid > 0 && grid <= ix->sm_count &&
+        kSmemHeaderBytes + p.ids_bytes + (uint64_t)kMergeScratchBytes <= (uint64_t)kSmemBudget)
         p.fuse_merge = 1;
-        const MergePlan m = plan_merge(p, mode, query_block_threads(p));
-        p.merge_ng = (uint32_t)m.ng;
-        p.merge_gpi = m.gpi;
-        p.merge_items = m.n_items;
-        if (kSmemHeaderBytes + p.ids_bytes + (uint64_t)kMergeScratchBytes > (uint64_t)kSmemBudget) p.fuse_merge = 0;
+    // solo path: one query, hashed and merged in the kernel; a share of every CTA's k-mers goes to a
+    // pool that is drained dynamically (tail balance)
+    p.solo = 0;
+    p.pool_share = 0;
+    p.solo_max_kmers = 0xffffffffu;
+    if (p.prehash && p.fuse_merge && n_queries == 1 && ix->opt_solo != 0) {
+        p.solo = 1;
+        const uint64_t c = p.items_per_slice;
+        uint64_t pp = (c >= 16 && h <= kPoolMaxH) ? (c * (uint64_t)ix->opt_pool_pct + 50) / 100 : 0;
+        if (pp > c) pp = c;
+        if (mode == BIGSI_B200_MODE_COUNTS && pp) {
+            uint32_t pps = bits_of(c + 2 * pp);
+            if (pps > (uint32_t)kSegPlanes) {  // cannot widen the segment counters: keep the static split
+                pp = 0;
+            } else {
+                p.planes_per_slot = pps;
+                p.solo_max_kmers = (1u << pps) - 1;
+            }
+        }
+        p.pool_share = (uint32_t)pp;
+    }
+    // merge geometry; it fixes the chunk-major layout of the partial planes, so stage 1 needs it as well
+    p.n_slots_total = query_n_slots(p);
+    if (p.fuse_merge) {
+        const uint32_t scratch = query_smem_bytes(p) - kSmemHeaderBytes - p.ids_bytes;  // the drained ring
+        plan_merge(p, mode, scratch, (uint64_t)grid, (uint32_t)ix->opt_merge_chunk_bytes);
+    } else {
+        plan_merge(p, mode, kMergeKernelSmem, (uint64_t)ix->sm_count * 3, (uint32_t)ix->opt_merge_chunk_bytes);
     }
     return 0;
 }
@@ -327,7 +355,7 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
     p.out_stride = out_stride;
     p.debug_flags = (uint32_t)ix->opt_debug_flags;
     if (p.debug_flags & 2u) {  // timeline stamps of the LAST launch, fetched with bigsi_b200_index_debug_read
-        cudaError_t de = ix->debug_ts.reserve((uint64_t)(grid > 0 ? grid : 1) * 64);
+        cudaError_t de = ix->debug_ts.reserve((uint64_t)(grid > 0 ? grid : 1) * kDebugStamps * 8);
         if (de != cudaSuccess) return fail_cuda(de, "debug buffer");
         p.debug_ts = static_cast<unsigned long long *>(ix->debug_ts.p);
     }
@@ -347,6 +375,23 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
         if (e != cudaSuccess) return fail_cuda(e, "partial-plane workspace");
     }
     p.partial = static_cast<uint8_t *>(ix->partial.p);
+    if (p.solo) {
+        // [claim counter + padding: 256 B][ready flags: grid x u64][ids: grid x pool_share x h x i32]
+        const uint64_t flags_bytes = round_up((uint64_t)grid * 8, 256);
+        const uint64_t need_pool = 256 + flags_bytes + (uint64_t)grid * p.pool_share * h * 4 + 16;
+        if (need_pool > ix->d_pool.cap) {
+            CK(cudaStreamSynchronize(stream));
+            cudaError_t e = ix->d_pool.reserve(need_pool);
+            if (e != cudaSuccess) return fail_cuda(e, "pool workspace");
+            CK(cudaMemsetAsync(ix->d_pool.p, 0, ix->d_pool.cap, stream));
+            ix->pool_epoch = 0;
+        }
+        uint8_t *pb = static_cast<uint8_t *>(ix->d_pool.p);
+        p.pool_counter = reinterpret_cast<unsigned int *>(pb);
+        p.pool_ready = reinterpret_cast<unsigned long long *>(pb + 256);
+        p.pool_ids = reinterpret_cast<int32_t *>(pb + 256 + flags_bytes);
+        p.pool_epoch = ++ix->pool_epoch;
+    }
     if (p.fuse_merge) {
         p.barrier = static_cast<unsigned long long *>(ix->d_barrier.p);
         ix->barrier_target += (uint64_t)grid;
@@ -394,7 +439,7 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
     s.last_kmers_per_stage = p.kmers_per_stage;
     s.last_n_stages = p.n_stages;
     s.last_n_slices = p.n_slices;
-    s.last_fused = (p.fuse_merge ? 1u : 0u) | (p.prehash ? 2u : 0u);
+    s.last_fused = (p.fuse_merge ? 1u : 0u) | (p.prehash ? 2u : 0u) | (p.solo ? 4u : 0u);
     return 0;
 }
 
@@ -526,7 +571,7 @@ int bigsi_b200_index_destroy(bigsi_b200_index *ix)
     cudaDeviceSynchronize();
     for (auto &t : ix->timed_free) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
     for (auto &t : ix->timed_used) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
-    DevBuf *bufs[] = {&ix->d_barrier, &ix->debug_ts, &ix->partial, &ix->d_kmers, &ix->d_rows, &ix->d_qoff, &ix->d_out, &ix->d_min,
+    DevBuf *bufs[] = {&ix->d_pool, &ix->d_barrier, &ix->debug_ts, &ix->partial, &ix->d_kmers, &ix->d_rows, &ix->d_qoff, &ix->d_out, &ix->d_min,
                       &ix->d_nhits, &ix->d_bloom, &ix->d_planted};
     for (DevBuf *b : bufs) b->release();
     ix->h_small.release();
@@ -569,6 +614,9 @@ int bigsi_b200_index_set_option(bigsi_b200_index *ix, const char *key, int64_t v
     else if (!strcmp(key, "debug_flags")) ix->opt_debug_flags = value;
     else if (!strcmp(key, "prehash")) ix->opt_prehash = value;
     else if (!strcmp(key, "fuse_merge")) ix->opt_fuse_merge = value;
+    else if (!strcmp(key, "merge_chunk_bytes")) ix->opt_merge_chunk_bytes = value;
+    else if (!strcmp(key, "solo")) ix->opt_solo = value;
+    else if (!strcmp(key, "pool_pct")) ix->opt_pool_pct = value > 100 ? 100 : value;
     else return fail(BIGSI_B200_ERR_INVALID, "unknown option '%s'", key);
     return 0;
 }

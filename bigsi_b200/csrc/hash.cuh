@@ -52,17 +52,33 @@ __host__ __device__ inline uint64_t hash_scratch_bytes(uint64_t cnt, uint32_t k)
     return cnt * ((uint64_t)k + 1 + 4ull * ((((uint64_t)k + 3) >> 2) | 1)) + 96;
 }
 
-// Block-cooperative hashing of cnt CONTIGUOUS k-mers starting at g0 (every thread of the CTA must
-// call it; contains __syncthreads).  (1) the bytes are staged in shared memory with one round trip
-// of 16-byte loads over the enclosing aligned window (the window leaves the k-mer array only
-// inside its first / last 16-byte line, which every CUDA allocation covers); (2) one thread per
-// k-mer decides the orientation; (3) one thread per (k-mer, 4-byte block) writes the canonical
-// bytes as little-endian words (zero padded, so the last word IS murmur's tail); (4) one thread per
-// (k-mer, seed) runs MurmurHash3 over those words and stores ids[km * h + seed].
-__device__ __forceinline__ void hash_kmers_cooperative(const uint8_t *g0, uint32_t cnt, int k, int h, uint32_t m,
-                                                       int canonical, uint8_t *scratch, int32_t *ids)
+// Synchronisation policies of a hashing group: the whole CTA, a subset of warps on a named
+// barrier, or one warp.
+struct SyncBlock {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+struct SyncNamed {
+    int id, nthreads;  // nthreads: a multiple of 32, every thread of the group calls
+    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+};
+struct SyncWarp {
+    __device__ __forceinline__ void operator()() const { __syncwarp(); }
+};
+
+// Group-cooperative hashing of cnt CONTIGUOUS k-mers starting at g0: thread `tid` of a group of
+// `nthreads` threads that synchronise with `sync` (every thread of the group must call; contains
+// group barriers).  (1) the bytes are staged in shared memory with one round trip of 16-byte loads
+// over the enclosing aligned window (the window leaves the k-mer array only inside its first / last
+// 16-byte line, which every CUDA allocation covers); (2) one thread per k-mer decides the
+// orientation; (3) one thread per (k-mer, 4-byte block) writes the canonical bytes as little-endian
+// words (zero padded, so the last word IS murmur's tail); (4) one thread per (k-mer, seed) runs
+// MurmurHash3 over those words and stores ids[km * h + seed].  `scratch` (16-byte aligned,
+// hash_scratch_bytes(cnt, k) bytes) and `ids` may be shared or global memory.
+template <typename Sync>
+__device__ __forceinline__ void hash_kmers_group(const uint8_t *g0, uint32_t cnt, int k, int h, uint32_t m, int canonical,
+                                                 uint8_t *scratch, int32_t *ids, uint32_t tid, uint32_t nthreads,
+                                                 const Sync &sync)
 {
-    const uint32_t nthreads = blockDim.x;
     const int nblocks = k >> 2, rem = k & 3;
     const uint32_t wpk = (uint32_t)(k + 3) >> 2;
     const uint32_t wstride = wpk | 1;  // odd stride: conflict-free LDS across k-mers
@@ -74,10 +90,10 @@ __device__ __forceinline__ void hash_kmers_cooperative(const uint8_t *g0, uint32
     const uint4 *a0 = reinterpret_cast<const uint4 *>(g0 - skew);
     const uint32_t nvec = (skew + nbytes + 15) >> 4;
     uint4 *sv = reinterpret_cast<uint4 *>(scratch);
-    for (uint32_t i = threadIdx.x; i < nvec; i += nthreads) sv[i] = __ldg(a0 + i);
-    __syncthreads();
+    for (uint32_t i = tid; i < nvec; i += nthreads) sv[i] = __ldg(a0 + i);
+    sync();
     const uint8_t *src = scratch + skew;
-    for (uint32_t km = threadIdx.x; km < cnt; km += nthreads) {
+    for (uint32_t km = tid; km < cnt; km += nthreads) {
         const uint8_t *s = src + (size_t)km * k;
         bool f = true;  // forward unless the reverse complement is lexicographically smaller
         if (canonical) {
@@ -91,8 +107,8 @@ __device__ __forceinline__ void hash_kmers_cooperative(const uint8_t *g0, uint32
         }
         fwd[km] = f ? 1 : 0;
     }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < cnt * wpk; i += nthreads) {
+    sync();
+    for (uint32_t i = tid; i < cnt * wpk; i += nthreads) {
         const uint32_t km = i / wpk, wi = i % wpk;
         const uint8_t *s = src + (size_t)km * k;
         const bool f = fwd[km] != 0;
@@ -104,8 +120,8 @@ __device__ __forceinline__ void hash_kmers_cooperative(const uint8_t *g0, uint32
         }
         cw[km * wstride + wi] = word;
     }
-    __syncthreads();
-    for (uint32_t w = threadIdx.x; w < cnt * (uint32_t)h; w += nthreads) {
+    sync();
+    for (uint32_t w = tid; w < cnt * (uint32_t)h; w += nthreads) {
         const uint32_t km = w / (uint32_t)h, seed = w % (uint32_t)h;
         const uint32_t *wp = cw + km * wstride;
         uint32_t h1 = seed;
@@ -113,6 +129,13 @@ __device__ __forceinline__ void hash_kmers_cooperative(const uint8_t *g0, uint32
         if (rem) h1 = murmur_tail(h1, wp[nblocks]);
         ids[w] = murmur_finish_mod(h1, (uint32_t)k, m);
     }
+}
+
+// the whole CTA as one group
+__device__ __forceinline__ void hash_kmers_cooperative(const uint8_t *g0, uint32_t cnt, int k, int h, uint32_t m,
+                                                       int canonical, uint8_t *scratch, int32_t *ids)
+{
+    hash_kmers_group(g0, cnt, k, h, m, canonical, scratch, ids, threadIdx.x, blockDim.x, SyncBlock());
 }
 
 }  // namespace bigsi

@@ -2,18 +2,22 @@
 // Device functions shared by the stand-alone merge kernels (merge_kernels.cu) and by the merge
 // phase that fused_query runs itself after a grid-wide barrier (query_kernels.cu).
 //
-// COUNTS.  For one (query, tile) the partial buffer holds S slots (one per slice the query spans)
-// of `pps` bit planes each: slot s, plane b, bit c  =  bit b of the number of k-mers of segment s
-// whose AND vector has column c set.  The count of column c is  sum_b 2^b * (number of slots whose
-// plane b has bit c set), so every plane is an independent VERTICAL POPCOUNT over the S slots --
-// the same Harley-Seal carry-save counting stage 1 does over k-mers.  Work item = (query, tile,
-// chunk of `gpi` word groups); a word group is 32/NG consecutive 32-bit words.  Thread layout:
-// lane = (word w of the group, slot group g) with 32/NG words x NG slot groups; warp = (plane b,
-// word group) pair.  Each thread counts its slots for its (word, plane) from double-buffered
-// batches of 16 independent loads, the NG slot groups are added with warp shuffles (bit-sliced
-// full adders), the per-plane counters go to shared memory and every thread then expands whole
-// columns: count = sum_{b,j} bit(cnt[b][j]) << (b + j).  The threshold (graph/bigsi.py:241-242)
-// is applied while the count is in a register.
+// Partial layout (written by stage 1's flush, query.cuh:partial_offset): CHUNK-major,
+//   [chunk of the tile][slot][plane][merge_cb bytes]
+// so the input of one merge work item = (query, tile, chunk) -- all slots the (tile, query) pair
+// spans, all planes, merge_cb bytes of columns -- is ONE contiguous region.  It is staged into
+// shared memory with bulk async copies (the same TMA path stage 1 gathers rows with) instead of
+// thousands of strided 4-byte loads.
+//
+// COUNTS.  Slot s, plane b, bit c = bit b of the number of k-mers of segment s whose AND vector has
+// column c set, so count(c) = sum_b 2^b * |{s : plane b of s has bit c}|: every plane is a VERTICAL
+// POPCOUNT over the slots.  Threads = (word w, plane b) pairs x Gs slot groups (Gs consecutive
+// lanes); each thread counts its slots with Harley-Seal carry-save blocks, the Gs groups are added
+// with warp shuffles (bit-sliced full adders) and the J = bits(n_slots) counter planes of every
+// (w, b) land in shared memory.  Expansion: a warp takes one word; per plane b lane j holds counter
+// plane j, a 32x32 bit transpose across the warp (5 shuffle steps) turns that into "lane c holds
+// the count of column c", shifted by b and summed.  The threshold (graph/bigsi.py:241-242) is
+// applied while the count is in a register; hits are compacted per warp.
 //
 // AND.  One plane per slot; AND over the slots (graph/bigsi.py:192-195).
 #pragma once
@@ -22,48 +26,57 @@
 
 namespace bigsi {
 
-constexpr int kCntPlanes = 16;        // counter planes per (word, plane): up to 65 535 slots per (tile, query)
-constexpr int kMergeMaxWarps = 16;
-constexpr int kMergeMaxItemWords = 32;  // words (of 32 columns) one work item covers at most
-// shared memory one merge item needs: [plane b][counter plane j][word] + compaction scratch
-constexpr int kMergeSmemBytes = kSegPlanes * kCntPlanes * kMergeMaxItemWords * 4 + 256;
+constexpr uint32_t kMaxSlotGroups = 8;  // lanes that share one (unit, plane) pair; each level of the shuffle tree costs ~100 instructions
+constexpr int kCntPlanes = 16;  // counter planes per (word, plane): up to 65 535 slots per (tile, query)
 
 struct MergeGeom {
-    uint32_t q, t, tb0, tw, cb;
-    uint64_t s_first, n_slots;  // slices spanned by (tile, query); n_slots == 0 when the query is empty
+    uint32_t q, t, chunk;
+    uint32_t col0;      // first column of the chunk (local column id)
+    uint32_t vw;        // valid 32-bit words in this chunk (the last chunk of a tile may be narrow)
+    uint64_t s_first;   // first partial slot of (tile, query)
+    uint64_t n_slots;   // slices spanned by (tile, query); 0 when the query is empty
 };
 
 // item -> (query, tile, chunk); false when the chunk lies past the end of a narrow last tile
-__device__ __forceinline__ bool merge_geometry(const QueryParams &P, uint64_t item, uint32_t words_per_item, MergeGeom &g)
+__device__ __forceinline__ bool merge_geometry(const QueryParams &P, uint64_t item, MergeGeom &g)
 {
-    const uint32_t chunk_bytes = words_per_item * 4;
-    const uint32_t cpt = (P.tile_bytes + chunk_bytes - 1) / chunk_bytes;
-    const uint32_t chunk = (uint32_t)(item % cpt);
+    if (P.n_queries == 1 && P.n_tiles == 1) {
+        // the common single-query case without any 64-bit division: every slice belongs to (tile 0, query 0)
+        g.chunk = (uint32_t)item;
+        g.t = g.q = 0;
+        const uint32_t cb0 = g.chunk * P.merge_cb;
+        if (cb0 >= P.row_bytes16) return false;
+        g.col0 = cb0 * 8;
+        g.vw = min(P.merge_cb, P.row_bytes16 - cb0) >> 2;
+        g.s_first = 0;
+        g.n_slots = P.total_kmers ? P.n_slices : 0;
+        return true;
+    }
+    const uint32_t cpt = P.merge_cpt;
+    g.chunk = (uint32_t)(item % cpt);
     const uint64_t tq = item / cpt;
     g.t = (uint32_t)(tq % P.n_tiles);
     g.q = (uint32_t)(tq / P.n_tiles);
-    g.tb0 = g.t * P.tile_bytes;
-    g.tw = min(P.tile_bytes, P.row_bytes16 - g.tb0);
-    g.cb = chunk * chunk_bytes;
-    if (g.cb >= g.tw) return false;
+    const uint32_t tb0 = g.t * P.tile_bytes;
+    const uint32_t tw = min(P.tile_bytes, P.row_bytes16 - tb0);
+    const uint32_t cb0 = g.chunk * P.merge_cb;
+    if (cb0 >= tw) return false;
+    g.col0 = (tb0 + cb0) * 8;
+    g.vw = min(P.merge_cb, tw - cb0) >> 2;
     // a single query spans [0, total_kmers) by contract: no dependent load in front of the planes
     const bool one = P.n_queries == 1;
     const uint64_t k0 = one ? 0ull : (uint64_t)__ldg(P.qoff + g.q);
     const uint64_t k1 = one ? P.total_kmers : (uint64_t)__ldg(P.qoff + g.q + 1);
     if (k1 > k0) {
         const uint64_t I0 = (uint64_t)g.t * P.total_kmers + k0, I1 = (uint64_t)g.t * P.total_kmers + k1;
-        g.s_first = I0 / P.items_per_slice;
-        g.n_slots = (I1 - 1) / P.items_per_slice - g.s_first + 1;
+        const uint64_t sl0 = I0 / P.items_per_slice;
+        g.n_slots = (I1 - 1) / P.items_per_slice - sl0 + 1;
+        g.s_first = sl0 + (uint64_t)g.t * P.n_queries + g.q;
     } else {
         g.s_first = 0;
         g.n_slots = 0;
     }
     return true;
-}
-inline uint64_t merge_item_count(const QueryParams &p, uint32_t words_per_item)
-{
-    const uint64_t cpt = (p.tile_bytes + words_per_item * 4 - 1) / (words_per_item * 4);
-    return cpt * p.n_tiles * p.n_queries;
 }
 
 // full-adder step of a bit-sliced add: acc += x (one plane), carry chained by the caller
@@ -74,241 +87,299 @@ __device__ __forceinline__ void fa(uint32_t &acc, uint32_t x, uint32_t &carry)
     carry = maj3(o, x, carry);
 }
 
-// One COUNTS work item, executed by the whole CTA (blockDim.x threads, a multiple of 32, at most
-// kMergeMaxWarps warps).  gpi = word groups per item; gpi * (32/NG) <= kMergeMaxItemWords.
-// All threads must call it (it contains __syncthreads); smem = kMergeSmemBytes of scratch.
-template <int NG>
-__device__ __forceinline__ void merge_counts_item(const QueryParams &P, uint64_t item, uint32_t gpi, uint8_t *smem)
+// 32x32 bit-matrix transpose across a warp: in = row `lane`, out = column `lane` (bit r = in[r] bit lane)
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, uint32_t lane)
 {
-    constexpr int WPG = 32 / NG;  // words per word group
-    uint32_t *sm = reinterpret_cast<uint32_t *>(smem);
-    uint32_t *warp_hits = sm + kSegPlanes * kCntPlanes * kMergeMaxItemWords;
-    unsigned long long *hit_base = reinterpret_cast<unsigned long long *>(warp_hits + kMergeMaxWarps + 2);
-    const uint32_t wpi = WPG * gpi;  // words per item
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const uint32_t m = s == 16 ? 0x0000ffffu : s == 8 ? 0x00ff00ffu : s == 4 ? 0x0f0f0f0fu : s == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
+        x = (lane & s) ? ((x & ~m) | ((y >> s) & m)) : ((x & m) | ((y & m) << s));
+    }
+    return x;
+}
 
+// Stage `bytes` (a multiple of 16) from global to shared memory with bulk async copies issued by warp 0
+// and wait for them.  Every thread of the CTA must call it; `phase` is the CTA-uniform parity of `mbar`.
+__device__ __forceinline__ void merge_stage_region(const QueryParams &P, uint8_t *dst, const uint8_t *src, uint32_t bytes,
+                                                   uint64_t *mbar, uint32_t &phase)
+{
+    __syncthreads();  // every reader of the previous contents is done
+    if (threadIdx.x < 32) {
+        const uint32_t lane = threadIdx.x;
+        if (lane == 0) BIGSI_TS(13);
+        if (!(P.debug_flags & 8u)) fence_proxy_async_all();  // partial planes were written through the generic proxy (by other SMs)
+        if (lane == 0) mbar_arrive_expect_tx(mbar, bytes);
+        __syncwarp();
+        uint32_t piece = ((bytes + 31) / 32 + 15) & ~15u;
+        if (piece < 2048) piece = 2048;
+        const uint32_t off = lane * piece;
+        if (off < bytes) bulk_g2s(dst + off, src + off, min(piece, bytes - off), mbar);
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1;
+}
+
+// One merge work item, executed by the whole CTA (all threads must call it: it contains
+// __syncthreads).  smem: 128-byte aligned scratch of P.merge_smem bytes; mbar: an initialised
+// (count 1) mbarrier owned by the merge phase; phase: its CTA-uniform parity.
+template <int MODE>
+__device__ __forceinline__ void merge_item(const QueryParams &P, uint64_t item, uint8_t *smem, uint64_t *mbar,
+                                           uint32_t &phase)
+{
     MergeGeom G;
-    const bool in_range = merge_geometry(P, item, wpi, G);  // block-uniform
+    if (!merge_geometry(P, item, G)) return;  // block-uniform
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const uint32_t pps = P.planes_per_slot;
-    const uint32_t J = in_range ? 32 - __clz((uint32_t)G.n_slots) : 0;  // counter planes needed: bits(S)
-    const uint64_t slot_stride = (uint64_t)pps * P.tile_bytes;
+    const uint32_t pps = MODE == kModeCounts ? P.planes_per_slot : 1;
+    const uint32_t cb = P.merge_cb;
+    const uint32_t wpi = cb >> 2;
+    const uint32_t J = MODE == kModeCounts ? 32 - __clz((uint32_t)G.n_slots) : 1;  // counter planes: bits(n_slots)
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);  // COUNTS: [w][b][J]; AND: [w]
+    const uint32_t cnt_bytes = (((MODE == kModeCounts ? wpi * pps * J : wpi) * 4) + 127) & ~127u;
+    uint8_t *stage = smem + cnt_bytes;
+    const uint32_t slot_bytes = pps * cb;
+    // slots staged per batch: >= 1 by plan; <= 255 so that a batch's counters fit kLocalPlanes bit planes
+    const uint32_t SB = min((P.merge_smem - cnt_bytes) / slot_bytes, 255u);
+    const uint8_t *region = P.partial + partial_offset(P, G.chunk, G.s_first, 0);
 
-    if (in_range) {
-        // warp-level work units: (plane b, word group wg), pps * gpi of them
-        for (uint32_t unit = warp; unit < pps * gpi; unit += nwarps) {
-            const uint32_t b = unit % pps, wg = unit / pps;
-            const uint32_t w = wg * WPG + lane % WPG, g = lane / WPG;
-            const bool valid = G.cb + w * 4 < G.tw;
-            uint32_t c[kCntPlanes];
+    // thread layout: Gs consecutive lanes share a (16-byte unit, plane) pair and split its slots
+    constexpr int kLocalPlanes = 8;
+    const uint32_t pairs = (G.vw >> 2) * pps;
+    uint32_t Gs = 1;
+    {
+        const uint32_t lim = (uint32_t)min((uint64_t)SB, G.n_slots);
+        while (Gs < kMaxSlotGroups && Gs < lim && pairs * (Gs * 2) <= blockDim.x) Gs <<= 1;
+    }
+    const uint32_t g = lane & (Gs - 1);
+    const uint32_t pairs_per_pass = blockDim.x / Gs;
+    const uint32_t stage_s = smem_u32(stage);
+
+    __syncthreads();  // the previous item's expansion is done with `cnt`
+    if (MODE == kModeAnd && G.n_slots == 0)  // an empty query is all-ones (reduce over nothing is the identity)
+        for (uint32_t w = threadIdx.x; w < G.vw; w += blockDim.x) cnt[w] = 0xffffffffu;
+
+    for (uint64_t s0 = 0; s0 < G.n_slots; s0 += SB) {
+        const uint32_t nb = (uint32_t)min((uint64_t)SB, G.n_slots - s0);
+        merge_stage_region(P, stage, region + s0 * slot_bytes, nb * slot_bytes, mbar, phase);
+        if (threadIdx.x == 0 && s0 == 0) BIGSI_TS(10);
+        const bool first = s0 == 0;
+        for (uint32_t p0 = (warp * 32) / Gs; p0 < pairs; p0 += pairs_per_pass) {  // warp-uniform trip count
+            const uint32_t p = p0 + lane / Gs;
+            const bool valid = p < pairs;
+            const uint32_t u = valid ? p / pps : 0, b = valid ? p - u * pps : 0;
+            const uint32_t n_mine = valid && g < nb ? (nb - g + Gs - 1) / Gs : 0;  // slots g, g + Gs, ...
+            const uint32_t src = stage_s + g * slot_bytes + b * cb + u * 16;
+            const uint32_t step = Gs * slot_bytes;
+            if (MODE == kModeCounts) {
+                // straight-line code on purpose: no data-dependent branches around loads / shuffles (a
+                // branch per plane costs more than the plane); all kLocalPlanes planes are always processed
+                uint32_t c[kLocalPlanes][4];
 #pragma unroll
-            for (int j = 0; j < kCntPlanes; ++j) c[j] = 0;
-            if (valid && g < G.n_slots) {
-                const uint32_t n_mine = (uint32_t)((G.n_slots - g + NG - 1) / NG);  // slots s_first + g, + NG, ...
-                const uint64_t step = (uint64_t)NG * slot_stride;
-                const uint8_t *src = P.partial + (G.s_first + g + (uint64_t)G.t * P.n_queries + G.q) * slot_stride +
-                                     (uint64_t)b * P.tile_bytes + G.cb + w * 4;
-                const uint32_t nhi = J > 3 ? J - 3 : 0;
-                // Batches of kB independent loads, double buffered: while one batch is counted the
-                // next is in flight (clamped index + select keeps the loads branch-free).  Plain
-                // weak loads: the planes were published before the kernel boundary / grid barrier.
-                constexpr int kB = 16;
-                uint32_t xn[kB];
-                auto load_batch = [&](uint32_t i0) {
+                for (int j = 0; j < kLocalPlanes; ++j)
 #pragma unroll
-                    for (int u = 0; u < kB; ++u)
-                        xn[u] = *reinterpret_cast<const uint32_t *>(src + (uint64_t)min(i0 + u, n_mine - 1) * step);
-                };
-                load_batch(0);
-                for (uint32_t i = 0; i < n_mine; i += kB) {
-                    uint32_t x[kB];
+                    for (int i = 0; i < 4; ++i) c[j][i] = 0;
+                for (uint32_t s = 0; s < n_mine; s += 8) {
+                    uint32_t x[8][4];
 #pragma unroll
-                    for (int u = 0; u < kB; ++u) x[u] = i + u < n_mine ? xn[u] : 0u;
-                    if (i + kB < n_mine) load_batch(i + kB);
+                    for (int v = 0; v < 8; ++v) {
+                        const uint32_t sv = min(s + v, n_mine - 1);  // clamped: always a valid slot
+                        const uint32_t keep = s + v < n_mine ? 0xffffffffu : 0u;
+                        uint32_t y0, y1, y2, y3;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(y0), "=r"(y1), "=r"(y2), "=r"(y3)
+                                     : "r"(src + sv * step));
+                        x[v][0] = y0 & keep;
+                        x[v][1] = y1 & keep;
+                        x[v][2] = y2 & keep;
+                        x[v][3] = y3 & keep;
+                    }
 #pragma unroll
-                    for (int v = 0; v < kB; v += 8) {
+                    for (int i = 0; i < 4; ++i) {
                         // Harley-Seal block: 8 inputs of weight 1 -> ones/twos/fours + a carry of weight 8
-                        uint32_t t0 = maj3(c[0], x[v + 0], x[v + 1]);
-                        c[0] = xor3(c[0], x[v + 0], x[v + 1]);
-                        uint32_t t1 = maj3(c[0], x[v + 2], x[v + 3]);
-                        c[0] = xor3(c[0], x[v + 2], x[v + 3]);
-                        const uint32_t f0 = maj3(c[1], t0, t1);
-                        c[1] = xor3(c[1], t0, t1);
-                        t0 = maj3(c[0], x[v + 4], x[v + 5]);
-                        c[0] = xor3(c[0], x[v + 4], x[v + 5]);
-                        t1 = maj3(c[0], x[v + 6], x[v + 7]);
-                        c[0] = xor3(c[0], x[v + 6], x[v + 7]);
-                        const uint32_t f1 = maj3(c[1], t0, t1);
-                        c[1] = xor3(c[1], t0, t1);
-                        uint32_t carry = maj3(c[2], f0, f1);
-                        c[2] = xor3(c[2], f0, f1);
+                        uint32_t t0 = maj3(c[0][i], x[0][i], x[1][i]);
+                        c[0][i] = xor3(c[0][i], x[0][i], x[1][i]);
+                        uint32_t t1 = maj3(c[0][i], x[2][i], x[3][i]);
+                        c[0][i] = xor3(c[0][i], x[2][i], x[3][i]);
+                        const uint32_t f0 = maj3(c[1][i], t0, t1);
+                        c[1][i] = xor3(c[1][i], t0, t1);
+                        t0 = maj3(c[0][i], x[4][i], x[5][i]);
+                        c[0][i] = xor3(c[0][i], x[4][i], x[5][i]);
+                        t1 = maj3(c[0][i], x[6][i], x[7][i]);
+                        c[0][i] = xor3(c[0][i], x[6][i], x[7][i]);
+                        const uint32_t f1 = maj3(c[1][i], t0, t1);
+                        c[1][i] = xor3(c[1][i], t0, t1);
+                        uint32_t carry = maj3(c[2][i], f0, f1);
+                        c[2][i] = xor3(c[2][i], f0, f1);
 #pragma unroll
-                        for (int j = 3; j < kCntPlanes; ++j) {
-                            if (j - 3 < (int)nhi) {
-                                const uint32_t o = c[j];
-                                c[j] = o ^ carry;
-                                carry = o & carry;
+                        for (int j = 3; j < kLocalPlanes; ++j) {
+                            const uint32_t o = c[j][i];
+                            c[j][i] = o ^ carry;
+                            carry = o & carry;
+                        }
+                    }
+                }
+                // add the Gs slot groups (lanes l and l ^ d hold the same pair); the sum is <= nb <= 255
+                for (uint32_t d = 1; d < Gs; d <<= 1) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint32_t carry = 0;
+#pragma unroll
+                        for (int j = 0; j < kLocalPlanes; ++j) {
+                            const uint32_t o = __shfl_xor_sync(0xffffffffu, c[j][i], d);
+                            fa(c[j][i], o, carry);
+                        }
+                    }
+                }
+                if (valid && g == 0) {
+                    if (first) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            uint32_t *dst = cnt + ((size_t)(u * 4 + i) * pps + b) * J;
+#pragma unroll
+                            for (int j = 0; j < kLocalPlanes; ++j)
+                                if (j < (int)J) dst[j] = c[j][i];
+                            for (uint32_t j = kLocalPlanes; j < J; ++j) dst[j] = 0u;
+                        }
+                    } else {  // later slot batches are added to the counters of the earlier ones
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            uint32_t *dst = cnt + ((size_t)(u * 4 + i) * pps + b) * J;
+                            uint32_t carry = 0;
+#pragma unroll
+                            for (int j = 0; j < kLocalPlanes; ++j) {
+                                if (j < (int)J) {
+                                    uint32_t a = dst[j];
+                                    fa(a, c[j][i], carry);
+                                    dst[j] = a;
+                                }
+                            }
+                            for (uint32_t j = kLocalPlanes; j < J; ++j) {
+                                const uint32_t a = dst[j];
+                                dst[j] = a ^ carry;
+                                carry = a & carry;
                             }
                         }
                     }
                 }
-            }
-            // add the NG slot groups: lanes l and l ^ (WPG * 2^k) hold the same word
-            if (NG > 1) {
+            } else {
+                uint32_t acc[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+                for (uint32_t s = 0; s < n_mine; ++s) {
+                    uint32_t x[4];
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3])
+                                 : "r"(src + s * step));
 #pragma unroll
-                for (int d = WPG; d < 32; d <<= 1) {
-                    uint32_t carry = 0;
-#pragma unroll
-                    for (int j = 0; j < kCntPlanes; ++j) {
-                        const uint32_t o = __shfl_xor_sync(0xffffffffu, c[j], d);
-                        fa(c[j], o, carry);
-                    }
+                    for (int i = 0; i < 4; ++i) acc[i] &= x[i];
                 }
-            }
-            if (g == 0) {
+                for (uint32_t d = 1; d < Gs; d <<= 1)
 #pragma unroll
-                for (int j = 0; j < kCntPlanes; ++j)
-                    if (j < (int)J) sm[(b * kCntPlanes + j) * kMergeMaxItemWords + w] = c[j];
+                    for (int i = 0; i < 4; ++i) acc[i] &= __shfl_xor_sync(0xffffffffu, acc[i], d);
+                if (valid && g == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) cnt[u * 4 + i] = first ? acc[i] : (cnt[u * 4 + i] & acc[i]);
+                }
             }
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) BIGSI_TS(11);
 
-    if (in_range) {
-        // expansion: one column per thread and pass
+    if (MODE == kModeCounts) {
         uint32_t *out = P.out ? reinterpret_cast<uint32_t *>(P.out) + (uint64_t)G.q * P.out_stride : nullptr;
         const bool thresholding = P.min_kmers != nullptr || P.min_by_value;
         const uint32_t thr = P.min_by_value ? P.min_kmers_value : (thresholding ? __ldg(P.min_kmers + G.q) : 0u);
-        const uint32_t col_base = (G.tb0 + G.cb) * 8;
-        const uint32_t ncols_here = min(wpi * 32u, (G.tw - G.cb) * 8u);  // never past this tile
-        for (uint32_t c0 = 0; c0 < ncols_here; c0 += blockDim.x) {
-            const uint32_t cc = c0 + threadIdx.x;
-            const uint32_t col = col_base + cc;
-            const bool live = cc < ncols_here && col < P.num_cols;
-            uint32_t cnt = 0;
-            if (live) {
-                // bit i of a little-endian 32-bit word of MSB-first bytes is column (i ^ 7) of that word
-                const uint32_t word = cc >> 5, bit = (cc & 31) ^ 7;
+        for (uint32_t w = warp; w < G.vw; w += nwarps) {
+            uint32_t total = 0;
+            const uint32_t *cw = cnt + (size_t)w * pps * J;
+            if (J <= 4) {
+                for (uint32_t b = 0; b < pps; ++b)
+                    for (uint32_t j = 0; j < J; ++j) total += ((cw[b * J + j] >> lane) & 1u) << (b + j);
+            } else {
+#pragma unroll 4
                 for (uint32_t b = 0; b < pps; ++b) {
-                    const uint32_t *row = sm + (b * kCntPlanes) * kMergeMaxItemWords + word;
-#pragma unroll
-                    for (int j0 = 0; j0 < kCntPlanes; j0 += 4) {  // four independent LDS per step
-                        if (j0 < (int)J) {
-                            uint32_t v[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) v[u] = j0 + u < (int)J ? row[(j0 + u) * kMergeMaxItemWords] : 0u;
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) cnt += ((v[u] >> bit) & 1u) << (b + j0 + u);
+                    const uint32_t x = lane < J ? cw[b * J + lane] : 0u;
+                    total += warp_transpose32(x, lane) << b;
+                }
+            }
+            // bit i of a little-endian 32-bit word of MSB-first bytes is column (i ^ 7) of that word
+            const uint32_t col = G.col0 + w * 32 + (lane ^ 7);
+            const bool live = col < P.num_cols;
+            if (live && out) out[col] = total;
+            if (thresholding) {  // counts >= min_kmers (graph/bigsi.py:241-242), warp-level compaction
+                const bool hit = live && total >= thr;
+                const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
+                if (ballot) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(P.n_hits + G.q, (unsigned long long)__popc(ballot));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (hit) {
+                        const uint64_t pos = base + __popc(ballot & ((1u << lane) - 1));
+                        if (pos < P.hit_cap) {
+                            P.hit_cols[(uint64_t)G.q * P.hit_cap + pos] = (int32_t)col;
+                            P.hit_counts[(uint64_t)G.q * P.hit_cap + pos] = total;
                         }
                     }
                 }
-                if (out) out[col] = cnt;
-            }
-            if (thresholding) {  // counts >= min_kmers (graph/bigsi.py:241-242), block-level compaction
-                const bool hit = live && cnt >= thr;
-                const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
-                if (lane == 0) warp_hits[warp] = __popc(ballot);
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    uint32_t tot = 0;
-                    for (uint32_t i = 0; i < nwarps; ++i) {
-                        const uint32_t v = warp_hits[i];
-                        warp_hits[i] = tot;
-                        tot += v;
-                    }
-                    *hit_base = tot ? atomicAdd(P.n_hits + G.q, (unsigned long long)tot) : 0ull;
-                }
-                __syncthreads();
-                if (hit) {
-                    const uint64_t pos = *hit_base + warp_hits[warp] + __popc(ballot & ((1u << lane) - 1));
-                    if (pos < P.hit_cap) {
-                        P.hit_cols[(uint64_t)G.q * P.hit_cap + pos] = (int32_t)col;
-                        P.hit_counts[(uint64_t)G.q * P.hit_cap + pos] = cnt;
-                    }
-                }
-                __syncthreads();
             }
         }
-    }
-    __syncthreads();  // smem is reused by the next item
-}
-
-// One AND work item: lanes = 8 words x 4 slot groups, every warp its own 8 words.
-constexpr int kAndNG = 4, kAndWPW = 32 / kAndNG;
-__device__ __forceinline__ void merge_and_item(const QueryParams &P, uint64_t item, uint8_t *smem)
-{
-    uint32_t *sm = reinterpret_cast<uint32_t *>(smem);
-    const uint32_t nwarps = blockDim.x >> 5;
-    const uint32_t wpi = kAndWPW * nwarps;  // words per item
-    MergeGeom G;
-    const bool in_range = merge_geometry(P, item, wpi, G);
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t w = warp * kAndWPW + lane % kAndWPW, g = lane / kAndWPW;
-    if (in_range) {
-        const bool valid = G.cb + w * 4 < G.tw;
-        const uint64_t slot_stride = (uint64_t)P.planes_per_slot * P.tile_bytes;
-        uint32_t acc = 0xffffffffu;
-        if (valid && g < G.n_slots) {
-            const uint32_t n_mine = (uint32_t)((G.n_slots - g + kAndNG - 1) / kAndNG);
-            const uint64_t step = (uint64_t)kAndNG * slot_stride;
-            const uint8_t *src =
-                P.partial + (G.s_first + g + (uint64_t)G.t * P.n_queries + G.q) * slot_stride + G.cb + w * 4;
-            for (uint32_t i = 0; i < n_mine; i += 16) {
-                uint32_t x[16];
-#pragma unroll
-                for (int u = 0; u < 16; ++u)
-                    x[u] = *reinterpret_cast<const uint32_t *>(src + (uint64_t)min(i + u, n_mine - 1) * step);
-#pragma unroll
-                for (int u = 0; u < 16; ++u) acc &= x[u];  // the clamped duplicates are harmless under AND
-            }
-        }
-#pragma unroll
-        for (int d = kAndWPW; d < 32; d <<= 1) acc &= __shfl_xor_sync(0xffffffffu, acc, d);
-        if (g == 0) sm[w] = valid ? acc : 0u;
-    }
-    __syncthreads();
-    if (in_range) {
+    } else {
         uint8_t *out = reinterpret_cast<uint8_t *>(P.out) + (uint64_t)G.q * P.out_stride;
         const uint32_t row_bytes = (P.num_cols + 7) >> 3;
-        const uint32_t nbytes_here = min(wpi * 4u, G.tw - G.cb);  // never past this tile
-        for (uint32_t c = threadIdx.x; c < nbytes_here; c += blockDim.x) {
-            const uint32_t byte = G.tb0 + G.cb + c;
+        const uint32_t byte0 = G.col0 >> 3;
+        for (uint32_t c = threadIdx.x; c < G.vw * 4; c += blockDim.x) {
+            const uint32_t byte = byte0 + c;
             if (byte >= row_bytes) break;
-            uint32_t v = (sm[c >> 2] >> (8 * (c & 3))) & 0xffu;
+            uint32_t v = (cnt[c >> 2] >> (8 * (c & 3))) & 0xffu;
             if (byte == row_bytes - 1 && (P.num_cols & 7)) v &= 0xff00u >> (P.num_cols & 7);
             out[byte] = (uint8_t)v;
         }
     }
-    __syncthreads();
+    if (threadIdx.x == 0) BIGSI_TS(12);
+    // the next item's staging starts with __syncthreads, which also protects `cnt`
 }
 
-// launch geometry of the merge work (shared by both launch styles)
-struct MergePlan {
-    int ng;             // slot groups per warp (1 or 4)
-    uint32_t gpi;       // word groups per item (COUNTS)
-    uint32_t wpi;       // words per item
-    uint64_t n_items;
-};
-inline MergePlan plan_merge(const QueryParams &p, int mode, uint32_t block_threads)
+// ------------------------------------------------------------------------------------------
+// launch geometry of the merge work (fixes the partial layout, so stage 1 needs it too)
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kMergeKernelThreads = 256;
+constexpr uint32_t kMergeKernelSmem = 64 * 1024;  // dynamic shared memory of the stand-alone merge kernels
+
+// Fills p.merge_cb / merge_cpt / merge_items / merge_smem.  `smem` = scratch one item may use,
+// `ctas` = CTAs that will share the items.  Needs tile geometry, slices and planes_per_slot.
+inline void plan_merge(QueryParams &p, int mode, uint32_t smem, uint64_t ctas, uint32_t cb_override = 0)
 {
-    MergePlan m;
-    const uint32_t nwarps = block_threads / 32;
-    if (mode == kModeAnd) {
-        m.ng = kAndNG;
-        m.gpi = nwarps;
-        m.wpi = kAndWPW * nwarps;
-    } else {
-        // slots one (tile, query) can span decide how many lanes share a word's slot loop
-        const uint64_t max_slots = p.max_query_kmers / p.items_per_slice + 2;
-        m.ng = max_slots <= 4 ? 1 : 4;
-        const uint32_t wpg = 32 / m.ng;
-        uint32_t gpi = nwarps / (p.planes_per_slot ? p.planes_per_slot : 1);
-        if (gpi < 1) gpi = 1;
-        if (gpi * wpg > (uint32_t)kMergeMaxItemWords) gpi = kMergeMaxItemWords / wpg;
-        m.gpi = gpi;
-        m.wpi = gpi * wpg;
+    const uint32_t pps = mode == kModeCounts ? (p.planes_per_slot ? p.planes_per_slot : 1) : 1;
+    const uint64_t max_slots = p.items_per_slice ? p.max_query_kmers / p.items_per_slice + 2 : 2;
+    uint32_t jmax = 0;
+    for (uint64_t v = max_slots; v; v >>= 1) ++jmax;
+    if (mode != kModeCounts) jmax = 1;
+    // parallelism: about one item per CTA when there are few (tile, query) pairs
+    const uint64_t tq = (uint64_t)p.n_tiles * (p.n_queries ? p.n_queries : 1);
+    uint64_t cb = p.tile_bytes;
+    if (tq < ctas) {
+        const uint64_t per = (ctas + tq - 1) / tq;  // chunks per tile wanted
+        cb = (p.tile_bytes + per - 1) / per;
     }
-    m.n_items = merge_item_count(p, m.wpi);
-    return m;
+    cb = (cb + 15) / 16 * 16;
+    // memory: counters [wpi][pps][jmax] + at least min(max_slots, 16) staged slots must fit
+    const uint64_t batch = max_slots < 16 ? max_slots : 16;
+    uint64_t cb_mem = (uint64_t)(smem - 256) / ((uint64_t)pps * (jmax + batch)) / 16 * 16;
+    if (cb_mem < 16) cb_mem = 16;
+    if (cb > cb_mem) cb = cb_mem;
+    if (cb > p.tile_bytes) cb = p.tile_bytes;
+    if (cb < 16) cb = 16;
+    uint64_t cpt = (p.tile_bytes + cb - 1) / cb;
+    cb = ((p.tile_bytes + cpt - 1) / cpt + 15) / 16 * 16;  // balance the chunks of a tile
+    if (cb_override) {
+        cb = ((uint64_t)cb_override + 15) / 16 * 16;
+        if (cb > cb_mem) cb = cb_mem;
+        if (cb > p.tile_bytes) cb = p.tile_bytes;
+    }
+    cpt = (p.tile_bytes + cb - 1) / cb;
+    p.merge_cb = (uint32_t)cb;
+    p.merge_cpt = (uint32_t)cpt;
+    p.merge_items = cpt * p.n_tiles * p.n_queries;
+    p.merge_smem = smem;
 }
 
 }  // namespace bigsi

@@ -6,34 +6,38 @@
 
 namespace bigsi {
 
-constexpr int kMergeThreads = 256;
-
-template <int NG>
-__global__ void __launch_bounds__(kMergeThreads) merge_counts_kernel(const __grid_constant__ QueryParams P,
-                                                                    const uint32_t gpi)
+template <int MODE>
+__global__ void __launch_bounds__(kMergeKernelThreads) merge_kernel(const __grid_constant__ QueryParams P)
 {
-    __shared__ __align__(16) uint8_t smem[kMergeSmemBytes];
+    extern __shared__ __align__(128) uint8_t merge_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
     grid_dependency_wait();  // stage 1 must have completed (PDL launch)
-    merge_counts_item<NG>(P, blockIdx.x, gpi, smem);
+    uint32_t phase = 0;
+    merge_item<MODE>(P, blockIdx.x, merge_smem, &bar, phase);
 }
 
-__global__ void __launch_bounds__(kMergeThreads) merge_and_kernel(const __grid_constant__ QueryParams P)
+cudaError_t merge_kernels_init()
 {
-    __shared__ __align__(16) uint8_t smem[1024];
-    grid_dependency_wait();
-    merge_and_item(P, blockIdx.x, smem);
+    cudaError_t e = cudaFuncSetAttribute(merge_kernel<kModeCounts>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kMergeKernelSmem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(merge_kernel<kModeAnd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMergeKernelSmem);
 }
 
-cudaError_t launch_merge(const QueryParams &p, int mode, cudaStream_t stream)
+cudaError_t launch_merge(const QueryParams &p_in, int mode, cudaStream_t stream)
 {
-    if (p.n_queries == 0) return cudaSuccess;
-    const MergePlan m = plan_merge(p, mode, kMergeThreads);
-    if (m.n_items == 0) return cudaSuccess;
-    if (m.n_items > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    const dim3 grid((unsigned)m.n_items), block(kMergeThreads);
-    if (mode == kModeAnd) return launch_pdl(merge_and_kernel, grid, block, 0, stream, p);
-    if (m.ng == 1) return launch_pdl(merge_counts_kernel<1>, grid, block, 0, stream, p, m.gpi);
-    return launch_pdl(merge_counts_kernel<4>, grid, block, 0, stream, p, m.gpi);
+    QueryParams p = p_in;
+    p.debug_ts = nullptr;  // the timeline buffer is sized for stage 1's grid
+    if (p.n_queries == 0 || p.merge_items == 0) return cudaSuccess;
+    if (p.merge_items > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    const dim3 grid((unsigned)p.merge_items), block(kMergeKernelThreads);
+    if (mode == kModeAnd) return launch_pdl(merge_kernel<kModeAnd>, grid, block, p.merge_smem, stream, p);
+    return launch_pdl(merge_kernel<kModeCounts>, grid, block, p.merge_smem, stream, p);
 }
 
 }  // namespace bigsi

@@ -24,6 +24,12 @@ __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// all state spaces: generic-proxy writes to GLOBAL memory (made visible by a fence / barrier) are ordered
+// before this thread's later async-proxy (bulk copy) reads of them
+__device__ __forceinline__ void fence_proxy_async_all()
+{
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -108,6 +114,21 @@ __device__ __forceinline__ uint32_t and3(uint32_t a, uint32_t b, uint32_t c) { r
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// signal a named barrier without waiting on it (the waiting side uses named_bar_sync with the same count)
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 }  // namespace bigsi

@@ -16,6 +16,7 @@ constexpr int kSmemBudget = 227 * 1024;
 constexpr uint32_t kMaxSliceItems = 65535;                      // a segment's count fits 16 bit planes
 constexpr int kSegPlanes = 16;
 constexpr int kMaxH = 1024;
+constexpr int kPoolMaxH = 8;   // the solo path pools k-mers only for h <= 8 (row-id stash in the smem header)
 constexpr int kMaxSinks = 9;   // host + up to 8 GPUs of one box
 
 enum { kModeCounts = 0, kModeAnd = 1 };
@@ -43,7 +44,7 @@ struct QueryParams {
     uint32_t items_per_slice; // <= kMaxSliceItems
     uint32_t n_slices;
     uint32_t slices_per_cta;
-    uint8_t *partial;         // [n_slots][planes_per_slot][tile_bytes]
+    uint8_t *partial;         // [merge_cpt chunks][n_slots_total][planes_per_slot][merge_cb bytes], see partial_offset
     uint32_t planes_per_slot; // COUNTS: bits(min(items_per_slice, longest query)); AND: 1
     uint32_t total_planes;    // bits(longest query) <= 32 (merge accumulator width)
     uint64_t max_query_kmers; // upper bound on the longest query (sizes the merge's slot loop)
@@ -62,10 +63,26 @@ struct QueryParams {
     uint32_t k;
     uint32_t num_rows;        // m
     uint32_t prehash;         // 1: hash in the prologue into the shared-memory id table
-    uint32_t ids_bytes;       // size of that table (between the mbarriers and the ring)
+    uint32_t ids_bytes;       // size of that table + the hashing scratch (between the mbarriers and the ring)
+    uint32_t ids_table_bytes; // the table alone; the hashing scratch follows it
+    // "solo" path (one query, one tile, one slice per CTA, in-kernel hashing and merge): the producer warp
+    // hashes the first ring-full of k-mers itself and starts gathering while the consumer warps hash the
+    // rest; the last pool_share k-mers of every CTA's range go to a shared POOL that the CTAs drain
+    // dynamically (atomic claims), so fast CTAs take over work of slow ones (tail balance)
+    uint32_t solo;
+    uint32_t pool_share;      // k-mers per CTA that go to the pool (0 = static split only)
+    uint32_t solo_max_kmers;  // most k-mers one CTA may count (2^planes_per_slot - 1)
+    int32_t *pool_ids;        // [grid][pool_share][h] row ids of the pooled k-mers, written by their owner CTA
+    unsigned long long *pool_ready;  // [grid] = pool_epoch once the owner's ids are visible
+    unsigned int *pool_counter;      // claim counter, zero at launch (reset behind the grid barrier)
+    unsigned long long pool_epoch;
     // optional in-kernel merge: stage 2 runs inside stage 1 after a grid-wide barrier
     uint32_t fuse_merge;
-    uint32_t merge_ng, merge_gpi;
+    // merge geometry (merge.cuh:plan_merge); it also fixes the layout of `partial`
+    uint32_t merge_cb;        // column chunk of one merge item in bytes (multiple of 16)
+    uint32_t merge_cpt;       // chunks per tile
+    uint32_t merge_smem;      // shared-memory scratch one merge item may use
+    uint64_t n_slots_total;   // partial slots of this launch (n_slices + n_tiles * n_queries)
     uint64_t merge_items;
     unsigned long long *barrier;        // monotonic arrival counter shared by all launches of a handle
     unsigned long long barrier_target;  // value the counter reaches when every CTA of THIS launch arrived
@@ -86,8 +103,26 @@ struct QueryParams {
     unsigned long long *done_counter;   // monotonic; the CTA that brings it to done_target is the last
     unsigned long long done_target;
     uint32_t debug_flags;     // bit 0: consumers skip the AND/count work (pure-gather ceiling measurement)
-    unsigned long long *debug_ts;  // optional [grid][8] timeline stamps (globaltimer ns), see fused_query
+    unsigned long long *debug_ts;  // optional [grid][kDebugStamps] timeline stamps (globaltimer ns), see fused_query
 };
+
+// timeline stamps per CTA (debug_flags bit 1): 0 entry, 1 producer first issue, 2 first slot landed,
+// 3 last slot consumed, 4 after flush, 5 producer last issue, 6 past the grid barrier, 7 merge phase
+// done, 8 past the PDL wait, 9 prologue hashing done, 10 merge: partial planes loaded + counted,
+// 11 merge: counters in shared memory, 12 merge: expansion done, 13 merge phase re-run done (bit 2)
+constexpr int kDebugStamps = 16;
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long debug_gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define BIGSI_TS(slot)                                                                          \
+    do {                                                                                        \
+        if (P.debug_ts) P.debug_ts[(size_t)blockIdx.x * kDebugStamps + (slot)] = debug_gtime(); \
+    } while (0)
+#endif
 
 inline uint32_t query_consumer_warps(const QueryParams &p) { return (p.tile_bytes + 511) / 512; }
 inline uint32_t query_block_threads(const QueryParams &p) { return (query_consumer_warps(p) + 1) * 32; }
@@ -103,10 +138,15 @@ inline uint64_t query_n_slots(const QueryParams &p)
 {
     return (uint64_t)p.n_slices + (uint64_t)p.n_tiles * p.n_queries;
 }
+// byte offset of (chunk of the tile, partial slot, plane) in `partial`: chunk-major, so that all slots
+// and planes of one merge item are contiguous
+__host__ __device__ inline uint64_t partial_offset(const QueryParams &p, uint32_t chunk, uint64_t slot, uint32_t plane)
+{
+    return (((uint64_t)chunk * p.n_slots_total + slot) * p.planes_per_slot + plane) * p.merge_cb;
+}
 inline uint64_t query_partial_bytes(const QueryParams &p)
 {
-    // + one slot of slack: the merge reads whole 16-plane groups
-    return (query_n_slots(p) * p.planes_per_slot + kSegPlanes) * p.tile_bytes;
+    return (uint64_t)p.merge_cpt * p.n_slots_total * p.planes_per_slot * p.merge_cb + 256;
 }
 
 // Stage 1: gather + AND + vertical count, per-segment bit planes -> p.partial.
@@ -116,6 +156,7 @@ inline uint64_t prehash_bytes_per_kmer(uint32_t k) { return (uint64_t)k + 1 + 4u
 // Stage 2: sum (or AND) the partial planes of every (query, column), expand to integers -> p.out.
 cudaError_t launch_merge(const QueryParams &p, int mode, cudaStream_t stream);
 cudaError_t query_kernels_init();  // opt-in to large dynamic shared memory
+cudaError_t merge_kernels_init();
 
 // ---- helper kernels (aux_kernels.cu) -------------------------------------------------------
 cudaError_t launch_hash_kmers(const char *d_kmers, uint64_t n, int k, int h, uint64_t m, int canonical,

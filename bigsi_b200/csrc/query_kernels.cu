@@ -29,19 +29,6 @@
 
 namespace bigsi {
 
-__device__ __forceinline__ unsigned long long gtime()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-// timeline slots per CTA: 0 entry, 1 producer first issue, 2 first slot landed, 3 last slot consumed,
-// 4 after flush, 5 producer last issue, 6 past the grid barrier, 7 merge phase done
-#define BIGSI_TS(slot)                                                            \
-    do {                                                                          \
-        if (P.debug_ts) P.debug_ts[(size_t)blockIdx.x * 8 + (slot)] = gtime();    \
-    } while (0)
-
 struct W4 {
     uint32_t v[4];
 };
@@ -181,9 +168,10 @@ __device__ __forceinline__ void stg128(void *p, const W4 &x)
     *reinterpret_cast<uint4 *>(p) = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
 }
 
-// write the planes of one segment to its partial slot (plane-major, tile_bytes per plane).  All
-// planes_per_slot planes are written (planes the segment cannot reach are zero in the counter), so
-// the merge loads them without looking at segment lengths.
+// write the planes of one segment to its partial slot: plane b of this thread's 16-byte unit goes to
+// slot_unit + b * plane_stride (plane_stride = merge_cb, see partial_offset).  All planes_per_slot
+// planes are written (planes the segment cannot reach are zero in the counter), so the merge loads
+// them without looking at segment lengths.
 __device__ __forceinline__ void flush_planes(const VCounter &c, uint32_t pps, uint8_t *slot_unit, uint32_t plane_stride)
 {
     stg128(slot_unit, c.ones);
@@ -334,16 +322,240 @@ __device__ __forceinline__ void tma_consumer(const QueryParams &P, const uint8_t
         if (threadIdx.x == 0) BIGSI_TS(3);
         if (active) {
             const uint64_t slot = (uint64_t)s.slice + (uint64_t)s.tile * P.n_queries + s.q;
-            uint8_t *dst = P.partial + slot * P.planes_per_slot * P.tile_bytes + unit * 16;
+            const uint32_t chunk = unit * 16 / P.merge_cb;  // merge chunk this unit's columns belong to
+            uint8_t *dst = P.partial + partial_offset(P, chunk, slot, 0) + (unit * 16 - chunk * P.merge_cb);
             if (MODE == kModeCounts) {
                 ctr.finish(nhi);
-                flush_planes(ctr, P.planes_per_slot, dst, P.tile_bytes);
+                flush_planes(ctr, P.planes_per_slot, dst, P.merge_cb);
             } else {
                 stg128(dst, acc);
             }
         }
         if (threadIdx.x == 0) BIGSI_TS(4);
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// "solo" path: one query, one tile, one slice per CTA, k-mers hashed in the kernel (QueryParams::solo)
+// ------------------------------------------------------------------------------------------
+constexpr int kBarHashGroup = 1;   // named barrier of the consumer warps while they hash
+constexpr int kBarIdsReady = 2;    // consumers -> producer: the id table is complete
+constexpr uint32_t kStageCntOffset = 640;  // uint32 [kMaxStages] k-mers per ring slot, in the shared-memory header
+constexpr uint32_t kPoolStashOffset = 768; // int32 [kPoolBatch][kPoolMaxH] row ids of one claimed pool batch
+constexpr int kPoolBatch = 8;
+
+struct SoloGeom {
+    uint64_t begin;     // first k-mer of this CTA's contiguous range
+    uint32_t cnt;       // k-mers in the range (hashed by this CTA)
+    uint32_t n_static;  // the first n_static are gathered by this CTA itself
+    uint32_t n_pool;    // the last n_pool go to the shared pool
+    uint32_t n_first;   // static k-mers the producer warp hashes itself (one ring-full)
+};
+__device__ __forceinline__ uint32_t solo_range_cnt(const QueryParams &P, uint32_t cta)
+{
+    const uint64_t b = (uint64_t)cta * P.items_per_slice;
+    return b >= P.total_kmers ? 0u : (uint32_t)min((uint64_t)P.items_per_slice, P.total_kmers - b);
+}
+__device__ __forceinline__ SoloGeom solo_geometry(const QueryParams &P)
+{
+    SoloGeom g;
+    g.begin = (uint64_t)blockIdx.x * P.items_per_slice;
+    g.cnt = solo_range_cnt(P, blockIdx.x);
+    g.n_pool = min(P.pool_share, g.cnt);
+    g.n_static = g.cnt - g.n_pool;
+    g.n_first = min(g.n_static, P.n_stages * P.kmers_per_stage);
+    return g;
+}
+
+__device__ __forceinline__ void solo_producer(const QueryParams &P, const SoloGeom &sg, uint8_t *smem, uint8_t *ring,
+                                              int32_t *ids, uint8_t *scratch, uint64_t *full, uint64_t *empty)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t h = P.h, G = P.kmers_per_stage;
+    const uint32_t tw = min(P.tile_bytes, P.row_bytes16);
+    const uint32_t seg_stride = P.tile_bytes;
+    const uint32_t stage_bytes = G * h * seg_stride;
+    const uint64_t policy = policy_evict_first();
+    volatile uint32_t *stage_cnt = reinterpret_cast<volatile uint32_t *>(smem + kStageCntOffset);
+    uint32_t stage = 0, parity = 0;
+    auto advance = [&]() {
+        if (++stage == P.n_stages) {
+            stage = 0;
+            parity ^= 1;
+        }
+    };
+    // one ring slot: nk k-mers whose row ids are id[0 .. nk*h), read through `load`
+    auto issue = [&](uint32_t nk, auto load) {
+        const uint32_t n_rows = nk * h;
+        uint8_t *dst0 = ring + (size_t)stage * stage_bytes;
+        mbar_wait(&empty[stage], parity ^ 1);  // slot drained by all consumer warps
+        if (lane == 0) {
+            stage_cnt[stage] = nk;
+            mbar_arrive_expect_tx(&full[stage], n_rows * tw);
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < n_rows; i += 32)
+            bulk_g2s_hint(dst0 + (size_t)i * seg_stride, P.matrix + (uint64_t)(uint32_t)load(i) * P.pitch, tw, &full[stage],
+                          policy);
+        advance();
+    };
+
+    // the first ring-full of k-mers is hashed by this warp alone, so the gather starts at once
+    hash_kmers_group(P.kmers + sg.begin * P.k, sg.n_first, (int)P.k, (int)h, P.num_rows, 1, scratch, ids, lane, 32u,
+                     SyncWarp());
+    __syncwarp();
+    if (lane == 0) BIGSI_TS(1);
+    uint32_t k0 = 0;
+    for (; k0 < sg.n_first; k0 += G) {
+        const int32_t *id = ids + (size_t)k0 * h;
+        issue(min(G, sg.n_first - k0), [&](uint32_t i) { return id[i]; });
+    }
+    named_bar_sync(kBarIdsReady, blockDim.x);  // the consumer warps have hashed the rest of the range
+    for (; k0 < sg.n_static; k0 += G) {
+        const int32_t *id = ids + (size_t)k0 * h;
+        issue(min(G, sg.n_static - k0), [&](uint32_t i) { return id[i]; });
+    }
+
+    // pool: claim kPoolBatch indices with one atomic (index -> owner CTA round-robin), resolve them lane
+    // parallel (owner's ready flag, row ids), then gather them one k-mer per ring slot.  At most `cap`
+    // pooled k-mers per CTA so that the segment counter cannot overflow; every claimed index below
+    // pool_total IS processed (a claim is only made with capacity reserved for all of it).
+    const uint32_t pool_total = P.pool_share * gridDim.x;
+    const uint32_t cap = P.solo_max_kmers - sg.n_static;
+    int32_t *stash = reinterpret_cast<int32_t *>(smem + kPoolStashOffset);  // [kPoolBatch][h <= kPoolMaxH]
+    uint32_t taken = 0;
+    bool exhausted = pool_total == 0;
+    while (!exhausted && taken < cap) {
+        const uint32_t n = min((uint32_t)kPoolBatch, cap - taken);
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(P.pool_counter, n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= pool_total) break;
+        const uint32_t idx = base + lane;
+        uint32_t owner = 0, j = 0;
+        bool real = false;
+        if (lane < n && idx < pool_total) {
+            owner = idx % gridDim.x;
+            j = idx / gridDim.x;
+            real = j < min(P.pool_share, solo_range_cnt(P, owner));  // short ranges pool fewer k-mers
+        }
+        if (base + n >= pool_total) exhausted = true;
+        if (real)
+            while (ld_acquire_gpu_u64(P.pool_ready + owner) < P.pool_epoch) {
+            }
+        const uint32_t real_mask = __ballot_sync(0xffffffffu, real);
+        for (uint32_t t0 = 0; t0 < n * h; t0 += 32) {  // warp-uniform trip count (shuffles inside)
+            const uint32_t t = t0 + lane;
+            const bool in = t < n * h;
+            const uint32_t e = in ? t / h : 0, r = t - e * h;
+            const uint32_t oe = __shfl_sync(0xffffffffu, owner, e), je = __shfl_sync(0xffffffffu, j, e);
+            if (in && ((real_mask >> e) & 1u)) stash[t] = __ldcg(P.pool_ids + ((size_t)oe * P.pool_share + je) * h + r);
+        }
+        __syncwarp();
+        for (uint32_t e = 0; e < n; ++e) {
+            if (!((real_mask >> e) & 1u)) continue;
+            const int32_t *id = stash + e * h;
+            issue(1, [&](uint32_t i) { return id[i]; });
+        }
+        __syncwarp();  // the stash is reused by the next batch
+        taken += __popc(real_mask);
+    }
+    // end marker: an empty slot
+    mbar_wait(&empty[stage], parity ^ 1);
+    if (lane == 0) {
+        stage_cnt[stage] = 0;
+        mbar_arrive(&full[stage]);
+        BIGSI_TS(5);
+    }
+}
+
+template <int MODE, int HC>
+__device__ __forceinline__ void solo_consumer(const QueryParams &P, const SoloGeom &sg, uint8_t *smem, const uint8_t *ring,
+                                              int32_t *ids, uint8_t *scratch, uint64_t *full, uint64_t *empty)
+{
+    const uint32_t unit = threadIdx.x, lane = threadIdx.x & 31;
+    const uint32_t consumer_threads = blockDim.x - 32;
+    const uint32_t h = HC ? HC : P.h, G = P.kmers_per_stage;
+    const uint32_t seg_stride = P.tile_bytes;
+    const uint32_t stage_bytes = G * h * seg_stride;
+    const uint32_t tw = min(P.tile_bytes, P.row_bytes16);
+    volatile uint32_t *stage_cnt = reinterpret_cast<volatile uint32_t *>(smem + kStageCntOffset);
+
+    // hash the part of the range the producer did not take, publish the pooled ids, release the producer
+    const uint32_t rest = sg.cnt - sg.n_first;
+    hash_kmers_group(P.kmers + (sg.begin + sg.n_first) * P.k, rest, (int)P.k, (int)P.h, P.num_rows, 1,
+                     scratch + ((hash_scratch_bytes(sg.n_first, P.k) + 127) & ~127ull), ids + (size_t)sg.n_first * P.h, unit,
+                     consumer_threads, SyncNamed{kBarHashGroup, (int)consumer_threads});
+    named_bar_sync(kBarHashGroup, consumer_threads);
+    if (P.pool_share) {
+        int32_t *dst = P.pool_ids + (size_t)blockIdx.x * P.pool_share * P.h;
+        const int32_t *src = ids + (size_t)sg.n_static * P.h;
+        for (uint32_t i = unit; i < sg.n_pool * P.h; i += consumer_threads) dst[i] = src[i];
+        __threadfence();
+        named_bar_sync(kBarHashGroup, consumer_threads);
+        if (unit == 0) st_release_gpu_u64(P.pool_ready + blockIdx.x, P.pool_epoch);
+    }
+    named_bar_arrive(kBarIdsReady, blockDim.x);
+    if (unit == 0) BIGSI_TS(9);
+
+    const bool active = unit * 16 < tw;
+    const uint32_t nhi = P.planes_per_slot > 3 ? P.planes_per_slot - 3 : 0;
+    VCounter ctr;
+    W4 acc;
+    if (MODE == kModeCounts) ctr.reset();
+    else acc = W4{{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}};
+    uint32_t stage = 0, parity = 0;
+    bool first_slot = true;
+    for (;;) {
+        mbar_wait(&full[stage], parity);
+        if (first_slot && unit == 0) BIGSI_TS(2);
+        first_slot = false;
+        const uint32_t gn = stage_cnt[stage];
+        if (gn == 0) break;  // end marker
+        if (active && !(P.debug_flags & 1u)) {
+            const uint8_t *base = ring + (size_t)stage * stage_bytes + unit * 16;
+            for (uint32_t g = 0; g < gn; ++g) {
+                const uint8_t *b = base + g * h * seg_stride;
+                W4 x = to_w4(lds128(b));
+                if (HC == 3) {
+                    const W4 y = to_w4(lds128(b + seg_stride));
+                    const W4 z = to_w4(lds128(b + 2 * seg_stride));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x.v[j] = and3(x.v[j], y.v[j], z.v[j]);
+                } else {
+                    for (uint32_t r = 1; r < h; ++r) {
+                        const W4 y = to_w4(lds128(b + r * seg_stride));
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) x.v[j] &= y.v[j];
+                    }
+                }
+                if (MODE == kModeCounts) {
+                    ctr.add(x, nhi);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc.v[j] &= x.v[j];
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == P.n_stages) {
+            stage = 0;
+            parity ^= 1;
+        }
+    }
+    if (unit == 0) BIGSI_TS(3);
+    if (active) {
+        const uint32_t chunk = unit * 16 / P.merge_cb;
+        uint8_t *dst = P.partial + partial_offset(P, chunk, blockIdx.x, 0) + (unit * 16 - chunk * P.merge_cb);
+        if (MODE == kModeCounts) {
+            ctr.finish(nhi);
+            flush_planes(ctr, P.planes_per_slot, dst, P.merge_cb);
+        } else {
+            stg128(dst, acc);
+        }
+    }
+    if (unit == 0) BIGSI_TS(4);
 }
 
 // grid-wide barrier over a monotonic arrival counter (all CTAs of the launch are co-resident: the
@@ -357,7 +569,6 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *counter, unsign
         unsigned long long seen;
         do {
             asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter) : "memory");
-            if (seen < target) __nanosleep(40);
         } while (seen < target);
         __threadfence();
     }
@@ -370,16 +581,19 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty = full + kMaxStages;
+    uint64_t *merge_bar = empty + kMaxStages;  // staging barrier of the merge phase
     int32_t *ids = reinterpret_cast<int32_t *>(smem + kSmemHeaderBytes);
     uint8_t *ring = smem + kSmemHeaderBytes + P.ids_bytes;
     const uint32_t consumer_warps = (blockDim.x >> 5) - 1;
 
     if (threadIdx.x == 0) {
         BIGSI_TS(0);
+        if (P.debug_ts) P.debug_ts[(size_t)blockIdx.x * kDebugStamps + 14] = (unsigned long long)clock64();
         for (uint32_t s = 0; s < P.n_stages; ++s) {
             mbar_init(&full[s], 1);                // one arrive.expect_tx by the producer + tx bytes
             mbar_init(&empty[s], consumer_warps);  // one arrive per consumer warp
         }
+        mbar_init(merge_bar, 1);
         fence_barrier_init();
     }
     __syncthreads();
@@ -387,6 +601,7 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
     // produced (k-mers / row ids) and overwrite what the previous query's merge may still read
     grid_launch_dependents();
     grid_dependency_wait();
+    if (threadIdx.x == 0) BIGSI_TS(8);
 
     if (P.n_hits != nullptr)  // hit counters of the fused threshold (stage 2 adds to them)
         for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < P.n_queries; q += gridDim.x * blockDim.x)
@@ -408,20 +623,27 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
         __syncthreads();
     }
 
-    if (P.prehash && have_work) {
-        // n_tiles == 1 and one slice per CTA: this CTA's k-mers are [begin, end), contiguous in memory.
-        // The (still empty) ring is the scratch; the ids land in their own table in front of it.
-        hash_kmers_cooperative(P.kmers + begin * P.k, (uint32_t)(end - begin), (int)P.k, (int)P.h, P.num_rows, 1, ring,
-                               ids);
-        fence_proxy_async();  // generic-proxy writes to the ring are ordered before the TMA writes
-        __syncthreads();
-    }
-
-    if (have_work) {
+    if (P.solo) {
+        const SoloGeom sg = solo_geometry(P);
+        uint8_t *scratch = smem + kSmemHeaderBytes + P.ids_table_bytes;
         if ((threadIdx.x >> 5) == consumer_warps)
-            tma_producer(P, ring, ids, full, empty, begin, end);
+            solo_producer(P, sg, smem, ring, ids, scratch, full, empty);
         else
-            tma_consumer<MODE, HC>(P, ring, full, empty, begin, end);
+            solo_consumer<MODE, HC>(P, sg, smem, ring, ids, scratch, full, empty);
+    } else {
+        if (P.prehash && have_work) {
+            // n_tiles == 1 and one slice per CTA: this CTA's k-mers are [begin, end), contiguous in memory
+            hash_kmers_cooperative(P.kmers + begin * P.k, (uint32_t)(end - begin), (int)P.k, (int)P.h, P.num_rows, 1,
+                                   smem + kSmemHeaderBytes + P.ids_table_bytes, ids);
+            __syncthreads();
+            if (threadIdx.x == 0) BIGSI_TS(9);
+        }
+        if (have_work) {
+            if ((threadIdx.x >> 5) == consumer_warps)
+                tma_producer(P, ring, ids, full, empty, begin, end);
+            else
+                tma_consumer<MODE, HC>(P, ring, full, empty, begin, end);
+        }
     }
 
     if (P.fuse_merge) {
@@ -429,25 +651,29 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
         // merge work items; the drained ring is the scratch
         grid_barrier(P.barrier, P.barrier_target);
         if (threadIdx.x == 0) BIGSI_TS(6);
-        for (uint64_t item = blockIdx.x; item < P.merge_items; item += gridDim.x) {
-            if (MODE == kModeCounts) {
-                if (P.merge_ng == 1) merge_counts_item<1>(P, item, P.merge_gpi, ring);
-                else merge_counts_item<4>(P, item, P.merge_gpi, ring);
-            } else {
-                merge_and_item(P, item, ring);
-            }
+        if (P.solo && blockIdx.x == 0 && threadIdx.x == 0) *P.pool_counter = 0u;  // every claim of this launch is done
+        uint32_t merge_phase = 0;
+        for (uint64_t item = blockIdx.x; item < P.merge_items; item += gridDim.x)
+            merge_item<MODE>(P, item, ring, merge_bar, merge_phase);
+        if (threadIdx.x == 0) {
+            BIGSI_TS(7);
+            if (P.debug_ts) P.debug_ts[(size_t)blockIdx.x * kDebugStamps + 15] = (unsigned long long)clock64();
         }
-        if (threadIdx.x == 0) BIGSI_TS(7);
+        if (P.debug_flags & 4u) {  // instrumentation only: run the merge phase again (warm caches), results are garbage
+            for (uint64_t item = blockIdx.x; item < P.merge_items; item += gridDim.x)
+                merge_item<MODE>(P, item, ring, merge_bar, merge_phase);
+            if (threadIdx.x == 0) BIGSI_TS(13);
+        }
 
         if (P.n_sinks) {
             // the last CTA to finish its merge items publishes query 0's hit list to every sink
-            __shared__ int s_last;
+            int *s_last = reinterpret_cast<int *>(smem + 2 * kMaxStages * 8 + 64);  // header space behind the mbarriers
             if (threadIdx.x == 0) {
                 __threadfence();
-                s_last = atomicAdd(P.done_counter, 1ull) + 1ull == P.done_target;
+                *s_last = atomicAdd(P.done_counter, 1ull) + 1ull == P.done_target;
             }
             __syncthreads();
-            if (s_last) {
+            if (*s_last) {
                 __threadfence();
                 const unsigned long long n = *reinterpret_cast<volatile unsigned long long *>(P.n_hits);
                 unsigned long long m = n < P.hit_cap ? n : P.hit_cap;
@@ -501,7 +727,7 @@ cudaError_t query_kernels_init()
     BIGSI_SET_SMEM((fused_query<kModeAnd, 3>))
     BIGSI_SET_SMEM((fused_query<kModeAnd, 0>))
 #undef BIGSI_SET_SMEM
-    return cudaSuccess;
+    return merge_kernels_init();
 }
 
 }  // namespace bigsi
