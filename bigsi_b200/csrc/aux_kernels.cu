@@ -15,7 +15,7 @@ constexpr int kHashSmemBytes = 40 * 1024;
 
 __global__ void __launch_bounds__(kHashThreads) hash_kmers_kernel(const uint8_t *__restrict__ kmers, uint64_t n, int k,
                                                                  int h, uint32_t m, int canonical, uint32_t kpb,
-                                                                 int use_smem, int32_t *__restrict__ rows_out)
+                                                                 int use_smem, int32_t *__restrict__ rows_out, uint64_t magic)
 {
     extern __shared__ __align__(16) uint8_t sk[];
     grid_dependency_wait();  // the previous query's fused kernel may still be reading rows_out
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(kHashThreads) hash_kmers_kernel(const uint8_t 
     const uint8_t *g0 = kmers + base * (uint64_t)k;
     const int nblocks = k >> 2, rem = k & 3;
     if (use_smem) {
-        hash_kmers_cooperative(g0, cnt, k, h, m, canonical, sk, rows_out + base * (uint64_t)h);
+        hash_kmers_cooperative(g0, cnt, k, h, m, canonical, sk, rows_out + base * (uint64_t)h, magic);
         return;
     }
     // very long "k-mers" (k > the staging buffer): one thread per (k-mer, seed) straight from global
@@ -75,7 +75,7 @@ cudaError_t launch_hash_kmers(const char *d_kmers, uint64_t n, int k, int h, uin
     const size_t smem = use_smem ? (size_t)kpb * per_kmer + 96 : 0;
     return launch_pdl(hash_kmers_kernel, dim3((unsigned)blocks), dim3(kHashThreads), smem, stream,
                       reinterpret_cast<const uint8_t *>(d_kmers), n, k, h, (uint32_t)m, canonical, kpb, use_smem,
-                      d_rows_out);
+                      d_rows_out, mod_magic((uint32_t)m));
 }
 
 // ------------------------------------------------------------------------------------------

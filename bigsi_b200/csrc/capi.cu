@@ -94,7 +94,7 @@ struct PinnedBuf {
         if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
-        cudaError_t e = cudaHostAlloc(&p, round_up(bytes, 4096), cudaHostAllocDefault);
+        cudaError_t e = cudaHostAlloc(&p, round_up(bytes, 4096), cudaHostAllocMapped | cudaHostAllocPortable);
         if (e == cudaSuccess) cap = round_up(bytes, 4096);
         return e;
     }
@@ -136,11 +136,13 @@ struct bigsi_b200_index {
     int64_t opt_tile_bytes = 0, opt_grid = 0, opt_kmers_per_stage = 0, opt_n_stages = 0, opt_ctas_per_sm = 0;
     bool timing = false;
     int64_t opt_debug_flags = 0;
-    int64_t opt_prehash = 1, opt_fuse_merge = 1, opt_merge_chunk_bytes = 0, opt_solo = 1, opt_pool_pct = 12;
+    int64_t opt_prehash = 1, opt_fuse_merge = 1, opt_merge_chunk_bytes = 0, opt_solo = 1, opt_pool_pct = 12, opt_zero_copy = 1;
     DevBuf d_pool;            // pool ids / ready flags / claim counter of the solo path
     uint64_t pool_epoch = 0;  // in-kernel hashing / in-kernel merge (1 = when possible)
     DevBuf d_barrier;                             // grid-barrier arrival counter of the fused kernel
-    uint64_t barrier_target = 0;
+    uint64_t barrier_target = 0, done_target = 0;
+    PinnedBuf h_sink, h_kmers;   // mapped pinned: result block the kernel publishes to / staging of pageable k-mers
+    uint64_t sink_seq = 0;
     // scratch
     DevBuf debug_ts;
     DevBuf partial, d_kmers, d_rows, d_qoff, d_out, d_min, d_nhits, d_bloom, d_planted;
@@ -181,6 +183,7 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
     p.total_kmers = total_kmers;
     p.num_cols = (uint32_t)ix->num_cols;
     p.num_rows = (uint32_t)ix->num_rows;
+    p.mod_magic = mod_magic((uint32_t)ix->num_rows);
     p.row_bytes16 = (uint32_t)round_up(row_bytes ? row_bytes : 1, 16);
 
     // column tile: as wide as the consumer warps allow, but >= 3 one-k-mer stages must fit in smem
@@ -313,6 +316,16 @@ struct HitsOut {
     uint32_t *counts = nullptr;
     unsigned long long *n = nullptr;
     uint64_t cap = 0;
+    // single-query extras: threshold by value (no device array), optional input gate, and result
+    // publication by the kernel itself to host / peer sinks (query.cuh:QueryParams)
+    bool by_value = false;
+    uint32_t min_value = 0;
+    const unsigned long long *wait_flag = nullptr;
+    unsigned long long wait_value = 0;
+    uint32_t n_sinks = 0, sink_spec = 0;
+    unsigned long long *sinks[kMaxSinks] = {};
+    unsigned long long sink_seq = 0;
+    bool *published = nullptr;  // set when the launch will publish to the sinks (needs the in-kernel merge)
 };
 
 // One query batch on `stream`.  Exactly one of d_rows / d_kmers is given; with k-mers the kernel
@@ -365,6 +378,23 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
         p.hit_counts = hits->counts;
         p.n_hits = hits->n;
         p.hit_cap = hits->cap;
+        if (hits->by_value) {
+            p.min_by_value = 1;
+            p.min_kmers_value = hits->min_value;
+        }
+        p.wait_flag = hits->wait_flag;
+        p.wait_value = hits->wait_value;
+        if (hits->published) *hits->published = false;
+        if (hits->n_sinks && p.fuse_merge && grid > 0 && n_queries == 1) {
+            p.n_sinks = hits->n_sinks;
+            p.sink_spec = hits->sink_spec;
+            p.sink_seq = hits->sink_seq;
+            for (uint32_t i = 0; i < hits->n_sinks; ++i) p.sinks[i] = hits->sinks[i];
+            p.done_counter = static_cast<unsigned long long *>(ix->d_barrier.p) + 16;
+            ix->done_target += (uint64_t)grid;
+            p.done_target = ix->done_target;
+            if (hits->published) *hits->published = true;
+        }
         // stage 1 zeroes the hit counters; without a stage-1 launch do it here
         if (grid == 0) CK(cudaMemsetAsync(hits->n, 0, n_queries * sizeof(unsigned long long), stream));
     }
@@ -497,7 +527,8 @@ int bigsi_b200_host_alloc(uint64_t bytes, void **ptr_out)
 {
     if (!ptr_out) return fail(BIGSI_B200_ERR_INVALID, "null ptr_out");
     *ptr_out = nullptr;
-    cudaError_t e = cudaHostAlloc(ptr_out, bytes ? bytes : 1, cudaHostAllocDefault);
+    // mapped + portable: the query kernel can read k-mers straight out of such a buffer (zero copy)
+    cudaError_t e = cudaHostAlloc(ptr_out, bytes ? bytes : 1, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) return fail_cuda(e, "cudaHostAlloc");
     return 0;
 }
@@ -575,6 +606,8 @@ int bigsi_b200_index_destroy(bigsi_b200_index *ix)
                       &ix->d_nhits, &ix->d_bloom, &ix->d_planted};
     for (DevBuf *b : bufs) b->release();
     ix->h_small.release();
+    ix->h_sink.release();
+    ix->h_kmers.release();
     if (ix->matrix) cudaFree(ix->matrix);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
@@ -616,6 +649,7 @@ int bigsi_b200_index_set_option(bigsi_b200_index *ix, const char *key, int64_t v
     else if (!strcmp(key, "fuse_merge")) ix->opt_fuse_merge = value;
     else if (!strcmp(key, "merge_chunk_bytes")) ix->opt_merge_chunk_bytes = value;
     else if (!strcmp(key, "solo")) ix->opt_solo = value;
+    else if (!strcmp(key, "zero_copy")) ix->opt_zero_copy = value;
     else if (!strcmp(key, "pool_pct")) ix->opt_pool_pct = value > 100 ? 100 : value;
     else return fail(BIGSI_B200_ERR_INVALID, "unknown option '%s'", key);
     return 0;
@@ -965,6 +999,91 @@ int bigsi_b200_search_rows(bigsi_b200_index *ix, int mode, const int32_t *rows, 
     return search_full(ix, mode, nullptr, rows, q_offsets, n_queries, 0, h, out, out_stride);
 }
 
+// BIGSI.search for ONE query with no staging copies: the kernel reads the raw k-mers straight out of
+// (mapped, pinned) host memory, takes the threshold by value and publishes the hit list itself into a
+// mapped host block; the host polls that block's sequence word instead of synchronising the stream.
+// Returns 1 when the path does not apply (the caller falls back to the staged path).
+static int search_one_zero_copy(bigsi_b200_index *ix, const char *kmers, const int64_t *qoff, int k, int h,
+                                uint32_t min_kmers, int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_out)
+{
+    if (!qoff || qoff[0] != 0 || qoff[1] <= 0 || !kmers || k < 1 || h < 1 || ix->num_cols == 0) return 1;
+    const uint64_t total = (uint64_t)qoff[1];
+    cudaError_t e;
+    // k-mers: use the caller's buffer when the device can address it, else one memcpy into our pinned buffer
+    const char *d_kmers = nullptr;
+    cudaPointerAttributes attr;
+    e = cudaPointerGetAttributes(&attr, kmers);
+    if (e == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+        d_kmers = static_cast<const char *>(attr.devicePointer);
+    } else {
+        (void)cudaGetLastError();
+        if ((e = ix->h_kmers.reserve(total * (uint64_t)k + 64)) != cudaSuccess) return fail_cuda(e, "pinned staging");
+        memcpy(ix->h_kmers.p, kmers, total * (uint64_t)k);
+        void *dp = nullptr;
+        CK(cudaHostGetDevicePointer(&dp, ix->h_kmers.p, 0));
+        d_kmers = static_cast<const char *>(dp);
+    }
+    const uint64_t spec = cap < 1024 ? cap : 1024;  // hits the host block holds; longer lists are fetched afterwards
+    if ((e = ix->h_sink.reserve(16 + 2 * spec * 4 + 64)) != cudaSuccess) return fail_cuda(e, "pinned result block");
+    if ((e = ix->d_nhits.reserve(8 + 2 * cap * 4 + 16)) != cudaSuccess) return fail_cuda(e, "staging");
+    volatile unsigned long long *blk = static_cast<volatile unsigned long long *>(ix->h_sink.p);
+    void *d_blk = nullptr;
+    CK(cudaHostGetDevicePointer(&d_blk, ix->h_sink.p, 0));
+    uint8_t *dev = static_cast<uint8_t *>(ix->d_nhits.p);
+    bool published = false;
+    HitsOut ho;
+    ho.n = reinterpret_cast<unsigned long long *>(dev);
+    ho.cols = reinterpret_cast<int32_t *>(dev + 8);
+    ho.counts = reinterpret_cast<uint32_t *>(dev + 8 + cap * 4);
+    ho.cap = cap;
+    ho.by_value = true;
+    ho.min_value = min_kmers;
+    ho.n_sinks = 1;
+    ho.sinks[0] = static_cast<unsigned long long *>(d_blk);
+    ho.sink_spec = (uint32_t)spec;
+    ho.sink_seq = ++ix->sink_seq;
+    ho.published = &published;
+    if (int rc = run_query(ix, BIGSI_B200_MODE_COUNTS, nullptr, d_kmers, k, nullptr, 1, total, total, h, nullptr, 0, ix->stream,
+                           &ho))
+        return rc;
+    uint64_t n = 0;
+    if (published) {
+        // poll the sequence word; look at the stream now and then so that a failed launch cannot hang us
+        uint64_t spins = 0;
+        while (blk[0] != ho.sink_seq) {
+            if ((++spins & 0x3fff) == 0) {
+                e = cudaStreamQuery(ix->stream);
+                if (e != cudaErrorNotReady) {
+                    if (e != cudaSuccess) return fail_cuda(e, "query kernel");
+                    if (blk[0] != ho.sink_seq) return fail(BIGSI_B200_ERR_CUDA, "query kernel finished without publishing its result");
+                }
+            }
+        }
+        n = blk[1];
+        const uint64_t m = n < cap ? n : cap;
+        const uint64_t ms = m < spec ? m : spec;
+        const int32_t *hc = reinterpret_cast<const int32_t *>(const_cast<unsigned long long *>(blk) + 2);
+        memcpy(cols_out, hc, ms * 4);
+        memcpy(counts_out, hc + spec, ms * 4);
+        if (m > spec) {  // a long hit list: the device buffers are complete once the block was published
+            CK(cudaMemcpyAsync(cols_out, ho.cols, m * 4, cudaMemcpyDeviceToHost, ix->stream));
+            CK(cudaMemcpyAsync(counts_out, ho.counts, m * 4, cudaMemcpyDeviceToHost, ix->stream));
+            CK(cudaStreamSynchronize(ix->stream));
+        }
+    } else {
+        CK(cudaMemcpyAsync(&n, ho.n, 8, cudaMemcpyDeviceToHost, ix->stream));
+        CK(cudaStreamSynchronize(ix->stream));
+        const uint64_t m = n < cap ? n : cap;
+        if (m) {
+            CK(cudaMemcpyAsync(cols_out, ho.cols, m * 4, cudaMemcpyDeviceToHost, ix->stream));
+            CK(cudaMemcpyAsync(counts_out, ho.counts, m * 4, cudaMemcpyDeviceToHost, ix->stream));
+            CK(cudaStreamSynchronize(ix->stream));
+        }
+    }
+    n_out[0] = n;
+    return 0;
+}
+
 int bigsi_b200_search_kmers_hits(bigsi_b200_index *ix, const char *kmers, const int64_t *q_offsets, uint64_t n_queries,
                                  int k, int h, const uint32_t *min_kmers, int32_t *cols_out, uint32_t *counts_out,
                                  uint64_t cap, uint64_t *n_out)
@@ -974,6 +1093,10 @@ int bigsi_b200_search_kmers_hits(bigsi_b200_index *ix, const char *kmers, const 
     if (!min_kmers || !n_out || (cap && (!cols_out || !counts_out))) return fail(BIGSI_B200_ERR_INVALID, "null pointer");
     DeviceGuard guard(ix->device);
     cudaError_t e;
+    if (n_queries == 1 && ix->opt_zero_copy != 0) {
+        int rc = search_one_zero_copy(ix, kmers, q_offsets, k, h, min_kmers[0], cols_out, counts_out, cap, n_out);
+        if (rc != 1) return rc;  // 1 = not applicable, take the staged path below
+    }
     // one device block [n_hits: Q x u64][cols: Q x cap][counts: Q x cap] so that small results come
     // back in ONE device-to-host copy
     const uint64_t n_bytes = n_queries * 8, list_bytes = n_queries * cap * 4;

@@ -52,18 +52,97 @@ __host__ __device__ inline uint64_t hash_scratch_bytes(uint64_t cnt, uint32_t k)
     return cnt * ((uint64_t)k + 1 + 4ull * ((((uint64_t)k + 3) >> 2) | 1)) + 96;
 }
 
-// Synchronisation policies of a hashing group: the whole CTA, a subset of warps on a named
-// barrier, or one warp.
-struct SyncBlock {
-    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+// Lemire's fastmod: a mod m for 32-bit a with magic = 2^64 / m + 1 (precomputed on the host; 0 for m == 1)
+__host__ __device__ inline uint64_t mod_magic(uint32_t m) { return m ? 0xffffffffffffffffull / m + 1ull : 0ull; }
+__device__ __forceinline__ uint32_t fastmod_u32(uint32_t a, uint64_t magic, uint32_t m)
+{
+    return (uint32_t)__umul64hi(magic * (uint64_t)a, (uint64_t)m);
+}
+// fmix32 + Python floor-mod of the SIGNED hash, with the precomputed magic
+__device__ __forceinline__ int32_t murmur_finish_fastmod(uint32_t h1, uint32_t len, uint32_t m, uint64_t magic)
+{
+    h1 ^= len;
+    h1 ^= h1 >> 16;
+    h1 *= 0x85ebca6bu;
+    h1 ^= h1 >> 13;
+    h1 *= 0xc2b2ae35u;
+    h1 ^= h1 >> 16;
+    if ((int32_t)h1 >= 0) return (int32_t)fastmod_u32(h1, magic, m);
+    const uint32_t r = fastmod_u32(0u - h1, magic, m);  // |s| mod m
+    return (int32_t)(r ? m - r : 0u);
+}
+// complement of four packed ASCII bases: A<->T, C<->G, anything else (and zero padding) unchanged
+__device__ __forceinline__ uint32_t comp_base4(uint32_t w)
+{
+    const uint32_t at = __vcmpeq4(w, 0x41414141u) | __vcmpeq4(w, 0x54545454u);
+    const uint32_t cg = __vcmpeq4(w, 0x43434343u) | __vcmpeq4(w, 0x47474747u);
+    return w ^ (at & 0x15151515u) ^ (cg & 0x04040404u);
+}
+
+// One k-mer of length k <= 32 entirely in registers: s = its bytes in SHARED memory.  Forward and
+// reverse-complement strings are built as eight little-endian words (zero padded), compared as
+// big-endian integers (= lexicographic byte order, utils/fncts.py:38-39), and the smaller one goes
+// through MurmurHash3_x86_32 for seeds 0..h-1 (the seed-independent k1 mixing is shared).
+__device__ __forceinline__ void hash_one_kmer_regs(const uint8_t *s, int k, int h, uint32_t m, uint64_t magic, int canonical,
+                                                   int32_t *ids)
+{
+    uint32_t F[8], R[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) F[j] = R[j] = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        if (i < k) {
+            F[i >> 2] |= (uint32_t)s[i] << (8 * (i & 3));
+            R[i >> 2] |= (uint32_t)s[k - 1 - i] << (8 * (i & 3));
+        }
+    }
+    bool fwd = true;
+    if (canonical) {
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {  // the lowest differing word (earliest bytes) decides last
+            R[j] = comp_base4(R[j]);
+            const uint32_t fb = __byte_perm(F[j], 0, 0x0123), rb = __byte_perm(R[j], 0, 0x0123);
+            if (fb != rb) fwd = fb < rb;
+        }
+    }
+    const int nblocks = k >> 2, rem = k & 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // seed-independent part of every block / of the tail
+        uint32_t k1 = fwd ? F[j] : R[j];
+        k1 *= 0xcc9e2d51u;
+        k1 = rotl32(k1, 15);
+        F[j] = k1 * 0x1b873593u;
+    }
+    for (int seed = 0; seed < h; ++seed) {
+        uint32_t h1 = (uint32_t)seed;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < nblocks) {
+                h1 ^= F[j];
+                h1 = rotl32(h1, 13);
+                h1 = h1 * 5u + 0xe6546b64u;
+            } else if (j == nblocks && rem) {
+                h1 ^= F[j];
+            }
+        }
+        ids[seed] = murmur_finish_fastmod(h1, (uint32_t)k, m, magic);
+    }
+}
+
+// Synchronisation of a hashing group: the whole CTA (id 0), a subset of warps on a named barrier
+// (id > 0, nthreads a multiple of 32), or one warp (nthreads == 32).  A runtime choice on purpose: the
+// hashing code exists ONCE per kernel (it runs once per launch, so its cost is instruction fetch).
+struct GroupSync {
+    int id, nthreads;
+    __device__ __forceinline__ void operator()() const
+    {
+        if (nthreads == 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+    }
 };
-struct SyncNamed {
-    int id, nthreads;  // nthreads: a multiple of 32, every thread of the group calls
-    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-};
-struct SyncWarp {
-    __device__ __forceinline__ void operator()() const { __syncwarp(); }
-};
+typedef GroupSync SyncNamed;
+__device__ __forceinline__ GroupSync SyncBlock() { return GroupSync{0, (int)blockDim.x}; }
+__device__ __forceinline__ GroupSync SyncWarp() { return GroupSync{0, 32}; }
 
 // Group-cooperative hashing of cnt CONTIGUOUS k-mers starting at g0: thread `tid` of a group of
 // `nthreads` threads that synchronise with `sync` (every thread of the group must call; contains
@@ -73,11 +152,10 @@ struct SyncWarp {
 // orientation; (3) one thread per (k-mer, 4-byte block) writes the canonical bytes as little-endian
 // words (zero padded, so the last word IS murmur's tail); (4) one thread per (k-mer, seed) runs
 // MurmurHash3 over those words and stores ids[km * h + seed].  `scratch` (16-byte aligned,
-// hash_scratch_bytes(cnt, k) bytes) and `ids` may be shared or global memory.
-template <typename Sync>
-__device__ __forceinline__ void hash_kmers_group(const uint8_t *g0, uint32_t cnt, int k, int h, uint32_t m, int canonical,
-                                                 uint8_t *scratch, int32_t *ids, uint32_t tid, uint32_t nthreads,
-                                                 const Sync &sync)
+// hash_scratch_bytes(cnt, k) bytes) and `ids` may be shared or global memory.  magic = mod_magic(m).
+static __device__ __noinline__ void hash_kmers_group(const uint8_t *g0, uint32_t cnt, int k, int h, uint32_t m, int canonical,
+                                             uint8_t *scratch, int32_t *ids, uint32_t tid, uint32_t nthreads,
+                                             const GroupSync sync, uint64_t magic)
 {
     const int nblocks = k >> 2, rem = k & 3;
     const uint32_t wpk = (uint32_t)(k + 3) >> 2;
@@ -93,6 +171,11 @@ __device__ __forceinline__ void hash_kmers_group(const uint8_t *g0, uint32_t cnt
     for (uint32_t i = tid; i < nvec; i += nthreads) sv[i] = __ldg(a0 + i);
     sync();
     const uint8_t *src = scratch + skew;
+    if (k <= 32) {  // the common case (k = 31): one thread per k-mer, no further barriers
+        for (uint32_t km = tid; km < cnt; km += nthreads)
+            hash_one_kmer_regs(src + (size_t)km * k, k, h, m, magic, canonical, ids + (size_t)km * h);
+        return;
+    }
     for (uint32_t km = tid; km < cnt; km += nthreads) {
         const uint8_t *s = src + (size_t)km * k;
         bool f = true;  // forward unless the reverse complement is lexicographically smaller
@@ -133,9 +216,9 @@ __device__ __forceinline__ void hash_kmers_group(const uint8_t *g0, uint32_t cnt
 
 // the whole CTA as one group
 __device__ __forceinline__ void hash_kmers_cooperative(const uint8_t *g0, uint32_t cnt, int k, int h, uint32_t m,
-                                                       int canonical, uint8_t *scratch, int32_t *ids)
+                                                       int canonical, uint8_t *scratch, int32_t *ids, uint64_t magic)
 {
-    hash_kmers_group(g0, cnt, k, h, m, canonical, scratch, ids, threadIdx.x, blockDim.x, SyncBlock());
+    hash_kmers_group(g0, cnt, k, h, m, canonical, scratch, ids, threadIdx.x, blockDim.x, SyncBlock(), magic);
 }
 
 }  // namespace bigsi

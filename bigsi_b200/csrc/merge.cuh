@@ -124,8 +124,7 @@ __device__ __forceinline__ void merge_stage_region(const QueryParams &P, uint8_t
 // __syncthreads).  smem: 128-byte aligned scratch of P.merge_smem bytes; mbar: an initialised
 // (count 1) mbarrier owned by the merge phase; phase: its CTA-uniform parity.
 template <int MODE>
-__device__ __forceinline__ void merge_item(const QueryParams &P, uint64_t item, uint8_t *smem, uint64_t *mbar,
-                                           uint32_t &phase)
+__device__ __forceinline__ void merge_item(const QueryParams &P, uint64_t item, uint8_t *smem, uint64_t *mbar, uint32_t &phase)
 {
     MergeGeom G;
     if (!merge_geometry(P, item, G)) return;  // block-uniform
@@ -295,7 +294,7 @@ __device__ __forceinline__ void merge_item(const QueryParams &P, uint64_t item, 
                 for (uint32_t b = 0; b < pps; ++b)
                     for (uint32_t j = 0; j < J; ++j) total += ((cw[b * J + j] >> lane) & 1u) << (b + j);
             } else {
-#pragma unroll 4
+#pragma unroll 2
                 for (uint32_t b = 0; b < pps; ++b) {
                     const uint32_t x = lane < J ? cw[b * J + lane] : 0u;
                     total += warp_transpose32(x, lane) << b;

@@ -62,6 +62,7 @@ struct QueryParams {
     const uint8_t *kmers;     // [total_kmers * k] raw ASCII k-mers, or null (then `rows` is used)
     uint32_t k;
     uint32_t num_rows;        // m
+    uint64_t mod_magic;       // hash.cuh:mod_magic(m), the fast-modulo constant of the in-kernel hashing
     uint32_t prehash;         // 1: hash in the prologue into the shared-memory id table
     uint32_t ids_bytes;       // size of that table + the hashing scratch (between the mbarriers and the ring)
     uint32_t ids_table_bytes; // the table alone; the hashing scratch follows it

@@ -402,7 +402,7 @@ __device__ __forceinline__ void solo_producer(const QueryParams &P, const SoloGe
 
     // the first ring-full of k-mers is hashed by this warp alone, so the gather starts at once
     hash_kmers_group(P.kmers + sg.begin * P.k, sg.n_first, (int)P.k, (int)h, P.num_rows, 1, scratch, ids, lane, 32u,
-                     SyncWarp());
+                     SyncWarp(), P.mod_magic);
     __syncwarp();
     if (lane == 0) BIGSI_TS(1);
     uint32_t k0 = 0;
@@ -485,15 +485,17 @@ __device__ __forceinline__ void solo_consumer(const QueryParams &P, const SoloGe
     const uint32_t rest = sg.cnt - sg.n_first;
     hash_kmers_group(P.kmers + (sg.begin + sg.n_first) * P.k, rest, (int)P.k, (int)P.h, P.num_rows, 1,
                      scratch + ((hash_scratch_bytes(sg.n_first, P.k) + 127) & ~127ull), ids + (size_t)sg.n_first * P.h, unit,
-                     consumer_threads, SyncNamed{kBarHashGroup, (int)consumer_threads});
+                     consumer_threads, GroupSync{kBarHashGroup, (int)consumer_threads}, P.mod_magic);
     named_bar_sync(kBarHashGroup, consumer_threads);
     if (P.pool_share) {
         int32_t *dst = P.pool_ids + (size_t)blockIdx.x * P.pool_share * P.h;
         const int32_t *src = ids + (size_t)sg.n_static * P.h;
         for (uint32_t i = unit; i < sg.n_pool * P.h; i += consumer_threads) dst[i] = src[i];
-        __threadfence();
         named_bar_sync(kBarHashGroup, consumer_threads);
-        if (unit == 0) st_release_gpu_u64(P.pool_ready + blockIdx.x, P.pool_epoch);
+        if (unit == 0) {  // one cumulative fence behind the barrier publishes every thread's ids
+            __threadfence();
+            st_release_gpu_u64(P.pool_ready + blockIdx.x, P.pool_epoch);
+        }
     }
     named_bar_arrive(kBarIdsReady, blockDim.x);
     if (unit == 0) BIGSI_TS(9);
@@ -575,7 +577,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *counter, unsign
     __syncthreads();
 }
 
-template <int MODE, int HC>
+template <int MODE, int HC, bool SOLO>
 __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_constant__ QueryParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -623,7 +625,7 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
         __syncthreads();
     }
 
-    if (P.solo) {
+    if (SOLO) {
         const SoloGeom sg = solo_geometry(P);
         uint8_t *scratch = smem + kSmemHeaderBytes + P.ids_table_bytes;
         if ((threadIdx.x >> 5) == consumer_warps)
@@ -634,7 +636,7 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
         if (P.prehash && have_work) {
             // n_tiles == 1 and one slice per CTA: this CTA's k-mers are [begin, end), contiguous in memory
             hash_kmers_cooperative(P.kmers + begin * P.k, (uint32_t)(end - begin), (int)P.k, (int)P.h, P.num_rows, 1,
-                                   smem + kSmemHeaderBytes + P.ids_table_bytes, ids);
+                                   smem + kSmemHeaderBytes + P.ids_table_bytes, ids, P.mod_magic);
             __syncthreads();
             if (threadIdx.x == 0) BIGSI_TS(9);
         }
@@ -651,7 +653,7 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
         // merge work items; the drained ring is the scratch
         grid_barrier(P.barrier, P.barrier_target);
         if (threadIdx.x == 0) BIGSI_TS(6);
-        if (P.solo && blockIdx.x == 0 && threadIdx.x == 0) *P.pool_counter = 0u;  // every claim of this launch is done
+        if (SOLO && blockIdx.x == 0 && threadIdx.x == 0) *P.pool_counter = 0u;  // every claim of this launch is done
         uint32_t merge_phase = 0;
         for (uint64_t item = blockIdx.x; item < P.merge_items; item += gridDim.x)
             merge_item<MODE>(P, item, ring, merge_bar, merge_phase);
@@ -659,12 +661,6 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
             BIGSI_TS(7);
             if (P.debug_ts) P.debug_ts[(size_t)blockIdx.x * kDebugStamps + 15] = (unsigned long long)clock64();
         }
-        if (P.debug_flags & 4u) {  // instrumentation only: run the merge phase again (warm caches), results are garbage
-            for (uint64_t item = blockIdx.x; item < P.merge_items; item += gridDim.x)
-                merge_item<MODE>(P, item, ring, merge_bar, merge_phase);
-            if (threadIdx.x == 0) BIGSI_TS(13);
-        }
-
         if (P.n_sinks) {
             // the last CTA to finish its merge items publishes query 0's hit list to every sink
             int *s_last = reinterpret_cast<int *>(smem + 2 * kMaxStages * 8 + 64);  // header space behind the mbarriers
@@ -705,7 +701,10 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
 template <int MODE, int HC>
 static cudaError_t launch_one(const QueryParams &p, int grid, cudaStream_t stream)
 {
-    return launch_ex(fused_query<MODE, HC>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream,
+    if (p.solo)
+        return launch_ex(fused_query<MODE, HC, true>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream,
+                         /*pdl=*/true, /*cooperative=*/true, p);
+    return launch_ex(fused_query<MODE, HC, false>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream,
                      /*pdl=*/true, /*cooperative=*/p.fuse_merge != 0, p);
 }
 
@@ -722,10 +721,14 @@ cudaError_t query_kernels_init()
 #define BIGSI_SET_SMEM(K)                                                                   \
     e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);  \
     if (e != cudaSuccess) return e;
-    BIGSI_SET_SMEM((fused_query<kModeCounts, 3>))
-    BIGSI_SET_SMEM((fused_query<kModeCounts, 0>))
-    BIGSI_SET_SMEM((fused_query<kModeAnd, 3>))
-    BIGSI_SET_SMEM((fused_query<kModeAnd, 0>))
+    BIGSI_SET_SMEM((fused_query<kModeCounts, 3, false>))
+    BIGSI_SET_SMEM((fused_query<kModeCounts, 3, true>))
+    BIGSI_SET_SMEM((fused_query<kModeCounts, 0, false>))
+    BIGSI_SET_SMEM((fused_query<kModeCounts, 0, true>))
+    BIGSI_SET_SMEM((fused_query<kModeAnd, 3, false>))
+    BIGSI_SET_SMEM((fused_query<kModeAnd, 3, true>))
+    BIGSI_SET_SMEM((fused_query<kModeAnd, 0, false>))
+    BIGSI_SET_SMEM((fused_query<kModeAnd, 0, true>))
 #undef BIGSI_SET_SMEM
     return merge_kernels_init();
 }

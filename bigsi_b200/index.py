@@ -43,6 +43,8 @@ class DeviceIndex:
         L = _lib.lib()
         check(L.bigsi_b200_index_create(device, num_rows, num_cols, col_capacity, col_offset, ctypes.byref(self._h)))
         self._L = L
+        self._hit_bufs = {}
+        self._one_query_offsets = np.zeros(2, dtype=np.int64)
 
     # -- lifecycle -----------------------------------------------------------
     def close(self):
@@ -153,25 +155,37 @@ class DeviceIndex:
 
     def search_kmers_hits(self, kmers, k, h, min_kmers, q_offsets=None, cap=None):
         """Fused search + threshold.  Returns a list (one per query) of (colours int32, counts
-        uint32) with count >= min_kmers[q], colours ascending."""
+        uint32, n_hits) with count >= min_kmers[q], colours ascending."""
         arr = kmers if isinstance(kmers, np.ndarray) else kmers_to_array(list(kmers), k)
-        arr = np.ascontiguousarray(arr, dtype=np.uint8)
-        q = self._offsets(q_offsets, arr.shape[0])
-        nq = q.size - 1
+        if arr.dtype != np.uint8 or not arr.flags.c_contiguous:
+            arr = np.ascontiguousarray(arr, dtype=np.uint8)
+        if q_offsets is None:
+            nq = 1
+            q = self._one_query_offsets
+            q[1] = arr.shape[0]
+        else:
+            q = self._offsets(q_offsets, arr.shape[0])
+            nq = q.size - 1
         mk = np.ascontiguousarray(np.broadcast_to(np.asarray(min_kmers, dtype=np.uint32), (nq,)))
-        nc = self.num_cols
-        cap = nc if cap is None else int(cap)
-        cols = np.empty((nq, max(cap, 1)), dtype=np.int32)
-        cnts = np.empty((nq, max(cap, 1)), dtype=np.uint32)
-        n = np.zeros(nq, dtype=np.uint64)
-        check(self._L.bigsi_b200_search_kmers_hits(self.handle, _ptr(arr), _ptr(q), nq, k, h, _ptr(mk), _ptr(cols),
-                                                   _ptr(cnts), cap, _ptr(n)))
+        cap = self.num_cols if cap is None else int(cap)
+        key = (nq, cap)
+        bufs = self._hit_bufs.get(key)
+        if bufs is None:  # output staging is reused between calls (results are copied out below)
+            bufs = (np.empty((nq, max(cap, 1)), dtype=np.int32), np.empty((nq, max(cap, 1)), dtype=np.uint32),
+                    np.zeros(nq, dtype=np.uint64))
+            if len(self._hit_bufs) > 8:
+                self._hit_bufs.clear()
+            self._hit_bufs[key] = bufs
+        cols, cnts, n = bufs
+        check(self._L.bigsi_b200_search_kmers_hits(self.handle, arr.ctypes.data, q.ctypes.data, nq, k, h, mk.ctypes.data,
+                                                   cols.ctypes.data, cnts.ctypes.data, cap, n.ctypes.data))
         res = []
         for i in range(nq):
-            ni = int(min(n[i], cap))
-            c, v = cols[i, :ni], cnts[i, :ni]
+            ni = int(n[i])
+            m = min(ni, cap)
+            c, v = cols[i, :m], cnts[i, :m]
             order = np.argsort(c, kind="stable")
-            res.append((c[order], v[order], int(n[i])))
+            res.append((c[order], v[order], ni))
         return res
 
     def lookup_kmers(self, kmers, k, h):

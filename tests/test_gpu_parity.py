@@ -52,7 +52,7 @@ def test_hash_random_vs_oracle(B, k):
         arr = _rand_kmers(rng, 3000, k, alphabet)
         # add reverse-complement palindromes and pairs
         arr[1] = np.frombuffer(O.canonical(bytes(arr[0])), dtype=np.uint8)
-        for h, m in ((1, 25), (3, 25_000_000), (5, 2_147_483_647), (2, 1)):
+        for h, m in ((1, 25), (3, 25_000_000), (5, 2_147_483_647), (2, 1), (4, 2), (3, 1000), (2, 1_073_741_827)):
             assert np.array_equal(B.hash_kmers(arr, k, h, m), O.hash_kmers(arr, k, h, m))
             nc = B.hash_kmers(arr, k, h, m, canonical=False)
             ref = np.array([[O.lib().oracle_hash_row(bytes(r), k, s, m) for s in range(h)] for r in arr[:50]])
@@ -449,3 +449,85 @@ def test_device_pointer_path_fused_threshold(B):
             else:
                 assert all(cnt[cc] == vv and cnt[cc] >= mins[q] for cc, vv in zip(c[0, q, :got], v[0, q, :got]))
     ix.close()
+
+
+# ---------------------------------------------------------------------------
+# single-query host path: zero-copy k-mers, threshold by value, kernel-published result block
+# ---------------------------------------------------------------------------
+def _pinned_copy(B, arr):
+    """arr copied into a buffer from bigsi_b200_host_alloc (mapped pinned memory); returns (view, free)."""
+    import ctypes
+
+    from bigsi_b200 import _lib
+
+    L = _lib.lib()
+    p = ctypes.c_void_p(0)
+    _lib.check(L.bigsi_b200_host_alloc(max(arr.nbytes, 1), ctypes.byref(p)))
+    buf = (ctypes.c_uint8 * max(arr.nbytes, 1)).from_address(p.value)
+    view = np.frombuffer(buf, dtype=np.uint8, count=arr.nbytes).reshape(arr.shape)
+    view[...] = arr
+    return view, lambda: L.bigsi_b200_host_free(p)
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_single_query_zero_copy_path(B, pinned):
+    rng = np.random.default_rng(41)
+    m, N, k, h = 10_007, 5000, 31, 3
+    ix, packed = _random_index(B, rng, m, N, density=0.9)
+    oix = O.OracleIndex(k, m, h, N, rows=packed)
+    free = None
+    try:
+        for n_kmers in (1, 37, 1500, 6000):
+            arr = _rand_kmers(rng, n_kmers, k)
+            if pinned:
+                arr, free_now = _pinned_copy(B, arr)
+            cnt = oix.counts(_kmer_strs(arr))
+            for frac in (1.0, 0.7, 0.0):
+                thr = int(math.ceil(n_kmers * frac))
+                exp = np.nonzero(cnt >= thr)[0]
+                # the default capacity (N) exceeds the 1024 hits the published block holds: long lists
+                # come back through the device buffers
+                cols, vals, n = ix.search_kmers_hits(arr, k, h, [thr])[0]
+                assert n == len(exp) and np.array_equal(cols, exp) and np.array_equal(vals, cnt[exp]), (n_kmers, frac)
+                cols, vals, n = ix.search_kmers_hits(arr, k, h, [thr], cap=64)[0]
+                assert n == len(exp) and len(cols) == min(64, len(exp))
+                assert all(cnt[c] == v and v >= thr for c, v in zip(cols, vals))
+            assert ix.info()["last_fused"] & 1
+            # same answers from the staged path
+            ix.set_option("zero_copy", 0)
+            thr = int(math.ceil(n_kmers * 0.7))
+            exp = np.nonzero(cnt >= thr)[0]
+            cols, vals, n = ix.search_kmers_hits(arr, k, h, [thr])[0]
+            assert n == len(exp) and np.array_equal(cols, exp) and np.array_equal(vals, cnt[exp])
+            ix.set_option("zero_copy", 1)
+            if pinned:
+                free_now()
+    finally:
+        ix.close()
+
+
+@pytest.mark.parametrize("opts", [
+    {"pool_pct": 0}, {"pool_pct": 50}, {"pool_pct": 100}, {"solo": 0}, {"n_stages": 2}, {"grid": 3},
+    {"merge_chunk_bytes": 16}, {"merge_chunk_bytes": 1024}, {"kmers_per_stage": 4, "pool_pct": 30},
+])
+def test_solo_path_geometries(B, opts):
+    """The single-query in-kernel path (producer-warp hashing, pooled tail k-mers, chunk-major merge)
+    under forced geometries; counts and hits must not depend on any of them."""
+    rng = np.random.default_rng(43)
+    m, N, k, h = 10_007, 7000, 31, 3
+    ix, packed = _random_index(B, rng, m, N, density=0.9)
+    oix = O.OracleIndex(k, m, h, N, rows=packed)
+    for key, val in opts.items():
+        ix.set_option(key, val)
+    try:
+        for n_kmers in (5, 148, 3000, 9000):
+            arr = _rand_kmers(rng, n_kmers, k)
+            cnt = oix.counts(_kmer_strs(arr))
+            thr = int(math.ceil(n_kmers * 0.75))
+            exp = np.nonzero(cnt >= thr)[0]
+            cols, vals, n = ix.search_kmers_hits(arr, k, h, [thr])[0]
+            assert n == len(exp) and np.array_equal(cols, exp) and np.array_equal(vals, cnt[exp]), (opts, n_kmers)
+            assert np.array_equal(ix.search_kmers(arr, k, h)[0].astype(np.int64), cnt.astype(np.int64))
+            assert np.array_equal(ix.search_kmers(arr, k, h, mode=1)[0], oix.presence(_kmer_strs(arr)))
+    finally:
+        ix.close()

@@ -44,3 +44,17 @@ for (f, ln), a in sorted(agg.items()):
     top = sorted(a[2].items(), key=lambda x: -x[1])[:3]
     print("%-18s %4d  instr %9d (%4.1f%%)  samples %5d (%4.1f%%)  %s" % (
         f, ln, a[0], 100.0 * a[0] / tot_i, a[1], 100.0 * a[1] / tot_s, " ".join("%s=%d" % (k[6:], v) for k, v in top if v)))
+
+# per-file totals and stall mix
+byfile = defaultdict(lambda: [0, 0, defaultdict(int)])
+for (f, ln), a in agg.items():
+    b = byfile[f]
+    b[0] += a[0]
+    b[1] += a[1]
+    for k, v in a[2].items():
+        b[2][k] += v
+print("\nper file:")
+for f, b in sorted(byfile.items(), key=lambda x: -x[1][1]):
+    top = sorted(b[2].items(), key=lambda x: -x[1])[:6]
+    print("%-22s instr %9d (%4.1f%%) samples %6d (%4.1f%%)  %s" % (f, b[0], 100.0 * b[0] / tot_i, b[1], 100.0 * b[1] / tot_s,
+                                                                 " ".join("%s=%d" % (k[6:], v) for k, v in top if v)))
