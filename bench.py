@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prewarm", type=int, default=300, help="untimed steps before the warm-up (clock ramp)")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N>1: query broadcast + hit all-gather inside the query kernel over NVLink peer memory (fused) or "
+                         "as two NCCL collectives per query (nccl)")
     return ap.parse_args()
 
 
@@ -207,6 +210,9 @@ def workload_config(args, n_gpus):
                     "merge and threshold in ONE kernel launch" % (args.m, H, K, args.cols, n_gpus, args.kmers),
         "m": args.m, "h": H, "k": K, "cols_per_gpu": args.cols, "kmers_per_query": args.kmers,
         "distinct_queries": N_DISTINCT,
+        "exchange": ("none (one shard)" if n_gpus == 1 else
+                     "in-kernel: query pushed to peers and hits all-gathered through NVLink peer memory, no collective call"
+                     if getattr(args, "exchange", "fused") == "fused" else "NCCL broadcast + all-gather per query"),
         "l2_policy": "inputs larger than L2: each step gathers %.1f MB of distinct rows, %d distinct queries rotate"
                      % (args.kmers * H * math.ceil(args.cols / 8) / 1e6, N_DISTINCT),
         "matrix_density": 0.5,
@@ -242,7 +248,8 @@ def run_b200(args):
     index.fill_synthetic(0, 1, pc, pt)
     fill_s = time.perf_counter() - t0
     shard = DeviceShard(index, K, H, cap=HIT_CAP)
-    searcher = ShardedSearcher(shard, dist if world > 1 else None, world, rank)
+    fused = world > 1 and args.exchange == "fused"
+    searcher = ShardedSearcher(shard, dist if world > 1 else None, world, rank, fused_max_kmers=U if fused else 0)
 
     queries = make_queries(N_DISTINCT, U)
     d_queries = torch.from_numpy(queries).to(dev)  # resident k-mer bytes (value arm)
@@ -258,6 +265,8 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def dev_step(i):
+        if fused:  # one kernel per rank and step, no collective: rank 0's k-mers are pushed by its kernel
+            return searcher.search_one_fused(d_queries[i % N_DISTINCT] if rank == 0 else None, U, U)
         return searcher.search_step(d_queries[i % N_DISTINCT], d_qoff, d_min, 1, U)
 
     # ---- correctness gate on the first query (planted all-ones columns must be the exact hits)
@@ -325,8 +334,12 @@ def run_b200(args):
         q = i % N_DISTINCT
         if world == 1:
             return index.search_kmers_hits(h_queries[q].numpy(), K, H, h_min, q_offsets=h_qoff, cap=HIT_CAP)[0]
-        d_k = h_queries[q].to(dev, non_blocking=True) if rank == 0 else d_queries[q]
-        g = searcher.search_step(d_k, d_qoff, d_min, 1, U)
+        if fused:
+            d_k = h_queries[q].to(dev, non_blocking=True) if rank == 0 else None
+            g = searcher.search_one_fused(d_k, U, U)
+        else:
+            d_k = h_queries[q].to(dev, non_blocking=True) if rank == 0 else d_queries[q]
+            g = searcher.search_step(d_k, d_qoff, d_min, 1, U)
         return g.cpu() if rank == 0 else None
 
     for i in range(max(args.warmup, 3)):
@@ -372,7 +385,9 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": 1e3 * float(te.item()) / e2e_steps,
                     "path": "bigsi_b200_search_kmers_hits (C ABI, pinned host buffers)" if world == 1 else
-                            "pinned host k-mers -> H2D -> hash -> NCCL broadcast -> fused query -> threshold -> NCCL all-gather -> D2H"},
+                            ("pinned host k-mers -> H2D on rank 0 -> ONE kernel per rank (k-mers pushed to the peers over NVLink in the prologue, "
+                             "hash, gather-AND-count, merge, threshold, hits published to every rank's result blocks) -> D2H" if fused else
+                             "pinned host k-mers -> H2D -> hash -> NCCL broadcast -> fused query -> threshold -> NCCL all-gather -> D2H")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "fused_query<COUNTS,h=3> (in-kernel hash prologue + gather-AND-popcount + grid barrier + merge/threshold phase)" if info["last_fused"] == 3 else "fused_query<COUNTS,h=3>", "kernel_ms": fused_avg_ms,

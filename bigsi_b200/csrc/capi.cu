@@ -126,8 +126,26 @@ struct TimedLaunch {
 
 }  // namespace
 
+// Column-sharded search without per-query collectives: every rank owns one device block
+//   [inbox flags: kExFlags x u64][inbox k-mer bytes][result blocks: 2 parities x world x block]
+// that its peers map (CUDA IPC across processes, plain peer access inside one process).  Rank 0's
+// kernel pushes the query into the peers' inboxes from its prologue; every rank's kernel publishes
+// its hit list into slot `rank` of every rank's result blocks and waits for the others' slots.
+struct Exchange {
+    int world = 0, rank = 0;
+    uint32_t spec = 0;
+    uint64_t max_kmer_bytes = 0, kmers_off = 0, sinks_off = 0, block_bytes = 0, total_bytes = 0;
+    uint8_t *local = nullptr;
+    uint8_t *peer[kMaxSinks] = {};
+    bool ipc_opened[kMaxSinks] = {};
+    bool ready = false;
+    uint64_t seq = 0;
+};
+constexpr uint64_t kExFlags = 1024;
+
 struct bigsi_b200_index {
     int device = 0;
+    Exchange ex;
     int sm_count = 0;
     uint64_t num_rows = 0, num_cols = 0, col_capacity = 0, col_offset = 0, pitch = 0;
     uint8_t *matrix = nullptr;
@@ -156,13 +174,16 @@ struct bigsi_b200_index {
 
 namespace {
 
-bool g_kernels_ready = false;
+bool g_kernels_ready[64] = {};  // function attributes (dynamic shared memory opt-in) are per device
 
 int ensure_kernels()
 {
-    if (g_kernels_ready) return 0;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(BIGSI_B200_ERR_INVALID, "device ordinal %d not supported", dev);
+    if (g_kernels_ready[dev]) return 0;
     CK(query_kernels_init());
-    g_kernels_ready = true;
+    g_kernels_ready[dev] = true;
     return 0;
 }
 
@@ -326,6 +347,15 @@ struct HitsOut {
     unsigned long long *sinks[kMaxSinks] = {};
     unsigned long long sink_seq = 0;
     bool *published = nullptr;  // set when the launch will publish to the sinks (needs the in-kernel merge)
+    // column-sharded exchange fused into the kernel (see Exchange below)
+    bool require_fused = false;  // fail before launching unless the plan hashes and merges in the kernel
+    uint32_t wait_per_cta = 0;
+    uint32_t n_push = 0;
+    uint8_t *push_kmers[kMaxSinks] = {};
+    unsigned long long *push_flags[kMaxSinks] = {};
+    unsigned long long push_value = 0;
+    uint32_t n_gather = 0;
+    const unsigned long long *gather_blocks[kMaxSinks] = {};
 };
 
 // One query batch on `stream`.  Exactly one of d_rows / d_kmers is given; with k-mers the kernel
@@ -382,8 +412,20 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
             p.min_by_value = 1;
             p.min_kmers_value = hits->min_value;
         }
+        if (hits->require_fused && !(p.prehash && p.fuse_merge && grid > 0))
+            return fail(BIGSI_B200_ERR_INVALID, "this query cannot run as one kernel (prehash=%u fuse_merge=%u grid=%d)", p.prehash,
+                        p.fuse_merge, grid);
         p.wait_flag = hits->wait_flag;
         p.wait_value = hits->wait_value;
+        p.wait_per_cta = hits->wait_per_cta;
+        p.n_push = hits->n_push;
+        p.push_value = hits->push_value;
+        for (uint32_t i = 0; i < hits->n_push; ++i) {
+            p.push_kmers[i] = hits->push_kmers[i];
+            p.push_flags[i] = hits->push_flags[i];
+        }
+        p.n_gather = hits->n_gather;
+        for (uint32_t i = 0; i < hits->n_gather; ++i) p.gather_blocks[i] = hits->gather_blocks[i];
         if (hits->published) *hits->published = false;
         if (hits->n_sinks && p.fuse_merge && grid > 0 && n_queries == 1) {
             p.n_sinks = hits->n_sinks;
@@ -598,6 +640,7 @@ int bigsi_b200_index_create(int device, uint64_t num_rows, uint64_t num_cols, ui
 int bigsi_b200_index_destroy(bigsi_b200_index *ix)
 {
     if (!ix) return 0;
+    bigsi_b200_exchange_destroy(ix);
     DeviceGuard guard(ix->device);
     cudaDeviceSynchronize();
     for (auto &t : ix->timed_free) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
@@ -1182,6 +1225,161 @@ int bigsi_b200_lookup_kmers(bigsi_b200_index *ix, const char *kmers, uint64_t n,
         return rc;
     CK(cudaMemcpy2DAsync(out, out_stride, ix->d_out.p, dstride, row_bytes, n, cudaMemcpyDeviceToHost, ix->stream));
     CK(cudaStreamSynchronize(ix->stream));
+    return 0;
+}
+
+// ============================================================================================
+// column-sharded exchange (multi-GPU, one handle per GPU)
+// ============================================================================================
+int bigsi_b200_exchange_create(bigsi_b200_index *ix, int world, int rank, uint64_t max_kmer_bytes, uint32_t spec,
+                               uint8_t *ipc_handle_out)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (world < 1 || world > kMaxSinks - 1 || rank < 0 || rank >= world)
+        return fail(BIGSI_B200_ERR_INVALID, "bad world/rank %d/%d (at most %d shards)", world, rank, kMaxSinks - 1);
+    if (spec == 0 || max_kmer_bytes == 0) return fail(BIGSI_B200_ERR_INVALID, "spec and max_kmer_bytes must be positive");
+    if (ix->ex.local) return fail(BIGSI_B200_ERR_INVALID, "exchange already created");
+    DeviceGuard guard(ix->device);
+    Exchange &ex = ix->ex;
+    ex.world = world;
+    ex.rank = rank;
+    ex.spec = spec;
+    ex.max_kmer_bytes = max_kmer_bytes;
+    ex.kmers_off = kExFlags * 8;
+    ex.sinks_off = ex.kmers_off + round_up(max_kmer_bytes + 64, 256);
+    ex.block_bytes = round_up(16 + 8ull * spec, 128);
+    ex.total_bytes = ex.sinks_off + 2ull * world * ex.block_bytes;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ex.local), ex.total_bytes);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(exchange)");
+    CK(cudaMemset(ex.local, 0, ex.total_bytes));
+    ex.peer[rank] = ex.local;
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t hdl;
+        CK(cudaIpcGetMemHandle(&hdl, ex.local));
+        static_assert(sizeof(hdl) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(ipc_handle_out, &hdl, 64);
+    }
+    ex.ready = world == 1;
+    return 0;
+}
+
+int bigsi_b200_exchange_open(bigsi_b200_index *ix, const uint8_t *ipc_handles)
+{
+    if (int rc = check_index(ix)) return rc;
+    Exchange &ex = ix->ex;
+    if (!ex.local) return fail(BIGSI_B200_ERR_INVALID, "exchange not created");
+    if (!ipc_handles) return fail(BIGSI_B200_ERR_INVALID, "null handles");
+    DeviceGuard guard(ix->device);
+    for (int r = 0; r < ex.world; ++r) {
+        if (r == ex.rank || ex.peer[r]) continue;
+        cudaIpcMemHandle_t hdl;
+        memcpy(&hdl, ipc_handles + 64 * r, 64);
+        void *ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, hdl, cudaIpcMemLazyEnablePeerAccess));
+        ex.peer[r] = static_cast<uint8_t *>(ptr);
+        ex.ipc_opened[r] = true;
+    }
+    ex.ready = true;
+    return 0;
+}
+
+int bigsi_b200_exchange_open_local(bigsi_b200_index *ix, bigsi_b200_index *const *peers)
+{
+    if (int rc = check_index(ix)) return rc;
+    Exchange &ex = ix->ex;
+    if (!ex.local) return fail(BIGSI_B200_ERR_INVALID, "exchange not created");
+    if (!peers) return fail(BIGSI_B200_ERR_INVALID, "null peers");
+    DeviceGuard guard(ix->device);
+    for (int r = 0; r < ex.world; ++r) {
+        if (r == ex.rank) continue;
+        const bigsi_b200_index *pr = peers[r];
+        if (!pr || !pr->ex.local || pr->ex.world != ex.world || pr->ex.rank != r || pr->ex.total_bytes != ex.total_bytes)
+            return fail(BIGSI_B200_ERR_INVALID, "peer %d has no matching exchange block", r);
+        if (pr->device != ix->device) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, ix->device, pr->device));
+            if (!can) return fail(BIGSI_B200_ERR_CUDA, "device %d cannot access device %d", ix->device, pr->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(pr->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail_cuda(e, "cudaDeviceEnablePeerAccess");
+            (void)cudaGetLastError();
+        }
+        ex.peer[r] = pr->ex.local;
+    }
+    ex.ready = true;
+    return 0;
+}
+
+int bigsi_b200_exchange_destroy(bigsi_b200_index *ix)
+{
+    if (!ix) return 0;
+    Exchange &ex = ix->ex;
+    if (!ex.local) return 0;
+    DeviceGuard guard(ix->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < ex.world; ++r)
+        if (ex.ipc_opened[r] && ex.peer[r]) cudaIpcCloseMemHandle(ex.peer[r]);
+    cudaFree(ex.local);
+    ex = Exchange();
+    return 0;
+}
+
+int bigsi_b200_exchange_search_dev(bigsi_b200_index *ix, const char *d_kmers, uint64_t n_kmers, int k, int h,
+                                   uint32_t min_kmers, void *stream, const void **d_blocks_out, uint64_t *block_bytes_out)
+{
+    if (int rc = check_index(ix)) return rc;
+    Exchange &ex = ix->ex;
+    if (!ex.local || !ex.ready) return fail(BIGSI_B200_ERR_INVALID, "exchange not created / peers not opened");
+    if (k < 1 || h < 1 || n_kmers == 0) return fail(BIGSI_B200_ERR_INVALID, "k, h and the number of k-mers must be positive");
+    if (n_kmers * (uint64_t)k > ex.max_kmer_bytes) return fail(BIGSI_B200_ERR_RANGE, "query larger than the exchange inbox");
+    if (ex.rank == 0 && (!d_kmers || (reinterpret_cast<uintptr_t>(d_kmers) & 15)))
+        return fail(BIGSI_B200_ERR_INVALID, "rank 0 needs the k-mers in a 16-byte aligned device buffer");
+    if (ix->num_cols == 0) return fail(BIGSI_B200_ERR_INVALID, "empty shard");
+    DeviceGuard guard(ix->device);
+    cudaError_t e;
+    if ((e = ix->d_nhits.reserve(8 + 8ull * ex.spec + 16)) != cudaSuccess) return fail_cuda(e, "staging");
+    const uint64_t seq = ex.seq + 1;
+    const uint64_t parity = seq & 1;
+    uint8_t *dev = static_cast<uint8_t *>(ix->d_nhits.p);
+    HitsOut ho;
+    ho.n = reinterpret_cast<unsigned long long *>(dev);
+    ho.cols = reinterpret_cast<int32_t *>(dev + 8);
+    ho.counts = reinterpret_cast<uint32_t *>(dev + 8 + 4ull * ex.spec);
+    ho.cap = ex.spec;
+    ho.by_value = true;
+    ho.min_value = min_kmers;
+    ho.require_fused = true;
+    ho.sink_spec = ex.spec;
+    ho.sink_seq = seq;
+    ho.n_sinks = (uint32_t)ex.world;
+    ho.n_gather = (uint32_t)ex.world;
+    for (int r = 0; r < ex.world; ++r) {
+        ho.sinks[r] = reinterpret_cast<unsigned long long *>(ex.peer[r] + ex.sinks_off + (parity * ex.world + ex.rank) * ex.block_bytes);
+        ho.gather_blocks[r] =
+            reinterpret_cast<const unsigned long long *>(ex.local + ex.sinks_off + (parity * ex.world + r) * ex.block_bytes);
+    }
+    const char *kmers = d_kmers;
+    if (ex.rank == 0) {
+        for (int r = 1; r < ex.world; ++r) {
+            ho.push_kmers[ho.n_push] = ex.peer[r] + ex.kmers_off;
+            ho.push_flags[ho.n_push] = reinterpret_cast<unsigned long long *>(ex.peer[r]);
+            ++ho.n_push;
+        }
+        ho.push_value = seq;
+    } else {
+        ho.wait_flag = reinterpret_cast<const unsigned long long *>(ex.local);
+        ho.wait_value = seq;
+        ho.wait_per_cta = 1;
+        kmers = reinterpret_cast<const char *>(ex.local + ex.kmers_off);
+    }
+    bool published = false;
+    ho.published = &published;
+    if (int rc = run_query(ix, BIGSI_B200_MODE_COUNTS, nullptr, kmers, k, nullptr, 1, n_kmers, n_kmers, h, nullptr, 0,
+                           static_cast<cudaStream_t>(stream), &ho))
+        return rc;
+    if (!published) return fail(BIGSI_B200_ERR_INVALID, "the launch could not publish its result");
+    ex.seq = seq;
+    if (d_blocks_out) *d_blocks_out = ex.local + ex.sinks_off + parity * ex.world * ex.block_bytes;
+    if (block_bytes_out) *block_bytes_out = ex.block_bytes;
     return 0;
 }
 

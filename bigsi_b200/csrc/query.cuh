@@ -94,6 +94,13 @@ struct QueryParams {
     // a peer GPU's or the host's memory and be published there by somebody else)
     const unsigned long long *wait_flag;
     unsigned long long wait_value;
+    uint32_t wait_per_cta;    // 1: CTA b waits on wait_flag[b] (its own slice of the k-mers was pushed by a peer's CTA b)
+    // query broadcast fused into the prologue (rank 0 of a column-sharded search): CTA b copies ITS slice of
+    // the k-mer bytes into every peer's inbox (NVLink stores) and then raises the peer's flag b
+    uint32_t n_push;
+    uint8_t *push_kmers[kMaxSinks];            // peers' inbox k-mer bytes (same offsets as `kmers`)
+    unsigned long long *push_flags[kMaxSinks]; // peers' per-CTA inbox flags
+    unsigned long long push_value;
     // result publication: after the merge phase the LAST CTA copies the hit list of query 0 to every
     // sink -- a block [0] = sequence flag, [1] = number of hits, then int32 cols[sink_spec], uint32
     // counts[sink_spec] -- in this GPU's, a peer GPU's (NVLink) or the host's (mapped pinned) memory
@@ -103,6 +110,10 @@ struct QueryParams {
     unsigned long long *sinks[kMaxSinks];
     unsigned long long *done_counter;   // monotonic; the CTA that brings it to done_target is the last
     unsigned long long done_target;
+    // all-gather completion: after publishing, the last CTA waits until these LOCAL blocks (the slots the
+    // peers publish into) carry sink_seq too, so that stream order implies "all shards have reported"
+    uint32_t n_gather;
+    const unsigned long long *gather_blocks[kMaxSinks];
     uint32_t debug_flags;     // bit 0: consumers skip the AND/count work (pure-gather ceiling measurement)
     unsigned long long *debug_ts;  // optional [grid][kDebugStamps] timeline stamps (globaltimer ns), see fused_query
 };

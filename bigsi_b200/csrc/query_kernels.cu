@@ -615,14 +615,36 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
     if (end > P.total_items) end = P.total_items;
     const bool have_work = begin < end;
 
-    if (P.wait_flag != nullptr) {  // the query is published by another GPU / the host: wait for it
+    // k-mers this CTA hashes itself (prehash geometry: one tile, one slice per CTA)
+    const uint64_t kb = (uint64_t)blockIdx.x * P.items_per_slice;
+    const uint32_t kcnt = (P.prehash && kb < P.total_kmers) ? (uint32_t)min((uint64_t)P.items_per_slice, P.total_kmers - kb) : 0u;
+    if (P.wait_flag != nullptr && (!P.wait_per_cta || kcnt)) {
+        // the query is published by another GPU / the host: wait for it (per CTA: for our own slice)
         if (threadIdx.x == 0) {
+            const unsigned long long *flag = P.wait_flag + (P.wait_per_cta ? blockIdx.x : 0);
             unsigned long long seen;
             do {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(P.wait_flag) : "memory");
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
             } while (seen < P.wait_value);
         }
         __syncthreads();
+    }
+    if (P.n_push && kcnt) {
+        // broadcast fused into the prologue: push our slice of the k-mer bytes (16-byte lines that cover it;
+        // neighbouring CTAs write identical bytes into shared boundary lines) to every peer, then raise flag b
+        const uint64_t b0 = kb * P.k, b1 = (kb + kcnt) * P.k;
+        const uint64_t a0 = b0 & ~15ull, nvec = (((b1 + 15) & ~15ull) - a0) >> 4;
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.kmers + a0);
+        for (uint64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+            const uint4 v = __ldg(src + i);
+            for (uint32_t r = 0; r < P.n_push; ++r) reinterpret_cast<uint4 *>(P.push_kmers[r] + a0)[i] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            for (uint32_t r = 0; r < P.n_push; ++r)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.push_flags[r] + blockIdx.x), "l"(P.push_value) : "memory");
+        }
     }
 
     if (SOLO) {
@@ -685,10 +707,16 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
                 __threadfence_system();
                 __syncthreads();
                 if (threadIdx.x < P.n_sinks) {
-                    volatile unsigned long long *blk = P.sinks[threadIdx.x];
-                    blk[1] = n;
-                    __threadfence_system();
-                    blk[0] = P.sink_seq;  // the flag goes last
+                    // {sequence word, number of hits} as ONE 16-byte store: the block header is never seen torn,
+                    // and the hit list was fenced above
+                    asm volatile("st.release.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(P.sinks[threadIdx.x]), "l"(P.sink_seq), "l"(n)
+                                 : "memory");
+                }
+                if (threadIdx.x < P.n_gather) {  // all-gather: every shard's block has arrived here
+                    unsigned long long seen;
+                    do {
+                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(P.gather_blocks[threadIdx.x]) : "memory");
+                    } while (seen != P.sink_seq);
                 }
             }
         }

@@ -124,6 +124,76 @@ class DeviceShard:
         return buf
 
 
+class _DevArray:
+    """Minimal __cuda_array_interface__ carrier so torch can view library-owned device memory."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class FusedExchange:
+    """The two exchanges of a column-sharded single-query search done by the query kernel itself
+    (include/bigsi_b200.h "column-sharded search ... WITHOUT per-query collectives"): rank 0's kernel
+    pushes the k-mer bytes into the peers' inboxes over NVLink, every rank's kernel publishes its hits
+    into every rank's result blocks and waits for the others.  No NCCL call per query; torch.distributed
+    is only used once, to exchange the CUDA IPC handles."""
+
+    def __init__(self, shard, world_size, rank, max_kmers, dist=None, peers=None):
+        import ctypes
+
+        from . import _lib
+
+        self._ct, self._lib = ctypes, _lib
+        self.shard, self.world, self.rank = shard, world_size, rank
+        self.spec = shard.cap
+        self._views = {}
+        L = _lib.lib()
+        handle = (ctypes.c_uint8 * 64)()
+        _lib.check(L.bigsi_b200_exchange_create(shard.index.handle, world_size, rank, max_kmers * shard.k, self.spec, handle))
+        if world_size > 1:
+            if peers is not None:  # all shards live in this process (tests): plain peer access
+                self._pending_peers = peers
+            else:
+                gathered = [None] * world_size
+                dist.all_gather_object(gathered, bytes(handle))
+                blob = b"".join(gathered)
+                _lib.check(L.bigsi_b200_exchange_open(shard.index.handle, (ctypes.c_uint8 * len(blob)).from_buffer_copy(blob)))
+                dist.barrier()
+
+    @staticmethod
+    def connect_local(exchanges):
+        """Same-process wiring of `world` FusedExchange objects (one per device)."""
+        import ctypes
+
+        from . import _lib
+
+        arr = (ctypes.c_void_p * len(exchanges))(*[e.shard.index.handle.value for e in exchanges])
+        for e in exchanges:
+            _lib.check(_lib.lib().bigsi_b200_exchange_open_local(e.shard.index.handle, arr))
+
+    def search(self, kmers_u8, n_kmers, min_kmers):
+        """One query (rank 0's k-mers decide).  Returns int32 [world, 2 + 2*spec] (LOCAL colours), the
+        packed layout of DeviceShard.hits for one query; a view of library memory that stays valid until
+        the next-but-one search."""
+        ct = self._ct
+        t = self.shard.torch
+        ptr, stride = ct.c_void_p(0), ct.c_uint64(0)
+        d_k = kmers_u8.data_ptr() if (self.rank == 0 and kmers_u8 is not None) else 0
+        self._lib.check(self._lib.lib().bigsi_b200_exchange_search_dev(
+            self.shard.index.handle, d_k, n_kmers, self.shard.k, self.shard.h, int(min_kmers), self.shard._stream(),
+            ct.byref(ptr), ct.byref(stride)))
+        view = self._views.get(ptr.value)
+        if view is None:  # two result buffers alternate: build each torch view once
+            words = stride.value // 4
+            blocks = t.as_tensor(_DevArray(ptr.value, (self.world, words), "<i4"), device=self.shard.device)
+            view = blocks[:, 2 : 4 + 2 * self.spec]  # drop the sequence word: [n (2 x int32) | cols | counts]
+            self._views[ptr.value] = view
+        return view
+
+    def close(self):
+        self._lib.lib().bigsi_b200_exchange_destroy(self.shard.index.handle)
+
+
 def unpack_hits(buf, n_queries, cap):
     """Inverse of DeviceShard.hits' packing for a [G, Q*(2+2*cap)] (or 1-D) int32 array on the host."""
     a = np.asarray(buf).reshape(-1, n_queries * (2 + 2 * cap))
@@ -138,12 +208,23 @@ class ShardedSearcher:
     living on `shard.device`; `dist` is torch.distributed (already initialised) or None for a
     single process."""
 
-    def __init__(self, shard, dist=None, world_size=1, rank=0):
+    def __init__(self, shard, dist=None, world_size=1, rank=0, fused_max_kmers=0):
+        """fused_max_kmers > 0 (CUDA shards only): single-query searches of up to that many k-mers use
+        the in-kernel exchange (FusedExchange) instead of a broadcast and an all-gather per query."""
         self.shard = shard
         self.dist = dist if world_size > 1 else None
         self.world_size = world_size
         self.rank = rank
         self.torch = shard.torch
+        self.fused = None
+        if fused_max_kmers and world_size > 1 and hasattr(shard, "index"):
+            self.fused = FusedExchange(shard, world_size, rank, fused_max_kmers, dist=dist)
+            self.fused_max_kmers = fused_max_kmers
+
+    def search_one_fused(self, kmers_u8, n_kmers, min_kmers):
+        """Single query through the in-kernel exchange; min_kmers is a host integer.  Same result layout
+        as search_step for one query."""
+        return self.fused.search(kmers_u8, n_kmers, min_kmers)
 
     def search_step(self, kmers_u8, q_offsets, min_kmers, n_queries, max_query_kmers=0):
         """One batched search: rank 0's k-mers decide; returns the packed hit buffers of all ranks,

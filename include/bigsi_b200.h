@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BIGSI_B200_ABI_VERSION 3
+#define BIGSI_B200_ABI_VERSION 4
 
 enum {
     BIGSI_B200_OK = 0,
@@ -84,9 +84,11 @@ int bigsi_b200_index_destroy(bigsi_b200_index *index); /* storage.delete_all()/c
 int bigsi_b200_index_get_info(const bigsi_b200_index *index, bigsi_b200_info *info_out);
 
 /* Tuning / instrumentation knobs (value 0 = automatic): "tile_bytes", "grid", "kmers_per_stage",
- * "n_stages", "ctas_per_sm", "debug_flags"; "prehash" / "fuse_merge" (default 1; 0 forces the
- * separate hash / merge kernels); "timing" (1 = bracket the fused kernel and the merge kernel of
- * every query launch with CUDA events, read back with bigsi_b200_index_timing_collect). */
+ * "n_stages", "ctas_per_sm", "merge_chunk_bytes", "debug_flags"; "prehash" / "fuse_merge" / "solo" /
+ * "zero_copy" (default 1; 0 forces the separate hash / merge kernels, the generic single-query
+ * path, the staged host copies); "pool_pct" (default 12: share of a query's k-mers that the CTAs
+ * claim dynamically); "timing" (1 = bracket the fused kernel and the merge kernel of every query
+ * launch with CUDA events, read back with bigsi_b200_index_timing_collect). */
 int bigsi_b200_index_set_option(bigsi_b200_index *index, const char *key, int64_t value);
 /* Synchronises, sums the event-timed durations recorded since the last collect and resets them.
  * fused_ms = fused gather-AND-count kernel, merge_ms = merge kernel, n = query launches timed. */
@@ -188,6 +190,36 @@ int bigsi_b200_search_kmers_hits(bigsi_b200_index *index, const char *kmers, con
 /* lookup(): per-k-mer AND vectors to host, out = uint8 [n][out_stride]. */
 int bigsi_b200_lookup_kmers(bigsi_b200_index *index, const char *kmers, uint64_t n, int k, int h,
                             uint8_t *out, uint64_t out_stride);
+
+/* ---- column-sharded search over several GPUs WITHOUT per-query collectives ------------------
+ * The reference has no distributed path; sample columns are independent (graph/index.py:42-80,
+ * graph/bigsi.py:192-230), so shard g holds all rows of its column range on its own GPU and a
+ * query needs two exchanges: the query itself to every shard, the per-shard hits back.  Both are
+ * fused into the query kernel: rank 0's kernel stores the k-mer bytes into its peers' inboxes from
+ * its prologue (NVLink peer stores + per-CTA flags), every rank's kernel publishes its hit list
+ * into slot `rank` of every rank's result blocks and finishes only when all slots of its own copy
+ * have arrived (all-gather semantics in stream order).  One handle per GPU; handles may live in
+ * different processes (CUDA IPC) or in one (open_local).  Calls are SPMD: every rank calls
+ * exchange_search_dev once per query with the same n_kmers / k / h / min_kmers.
+ *
+ * create: allocates this rank's block; ipc_handle_out (64 bytes, may be NULL) is what the other
+ *         processes pass to open.  spec = hits one result block holds (longer hit lists are cut,
+ *         the count stays exact); max_kmer_bytes = largest query (n_kmers * k).
+ * open / open_local: map the peers' blocks (handles: world x 64 bytes in rank order; peers: world
+ *         handles of the same process).
+ * search_dev: d_kmers = n_kmers * k raw unique k-mers on rank 0's device, 16-byte aligned (ignored
+ *         on other ranks).  *d_blocks_out = device pointer to `world` result blocks of
+ *         *block_bytes_out bytes each, block r = { u64 seq; u64 n_hits; int32 cols[spec]; uint32
+ *         counts[spec] } with LOCAL column ids of shard r; valid in stream order after the call and
+ *         until the next-but-one search on this handle. */
+int bigsi_b200_exchange_create(bigsi_b200_index *index, int world, int rank, uint64_t max_kmer_bytes, uint32_t spec,
+                               uint8_t *ipc_handle_out);
+int bigsi_b200_exchange_open(bigsi_b200_index *index, const uint8_t *ipc_handles);
+int bigsi_b200_exchange_open_local(bigsi_b200_index *index, bigsi_b200_index *const *peers);
+int bigsi_b200_exchange_search_dev(bigsi_b200_index *index, const char *d_kmers, uint64_t n_kmers, int k, int h,
+                                   uint32_t min_kmers, void *stream, const void **d_blocks_out,
+                                   uint64_t *block_bytes_out);
+int bigsi_b200_exchange_destroy(bigsi_b200_index *index);
 
 #ifdef __cplusplus
 }

@@ -531,3 +531,56 @@ def test_solo_path_geometries(B, opts):
             assert np.array_equal(ix.search_kmers(arr, k, h, mode=1)[0], oix.presence(_kmer_strs(arr)))
     finally:
         ix.close()
+
+
+# ---------------------------------------------------------------------------
+# multi-GPU: broadcast + all-gather fused into the query kernel (needs >= 2 GPUs)
+# ---------------------------------------------------------------------------
+def test_fused_exchange_two_shards_one_process(B):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from bigsi_b200.sharded import DeviceShard, FusedExchange, merge_shard_hits, unpack_hits
+
+    rng = np.random.default_rng(47)
+    m, N, k, h, cap = 10_007, 6000, 31, 3, 256
+    rb = (N + 7) // 8
+    rows = rng.random((m, rb * 8)) < 0.93
+    rows[:, N:] = False
+    packed = np.packbits(rows, axis=1)
+    oix = O.OracleIndex(k, m, h, N, rows=packed)
+    half = 3000  # multiple of 8
+    shards, exs = [], []
+    for g in range(2):
+        ix = B.DeviceIndex(m, half, col_offset=g * half, device=g)
+        ix.upload_rows(0, packed, src_byte_offset=g * half // 8)
+        shards.append(DeviceShard(ix, k, h, cap=cap))
+    for g in range(2):
+        exs.append(FusedExchange(shards[g], 2, g, 12_000, peers=True))
+    FusedExchange.connect_local(exs)
+    try:
+        for step, n_kmers in enumerate((1, 60, 700, 5000, 9000, 333)):
+            arr = _rand_kmers(rng, n_kmers, k)
+            cnt = oix.counts(_kmer_strs(arr))
+            thr = int(math.ceil(n_kmers * 0.8))
+            d_k = torch.from_numpy(arr).to(shards[0].device)
+            # rank 1 first: its kernel waits for rank 0's push
+            with torch.cuda.device(1):
+                g1 = exs[1].search(None, n_kmers, thr)
+            with torch.cuda.device(0):
+                g0 = exs[0].search(d_k, n_kmers, thr)
+            torch.cuda.synchronize(0)
+            torch.cuda.synchronize(1)
+            exp = np.nonzero(cnt >= thr)[0]
+            for g in (g0, g1):  # both ranks hold both shards' hits (all-gather)
+                n, cols, vals = unpack_hits(g.cpu().numpy(), 1, cap)
+                assert int(n[:, 0].sum()) == len(exp), (step, n_kmers)
+                if (n[:, 0] <= cap).all():
+                    gc, gv = merge_shard_hits(n[:, 0], cols[:, 0], vals[:, 0], [0, half])
+                    assert np.array_equal(gc, exp) and np.array_equal(gv, cnt[exp])
+    finally:
+        for e in exs:
+            e.close()
+        for s in shards:
+            s.index.close()
