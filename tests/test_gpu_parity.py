@@ -584,3 +584,109 @@ def test_fused_exchange_two_shards_one_process(B):
             e.close()
         for s in shards:
             s.index.close()
+
+
+# ---------------------------------------------------------------------------
+# BASELINE configs 3-5 at full per-GPU size (one 50 000-column shard of the ENA-scale index)
+# ---------------------------------------------------------------------------
+_PLANTED = [0, 1, 49_999, 25_000, 7, 12_345, 33_333]
+_PLANTED_THR = [0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, int(0.95 * 2 ** 32), int(0.6 * 2 ** 32), int(0.41 * 2 ** 32),
+                int(0.3 * 2 ** 32)]
+
+
+@pytest.fixture(scope="module")
+def big_shard(B):
+    """Shard 3 of the 8-shard config-3 index: columns [150 000, 200 000) of N = 400 000, m = 25 M."""
+    import torch
+
+    free, total = torch.cuda.mem_get_info(0)
+    m, N, off = 25_000_000, 50_000, 150_000
+    if free < m * 6272 + (6 << 30):
+        pytest.skip("needs %.0f GB of free HBM" % (m * 6272 / 1e9))
+    planted = [off + c for c in _PLANTED]
+    ix = B.DeviceIndex(m, N, col_offset=off)
+    ix.fill_synthetic(0, 1, planted, _PLANTED_THR)
+    oix = O.OracleIndex(31, m, 3, N, synth=O.SynthSpec(0, 1, planted, _PLANTED_THR), col_offset=off)
+    yield ix, oix
+    ix.close()
+
+
+def _unique_kmers_of(seq_arr, k):
+    """Raw unique k-mers of an ACGT sequence (set semantics, graph/index.py:45), first-occurrence order."""
+    assert k <= 32
+    win = np.lib.stride_tricks.sliding_window_view(seq_arr, k)
+    code = np.zeros(256, dtype=np.uint64)
+    code[[65, 67, 71, 84]] = [0, 1, 2, 3]
+    packed = (code[win] << (2 * np.arange(k, dtype=np.uint64))).sum(axis=1, dtype=np.uint64)  # exact 2-bit key
+    _, first = np.unique(packed, return_index=True)
+    return np.ascontiguousarray(win[np.sort(first)])
+
+
+def test_config3_megabase_query_full_size(B, big_shard):
+    """1 Mbp query (999 970 k-mers) on one shard: additivity against verified 10 000-k-mer pieces,
+    planted columns, AND mode, and the threshold path of config 4 on the same counts."""
+    ix, oix = big_shard
+    k, h = 31, 3
+    rng = np.random.default_rng(2)
+    seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=1_000_000)]
+    arr = _unique_kmers_of(seq, k)
+    U = arr.shape[0]
+    assert 999_000 < U <= 999_970
+    got = ix.search_kmers(arr, k, h)[0].astype(np.int64)
+    assert ix.info()["last_n_slices"] >= 148
+    # all-ones planted columns count every k-mer; the graded ones are ordered by density
+    assert got[0] == U and got[1] == U and got[49_999] == U
+    assert got[25_000] > got[7] > got[100] > got[12_345] > got[33_333]  # densities .95 > .6 > .5 (plain) > .41 > .3
+    # additivity: the sum over 100 disjoint pieces must reproduce the big query exactly ...
+    piece = 10_000
+    acc = np.zeros_like(got)
+    verified = 0
+    for i, p0 in enumerate(range(0, U, piece)):
+        part = arr[p0 : p0 + piece]
+        c = ix.search_kmers(part, k, h)[0].astype(np.int64)
+        if i in (0, 57):  # ... and pieces are checked against the oracle (rows regenerated on the CPU)
+            assert np.array_equal(c, oix.counts(_kmer_strs(part)).astype(np.int64))
+            verified += 1
+        acc += c
+    assert verified == 2 and np.array_equal(acc, got)
+    # exact filter == AND mode == threshold at U
+    pres = np.unpackbits(ix.search_kmers(arr, k, h, mode=1)[0])[:50_000]
+    assert np.array_equal(np.nonzero(pres)[0], np.nonzero(got == U)[0])
+    cols, vals, n = ix.search_kmers_hits(arr, k, h, [U])[0]
+    assert cols.tolist() == [0, 1, 49_999] and n == 3
+    # config 4: score >= 0.4 on the megabase query
+    mk = math.ceil(U * 0.4)
+    cols, vals, n = ix.search_kmers_hits(arr, k, h, [mk])[0]
+    e = np.nonzero(got >= mk)[0]
+    assert np.array_equal(cols, e) and np.array_equal(vals.astype(np.int64), got[e])
+    assert cols.tolist() == [0, 1, 25_000, 49_999]  # 0.95^3 = 0.86 >= 0.4; 0.6^3 = 0.22 and the rest are below
+
+
+def test_config5_batch_of_1000_queries_full_size(B, big_shard):
+    """1 000 queries x 1 000 k-mers in one launch, independent and heavily overlapping variants:
+    batch == one by one == oracle; thresholds per query."""
+    ix, oix = big_shard
+    k, h, Q, L = 31, 3, 1000, 1000
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    indep = acgt[rng.integers(0, 4, size=(Q * L, k))]
+    base = acgt[rng.integers(0, 4, size=100_000 + k)]
+    win = np.lib.stride_tricks.sliding_window_view(base, k)
+    starts = rng.integers(0, 100_000 - L, size=Q)
+    shared = np.ascontiguousarray(np.concatenate([win[s : s + L] for s in starts]))  # windows of one sequence
+    qoff = np.arange(0, Q * L + 1, L)
+    for name, arr in (("independent", indep), ("shared", shared)):
+        counts = ix.search_kmers(arr, k, h, q_offsets=qoff)
+        assert counts.shape[0] == Q
+        assert (counts[:, 0] == L).all() and (counts[:, 49_999] == L).all()
+        for q in (0, 499, 999):
+            part = arr[q * L : (q + 1) * L]
+            assert np.array_equal(counts[q].astype(np.int64), oix.counts(_kmer_strs(part)).astype(np.int64)), (name, q)
+            assert np.array_equal(ix.search_kmers(part, k, h)[0], counts[q]), (name, q)
+        mins = np.full(Q, math.ceil(L * 0.4), dtype=np.uint32)
+        mins[::2] = L
+        res = ix.search_kmers_hits(arr, k, h, mins, q_offsets=qoff, cap=256)
+        for q in (0, 1, 2, 777):
+            cols, vals, n = res[q]
+            e = np.nonzero(counts[q] >= mins[q])[0]
+            assert n == len(e) and np.array_equal(cols, e) and np.array_equal(vals, counts[q][e]), (name, q)
