@@ -80,6 +80,7 @@ SIGNATURES = {
     "bigsi_b200_search_rows": (_int, [_vp, _int, _vp, _vp, _u64, _int, _vp, _u64]),
     "bigsi_b200_search_kmers_hits": (_int, [_vp, _vp, _vp, _u64, _int, _int, _vp, _vp, _vp, _u64, _vp]),
     "bigsi_b200_lookup_kmers": (_int, [_vp, _vp, _u64, _int, _int, _vp, _u64]),
+    "bigsi_b200_search_sequence": (_int, [_vp, _vp, _u64, _int, _int, ctypes.c_double, _vp, _vp, _u64, _vp, _vp]),
     "bigsi_b200_exchange_create": (_int, [_vp, _int, _int, _u64, ctypes.c_uint32, _vp]),
     "bigsi_b200_exchange_open": (_int, [_vp, _vp]),
     "bigsi_b200_exchange_open_local": (_int, [_vp, _vp]),

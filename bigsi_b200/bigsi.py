@@ -243,14 +243,43 @@ class BIGSI(SampleMetadata):
         return {km: _bits.from_packed(packed[i], nbits) for i, km in enumerate(uk)}
 
     def search(self, seq, threshold=1.0, score=False):
-        """graph/bigsi.py:174-190."""
-        self.__validate_search_query(seq)
+        """graph/bigsi.py:174-190.  Without scoring the whole filter stage (k-mer windows, set(kmers),
+        min_kmers, hashing, row gather, AND / count, threshold) is ONE C-ABI call on the device
+        (bigsi_b200_search_sequence); Python keeps the validation, the ordering rules and the result
+        dictionaries."""
         assert threshold <= 1
+        native = not score and isinstance(seq, str) and seq.isascii()
+        if not native:
+            return self._search_host_kmers(seq, threshold, score)
+        n = self.num_samples
+        colours, found, n_hits, num_kmers = self.index.search_sequence(seq.encode("ascii"), self.kmer_size, self.num_hashes,
+                                                                       threshold, cap=max(self.index.num_cols, 1))
+        if num_kmers <= self.min_unique_kmers_in_query:
+            self.__warn_few_kmers(num_kmers)
+        if num_kmers == 0:
+            # the reference reduces over an empty list of per-k-mer vectors (utils/fncts.py:24-25)
+            raise TypeError("reduce() of empty iterable with no initial value")
+        keep = colours < n
+        colours, found = colours[keep], found[keep]
+        if threshold == 1.0:
+            # exact_filter (graph/bigsi.py:192-205): ascending colour, every k-mer found
+            names = self.colours_to_samples(colours.tolist())
+            results = [BigsiQueryResult(colour=int(c), sample_name=names[int(c)], num_kmers=num_kmers, num_kmers_found=num_kmers)
+                       for c in colours]
+        else:
+            # inexact_filter (graph/bigsi.py:211-230): stable sort by count, descending
+            order = np.argsort(-found.astype(np.int64), kind="stable")
+            results = [BigsiQueryResult(colour=int(colours[i]), sample_name=self.colour_to_sample(int(colours[i])),
+                                        num_kmers_found=int(found[i]), num_kmers=num_kmers) for i in order]
+        return [r.todict() for r in results if not r.sample_name == DELETION_SPECIAL_SAMPLE_NAME]
+
+    def _search_host_kmers(self, seq, threshold, score):
+        """The same search with the k-mer set built in Python (non-ASCII sequences, score=True)."""
+        self.__validate_search_query(seq)
         kmers = list(self.seq_to_kmers(seq))
         uk = unique_kmers(kmers)
         num_kmers = len(uk)
         if num_kmers == 0:
-            # the reference reduces over an empty list of per-k-mer vectors (utils/fncts.py:24-25)
             raise TypeError("reduce() of empty iterable with no initial value")
         min_kmers = math.ceil(num_kmers * threshold)
         arr = kmers_to_array(uk, self.kmer_size)
@@ -288,6 +317,13 @@ class BIGSI(SampleMetadata):
 
     def score(self, kmers, unique, results):
         raise NotImplementedError("score=True (Scorer post-processing) is listed under 'next' in DESIGN.md")
+
+    def __warn_few_kmers(self, n):
+        logger.warning(
+            "Query string should contain at least %i unique kmers. Your query contained %i unique kmers, and as a "
+            "result the false discovery rate may be high. In future this will become an error."
+            % (self.min_unique_kmers_in_query, n)
+        )
 
     def __validate_search_query(self, seq):
         kmers = set()

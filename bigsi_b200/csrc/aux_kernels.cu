@@ -201,6 +201,77 @@ cudaError_t launch_set_column(uint8_t *matrix, uint64_t pitch, uint64_t num_rows
 }
 
 // ------------------------------------------------------------------------------------------
+// K8: query front-end.  seq_to_kmers + set(kmers) (bigsi/utils/fncts.py:63-65, graph/index.py:45,
+// graph/bigsi.py:177-179): every window of length k of the sequence, de-duplicated as RAW byte
+// strings.  One thread per window inserts (fingerprint tag, window index) into an open-addressing
+// table; a hit with the same tag is confirmed by comparing the k bytes, so the result is exact, not
+// probabilistic.  First occurrences are compacted (order unspecified: the query is a set) into a
+// dense k-mer array the search kernels take; *counter ends up as U = number of unique k-mers.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dedup_windows_kernel(const uint8_t *__restrict__ seq, uint64_t n, int k,
+                                                            unsigned long long *table, uint64_t mask,
+                                                            uint8_t *__restrict__ out_kmers, unsigned long long *counter)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    bool first = false;
+    if (i < n) {
+        const uint8_t *w = seq + i;
+        uint64_t fp = 0xcbf29ce484222325ull;  // FNV-1a over the bytes, then a 64-bit finaliser
+        for (int j = 0; j < k; ++j) fp = (fp ^ w[j]) * 0x100000001b3ull;
+        fp ^= fp >> 33;
+        fp *= 0xff51afd7ed558ccdull;
+        fp ^= fp >> 33;
+        const unsigned long long tag = fp >> 32;
+        const unsigned long long entry = (tag << 32) | (unsigned long long)(i + 1);
+        uint64_t slot = fp & mask;
+        for (;;) {
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(table + slot);
+            if (cur == 0ull) {
+                cur = atomicCAS(table + slot, 0ull, entry);
+                if (cur == 0ull) {
+                    first = true;
+                    break;
+                }
+            }
+            if ((cur >> 32) == tag) {  // same tag: the same k-mer seen earlier, or a true collision
+                const uint8_t *o = seq + ((cur & 0xffffffffull) - 1);
+                bool same = true;
+                for (int j = 0; j < k; ++j)
+                    if (o[j] != w[j]) {
+                        same = false;
+                        break;
+                    }
+                if (same) break;
+            }
+            slot = (slot + 1) & mask;
+        }
+    }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, first);
+    if (ballot) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (first) {
+            uint8_t *dst = out_kmers + (base + __popc(ballot & ((1u << lane) - 1))) * (uint64_t)k;
+            for (int j = 0; j < k; ++j) dst[j] = seq[i + j];
+        }
+    }
+}
+
+cudaError_t launch_dedup_windows(const uint8_t *d_seq, uint64_t n_windows, int k, unsigned long long *d_table,
+                                 uint64_t table_entries, uint8_t *d_out_kmers, unsigned long long *d_counter,
+                                 cudaStream_t stream)
+{
+    if (n_windows == 0) return cudaSuccess;
+    const uint64_t blocks = (n_windows + 255) / 256;
+    if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    dedup_windows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_seq, n_windows, k, d_table, table_entries - 1, d_out_kmers,
+                                                               d_counter);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // K7: synthetic index, a pure function of (seed, row, GLOBAL column).  Same arithmetic as
 // oracle/bigsi_oracle.c oracle_synth_row (the spec is in DESIGN.md "Synthetic index").
 // ------------------------------------------------------------------------------------------

@@ -1,5 +1,6 @@
 // C ABI of libbigsi_b200.so (include/bigsi_b200.h): index lifecycle, launch planning and the
 // host-buffer entry points.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -163,6 +164,7 @@ struct bigsi_b200_index {
     uint64_t sink_seq = 0;
     // scratch
     DevBuf debug_ts;
+    DevBuf d_seq, d_table;   // query front-end: sequence bytes, de-duplication table (+ counter)
     DevBuf partial, d_kmers, d_rows, d_qoff, d_out, d_min, d_nhits, d_bloom, d_planted;
     PinnedBuf h_small;
     // timing
@@ -645,7 +647,7 @@ int bigsi_b200_index_destroy(bigsi_b200_index *ix)
     cudaDeviceSynchronize();
     for (auto &t : ix->timed_free) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
     for (auto &t : ix->timed_used) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
-    DevBuf *bufs[] = {&ix->d_pool, &ix->d_barrier, &ix->debug_ts, &ix->partial, &ix->d_kmers, &ix->d_rows, &ix->d_qoff, &ix->d_out, &ix->d_min,
+    DevBuf *bufs[] = {&ix->d_seq, &ix->d_table, &ix->d_pool, &ix->d_barrier, &ix->debug_ts, &ix->partial, &ix->d_kmers, &ix->d_rows, &ix->d_qoff, &ix->d_out, &ix->d_min,
                       &ix->d_nhits, &ix->d_bloom, &ix->d_planted};
     for (DevBuf *b : bufs) b->release();
     ix->h_small.release();
@@ -1046,6 +1048,9 @@ int bigsi_b200_search_rows(bigsi_b200_index *ix, int mode, const int32_t *rows, 
 // (mapped, pinned) host memory, takes the threshold by value and publishes the hit list itself into a
 // mapped host block; the host polls that block's sequence word instead of synchronising the stream.
 // Returns 1 when the path does not apply (the caller falls back to the staged path).
+static int search_one_published(bigsi_b200_index *ix, const char *d_kmers, uint64_t total, int k, int h, uint32_t min_kmers,
+                                int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_out);
+
 static int search_one_zero_copy(bigsi_b200_index *ix, const char *kmers, const int64_t *qoff, int k, int h,
                                 uint32_t min_kmers, int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_out)
 {
@@ -1066,6 +1071,15 @@ static int search_one_zero_copy(bigsi_b200_index *ix, const char *kmers, const i
         CK(cudaHostGetDevicePointer(&dp, ix->h_kmers.p, 0));
         d_kmers = static_cast<const char *>(dp);
     }
+    return search_one_published(ix, d_kmers, total, k, h, min_kmers, cols_out, counts_out, cap, n_out);
+}
+
+// One query whose unique raw k-mers are device-addressable: launch with the threshold by value, let the
+// kernel publish the hit list into the mapped host block and poll it.
+static int search_one_published(bigsi_b200_index *ix, const char *d_kmers, uint64_t total, int k, int h, uint32_t min_kmers,
+                                int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_out)
+{
+    cudaError_t e;
     const uint64_t spec = cap < 1024 ? cap : 1024;  // hits the host block holds; longer lists are fetched afterwards
     if ((e = ix->h_sink.reserve(16 + 2 * spec * 4 + 64)) != cudaSuccess) return fail_cuda(e, "pinned result block");
     if ((e = ix->d_nhits.reserve(8 + 2 * cap * 4 + 16)) != cudaSuccess) return fail_cuda(e, "staging");
@@ -1226,6 +1240,48 @@ int bigsi_b200_lookup_kmers(bigsi_b200_index *ix, const char *kmers, uint64_t n,
     CK(cudaMemcpy2DAsync(out, out_stride, ix->d_out.p, dstride, row_bytes, n, cudaMemcpyDeviceToHost, ix->stream));
     CK(cudaStreamSynchronize(ix->stream));
     return 0;
+}
+
+// ============================================================================================
+// query front-end + search: BIGSI.search's filter stage for one sequence (graph/bigsi.py:174-230)
+// ============================================================================================
+int bigsi_b200_search_sequence(bigsi_b200_index *ix, const char *seq, uint64_t len, int k, int h, double threshold,
+                               int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_hits_out,
+                               uint64_t *num_kmers_out)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (!n_hits_out || !num_kmers_out || (cap && (!cols_out || !counts_out))) return fail(BIGSI_B200_ERR_INVALID, "null pointer");
+    if (k < 1 || h < 1) return fail(BIGSI_B200_ERR_INVALID, "k and h must be >= 1");
+    if (len && !seq) return fail(BIGSI_B200_ERR_INVALID, "null sequence");
+    *n_hits_out = 0;
+    *num_kmers_out = 0;
+    if (len < (uint64_t)k) return 0;  // no window: the caller reproduces the reference's TypeError
+    const uint64_t n = len - (uint64_t)k + 1;
+    if (n > 0xfffffff0ull) return fail(BIGSI_B200_ERR_RANGE, "sequence too long");
+    DeviceGuard guard(ix->device);
+    cudaError_t e;
+    uint64_t T = 1024;
+    while (T < 2 * n) T <<= 1;
+    if ((e = ix->d_seq.reserve(len + 64)) != cudaSuccess) return fail_cuda(e, "sequence staging");
+    if ((e = ix->d_table.reserve(T * 8 + 64)) != cudaSuccess) return fail_cuda(e, "de-duplication table");
+    if ((e = ix->d_kmers.reserve(n * (uint64_t)k + 64)) != cudaSuccess) return fail_cuda(e, "k-mer staging");
+    if ((e = ix->h_small.reserve(64)) != cudaSuccess) return fail_cuda(e, "pinned staging");
+    unsigned long long *d_counter = reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(ix->d_table.p) + T * 8);
+    CK(cudaMemcpyAsync(ix->d_seq.p, seq, len, cudaMemcpyHostToDevice, ix->stream));
+    CK(cudaMemsetAsync(ix->d_table.p, 0, T * 8 + 8, ix->stream));
+    CK(launch_dedup_windows(static_cast<const uint8_t *>(ix->d_seq.p), n, k, static_cast<unsigned long long *>(ix->d_table.p), T,
+                            static_cast<uint8_t *>(ix->d_kmers.p), d_counter, ix->stream));
+    ix->kernel_launches++;
+    CK(cudaMemcpyAsync(ix->h_small.p, d_counter, 8, cudaMemcpyDeviceToHost, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    const uint64_t U = *static_cast<const unsigned long long *>(ix->h_small.p);
+    *num_kmers_out = U;
+    if (ix->num_cols == 0) return 0;
+    // min_kmers = math.ceil(U * threshold) in IEEE double (graph/bigsi.py:179); <= 0 keeps every sample
+    const double need = ceil((double)U * threshold);
+    const uint32_t min_kmers = need <= 0.0 ? 0u : need >= 4294967295.0 ? 0xffffffffu : (uint32_t)need;
+    return search_one_published(ix, static_cast<const char *>(ix->d_kmers.p), U, k, h, min_kmers, cols_out, counts_out, cap,
+                                n_hits_out);
 }
 
 // ============================================================================================

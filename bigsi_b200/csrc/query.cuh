@@ -179,6 +179,11 @@ cudaError_t launch_threshold(const uint32_t *d_counts, uint64_t counts_stride, u
                              uint64_t num_cols, const uint32_t *d_min_kmers, int32_t *d_cols_out,
                              uint32_t *d_counts_out, uint64_t cap, unsigned long long *d_n_out,
                              cudaStream_t stream);
+// query front-end: unique raw k-mers of a sequence (table_entries: a power of two >= 2 * n_windows, zeroed;
+// *d_counter zeroed, receives U)
+cudaError_t launch_dedup_windows(const uint8_t *d_seq, uint64_t n_windows, int k, unsigned long long *d_table,
+                                 uint64_t table_entries, uint8_t *d_out_kmers, unsigned long long *d_counter,
+                                 cudaStream_t stream);
 cudaError_t launch_set_column(uint8_t *matrix, uint64_t pitch, uint64_t num_rows, uint64_t col,
                               const uint8_t *d_bloom, uint64_t n_bits, cudaStream_t stream);
 cudaError_t launch_fill_synthetic(uint8_t *matrix, uint64_t pitch, uint64_t num_rows, uint64_t num_cols,

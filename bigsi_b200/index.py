@@ -45,6 +45,7 @@ class DeviceIndex:
         self._L = L
         self._hit_bufs = {}
         self._one_query_offsets = np.zeros(2, dtype=np.int64)
+        self._num_kmers_out = np.zeros(1, dtype=np.uint64)
 
     # -- lifecycle -----------------------------------------------------------
     def close(self):
@@ -187,6 +188,35 @@ class DeviceIndex:
             order = np.argsort(c, kind="stable")
             res.append((c[order], v[order], ni))
         return res
+
+    def search_sequence(self, seq, k, h, threshold, cap=None):
+        """BIGSI.search's filter stage for one sequence, entirely on the device (windows -> set of raw
+        k-mers -> min_kmers = ceil(U * threshold) -> hash -> gather-AND-count -> threshold).
+        seq: bytes / bytearray / uint8 array.  Returns (colours int32 ascending, counts uint32,
+        n_hits, num_kmers U); U == 0 when the sequence is shorter than k."""
+        if isinstance(seq, (bytes, bytearray)):
+            arr = np.frombuffer(seq, dtype=np.uint8)
+        else:
+            arr = np.ascontiguousarray(seq, dtype=np.uint8)
+        cap = self.num_cols if cap is None else int(cap)
+        key = (1, cap)
+        bufs = self._hit_bufs.get(key)
+        if bufs is None:
+            bufs = (np.empty((1, max(cap, 1)), dtype=np.int32), np.empty((1, max(cap, 1)), dtype=np.uint32),
+                    np.zeros(1, dtype=np.uint64))
+            if len(self._hit_bufs) > 8:
+                self._hit_bufs.clear()
+            self._hit_bufs[key] = bufs
+        cols, cnts, n = bufs
+        u = self._num_kmers_out
+        check(self._L.bigsi_b200_search_sequence(self.handle, arr.ctypes.data if arr.size else 0, arr.size, k, h,
+                                                 float(threshold), cols.ctypes.data, cnts.ctypes.data, cap, n.ctypes.data,
+                                                 u.ctypes.data))
+        ni = int(n[0])
+        m = min(ni, cap)
+        c, v = cols[0, :m], cnts[0, :m]
+        order = np.argsort(c, kind="stable")
+        return c[order], v[order], ni, int(u[0])
 
     def lookup_kmers(self, kmers, k, h):
         """Per-k-mer AND vectors: uint8 [n, ceil(N/8)] (graph/index.py:42-49)."""

@@ -187,6 +187,15 @@ int bigsi_b200_search_rows(bigsi_b200_index *index, int mode, const int32_t *row
 int bigsi_b200_search_kmers_hits(bigsi_b200_index *index, const char *kmers, const int64_t *q_offsets,
                                  uint64_t n_queries, int k, int h, const uint32_t *min_kmers,
                                  int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_out);
+/* BIGSI.search's whole filter stage for ONE sequence (graph/bigsi.py:174-230) on the device: every
+ * window of length k (utils/fncts.py:63-65), de-duplicated as RAW byte strings (graph/index.py:45),
+ * *num_kmers_out = U = number of unique k-mers, min_kmers = ceil(U * threshold) in IEEE double
+ * (<= 0 keeps every column), then canonical + hash + gather-AND-count + threshold.  Hits as in
+ * bigsi_b200_search_kmers_hits for one query (order unspecified, *n_hits_out may exceed cap).
+ * len < k: no window, both outputs 0 (the reference raises TypeError there; the caller decides). */
+int bigsi_b200_search_sequence(bigsi_b200_index *index, const char *seq, uint64_t len, int k, int h, double threshold,
+                               int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_hits_out,
+                               uint64_t *num_kmers_out);
 /* lookup(): per-k-mer AND vectors to host, out = uint8 [n][out_stride]. */
 int bigsi_b200_lookup_kmers(bigsi_b200_index *index, const char *kmers, uint64_t n, int k, int h,
                             uint8_t *out, uint64_t out_stride);

@@ -690,3 +690,49 @@ def test_config5_batch_of_1000_queries_full_size(B, big_shard):
             cols, vals, n = res[q]
             e = np.nonzero(counts[q] >= mins[q])[0]
             assert n == len(e) and np.array_equal(cols, e) and np.array_equal(vals, counts[q][e]), (name, q)
+
+
+# ---------------------------------------------------------------------------
+# native query front-end: sequence -> set of raw k-mers -> search, one C-ABI call
+# ---------------------------------------------------------------------------
+def test_search_sequence_front_end(B):
+    rng = np.random.default_rng(53)
+    m, N, h = 10_007, 3000, 3
+    ix, packed = _random_index(B, rng, m, N, density=0.9)
+    try:
+        for k in (5, 11, 31, 32):
+            oix = O.OracleIndex(k, m, h, N, rows=packed)
+            base = "".join(rng.choice(list("ACGT"), size=700))
+            seqs = [
+                base,                                # all windows distinct (k >= 11) or heavily repeated (k = 5)
+                base[:300] + base[:300] + base[100:250],   # repeats: duplicate raw k-mers count once
+                "ACGT" * 40,                         # four distinct windows at most
+                base[:120].lower() + "N" + base[120:200] + "-" + base[:50],  # non-ACGT bytes pass through
+                base[:k],                            # exactly one window
+                "A" * (k + 30),                      # one unique k-mer, many windows
+            ]
+            for seq in seqs:
+                uk = O.unique_kmers(seq, k)
+                cnt = oix.counts(uk)
+                for thr in (1.0, 0.75, 0.3, 0.0, -0.5):
+                    cols, vals, n_hits, U = ix.search_sequence(seq.encode(), k, h, thr)
+                    assert U == len(uk), (k, seq[:16], U, len(uk))
+                    mk = max(math.ceil(len(uk) * thr), 0)
+                    exp = np.nonzero(cnt >= mk)[0]
+                    assert n_hits == len(exp) and np.array_equal(cols, exp) and np.array_equal(vals, cnt[exp]), (k, thr)
+            # shorter than k: no window
+            cols, vals, n_hits, U = ix.search_sequence(base[: k - 1].encode(), k, h, 1.0)
+            assert U == 0 and n_hits == 0
+        # a long sequence (beyond the in-kernel hashing limit): 300 kbp with a duplicated 50 kbp block
+        k = 31
+        oix = O.OracleIndex(k, m, h, N, rows=packed)
+        long_seq = "".join(rng.choice(list("ACGT"), size=250_000))
+        long_seq = long_seq + long_seq[40_000:90_000]
+        uk = O.unique_kmers(long_seq, k)
+        cnt = oix.counts(uk)
+        mk = math.ceil(len(uk) * 0.6)
+        cols, vals, n_hits, U = ix.search_sequence(long_seq.encode(), k, h, 0.6)
+        exp = np.nonzero(cnt >= mk)[0]
+        assert U == len(uk) and n_hits == len(exp) and np.array_equal(cols, exp) and np.array_equal(vals, cnt[exp])
+    finally:
+        ix.close()

@@ -55,3 +55,6 @@ for i in range(200):
     f(*args[i % 64])
 fm, mm, nn = ix.timing_collect()
 print("kernel (events) in the zero-copy path %.1f us" % (1e3 * fm / nn))
+seq = bytes(acgt[rng.integers(0, 4, size=U + K - 1)])
+seqs = [bytes(acgt[rng.integers(0, 4, size=U + K - 1)]) for _ in range(16)]
+print("search_sequence (wrapper, 10 030-base sequence, threshold 1.0)  %.1f us" % timeit(lambda i: ix.search_sequence(seqs[i % 16], K, H, 1.0, cap=CAP)))
