@@ -49,6 +49,22 @@ class Info(ctypes.Structure):
         return {name: getattr(self, name) for name, _ in self._fields_}
 
 
+class FileHeader(ctypes.Structure):
+    """bigsi_b200_file_header (include/bigsi_b200.h)."""
+
+    _fields_ = [
+        ("magic", ctypes.c_char * 8),
+        ("version", ctypes.c_uint32),
+        ("header_bytes", ctypes.c_uint32),
+        ("num_rows", ctypes.c_uint64),
+        ("num_cols", ctypes.c_uint64),
+        ("col_offset", ctypes.c_uint64),
+        ("row_bytes", ctypes.c_uint64),
+        ("meta_bytes", ctypes.c_uint64),
+        ("rows_offset", ctypes.c_uint64),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/bigsi_b200.h declares
 _u64, _i64, _int, _vp = ctypes.c_uint64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p
 SIGNATURES = {
@@ -81,6 +97,13 @@ SIGNATURES = {
     "bigsi_b200_search_kmers_hits": (_int, [_vp, _vp, _vp, _u64, _int, _int, _vp, _vp, _vp, _u64, _vp]),
     "bigsi_b200_lookup_kmers": (_int, [_vp, _vp, _u64, _int, _int, _vp, _u64]),
     "bigsi_b200_search_sequence": (_int, [_vp, _vp, _u64, _int, _int, ctypes.c_double, _vp, _vp, _u64, _vp, _vp]),
+    "bigsi_b200_bloom_kmers": (_int, [_int, _vp, _u64, _int, _int, _u64, _int, _vp]),
+    "bigsi_b200_index_build_columns": (_int, [_vp, _u64, _u64, _vp, _u64, _u64]),
+    "bigsi_b200_index_build_columns_dev": (_int, [_vp, _u64, _u64, _vp, _u64, _u64, _vp]),
+    "bigsi_b200_sequence_presence": (_int, [_vp, _vp, _u64, _int, _int, _vp, _u64, _vp]),
+    "bigsi_b200_index_save": (_int, [_vp, ctypes.c_char_p, _vp, _u64]),
+    "bigsi_b200_file_info": (_int, [ctypes.c_char_p, _vp, _vp, _u64]),
+    "bigsi_b200_index_load_rows": (_int, [_vp, ctypes.c_char_p, _u64, _u64, _u64, _u64, _u64]),
     "bigsi_b200_exchange_create": (_int, [_vp, _int, _int, _u64, ctypes.c_uint32, _vp]),
     "bigsi_b200_exchange_open": (_int, [_vp, _vp]),
     "bigsi_b200_exchange_open_local": (_int, [_vp, _vp]),

@@ -14,6 +14,7 @@ DeviceIndex + the fused CUDA kernel:
 The reference constructs BIGSI(config) per request/worker (bigsi/__main__.py:204,76); the GPU
 index is therefore cached per process, keyed by the storage name, and never re-uploaded per call.
 """
+import json
 import logging
 import math
 
@@ -22,8 +23,9 @@ import numpy as np
 from . import bits as _bits
 from ._lib import MODE_AND, MODE_COUNTS
 from .bloom import BloomFilter
-from .index import DeviceIndex, hash_kmers, kmers_to_array
+from .index import DeviceIndex, bloom_kmers, file_info, hash_kmers, kmers_to_array
 from .metadata import DELETION_SPECIAL_SAMPLE_NAME, SampleMetadata
+from .scoring import Scorer
 from .utils import convert_query_kmers, seq_to_kmers, unique_kmers
 
 logger = logging.getLogger(__name__)
@@ -116,6 +118,7 @@ class BIGSI(SampleMetadata):
         self._store = _STORES[name]
         SampleMetadata.__init__(self, self._store.meta)
         self.min_unique_kmers_in_query = MIN_UNIQUE_KMERS_IN_QUERY
+        self.scorer = Scorer(self.num_samples)  # graph/bigsi.py:140 (DB size fixed at construction)
 
     # -- properties ------------------------------------------------------------
     @property
@@ -162,22 +165,20 @@ class BIGSI(SampleMetadata):
         store = _Store(index, m, h, k)
         try:
             SampleMetadata(store.meta).add_samples(samples)
-            packed = []
-            for bf in bloomfilters:
-                if isinstance(bf, BloomFilter):
-                    bf = bf.bitarray
-                p = _bits.to_packed(bf, m)
-                if p.size * 8 < m:
-                    raise ValueError("bloom filter shorter than m=%d bits" % m)
-                packed.append(p[: (m + 7) // 8])
-            # matrix/transpose.py:33-43: N filters of m bits -> m rows of N bits, in row chunks
-            if n:
-                rows_per_chunk = max(1, (1 << 26) // max(n, 1))
-                for r0 in range(0, m, rows_per_chunk):
-                    r1 = min(m, r0 + rows_per_chunk)
-                    b0, b1 = r0 // 8, (r1 + 7) // 8
-                    X = np.stack([np.unpackbits(p[b0:b1])[r0 - b0 * 8 : r1 - b0 * 8] for p in packed], axis=1)
-                    index.upload_rows(r0, np.packbits(X, axis=1))
+            nbytes = (m + 7) // 8
+            # matrix/transpose.py:33-50 + matrix/bitmatrix.py:19-25: the N filters of m bits become the N
+            # columns of the m x N matrix -- one bit-transpose kernel per staged group of filters
+            group = max(32, ((256 << 20) // max(nbytes, 1)) // 32 * 32)
+            for c0 in range(0, n, group):
+                packed = np.zeros((min(group, n - c0), nbytes), dtype=np.uint8)
+                for i, bf in enumerate(bloomfilters[c0 : c0 + group]):
+                    if isinstance(bf, BloomFilter):
+                        bf = bf.bitarray
+                    p = _bits.to_packed(bf, m)
+                    if p.size * 8 < m:
+                        raise ValueError("bloom filter shorter than m=%d bits" % m)
+                    packed[i] = p[:nbytes]
+                index.build_columns(c0, packed, m)
         except Exception:
             store.close()
             raise
@@ -248,8 +249,7 @@ class BIGSI(SampleMetadata):
         (bigsi_b200_search_sequence); Python keeps the validation, the ordering rules and the result
         dictionaries."""
         assert threshold <= 1
-        native = not score and isinstance(seq, str) and seq.isascii()
-        if not native:
+        if not (isinstance(seq, str) and seq.isascii()):
             return self._search_host_kmers(seq, threshold, score)
         n = self.num_samples
         colours, found, n_hits, num_kmers = self.index.search_sequence(seq.encode("ascii"), self.kmer_size, self.num_hashes,
@@ -271,6 +271,8 @@ class BIGSI(SampleMetadata):
             order = np.argsort(-found.astype(np.int64), kind="stable")
             results = [BigsiQueryResult(colour=int(colours[i]), sample_name=self.colour_to_sample(int(colours[i])),
                                         num_kmers_found=int(found[i]), num_kmers=num_kmers) for i in order]
+        if score:
+            self.score(seq, results)
         return [r.todict() for r in results if not r.sample_name == DELETION_SPECIAL_SAMPLE_NAME]
 
     def _search_host_kmers(self, seq, threshold, score):
@@ -288,7 +290,7 @@ class BIGSI(SampleMetadata):
         else:
             results = self.inexact_filter(arr, num_kmers, min_kmers)
         if score:
-            self.score(kmers, uk, results)
+            self.score(seq, results)
         return [r.todict() for r in results if not r.sample_name == DELETION_SPECIAL_SAMPLE_NAME]
 
     def exact_filter(self, kmer_array, num_kmers):
@@ -315,8 +317,127 @@ class BIGSI(SampleMetadata):
         return [BigsiQueryResult(colour=int(colours[i]), sample_name=self.colour_to_sample(int(colours[i])),
                                  num_kmers_found=int(found[i]), num_kmers=num_kmers) for i in order]
 
-    def score(self, kmers, unique, results):
-        raise NotImplementedError("score=True (Scorer post-processing) is listed under 'next' in DESIGN.md")
+    def score(self, seq, results):
+        """graph/bigsi.py:232-239: for every hit, the presence of EVERY window of the query (in sequence
+        order, duplicates included) in the hit's column -> Scorer.  The K x hits presence bits come from
+        the GPU (bigsi_b200_sequence_presence) instead of a K x N int32 matrix built by repeated vstack."""
+        if not results:
+            return
+        if len(seq) - self.kmer_size + 1 == 1:
+            # a single window: the reference's unpack_and_cat yields a 1-D array and X[:, colour] raises
+            raise IndexError("too many indices for array: array is 1-dimensional, but 2 were indexed")
+        presence = self.index.sequence_presence(seq.encode("ascii"), self.kmer_size, self.num_hashes,
+                                                [r.colour for r in results])
+        for res, row in zip(results, presence):
+            col = row.tobytes().decode("ascii")
+            score_results = self.scorer.score(col)
+            score_results["kmer-presence"] = col
+            res.add_score(score_results)
+
+    # -- persistence (SURVEY.md section 8f rank 2) --------------------------------
+    def _meta_entries(self):
+        return [[key[1], value] for key, value in self._store.meta.items()]
+
+    def save(self, path):
+        """Flat index file (include/bigsi_b200.h "persistence"): rows in the reference's byte layout plus
+        the ksi:* / metadata:* keys as JSON.  Replaces the durability of the reference's KV stores."""
+        meta = {"format": "bigsi_b200/1", "k": self._store.kmer_size, "m": self.bloomfilter_size, "h": self.num_hashes,
+                "metadata": self._meta_entries()}
+        self.index.save(path, json.dumps(meta, separators=(",", ":")).encode("utf-8"))
+
+    @classmethod
+    def load(cls, config, path):
+        """Open an index file written by save() into HBM (file -> pinned double buffer -> device) and
+        register it under config's storage name.  config["k"/"m"/"h"] are taken from the file."""
+        hd, meta_bytes = file_info(path)
+        meta = json.loads(meta_bytes.decode("utf-8"))
+        sc = config.get("storage-config", {}) or {}
+        capacity = max(int(sc.get("col_capacity", 0)), hd["num_cols"], 1)
+        index = DeviceIndex(hd["num_rows"], hd["num_cols"], col_capacity=capacity, col_offset=hd["col_offset"],
+                            device=_device(config))
+        try:
+            index.load_rows(path, hd["rows_offset"], hd["row_bytes"], 0, 0, hd["num_rows"])
+        except Exception:
+            index.close()
+            raise
+        store = _Store(index, meta["m"], meta["h"], meta["k"])
+        for key, value in meta["metadata"]:
+            store.meta[("metadata", key)] = value
+        config["k"], config["m"], config["h"] = meta["k"], meta["m"], meta["h"]
+        name = _store_name(config)
+        if name in _STORES:
+            _STORES.pop(name).close()
+        _STORES[name] = store
+        return cls(config)
+
+    def to_kv(self, rows_per_chunk=4096):
+        """The index as the reference's v0.3 key/value schema (storage/base.py:29-52,77-94; graph/index.py:10-11;
+        matrix/bitmatrix.py:3-4; graph/metadata.py:8-10,111-112): a dict a reference storage backend could
+        be filled from (`storage[k] = v`)."""
+        kv = {}
+
+        def put_int(key, value):
+            kv[("%s:int" % key).encode("utf-8")] = str(int(value)).encode("utf-8")
+
+        put_int("ksi:bloomfilter_size", self.bloomfilter_size)
+        put_int("ksi:num_hashes", self.num_hashes)
+        put_int("number_of_rows", self.bloomfilter_size)
+        put_int("number_of_cols", self.index.num_cols)
+        for (_, key), value in self._store.meta.items():
+            if isinstance(value, int):
+                put_int("metadata:%s" % key, value)
+            else:
+                kv[("metadata:%s:string" % key).encode("utf-8")] = str(value).encode("utf-8")
+        m = self.bloomfilter_size
+        for r0 in range(0, m, rows_per_chunk):
+            rows = self.index.download_rows(r0, min(rows_per_chunk, m - r0))
+            for i in range(rows.shape[0]):
+                kv[b"%d:bitarray" % (r0 + i)] = rows[i].tobytes()
+        return kv
+
+    @classmethod
+    def from_kv(cls, config, kv, rows_per_chunk=4096):
+        """Import an index from the reference's v0.3 key/value schema (any mapping with bytes keys, e.g.
+        a dump of its RocksDB/BerkeleyDB store) into HBM and register it under config's storage name."""
+        def get_int(key):
+            return int(bytes(kv[("%s:int" % key).encode("utf-8")]).decode("utf-8"))
+
+        m, h = get_int("ksi:bloomfilter_size"), get_int("ksi:num_hashes")
+        n_rows, n_cols = get_int("number_of_rows"), get_int("number_of_cols")
+        if n_rows != m:
+            raise ValueError("number_of_rows=%d differs from ksi:bloomfilter_size=%d" % (n_rows, m))
+        sc = config.get("storage-config", {}) or {}
+        capacity = max(int(sc.get("col_capacity", 0)), n_cols, 1)
+        index = DeviceIndex(m, n_cols, col_capacity=capacity, col_offset=0, device=_device(config))
+        store = _Store(index, m, h, config["k"])
+        try:
+            row_bytes = (n_cols + 7) // 8
+            for r0 in range(0, m, rows_per_chunk):
+                n = min(rows_per_chunk, m - r0)
+                buf = np.zeros((n, max(row_bytes, 1)), dtype=np.uint8)
+                for i in range(n):
+                    v = np.frombuffer(bytes(kv[b"%d:bitarray" % (r0 + i)]), dtype=np.uint8)
+                    buf[i, : min(v.size, row_bytes)] = v[:row_bytes]
+                if row_bytes:
+                    index.upload_rows(r0, buf)
+            for key, value in kv.items():
+                key = bytes(key).decode("utf-8")
+                if not key.startswith("metadata:"):
+                    continue
+                name, kind = key[len("metadata:"):].rsplit(":", 1)
+                if kind == "int":  # sample name -> colour, or the colour count
+                    store.meta[("metadata", name)] = int(bytes(value).decode("utf-8"))
+                else:              # colour -> sample name
+                    store.meta[("metadata", int(name))] = bytes(value).decode("utf-8")
+        except Exception:
+            store.close()
+            raise
+        config["m"], config["h"] = m, h
+        name = _store_name(config)
+        if name in _STORES:
+            _STORES.pop(name).close()
+        _STORES[name] = store
+        return cls(config)
 
     def __warn_few_kmers(self, n):
         logger.warning(

@@ -2,7 +2,7 @@
 import numpy as np
 
 from . import bits as _bits
-from .index import hash_kmers
+from .index import bloom_kmers, hash_kmers
 
 
 def generate_hashes(element, number_hash_functions, bloomfilter_size, device=0):
@@ -15,22 +15,24 @@ def generate_hashes(element, number_hash_functions, bloomfilter_size, device=0):
 
 
 class BloomFilter(object):
-    """bigsi/bloom/bloomfilter.py:16-32.  Bits are zero-initialised here (the reference leaves
-    `bitarray(m)` uninitialised, which is why its shipped .bloom fixtures carry stray bits)."""
+    """bigsi/bloom/bloomfilter.py:16-32.  The filter is kept as the packed MSB-first bytes of the
+    reference's bitarray; `update` hashes the elements AND sets the bits on the GPU
+    (bigsi_b200_bloom_kmers).  Bits are zero-initialised here (the reference leaves `bitarray(m)`
+    uninitialised, which is why its shipped .bloom fixtures carry stray bits)."""
 
     def __init__(self, m, h, device=0):
         self.m = m
         self.h = h
         self.device = device
-        self._bools = np.zeros(m, dtype=bool)
+        self._packed = np.zeros((m + 7) // 8, dtype=np.uint8)
 
     @property
     def bitarray(self):
-        return _bits.from_packed(np.packbits(self._bools), self.m)
+        return _bits.from_packed(self._packed, self.m)
 
     def add(self, e):
         for i in generate_hashes(e, self.h, self.m, self.device):
-            self._bools[i] = True
+            self._packed[i >> 3] |= 0x80 >> (i & 7)
 
     def update(self, elements):
         elements = list(elements)
@@ -40,9 +42,9 @@ class BloomFilter(object):
         if len(lens) == 1:
             k = lens.pop()
             arr = np.frombuffer("".join(elements).encode("utf-8"), dtype=np.uint8)
-            if arr.size == len(elements) * k:
-                r = hash_kmers(arr.reshape(len(elements), k), k, self.h, self.m, canonical=False, device=self.device)
-                self._bools[r.reshape(-1)] = True
+            if k and arr.size == len(elements) * k:
+                self._packed |= bloom_kmers(arr.reshape(len(elements), k), k, self.h, self.m, canonical=False,
+                                            device=self.device)
                 return self
         for e in elements:
             self.add(e)

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libbigsi_b200.so")
-SOURCES = ["capi.cu", "query_kernels.cu", "merge_kernels.cu", "aux_kernels.cu"]
+SOURCES = ["capi.cu", "query_kernels.cu", "merge_kernels.cu", "aux_kernels.cu", "build_kernels.cu"]
 HEADERS = ["ptx.cuh", "query.cuh", "launch.cuh", "hash.cuh", "merge.cuh", os.path.join("..", "..", "include", "bigsi_b200.h")]
 
 NVCC_FLAGS = [

@@ -1,5 +1,7 @@
 // C ABI of libbigsi_b200.so (include/bigsi_b200.h): index lifecycle, launch planning and the
 // host-buffer entry points.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <algorithm>
+#include <cerrno>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1282,6 +1284,304 @@ int bigsi_b200_search_sequence(bigsi_b200_index *ix, const char *seq, uint64_t l
     const uint32_t min_kmers = need <= 0.0 ? 0u : need >= 4294967295.0 ? 0xffffffffu : (uint32_t)need;
     return search_one_published(ix, static_cast<const char *>(ix->d_kmers.p), U, k, h, min_kmers, cols_out, counts_out, cap,
                                 n_hits_out);
+}
+
+// ============================================================================================
+// build path: Bloom filters on the device, N x m -> m x N transpose
+// ============================================================================================
+int bigsi_b200_bloom_kmers(int device, const char *kmers, uint64_t n, int k, int h, uint64_t m, int canonical,
+                           uint8_t *bloom_out)
+{
+    if (k < 1 || h < 1) return fail(BIGSI_B200_ERR_INVALID, "k and h must be >= 1");
+    if (m == 0 || m > 0x7fffffffull) return fail(BIGSI_B200_ERR_INVALID, "m must be in [1, 2^31-1]");
+    if (!bloom_out || (n && !kmers)) return fail(BIGSI_B200_ERR_INVALID, "null pointer");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
+    if (ndev == 0) return fail(BIGSI_B200_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return fail(BIGSI_B200_ERR_INVALID, "device out of range");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
+    const uint64_t nbytes = (m + 7) / 8, words_bytes = round_up(nbytes, 4);
+    DevBuf d_k, d_r, d_b;
+    int rc = 0;
+    auto done = [&](int code) {
+        d_k.release();
+        d_r.release();
+        d_b.release();
+        return code;
+    };
+    if ((e = d_b.reserve(words_bytes)) != cudaSuccess) return done(fail_cuda(e, "bloom buffer"));
+    if ((e = cudaMemsetAsync(d_b.p, 0, words_bytes, nullptr)) != cudaSuccess) return done(fail_cuda(e, "memset"));
+    if (n) {
+        if ((e = d_k.reserve(n * (uint64_t)k)) != cudaSuccess) return done(fail_cuda(e, "k-mer staging"));
+        if ((e = d_r.reserve(n * (uint64_t)h * 4)) != cudaSuccess) return done(fail_cuda(e, "row-id staging"));
+        if ((e = cudaMemcpyAsync(d_k.p, kmers, n * (uint64_t)k, cudaMemcpyHostToDevice, nullptr)) != cudaSuccess)
+            return done(fail_cuda(e, "k-mer copy"));
+        if ((rc = bigsi_b200_hash_kmers_dev(static_cast<const char *>(d_k.p), n, k, h, m, canonical, static_cast<int32_t *>(d_r.p),
+                                            nullptr)))
+            return done(rc);
+        if ((e = launch_bloom_set_bits(static_cast<const int32_t *>(d_r.p), n * (uint64_t)h, static_cast<uint8_t *>(d_b.p),
+                                       nullptr)) != cudaSuccess)
+            return done(fail_cuda(e, "bloom_set_bits"));
+    }
+    e = cudaMemcpy(bloom_out, d_b.p, nbytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return done(fail_cuda(e, "bloom copy"));
+    return done(0);
+}
+
+static int build_columns_check(bigsi_b200_index *ix, uint64_t col0, uint64_t n_blooms, uint64_t n_bits)
+{
+    if (n_bits > ix->num_rows) return fail(BIGSI_B200_ERR_RANGE, "bloom filters longer than m");
+    if (col0 > ix->num_cols) return fail(BIGSI_B200_ERR_RANGE, "first column %llu beyond num_cols=%llu", (unsigned long long)col0,
+                                         (unsigned long long)ix->num_cols);
+    if (col0 + n_blooms > ix->col_capacity)
+        return fail(BIGSI_B200_ERR_RANGE, "columns [%llu,%llu) exceed the column capacity %llu", (unsigned long long)col0,
+                    (unsigned long long)(col0 + n_blooms), (unsigned long long)ix->col_capacity);
+    return 0;
+}
+
+int bigsi_b200_index_build_columns_dev(bigsi_b200_index *ix, uint64_t col0, uint64_t n_blooms, const uint8_t *d_blooms,
+                                       uint64_t bloom_stride, uint64_t n_bits, void *stream)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (n_blooms == 0) return 0;
+    if (!d_blooms) return fail(BIGSI_B200_ERR_INVALID, "null bloom filters");
+    if (int rc = build_columns_check(ix, col0, n_blooms, n_bits)) return rc;
+    if ((bloom_stride & 31) || bloom_stride < (ix->num_rows + 255) / 256 * 32 || (reinterpret_cast<uintptr_t>(d_blooms) & 15))
+        return fail(BIGSI_B200_ERR_INVALID, "device bloom filters need a 16-byte aligned base and a stride that is a multiple "
+                                            "of 32 bytes and >= ceil(m/256)*32");
+    DeviceGuard guard(ix->device);
+    CK(launch_transpose_blooms(ix->matrix, ix->pitch, ix->num_rows, col0, n_blooms, d_blooms, bloom_stride, n_bits,
+                               static_cast<cudaStream_t>(stream)));
+    ix->kernel_launches++;
+    if (col0 + n_blooms > ix->num_cols) ix->num_cols = col0 + n_blooms;
+    return 0;
+}
+
+int bigsi_b200_index_build_columns(bigsi_b200_index *ix, uint64_t col0, uint64_t n_blooms, const uint8_t *blooms,
+                                   uint64_t bloom_stride, uint64_t n_bits)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (n_blooms == 0) return 0;
+    if (!blooms) return fail(BIGSI_B200_ERR_INVALID, "null bloom filters");
+    const uint64_t nbytes = (n_bits + 7) / 8;
+    if (bloom_stride < nbytes) return fail(BIGSI_B200_ERR_INVALID, "bloom_stride smaller than a filter");
+    if (int rc = build_columns_check(ix, col0, n_blooms, n_bits)) return rc;
+    DeviceGuard guard(ix->device);
+    // stage the filters in chunks of whole 32-column words (<= ~1 GiB of HBM), transpose chunk by chunk
+    const uint64_t dstride = (ix->num_rows + 255) / 256 * 32;
+    uint64_t chunk = (1ull << 30) / dstride;
+    chunk = chunk < 32 ? 32 : chunk / 32 * 32;
+    cudaError_t e;
+    uint64_t done = 0;
+    while (done < n_blooms) {
+        const uint64_t c0 = col0 + done;
+        uint64_t nb = n_blooms - done;
+        const uint64_t to_word_end = chunk - (c0 & 31);  // later chunks start on a word boundary
+        if (nb > to_word_end) nb = to_word_end;
+        if ((e = ix->d_bloom.reserve(nb * dstride)) != cudaSuccess) return fail_cuda(e, "bloom staging");
+        if (dstride > nbytes) CK(cudaMemsetAsync(ix->d_bloom.p, 0, nb * dstride, ix->stream));
+        if (nbytes)
+            CK(cudaMemcpy2DAsync(ix->d_bloom.p, dstride, blooms + done * bloom_stride, bloom_stride, nbytes, nb,
+                                 cudaMemcpyHostToDevice, ix->stream));
+        CK(launch_transpose_blooms(ix->matrix, ix->pitch, ix->num_rows, c0, nb, static_cast<const uint8_t *>(ix->d_bloom.p),
+                                   dstride, n_bits, ix->stream));
+        ix->kernel_launches++;
+        CK(cudaStreamSynchronize(ix->stream));
+        done += nb;
+    }
+    if (col0 + n_blooms > ix->num_cols) ix->num_cols = col0 + n_blooms;
+    return 0;
+}
+
+// ============================================================================================
+// score=True support: per-window presence of the hit columns
+// ============================================================================================
+int bigsi_b200_sequence_presence(bigsi_b200_index *ix, const char *seq, uint64_t len, int k, int h, const int32_t *cols,
+                                 uint64_t n_cols, uint8_t *out)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (k < 1 || h < 1) return fail(BIGSI_B200_ERR_INVALID, "k and h must be >= 1");
+    if (len < (uint64_t)k || n_cols == 0) return 0;
+    if (!seq || !cols || !out) return fail(BIGSI_B200_ERR_INVALID, "null pointer");
+    for (uint64_t i = 0; i < n_cols; ++i)
+        if (cols[i] < 0 || (uint64_t)cols[i] >= ix->col_capacity)
+            return fail(BIGSI_B200_ERR_RANGE, "column %d outside the matrix", cols[i]);
+    const uint64_t n = len - (uint64_t)k + 1;
+    DeviceGuard guard(ix->device);
+    cudaError_t e;
+    if ((e = ix->d_seq.reserve(len + 64)) != cudaSuccess) return fail_cuda(e, "sequence staging");
+    if ((e = ix->d_rows.reserve(n * (uint64_t)h * 4)) != cudaSuccess) return fail_cuda(e, "row-id staging");
+    if ((e = ix->d_min.reserve(n_cols * 4)) != cudaSuccess) return fail_cuda(e, "column staging");
+    if ((e = ix->d_out.reserve(n * n_cols)) != cudaSuccess) return fail_cuda(e, "presence staging");
+    CK(cudaMemcpyAsync(ix->d_seq.p, seq, len, cudaMemcpyHostToDevice, ix->stream));
+    CK(cudaMemcpyAsync(ix->d_min.p, cols, n_cols * 4, cudaMemcpyHostToDevice, ix->stream));
+    CK(launch_hash_windows(static_cast<const uint8_t *>(ix->d_seq.p), n, k, h, ix->num_rows, static_cast<int32_t *>(ix->d_rows.p),
+                           ix->stream));
+    CK(launch_presence(ix->matrix, ix->pitch, static_cast<const int32_t *>(ix->d_rows.p), n, h,
+                       static_cast<const int32_t *>(ix->d_min.p), n_cols, static_cast<uint8_t *>(ix->d_out.p), ix->stream));
+    ix->kernel_launches += 2;
+    CK(cudaMemcpyAsync(out, ix->d_out.p, n * n_cols, cudaMemcpyDeviceToHost, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    return 0;
+}
+
+// ============================================================================================
+// persistence: flat index file <-> HBM through two pinned buffers
+// ============================================================================================
+namespace {
+constexpr char kFileMagic[8] = {'B', 'I', 'G', 'S', 'I', 'B', '2', '\n'};
+constexpr uint64_t kFileAlign = 4096;
+constexpr uint64_t kIoChunkBytes = 32ull << 20;
+
+struct FileCloser {
+    FILE *f;
+    ~FileCloser()
+    {
+        if (f) fclose(f);
+    }
+};
+}  // namespace
+
+int bigsi_b200_index_save(bigsi_b200_index *ix, const char *path, const void *meta, uint64_t meta_bytes)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (!path || (meta_bytes && !meta)) return fail(BIGSI_B200_ERR_INVALID, "null pointer");
+    const uint64_t row_bytes = (ix->num_cols + 7) / 8;
+    bigsi_b200_file_header hd;
+    memset(&hd, 0, sizeof hd);
+    memcpy(hd.magic, kFileMagic, 8);
+    hd.version = 1;
+    hd.header_bytes = (uint32_t)sizeof hd;
+    hd.num_rows = ix->num_rows;
+    hd.num_cols = ix->num_cols;
+    hd.col_offset = ix->col_offset;
+    hd.row_bytes = row_bytes;
+    hd.meta_bytes = meta_bytes;
+    hd.rows_offset = round_up(sizeof hd + meta_bytes, kFileAlign);
+    FileCloser fc{fopen(path, "wb")};
+    if (!fc.f) return fail(BIGSI_B200_ERR_INVALID, "cannot open %s for writing: %s", path, strerror(errno));
+    if (fwrite(&hd, sizeof hd, 1, fc.f) != 1 || (meta_bytes && fwrite(meta, 1, meta_bytes, fc.f) != meta_bytes))
+        return fail(BIGSI_B200_ERR_INVALID, "write to %s failed: %s", path, strerror(errno));
+    std::vector<uint8_t> pad(hd.rows_offset - sizeof hd - meta_bytes, 0);
+    if (!pad.empty() && fwrite(pad.data(), 1, pad.size(), fc.f) != pad.size())
+        return fail(BIGSI_B200_ERR_INVALID, "write to %s failed: %s", path, strerror(errno));
+    if (row_bytes == 0) return 0;
+    DeviceGuard guard(ix->device);
+    // device -> pinned buffer A while buffer B is being written to the file
+    const uint64_t rows_per_chunk = kIoChunkBytes / row_bytes ? kIoChunkBytes / row_bytes : 1;
+    PinnedBuf buf[2];
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int rc = 0;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = buf[i].reserve(rows_per_chunk * row_bytes);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) rc = fail_cuda(e, "pinned staging");
+    const uint64_t n_chunks = (ix->num_rows + rows_per_chunk - 1) / rows_per_chunk;
+    auto issue = [&](uint64_t c) {
+        const uint64_t r0 = c * rows_per_chunk, nr = std::min(rows_per_chunk, ix->num_rows - r0);
+        cudaError_t ee = cudaMemcpy2DAsync(buf[c & 1].p, row_bytes, ix->matrix + r0 * ix->pitch, ix->pitch, row_bytes, nr,
+                                           cudaMemcpyDeviceToHost, ix->stream);
+        if (ee == cudaSuccess) ee = cudaEventRecord(ev[c & 1], ix->stream);
+        return ee;
+    };
+    if (!rc && (e = issue(0)) != cudaSuccess) rc = fail_cuda(e, "device-to-host copy");
+    for (uint64_t c = 0; c < n_chunks && !rc; ++c) {
+        if (c + 1 < n_chunks && (e = issue(c + 1)) != cudaSuccess) {
+            rc = fail_cuda(e, "device-to-host copy");
+            break;
+        }
+        if ((e = cudaEventSynchronize(ev[c & 1])) != cudaSuccess) {
+            rc = fail_cuda(e, "device-to-host copy");
+            break;
+        }
+        const uint64_t r0 = c * rows_per_chunk, nr = std::min(rows_per_chunk, ix->num_rows - r0);
+        if (fwrite(buf[c & 1].p, 1, nr * row_bytes, fc.f) != nr * row_bytes)
+            rc = fail(BIGSI_B200_ERR_INVALID, "write to %s failed: %s", path, strerror(errno));
+    }
+    cudaStreamSynchronize(ix->stream);
+    for (int i = 0; i < 2; ++i) {
+        buf[i].release();
+        if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+    if (!rc && fflush(fc.f) != 0) rc = fail(BIGSI_B200_ERR_INVALID, "flush of %s failed: %s", path, strerror(errno));
+    return rc;
+}
+
+int bigsi_b200_file_info(const char *path, bigsi_b200_file_header *header_out, void *meta_out, uint64_t meta_cap)
+{
+    if (!path || !header_out) return fail(BIGSI_B200_ERR_INVALID, "null pointer");
+    FileCloser fc{fopen(path, "rb")};
+    if (!fc.f) return fail(BIGSI_B200_ERR_INVALID, "cannot open %s: %s", path, strerror(errno));
+    bigsi_b200_file_header hd;
+    if (fread(&hd, sizeof hd, 1, fc.f) != 1 || memcmp(hd.magic, kFileMagic, 8) != 0)
+        return fail(BIGSI_B200_ERR_INVALID, "%s is not a bigsi_b200 index file", path);
+    if (hd.version != 1 || hd.header_bytes != sizeof hd || hd.row_bytes != (hd.num_cols + 7) / 8 ||
+        hd.rows_offset < sizeof hd + hd.meta_bytes)
+        return fail(BIGSI_B200_ERR_INVALID, "%s: unsupported or corrupt header (version %u)", path, hd.version);
+    *header_out = hd;
+    if (meta_out && meta_cap) {
+        const uint64_t n = hd.meta_bytes < meta_cap ? hd.meta_bytes : meta_cap;
+        if (n && fread(meta_out, 1, n, fc.f) != n) return fail(BIGSI_B200_ERR_INVALID, "%s: truncated metadata", path);
+    }
+    return 0;
+}
+
+int bigsi_b200_index_load_rows(bigsi_b200_index *ix, const char *path, uint64_t file_offset, uint64_t file_stride,
+                               uint64_t src_byte_offset, uint64_t row0, uint64_t n_rows)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (!path) return fail(BIGSI_B200_ERR_INVALID, "null path");
+    if (n_rows == 0) return 0;
+    if (row0 + n_rows > ix->num_rows) return fail(BIGSI_B200_ERR_RANGE, "rows out of range");
+    const uint64_t row_bytes = (ix->num_cols + 7) / 8;
+    if (row_bytes == 0) return 0;
+    if (file_stride < src_byte_offset + row_bytes) return fail(BIGSI_B200_ERR_INVALID, "file rows narrower than this shard");
+    FileCloser fc{fopen(path, "rb")};
+    if (!fc.f) return fail(BIGSI_B200_ERR_INVALID, "cannot open %s: %s", path, strerror(errno));
+    if (fseeko(fc.f, (off_t)file_offset, SEEK_SET) != 0) return fail(BIGSI_B200_ERR_INVALID, "seek in %s failed", path);
+    DeviceGuard guard(ix->device);
+    // file -> pinned buffer B while buffer A travels to the device (cudaMemcpy2DAsync from pinned memory)
+    const uint64_t rows_per_chunk = kIoChunkBytes / file_stride ? kIoChunkBytes / file_stride : 1;
+    PinnedBuf buf[2];
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int rc = 0;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = buf[i].reserve(rows_per_chunk * file_stride);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) rc = fail_cuda(e, "pinned staging");
+    const uint8_t last_mask = (ix->num_cols & 7) ? (uint8_t)(0xff00u >> (ix->num_cols & 7)) : (uint8_t)0xff;
+    const uint64_t n_chunks = (n_rows + rows_per_chunk - 1) / rows_per_chunk;
+    for (uint64_t c = 0; c < n_chunks && !rc; ++c) {
+        const uint64_t r0 = c * rows_per_chunk, nr = std::min(rows_per_chunk, n_rows - r0);
+        uint8_t *b = static_cast<uint8_t *>(buf[c & 1].p);
+        if (c >= 2 && (e = cudaEventSynchronize(ev[c & 1])) != cudaSuccess) {  // the copy that used this buffer is done
+            rc = fail_cuda(e, "host-to-device copy");
+            break;
+        }
+        if (fread(b, 1, nr * file_stride, fc.f) != nr * file_stride) {
+            rc = fail(BIGSI_B200_ERR_INVALID, "%s: truncated row data", path);
+            break;
+        }
+        if (last_mask != 0xff)  // columns >= num_cols of a wider file row must not leak into the padding
+            for (uint64_t i = 0; i < nr; ++i) b[i * file_stride + src_byte_offset + row_bytes - 1] &= last_mask;
+        e = cudaMemcpy2DAsync(ix->matrix + (row0 + r0) * ix->pitch, ix->pitch, b + src_byte_offset, file_stride, row_bytes, nr,
+                              cudaMemcpyHostToDevice, ix->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[c & 1], ix->stream);
+        if (e != cudaSuccess) rc = fail_cuda(e, "host-to-device copy");
+    }
+    e = cudaStreamSynchronize(ix->stream);
+    if (!rc && e != cudaSuccess) rc = fail_cuda(e, "host-to-device copy");
+    for (int i = 0; i < 2; ++i) {
+        buf[i].release();
+        if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+    return rc;
 }
 
 // ============================================================================================

@@ -191,4 +191,13 @@ cudaError_t launch_fill_synthetic(uint8_t *matrix, uint64_t pitch, uint64_t num_
                                   const uint64_t *d_planted_cols, const uint32_t *d_planted_thr, int n_planted,
                                   cudaStream_t stream);
 
+// ---- build path / scoring support (build_kernels.cu) -----------------------------------------
+cudaError_t launch_bloom_set_bits(const int32_t *d_rows, uint64_t n, uint8_t *d_bloom, cudaStream_t stream);
+cudaError_t launch_transpose_blooms(uint8_t *matrix, uint64_t pitch, uint64_t num_rows, uint64_t col0, uint64_t n_blooms,
+                                    const uint8_t *d_blooms, uint64_t bloom_stride, uint64_t n_bits, cudaStream_t stream);
+cudaError_t launch_hash_windows(const uint8_t *d_seq, uint64_t n_windows, int k, int h, uint64_t m, int32_t *d_rows_out,
+                                cudaStream_t stream);
+cudaError_t launch_presence(const uint8_t *matrix, uint64_t pitch, const int32_t *d_rows, uint64_t n_windows, int h,
+                            const int32_t *d_cols, uint64_t n_cols, uint8_t *d_out, cudaStream_t stream);
+
 }  // namespace bigsi

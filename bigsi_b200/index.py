@@ -5,6 +5,7 @@ Python face of the C ABI (include/bigsi_b200.h).  Replaces the reference's stora
 addressed by number in one packed HBM array instead of by key in a KV store.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -35,6 +36,28 @@ def hash_kmers(kmers, k, h, m, canonical=True, device=0):
     out = np.empty((arr.shape[0], h), dtype=np.int32)
     check(_lib.lib().bigsi_b200_hash_kmers(device, _ptr(arr), arr.shape[0], k, h, m, 1 if canonical else 0, _ptr(out)))
     return out
+
+
+def bloom_kmers(kmers, k, h, m, canonical=True, device=0):
+    """Packed MSB-first Bloom filter bytes (uint8 [ceil(m/8)]) of n k-mers, built on the GPU
+    (bigsi/bloom/bloomfilter.py:16-32; .bloom file layout of bigsi/cmds/bloom.py:26-27)."""
+    arr = kmers if isinstance(kmers, np.ndarray) else kmers_to_array(list(kmers), k)
+    arr = np.ascontiguousarray(arr, dtype=np.uint8)
+    out = np.zeros((m + 7) // 8, dtype=np.uint8)
+    check(_lib.lib().bigsi_b200_bloom_kmers(device, _ptr(arr), arr.shape[0] if arr.ndim == 2 else 0, k, h, m,
+                                            1 if canonical else 0, _ptr(out)))
+    return out
+
+
+def file_info(path):
+    """(header dict, metadata bytes) of an index file written by DeviceIndex.save."""
+    hd = _lib.FileHeader()
+    L = _lib.lib()
+    check(L.bigsi_b200_file_info(os.fsencode(path), ctypes.byref(hd), None, 0))
+    meta = ctypes.create_string_buffer(max(int(hd.meta_bytes), 1))
+    check(L.bigsi_b200_file_info(os.fsencode(path), ctypes.byref(hd), meta, int(hd.meta_bytes)))
+    d = {name: getattr(hd, name) for name, _ in hd._fields_ if name != "magic"}
+    return d, meta.raw[: int(hd.meta_bytes)]
 
 
 class DeviceIndex:
@@ -110,6 +133,42 @@ class DeviceIndex:
         if bloom_packed.size * 8 < n_bits:
             raise ValueError("bloom filter shorter than n_bits")
         check(self._L.bigsi_b200_index_set_column(self.handle, col, _ptr(bloom_packed), n_bits))
+
+    def build_columns(self, col0, blooms, n_bits=None):
+        """BIGSI.build's transpose / bulk insert on the device: blooms = uint8 [n, >= ceil(n_bits/8)]
+        packed MSB-first Bloom filters -> local columns [col0, col0 + n)."""
+        blooms = np.ascontiguousarray(blooms, dtype=np.uint8)
+        if blooms.ndim != 2:
+            raise ValueError("blooms must be 2-D (n_filters, bytes)")
+        n_bits = self.num_rows if n_bits is None else int(n_bits)
+        if blooms.shape[1] * 8 < n_bits:
+            raise ValueError("bloom filters shorter than n_bits")
+        check(self._L.bigsi_b200_index_build_columns(self.handle, col0, blooms.shape[0], _ptr(blooms),
+                                                     blooms.strides[0] if blooms.shape[0] else 0, n_bits))
+
+    def build_columns_dev(self, col0, n_blooms, d_blooms, bloom_stride, n_bits, stream=0):
+        check(self._L.bigsi_b200_index_build_columns_dev(self.handle, col0, n_blooms, d_blooms, bloom_stride, n_bits, stream))
+
+    def save(self, path, meta=b""):
+        """Write the shard to a flat index file (include/bigsi_b200.h "persistence")."""
+        meta = bytes(meta)
+        check(self._L.bigsi_b200_index_save(self.handle, os.fsencode(path), meta, len(meta)))
+
+    def load_rows(self, path, file_offset, file_stride, src_byte_offset=0, row0=0, n_rows=None):
+        n_rows = self.num_rows - row0 if n_rows is None else n_rows
+        check(self._L.bigsi_b200_index_load_rows(self.handle, os.fsencode(path), file_offset, file_stride, src_byte_offset,
+                                                 row0, n_rows))
+
+    def sequence_presence(self, seq, k, h, cols):
+        """score=True support: uint8 [len(cols), len(seq)-k+1] of the characters '0'/'1' -- row c is the
+        reference's "kmer-presence" string of local column cols[c] (graph/bigsi.py:232-239)."""
+        arr = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.ascontiguousarray(seq, dtype=np.uint8)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        n = max(arr.size - k + 1, 0)
+        out = np.zeros((cols.size, n), dtype=np.uint8)
+        if n and cols.size:
+            check(self._L.bigsi_b200_sequence_presence(self.handle, _ptr(arr), arr.size, k, h, _ptr(cols), cols.size, _ptr(out)))
+        return out
 
     def fill_synthetic(self, seed=0, and_draws=1, planted_cols=(), planted_thr=()):
         pc = np.ascontiguousarray(planted_cols, dtype=np.uint64)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BIGSI_B200_ABI_VERSION 4
+#define BIGSI_B200_ABI_VERSION 5
 
 enum {
     BIGSI_B200_OK = 0,
@@ -199,6 +199,53 @@ int bigsi_b200_search_sequence(bigsi_b200_index *index, const char *seq, uint64_
 /* lookup(): per-k-mer AND vectors to host, out = uint8 [n][out_stride]. */
 int bigsi_b200_lookup_kmers(bigsi_b200_index *index, const char *kmers, uint64_t n, int k, int h,
                             uint8_t *out, uint64_t out_stride);
+
+/* ---- build path ------------------------------------------------
+ * BIGSI.bloom (graph/bigsi.py:150-155 -> bloom/bloomfilter.py:16-32): the m-bit Bloom filter of n
+ * k-mers (n*k raw ASCII bytes), hashed like bigsi_b200_hash_kmers and written as the reference's
+ * `bitarray.tobytes()` / .bloom file bytes (ceil(m/8) bytes, MSB first, cmds/bloom.py:26-27). */
+int bigsi_b200_bloom_kmers(int device, const char *kmers, uint64_t n, int k, int h, uint64_t m, int canonical,
+                           uint8_t *bloom_out);
+/* BIGSI.build's transpose and bulk insert (matrix/transpose.py:33-50 -> graph/index.py:27-40 ->
+ * matrix/bitmatrix.py:19-25,67-75) as one bit-transpose kernel: n_blooms Bloom filters of n_bits bits
+ * (MSB-first bytes, filter i at blooms + i*bloom_stride; rows >= n_bits get 0) become the LOCAL
+ * columns [col0, col0+n_blooms).  col0 <= num_cols; num_cols grows to col0+n_blooms (<= col_capacity);
+ * other columns keep their bits.  The _dev variant takes filters already in device memory (16-byte
+ * aligned, stride a multiple of 32 bytes and >= ceil(m/256)*32) and is stream-ordered. */
+int bigsi_b200_index_build_columns(bigsi_b200_index *index, uint64_t col0, uint64_t n_blooms, const uint8_t *blooms,
+                                   uint64_t bloom_stride, uint64_t n_bits);
+int bigsi_b200_index_build_columns_dev(bigsi_b200_index *index, uint64_t col0, uint64_t n_blooms, const uint8_t *d_blooms,
+                                       uint64_t bloom_stride, uint64_t n_bits, void *stream);
+
+/* ---- score=True support (graph/bigsi.py:232-239 with unpack_and_cat,
+ * graph/bigsi.py:47-56): for EVERY window of length k of seq (duplicates included, sequence order) and
+ * each of the n_cols LOCAL columns: out[c*n_windows + w] = '1' if the window's canonical k-mer is
+ * present in column cols[c] (AND of its h rows), else '0' -- row c of `out` is the reference's
+ * "kmer-presence" string of that hit.  n_windows = len-k+1; nothing is written when len < k. */
+int bigsi_b200_sequence_presence(bigsi_b200_index *index, const char *seq, uint64_t len, int k, int h,
+                                 const int32_t *cols, uint64_t n_cols, uint8_t *out);
+
+/* ---- persistence (replaces the durability of storage/*.py) ---------
+ * Flat file: this header, meta_bytes of caller-defined metadata (the Python layer stores JSON: k, h,
+ * the metadata:* keys of graph/metadata.py), zero padding up to rows_offset, then num_rows rows of
+ * row_bytes bytes each -- the concatenation of the reference's "<row>:bitarray" values
+ * (storage/base.py:86-94) in row order.  Little-endian. */
+typedef struct {
+    char magic[8];        /* "BIGSIB2\n" */
+    uint32_t version;     /* 1 */
+    uint32_t header_bytes;
+    uint64_t num_rows, num_cols, col_offset, row_bytes, meta_bytes, rows_offset;
+} bigsi_b200_file_header;
+/* HBM -> file through two pinned buffers (the copy of chunk i+1 overlaps the write of chunk i). */
+int bigsi_b200_index_save(bigsi_b200_index *index, const char *path, const void *meta, uint64_t meta_bytes);
+/* Header (+ up to meta_cap bytes of metadata) of an index file. */
+int bigsi_b200_file_info(const char *path, bigsi_b200_file_header *header_out, void *meta_out, uint64_t meta_cap);
+/* file -> HBM through two pinned buffers (the read of chunk i+1 overlaps the upload of chunk i): rows
+ * [row0, row0+n_rows) of the index are taken from file_offset + i*file_stride + src_byte_offset (a
+ * column shard loads its byte range of a full-width file: src_byte_offset = col_offset/8).  Works on
+ * any file of fixed-stride rows in the reference's byte layout, not only on bigsi_b200_index_save's. */
+int bigsi_b200_index_load_rows(bigsi_b200_index *index, const char *path, uint64_t file_offset, uint64_t file_stride,
+                               uint64_t src_byte_offset, uint64_t row0, uint64_t n_rows);
 
 /* ---- column-sharded search over several GPUs WITHOUT per-query collectives ------------------
  * The reference has no distributed path; sample columns are independent (graph/index.py:42-80,

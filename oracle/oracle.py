@@ -253,6 +253,44 @@ class OracleIndex:
         return format_results(hits, U, self.samples)
 
 
+    # -- graph/bigsi.py:232-239 (score=True): per-window presence of a column -----
+    def presence_strings(self, seq, cols):
+        """For every window of seq (sequence order, duplicates included) and every column in cols:
+        '1' if the window's k-mer is present in the column -- what the reference extracts with
+        unpack_and_cat (graph/bigsi.py:47-56) as X[:, colour]."""
+        kmers = list(seq_to_kmers(seq, self.k))
+        if not kmers:
+            return ["" for _ in cols]
+        uk = unique_kmers(kmers, self.k)
+        bits = np.unpackbits(self.lookup_packed(uk), axis=1)  # [U, 8*row_bytes]
+        pos = {km: i for i, km in enumerate(uk)}
+        order = np.array([pos[km] for km in kmers], dtype=np.int64)
+        return ["".join("1" if b else "0" for b in bits[order, c]) for c in cols]
+
+    # -- storage schema (storage/base.py:29-52,77-94; SURVEY.md appendix C) ------
+    def to_kv(self, metadata):
+        """The reference's v0.3 key/value store content for this index.  metadata: dict with
+        "colour_count", {sample name: colour} under "samples" and {colour: name} under "colours"."""
+        assert self.rows is not None
+        kv = {}
+
+        def put_int(key, v):
+            kv[(key + ":int").encode()] = str(int(v)).encode()
+
+        put_int("ksi:bloomfilter_size", self.m)
+        put_int("ksi:num_hashes", self.h)
+        put_int("number_of_rows", self.m)
+        put_int("number_of_cols", self.num_cols)
+        put_int("metadata:colour_count", metadata["colour_count"])
+        for name, colour in metadata["samples"].items():
+            put_int("metadata:%s" % name, colour)
+        for colour, name in metadata["colours"].items():
+            kv[("metadata:%d:string" % colour).encode()] = name.encode()
+        for r in range(self.m):
+            kv[b"%d:bitarray" % r] = self.rows[r].tobytes()
+        return kv
+
+
 # ---------------------------------------------------------------------------
 # row-id level entry points (used to check the device kernels without hashing)
 # ---------------------------------------------------------------------------

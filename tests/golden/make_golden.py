@@ -238,7 +238,118 @@ def golden_config1():
     dump("config1.json", out)
 
 
+# ---------------------------------------------------------------------------
+def _plain(o):
+    """numpy scalars -> Python scalars so that the JSON round trip compares equal."""
+    if isinstance(o, dict):
+        return {k: _plain(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_plain(v) for v in o]
+    if hasattr(o, "item") and not isinstance(o, (str, bytes)):
+        return o.item()
+    return o
+
+
+def golden_scores():
+    """score=True (graph/bigsi.py:232-239 -> scoring/score.py:96-116): the Scorer alone on random
+    presence strings, and whole searches with score=True (k = 31: the Scorer hard-wires it)."""
+    from bigsi.scoring import Scorer
+    from bigsi.storage import get_storage
+
+    rng = random.Random(9876)
+    scorer_cases = []
+    for db in (0, 1, 3, 70, 5 * 10 ** 5):
+        sc = Scorer(db)
+        for L in (1, 2, 3, 4, 5, 17, 34, 35, 36, 100, 257, 1200):
+            for p1 in (0.0, 0.3, 0.8, 0.97, 1.0):
+                # runs, not independent bits: presence strings are long stretches of 1 broken by gaps
+                s, cur = [], "1" if rng.random() < p1 else "0"
+                while len(s) < L:
+                    run = rng.randrange(1, 60)
+                    s.extend(cur * run)
+                    cur = "1" if rng.random() < p1 else "0"
+                s = "".join(s[:L])
+                scorer_cases.append({"db_size": db, "s": s, "result": _plain(sc.score(s))})
+    searches = []
+    for ci, (k, m, h, n, L) in enumerate([(31, 5003, 3, 12, 220), (31, 1000, 2, 40, 120)]):
+        cfg = dict_config("golden_score%d" % ci, k, m, h)
+        get_storage(cfg).delete_all()
+        base = rand_seq(rng, L)
+        seqs = [base] + [mutate(rng, base, rng.randrange(1, 5)) for _ in range(n - 1)]
+        samples = ["s%d" % i for i in range(n)]
+        blooms = [BIGSI.bloom(cfg, seq_to_kmers(sq, k)) for sq in seqs]
+        bigsi = BIGSI.build(cfg, blooms, samples)
+        queries = []
+        for thr in (1.0, 0.7, 0.3, 0.0):
+            for q in (base, seqs[3], mutate(rng, base, 4), base + base[:50]):
+                queries.append({"seq": q, "threshold": thr})
+        queries.append({"seq": base[:k], "threshold": 1.0})       # one window: IndexError in the reference
+        queries.append({"seq": base[: k + 1], "threshold": 1.0})  # two windows
+        queries.append({"seq": rand_seq(rng, 80), "threshold": 1.0})  # no hit: nothing to score
+        res = []
+        for q in queries:
+            entry = dict(q)
+            try:
+                entry["result"] = _plain(bigsi.search(q["seq"], q["threshold"], score=True))
+            except BaseException as e:
+                entry["raises"] = type(e).__name__
+            res.append(entry)
+        searches.append({"k": k, "m": m, "h": h, "samples": samples, "sample_seqs": seqs,
+                         "blooms_b64": [base64.b64encode(b.tobytes()).decode("ascii") for b in blooms],
+                         "queries": res})
+        bigsi.delete()
+    # the reference's own known-answer test (tests/scoring.py:10-31), read from its test file
+    import ast
+    import re
+
+    src = open(os.path.join(REFERENCE_ROOT, "bigsi", "tests", "scoring.py")).read()
+    kat_s = re.search(r's = "([01]+)"', src).group(1)
+    kat_expected = ast.literal_eval(re.search(r"scorer\.score\(s\) == (\{.*?\})", src, re.S).group(1))
+    kat = {"db_size": 5 * 10 ** 5, "s": kat_s, "expected_by_reference_test": kat_expected,
+           "result": _plain(Scorer(5 * 10 ** 5).score(kat_s))}
+    assert kat["result"] == kat_expected
+    dump("scores.json", {"reference_kat": kat, "scorer": scorer_cases, "searches": searches})
+
+
+def golden_kv_store():
+    """The reference's complete key/value store (v0.3 schema) after build + insert +
+    delete_sample: every key and value the reference wrote, for the import/export parity tests."""
+    from bigsi.storage import get_storage
+    from oracle.ref_harness import _DICT_STORES
+
+    rng = random.Random(2468)
+    out = []
+    for ci, (k, m, h, n, L, extra) in enumerate([(5, 300, 2, 5, 60, 4), (31, 1000, 3, 13, 150, 1), (7, 257, 3, 8, 50, 0)]):
+        cfg = dict_config("golden_kv%d" % ci, k, m, h)
+        get_storage(cfg).delete_all()
+        base = rand_seq(rng, L)
+        seqs = [mutate(rng, base, rng.randrange(0, 6)) for _ in range(n)]
+        samples = ["sample%d" % i for i in range(n)]
+        if ci == 0:
+            samples[2] = "0"  # a sample whose NAME is a colour number: int and string keys must not collide
+        blooms = [BIGSI.bloom(cfg, seq_to_kmers(sq, k)) for sq in seqs]
+        bigsi = BIGSI.build(cfg, blooms, samples)
+        ins = []
+        for j in range(extra):
+            sq = mutate(rng, base, 2)
+            bigsi.insert(BIGSI.bloom(cfg, seq_to_kmers(sq, k)), "ins%d" % j)
+            ins.append(sq)
+        if ci != 2:
+            bigsi.delete_sample(samples[1])
+        store = _DICT_STORES[cfg["storage-config"]["filename"]]
+        kv = [[base64.b64encode(bytes(key)).decode("ascii"), base64.b64encode(bytes(val)).decode("ascii")]
+              for key, val in sorted(store.items())]
+        queries = run_queries(bigsi, [{"seq": s_, "threshold": t} for s_ in (base, seqs[0], seqs[-1]) for t in (1.0, 0.6, 0.0)])
+        out.append({"k": k, "m": m, "h": h, "samples": samples, "sample_seqs": seqs, "inserted_seqs": ins,
+                    "deleted": samples[1] if ci != 2 else None, "kv_b64": kv, "queries": queries,
+                    "num_samples": bigsi.num_samples})
+        bigsi.delete()
+    dump("kv_store.json", out)
+
+
 if __name__ == "__main__":
     golden_hashes()
     golden_search()
     golden_config1()
+    golden_scores()
+    golden_kv_store()
