@@ -48,9 +48,12 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prewarm", type=int, default=300, help="untimed steps before the warm-up (clock ramp)")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
-                    help="N>1: query broadcast + hit all-gather inside the query kernel over NVLink peer memory (fused) or "
-                         "as two NCCL collectives per query (nccl)")
+    ap.add_argument("--exchange", default="pipelined", choices=["pipelined", "fused", "nccl"],
+                    help="N>1: query broadcast + hit all-gather inside the query kernel over NVLink peer memory, "
+                         "pipelined (the kernel of query s waits for the shards' hits of query s-1 only; default) or "
+                         "lock-step (fused), or as two NCCL collectives per query (nccl)")
+    ap.add_argument("--timeline", action="store_true",
+                    help="diagnostics: after the timed region print every rank's per-CTA kernel timeline (stderr)")
     return ap.parse_args()
 
 
@@ -211,8 +214,12 @@ def workload_config(args, n_gpus):
         "m": args.m, "h": H, "k": K, "cols_per_gpu": args.cols, "kmers_per_query": args.kmers,
         "distinct_queries": N_DISTINCT,
         "exchange": ("none (one shard)" if n_gpus == 1 else
-                     "in-kernel: query pushed to peers and hits all-gathered through NVLink peer memory, no collective call"
-                     if getattr(args, "exchange", "fused") == "fused" else "NCCL broadcast + all-gather per query"),
+                     "in-kernel, pipelined: query pushed to peers and hits all-gathered through NVLink peer memory by the query "
+                     "kernel, no collective call; the kernel of query s completes the all-gather of query s-1, the last "
+                     "query is drained inside the timed region"
+                     if getattr(args, "exchange", "pipelined") == "pipelined" else
+                     "in-kernel, lock-step: query pushed to peers and hits all-gathered through NVLink peer memory, no collective call"
+                     if getattr(args, "exchange", "pipelined") == "fused" else "NCCL broadcast + all-gather per query"),
         "l2_policy": "inputs larger than L2: each step gathers %.1f MB of distinct rows, %d distinct queries rotate"
                      % (args.kmers * H * math.ceil(args.cols / 8) / 1e6, N_DISTINCT),
         "matrix_density": 0.5,
@@ -248,7 +255,8 @@ def run_b200(args):
     index.fill_synthetic(0, 1, pc, pt)
     fill_s = time.perf_counter() - t0
     shard = DeviceShard(index, K, H, cap=HIT_CAP)
-    fused = world > 1 and args.exchange == "fused"
+    fused = world > 1 and args.exchange in ("fused", "pipelined")
+    piped = world > 1 and args.exchange == "pipelined"
     searcher = ShardedSearcher(shard, dist if world > 1 else None, world, rank, fused_max_kmers=U if fused else 0)
 
     queries = make_queries(N_DISTINCT, U)
@@ -266,11 +274,17 @@ def run_b200(args):
 
     def dev_step(i):
         if fused:  # one kernel per rank and step, no collective: rank 0's k-mers are pushed by its kernel
-            return searcher.search_one_fused(d_queries[i % N_DISTINCT] if rank == 0 else None, U, U)
+            return searcher.search_one_fused(d_queries[i % N_DISTINCT] if rank == 0 else None, U, U, pipelined=piped)
         return searcher.search_step(d_queries[i % N_DISTINCT], d_qoff, d_min, 1, U)
+
+    def dev_drain():
+        """Pipelined exchange: complete the all-gather of the last query (a no-op otherwise)."""
+        return searcher.drain_fused() if piped else None
 
     # ---- correctness gate on the first query (planted all-ones columns must be the exact hits)
     g = dev_step(0)
+    if piped:
+        g = dev_drain()
     torch.cuda.synchronize()
     n, hc, hv = unpack_hits(g.cpu().numpy(), 1, HIT_CAP)
     for r in range(world):
@@ -280,9 +294,11 @@ def run_b200(args):
     # ---- pre-warm (clocks), then W warm-up steps, then K timed steps: device-resident inputs
     for i in range(args.prewarm):
         dev_step(i)
+    dev_drain()
     barrier()
     for i in range(args.warmup):
         dev_step(i)
+    dev_drain()
     barrier()
     launches0 = index.info()["kernel_launches"]
     sampler = ClockSampler(local_rank)
@@ -291,6 +307,7 @@ def run_b200(args):
     ev0.record()
     for i in range(args.steps):
         dev_step(args.warmup + i)
+    dev_drain()  # every query's hits have arrived on this rank before the clock stops
     ev1.record()
     barrier()
     clocks = sampler.stop()
@@ -302,10 +319,39 @@ def run_b200(args):
     ms_max = float(t.item())
     value = world * U * args.steps / (ms_max * 1e-3)
 
+    if args.timeline:
+        import ctypes
+
+        from bigsi_b200 import _lib as _L
+        index.set_option("debug_flags", 2)
+        for i in range(50):
+            dev_step(i)
+        dev_drain()
+        barrier()
+        grid = index.info()["last_grid"]
+        buf = np.zeros(grid * 16, dtype=np.uint64)
+        # the drain kernel does not stamp: the buffer holds the last query kernel's stamps
+        _L.check(_L.lib().bigsi_b200_index_debug_read(index.handle, ctypes.c_void_p(buf.ctypes.data), buf.size))
+        ts = buf.reshape(grid, 16).astype(np.int64)
+        t0 = ts[:, 0].min()
+        names = ["entry", "prod_first_issue", "first_slot_landed", "last_slot_consumed", "flushed", "prod_last_issue",
+                 "past_grid_barrier", "merge_done", "past_pdl_wait", "hash_done", "merge_loaded", "merge_in_smem",
+                 "merge_expanded", "merge_stage_issue"]
+        lines = ["rank %d timeline (us since the first CTA entered; min / median / max over CTAs; last CTA separately)" % rank]
+        for j, nm in enumerate(names):
+            col = ts[:-1, j]
+            col = (col[col > 0] - t0) / 1e3
+            if col.size:
+                lines.append("  %-20s %7.2f %7.2f %7.2f   last CTA %7.2f" % (nm, col.min(), np.median(col), col.max(),
+                                                                            (ts[-1, j] - t0) / 1e3 if ts[-1, j] > 0 else -1))
+        sys.stderr.write("\n".join(lines) + "\n")
+        index.set_option("debug_flags", 0)
+
     # ---- roofline pass: same K steps with the fused kernel bracketed by CUDA events on its stream
     index.set_option("timing", 1)
     for i in range(args.steps):
         dev_step(args.warmup + i)
+    dev_drain()
     barrier()
     fused_ms, merge_ms, n_timed = index.timing_collect()
     index.set_option("timing", 0)
@@ -334,6 +380,20 @@ def run_b200(args):
         q = i % N_DISTINCT
         if world == 1:
             return index.search_kmers_hits(h_queries[q].numpy(), K, H, h_min, q_offsets=h_qoff, cap=HIT_CAP)[0]
+        if piped:
+            # pinned host k-mers -> H2D -> kernel of query i; its return value is the COMPLETE result of query i-1,
+            # copied to pinned host memory behind the kernel; the host then waits for the copy enqueued one step
+            # earlier, so the host->device->host legs of consecutive queries overlap (results arrive two steps late)
+            d_k = h_queries[q].to(dev, non_blocking=True) if rank == 0 else None
+            prev = searcher.search_one_fused(d_k, U, U, pipelined=True)
+            if rank != 0:
+                return None
+            slot = i % 3
+            if prev is not None:
+                e2e_host[slot].copy_(prev, non_blocking=True)
+            e2e_ev[slot].record()
+            e2e_ev[(i - 1) % 3].synchronize()
+            return e2e_host[(i - 1) % 3]
         if fused:
             d_k = h_queries[q].to(dev, non_blocking=True) if rank == 0 else None
             g = searcher.search_one_fused(d_k, U, U)
@@ -342,13 +402,23 @@ def run_b200(args):
             g = searcher.search_step(d_k, d_qoff, d_min, 1, U)
         return g.cpu() if rank == 0 else None
 
+    if piped:
+        e2e_host = [torch.empty((world, 2 + 2 * HIT_CAP), dtype=torch.int32).pin_memory() for _ in range(3)]
+        e2e_ev = [torch.cuda.Event() for _ in range(3)]
+        for ev in e2e_ev:
+            ev.record()
     for i in range(max(args.warmup, 3)):
         e2e_step(i)
+    dev_drain()
     barrier()
     e2e_steps = min(args.steps, 500)
     w0 = time.perf_counter()
     for i in range(e2e_steps):
         res = e2e_step(args.warmup + i)
+    if piped:  # the last query's hits: drain, then to the host
+        last = dev_drain()
+        if rank == 0:
+            res = last.cpu()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - w0  # host calls synchronise every step, so wall clock == device time + host overhead
     barrier()
@@ -386,7 +456,9 @@ def run_b200(args):
                     "steps": e2e_steps, "ms_per_step": 1e3 * float(te.item()) / e2e_steps,
                     "path": "bigsi_b200_search_kmers_hits (C ABI, pinned host buffers)" if world == 1 else
                             ("pinned host k-mers -> H2D on rank 0 -> ONE kernel per rank (k-mers pushed to the peers over NVLink in the prologue, "
-                             "hash, gather-AND-count, merge, threshold, hits published to every rank's result blocks) -> D2H" if fused else
+                             "hash, gather-AND-count, merge, threshold, hits published to every rank's result blocks) -> D2H"
+                             + ("; pipelined: query i's kernel completes the all-gather of query i-1, whose D2H the host awaits one step later" if piped else "")
+                             if fused else
                              "pinned host k-mers -> H2D -> hash -> NCCL broadcast -> fused query -> threshold -> NCCL all-gather -> D2H")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -109,6 +109,9 @@ SIGNATURES = {
     "bigsi_b200_exchange_open_local": (_int, [_vp, _vp]),
     "bigsi_b200_exchange_search_dev": (_int, [_vp, _vp, _u64, _int, _int, ctypes.c_uint32, _vp, c_void_pp,
                                               ctypes.POINTER(_u64)]),
+    "bigsi_b200_exchange_search_pipelined_dev": (_int, [_vp, _vp, _u64, _int, _int, ctypes.c_uint32, _vp, c_void_pp,
+                                                        ctypes.POINTER(_u64)]),
+    "bigsi_b200_exchange_drain_dev": (_int, [_vp, _vp, c_void_pp, ctypes.POINTER(_u64)]),
     "bigsi_b200_exchange_destroy": (_int, [_vp]),
 }
 

@@ -130,21 +130,27 @@ struct TimedLaunch {
 }  // namespace
 
 // Column-sharded search without per-query collectives: every rank owns one device block
-//   [inbox flags: kExFlags x u64][inbox k-mer bytes][result blocks: 2 parities x world x block]
+//   [inbox flags: kExFlags x u64][2 inboxes of k-mer bytes][2 low-latency inboxes][result blocks: 3 generations x world x block]
 // that its peers map (CUDA IPC across processes, plain peer access inside one process).  Rank 0's
 // kernel pushes the query into the peers' inboxes from its prologue; every rank's kernel publishes
-// its hit list into slot `rank` of every rank's result blocks and waits for the others' slots.
+// its hit list into slot `rank` of every rank's result blocks and waits for the others' slots --
+// those of the same query (lock-step) or, pipelined, those of the PREVIOUS query before it
+// publishes.  Query s uses inbox s % 2 and result generation s % 3: a shard overwrites generation
+// s % 3 only after it has seen every shard's publication of s-1, i.e. after every shard has launched
+// past its consumer of s-3; rank 0 overwrites inbox s % 2 only after every shard has published s-2.
 struct Exchange {
     int world = 0, rank = 0;
     uint32_t spec = 0;
-    uint64_t max_kmer_bytes = 0, kmers_off = 0, sinks_off = 0, block_bytes = 0, total_bytes = 0;
+    uint64_t max_kmer_bytes = 0, kmers_off = 0, kmers_stride = 0, ll_off = 0, sinks_off = 0, block_bytes = 0, total_bytes = 0;
     uint8_t *local = nullptr;
     uint8_t *peer[kMaxSinks] = {};
     bool ipc_opened[kMaxSinks] = {};
     bool ready = false;
-    uint64_t seq = 0;
+    uint64_t seq = 0;            // queries launched on this shard
+    uint64_t published_seq = 0;  // ... whose hit list this shard has sent to the others
 };
 constexpr uint64_t kExFlags = 1024;
+constexpr uint64_t kExInboxes = 2, kExGenerations = 3;
 
 struct bigsi_b200_index {
     int device = 0;
@@ -360,6 +366,14 @@ struct HitsOut {
     unsigned long long push_value = 0;
     uint32_t n_gather = 0;
     const unsigned long long *gather_blocks[kMaxSinks] = {};
+    bool gather_first = false;  // pipelined: no publication at the end; CTA 0 waits for the previous query's blocks
+    unsigned long long gather_seq = 0;
+    uint4 *ll_push[kMaxSinks] = {};  // solo path: the peers' low-latency inboxes / this shard's own
+    const uint4 *ll_in = nullptr;
+    uint32_t ll_flag = 0;
+    uint32_t n_pub = 0;         // deferred publication of the previous query's hit list from this kernel's prologue
+    unsigned long long pub_seq = 0;
+    unsigned long long *pub_sinks[kMaxSinks] = {};
 };
 
 // One query batch on `stream`.  Exactly one of d_rows / d_kmers is given; with k-mers the kernel
@@ -430,6 +444,15 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
         }
         p.n_gather = hits->n_gather;
         for (uint32_t i = 0; i < hits->n_gather; ++i) p.gather_blocks[i] = hits->gather_blocks[i];
+        p.gather_first = hits->gather_first ? 1u : 0u;
+        p.gather_seq = hits->gather_seq;
+        for (uint32_t i = 0; i < hits->n_push; ++i) p.ll_push[i] = hits->ll_push[i];
+        p.ll_in = hits->ll_in;
+        p.ll_flag = hits->ll_flag;
+        p.n_pub = hits->n_pub;
+        p.pub_seq = hits->pub_seq;
+        for (uint32_t i = 0; i < hits->n_pub; ++i) p.pub_sinks[i] = hits->pub_sinks[i];
+        p.sink_spec = hits->sink_spec;
         if (hits->published) *hits->published = false;
         if (hits->n_sinks && p.fuse_merge && grid > 0 && n_queries == 1) {
             p.n_sinks = hits->n_sinks;
@@ -1602,9 +1625,11 @@ int bigsi_b200_exchange_create(bigsi_b200_index *ix, int world, int rank, uint64
     ex.spec = spec;
     ex.max_kmer_bytes = max_kmer_bytes;
     ex.kmers_off = kExFlags * 8;
-    ex.sinks_off = ex.kmers_off + round_up(max_kmer_bytes + 64, 256);
+    ex.kmers_stride = round_up(max_kmer_bytes + 64, 256);
+    ex.ll_off = ex.kmers_off + kExInboxes * ex.kmers_stride;  // LL inboxes: every data byte takes two (hash.cuh:ll_store_line)
+    ex.sinks_off = ex.ll_off + kExInboxes * 2 * ex.kmers_stride;
     ex.block_bytes = round_up(16 + 8ull * spec, 128);
-    ex.total_bytes = ex.sinks_off + 2ull * world * ex.block_bytes;
+    ex.total_bytes = ex.sinks_off + kExGenerations * world * ex.block_bytes;
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ex.local), ex.total_bytes);
     if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(exchange)");
     CK(cudaMemset(ex.local, 0, ex.total_bytes));
@@ -1679,10 +1704,16 @@ int bigsi_b200_exchange_destroy(bigsi_b200_index *ix)
     return 0;
 }
 
-int bigsi_b200_exchange_search_dev(bigsi_b200_index *ix, const char *d_kmers, uint64_t n_kmers, int k, int h,
-                                   uint32_t min_kmers, void *stream, const void **d_blocks_out, uint64_t *block_bytes_out)
+// slot `rank` of generation seq % 3 in shard r's result blocks: where this shard's hits of query `seq` go
+static unsigned long long *exchange_slot(const Exchange &ex, int r, uint64_t seq)
 {
-    if (int rc = check_index(ix)) return rc;
+    return reinterpret_cast<unsigned long long *>(ex.peer[r] + ex.sinks_off +
+                                                  ((seq % kExGenerations) * ex.world + ex.rank) * ex.block_bytes);
+}
+
+static int exchange_search(bigsi_b200_index *ix, const char *d_kmers, uint64_t n_kmers, int k, int h, uint32_t min_kmers,
+                           cudaStream_t stream, bool pipelined)
+{
     Exchange &ex = ix->ex;
     if (!ex.local || !ex.ready) return fail(BIGSI_B200_ERR_INVALID, "exchange not created / peers not opened");
     if (k < 1 || h < 1 || n_kmers == 0) return fail(BIGSI_B200_ERR_INVALID, "k, h and the number of k-mers must be positive");
@@ -1690,11 +1721,10 @@ int bigsi_b200_exchange_search_dev(bigsi_b200_index *ix, const char *d_kmers, ui
     if (ex.rank == 0 && (!d_kmers || (reinterpret_cast<uintptr_t>(d_kmers) & 15)))
         return fail(BIGSI_B200_ERR_INVALID, "rank 0 needs the k-mers in a 16-byte aligned device buffer");
     if (ix->num_cols == 0) return fail(BIGSI_B200_ERR_INVALID, "empty shard");
-    DeviceGuard guard(ix->device);
     cudaError_t e;
     if ((e = ix->d_nhits.reserve(8 + 8ull * ex.spec + 16)) != cudaSuccess) return fail_cuda(e, "staging");
     const uint64_t seq = ex.seq + 1;
-    const uint64_t parity = seq & 1;
+    const uint64_t inbox = seq % kExInboxes;
     uint8_t *dev = static_cast<uint8_t *>(ix->d_nhits.p);
     HitsOut ho;
     ho.n = reinterpret_cast<unsigned long long *>(dev);
@@ -1706,18 +1736,30 @@ int bigsi_b200_exchange_search_dev(bigsi_b200_index *ix, const char *d_kmers, ui
     ho.require_fused = true;
     ho.sink_spec = ex.spec;
     ho.sink_seq = seq;
-    ho.n_sinks = (uint32_t)ex.world;
-    ho.n_gather = (uint32_t)ex.world;
+    ho.ll_flag = (uint32_t)seq ? (uint32_t)seq : 0x80000000u;  // an LL inbox is reused every second query: never 0, never the old value
+    // lock-step: publish at the end of the kernel, then wait for this query's blocks.  Pipelined: no publication at
+    // the end (the NEXT kernel's prologue, or the drain, sends this query's hits); wait for the previous query's blocks
+    ho.n_sinks = pipelined ? 0u : (uint32_t)ex.world;
+    ho.gather_first = pipelined;
+    ho.gather_seq = pipelined ? seq - 1 : seq;
+    ho.n_gather = pipelined && seq == 1 ? 0u : (uint32_t)ex.world;
+    const uint64_t ggen = ho.gather_seq % kExGenerations;
     for (int r = 0; r < ex.world; ++r) {
-        ho.sinks[r] = reinterpret_cast<unsigned long long *>(ex.peer[r] + ex.sinks_off + (parity * ex.world + ex.rank) * ex.block_bytes);
+        ho.sinks[r] = exchange_slot(ex, r, seq);
         ho.gather_blocks[r] =
-            reinterpret_cast<const unsigned long long *>(ex.local + ex.sinks_off + (parity * ex.world + r) * ex.block_bytes);
+            reinterpret_cast<const unsigned long long *>(ex.local + ex.sinks_off + (ggen * ex.world + r) * ex.block_bytes);
+    }
+    if (ex.published_seq < ex.seq) {  // the previous query was pipelined: this kernel's prologue publishes its hits
+        ho.n_pub = (uint32_t)ex.world;
+        ho.pub_seq = ex.seq;
+        for (int r = 0; r < ex.world; ++r) ho.pub_sinks[r] = exchange_slot(ex, r, ex.seq);
     }
     const char *kmers = d_kmers;
     if (ex.rank == 0) {
         for (int r = 1; r < ex.world; ++r) {
-            ho.push_kmers[ho.n_push] = ex.peer[r] + ex.kmers_off;
+            ho.push_kmers[ho.n_push] = ex.peer[r] + ex.kmers_off + inbox * ex.kmers_stride;
             ho.push_flags[ho.n_push] = reinterpret_cast<unsigned long long *>(ex.peer[r]);
+            ho.ll_push[ho.n_push] = reinterpret_cast<uint4 *>(ex.peer[r] + ex.ll_off + inbox * 2 * ex.kmers_stride);
             ++ho.n_push;
         }
         ho.push_value = seq;
@@ -1725,17 +1767,77 @@ int bigsi_b200_exchange_search_dev(bigsi_b200_index *ix, const char *d_kmers, ui
         ho.wait_flag = reinterpret_cast<const unsigned long long *>(ex.local);
         ho.wait_value = seq;
         ho.wait_per_cta = 1;
-        kmers = reinterpret_cast<const char *>(ex.local + ex.kmers_off);
+        kmers = reinterpret_cast<const char *>(ex.local + ex.kmers_off + inbox * ex.kmers_stride);
+        ho.ll_in = reinterpret_cast<const uint4 *>(ex.local + ex.ll_off + inbox * 2 * ex.kmers_stride);
     }
     bool published = false;
     ho.published = &published;
-    if (int rc = run_query(ix, BIGSI_B200_MODE_COUNTS, nullptr, kmers, k, nullptr, 1, n_kmers, n_kmers, h, nullptr, 0,
-                           static_cast<cudaStream_t>(stream), &ho))
+    if (int rc = run_query(ix, BIGSI_B200_MODE_COUNTS, nullptr, kmers, k, nullptr, 1, n_kmers, n_kmers, h, nullptr, 0, stream, &ho))
         return rc;
-    if (!published) return fail(BIGSI_B200_ERR_INVALID, "the launch could not publish its result");
+    if (!pipelined && !published) return fail(BIGSI_B200_ERR_INVALID, "the launch could not publish its result");
+    ex.published_seq = pipelined ? ex.seq : seq;  // everything up to the previous query (pipelined) / this one is out
     ex.seq = seq;
-    if (d_blocks_out) *d_blocks_out = ex.local + ex.sinks_off + parity * ex.world * ex.block_bytes;
+    return 0;
+}
+
+static const void *exchange_blocks(const Exchange &ex, uint64_t seq)
+{
+    return ex.local + ex.sinks_off + (seq % kExGenerations) * ex.world * ex.block_bytes;
+}
+
+int bigsi_b200_exchange_search_dev(bigsi_b200_index *ix, const char *d_kmers, uint64_t n_kmers, int k, int h,
+                                   uint32_t min_kmers, void *stream, const void **d_blocks_out, uint64_t *block_bytes_out)
+{
+    if (int rc = check_index(ix)) return rc;
+    DeviceGuard guard(ix->device);
+    if (int rc = exchange_search(ix, d_kmers, n_kmers, k, h, min_kmers, static_cast<cudaStream_t>(stream), false)) return rc;
+    if (d_blocks_out) *d_blocks_out = exchange_blocks(ix->ex, ix->ex.seq);
+    if (block_bytes_out) *block_bytes_out = ix->ex.block_bytes;
+    return 0;
+}
+
+int bigsi_b200_exchange_search_pipelined_dev(bigsi_b200_index *ix, const char *d_kmers, uint64_t n_kmers, int k, int h,
+                                             uint32_t min_kmers, void *stream, const void **d_prev_blocks_out,
+                                             uint64_t *block_bytes_out)
+{
+    if (int rc = check_index(ix)) return rc;
+    DeviceGuard guard(ix->device);
+    if (int rc = exchange_search(ix, d_kmers, n_kmers, k, h, min_kmers, static_cast<cudaStream_t>(stream), true)) return rc;
+    if (d_prev_blocks_out) *d_prev_blocks_out = ix->ex.seq >= 2 ? exchange_blocks(ix->ex, ix->ex.seq - 1) : nullptr;
+    if (block_bytes_out) *block_bytes_out = ix->ex.block_bytes;
+    return 0;
+}
+
+int bigsi_b200_exchange_drain_dev(bigsi_b200_index *ix, void *stream, const void **d_blocks_out, uint64_t *block_bytes_out)
+{
+    if (int rc = check_index(ix)) return rc;
+    Exchange &ex = ix->ex;
+    if (!ex.local || !ex.ready) return fail(BIGSI_B200_ERR_INVALID, "exchange not created / peers not opened");
+    if (d_blocks_out) *d_blocks_out = nullptr;
     if (block_bytes_out) *block_bytes_out = ex.block_bytes;
+    if (ex.seq == 0) return 0;
+    DeviceGuard guard(ix->device);
+    const uint8_t *base = static_cast<const uint8_t *>(exchange_blocks(ex, ex.seq));
+    QueryParams p;
+    memset(&p, 0, sizeof p);
+    uint8_t *dev = static_cast<uint8_t *>(ix->d_nhits.p);  // the hit buffers every exchange search of this handle uses
+    p.n_hits = reinterpret_cast<unsigned long long *>(dev);
+    p.hit_cols = reinterpret_cast<int32_t *>(dev + 8);
+    p.hit_counts = reinterpret_cast<uint32_t *>(dev + 8 + 4ull * ex.spec);
+    p.hit_cap = ex.spec;
+    p.sink_spec = ex.spec;
+    if (ex.published_seq < ex.seq) {
+        p.n_pub = (uint32_t)ex.world;
+        p.pub_seq = ex.seq;
+        for (int r = 0; r < ex.world; ++r) p.pub_sinks[r] = exchange_slot(ex, r, ex.seq);
+    }
+    p.n_gather = (uint32_t)ex.world;
+    p.gather_seq = ex.seq;
+    for (int r = 0; r < ex.world; ++r) p.gather_blocks[r] = reinterpret_cast<const unsigned long long *>(base + r * ex.block_bytes);
+    CK(launch_exchange_drain(p, static_cast<cudaStream_t>(stream)));
+    ex.published_seq = ex.seq;
+    ix->kernel_launches++;
+    if (d_blocks_out) *d_blocks_out = base;
     return 0;
 }
 

@@ -129,6 +129,24 @@ __device__ __forceinline__ void hash_one_kmer_regs(const uint8_t *s, int k, int 
     }
 }
 
+// "Low-latency" transfer of 16 data bytes between GPUs without a fence or a separate ready flag: two 16-byte
+// stores {d0, flag, d1, flag}, {d2, flag, d3, flag}; 8-byte halves are written atomically, so the receiver
+// re-reads a line until all four flags match the value it expects (the scheme of NCCL's LL protocol).
+__device__ __forceinline__ void ll_store_line(uint4 *dst, const uint4 &v, uint32_t flag)
+{
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(v.x), "r"(flag), "r"(v.y), "r"(flag) : "memory");
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 1), "r"(v.z), "r"(flag), "r"(v.w), "r"(flag) : "memory");
+}
+__device__ __forceinline__ uint4 ll_load_line(const uint4 *src, uint32_t flag)
+{
+    uint4 p, q;
+    do {
+        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(p.x), "=r"(p.y), "=r"(p.z), "=r"(p.w) : "l"(src) : "memory");
+        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(src + 1) : "memory");
+    } while (p.y != flag || p.w != flag || q.y != flag || q.w != flag);
+    return make_uint4(p.x, p.z, q.x, q.z);
+}
+
 // Synchronisation of a hashing group: the whole CTA (id 0), a subset of warps on a named barrier
 // (id > 0, nthreads a multiple of 32), or one warp (nthreads == 32).  A runtime choice on purpose: the
 // hashing code exists ONCE per kernel (it runs once per launch, so its cost is instruction fetch).
@@ -153,9 +171,16 @@ __device__ __forceinline__ GroupSync SyncWarp() { return GroupSync{0, 32}; }
 // words (zero padded, so the last word IS murmur's tail); (4) one thread per (k-mer, seed) runs
 // MurmurHash3 over those words and stores ids[km * h + seed].  `scratch` (16-byte aligned,
 // hash_scratch_bytes(cnt, k) bytes) and `ids` may be shared or global memory.  magic = mod_magic(m).
+//
+// ll_base != nullptr: the k-mer bytes are not read from g0 but from a "low-latency" inbox another GPU writes
+// over NVLink (see LlLine): 16-byte data line j of the k-mer array that starts at kmers_base (16-byte aligned)
+// lives in the line pair ll_base[2j], ll_base[2j+1]; every 8-byte half carries 4 data bytes and the 32-bit
+// flag of the query, so a line is simply re-read until all its flags equal ll_flag -- no separate ready
+// flag, no fence on the sender's side, and the wait is per 16-byte line.
 static __device__ __noinline__ void hash_kmers_group(const uint8_t *g0, uint32_t cnt, int k, int h, uint32_t m, int canonical,
                                              uint8_t *scratch, int32_t *ids, uint32_t tid, uint32_t nthreads,
-                                             const GroupSync sync, uint64_t magic)
+                                             const GroupSync sync, uint64_t magic, const uint4 *ll_base = nullptr,
+                                             const uint8_t *kmers_base = nullptr, uint32_t ll_flag = 0)
 {
     const int nblocks = k >> 2, rem = k & 3;
     const uint32_t wpk = (uint32_t)(k + 3) >> 2;
@@ -168,7 +193,12 @@ static __device__ __noinline__ void hash_kmers_group(const uint8_t *g0, uint32_t
     const uint4 *a0 = reinterpret_cast<const uint4 *>(g0 - skew);
     const uint32_t nvec = (skew + nbytes + 15) >> 4;
     uint4 *sv = reinterpret_cast<uint4 *>(scratch);
-    for (uint32_t i = tid; i < nvec; i += nthreads) sv[i] = __ldg(a0 + i);
+    if (ll_base == nullptr) {
+        for (uint32_t i = tid; i < nvec; i += nthreads) sv[i] = __ldg(a0 + i);
+    } else {
+        const uint4 *ll = ll_base + 2 * (size_t)((reinterpret_cast<const uint8_t *>(a0) - kmers_base) >> 4);
+        for (uint32_t i = tid; i < nvec; i += nthreads) sv[i] = ll_load_line(ll + 2 * (size_t)i, ll_flag);
+    }
     sync();
     const uint8_t *src = scratch + skew;
     if (k <= 32) {  // the common case (k = 31): one thread per k-mer, no further barriers

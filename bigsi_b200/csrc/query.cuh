@@ -101,6 +101,12 @@ struct QueryParams {
     uint8_t *push_kmers[kMaxSinks];            // peers' inbox k-mer bytes (same offsets as `kmers`)
     unsigned long long *push_flags[kMaxSinks]; // peers' per-CTA inbox flags
     unsigned long long push_value;
+    // solo path: the same broadcast without fences or flags ("low-latency" lines, hash.cuh:ll_store_line) --
+    // rank 0's consumer threads store their CTA's slice into every peer's LL inbox before they hash it; the
+    // peers' hashing reads its k-mer bytes from its own LL inbox and spins per 16-byte line on the embedded flag
+    uint4 *ll_push[kMaxSinks];   // peers' LL inboxes (line pair j <-> bytes [16j, 16j+16) of `kmers`)
+    const uint4 *ll_in;          // this shard's LL inbox when the query comes from a peer, else null
+    uint32_t ll_flag;            // low 32 bits of the query's sequence number (never 0)
     // result publication: after the merge phase the LAST CTA copies the hit list of query 0 to every
     // sink -- a block [0] = sequence flag, [1] = number of hits, then int32 cols[sink_spec], uint32
     // counts[sink_spec] -- in this GPU's, a peer GPU's (NVLink) or the host's (mapped pinned) memory
@@ -114,6 +120,16 @@ struct QueryParams {
     // peers publish into) carry sink_seq too, so that stream order implies "all shards have reported"
     uint32_t n_gather;
     const unsigned long long *gather_blocks[kMaxSinks];
+    // pipelined variant (gather_first): nothing is published at the end of the kernel.  The hit list of the
+    // PREVIOUS query (still in hit_cols / hit_counts / n_hits) is published from THIS kernel's prologue by its
+    // last CTA (pub_sinks, sequence pub_seq), where the NVLink latency overlaps the gather; the blocks waited
+    // for are those of the previous query (gather_seq), polled by CTA 0 behind the grid barrier while the
+    // other CTAs merge.  Kernel completion then implies "the previous query is complete on this shard".
+    uint32_t gather_first;
+    unsigned long long gather_seq;
+    uint32_t n_pub;
+    unsigned long long pub_seq;
+    unsigned long long *pub_sinks[kMaxSinks];
     uint32_t debug_flags;     // bit 0: consumers skip the AND/count work (pure-gather ceiling measurement)
     unsigned long long *debug_ts;  // optional [grid][kDebugStamps] timeline stamps (globaltimer ns), see fused_query
 };
@@ -168,6 +184,8 @@ inline uint64_t prehash_bytes_per_kmer(uint32_t k) { return (uint64_t)k + 1 + 4u
 // Stage 2: sum (or AND) the partial planes of every (query, column), expand to integers -> p.out.
 cudaError_t launch_merge(const QueryParams &p, int mode, cudaStream_t stream);
 cudaError_t query_kernels_init();  // opt-in to large dynamic shared memory
+// drain of the pipelined exchange (uses n_hits/hit_*/sink_spec, n_pub/pub_*, n_gather/gather_* of p)
+cudaError_t launch_exchange_drain(const QueryParams &p, cudaStream_t stream);
 cudaError_t merge_kernels_init();
 
 // ---- helper kernels (aux_kernels.cu) -------------------------------------------------------

@@ -402,7 +402,7 @@ __device__ __forceinline__ void solo_producer(const QueryParams &P, const SoloGe
 
     // the first ring-full of k-mers is hashed by this warp alone, so the gather starts at once
     hash_kmers_group(P.kmers + sg.begin * P.k, sg.n_first, (int)P.k, (int)h, P.num_rows, 1, scratch, ids, lane, 32u,
-                     SyncWarp(), P.mod_magic);
+                     SyncWarp(), P.mod_magic, P.ll_in, P.kmers, P.ll_flag);
     __syncwarp();
     if (lane == 0) BIGSI_TS(1);
     uint32_t k0 = 0;
@@ -481,11 +481,23 @@ __device__ __forceinline__ void solo_consumer(const QueryParams &P, const SoloGe
     const uint32_t tw = min(P.tile_bytes, P.row_bytes16);
     volatile uint32_t *stage_cnt = reinterpret_cast<volatile uint32_t *>(smem + kStageCntOffset);
 
+    if (P.n_push && sg.cnt) {
+        // query broadcast (rank 0 of a column-sharded search): this CTA's slice of the k-mer bytes (the 16-byte
+        // lines that cover it; neighbouring CTAs write identical lines at the boundaries) goes to every peer's LL
+        // inbox over NVLink -- plain stores with the flag embedded, nothing to wait for
+        const uint64_t b0 = sg.begin * P.k, b1 = (sg.begin + sg.cnt) * P.k;
+        const uint64_t l0 = b0 >> 4, nvec = ((b1 + 15) >> 4) - l0;
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.kmers) + l0;
+        for (uint64_t i = unit; i < nvec; i += consumer_threads) {
+            const uint4 v = __ldg(src + i);
+            for (uint32_t r = 0; r < P.n_push; ++r) ll_store_line(P.ll_push[r] + 2 * (l0 + i), v, P.ll_flag);
+        }
+    }
     // hash the part of the range the producer did not take, publish the pooled ids, release the producer
     const uint32_t rest = sg.cnt - sg.n_first;
     hash_kmers_group(P.kmers + (sg.begin + sg.n_first) * P.k, rest, (int)P.k, (int)P.h, P.num_rows, 1,
                      scratch + ((hash_scratch_bytes(sg.n_first, P.k) + 127) & ~127ull), ids + (size_t)sg.n_first * P.h, unit,
-                     consumer_threads, GroupSync{kBarHashGroup, (int)consumer_threads}, P.mod_magic);
+                     consumer_threads, GroupSync{kBarHashGroup, (int)consumer_threads}, P.mod_magic, P.ll_in, P.kmers, P.ll_flag);
     named_bar_sync(kBarHashGroup, consumer_threads);
     if (P.pool_share) {
         int32_t *dst = P.pool_ids + (size_t)blockIdx.x * P.pool_share * P.h;
@@ -560,6 +572,29 @@ __device__ __forceinline__ void solo_consumer(const QueryParams &P, const SoloGe
     if (unit == 0) BIGSI_TS(4);
 }
 
+// The hit list of query 0 (n_hits, hit_cols, hit_counts) -> every sink block: payload, system-scope fence, then
+// {sequence word, number of hits} as ONE 16-byte release store, so the block header is never seen torn.
+// Every thread of the CTA must call it.
+__device__ __forceinline__ void publish_hits(const QueryParams &P, unsigned long long *const *sinks, uint32_t n_sinks,
+                                             unsigned long long seq)
+{
+    const unsigned long long n = *reinterpret_cast<volatile unsigned long long *>(P.n_hits);
+    unsigned long long m = n < P.hit_cap ? n : P.hit_cap;
+    if (m > P.sink_spec) m = P.sink_spec;
+    for (uint32_t sidx = 0; sidx < n_sinks; ++sidx) {
+        int32_t *dc = reinterpret_cast<int32_t *>(sinks[sidx] + 2);
+        uint32_t *dv = reinterpret_cast<uint32_t *>(dc + P.sink_spec);
+        for (uint32_t i = threadIdx.x; i < (uint32_t)m; i += blockDim.x) {
+            dc[i] = __ldcg(P.hit_cols + i);
+            dv[i] = __ldcg(P.hit_counts + i);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < n_sinks)
+        asm volatile("st.release.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(sinks[threadIdx.x]), "l"(seq), "l"(n) : "memory");
+}
+
 // grid-wide barrier over a monotonic arrival counter (all CTAs of the launch are co-resident: the
 // kernel is launched cooperatively with at most one CTA per SM)
 __device__ __forceinline__ void grid_barrier(unsigned long long *counter, unsigned long long target)
@@ -605,9 +640,27 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
     grid_dependency_wait();
     if (threadIdx.x == 0) BIGSI_TS(8);
 
-    if (P.n_hits != nullptr)  // hit counters of the fused threshold (stage 2 adds to them)
+    if (P.n_pub) {
+        // pipelined exchange: the previous query's hit list is still in the hit buffers; the LAST CTA (whose
+        // k-mer range is the short remainder) sends it to every shard now, then clears the counter
+        if (blockIdx.x == gridDim.x - 1) {
+            publish_hits(P, P.pub_sinks, P.n_pub, P.pub_seq);
+            if (threadIdx.x == 0) P.n_hits[0] = 0ull;
+        }
+    } else if (P.n_hits != nullptr) {  // hit counters of the fused threshold (stage 2 adds to them)
         for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < P.n_queries; q += gridDim.x * blockDim.x)
             P.n_hits[q] = 0ull;
+    }
+    if (P.gather_first && blockIdx.x == gridDim.x - 1 && threadIdx.x < P.n_gather) {
+        // pipelined exchange: every shard has published the PREVIOUS query's hits (from the prologue of its own
+        // kernel of THIS query, unconditionally and BEFORE it waits here itself, so this cannot deadlock).  Polled
+        // by the last CTA, whose k-mer range is the short remainder; kernel completion then implies "the
+        // previous query is complete on this shard".
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(P.gather_blocks[threadIdx.x]) : "memory");
+        } while (seen != P.gather_seq);
+    }
 
     const uint64_t span = (uint64_t)P.slices_per_cta * P.items_per_slice;
     const uint64_t begin = (uint64_t)blockIdx.x * span;
@@ -618,7 +671,7 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
     // k-mers this CTA hashes itself (prehash geometry: one tile, one slice per CTA)
     const uint64_t kb = (uint64_t)blockIdx.x * P.items_per_slice;
     const uint32_t kcnt = (P.prehash && kb < P.total_kmers) ? (uint32_t)min((uint64_t)P.items_per_slice, P.total_kmers - kb) : 0u;
-    if (P.wait_flag != nullptr && (!P.wait_per_cta || kcnt)) {
+    if (P.wait_flag != nullptr && (!P.wait_per_cta || kcnt) && !(SOLO && P.ll_in != nullptr)) {
         // the query is published by another GPU / the host: wait for it (per CTA: for our own slice)
         if (threadIdx.x == 0) {
             const unsigned long long *flag = P.wait_flag + (P.wait_per_cta ? blockIdx.x : 0);
@@ -629,8 +682,8 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
         }
         __syncthreads();
     }
-    if (P.n_push && kcnt) {
-        // broadcast fused into the prologue: push our slice of the k-mer bytes (16-byte lines that cover it;
+    if (P.n_push && kcnt && !SOLO) {
+        // broadcast fused into the prologue (solo path: done by the producer warp, see solo_producer): push our slice of the k-mer bytes (16-byte lines that cover it;
         // neighbouring CTAs write identical bytes into shared boundary lines) to every peer, then raise flag b
         const uint64_t b0 = kb * P.k, b1 = (kb + kcnt) * P.k;
         const uint64_t a0 = b0 & ~15ull, nvec = (((b1 + 15) & ~15ull) - a0) >> 4;
@@ -693,30 +746,12 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
             __syncthreads();
             if (*s_last) {
                 __threadfence();
-                const unsigned long long n = *reinterpret_cast<volatile unsigned long long *>(P.n_hits);
-                unsigned long long m = n < P.hit_cap ? n : P.hit_cap;
-                if (m > P.sink_spec) m = P.sink_spec;
-                for (uint32_t sidx = 0; sidx < P.n_sinks; ++sidx) {
-                    int32_t *dc = reinterpret_cast<int32_t *>(P.sinks[sidx] + 2);
-                    uint32_t *dv = reinterpret_cast<uint32_t *>(dc + P.sink_spec);
-                    for (uint32_t i = threadIdx.x; i < (uint32_t)m; i += blockDim.x) {
-                        dc[i] = __ldcg(P.hit_cols + i);
-                        dv[i] = __ldcg(P.hit_counts + i);
-                    }
-                }
-                __threadfence_system();
-                __syncthreads();
-                if (threadIdx.x < P.n_sinks) {
-                    // {sequence word, number of hits} as ONE 16-byte store: the block header is never seen torn,
-                    // and the hit list was fenced above
-                    asm volatile("st.release.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(P.sinks[threadIdx.x]), "l"(P.sink_seq), "l"(n)
-                                 : "memory");
-                }
-                if (threadIdx.x < P.n_gather) {  // all-gather: every shard's block has arrived here
+                publish_hits(P, P.sinks, P.n_sinks, P.sink_seq);
+                if (!P.gather_first && threadIdx.x < P.n_gather) {  // all-gather: every shard's block has arrived here
                     unsigned long long seen;
                     do {
                         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(P.gather_blocks[threadIdx.x]) : "memory");
-                    } while (seen != P.sink_seq);
+                    } while (seen != P.gather_seq);
                 }
             }
         }
@@ -741,6 +776,25 @@ cudaError_t launch_query(const QueryParams &p, int mode, int grid, cudaStream_t 
     if (mode == kModeCounts)
         return p.h == 3 ? launch_one<kModeCounts, 3>(p, grid, stream) : launch_one<kModeCounts, 0>(p, grid, stream);
     return p.h == 3 ? launch_one<kModeAnd, 3>(p, grid, stream) : launch_one<kModeAnd, 0>(p, grid, stream);
+}
+
+// drain of the pipelined exchange: publishes the last query's hit list if no later kernel has done so, then
+// returns (in stream order) once every shard's block of that query has arrived (P.gather_blocks == P.gather_seq)
+__global__ void __launch_bounds__(256) exchange_drain_kernel(const __grid_constant__ QueryParams P)
+{
+    if (P.n_pub) publish_hits(P, P.pub_sinks, P.n_pub, P.pub_seq);
+    if (threadIdx.x < P.n_gather) {
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(P.gather_blocks[threadIdx.x]) : "memory");
+        } while (seen != P.gather_seq);
+    }
+}
+
+cudaError_t launch_exchange_drain(const QueryParams &p, cudaStream_t stream)
+{
+    exchange_drain_kernel<<<1, 256, 0, stream>>>(p);
+    return cudaGetLastError();
 }
 
 cudaError_t query_kernels_init()

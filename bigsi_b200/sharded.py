@@ -171,24 +171,39 @@ class FusedExchange:
         for e in exchanges:
             _lib.check(_lib.lib().bigsi_b200_exchange_open_local(e.shard.index.handle, arr))
 
-    def search(self, kmers_u8, n_kmers, min_kmers):
+    def _view(self, ptr, stride):
+        if not ptr:
+            return None
+        view = self._views.get(ptr)
+        if view is None:  # three generations of result blocks rotate: build each torch view once
+            t = self.shard.torch
+            blocks = t.as_tensor(_DevArray(ptr, (self.world, stride // 4), "<i4"), device=self.shard.device)
+            view = blocks[:, 2 : 4 + 2 * self.spec]  # drop the sequence word: [n (2 x int32) | cols | counts]
+            self._views[ptr] = view
+        return view
+
+    def search(self, kmers_u8, n_kmers, min_kmers, pipelined=False):
         """One query (rank 0's k-mers decide).  Returns int32 [world, 2 + 2*spec] (LOCAL colours), the
         packed layout of DeviceShard.hits for one query; a view of library memory that stays valid until
-        the next-but-one search."""
+        the next-but-one search.  pipelined=True: the kernel does not wait for the other shards' hits of
+        THIS query; the return value is the complete result of the PREVIOUS query (None after the first
+        call) and drain() completes the last one."""
         ct = self._ct
-        t = self.shard.torch
         ptr, stride = ct.c_void_p(0), ct.c_uint64(0)
         d_k = kmers_u8.data_ptr() if (self.rank == 0 and kmers_u8 is not None) else 0
-        self._lib.check(self._lib.lib().bigsi_b200_exchange_search_dev(
-            self.shard.index.handle, d_k, n_kmers, self.shard.k, self.shard.h, int(min_kmers), self.shard._stream(),
-            ct.byref(ptr), ct.byref(stride)))
-        view = self._views.get(ptr.value)
-        if view is None:  # two result buffers alternate: build each torch view once
-            words = stride.value // 4
-            blocks = t.as_tensor(_DevArray(ptr.value, (self.world, words), "<i4"), device=self.shard.device)
-            view = blocks[:, 2 : 4 + 2 * self.spec]  # drop the sequence word: [n (2 x int32) | cols | counts]
-            self._views[ptr.value] = view
-        return view
+        L = self._lib.lib()
+        fn = L.bigsi_b200_exchange_search_pipelined_dev if pipelined else L.bigsi_b200_exchange_search_dev
+        self._lib.check(fn(self.shard.index.handle, d_k, n_kmers, self.shard.k, self.shard.h, int(min_kmers),
+                           self.shard._stream(), ct.byref(ptr), ct.byref(stride)))
+        return self._view(ptr.value, stride.value)
+
+    def drain(self):
+        """Completes the last pipelined query: its result view, valid in stream order."""
+        ct = self._ct
+        ptr, stride = ct.c_void_p(0), ct.c_uint64(0)
+        self._lib.check(self._lib.lib().bigsi_b200_exchange_drain_dev(self.shard.index.handle, self.shard._stream(),
+                                                                       ct.byref(ptr), ct.byref(stride)))
+        return self._view(ptr.value, stride.value)
 
     def close(self):
         self._lib.lib().bigsi_b200_exchange_destroy(self.shard.index.handle)
@@ -221,10 +236,13 @@ class ShardedSearcher:
             self.fused = FusedExchange(shard, world_size, rank, fused_max_kmers, dist=dist)
             self.fused_max_kmers = fused_max_kmers
 
-    def search_one_fused(self, kmers_u8, n_kmers, min_kmers):
+    def search_one_fused(self, kmers_u8, n_kmers, min_kmers, pipelined=False):
         """Single query through the in-kernel exchange; min_kmers is a host integer.  Same result layout
-        as search_step for one query."""
-        return self.fused.search(kmers_u8, n_kmers, min_kmers)
+        as search_step for one query.  pipelined=True returns the PREVIOUS query's result (FusedExchange.search)."""
+        return self.fused.search(kmers_u8, n_kmers, min_kmers, pipelined)
+
+    def drain_fused(self):
+        return self.fused.drain()
 
     def search_step(self, kmers_u8, q_offsets, min_kmers, n_queries, max_query_kmers=0):
         """One batched search: rank 0's k-mers decide; returns the packed hit buffers of all ranks,

@@ -267,7 +267,7 @@ int bigsi_b200_index_load_rows(bigsi_b200_index *index, const char *path, uint64
  *         on other ranks).  *d_blocks_out = device pointer to `world` result blocks of
  *         *block_bytes_out bytes each, block r = { u64 seq; u64 n_hits; int32 cols[spec]; uint32
  *         counts[spec] } with LOCAL column ids of shard r; valid in stream order after the call and
- *         until the next-but-one search on this handle. */
+ *         until the next-but-one search on this handle (three generations of blocks rotate). */
 int bigsi_b200_exchange_create(bigsi_b200_index *index, int world, int rank, uint64_t max_kmer_bytes, uint32_t spec,
                                uint8_t *ipc_handle_out);
 int bigsi_b200_exchange_open(bigsi_b200_index *index, const uint8_t *ipc_handles);
@@ -275,6 +275,18 @@ int bigsi_b200_exchange_open_local(bigsi_b200_index *index, bigsi_b200_index *co
 int bigsi_b200_exchange_search_dev(bigsi_b200_index *index, const char *d_kmers, uint64_t n_kmers, int k, int h,
                                    uint32_t min_kmers, void *stream, const void **d_blocks_out,
                                    uint64_t *block_bytes_out);
+/* Pipelined variant: the kernel of query s waits for every shard's publication of query s-1 BEFORE it
+ * publishes its own hits and does not wait for query s at all, so consecutive queries overlap across
+ * the shards (a shard runs at the pace of its own kernel instead of kernel + two NVLink latencies).
+ * *d_prev_blocks_out = the complete result blocks of the PREVIOUS query (NULL after the first call),
+ * valid in stream order after this call and until the next-but-one call on this handle; consume them
+ * (e.g. copy them out on the same stream) before that.  bigsi_b200_exchange_drain_dev completes the
+ * LAST query: it returns its blocks once (in stream order) every shard has published them. */
+int bigsi_b200_exchange_search_pipelined_dev(bigsi_b200_index *index, const char *d_kmers, uint64_t n_kmers, int k,
+                                             int h, uint32_t min_kmers, void *stream, const void **d_prev_blocks_out,
+                                             uint64_t *block_bytes_out);
+int bigsi_b200_exchange_drain_dev(bigsi_b200_index *index, void *stream, const void **d_blocks_out,
+                                  uint64_t *block_bytes_out);
 int bigsi_b200_exchange_destroy(bigsi_b200_index *index);
 
 #ifdef __cplusplus
