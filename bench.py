@@ -379,7 +379,9 @@ def run_b200(args):
     def e2e_step(i):
         q = i % N_DISTINCT
         if world == 1:
-            return index.search_kmers_hits(h_queries[q].numpy(), K, H, h_min, q_offsets=h_qoff, cap=HIT_CAP)[0]
+            # the reference-facing call: BIGSI.search takes a SEQUENCE (graph/bigsi.py:174); its filter stage is one
+            # C-ABI call on host buffers (windows -> set of raw k-mers -> threshold -> hash -> gather-AND-count -> hits)
+            return index.search_sequence(h_seqs[q], K, H, 1.0, cap=HIT_CAP)
         if piped:
             # pinned host k-mers -> H2D -> kernel of query i; its return value is the COMPLETE result of query i-1,
             # copied to pinned host memory behind the kernel; the host then waits for the copy enqueued one step
@@ -402,6 +404,14 @@ def run_b200(args):
             g = searcher.search_step(d_k, d_qoff, d_min, 1, U)
         return g.cpu() if rank == 0 else None
 
+    if world == 1:
+        # 64 distinct random sequences of U + K - 1 bases: U windows, all distinct (checked), so one call = U lookups
+        h_seqs = []
+        for q in range(N_DISTINCT):
+            rng = np.random.default_rng(1000 + q)
+            h_seqs.append(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=U + K - 1)].tobytes())
+            c, v, nh, uq = index.search_sequence(h_seqs[q], K, H, 1.0, cap=HIT_CAP)
+            assert uq == U and sorted(c.tolist()) == [0, 1, cols - 1] and set(v.tolist()) == {U}, (q, uq, c[:8], v[:8])
     if piped:
         e2e_host = [torch.empty((world, 2 + 2 * HIT_CAP), dtype=torch.int32).pin_memory() for _ in range(3)]
         e2e_ev = [torch.cuda.Event() for _ in range(3)]
@@ -427,8 +437,18 @@ def run_b200(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * U * e2e_steps / float(te.item())
     n_hits = 3
-    h2d = U * K + 16 + 4
-    d2h = 8 + n_hits * 8 if world == 1 else world * (2 + 2 * HIT_CAP) * 4
+    h2d = (U + K - 1) if world == 1 else U * K + 16 + 4
+    d2h = 24 + n_hits * 8 if world == 1 else world * (2 + 2 * HIT_CAP) * 4
+    e2e_kmers = None
+    if world == 1:  # the same query handed over as U unique raw k-mers (31 bytes each) instead of the sequence
+        for i in range(3):
+            index.search_kmers_hits(h_queries[i].numpy(), K, H, h_min, q_offsets=h_qoff, cap=HIT_CAP)
+        w0 = time.perf_counter()
+        for i in range(e2e_steps):
+            index.search_kmers_hits(h_queries[(args.warmup + i) % N_DISTINCT].numpy(), K, H, h_min, q_offsets=h_qoff, cap=HIT_CAP)
+        dt = time.perf_counter() - w0
+        e2e_kmers = {"value": U * e2e_steps / dt, "ms_per_step": 1e3 * dt / e2e_steps, "h2d_bytes_per_step": U * K + 16 + 4,
+                     "path": "bigsi_b200_search_kmers_hits (C ABI, pinned host k-mers read zero-copy by the kernel)"}
 
     # ---- AND-mode (exact_filter) kernel, for context
     d_and = torch.empty((1, (cols + 7) // 8 + 16), dtype=torch.uint8, device=dev)
@@ -454,7 +474,8 @@ def run_b200(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": 1e3 * float(te.item()) / e2e_steps,
-                    "path": "bigsi_b200_search_kmers_hits (C ABI, pinned host buffers)" if world == 1 else
+                    "path": "bigsi_b200_search_sequence (C ABI, host sequence in, hit list out: front-end kernel + ONE query kernel, "
+                            "no host round trip in between)" if world == 1 else
                             ("pinned host k-mers -> H2D on rank 0 -> ONE kernel per rank (k-mers pushed to the peers over NVLink in the prologue, "
                              "hash, gather-AND-count, merge, threshold, hits published to every rank's result blocks) -> D2H"
                              + ("; pipelined: query i's kernel completes the all-gather of query i-1, whose D2H the host awaits one step later" if piped else "")
@@ -473,6 +494,8 @@ def run_b200(args):
                                                         "last_n_slices")},
             "index": {"matrix_bytes": info["matrix_bytes"], "row_pitch_bytes": info["row_pitch_bytes"], "fill_seconds": fill_s},
         }
+        if e2e_kmers is not None:
+            line["e2e_kmers_path"] = e2e_kmers
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))

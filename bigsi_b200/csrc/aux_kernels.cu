@@ -210,13 +210,28 @@ cudaError_t launch_set_column(uint8_t *matrix, uint64_t pitch, uint64_t num_rows
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dedup_windows_kernel(const uint8_t *__restrict__ seq, uint64_t n, int k,
                                                             unsigned long long *table, uint64_t mask,
-                                                            uint8_t *__restrict__ out_kmers, unsigned long long *counter)
+                                                            uint8_t *__restrict__ out_kmers, unsigned long long *counter,
+                                                            unsigned int *ticket, double threshold, uint32_t *min_out)
 {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // The block's span of the sequence (its 256 windows = 256 + k - 1 bytes) is staged in shared memory with one
+    // round trip of 16-byte loads: `seq` may be mapped pinned HOST memory (zero-copy over PCIe), where the k
+    // dependent byte loads per window below would each cost a bus round trip.  The aligned window reaches at
+    // most 15 bytes past either end of the sequence, inside the allocation's padding.
+    extern __shared__ __align__(16) uint8_t span[];
+    grid_dependency_wait();   // PDL: the previous query may still be reading out_kmers / the counter
+    grid_launch_dependents();
+    const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x;
+    const uint64_t i = i0 + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
+    const uint64_t span_bytes = min((uint64_t)blockDim.x, n - i0) + (uint64_t)k - 1;
+    const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(seq + i0) & 15);
+    const uint4 *a0 = reinterpret_cast<const uint4 *>(seq + i0 - skew);
+    for (uint32_t v = threadIdx.x; v < (uint32_t)((skew + span_bytes + 15) >> 4); v += blockDim.x)
+        reinterpret_cast<uint4 *>(span)[v] = ldg128_stream(a0 + v);
+    __syncthreads();
     bool first = false;
     if (i < n) {
-        const uint8_t *w = seq + i;
+        const uint8_t *w = span + skew + threadIdx.x;
         uint64_t fp = 0xcbf29ce484222325ull;  // FNV-1a over the bytes, then a 64-bit finaliser
         for (int j = 0; j < k; ++j) fp = (fp ^ w[j]) * 0x100000001b3ull;
         fp ^= fp >> 33;
@@ -254,21 +269,39 @@ __global__ void __launch_bounds__(256) dedup_windows_kernel(const uint8_t *__res
         base = __shfl_sync(0xffffffffu, base, 0);
         if (first) {
             uint8_t *dst = out_kmers + (base + __popc(ballot & ((1u << lane) - 1))) * (uint64_t)k;
-            for (int j = 0; j < k; ++j) dst[j] = seq[i + j];
+            const uint8_t *w = span + skew + threadIdx.x;
+            for (int j = 0; j < k; ++j) dst[j] = w[j];
+        }
+    }
+    if (min_out != nullptr) {
+        // the last block to finish knows U: min_kmers = math.ceil(U * threshold) in IEEE double (graph/bigsi.py:179)
+        __shared__ bool last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            last = atomicAdd(ticket, 1u) + 1u == gridDim.x;
+        }
+        __syncthreads();
+        if (last && threadIdx.x == 0) {
+            __threadfence();
+            const unsigned long long U = *reinterpret_cast<volatile unsigned long long *>(counter);
+            const double need = ceil(__dmul_rn((double)U, threshold));
+            *min_out = need <= 0.0 ? 0u : need >= 4294967295.0 ? 0xffffffffu : (uint32_t)need;
         }
     }
 }
 
 cudaError_t launch_dedup_windows(const uint8_t *d_seq, uint64_t n_windows, int k, unsigned long long *d_table,
                                  uint64_t table_entries, uint8_t *d_out_kmers, unsigned long long *d_counter,
-                                 cudaStream_t stream)
+                                 unsigned int *d_ticket, double threshold, uint32_t *d_min_out, cudaStream_t stream)
 {
     if (n_windows == 0) return cudaSuccess;
     const uint64_t blocks = (n_windows + 255) / 256;
     if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    dedup_windows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_seq, n_windows, k, d_table, table_entries - 1, d_out_kmers,
-                                                               d_counter);
-    return cudaGetLastError();
+    const size_t smem = 256 + (size_t)k - 1 + 32;
+    if (smem > 48 * 1024) return cudaErrorInvalidConfiguration;
+    return launch_pdl(dedup_windows_kernel, dim3((unsigned)blocks), dim3(256), smem, stream, d_seq, n_windows, k, d_table,
+                      table_entries - 1, d_out_kmers, d_counter, d_ticket, threshold, d_min_out);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -172,7 +172,8 @@ struct bigsi_b200_index {
     uint64_t sink_seq = 0;
     // scratch
     DevBuf debug_ts;
-    DevBuf d_seq, d_table;   // query front-end: sequence bytes, de-duplication table (+ counter)
+    DevBuf d_seq, d_table;   // query front-end: sequence bytes, de-duplication table (+ counter, ticket, threshold)
+    uint64_t table_clean_bytes = 0;  // leading bytes of d_table known to be zero
     DevBuf partial, d_kmers, d_rows, d_qoff, d_out, d_min, d_nhits, d_bloom, d_planted;
     PinnedBuf h_small;
     // timing
@@ -368,6 +369,11 @@ struct HitsOut {
     const unsigned long long *gather_blocks[kMaxSinks] = {};
     bool gather_first = false;  // pipelined: no publication at the end; CTA 0 waits for the previous query's blocks
     unsigned long long gather_seq = 0;
+    // the number of k-mers comes from a preceding kernel (query front-end): only the solo path can follow it;
+    // run_query returns 1 without launching anything when the plan is a different one
+    const unsigned long long *total_dev = nullptr;
+    unsigned long long *scrub = nullptr;  // words the kernel clears behind its grid barrier (front-end table)
+    uint64_t scrub_words = 0;
     uint4 *ll_push[kMaxSinks] = {};  // solo path: the peers' low-latency inboxes / this shard's own
     const uint4 *ll_in = nullptr;
     uint32_t ll_flag = 0;
@@ -429,6 +435,12 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
         if (hits->by_value) {
             p.min_by_value = 1;
             p.min_kmers_value = hits->min_value;
+        }
+        if (hits->total_dev) {
+            if (!(p.solo && p.fuse_merge && grid > 0 && hits->n_sinks)) return 1;
+            p.total_dev = hits->total_dev;
+            p.scrub = hits->scrub;
+            p.scrub_words = hits->scrub_words;
         }
         if (hits->require_fused && !(p.prehash && p.fuse_merge && grid > 0))
             return fail(BIGSI_B200_ERR_INVALID, "this query cannot run as one kernel (prehash=%u fuse_merge=%u grid=%d)", p.prehash,
@@ -1074,7 +1086,9 @@ int bigsi_b200_search_rows(bigsi_b200_index *ix, int mode, const int32_t *rows, 
 // mapped host block; the host polls that block's sequence word instead of synchronising the stream.
 // Returns 1 when the path does not apply (the caller falls back to the staged path).
 static int search_one_published(bigsi_b200_index *ix, const char *d_kmers, uint64_t total, int k, int h, uint32_t min_kmers,
-                                int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_out);
+                                int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_out,
+                                const unsigned long long *total_dev = nullptr, const uint32_t *d_min = nullptr,
+                                uint64_t *total_out = nullptr, unsigned long long *scrub = nullptr, uint64_t scrub_words = 0);
 
 static int search_one_zero_copy(bigsi_b200_index *ix, const char *kmers, const int64_t *qoff, int k, int h,
                                 uint32_t min_kmers, int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_out)
@@ -1101,8 +1115,13 @@ static int search_one_zero_copy(bigsi_b200_index *ix, const char *kmers, const i
 
 // One query whose unique raw k-mers are device-addressable: launch with the threshold by value, let the
 // kernel publish the hit list into the mapped host block and poll it.
+// total_dev / d_min (query front-end): the number of k-mers (<= total) and the threshold are device words a
+// preceding kernel in the stream writes; *total_out receives the number the kernel saw.  Returns 1 without
+// launching anything when the launch plan cannot follow a device-side count.
 static int search_one_published(bigsi_b200_index *ix, const char *d_kmers, uint64_t total, int k, int h, uint32_t min_kmers,
-                                int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_out)
+                                int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_out,
+                                const unsigned long long *total_dev, const uint32_t *d_min, uint64_t *total_out,
+                                unsigned long long *scrub, uint64_t scrub_words)
 {
     cudaError_t e;
     const uint64_t spec = cap < 1024 ? cap : 1024;  // hits the host block holds; longer lists are fetched afterwards
@@ -1118,17 +1137,26 @@ static int search_one_published(bigsi_b200_index *ix, const char *d_kmers, uint6
     ho.cols = reinterpret_cast<int32_t *>(dev + 8);
     ho.counts = reinterpret_cast<uint32_t *>(dev + 8 + cap * 4);
     ho.cap = cap;
-    ho.by_value = true;
-    ho.min_value = min_kmers;
+    if (d_min) {
+        ho.min_kmers = d_min;
+    } else {
+        ho.by_value = true;
+        ho.min_value = min_kmers;
+    }
+    ho.total_dev = total_dev;
+    ho.scrub = scrub;
+    ho.scrub_words = scrub_words;
     ho.n_sinks = 1;
     ho.sinks[0] = static_cast<unsigned long long *>(d_blk);
     ho.sink_spec = (uint32_t)spec;
-    ho.sink_seq = ++ix->sink_seq;
+    ho.sink_seq = ix->sink_seq + 1;
     ho.published = &published;
     if (int rc = run_query(ix, BIGSI_B200_MODE_COUNTS, nullptr, d_kmers, k, nullptr, 1, total, total, h, nullptr, 0, ix->stream,
                            &ho))
         return rc;
+    ++ix->sink_seq;
     uint64_t n = 0;
+    if (total_dev && !published) return fail(BIGSI_B200_ERR_CUDA, "internal: front-end launch without publication");
     if (published) {
         // poll the sequence word; look at the stream now and then so that a failed launch cannot hang us
         uint64_t spins = 0;
@@ -1142,6 +1170,7 @@ static int search_one_published(bigsi_b200_index *ix, const char *d_kmers, uint6
             }
         }
         n = blk[1];
+        if (total_out) *total_out = total_dev ? blk[2 + spec] : total;
         const uint64_t m = n < cap ? n : cap;
         const uint64_t ms = m < spec ? m : spec;
         const int32_t *hc = reinterpret_cast<const int32_t *>(const_cast<unsigned long long *>(blk) + 2);
@@ -1287,26 +1316,59 @@ int bigsi_b200_search_sequence(bigsi_b200_index *ix, const char *seq, uint64_t l
     cudaError_t e;
     uint64_t T = 1024;
     while (T < 2 * n) T <<= 1;
-    if ((e = ix->d_seq.reserve(len + 64)) != cudaSuccess) return fail_cuda(e, "sequence staging");
-    if ((e = ix->d_table.reserve(T * 8 + 64)) != cudaSuccess) return fail_cuda(e, "de-duplication table");
+    // [table: T x u64][U: u64][ticket: u32][min_kmers: u32]; the block is cleared behind every query, so it is
+    // clean on entry unless it has just been (re)allocated
+    const uint64_t tail = T * 8, clear_bytes = tail + 16;
+    const uint64_t old_cap = ix->d_table.cap;
+    if ((e = ix->h_kmers.reserve(len + 64)) != cudaSuccess) return fail_cuda(e, "pinned sequence staging");
+    if ((e = ix->d_table.reserve(clear_bytes + 64)) != cudaSuccess) return fail_cuda(e, "de-duplication table");
     if ((e = ix->d_kmers.reserve(n * (uint64_t)k + 64)) != cudaSuccess) return fail_cuda(e, "k-mer staging");
     if ((e = ix->h_small.reserve(64)) != cudaSuccess) return fail_cuda(e, "pinned staging");
-    unsigned long long *d_counter = reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(ix->d_table.p) + T * 8);
-    CK(cudaMemcpyAsync(ix->d_seq.p, seq, len, cudaMemcpyHostToDevice, ix->stream));
-    CK(cudaMemsetAsync(ix->d_table.p, 0, T * 8 + 8, ix->stream));
-    CK(launch_dedup_windows(static_cast<const uint8_t *>(ix->d_seq.p), n, k, static_cast<unsigned long long *>(ix->d_table.p), T,
-                            static_cast<uint8_t *>(ix->d_kmers.p), d_counter, ix->stream));
+    if (ix->d_table.cap != old_cap || ix->table_clean_bytes < clear_bytes) {
+        CK(cudaMemsetAsync(ix->d_table.p, 0, ix->d_table.cap, ix->stream));
+        ix->table_clean_bytes = ix->d_table.cap;
+    }
+    uint8_t *tb = static_cast<uint8_t *>(ix->d_table.p);
+    unsigned long long *d_counter = reinterpret_cast<unsigned long long *>(tb + tail);
+    unsigned int *d_ticket = reinterpret_cast<unsigned int *>(tb + tail + 8);
+    uint32_t *d_min = reinterpret_cast<uint32_t *>(tb + tail + 12);
+    // the sequence stays in (mapped, pinned) host memory: the front-end kernel stages its spans itself
+    memcpy(ix->h_kmers.p, seq, len);
+    void *d_seq = nullptr;
+    CK(cudaHostGetDevicePointer(&d_seq, ix->h_kmers.p, 0));
+    CK(launch_dedup_windows(static_cast<const uint8_t *>(d_seq), n, k, static_cast<unsigned long long *>(ix->d_table.p), T,
+                            static_cast<uint8_t *>(ix->d_kmers.p), d_counter, d_ticket, threshold, d_min, ix->stream));
     ix->kernel_launches++;
-    CK(cudaMemcpyAsync(ix->h_small.p, d_counter, 8, cudaMemcpyDeviceToHost, ix->stream));
-    CK(cudaStreamSynchronize(ix->stream));
-    const uint64_t U = *static_cast<const unsigned long long *>(ix->h_small.p);
+    ix->table_clean_bytes = 0;
+    int rc = 1;
+    uint64_t U = 0;
+    bool scrubbed = false;
+    if (ix->num_cols && ix->opt_zero_copy != 0) {
+        // no host round trip: the search kernel reads U and min_kmers = ceil(U * threshold) from the device; it also
+        // clears the table (T words) and the count / ticket / threshold words behind it for the next query
+        rc = search_one_published(ix, static_cast<const char *>(ix->d_kmers.p), n, k, h, 0, cols_out, counts_out, cap, n_hits_out,
+                                  d_counter, d_min, &U, static_cast<unsigned long long *>(ix->d_table.p), T);
+        scrubbed = rc == 0;
+    }
+    if (rc == 1) {  // the plan cannot follow a device-side count (or the shard is empty): fetch U, then search
+        CK(cudaMemcpyAsync(ix->h_small.p, d_counter, 8, cudaMemcpyDeviceToHost, ix->stream));
+        CK(cudaStreamSynchronize(ix->stream));
+        U = *static_cast<const unsigned long long *>(ix->h_small.p);
+        rc = 0;
+        if (ix->num_cols) {
+            // min_kmers = math.ceil(U * threshold) in IEEE double (graph/bigsi.py:179); <= 0 keeps every sample
+            const double need = ceil((double)U * threshold);
+            const uint32_t min_kmers = need <= 0.0 ? 0u : need >= 4294967295.0 ? 0xffffffffu : (uint32_t)need;
+            rc = search_one_published(ix, static_cast<const char *>(ix->d_kmers.p), U, k, h, min_kmers, cols_out, counts_out, cap,
+                                      n_hits_out);
+        }
+    }
+    if (rc) return rc;
     *num_kmers_out = U;
-    if (ix->num_cols == 0) return 0;
-    // min_kmers = math.ceil(U * threshold) in IEEE double (graph/bigsi.py:179); <= 0 keeps every sample
-    const double need = ceil((double)U * threshold);
-    const uint32_t min_kmers = need <= 0.0 ? 0u : need >= 4294967295.0 ? 0xffffffffu : (uint32_t)need;
-    return search_one_published(ix, static_cast<const char *>(ix->d_kmers.p), U, k, h, min_kmers, cols_out, counts_out, cap,
-                                n_hits_out);
+    // clear the table for the next query now, off its critical path (the fast path's kernel has done it itself)
+    if (!scrubbed) CK(cudaMemsetAsync(ix->d_table.p, 0, clear_bytes, ix->stream));
+    ix->table_clean_bytes = clear_bytes;
+    return 0;
 }
 
 // ============================================================================================

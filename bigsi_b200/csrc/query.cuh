@@ -71,6 +71,13 @@ struct QueryParams {
     // rest; the last pool_share k-mers of every CTA's range go to a shared POOL that the CTAs drain
     // dynamically (atomic claims), so fast CTAs take over work of slow ones (tail balance)
     uint32_t solo;
+    // the query front-end (dedup_windows_kernel) determines the number of unique k-mers on the device: the
+    // kernel then reads it here (total_kmers is the upper bound the launch was planned for) and reports it in
+    // word 2 + sink_spec of every sink block
+    const unsigned long long *total_dev;
+    unsigned long long *scrub;   // [scrub_words] cleared behind the grid barrier (the front-end's table), or null; the two
+                                 // words behind it ({U}, {ticket, threshold}) are cleared by the last CTA after publishing
+    uint64_t scrub_words;
     uint32_t pool_share;      // k-mers per CTA that go to the pool (0 = static split only)
     uint32_t solo_max_kmers;  // most k-mers one CTA may count (2^planes_per_slot - 1)
     int32_t *pool_ids;        // [grid][pool_share][h] row ids of the pooled k-mers, written by their owner CTA
@@ -199,9 +206,11 @@ cudaError_t launch_threshold(const uint32_t *d_counts, uint64_t counts_stride, u
                              cudaStream_t stream);
 // query front-end: unique raw k-mers of a sequence (table_entries: a power of two >= 2 * n_windows, zeroed;
 // *d_counter zeroed, receives U)
+// d_ticket (zeroed) / d_min_out: the last block to finish stores min_kmers = ceil(U * threshold) (IEEE double,
+// graph/bigsi.py:179; <= 0 -> 0) to *d_min_out, so that the search kernel can follow without a host round trip
 cudaError_t launch_dedup_windows(const uint8_t *d_seq, uint64_t n_windows, int k, unsigned long long *d_table,
                                  uint64_t table_entries, uint8_t *d_out_kmers, unsigned long long *d_counter,
-                                 cudaStream_t stream);
+                                 unsigned int *d_ticket, double threshold, uint32_t *d_min_out, cudaStream_t stream);
 cudaError_t launch_set_column(uint8_t *matrix, uint64_t pitch, uint64_t num_rows, uint64_t col,
                               const uint8_t *d_bloom, uint64_t n_bits, cudaStream_t stream);
 cudaError_t launch_fill_synthetic(uint8_t *matrix, uint64_t pitch, uint64_t num_rows, uint64_t num_cols,

@@ -350,17 +350,21 @@ struct SoloGeom {
     uint32_t n_static;  // the first n_static are gathered by this CTA itself
     uint32_t n_pool;    // the last n_pool go to the shared pool
     uint32_t n_first;   // static k-mers the producer warp hashes itself (one ring-full)
+    uint64_t total;     // k-mers of the query: P.total_kmers, or *P.total_dev when a preceding kernel determines it
 };
-__device__ __forceinline__ uint32_t solo_range_cnt(const QueryParams &P, uint32_t cta)
+__device__ __forceinline__ uint32_t solo_range_cnt(const QueryParams &P, uint32_t cta, uint64_t total)
 {
     const uint64_t b = (uint64_t)cta * P.items_per_slice;
-    return b >= P.total_kmers ? 0u : (uint32_t)min((uint64_t)P.items_per_slice, P.total_kmers - b);
+    return b >= total ? 0u : (uint32_t)min((uint64_t)P.items_per_slice, total - b);
 }
 __device__ __forceinline__ SoloGeom solo_geometry(const QueryParams &P)
 {
     SoloGeom g;
+    // the geometry was planned for P.total_kmers (an upper bound when total_dev is set): fewer k-mers only
+    // leave the ranges of the last CTAs short or empty
+    g.total = P.total_dev ? min((uint64_t)__ldcg(P.total_dev), P.total_kmers) : P.total_kmers;
     g.begin = (uint64_t)blockIdx.x * P.items_per_slice;
-    g.cnt = solo_range_cnt(P, blockIdx.x);
+    g.cnt = solo_range_cnt(P, blockIdx.x, g.total);
     g.n_pool = min(P.pool_share, g.cnt);
     g.n_static = g.cnt - g.n_pool;
     g.n_first = min(g.n_static, P.n_stages * P.kmers_per_stage);
@@ -437,7 +441,7 @@ __device__ __forceinline__ void solo_producer(const QueryParams &P, const SoloGe
         if (lane < n && idx < pool_total) {
             owner = idx % gridDim.x;
             j = idx / gridDim.x;
-            real = j < min(P.pool_share, solo_range_cnt(P, owner));  // short ranges pool fewer k-mers
+            real = j < min(P.pool_share, solo_range_cnt(P, owner, sg.total));  // short ranges pool fewer k-mers
         }
         if (base + n >= pool_total) exhausted = true;
         if (real)
@@ -589,10 +593,16 @@ __device__ __forceinline__ void publish_hits(const QueryParams &P, unsigned long
             dv[i] = __ldcg(P.hit_counts + i);
         }
     }
-    __threadfence_system();
+    if (P.total_dev && threadIdx.x < n_sinks)  // the query's k-mer count was determined on the device: report it
+        sinks[threadIdx.x][2 + P.sink_spec] = __ldcg(P.total_dev);
+    // ONE system-scope fence per sink on the critical path: the CTA barrier orders every thread's payload
+    // stores before the publishing thread's fence (fences are cumulative -- the same pattern grid-wide barriers
+    // rely on), and the header store behind the fence can then be a plain one
     __syncthreads();
-    if (threadIdx.x < n_sinks)
-        asm volatile("st.release.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(sinks[threadIdx.x]), "l"(seq), "l"(n) : "memory");
+    if (threadIdx.x < n_sinks) {
+        __threadfence_system();
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(sinks[threadIdx.x]), "l"(seq), "l"(n) : "memory");
+    }
 }
 
 // grid-wide barrier over a monotonic arrival counter (all CTAs of the launch are co-resident: the
@@ -729,6 +739,12 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
         grid_barrier(P.barrier, P.barrier_target);
         if (threadIdx.x == 0) BIGSI_TS(6);
         if (SOLO && blockIdx.x == 0 && threadIdx.x == 0) *P.pool_counter = 0u;  // every claim of this launch is done
+        if (P.scrub_words) {
+            // query front-end: its de-duplication table is dead once every CTA has read its k-mers; clear it for the
+            // next query here, where the stores overlap the merge (saves a memset node per query)
+            for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.scrub_words; i += (uint64_t)gridDim.x * blockDim.x)
+                P.scrub[i] = 0ull;
+        }
         uint32_t merge_phase = 0;
         for (uint64_t item = blockIdx.x; item < P.merge_items; item += gridDim.x)
             merge_item<MODE>(P, item, ring, merge_bar, merge_phase);
@@ -747,6 +763,9 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
             if (*s_last) {
                 __threadfence();
                 publish_hits(P, P.sinks, P.n_sinks, P.sink_seq);
+                // front-end words behind its table ({U}, {ticket, threshold}): every reader is done -- this CTA is
+                // the last one of the launch -- so they are re-armed here for the next query
+                if (P.scrub_words && threadIdx.x < 2) P.scrub[P.scrub_words + threadIdx.x] = 0ull;
                 if (!P.gather_first && threadIdx.x < P.n_gather) {  // all-gather: every shard's block has arrived here
                     unsigned long long seen;
                     do {

@@ -58,3 +58,23 @@ print("kernel (events) in the zero-copy path %.1f us" % (1e3 * fm / nn))
 seq = bytes(acgt[rng.integers(0, 4, size=U + K - 1)])
 seqs = [bytes(acgt[rng.integers(0, 4, size=U + K - 1)]) for _ in range(16)]
 print("search_sequence (wrapper, 10 030-base sequence, threshold 1.0)  %.1f us" % timeit(lambda i: ix.search_sequence(seqs[i % 16], K, H, 1.0, cap=CAP)))
+nh = np.zeros(1, dtype=np.uint64)
+nu = np.zeros(1, dtype=np.uint64)
+g = L.bigsi_b200_search_sequence
+sargs = [(ix.handle, s, len(s), K, H, ctypes.c_double(1.0), cols.ctypes.data, cnts.ctypes.data, CAP, nh.ctypes.data, nu.ctypes.data)
+         for s in seqs]
+print("search_sequence (bare ctypes)  %.1f us" % timeit(lambda i: g(*sargs[i % 16])))
+assert nh[0] == 3 and nu[0] == U, (nh, nu)
+for i in range(200):
+    g(*sargs[i % 16])
+fm, mm, nn = ix.timing_collect()
+print("query kernel (events) in the sequence path %.1f us" % (1e3 * fm / nn))
+ix.set_option("timing", 0)
+ix.set_option("zero_copy", 0)
+print("search_sequence (bare ctypes, host round trip for U)  %.1f us" % timeit(lambda i: g(*sargs[i % 16])))
+ix.set_option("zero_copy", 1)
+# host-side cost of the call alone: an empty-ish query (k-mer count 1) through the same entry point
+tiny = [bytes(acgt[rng.integers(0, 4, size=K)]) for _ in range(16)]
+targs = [(ix.handle, s, len(s), K, H, ctypes.c_double(1.0), cols.ctypes.data, cnts.ctypes.data, CAP, nh.ctypes.data, nu.ctypes.data)
+         for s in tiny]
+print("search_sequence (bare ctypes, ONE k-mer: launch + front-end + kernel fixed costs)  %.1f us" % timeit(lambda i: g(*targs[i % 16])))
