@@ -374,9 +374,7 @@ struct HitsOut {
     const unsigned long long *total_dev = nullptr;
     unsigned long long *scrub = nullptr;  // words the kernel clears behind its grid barrier (front-end table)
     uint64_t scrub_words = 0;
-    uint4 *ll_push[kMaxSinks] = {};  // solo path: the peers' low-latency inboxes / this shard's own
-    const uint4 *ll_in = nullptr;
-    uint32_t ll_flag = 0;
+    LlRoute ll = {};  // solo path: the k-mer bytes travel through the shards' low-latency inboxes
     uint32_t n_pub = 0;         // deferred publication of the previous query's hit list from this kernel's prologue
     unsigned long long pub_seq = 0;
     unsigned long long *pub_sinks[kMaxSinks] = {};
@@ -458,9 +456,8 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
         for (uint32_t i = 0; i < hits->n_gather; ++i) p.gather_blocks[i] = hits->gather_blocks[i];
         p.gather_first = hits->gather_first ? 1u : 0u;
         p.gather_seq = hits->gather_seq;
-        for (uint32_t i = 0; i < hits->n_push; ++i) p.ll_push[i] = hits->ll_push[i];
-        p.ll_in = hits->ll_in;
-        p.ll_flag = hits->ll_flag;
+        p.ll = hits->ll;
+        p.ll.kmers_base = reinterpret_cast<const uint8_t *>(d_kmers);
         p.n_pub = hits->n_pub;
         p.pub_seq = hits->pub_seq;
         for (uint32_t i = 0; i < hits->n_pub; ++i) p.pub_sinks[i] = hits->pub_sinks[i];
@@ -1798,7 +1795,8 @@ static int exchange_search(bigsi_b200_index *ix, const char *d_kmers, uint64_t n
     ho.require_fused = true;
     ho.sink_spec = ex.spec;
     ho.sink_seq = seq;
-    ho.ll_flag = (uint32_t)seq ? (uint32_t)seq : 0x80000000u;  // an LL inbox is reused every second query: never 0, never the old value
+    ho.ll.flag = (uint32_t)seq ? (uint32_t)seq : 0x80000000u;  // an LL inbox is reused every second query: never 0, never the old value
+    auto ll_inbox = [&](int r) { return reinterpret_cast<uint4 *>(ex.peer[r] + ex.ll_off + inbox * 2 * ex.kmers_stride); };
     // lock-step: publish at the end of the kernel, then wait for this query's blocks.  Pipelined: no publication at
     // the end (the NEXT kernel's prologue, or the drain, sends this query's hits); wait for the previous query's blocks
     ho.n_sinks = pipelined ? 0u : (uint32_t)ex.world;
@@ -1821,7 +1819,7 @@ static int exchange_search(bigsi_b200_index *ix, const char *d_kmers, uint64_t n
         for (int r = 1; r < ex.world; ++r) {
             ho.push_kmers[ho.n_push] = ex.peer[r] + ex.kmers_off + inbox * ex.kmers_stride;
             ho.push_flags[ho.n_push] = reinterpret_cast<unsigned long long *>(ex.peer[r]);
-            ho.ll_push[ho.n_push] = reinterpret_cast<uint4 *>(ex.peer[r] + ex.ll_off + inbox * 2 * ex.kmers_stride);
+            ho.ll.out[ho.n_push] = ll_inbox(r);
             ++ho.n_push;
         }
         ho.push_value = seq;
@@ -1830,7 +1828,7 @@ static int exchange_search(bigsi_b200_index *ix, const char *d_kmers, uint64_t n
         ho.wait_value = seq;
         ho.wait_per_cta = 1;
         kmers = reinterpret_cast<const char *>(ex.local + ex.kmers_off + inbox * ex.kmers_stride);
-        ho.ll_in = reinterpret_cast<const uint4 *>(ex.local + ex.ll_off + inbox * 2 * ex.kmers_stride);
+        ho.ll.in = ll_inbox(ex.rank);
     }
     bool published = false;
     ho.published = &published;

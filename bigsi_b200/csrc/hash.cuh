@@ -147,6 +147,18 @@ __device__ __forceinline__ uint4 ll_load_line(const uint4 *src, uint32_t flag)
     return make_uint4(p.x, p.z, q.x, q.z);
 }
 
+// Route of a query's k-mer bytes in a column-sharded search: rank 0 stores every 16-byte line of the k-mer
+// array into every peer's LL inbox (out[0..n_push)); a peer reads its k-mers from its own inbox `in`.
+// (A scatter + relay route -- every shard forwarding one segment -- balances the NVLink ports but makes the
+// peers wait for each other by one hop in EVERY query: measured 2.5 us per query on 4 GPUs; the star costs
+// rank 0's port (world-1) x 2 x the query = 4.3 MB per 10 000-k-mer query on 8 GPUs, a few per cent of it.)
+struct LlRoute {
+    const uint4 *in;           // this shard's LL inbox (null on rank 0 and outside a sharded search)
+    const uint8_t *kmers_base; // address line 0 corresponds to (16-byte aligned)
+    uint32_t flag;             // low 32 bits of the query's sequence number (never 0)
+    uint4 *out[8];             // rank 0: the peers' LL inboxes
+};
+
 // Synchronisation of a hashing group: the whole CTA (id 0), a subset of warps on a named barrier
 // (id > 0, nthreads a multiple of 32), or one warp (nthreads == 32).  A runtime choice on purpose: the
 // hashing code exists ONCE per kernel (it runs once per launch, so its cost is instruction fetch).
@@ -172,15 +184,14 @@ __device__ __forceinline__ GroupSync SyncWarp() { return GroupSync{0, 32}; }
 // MurmurHash3 over those words and stores ids[km * h + seed].  `scratch` (16-byte aligned,
 // hash_scratch_bytes(cnt, k) bytes) and `ids` may be shared or global memory.  magic = mod_magic(m).
 //
-// ll_base != nullptr: the k-mer bytes are not read from g0 but from a "low-latency" inbox another GPU writes
-// over NVLink (see LlLine): 16-byte data line j of the k-mer array that starts at kmers_base (16-byte aligned)
-// lives in the line pair ll_base[2j], ll_base[2j+1]; every 8-byte half carries 4 data bytes and the 32-bit
-// flag of the query, so a line is simply re-read until all its flags equal ll_flag -- no separate ready
-// flag, no fence on the sender's side, and the wait is per 16-byte line.
+// route->in != nullptr: the k-mer bytes are not read from g0 but from a "low-latency" inbox other GPUs write
+// over NVLink (LlRoute): 16-byte data line j of the k-mer array that starts at kmers_base (16-byte aligned)
+// lives in the line pair in[2j], in[2j+1]; every 8-byte half carries 4 data bytes and the 32-bit flag of the
+// query, so a line is simply re-read until all its flags match -- no separate ready flag, no fence on the
+// sender's side, and the wait is per 16-byte line.
 static __device__ __noinline__ void hash_kmers_group(const uint8_t *g0, uint32_t cnt, int k, int h, uint32_t m, int canonical,
                                              uint8_t *scratch, int32_t *ids, uint32_t tid, uint32_t nthreads,
-                                             const GroupSync sync, uint64_t magic, const uint4 *ll_base = nullptr,
-                                             const uint8_t *kmers_base = nullptr, uint32_t ll_flag = 0)
+                                             const GroupSync sync, uint64_t magic, const LlRoute *route = nullptr)
 {
     const int nblocks = k >> 2, rem = k & 3;
     const uint32_t wpk = (uint32_t)(k + 3) >> 2;
@@ -193,11 +204,14 @@ static __device__ __noinline__ void hash_kmers_group(const uint8_t *g0, uint32_t
     const uint4 *a0 = reinterpret_cast<const uint4 *>(g0 - skew);
     const uint32_t nvec = (skew + nbytes + 15) >> 4;
     uint4 *sv = reinterpret_cast<uint4 *>(scratch);
-    if (ll_base == nullptr) {
+    if (route == nullptr || route->in == nullptr) {
         for (uint32_t i = tid; i < nvec; i += nthreads) sv[i] = __ldg(a0 + i);
     } else {
-        const uint4 *ll = ll_base + 2 * (size_t)((reinterpret_cast<const uint8_t *>(a0) - kmers_base) >> 4);
-        for (uint32_t i = tid; i < nvec; i += nthreads) sv[i] = ll_load_line(ll + 2 * (size_t)i, ll_flag);
+        const uint64_t line0 = (uint64_t)(reinterpret_cast<const uint8_t *>(a0) - route->kmers_base) >> 4;
+        for (uint32_t i = tid; i < nvec; i += nthreads) {
+            const uint64_t line = line0 + i;
+            sv[i] = ll_load_line(route->in + 2 * line, route->flag);
+        }
     }
     sync();
     const uint8_t *src = scratch + skew;

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "hash.cuh"
+
 namespace bigsi {
 
 constexpr int kMaxConsumerWarps = 13;                           // 416 consumer threads, one 16-byte unit each
@@ -111,9 +113,7 @@ struct QueryParams {
     // solo path: the same broadcast without fences or flags ("low-latency" lines, hash.cuh:ll_store_line) --
     // rank 0's consumer threads store their CTA's slice into every peer's LL inbox before they hash it; the
     // peers' hashing reads its k-mer bytes from its own LL inbox and spins per 16-byte line on the embedded flag
-    uint4 *ll_push[kMaxSinks];   // peers' LL inboxes (line pair j <-> bytes [16j, 16j+16) of `kmers`)
-    const uint4 *ll_in;          // this shard's LL inbox when the query comes from a peer, else null
-    uint32_t ll_flag;            // low 32 bits of the query's sequence number (never 0)
+    LlRoute ll;                  // hash.cuh: who sends which segment of the k-mer bytes to whom
     // result publication: after the merge phase the LAST CTA copies the hit list of query 0 to every
     // sink -- a block [0] = sequence flag, [1] = number of hits, then int32 cols[sink_spec], uint32
     // counts[sink_spec] -- in this GPU's, a peer GPU's (NVLink) or the host's (mapped pinned) memory

@@ -406,13 +406,34 @@ __device__ __forceinline__ void solo_producer(const QueryParams &P, const SoloGe
 
     // the first ring-full of k-mers is hashed by this warp alone, so the gather starts at once
     hash_kmers_group(P.kmers + sg.begin * P.k, sg.n_first, (int)P.k, (int)h, P.num_rows, 1, scratch, ids, lane, 32u,
-                     SyncWarp(), P.mod_magic, P.ll_in, P.kmers, P.ll_flag);
+                     SyncWarp(), P.mod_magic, &P.ll);
     __syncwarp();
     if (lane == 0) BIGSI_TS(1);
     uint32_t k0 = 0;
     for (; k0 < sg.n_first; k0 += G) {
         const int32_t *id = ids + (size_t)k0 * h;
         issue(min(G, sg.n_first - k0), [&](uint32_t i) { return id[i]; });
+    }
+    if (P.n_push && sg.cnt) {
+        // query broadcast (rank 0 of a column-sharded search), off the critical path: the first ring-full is in
+        // flight and the consumer warps are still hashing, so this warp has nothing else to do.  This CTA's slice
+        // of the k-mer bytes (the 16-byte lines that cover it; neighbouring CTAs write identical lines at the
+        // boundaries) goes into every peer's LL inbox over NVLink -- plain stores with the flag embedded: no fence
+        // (which would also wait for the bulk copies in flight), nothing to wait for
+        const uint64_t b0 = sg.begin * P.k, b1 = (sg.begin + sg.cnt) * P.k;
+        const uint64_t l0 = b0 >> 4, nvec = ((b1 + 15) >> 4) - l0;
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.kmers) + l0;
+        constexpr int kBatch = 6;  // loads in flight per lane: a 68-k-mer slice (133 lines) is one batch
+        for (uint64_t i0 = lane; i0 < nvec; i0 += 32 * kBatch) {
+            uint4 v[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u)
+                if (i0 + 32 * u < nvec) v[u] = __ldg(src + i0 + 32 * u);
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u)
+                if (i0 + 32 * u < nvec)
+                    for (uint32_t r = 0; r < P.n_push; ++r) ll_store_line(P.ll.out[r] + 2 * (l0 + i0 + 32 * u), v[u], P.ll.flag);
+        }
     }
     named_bar_sync(kBarIdsReady, blockDim.x);  // the consumer warps have hashed the rest of the range
     for (; k0 < sg.n_static; k0 += G) {
@@ -485,23 +506,11 @@ __device__ __forceinline__ void solo_consumer(const QueryParams &P, const SoloGe
     const uint32_t tw = min(P.tile_bytes, P.row_bytes16);
     volatile uint32_t *stage_cnt = reinterpret_cast<volatile uint32_t *>(smem + kStageCntOffset);
 
-    if (P.n_push && sg.cnt) {
-        // query broadcast (rank 0 of a column-sharded search): this CTA's slice of the k-mer bytes (the 16-byte
-        // lines that cover it; neighbouring CTAs write identical lines at the boundaries) goes to every peer's LL
-        // inbox over NVLink -- plain stores with the flag embedded, nothing to wait for
-        const uint64_t b0 = sg.begin * P.k, b1 = (sg.begin + sg.cnt) * P.k;
-        const uint64_t l0 = b0 >> 4, nvec = ((b1 + 15) >> 4) - l0;
-        const uint4 *src = reinterpret_cast<const uint4 *>(P.kmers) + l0;
-        for (uint64_t i = unit; i < nvec; i += consumer_threads) {
-            const uint4 v = __ldg(src + i);
-            for (uint32_t r = 0; r < P.n_push; ++r) ll_store_line(P.ll_push[r] + 2 * (l0 + i), v, P.ll_flag);
-        }
-    }
     // hash the part of the range the producer did not take, publish the pooled ids, release the producer
     const uint32_t rest = sg.cnt - sg.n_first;
     hash_kmers_group(P.kmers + (sg.begin + sg.n_first) * P.k, rest, (int)P.k, (int)P.h, P.num_rows, 1,
                      scratch + ((hash_scratch_bytes(sg.n_first, P.k) + 127) & ~127ull), ids + (size_t)sg.n_first * P.h, unit,
-                     consumer_threads, GroupSync{kBarHashGroup, (int)consumer_threads}, P.mod_magic, P.ll_in, P.kmers, P.ll_flag);
+                     consumer_threads, GroupSync{kBarHashGroup, (int)consumer_threads}, P.mod_magic, &P.ll);
     named_bar_sync(kBarHashGroup, consumer_threads);
     if (P.pool_share) {
         int32_t *dst = P.pool_ids + (size_t)blockIdx.x * P.pool_share * P.h;
@@ -681,7 +690,7 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
     // k-mers this CTA hashes itself (prehash geometry: one tile, one slice per CTA)
     const uint64_t kb = (uint64_t)blockIdx.x * P.items_per_slice;
     const uint32_t kcnt = (P.prehash && kb < P.total_kmers) ? (uint32_t)min((uint64_t)P.items_per_slice, P.total_kmers - kb) : 0u;
-    if (P.wait_flag != nullptr && (!P.wait_per_cta || kcnt) && !(SOLO && P.ll_in != nullptr)) {
+    if (P.wait_flag != nullptr && (!P.wait_per_cta || kcnt) && !(SOLO && P.ll.in != nullptr)) {
         // the query is published by another GPU / the host: wait for it (per CTA: for our own slice)
         if (threadIdx.x == 0) {
             const unsigned long long *flag = P.wait_flag + (P.wait_per_cta ? blockIdx.x : 0);

@@ -586,30 +586,33 @@ def test_fused_exchange_two_shards_one_process(B):
             s.index.close()
 
 
-def test_fused_exchange_pipelined_two_shards(B):
-    """Pipelined exchange: query s returns the complete result of query s-1, drain() the last one;
-    mixed with lock-step searches on the same exchange."""
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_fused_exchange_pipelined(B, world):
+    """Pipelined exchange over `world` shards in one process: query s returns the complete result of query
+    s-1, drain() the last one; lock-step searches mixed in on the same exchange.  world >= 3 exercises the
+    scatter + relay route of the k-mer bytes (rank 0 -> relay shard -> the other shards)."""
     import torch
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     from bigsi_b200.sharded import DeviceShard, FusedExchange, merge_shard_hits, unpack_hits
 
-    rng = np.random.default_rng(53)
-    m, N, k, h, cap = 20_011, 4000, 31, 3, 2048
+    rng = np.random.default_rng(53 + world)
+    part = 2000  # columns per shard, a multiple of 8
+    m, N, k, h, cap = 20_011, part * world, 31, 3, 2048
     rb = (N + 7) // 8
     rows = rng.random((m, rb * 8)) < 0.9
     rows[:, N:] = False
     packed = np.packbits(rows, axis=1)
     oix = O.OracleIndex(k, m, h, N, rows=packed)
-    half = 2000
+    offs = [g * part for g in range(world)]
     shards, exs = [], []
-    for g in range(2):
-        ix = B.DeviceIndex(m, half, col_offset=g * half, device=g)
-        ix.upload_rows(0, packed, src_byte_offset=g * half // 8)
+    for g in range(world):
+        ix = B.DeviceIndex(m, part, col_offset=offs[g], device=g)
+        ix.upload_rows(0, packed, src_byte_offset=offs[g] // 8)
         shards.append(DeviceShard(ix, k, h, cap=cap))
-    for g in range(2):
-        exs.append(FusedExchange(shards[g], 2, g, 8000, peers=True))
+    for g in range(world):
+        exs.append(FusedExchange(shards[g], world, g, 8000, peers=True))
     FusedExchange.connect_local(exs)
 
     def expect(arr, thr):
@@ -618,43 +621,51 @@ def test_fused_exchange_pipelined_two_shards(B):
         return e, cnt[e]
 
     def check(views, want, tag):
-        for g in views:
+        for g in views:  # every shard holds every shard's hits (all-gather)
             n, cols, vals = unpack_hits(g.cpu().numpy(), 1, cap)
             assert (n[:, 0] <= cap).all()
-            gc, gv = merge_shard_hits(n[:, 0], cols[:, 0], vals[:, 0], [0, half])
+            gc, gv = merge_shard_hits(n[:, 0], cols[:, 0], vals[:, 0], offs)
             assert np.array_equal(gc, want[0]) and np.array_equal(gv, want[1]), tag
+
+    def launch(arr, n_kmers, thr, pipelined):
+        d_k = torch.from_numpy(arr).to(shards[0].device)
+        out = [None] * world
+        for g in range(world - 1, -1, -1):  # the peers first: their kernels wait for rank 0's k-mers
+            with torch.cuda.device(g):
+                out[g] = exs[g].search(d_k if g == 0 else None, n_kmers, thr, pipelined=pipelined)
+        return out
 
     try:
         sizes = [40, 3000, 1, 7000, 512, 2500, 6000, 90, 4000, 4000, 333, 8000]
+        lockstep_steps = (5, 9)  # lock-step searches in between: generations and inboxes keep rotating
         pending = None
         for step, n_kmers in enumerate(sizes):
             arr = _rand_kmers(rng, n_kmers, k)
             thr = int(math.ceil(n_kmers * 0.85))
-            d_k = torch.from_numpy(arr).to(shards[0].device)
-            lockstep = step in (5, 9)  # lock-step searches in between: the generations keep rotating
-            with torch.cuda.device(1):
-                g1 = exs[1].search(None, n_kmers, thr, pipelined=not lockstep)
-            with torch.cuda.device(0):
-                g0 = exs[0].search(d_k, n_kmers, thr, pipelined=not lockstep)
+            lockstep = step in lockstep_steps
+            views = launch(arr, n_kmers, thr, not lockstep)
             if lockstep:
-                torch.cuda.synchronize(0)
-                torch.cuda.synchronize(1)
-                check((g0, g1), expect(arr, thr), ("lockstep", step))
+                for g in range(world):
+                    torch.cuda.synchronize(g)
+                check(views, expect(arr, thr), ("lockstep", step))
                 pending = None
                 continue
-            if pending is not None and step - 1 not in (5, 9):
+            if pending is not None:
                 # the PREVIOUS query's blocks: complete in stream order, no host synchronisation in between
-                assert g0 is not None and g1 is not None
-                c0, c1 = g0.clone(), g1.clone()  # consumed on each shard's own stream
-                check((c0, c1), pending, ("pipelined", step - 1))
+                assert all(v is not None for v in views)
+                copies = []
+                for g in range(world):
+                    with torch.cuda.device(g):
+                        copies.append(views[g].clone())  # consumed on each shard's own stream
+                check(copies, pending, ("pipelined", step - 1))
             else:
-                assert (g0 is None) == (step == 0)
+                assert all((v is None) == (step == 0) for v in views)
             pending = expect(arr, thr)
-        with torch.cuda.device(1):
-            g1 = exs[1].drain()
-        with torch.cuda.device(0):
-            g0 = exs[0].drain()
-        check((g0, g1), pending, "drain")
+        last = []
+        for g in range(world - 1, -1, -1):
+            with torch.cuda.device(g):
+                last.append(exs[g].drain())
+        check(last, pending, "drain")
     finally:
         for e in exs:
             e.close()
