@@ -9,6 +9,7 @@ from .bigsi import BIGSI, BigsiQueryResult, DEFAULT_CONFIG  # noqa: F401
 from .bloom import BloomFilter, generate_hashes, load_bitarray  # noqa: F401
 from .index import DeviceIndex, hash_kmers, hash_kmers_dev, kmers_to_array, threshold_dev  # noqa: F401
 from .metadata import DELETION_SPECIAL_SAMPLE_NAME, SampleMetadata  # noqa: F401
+from .scoring import Scorer  # noqa: F401
 from .utils import canonical, convert_query_kmer, reverse_comp, seq_to_kmers  # noqa: F401
 
 __version__ = "0.1.0"

@@ -347,9 +347,52 @@ def golden_kv_store():
     dump("kv_store.json", out)
 
 
+def golden_service():
+    """The response renderings of the reference's request handlers (bigsi/__main__.py:41-72, 261-299).  The
+    module itself cannot be imported here (hug, pyfasta, humanfriendly are absent), so the two pure functions
+    `d_to_csv` and `search_bigsi` are taken out of its source with `ast` and executed unmodified."""
+    import ast
+    import csv
+    import io
+    from bigsi.storage import get_storage
+
+    src = open(os.path.join(REFERENCE_ROOT, "bigsi", "__main__.py")).read()
+    tree = ast.parse(src)
+    ns = {"io": io, "csv": csv}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("d_to_csv", "search_bigsi"):
+            exec(compile(ast.Module([node], []), "bigsi/__main__.py", "exec"), ns)
+    d_to_csv, search_bigsi = ns["d_to_csv"], ns["search_bigsi"]
+    rng = random.Random(1357)
+    k, m, h, n, L = 31, 2003, 3, 9, 160
+    cfg = dict_config("golden_service", k, m, h)
+    get_storage(cfg).delete_all()
+    base = rand_seq(rng, L)
+    seqs = [base] + [mutate(rng, base, rng.randrange(1, 4)) for _ in range(n - 1)]
+    samples = ["sample %d" % i for i in range(n)]  # names with a blank: quoted in CSV
+    blooms = [BIGSI.bloom(cfg, seq_to_kmers(sq, k)) for sq in seqs]
+    bigsi = BIGSI.build(cfg, blooms, samples)
+    records = [base, seqs[2][:100], rand_seq(rng, 90), mutate(rng, base, 2), base[20:140]]
+    out = {"k": k, "m": m, "h": h, "samples": samples, "sample_seqs": seqs, "records": records, "cases": []}
+    for threshold, score in ((1.0, False), (0.5, False), (0.5, True), (0.0, False)):
+        dd = [search_bigsi(bigsi, seq, threshold, score) for seq in records]
+        out["cases"].append({
+            "threshold": threshold, "score": score,
+            "responses": _plain(dd),
+            "csv": [[d_to_csv(d, wh, cr) for d in dd] for wh, cr in ((True, True), (True, False), (False, True), (False, False))],
+            # the non-streaming bulk_search bodies (bigsi/__main__.py:285-288)
+            "bulk_csv": "\n".join([d_to_csv(d, False, False) for d in dd]),
+            "bulk_json": json.dumps(_plain(dd), indent=4),
+            "search_json": json.dumps(_plain(dd[0]), indent=4),
+        })
+    bigsi.delete()
+    dump("service.json", out)
+
+
 if __name__ == "__main__":
     golden_hashes()
     golden_search()
     golden_config1()
     golden_scores()
     golden_kv_store()
+    golden_service()

@@ -1,0 +1,56 @@
+"""The resident service layer (bigsi_b200/service.py) against renderings produced by the reference's own
+request-handler functions (tests/golden/make_golden.py:golden_service; bigsi/__main__.py:41-72, 261-299)."""
+import json
+
+import numpy as np
+import pytest
+
+from bigsi_b200 import service
+from tests.golden_util import load
+
+
+def test_d_to_csv_matches_reference_renderings():
+    g = load("service.json")
+    flags = ((True, True), (True, False), (False, True), (False, False))
+    for case in g["cases"]:
+        for (wh, cr), want in zip(flags, case["csv"]):
+            for d, w in zip(case["responses"], want):
+                assert service.d_to_csv(d, wh, cr) == w
+        assert "\n".join(service.d_to_csv(d, False, False) for d in case["responses"]) == case["bulk_csv"]
+    assert service.d_to_csv({"query": "ACGT", "results": []}) == ""
+    assert service.d_to_csv({"query": "ACGT", "results": []}, False, False) == ""
+
+
+def test_read_fasta(tmp_path):
+    p = tmp_path / "q.fasta"
+    p.write_text(">r1 first\nACGT\nTTGA\n\n>r2\nGGGG\n>empty\n>r3\nAC\nGT")
+    assert service.read_fasta(str(p)) == [("r1 first", "ACGTTTGA"), ("r2", "GGGG"), ("empty", ""), ("r3", "ACGT")]
+
+
+@pytest.mark.gpu
+def test_bulk_search_matches_reference_bodies(tmp_path):
+    import bigsi_b200 as B
+
+    g = load("service.json")
+    cfg = {"k": g["k"], "m": g["m"], "h": g["h"], "storage-config": {"filename": "service-golden"}}
+    bigsi = B.BIGSI.build(cfg, [B.BIGSI.bloom(cfg, B.seq_to_kmers(s, g["k"])) for s in g["sample_seqs"]], g["samples"])
+    fasta = tmp_path / "records.fasta"
+    fasta.write_text("".join(">rec%d\n%s\n%s\n" % (i, s[:50], s[50:]) for i, s in enumerate(g["records"])))
+    try:
+        for case in g["cases"]:
+            t, sc = case["threshold"], case["score"]
+            assert service.bulk_search(cfg, str(fasta), t, sc, format="json") == case["bulk_json"]
+            assert service.bulk_search(cfg, g["records"], t, sc, format="csv") == case["bulk_csv"]
+            assert service.search(cfg, g["records"][0], t, sc) == case["search_json"]
+            assert service.search(cfg, g["records"][0], t, sc, format="csv") == case["csv"][0][0]
+            lines = []
+            assert service.bulk_search(cfg, g["records"], t, sc, format="json", stream=True, write=lines.append) is None
+            assert [json.loads(l) for l in lines] == case["responses"]
+            lines = []
+            service.bulk_search(cfg, g["records"], t, sc, format="csv", stream=True, write=lines.append)
+            n = len(g["records"])
+            assert lines[0] == case["csv"][1][0]                      # header, no final LF
+            assert lines[1 : n - 1] == case["csv"][3][1 : n - 1]       # no header, no final LF
+            assert lines[n - 1] == case["csv"][2][n - 1]               # the last record keeps its final LF
+    finally:
+        bigsi.delete()
