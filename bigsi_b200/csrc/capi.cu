@@ -163,7 +163,7 @@ struct bigsi_b200_index {
     int64_t opt_tile_bytes = 0, opt_grid = 0, opt_kmers_per_stage = 0, opt_n_stages = 0, opt_ctas_per_sm = 0;
     bool timing = false;
     int64_t opt_debug_flags = 0;
-    int64_t opt_prehash = 1, opt_fuse_merge = 1, opt_merge_chunk_bytes = 0, opt_solo = 1, opt_pool_pct = 12, opt_zero_copy = 1;
+    int64_t opt_prehash = 1, opt_fuse_merge = 1, opt_merge_chunk_bytes = 0, opt_solo = 1, opt_pool_pct = 12, opt_zero_copy = 1, opt_cooperative = 0;
     DevBuf d_pool;            // pool ids / ready flags / claim counter of the solo path
     uint64_t pool_epoch = 0;  // in-kernel hashing / in-kernel merge (1 = when possible)
     DevBuf d_barrier;                             // grid-barrier arrival counter of the fused kernel
@@ -419,6 +419,7 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
     p.out = d_out;
     p.out_stride = out_stride;
     p.debug_flags = (uint32_t)ix->opt_debug_flags;
+    p.plain_launch = ix->opt_cooperative ? 0u : 1u;
     if (p.debug_flags & 2u) {  // timeline stamps of the LAST launch, fetched with bigsi_b200_index_debug_read
         cudaError_t de = ix->debug_ts.reserve((uint64_t)(grid > 0 ? grid : 1) * kDebugStamps * 8);
         if (de != cudaSuccess) return fail_cuda(de, "debug buffer");
@@ -729,6 +730,7 @@ int bigsi_b200_index_set_option(bigsi_b200_index *ix, const char *key, int64_t v
     else if (!strcmp(key, "merge_chunk_bytes")) ix->opt_merge_chunk_bytes = value;
     else if (!strcmp(key, "solo")) ix->opt_solo = value;
     else if (!strcmp(key, "zero_copy")) ix->opt_zero_copy = value;
+    else if (!strcmp(key, "cooperative")) ix->opt_cooperative = value;
     else if (!strcmp(key, "pool_pct")) ix->opt_pool_pct = value > 100 ? 100 : value;
     else return fail(BIGSI_B200_ERR_INVALID, "unknown option '%s'", key);
     return 0;

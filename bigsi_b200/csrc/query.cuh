@@ -137,6 +137,8 @@ struct QueryParams {
     uint32_t n_pub;
     unsigned long long pub_seq;
     unsigned long long *pub_sinks[kMaxSinks];
+    uint32_t plain_launch;    // 1: launch WITHOUT the cooperative attribute (option "cooperative" = 0): the grid barrier
+                              // then relies on grid <= resident CTA capacity alone; lets PDL start the next grid's CTAs early
     uint32_t debug_flags;     // bit 0: consumers skip the AND/count work (pure-gather ceiling measurement)
     unsigned long long *debug_ts;  // optional [grid][kDebugStamps] timeline stamps (globaltimer ns), see fused_query
 };

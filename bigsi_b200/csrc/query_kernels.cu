@@ -794,9 +794,9 @@ static cudaError_t launch_one(const QueryParams &p, int grid, cudaStream_t strea
 {
     if (p.solo)
         return launch_ex(fused_query<MODE, HC, true>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream,
-                         /*pdl=*/true, /*cooperative=*/true, p);
+                         /*pdl=*/true, /*cooperative=*/!p.plain_launch, p);
     return launch_ex(fused_query<MODE, HC, false>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream,
-                     /*pdl=*/true, /*cooperative=*/p.fuse_merge != 0, p);
+                     /*pdl=*/true, /*cooperative=*/p.fuse_merge != 0 && !p.plain_launch, p);
 }
 
 cudaError_t launch_query(const QueryParams &p, int mode, int grid, cudaStream_t stream)

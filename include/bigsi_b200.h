@@ -87,7 +87,11 @@ int bigsi_b200_index_get_info(const bigsi_b200_index *index, bigsi_b200_info *in
  * "n_stages", "ctas_per_sm", "merge_chunk_bytes", "debug_flags"; "prehash" / "fuse_merge" / "solo" /
  * "zero_copy" (default 1; 0 forces the separate hash / merge kernels, the generic single-query
  * path, the staged host copies); "pool_pct" (default 12: share of a query's k-mers that the CTAs
- * claim dynamically); "timing" (1 = bracket the fused kernel and the merge kernel of every query
+ * claim dynamically); "cooperative" (default 0: the single-kernel path is launched WITHOUT the cooperative
+ * attribute -- its grid barrier is safe because the plan keeps the grid within the resident-CTA capacity and a
+ * stream's grids become resident in order, and programmatic dependent launch can then start the next query's
+ * CTAs while the previous query's last CTAs finish, 2 us per query; 1 = cooperative launch, which makes the
+ * driver verify co-residency); "timing" (1 = bracket the fused kernel and the merge kernel of every query
  * launch with CUDA events, read back with bigsi_b200_index_timing_collect). */
 int bigsi_b200_index_set_option(bigsi_b200_index *index, const char *key, int64_t value);
 /* Synchronises, sums the event-timed durations recorded since the last collect and resets them.
