@@ -84,12 +84,80 @@ __global__ void __launch_bounds__(256) transpose_blooms_kernel(uint8_t *__restri
     }
 }
 
+// Wide variant: one warp = 256 rows x FOUR aligned 32-column words (128 columns), one CTA = 256 rows x 1 024
+// columns.  Lane l holds 32 bytes of the four filters l, l+32, l+64, l+96 of its warp's column range; per 32-row
+// block the four 32x32 transposes leave lane j with the 128 columns of row j, written as ONE 16-byte store
+// (the pitch is a multiple of 128 bytes and the first word a multiple of 4, so the address is 16-byte
+// aligned).  Words only partly inside [col0, col0 + n) fall back to the per-word read-modify-write.
+__global__ void __launch_bounds__(256) transpose_blooms_wide_kernel(uint8_t *__restrict__ matrix, uint64_t pitch,
+                                                                    uint64_t num_rows, uint64_t col0, uint64_t n_blooms,
+                                                                    const uint8_t *__restrict__ blooms, uint64_t bloom_stride,
+                                                                    uint64_t n_bits)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t word0 = ((col0 >> 5) & ~3ull) + ((uint64_t)blockIdx.y * 8 + warp) * 4;  // first of this warp's 4 words
+    const uint64_t r0 = (uint64_t)blockIdx.x * 256;
+    uint32_t w[4][8], vmask[4];
+    bool any = false, all = true;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint64_t col = (word0 + g) * 32 + lane;
+        const bool valid = col >= col0 && col < col0 + n_blooms;
+        vmask[g] = __ballot_sync(0xffffffffu, valid);
+        any |= vmask[g] != 0;
+        all &= vmask[g] == 0xffffffffu;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) w[g][s] = 0;
+        if (valid) {
+            const uint8_t *src = blooms + (col - col0) * bloom_stride + (r0 >> 3);
+            const uint4 a = ldg128_stream(src), b = ldg128_stream(src + 16);
+            w[g][0] = a.x; w[g][1] = a.y; w[g][2] = a.z; w[g][3] = a.w;
+            w[g][4] = b.x; w[g][5] = b.y; w[g][6] = b.z; w[g][7] = b.w;
+        }
+    }
+    if (!any) return;  // warp-uniform
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        const uint64_t rb = r0 + 32 * s;
+        uint32_t rowmask = 0xffffffffu;  // rows of this block below n_bits
+        if (rb >= n_bits) rowmask = 0;
+        else if (n_bits - rb < 32) rowmask = (1u << (uint32_t)(n_bits - rb)) - 1u;
+        uint32_t y[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) y[g] = msb_first_swizzle(warp_transpose32(msb_first_swizzle(w[g][s]) & rowmask, lane));
+        const uint64_t row = rb + lane;
+        if (row < num_rows) {
+            uint32_t *dst = reinterpret_cast<uint32_t *>(matrix + row * pitch + word0 * 4);
+            if (all) {
+                *reinterpret_cast<uint4 *>(dst) = make_uint4(y[0], y[1], y[2], y[3]);
+            } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (vmask[g] == 0) continue;
+                    const uint32_t smask = msb_first_swizzle(vmask[g]);
+                    dst[g] = vmask[g] == 0xffffffffu ? y[g] : ((dst[g] & ~smask) | (y[g] & smask));
+                }
+            }
+        }
+    }
+}
+
+constexpr bool kTransposeWide = true;  // false: the one-word-per-warp kernel above
+
 cudaError_t launch_transpose_blooms(uint8_t *matrix, uint64_t pitch, uint64_t num_rows, uint64_t col0, uint64_t n_blooms,
                                     const uint8_t *d_blooms, uint64_t bloom_stride, uint64_t n_bits, cudaStream_t stream)
 {
     if (n_blooms == 0 || num_rows == 0) return cudaSuccess;
     const uint64_t row_blocks = (num_rows + 255) / 256;
     if ((bloom_stride & 31) || bloom_stride < row_blocks * 32) return cudaErrorInvalidValue;
+    if (kTransposeWide) {
+        const uint64_t w_first = (col0 >> 5) & ~3ull, w_end = (col0 + n_blooms + 31) >> 5;  // words [w_first, w_end)
+        const uint64_t gy = (w_end - w_first + 31) / 32;  // 8 warps x 4 words per CTA
+        if (row_blocks > 0x7fffffffull || gy > 65535) return cudaErrorInvalidConfiguration;
+        transpose_blooms_wide_kernel<<<dim3((unsigned)row_blocks, (unsigned)gy), 256, 0, stream>>>(
+            matrix, pitch, num_rows, col0, n_blooms, d_blooms, bloom_stride, n_bits);
+        return cudaGetLastError();
+    }
     const uint64_t words = ((col0 + n_blooms + 31) >> 5) - (col0 >> 5);
     const uint64_t gy = (words + 7) / 8;
     if (row_blocks > 0x7fffffffull || gy > 65535) return cudaErrorInvalidConfiguration;
