@@ -255,10 +255,14 @@ int bigsi_b200_index_load_rows(bigsi_b200_index *index, const char *path, uint64
  * The reference has no distributed path; sample columns are independent (graph/index.py:42-80,
  * graph/bigsi.py:192-230), so shard g holds all rows of its column range on its own GPU and a
  * query needs two exchanges: the query itself to every shard, the per-shard hits back.  Both are
- * fused into the query kernel: rank 0's kernel stores the k-mer bytes into its peers' inboxes from
- * its prologue (NVLink peer stores + per-CTA flags), every rank's kernel publishes its hit list
- * into slot `rank` of every rank's result blocks and finishes only when all slots of its own copy
- * have arrived (all-gather semantics in stream order).  One handle per GPU; handles may live in
+ * fused into the query kernel: rank 0's kernel stores the k-mer bytes into its peers' inboxes over
+ * NVLink as "low-latency lines" (every 8 bytes carry 4 data bytes and the query's 32-bit sequence
+ * number, so the receiving kernel spins per 16-byte line and no fence or separate flag is needed;
+ * row tiles wider than one column tile use plain stores + per-CTA flags instead), every rank's
+ * kernel publishes its hit list into slot `rank` of every rank's result blocks and finishes only
+ * when all slots of its own copy have arrived (all-gather semantics in stream order).  Do not
+ * interleave other searches on the same handle with a pipelined sequence before its drain (they
+ * share the handle's hit buffers).  One handle per GPU; handles may live in
  * different processes (CUDA IPC) or in one (open_local).  Calls are SPMD: every rank calls
  * exchange_search_dev once per query with the same n_kmers / k / h / min_kmers.
  *
@@ -279,9 +283,10 @@ int bigsi_b200_exchange_open_local(bigsi_b200_index *index, bigsi_b200_index *co
 int bigsi_b200_exchange_search_dev(bigsi_b200_index *index, const char *d_kmers, uint64_t n_kmers, int k, int h,
                                    uint32_t min_kmers, void *stream, const void **d_blocks_out,
                                    uint64_t *block_bytes_out);
-/* Pipelined variant: the kernel of query s waits for every shard's publication of query s-1 BEFORE it
- * publishes its own hits and does not wait for query s at all, so consecutive queries overlap across
- * the shards (a shard runs at the pace of its own kernel instead of kernel + two NVLink latencies).
+/* Pipelined variant: the kernel of query s does not publish at its end; the LAST CTA of the kernel of
+ * query s+1 publishes query s's hit list from its prologue (where the NVLink latency overlaps the gather)
+ * and then waits for every shard's publication of query s, so consecutive queries overlap across the
+ * shards (a shard runs at the pace of its own kernel instead of kernel + two NVLink latencies).
  * *d_prev_blocks_out = the complete result blocks of the PREVIOUS query (NULL after the first call),
  * valid in stream order after this call and until the next-but-one call on this handle; consume them
  * (e.g. copy them out on the same stream) before that.  bigsi_b200_exchange_drain_dev completes the
