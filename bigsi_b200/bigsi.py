@@ -66,6 +66,17 @@ def _device(config):
     return int((config.get("storage-config", {}) or {}).get("device", 0))
 
 
+def merge_packed_rows(a, n1, b, n2):
+    """Bit-concatenate packed MSB-first rows: uint8 [n, >= ceil(n1/8)] and [n, >= ceil(n2/8)] ->
+    uint8 [n, ceil((n1+n2)/8)]; columns 0..n1-1 from a, n1..n1+n2-1 from b (graph/index.py:54-60)."""
+    n = a.shape[0]
+    A = np.unpackbits(np.ascontiguousarray(a, dtype=np.uint8), axis=1)[:, :n1] if n1 else np.zeros((n, 0), dtype=np.uint8)
+    Bb = np.unpackbits(np.ascontiguousarray(b, dtype=np.uint8), axis=1)[:, :n2] if n2 else np.zeros((n, 0), dtype=np.uint8)
+    if n1 + n2 == 0:
+        return np.zeros((n, 0), dtype=np.uint8)
+    return np.packbits(np.concatenate([A, Bb], axis=1), axis=1)
+
+
 def validate_build_params(bloomfilters, samples):
     if not len(bloomfilters) == len(samples):
         raise ValueError("There must be the same number of bloomfilters and sample names")
@@ -224,7 +235,35 @@ class BIGSI(SampleMetadata):
             st.close()
 
     def merge(self, bigsi):
-        raise NotImplementedError("merge is an offline maintenance path outside the GPU search scope (DESIGN.md)")
+        """graph/bigsi.py:252-260: append the columns and the samples of another index with the same
+        (m, h, k).  Rows are cut to num_cols bits and extended (graph/index.py:54-60); samples are added in
+        colour order, a name that cannot be added (duplicate, or the tombstone of a deleted sample) gets the
+        suffix "_duplicate_in_merge" (graph/metadata.py:74-80).  An offline maintenance path: the rows make a
+        host round trip in chunks (download, bit-concatenate, upload into a re-pitched matrix)."""
+        assert self.bloomfilter_size == bigsi.bloomfilter_size
+        assert self.num_hashes == bigsi.num_hashes
+        assert self.kmer_size == bigsi.kmer_size
+        old, other = self.index, bigsi.index
+        info = old.info()
+        n1, n2 = info["num_cols"], other.num_cols
+        new = DeviceIndex(info["num_rows"], n1 + n2, col_capacity=max(info["col_capacity"], n1 + n2),
+                          col_offset=info["col_offset"], device=info["device"])
+        try:
+            step = max(1, (1 << 24) // max((n1 + n2 + 7) // 8, 1))
+            for r0 in range(0, info["num_rows"], step):
+                n = min(step, info["num_rows"] - r0)
+                new.upload_rows(r0, merge_packed_rows(old.download_rows(r0, n), n1, other.download_rows(r0, n), n2))
+        except Exception:
+            new.close()
+            raise
+        self._store.index = new
+        old.close()
+        for c in range(bigsi.num_samples):
+            sample = bigsi.colour_to_sample(c)
+            try:
+                self.add_sample(sample)
+            except ValueError:
+                self.add_sample(sample + "_duplicate_in_merge")
 
     # -- query path ------------------------------------------------------------
     def seq_to_kmers(self, seq):

@@ -389,6 +389,43 @@ def golden_service():
     dump("service.json", out)
 
 
+def golden_merge():
+    """BIGSI.merge (graph/bigsi.py:252-260): two indexes with odd column counts, a shared sample name and a
+    deleted sample in the second one; the complete store of the merged index and queries on it."""
+    from bigsi.storage import get_storage
+    from oracle.ref_harness import _DICT_STORES
+
+    rng = random.Random(8642)
+    k, m, h = 11, 509, 3
+    base = rand_seq(rng, 120)
+    out = []
+    for ci, (n1, n2) in enumerate([(5, 9), (8, 3), (1, 16)]):
+        cfgs = [dict_config("golden_merge%d_%d" % (ci, j), k, m, h) for j in range(2)]
+        for c in cfgs:
+            get_storage(c).delete_all()
+        seqs1 = [mutate(rng, base, rng.randrange(0, 5)) for _ in range(n1)]
+        seqs2 = [mutate(rng, base, rng.randrange(0, 5)) for _ in range(n2)]
+        names1 = ["a%d" % i for i in range(n1)]
+        names2 = ["b%d" % i for i in range(n2)]
+        names2[0] = names1[0]  # duplicate name across the two indexes
+        b1 = BIGSI.build(cfgs[0], [BIGSI.bloom(cfgs[0], seq_to_kmers(s_, k)) for s_ in seqs1], names1)
+        b2 = BIGSI.build(cfgs[1], [BIGSI.bloom(cfgs[1], seq_to_kmers(s_, k)) for s_ in seqs2], names2)
+        if n2 > 2:
+            b2.delete_sample(names2[2])  # its colour carries the tombstone name into the merge
+        b1.merge(b2)
+        store = _DICT_STORES[cfgs[0]["storage-config"]["filename"]]
+        kv = [[base64.b64encode(bytes(key)).decode("ascii"), base64.b64encode(bytes(val)).decode("ascii")]
+              for key, val in sorted(store.items())]
+        merged = BIGSI(cfgs[0])
+        queries = run_queries(merged, [{"seq": s_, "threshold": t} for s_ in (base, seqs1[0], seqs2[-1]) for t in (1.0, 0.7, 0.0)])
+        out.append({"k": k, "m": m, "h": h, "seqs1": seqs1, "seqs2": seqs2, "names1": names1, "names2": names2,
+                    "deleted_in_2": names2[2] if n2 > 2 else None, "kv_b64": kv, "queries": queries,
+                    "num_samples": merged.num_samples})
+        b1.delete()
+        b2.delete()
+    dump("merge.json", out)
+
+
 if __name__ == "__main__":
     golden_hashes()
     golden_search()
@@ -396,3 +433,4 @@ if __name__ == "__main__":
     golden_scores()
     golden_kv_store()
     golden_service()
+    golden_merge()
