@@ -10,8 +10,13 @@ No web framework: wiring these functions to HTTP routes is the deployment's busi
 import csv
 import io
 import json
+import os
 
+import numpy as np
+
+from . import bits as _bits
 from .bigsi import BIGSI
+from .cortex import extract_kmers_from_ctx
 
 CITATION = "http://dx.doi.org/10.1038/s41587-018-0010-1"  # bigsi/__main__.py:71
 
@@ -87,3 +92,60 @@ def bulk_search(config, fasta, threshold=1.0, score=False, format="json", stream
         else:
             write(json.dumps(d))
     return None
+
+
+# -- ingest and build commands (bigsi/__main__.py:118-180, bigsi/cmds/bloom.py, bigsi/cmds/build.py) -------------
+def bloom(config, ctx, outfile):
+    """`bigsi bloom` (__main__.py:118-131 -> cmds/bloom.py:19-27): the k-mers of a McCortex graph -> Bloom filter
+    (hashed and set on the GPU) -> a .bloom file, the raw MSB-first bytes of the filter."""
+    outfile = os.path.realpath(outfile)
+    bf = BIGSI.bloom(config, extract_kmers_from_ctx(ctx, config["k"]))
+    directory = os.path.dirname(outfile)
+    if not os.path.exists(directory):
+        os.makedirs(directory)
+    with open(outfile, "wb") as of:
+        of.write(bf.tobytes())
+    return outfile
+
+
+def load_bloomfilter(path, m):
+    """cmds/build.py:22-28: a .bloom file -> packed uint8 [ceil(m/8)] (what BIGSI.build takes as one filter)."""
+    data = np.fromfile(path, dtype=np.uint8)
+    if data.size * 8 < m:
+        raise ValueError("%s holds %d bits, the index needs m=%d" % (path, data.size * 8, m))
+    return _bits.from_packed(data[: (m + 7) // 8], m)
+
+
+def build(config, bloomfilters=(), samples=(), from_file=None):
+    """`bigsi build` (__main__.py:133-174 -> cmds/build.py:43-66): .bloom files (listed directly or in a TSV of
+    `bloom_path<TAB>sample_name`) become the columns of a new resident index.  The reference chunks the build to
+    bound host memory (9/8 m bytes per filter) and merges the chunks; here the filters are staged to the GPU in
+    groups by BIGSI.build and transposed there."""
+    bloomfilters, samples = list(bloomfilters), list(samples)
+    if from_file and bloomfilters:
+        raise ValueError("You can only specify blooms via from_file or bloomfilters, but not both")
+    if from_file:
+        with open(from_file, "r") as tsv:
+            for row in csv.reader(tsv, delimiter="\t"):
+                bloomfilters.append(row[0])
+                samples.append(row[1])
+    if samples:
+        assert len(samples) == len(bloomfilters)
+    else:
+        samples = list(bloomfilters)
+    m = config["m"]
+    BIGSI.build(config, [load_bloomfilter(p, m) for p in bloomfilters], samples)
+    return {"result": "success"}
+
+
+def insert(config, bloomfilter, sample):
+    """`bigsi insert` (__main__.py:105-116 -> cmds/insert.py): one .bloom file as a new column."""
+    index = BIGSI(config)
+    index.insert(load_bloomfilter(bloomfilter, index.bloomfilter_size), sample)
+    return {"result": "success"}
+
+
+def merge(config, merge_config):
+    """`bigsi merge` (__main__.py:176-183)."""
+    BIGSI(config).merge(BIGSI(merge_config))
+    return {"result": "merged %s into %s." % (merge_config, config)}

@@ -426,6 +426,32 @@ def golden_merge():
     dump("merge.json", out)
 
 
+def golden_cortex():
+    """.ctx ingest (utils/cortex.py:23-27, 170-264): small version-6 graphs (written by bigsi_b200.cortex.write_ctx,
+    several colours, several k) and the k-mers the reference's reader extracts from them."""
+    import tempfile
+
+    from bigsi_b200.cortex import write_ctx
+
+    rng = random.Random(97531)
+    out = []
+    with tempfile.TemporaryDirectory() as d:
+        for k, ncols, n in ((31, 1, 120), (31, 3, 40), (21, 2, 60), (13, 1, 33), (3, 1, 10)):
+            kmers = [rand_seq(rng, k) for _ in range(n)]
+            if k == 31:
+                kmers.append("A" * 31)          # its own reverse complement's complement: T...T > A...A
+                kmers.append("ACGT" * 7 + "ACG")
+            path = os.path.join(d, "g.ctx")
+            write_ctx(path, kmers, sample_names=["sample %d" % i for i in range(ncols)])
+            with open(path, "rb") as f:
+                raw = f.read()
+            case = {"k": k, "ncols": ncols, "ctx_b64": base64.b64encode(raw).decode("ascii"), "extract": {}}
+            for kk in sorted({k, max(1, k - 4)}):
+                case["extract"][str(kk)] = list(extract_kmers_from_ctx(path, kk))
+            out.append(case)
+    dump("cortex.json", out)
+
+
 if __name__ == "__main__":
     golden_hashes()
     golden_search()
@@ -434,3 +460,4 @@ if __name__ == "__main__":
     golden_kv_store()
     golden_service()
     golden_merge()
+    golden_cortex()

@@ -54,3 +54,56 @@ def test_bulk_search_matches_reference_bodies(tmp_path):
             assert lines[n - 1] == case["csv"][2][n - 1]               # the last record keeps its final LF
     finally:
         bigsi.delete()
+
+
+@pytest.mark.gpu
+def test_commands_ctx_to_bloom_to_build_to_search(tmp_path):
+    """`bigsi bloom` / `build` / `insert` / `merge` as functions (bigsi/__main__.py:105-183): McCortex graphs ->
+    .bloom files (GPU hashing) -> TSV build (GPU transpose) -> search, against the oracle on the k-mers the
+    reference's reader extracted from the same graphs (tests/golden/cortex.json)."""
+    import base64
+
+    import bigsi_b200 as B
+    from oracle import oracle as O
+
+    cases = [c for c in load("cortex.json") if c["k"] == 31]
+    k, m, h = 31, 4099, 3
+    cfg = {"k": k, "m": m, "h": h, "storage-config": {"filename": "cmd-main"}}
+    cfg2 = {"k": k, "m": m, "h": h, "storage-config": {"filename": "cmd-other"}}
+    rows_tsv, oblooms, names = [], [], []
+    for i, case in enumerate(cases):
+        ctx = tmp_path / ("s%d.ctx" % i)
+        ctx.write_bytes(base64.b64decode(case["ctx_b64"]))
+        out = service.bloom(cfg, str(ctx), str(tmp_path / "blooms" / ("s%d.bloom" % i)))
+        kmers = case["extract"]["31"]
+        ob = O.OracleIndex.bloom(k, m, h, [O.canonical(x) for x in kmers])
+        assert np.array_equal(np.fromfile(out, dtype=np.uint8), ob)  # the .bloom file IS the filter's bytes
+        rows_tsv.append("%s\t%s" % (out, "sample%d" % i))
+        oblooms.append(ob)
+        names.append("sample%d" % i)
+    tsv = tmp_path / "build.tsv"
+    tsv.write_text("\n".join(rows_tsv) + "\n")
+    try:
+        assert service.build(cfg, from_file=str(tsv)) == {"result": "success"}
+        bigsi = B.BIGSI(cfg)
+        oix = O.OracleIndex.build(k, m, h, oblooms, names)
+        assert np.array_equal(bigsi.index.download_rows(0, m), oix.rows)
+        q = cases[0]["extract"]["31"][3]
+        assert bigsi.search(q) == oix.search(q) and bigsi.search(q)
+        with pytest.raises(ValueError):
+            service.build(cfg, bloomfilters=["x"], from_file=str(tsv))
+        # insert one more filter from its file, then merge a second index built from the same files
+        assert service.insert(cfg, rows_tsv[0].split("\t")[0], "again") == {"result": "success"}
+        assert B.BIGSI(cfg).num_samples == len(names) + 1
+        service.build(cfg2, bloomfilters=[r.split("\t")[0] for r in rows_tsv])  # samples default to the paths
+        service.merge(cfg, cfg2)
+        merged = B.BIGSI(cfg)
+        assert merged.num_samples == 2 * len(names) + 1
+        res = merged.search(q)
+        assert [r["sample_name"] for r in res][:1] == ["sample0"] and len(res) >= 3  # sample0, again, the merged copy
+    finally:
+        for c in (cfg, cfg2):
+            try:
+                B.BIGSI(c).delete()
+            except KeyError:
+                pass
