@@ -2,15 +2,16 @@
 """bench.py -- BIGSI search hot path on B200 (BASELINE.json configs[1], weak-scaled by column shard).
 
 Workload (config.workload): synthetic m=25 000 000, h=3, k=31 index with 50 000 sample columns
-PER GPU resident in HBM (156.8 GB/GPU); one STEP = one 10 000-k-mer query run through the hot
-path: canonical+murmur3 hash kernel -> fused gather-AND-popcount kernel -> merge -> threshold at
-min_kmers = U (an exact query through the count path).  64 distinct queries rotate so that
-consecutive steps never touch the same rows (187.5 MB of rows per step > 126 MB L2).
+PER GPU resident in HBM (156.8 GB/GPU); one STEP = a block of 64 distinct 10 000-k-mer queries, each
+run through the hot path on its own: canonical+murmur3 hashing, gather-AND-popcount (gather kernel),
+merge + threshold at min_kmers = U (reduce kernel; an exact query through the count path), i.e. 2 kernel
+launches per query, no batching across queries.  The 64 queries of a step are all different
+(187.5 MB of rows per query > 126 MB L2), every query's hit list is produced separately.
 
 Metric: k-mer row-AND lookups/s, one lookup = gather h rows of one 50 000-column shard and AND
 them (18 750 algorithmic bytes).  At N GPUs every rank looks the same k-mers up in its own
-column shard (rank 0 broadcasts the row ids, hits are all-gathered), so the whole-job value is
-N * U * steps / time.
+column shard (rank 0's gather kernel pushes the k-mers to the peers, the reduce kernels all-gather
+the hits), so the whole-job value is N * U * 64 * steps / time.
 
 `--impl reference` times the CPU oracle port of the reference's algorithm (oracle/, OpenMP on all
 host cores) on the same workload; see DESIGN.md "Measurement".
@@ -33,25 +34,25 @@ K, H = 31, 3
 METRIC = "kmer_row_and_lookups_per_sec"
 UNIT = "lookups/s (1 lookup = h=3 row gather+AND over one 50 000-column shard = 18 750 B)"
 N_DISTINCT = 64
+QUERIES_PER_STEP = 64  # one step = every distinct query once
 HIT_CAP = 1024
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40, help="timed steps; one step = 64 queries")
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--m", type=int, default=25_000_000, help="Bloom filter size (rows); default = BASELINE")
     ap.add_argument("--cols", type=int, default=50_000, help="sample columns per GPU")
     ap.add_argument("--kmers", type=int, default=10_000, help="unique k-mers per query")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--prewarm", type=int, default=300, help="untimed steps before the warm-up (clock ramp)")
-    ap.add_argument("--exchange", default="pipelined", choices=["pipelined", "fused", "nccl"],
-                    help="N>1: query broadcast + hit all-gather inside the query kernel over NVLink peer memory, "
-                         "pipelined (the kernel of query s waits for the shards' hits of query s-1 only; default) or "
-                         "lock-step (fused), or as two NCCL collectives per query (nccl)")
+    ap.add_argument("--prewarm", type=int, default=5, help="untimed steps before the warm-up (clock ramp)")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N>1: query broadcast + hit all-gather inside the query kernels over NVLink peer memory (default), "
+                         "or as two NCCL collectives per query (nccl)")
     ap.add_argument("--opt", action="append", default=[], help="diagnostics: index option key=value (repeatable)")
     ap.add_argument("--timeline", action="store_true",
                     help="diagnostics: after the timed region print every rank's per-CTA kernel timeline (stderr)")
@@ -146,16 +147,18 @@ class ClockSampler(threading.Thread):
 # CPU oracle leg (cpu_baseline and --impl reference)
 # ---------------------------------------------------------------------------------------------
 class CpuArm:
-    """The oracle port of the reference's algorithm on the same synthetic workload.  Rows the
-    queries touch are regenerated from the synthetic index's pure function BEFORE timing (the
-    reference's in-memory store would hold them already)."""
+    """The oracle port of the reference's algorithm on the same synthetic workload: `shards` column shards of
+    `cols` columns (the N-GPU job's whole index).  Rows the queries touch are regenerated from the synthetic
+    index's pure function BEFORE timing (the reference's in-memory store would hold them already)."""
 
-    def __init__(self, args, n_queries):
+    def __init__(self, args, n_queries, shards=1):
         from oracle import oracle as O
 
         self.O = O
+        O.lib().oracle_set_num_threads(os.cpu_count() or 1)  # torchrun pins OMP_NUM_THREADS=1: use every host core
         self.cores = O.lib().oracle_num_threads()
-        pc, pt = planted_columns(1, args.cols)
+        self.shards = shards
+        pc, pt = planted_columns(shards, args.cols)
         self.spec = O.SynthSpec(0, 1, pc, pt)
         self.m, self.cols, self.u = args.m, args.cols, args.kmers
         self.queries = make_queries(n_queries, args.kmers)
@@ -163,43 +166,51 @@ class CpuArm:
         for q in range(n_queries):
             r = O.hash_kmers(self.queries[q], K, H, self.m)
             uniq, inv = np.unique(r.reshape(-1), return_inverse=True)
-            store = self.spec.rows(uniq, 0, self.cols)
-            self.stores.append((store, np.ascontiguousarray(inv.reshape(r.shape), dtype=np.int64), uniq))
+            per_shard = [self.spec.rows(uniq, g * self.cols, self.cols) for g in range(shards)]
+            self.stores.append((per_shard, uniq))
 
     def step(self, q):
-        """hash + per-k-mer AND + per-column count + threshold (graph/index.py:62-80, graph/bigsi.py:35-44,211-242)."""
+        """hash + per-k-mer AND + per-column count + threshold (graph/index.py:62-80, graph/bigsi.py:35-44,211-242),
+        over every shard of the index."""
         O = self.O
-        store, slot, uniq = self.stores[q]
+        per_shard, uniq = self.stores[q]
         r = O.hash_kmers(self.queries[q], K, H, self.m)  # canonical + murmur3, as the reference does per query
         # row ids -> slots of the in-memory store (the reference's dict lookup by row key)
-        slot2 = np.searchsorted(uniq, r.reshape(-1)).reshape(r.shape).astype(np.int64)
-        cnt = O.counts_from_rows(store, slot2, self.cols)
-        return np.nonzero(cnt >= self.u)[0]
+        slot = np.searchsorted(uniq, r.reshape(-1)).reshape(r.shape).astype(np.int64)
+        hits = []
+        for g, store in enumerate(per_shard):
+            cnt = O.counts_from_rows(store, slot, self.cols)
+            hits.append(np.nonzero(cnt >= self.u)[0] + g * self.cols)
+        return np.concatenate(hits)
 
 
 def run_reference(args):
+    """--impl reference: the reference's algorithm (oracle port, OpenMP on every host core) on the GPU arm's
+    config: the whole N-shard index, one full query per step.  Under torchrun rank 0 alone runs it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    nq = max(1, min(8, args.steps + args.warmup))
-    arm = CpuArm(args, nq)
+    shards = max(1, args.gpus)
+    nq = max(1, min(4, args.steps + args.warmup))
+    arm = CpuArm(args, nq, shards)
     for i in range(args.warmup):
         arm.step(i % nq)
     t0 = time.perf_counter()
     for i in range(args.steps):
         hits = arm.step((args.warmup + i) % nq)
     dt = time.perf_counter() - t0
-    assert len(hits) >= 3
-    value = args.kmers * args.steps / dt
+    assert len(hits) >= 3 * shards
+    value = shards * args.kmers * args.steps / dt
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, shards),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port",
-                         "sample": "every step = one full %d-k-mer query on one %d-column shard (rows it touches "
-                                   "pre-generated in host RAM, %d distinct queries rotating)" % (args.kmers, args.cols, nq)},
+                         "sample": "every step = ONE full %d-k-mer query over all %d column shards of %d columns (a bounded "
+                                   "sample of the GPU arm's step of %d such queries; rows it touches pre-generated in host RAM, "
+                                   "%d distinct queries rotating)" % (args.kmers, shards, args.cols, QUERIES_PER_STEP, nq)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -210,18 +221,17 @@ def run_reference(args):
 def workload_config(args, n_gpus):
     return {
         "workload": "BASELINE configs[1]: synthetic m=%d h=%d k=%d, N=%d columns per GPU (x%d GPUs, column-sharded), "
-                    "one %d-k-mer exact query (min_kmers=U) per step: canonical+murmur3 hash, fused gather-AND-popcount, "
-                    "merge and threshold in ONE kernel launch" % (args.m, H, K, args.cols, n_gpus, args.kmers),
+                    "%d-k-mer exact queries (min_kmers=U), each on its own: canonical+murmur3 hash + gather-AND-popcount "
+                    "(gather kernel), merge + threshold (reduce kernel); one step = %d distinct queries back to back"
+                    % (args.m, H, K, args.cols, n_gpus, args.kmers, QUERIES_PER_STEP),
         "m": args.m, "h": H, "k": K, "cols_per_gpu": args.cols, "kmers_per_query": args.kmers,
-        "distinct_queries": N_DISTINCT,
+        "distinct_queries": N_DISTINCT, "queries_per_step": QUERIES_PER_STEP,
         "exchange": ("none (one shard)" if n_gpus == 1 else
-                     "in-kernel, pipelined: query pushed to peers and hits all-gathered through NVLink peer memory by the query "
-                     "kernel, no collective call; the kernel of query s completes the all-gather of query s-1, the last "
-                     "query is drained inside the timed region"
-                     if getattr(args, "exchange", "pipelined") == "pipelined" else
-                     "in-kernel, lock-step: query pushed to peers and hits all-gathered through NVLink peer memory, no collective call"
-                     if getattr(args, "exchange", "pipelined") == "fused" else "NCCL broadcast + all-gather per query"),
-        "l2_policy": "inputs larger than L2: each step gathers %.1f MB of distinct rows, %d distinct queries rotate"
+                     "in-kernel: rank 0's gather kernel pushes the query to the peers, every rank's reduce kernel publishes its hits "
+                     "to every rank and waits for the others' (while the next query's gather kernel runs) -- NVLink peer memory, "
+                     "no collective call"
+                     if getattr(args, "exchange", "fused") == "fused" else "NCCL broadcast + all-gather per query"),
+        "l2_policy": "inputs larger than L2: each query gathers %.1f MB of distinct rows, %d distinct queries rotate"
                      % (args.kmers * H * math.ceil(args.cols / 8) / 1e6, N_DISTINCT),
         "matrix_density": 0.5,
     }
@@ -249,18 +259,18 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    U, cols = args.kmers, args.cols
+    U, cols, QPS = args.kmers, args.cols, QUERIES_PER_STEP
     pc, pt = planted_columns(world, cols)
     index = bigsi_b200.DeviceIndex(args.m, cols, col_offset=rank * cols, device=local_rank)
     t0 = time.perf_counter()
     index.fill_synthetic(0, 1, pc, pt)
     fill_s = time.perf_counter() - t0
+    index.set_option("inputs_ready", 1)  # the k-mer buffers below are resident / host-written before every call
     for kv in args.opt:
         key, val = kv.split("=")
         index.set_option(key, int(val))
     shard = DeviceShard(index, K, H, cap=HIT_CAP)
-    fused = world > 1 and args.exchange in ("fused", "pipelined")
-    piped = world > 1 and args.exchange == "pipelined"
+    fused = world > 1 and args.exchange == "fused"
     searcher = ShardedSearcher(shard, dist if world > 1 else None, world, rank, fused_max_kmers=U if fused else 0)
 
     queries = make_queries(N_DISTINCT, U)
@@ -270,92 +280,100 @@ def run_b200(args):
     d_min = torch.tensor([U], dtype=torch.int32, device=dev)
     h_min = np.array([U], dtype=np.uint32)
     h_qoff = np.array([0, U], dtype=np.int64)
+    # the ClockSampler (NVML init, thread) exists BEFORE any barrier that precedes a timed region
+    sampler = ClockSampler(local_rank)
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
+
+    def dev_query(q, min_kmers=U):
+        if fused:  # 2 kernels per rank and query, no collective: rank 0's k-mers are pushed by its gather kernel
+            return searcher.search_one_fused(d_queries[q] if rank == 0 else None, U, min_kmers)
+        if min_kmers != U:
+            return searcher.search_step(d_queries[q], d_qoff, torch.tensor([min_kmers], dtype=torch.int32, device=dev), 1, U)
+        return searcher.search_step(d_queries[q], d_qoff, d_min, 1, U)
 
     def dev_step(i):
-        if fused:  # one kernel per rank and step, no collective: rank 0's k-mers are pushed by its kernel
-            return searcher.search_one_fused(d_queries[i % N_DISTINCT] if rank == 0 else None, U, U, pipelined=piped)
-        return searcher.search_step(d_queries[i % N_DISTINCT], d_qoff, d_min, 1, U)
+        for j in range(QPS):
+            g = dev_query((i * QPS + j) % N_DISTINCT)
+        return g
 
-    def dev_drain():
-        """Pipelined exchange: complete the all-gather of the last query (a no-op otherwise)."""
-        return searcher.drain_fused() if piped else None
-
-    # ---- correctness gate on the first query (planted all-ones columns must be the exact hits)
-    g = dev_step(0)
-    if piped:
-        g = dev_drain()
+    # ---- correctness gate (the parity tests proper are tests/, this guards the bench's own wiring): query 0
+    # exact -> exactly the planted all-ones columns on every shard; query 1 at score >= 0.4 -> those plus the graded
+    # column of density 0.95, whose count must be the same through the batch path (generic kernel) of the same shard
+    g = dev_query(0)
     torch.cuda.synchronize()
     n, hc, hv = unpack_hits(g.cpu().numpy(), 1, HIT_CAP)
     for r in range(world):
         got = sorted(hc[r, 0, : int(n[r, 0])].tolist())
         assert got == [0, 1, cols - 1], "rank %d: unexpected exact hits %r" % (r, got[:10])
+    thr04 = int(math.ceil(U * 0.4))
+    g = dev_query(1, thr04)
+    torch.cuda.synchronize()
+    n, hc, hv = unpack_hits(g.cpu().numpy(), 1, HIT_CAP)
+    d_cnt = torch.zeros((1, cols + 8), dtype=torch.int32, device=dev)
+    rows1 = shard.hash(d_queries[1])
+    index.query_dev(0, rows1.data_ptr(), d_qoff.data_ptr(), 1, U, H, d_cnt.data_ptr(), d_cnt.shape[1],
+                    torch.cuda.current_stream().cuda_stream, U)
+    cnt_local = d_cnt[0, :cols].cpu().numpy().astype(np.int64)
+    exp_local = np.nonzero(cnt_local >= thr04)[0]
+    assert set(exp_local.tolist()) == {0, 1, cols - 1, cols // 2}, exp_local[:10]
+    mine = 0 if world == 1 else rank
+    order = np.argsort(hc[mine, 0, : int(n[mine, 0])])
+    assert np.array_equal(hc[mine, 0, : int(n[mine, 0])][order], exp_local), "graded hits differ between the two paths"
+    assert np.array_equal(hv[mine, 0, : int(n[mine, 0])][order].astype(np.int64), cnt_local[exp_local])
+    for r in range(world):  # every shard reports its own graded column with a count near 0.95^3 * U
+        got = dict(zip(hc[r, 0, : int(n[r, 0])].tolist(), hv[r, 0, : int(n[r, 0])].tolist()))
+        assert sorted(got) == [0, 1, cols // 2, cols - 1], "rank %d: graded hits %r" % (r, sorted(got)[:10])
+        assert abs(got[cols // 2] - 0.95 ** 3 * U) < 0.03 * U and got[0] == got[1] == got[cols - 1] == U
 
-    # ---- pre-warm (clocks), then W warm-up steps, then K timed steps: device-resident inputs
-    for i in range(args.prewarm):
+    # ---- pre-warm (clocks), W warm-up steps, aligned start, K timed steps: device-resident inputs
+    for i in range(args.prewarm + args.warmup):
         dev_step(i)
-    dev_drain()
-    barrier()
-    for i in range(args.warmup):
-        dev_step(i)
-    dev_drain()
-    barrier()
     launches0 = index.info()["kernel_launches"]
-    sampler = ClockSampler(local_rank)
     sampler.start()
+    barrier()
+    dev_query(0)  # device-side rendezvous: one untimed query through the exchange right before the clock starts
+    barrier()
+    if fused:
+        searcher.fused.wait_ns()  # reset the wait counter
+        launches0 = index.info()["kernel_launches"]
+        barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
         dev_step(args.warmup + i)
-    dev_drain()  # every query's hits have arrived on this rank before the clock stops
-    ev1.record()
-    barrier()
+    ev1.record()  # every query's hits have arrived on this rank when this event completes (stream order)
+    torch.cuda.synchronize()
     clocks = sampler.stop()
+    barrier()
     ms = ev0.elapsed_time(ev1)
     launches = index.info()["kernel_launches"] - launches0
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    exchange_wait_us = None
+    if fused:
+        w_ns, _ = searcher.fused.wait_ns()
+        exchange_wait_us = w_ns / 1e3 / (args.steps * QPS)
+    t = torch.tensor([ms, exchange_wait_us or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * U * args.steps / (ms_max * 1e-3)
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        per_rank = torch.stack(gathered).cpu().numpy()
+    else:
+        per_rank = t.cpu().numpy()[None]
+    ms_max = float(per_rank[:, 0].max())
+    n_queries = args.steps * QPS
+    value = world * U * n_queries / (ms_max * 1e-3)
 
     if args.timeline:
-        import ctypes
+        dump_timeline(index, dev_query, barrier, rank)
 
-        from bigsi_b200 import _lib as _L
-        index.set_option("debug_flags", 2)
-        for i in range(50):
-            dev_step(i)
-        dev_drain()
-        barrier()
-        grid = index.info()["last_grid"]
-        buf = np.zeros(grid * 16, dtype=np.uint64)
-        # the drain kernel does not stamp: the buffer holds the last query kernel's stamps
-        _L.check(_L.lib().bigsi_b200_index_debug_read(index.handle, ctypes.c_void_p(buf.ctypes.data), buf.size))
-        ts = buf.reshape(grid, 16).astype(np.int64)
-        t0 = ts[:, 0].min()
-        names = ["entry", "prod_first_issue", "first_slot_landed", "last_slot_consumed", "flushed", "prod_last_issue",
-                 "past_grid_barrier", "merge_done", "past_pdl_wait", "hash_done", "merge_loaded", "merge_in_smem",
-                 "merge_expanded", "merge_stage_issue"]
-        lines = ["rank %d timeline (us since the first CTA entered; min / median / max over CTAs; last CTA separately)" % rank]
-        for j, nm in enumerate(names):
-            col = ts[:-1, j]
-            col = (col[col > 0] - t0) / 1e3
-            if col.size:
-                lines.append("  %-20s %7.2f %7.2f %7.2f   last CTA %7.2f" % (nm, col.min(), np.median(col), col.max(),
-                                                                            (ts[-1, j] - t0) / 1e3 if ts[-1, j] > 0 else -1))
-        sys.stderr.write("\n".join(lines) + "\n")
-        index.set_option("debug_flags", 0)
-
-    # ---- roofline pass: same K steps with the fused kernel bracketed by CUDA events on its stream
+    # ---- isolated pass: one CUDA-event pair per launch (serialises the launches, no overlap between queries)
     index.set_option("timing", 1)
-    for i in range(args.steps):
-        dev_step(args.warmup + i)
-    dev_drain()
+    for j in range(QPS):
+        dev_query(j)
     barrier()
     fused_ms, merge_ms, n_timed = index.timing_collect()
     index.set_option("timing", 0)
@@ -363,11 +381,10 @@ def run_b200(args):
     fused_avg_ms = fused_ms / max(n_timed, 1)
     merge_avg_ms = merge_ms / max(n_timed, 1)
     algo_bytes = info["last_algorithmic_bytes"]
-    # The timed region is `steps` back-to-back launches of ONE kernel, bracketed by a CUDA-event pair on its stream:
-    # its average launch duration there is ms / steps (consecutive launches overlap by the programmatic-dependent-
-    # launch prologue, so this is what a launch costs in the stream).  The second pass brackets EVERY launch with
-    # its own event pair, which serialises the launches and adds the launch gap: reported as *_isolated.
-    kernel_ms = ms_max / args.steps
+    # The timed region is steps x 64 back-to-back queries, bracketed by ONE CUDA-event pair on their stream.  A query =
+    # one gather kernel (all the row traffic) + one small reduce kernel that runs concurrently with the NEXT query's
+    # gather kernel; the gather kernel's average launch duration in the stream is therefore region / queries.
+    kernel_ms = ms_max / n_queries
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     achieved_isolated = algo_bytes / (fused_avg_ms * 1e-3) / 1e9
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -376,89 +393,18 @@ def run_b200(args):
             peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "fused_query_dram_bytes.json")
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r2_gather_dram_bytes.json")
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         except Exception:
             traffic = None
 
-    # ---- e2e arm: the C-ABI host call (N=1) / pinned host -> device -> exchange -> host (N>1)
-    def e2e_step(i):
-        q = i % N_DISTINCT
-        if world == 1:
-            # the reference-facing call: BIGSI.search takes a SEQUENCE (graph/bigsi.py:174); its filter stage is one
-            # C-ABI call on host buffers (windows -> set of raw k-mers -> threshold -> hash -> gather-AND-count -> hits)
-            return index.search_sequence(h_seqs[q], K, H, 1.0, cap=HIT_CAP)
-        if piped:
-            # pinned host k-mers -> H2D -> kernel of query i; its return value is the COMPLETE result of query i-1,
-            # copied to pinned host memory behind the kernel; the host then waits for the copy enqueued one step
-            # earlier, so the host->device->host legs of consecutive queries overlap (results arrive two steps late)
-            d_k = h_queries[q].to(dev, non_blocking=True) if rank == 0 else None
-            prev = searcher.search_one_fused(d_k, U, U, pipelined=True)
-            if rank != 0:
-                return None
-            slot = i % 3
-            if prev is not None:
-                e2e_host[slot].copy_(prev, non_blocking=True)
-            e2e_ev[slot].record()
-            e2e_ev[(i - 1) % 3].synchronize()
-            return e2e_host[(i - 1) % 3]
-        if fused:
-            d_k = h_queries[q].to(dev, non_blocking=True) if rank == 0 else None
-            g = searcher.search_one_fused(d_k, U, U)
-        else:
-            d_k = h_queries[q].to(dev, non_blocking=True) if rank == 0 else d_queries[q]
-            g = searcher.search_step(d_k, d_qoff, d_min, 1, U)
-        return g.cpu() if rank == 0 else None
-
-    if world == 1:
-        # 64 distinct random sequences of U + K - 1 bases: U windows, all distinct (checked), so one call = U lookups
-        h_seqs = []
-        for q in range(N_DISTINCT):
-            rng = np.random.default_rng(1000 + q)
-            h_seqs.append(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=U + K - 1)].tobytes())
-            c, v, nh, uq = index.search_sequence(h_seqs[q], K, H, 1.0, cap=HIT_CAP)
-            assert uq == U and sorted(c.tolist()) == [0, 1, cols - 1] and set(v.tolist()) == {U}, (q, uq, c[:8], v[:8])
-    if piped:
-        e2e_host = [torch.empty((world, 2 + 2 * HIT_CAP), dtype=torch.int32).pin_memory() for _ in range(3)]
-        e2e_ev = [torch.cuda.Event() for _ in range(3)]
-        for ev in e2e_ev:
-            ev.record()
-    for i in range(max(args.warmup, 3)):
-        e2e_step(i)
-    dev_drain()
-    barrier()
-    e2e_steps = min(args.steps, 500)
-    w0 = time.perf_counter()
-    for i in range(e2e_steps):
-        res = e2e_step(args.warmup + i)
-    if piped:  # the last query's hits: drain, then to the host
-        last = dev_drain()
-        if rank == 0:
-            res = last.cpu()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - w0  # host calls synchronise every step, so wall clock == device time + host overhead
-    barrier()
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * U * e2e_steps / float(te.item())
-    n_hits = 3
-    h2d = (U + K - 1) if world == 1 else U * K + 16 + 4
-    d2h = 24 + n_hits * 8 if world == 1 else world * (2 + 2 * HIT_CAP) * 4
-    e2e_kmers = None
-    if world == 1:  # the same query handed over as U unique raw k-mers (31 bytes each) instead of the sequence
-        for i in range(3):
-            index.search_kmers_hits(h_queries[i].numpy(), K, H, h_min, q_offsets=h_qoff, cap=HIT_CAP)
-        w0 = time.perf_counter()
-        for i in range(e2e_steps):
-            index.search_kmers_hits(h_queries[(args.warmup + i) % N_DISTINCT].numpy(), K, H, h_min, q_offsets=h_qoff, cap=HIT_CAP)
-        dt = time.perf_counter() - w0
-        e2e_kmers = {"value": U * e2e_steps / dt, "ms_per_step": 1e3 * dt / e2e_steps, "h2d_bytes_per_step": U * K + 16 + 4,
-                     "path": "bigsi_b200_search_kmers_hits (C ABI, pinned host k-mers read zero-copy by the kernel)"}
+    # ---- e2e arm: host buffers in, hit lists out, through the C ABI
+    e2e = run_e2e(args, index, searcher, shard, queries, h_queries, barrier, rank, world, dev, fused)
 
     # ---- AND-mode (exact_filter) kernel, for context
     d_and = torch.empty((1, (cols + 7) // 8 + 16), dtype=torch.uint8, device=dev)
@@ -476,40 +422,38 @@ def run_b200(args):
         cpu_baseline = run_cpu_baseline(args)
 
     if rank == 0:
+        streamed = bool(info["last_fused"] & 8)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitwise (LOP3) / u32 counts", "data": "synthetic",
             "config": workload_config(args, world),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": 1e3 * float(te.item()) / e2e_steps,
-                    "path": "bigsi_b200_search_sequence (C ABI, host sequence in, hit list out: front-end kernel + ONE query kernel, "
-                            "no host round trip in between)" if world == 1 else
-                            ("pinned host k-mers -> H2D on rank 0 -> ONE kernel per rank (k-mers pushed to the peers over NVLink in the prologue, "
-                             "hash, gather-AND-count, merge, threshold, hits published to every rank's result blocks) -> D2H"
-                             + ("; pipelined: query i's kernel completes the all-gather of query i-1, whose D2H the host awaits one step later" if piped else "")
-                             if fused else
-                             "pinned host k-mers -> H2D -> hash -> NCCL broadcast -> fused query -> threshold -> NCCL all-gather -> D2H")},
+            "us_per_query": 1e3 * ms_max / n_queries,
+            "per_rank_ms_per_step": [float(x) / args.steps for x in per_rank[:, 0]],
+            "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "fused_query<COUNTS,h=3> (in-kernel hash prologue + gather-AND-popcount + grid barrier + merge/threshold phase)" if info["last_fused"] == 3 else "fused_query<COUNTS,h=3>", "kernel_ms": kernel_ms,
-                         "timing": "CUDA events around the timed region of back-to-back launches, / launches",
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "gather_solo<COUNTS,h=3> (in-kernel hash prologue + TMA row gather + AND + bit-sliced count; its "
+                                   "reduce_kernel runs concurrently with the next query's gather)" if streamed else "fused_query<COUNTS,h=3>",
+                         "kernel_ms": kernel_ms,
+                         "timing": "one CUDA-event pair around the timed region of back-to-back queries, / queries",
                          "kernel_ms_isolated": fused_avg_ms, "achieved_isolated": achieved_isolated,
                          "frac_isolated": achieved_isolated / peak,
-                         "timing_isolated": "one CUDA-event pair per launch (serialises the launches, includes the launch gap)",
+                         "timing_isolated": "one CUDA-event pair per launch (serialises the launches: no overlap between queries, includes the launch gap)",
                          "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
-                         "frac_of_8TBps_nominal": achieved / 8000.0, "merge_kernel_ms": merge_avg_ms,
+                         "frac_of_8TBps_nominal": achieved / 8000.0, "reduce_kernel_ms_isolated": merge_avg_ms,
                          "launches_timed": int(n_timed)},
             "and_mode": {"kernel_ms": and_ms / max(and_n, 1), "achieved_GBps": algo_bytes / (and_ms / max(and_n, 1) * 1e-3) / 1e9,
                          "merge_kernel_ms": and_merge_ms / max(and_n, 1)},
             "launch_geometry": {kk: info[kk] for kk in ("last_grid", "last_block", "last_smem_bytes", "last_tile_bytes",
                                                         "last_n_tiles", "last_kmers_per_stage", "last_n_stages",
-                                                        "last_n_slices")},
+                                                        "last_n_slices", "last_reduce_grid")},
             "index": {"matrix_bytes": info["matrix_bytes"], "row_pitch_bytes": info["row_pitch_bytes"], "fill_seconds": fill_s},
         }
-        if e2e_kmers is not None:
-            line["e2e_kmers_path"] = e2e_kmers
+        if exchange_wait_us is not None:
+            line["exchange_wait_us_per_query"] = [float(x) for x in per_rank[:, 1]]
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))
@@ -517,6 +461,121 @@ def run_b200(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def run_e2e(args, index, searcher, shard, queries, h_queries, barrier, rank, world, dev, fused):
+    """The same metric end to end: HOST buffers in, hit lists in HOST memory out, every step.  N = 1: the
+    reference-facing C-ABI call bigsi_b200_search_sequence (BIGSI.search takes a SEQUENCE, graph/bigsi.py:174), 64
+    calls per step.  N > 1: rank 0's pinned host k-mers are read by its gather kernel (zero copy over PCIe) and
+    pushed to the peers; the all-gathered hits are copied to pinned host memory behind every query."""
+    import torch
+
+    U, cols, QPS = args.kmers, args.cols, QUERIES_PER_STEP
+    e2e_steps = max(1, min(args.steps, 10))
+    extra = {}
+    if world == 1:
+        # 64 distinct random sequences of U + K - 1 bases: U windows, all distinct (checked), so one call = U lookups
+        h_seqs = []
+        for q in range(N_DISTINCT):
+            rng = np.random.default_rng(1000 + q)
+            h_seqs.append(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=U + K - 1)].tobytes())
+            c, v, nh, uq = index.search_sequence(h_seqs[q], K, H, 1.0, cap=HIT_CAP)
+            assert uq == U and sorted(c.tolist()) == [0, 1, cols - 1] and set(v.tolist()) == {U}, (q, uq, c[:8], v[:8])
+
+        def e2e_step(i):
+            for j in range(QPS):
+                res = index.search_sequence(h_seqs[(i * QPS + j) % N_DISTINCT], K, H, 1.0, cap=HIT_CAP)
+            return res
+
+        h2d, d2h = QPS * (U + K - 1), QPS * (24 + 3 * 8)
+        path = ("bigsi_b200_search_sequence (C ABI, host sequence in, hit list out: front-end kernel + gather kernel + "
+                "reduce kernel, no host round trip in between), %d synchronous calls per step" % QPS)
+    else:
+        h_out = [torch.empty((world, 2 + 2 * HIT_CAP), dtype=torch.int32).pin_memory() for _ in range(4)]
+        d_qoff = torch.tensor([0, U], dtype=torch.int64, device=dev)
+        d_min = torch.tensor([U], dtype=torch.int32, device=dev)
+
+        def e2e_step(i):
+            for j in range(QPS):
+                q = (i * QPS + j) % N_DISTINCT
+                if fused:
+                    g = searcher.search_one_fused(h_queries[q].data_ptr() if rank == 0 else None, U, U)
+                else:
+                    d_k = h_queries[q].to(dev, non_blocking=True)
+                    g = searcher.search_step(d_k, d_qoff, d_min, 1, U)
+                if rank == 0:
+                    h_out[j % 4].copy_(g, non_blocking=True)
+            torch.cuda.synchronize()
+            return h_out[(QPS - 1) % 4]
+
+        h2d, d2h = QPS * U * K, QPS * world * (2 + 2 * HIT_CAP) * 4
+        path = ("rank 0: pinned host k-mers read zero-copy by the gather kernel and pushed to the peers over NVLink; 2 kernels "
+                "per rank and query; all-gathered hit blocks -> pinned host memory (cudaMemcpyAsync) behind every query"
+                if fused else "pinned host k-mers -> H2D -> NCCL broadcast -> query -> NCCL all-gather -> D2H")
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    w0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(2 + i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0  # the host calls synchronise every step, so wall clock == device time + host overhead
+    barrier()
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    if world == 1:  # the same query handed over as U unique raw k-mers (31 bytes each) instead of the sequence
+        h_min = np.array([U], dtype=np.uint32)
+        h_qoff = np.array([0, U], dtype=np.int64)
+        for i in range(3):
+            index.search_kmers_hits(h_queries[i].numpy(), K, H, h_min, q_offsets=h_qoff, cap=HIT_CAP)
+        w0 = time.perf_counter()
+        nk = QPS * min(e2e_steps, 3)
+        for i in range(nk):
+            index.search_kmers_hits(h_queries[i % N_DISTINCT].numpy(), K, H, h_min, q_offsets=h_qoff, cap=HIT_CAP)
+        dt = time.perf_counter() - w0
+        extra["kmers_path"] = {"value": U * nk / dt, "us_per_query": 1e6 * dt / nk, "h2d_bytes_per_query": U * K + 16 + 4,
+                               "path": "bigsi_b200_search_kmers_hits (C ABI, pinned host k-mers read zero-copy by the kernel)"}
+    out = {"value": world * U * QPS * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "us_per_query": 1e6 * e2e_s / (e2e_steps * QPS), "path": path}
+    out.update(extra)
+    return out
+
+
+def dump_timeline(index, dev_query, barrier, rank):
+    """Diagnostics: per-CTA globaltimer stamps of the last gather / reduce kernels of a short burst (stderr)."""
+    import ctypes
+
+    from bigsi_b200 import _lib as _L
+
+    index.set_option("debug_flags", 2)
+    for i in range(24):
+        dev_query(i)
+    barrier()
+    info = index.info()
+    grid, rgrid = info["last_grid"], info["last_reduce_grid"]
+    buf = np.zeros((grid + rgrid) * 16, dtype=np.uint64)
+    _L.check(_L.lib().bigsi_b200_index_debug_read(index.handle, ctypes.c_void_p(buf.ctypes.data), buf.size))
+    ts = buf.reshape(grid + rgrid, 16).astype(np.int64)
+    t0 = ts[:grid, 0].min()
+    lines = ["rank %d timeline of the last query (us since its first gather CTA entered; min / median / max over CTAs)" % rank]
+    for title, block, names in (("gather kernel", ts[:grid], {0: "entry", 8: "past_gate", 1: "prod_first_issue", 9: "hash_done",
+                                                             2: "first_slot_landed", 5: "prod_last_issue", 3: "last_slot_consumed",
+                                                             4: "flushed"}),
+                                ("reduce kernel", ts[grid:], {0: "entry", 8: "past_dependency_wait", 13: "stage_issue",
+                                                             10: "planes_loaded", 11: "counters_in_smem", 12: "expanded",
+                                                             7: "items_done", 6: "last_cta_gathered"})):
+        lines.append(" " + title)
+        for j, nm in names.items():
+            col = block[:, j]
+            col = (col[col > 0] - t0) / 1e3
+            if col.size:
+                lines.append("  %-22s %8.2f %8.2f %8.2f   (n=%d)" % (nm, col.min(), np.median(col), col.max(), col.size))
+    sys.stderr.write("\n".join(lines) + "\n")
+    index.set_option("debug_flags", 0)
 
 
 def run_cpu_baseline(args):

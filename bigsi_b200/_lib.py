@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbigsi_b200.so")
 
 OK = 0
-ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_NO_DEVICE, ERR_RANGE = -1, -2, -3, -4, -5
+ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_NO_DEVICE, ERR_RANGE, ERR_TIMEOUT = -1, -2, -3, -4, -5, -6
 MODE_COUNTS, MODE_AND = 0, 1
 
 c_u8p = ctypes.POINTER(ctypes.c_uint8)
@@ -42,7 +42,7 @@ class Info(ctypes.Structure):
         ("kernel_launches", ctypes.c_uint64),
         ("scratch_bytes", ctypes.c_uint64),
         ("last_fused", ctypes.c_uint32),
-        ("reserved", ctypes.c_uint32),
+        ("last_reduce_grid", ctypes.c_uint32),
     ]
 
     def asdict(self):
@@ -80,6 +80,7 @@ SIGNATURES = {
     "bigsi_b200_index_timing_collect": (_int, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                                ctypes.POINTER(_u64)]),
     "bigsi_b200_index_debug_read": (_int, [_vp, _vp, _u64]),
+    "bigsi_b200_index_status": (_int, [_vp]),
     "bigsi_b200_index_upload_rows": (_int, [_vp, _u64, _u64, _vp, _u64, _u64]),
     "bigsi_b200_index_download_rows": (_int, [_vp, _u64, _u64, _vp, _u64]),
     "bigsi_b200_index_set_column": (_int, [_vp, _u64, _vp, _u64]),
@@ -109,9 +110,7 @@ SIGNATURES = {
     "bigsi_b200_exchange_open_local": (_int, [_vp, _vp]),
     "bigsi_b200_exchange_search_dev": (_int, [_vp, _vp, _u64, _int, _int, ctypes.c_uint32, _vp, c_void_pp,
                                               ctypes.POINTER(_u64)]),
-    "bigsi_b200_exchange_search_pipelined_dev": (_int, [_vp, _vp, _u64, _int, _int, ctypes.c_uint32, _vp, c_void_pp,
-                                                        ctypes.POINTER(_u64)]),
-    "bigsi_b200_exchange_drain_dev": (_int, [_vp, _vp, c_void_pp, ctypes.POINTER(_u64)]),
+    "bigsi_b200_exchange_wait_ns": (_int, [_vp, ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
     "bigsi_b200_exchange_destroy": (_int, [_vp]),
 }
 

@@ -130,27 +130,26 @@ struct TimedLaunch {
 }  // namespace
 
 // Column-sharded search without per-query collectives: every rank owns one device block
-//   [inbox flags: kExFlags x u64][2 inboxes of k-mer bytes][2 low-latency inboxes][result blocks: 3 generations x world x block]
-// that its peers map (CUDA IPC across processes, plain peer access inside one process).  Rank 0's
-// kernel pushes the query into the peers' inboxes from its prologue; every rank's kernel publishes
-// its hit list into slot `rank` of every rank's result blocks and waits for the others' slots --
-// those of the same query (lock-step) or, pipelined, those of the PREVIOUS query before it
-// publishes.  Query s uses inbox s % 2 and result generation s % 3: a shard overwrites generation
-// s % 3 only after it has seen every shard's publication of s-1, i.e. after every shard has launched
-// past its consumer of s-3; rank 0 overwrites inbox s % 2 only after every shard has published s-2.
+//   [kExInboxes low-latency inboxes][result blocks: kExGenerations generations x world x block]
+// that its peers map (CUDA IPC across processes, plain peer access inside one process).  Rank 0's gather
+// kernel pushes the query into the peers' inboxes (LL lines); every rank's reduce kernel publishes its hit
+// list into slot `rank` of every rank's result blocks and waits (bounded) for the others' slots of the same
+// query while the next query's gather kernel already runs.  Query s uses inbox s % kExInboxes and result
+// generation s % kExGenerations.  Reuse is safe because of the streamed path's entry gate: the gather kernel of
+// query s starts only after THIS rank's reduce kernel of query s - kStreamRing has seen every shard's block of
+// that query, i.e. after every shard has finished reading the inbox of s - kStreamRing and has launched past
+// its consumers of generations <= s - kExGenerations.
 struct Exchange {
     int world = 0, rank = 0;
     uint32_t spec = 0;
-    uint64_t max_kmer_bytes = 0, kmers_off = 0, kmers_stride = 0, ll_off = 0, sinks_off = 0, block_bytes = 0, total_bytes = 0;
+    uint64_t max_kmer_bytes = 0, kmers_stride = 0, ll_off = 0, sinks_off = 0, block_bytes = 0, total_bytes = 0;
     uint8_t *local = nullptr;
     uint8_t *peer[kMaxSinks] = {};
     bool ipc_opened[kMaxSinks] = {};
     bool ready = false;
     uint64_t seq = 0;            // queries launched on this shard
-    uint64_t published_seq = 0;  // ... whose hit list this shard has sent to the others
 };
-constexpr uint64_t kExFlags = 1024;
-constexpr uint64_t kExInboxes = 2, kExGenerations = 3;
+constexpr uint64_t kExInboxes = kStreamRing, kExGenerations = 2 * kStreamRing;
 
 struct bigsi_b200_index {
     int device = 0;
@@ -163,9 +162,18 @@ struct bigsi_b200_index {
     int64_t opt_tile_bytes = 0, opt_grid = 0, opt_kmers_per_stage = 0, opt_n_stages = 0, opt_ctas_per_sm = 0;
     bool timing = false;
     int64_t opt_debug_flags = 0;
-    int64_t opt_prehash = 1, opt_fuse_merge = 1, opt_merge_chunk_bytes = 0, opt_solo = 1, opt_pool_pct = 12, opt_zero_copy = 1, opt_cooperative = 0;
-    DevBuf d_pool;            // pool ids / ready flags / claim counter of the solo path
-    uint64_t pool_epoch = 0;  // in-kernel hashing / in-kernel merge (1 = when possible)
+    int64_t opt_prehash = 1, opt_fuse_merge = 1, opt_merge_chunk_bytes = 0, opt_solo = 1, opt_pool_pct = 12, opt_zero_copy = 1, opt_cooperative = 1;
+    int64_t opt_inputs_ready = 0, opt_spin_timeout_ms = 10000;
+    // streamed single-query launches (query.cuh:kStreamRing): ring-buffered scratch + the completion / abort words
+    DevBuf d_pool;            // kStreamRing x [ready flags: grid x u64][ids: grid x pool_share x h x i32]
+    uint64_t pool_slot_bytes = 0;
+    uint64_t pool_epoch = 0;
+    DevBuf stream_partial;    // kStreamRing x partial planes
+    uint64_t stream_partial_slot = 0;
+    DevBuf d_stream;          // [done: 64 B][abort: 64 B][wait_ns: 64 B][kStreamStates x QState]
+    PinnedBuf h_status;       // mapped: word 0 = mirror of the abort word
+    DevBuf d_hits_ring;       // host-buffer paths: kStreamStates x {n_hits, cols[cap], counts[cap]}
+    uint64_t stream_seq = 0;  // streamed queries launched on this handle
     DevBuf d_barrier;                             // grid-barrier arrival counter of the fused kernel
     uint64_t barrier_target = 0, done_target = 0;
     PinnedBuf h_sink, h_kmers;   // mapped pinned: result block the kernel publishes to / staging of pageable k-mers
@@ -184,6 +192,11 @@ struct bigsi_b200_index {
 };
 
 namespace {
+
+constexpr uint64_t kStreamStateBytes = 3 * 64 + (uint64_t)kStreamStates * sizeof(QState);
+// shared memory a streamed gather CTA may use so that a reduce CTA (kReduceSmemBytes + its static words) still
+// fits on the same SM; every resident CTA reserves 1 KB
+constexpr uint64_t kStreamGatherSmem = (uint64_t)kSmBytes - 2 * 1024 - kReduceSmemBytes - 512;
 
 bool g_kernels_ready[64] = {};  // function attributes (dynamic shared memory opt-in) are per device
 
@@ -284,8 +297,18 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
         }
     }
 
+    // solo = STREAMED path: one query, hashed in the kernel, one slice per CTA; the merge runs as a separate
+    // reduce kernel that overlaps the next query's gather (no grid barrier).  Its shared memory leaves room for
+    // a reduce CTA on the same SM; a share of every CTA's k-mers goes to a pool that is drained dynamically.
+    p.solo = p.stream = 0;
+    p.pool_share = 0;
+    p.solo_max_kmers = 0xffffffffu;
+    if (p.prehash && n_queries == 1 && ix->opt_solo != 0 && grid > 0 &&
+        kSmemHeaderBytes + p.ids_bytes + 3ull * h * tile <= kStreamGatherSmem)
+        p.solo = p.stream = 1;
+
     // ring geometry
-    const uint64_t ring_avail = smem_avail - p.ids_bytes;
+    const uint64_t ring_avail = (p.solo ? kStreamGatherSmem - kSmemHeaderBytes : smem_avail) - p.ids_bytes;
     const uint64_t kmer_bytes = (uint64_t)h * tile;
     uint32_t G = 1;
     if (ix->opt_kmers_per_stage > 0) {
@@ -305,18 +328,13 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
     p.kmers_per_stage = G;
     p.n_stages = (uint32_t)stages;
 
-    // in-kernel merge: needs every CTA resident at once (one CTA per SM, grid <= SM count)
+    // in-kernel merge of the generic path: needs every CTA resident at once (one CTA per SM, grid <= SM count;
+    // launched cooperatively, so the driver verifies it)
     p.fuse_merge = 0;
-    if (ix->opt_fuse_merge != 0 && grid > 0 && grid <= ix->sm_count &&
+    if (!p.solo && ix->opt_fuse_merge != 0 && grid > 0 && grid <= ix->sm_count &&
         kSmemHeaderBytes + p.ids_bytes + (uint64_t)kMergeScratchBytes <= (uint64_t)kSmemBudget)
         p.fuse_merge = 1;
-    // solo path: one query, hashed and merged in the kernel; a share of every CTA's k-mers goes to a
-    // pool that is drained dynamically (tail balance)
-    p.solo = 0;
-    p.pool_share = 0;
-    p.solo_max_kmers = 0xffffffffu;
-    if (p.prehash && p.fuse_merge && n_queries == 1 && ix->opt_solo != 0) {
-        p.solo = 1;
+    if (p.solo) {
         const uint64_t c = p.items_per_slice;
         uint64_t pp = (c >= 16 && h <= kPoolMaxH) ? (c * (uint64_t)ix->opt_pool_pct + 50) / 100 : 0;
         if (pp > c) pp = c;
@@ -336,6 +354,8 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
     if (p.fuse_merge) {
         const uint32_t scratch = query_smem_bytes(p) - kSmemHeaderBytes - p.ids_bytes;  // the drained ring
         plan_merge(p, mode, scratch, (uint64_t)grid, (uint32_t)ix->opt_merge_chunk_bytes);
+    } else if (p.stream) {
+        plan_merge(p, mode, kReduceSmemBytes, (uint64_t)ix->sm_count, (uint32_t)ix->opt_merge_chunk_bytes);
     } else {
         plan_merge(p, mode, kMergeKernelSmem, (uint64_t)ix->sm_count * 3, (uint32_t)ix->opt_merge_chunk_bytes);
     }
@@ -348,37 +368,45 @@ struct HitsOut {
     uint32_t *counts = nullptr;
     unsigned long long *n = nullptr;
     uint64_t cap = 0;
-    // single-query extras: threshold by value (no device array), optional input gate, and result
-    // publication by the kernel itself to host / peer sinks (query.cuh:QueryParams)
+    // single-query extras: threshold by value (no device array) and result publication by the kernel itself to
+    // host / peer sinks (query.cuh:QueryParams)
     bool by_value = false;
     uint32_t min_value = 0;
-    const unsigned long long *wait_flag = nullptr;
-    unsigned long long wait_value = 0;
     uint32_t n_sinks = 0, sink_spec = 0;
     unsigned long long *sinks[kMaxSinks] = {};
     unsigned long long sink_seq = 0;
-    bool *published = nullptr;  // set when the launch will publish to the sinks (needs the in-kernel merge)
-    // column-sharded exchange fused into the kernel (see Exchange below)
-    bool require_fused = false;  // fail before launching unless the plan hashes and merges in the kernel
-    uint32_t wait_per_cta = 0;
+    bool *published = nullptr;  // set when the launch will publish to the sinks
+    // column-sharded exchange fused into the kernels (see Exchange above)
+    bool require_stream = false;  // fail before launching unless the plan is the streamed single-query one
+    bool inputs_ready = false;    // the k-mers are not produced by the preceding kernel of the stream
     uint32_t n_push = 0;
-    uint8_t *push_kmers[kMaxSinks] = {};
-    unsigned long long *push_flags[kMaxSinks] = {};
-    unsigned long long push_value = 0;
     uint32_t n_gather = 0;
     const unsigned long long *gather_blocks[kMaxSinks] = {};
-    bool gather_first = false;  // pipelined: no publication at the end; CTA 0 waits for the previous query's blocks
     unsigned long long gather_seq = 0;
-    // the number of k-mers comes from a preceding kernel (query front-end): only the solo path can follow it;
+    // the number of k-mers comes from a preceding kernel (query front-end): only the streamed path can follow it;
     // run_query returns 1 without launching anything when the plan is a different one
     const unsigned long long *total_dev = nullptr;
-    unsigned long long *scrub = nullptr;  // words the kernel clears behind its grid barrier (front-end table)
+    unsigned long long *scrub = nullptr;  // words the reduce kernel clears (front-end table)
     uint64_t scrub_words = 0;
-    LlRoute ll = {};  // solo path: the k-mer bytes travel through the shards' low-latency inboxes
-    uint32_t n_pub = 0;         // deferred publication of the previous query's hit list from this kernel's prologue
-    unsigned long long pub_seq = 0;
-    unsigned long long *pub_sinks[kMaxSinks] = {};
+    LlRoute ll = {};  // the k-mer bytes travel through the shards' low-latency inboxes
 };
+
+// the sticky abort word of the handle (ptx.cuh:raise_abort), as the host sees it
+unsigned long long abort_state(const bigsi_b200_index *ix)
+{
+    return ix->h_status.p ? *static_cast<volatile unsigned long long *>(ix->h_status.p) : 0ull;
+}
+int fail_aborted(unsigned long long v)
+{
+    static const char *what[] = {"?", "a query waited for the reduce kernel of an earlier query (entry gate)",
+                                 "a CTA waited for another CTA's pooled row ids",
+                                 "a shard waited for the query bytes of rank 0 (was rank 0's search launched?)",
+                                 "a shard waited for another shard's hit list (was the search launched on every rank?)",
+                                 "a reduce kernel waited for its predecessor (completion chain)"};
+    const unsigned code = (unsigned)(v & 0xff);
+    return fail(BIGSI_B200_ERR_TIMEOUT, "device-side wait timed out in query %llu: %s; the handle is unusable (destroy it)",
+                (unsigned long long)(v >> 8), what[code < 6 ? code : 0]);
+}
 
 // One query batch on `stream`.  Exactly one of d_rows / d_kmers is given; with k-mers the kernel
 // hashes them itself when the plan allows, otherwise the hash kernel runs first into scratch rows.
@@ -389,6 +417,7 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
     if (mode != BIGSI_B200_MODE_COUNTS && mode != BIGSI_B200_MODE_AND)
         return fail(BIGSI_B200_ERR_INVALID, "unknown query mode %d", mode);
     if (n_queries == 0) return 0;
+    if (const unsigned long long av = abort_state(ix)) return fail_aborted(av);
     const uint64_t row_bytes = (ix->num_cols + 7) / 8;
     if (d_out && (mode == BIGSI_B200_MODE_COUNTS ? out_stride < ix->num_cols : out_stride < row_bytes))
         return fail(BIGSI_B200_ERR_INVALID, "out_stride %llu too small", (unsigned long long)out_stride);
@@ -420,11 +449,17 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
     p.out_stride = out_stride;
     p.debug_flags = (uint32_t)ix->opt_debug_flags;
     p.plain_launch = ix->opt_cooperative ? 0u : 1u;
+    int reduce_grid = 0;
+    if (p.stream) {
+        reduce_grid = (int)std::min<uint64_t>(p.merge_items, (uint64_t)ix->sm_count);
+        if (reduce_grid < 1) reduce_grid = 1;
+    }
     if (p.debug_flags & 2u) {  // timeline stamps of the LAST launch, fetched with bigsi_b200_index_debug_read
-        cudaError_t de = ix->debug_ts.reserve((uint64_t)(grid > 0 ? grid : 1) * kDebugStamps * 8);
+        cudaError_t de = ix->debug_ts.reserve((uint64_t)((grid > 0 ? grid : 1) + reduce_grid) * kDebugStamps * 8);
         if (de != cudaSuccess) return fail_cuda(de, "debug buffer");
         p.debug_ts = static_cast<unsigned long long *>(ix->debug_ts.p);
     }
+    bool will_publish = false;
     if (hits) {
         p.min_kmers = hits->min_kmers;
         p.hit_cols = hits->cols;
@@ -436,105 +471,161 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
             p.min_kmers_value = hits->min_value;
         }
         if (hits->total_dev) {
-            if (!(p.solo && p.fuse_merge && grid > 0 && hits->n_sinks)) return 1;
+            if (!(p.stream && hits->n_sinks)) return 1;
             p.total_dev = hits->total_dev;
             p.scrub = hits->scrub;
             p.scrub_words = hits->scrub_words;
         }
-        if (hits->require_fused && !(p.prehash && p.fuse_merge && grid > 0))
-            return fail(BIGSI_B200_ERR_INVALID, "this query cannot run as one kernel (prehash=%u fuse_merge=%u grid=%d)", p.prehash,
-                        p.fuse_merge, grid);
-        p.wait_flag = hits->wait_flag;
-        p.wait_value = hits->wait_value;
-        p.wait_per_cta = hits->wait_per_cta;
+        if (hits->require_stream && !p.stream)
+            return fail(BIGSI_B200_ERR_INVALID, "this query cannot run as a streamed single-query launch (prehash=%u grid=%d)",
+                        p.prehash, grid);
         p.n_push = hits->n_push;
-        p.push_value = hits->push_value;
-        for (uint32_t i = 0; i < hits->n_push; ++i) {
-            p.push_kmers[i] = hits->push_kmers[i];
-            p.push_flags[i] = hits->push_flags[i];
-        }
         p.n_gather = hits->n_gather;
         for (uint32_t i = 0; i < hits->n_gather; ++i) p.gather_blocks[i] = hits->gather_blocks[i];
-        p.gather_first = hits->gather_first ? 1u : 0u;
         p.gather_seq = hits->gather_seq;
         p.ll = hits->ll;
         p.ll.kmers_base = reinterpret_cast<const uint8_t *>(d_kmers);
-        p.n_pub = hits->n_pub;
-        p.pub_seq = hits->pub_seq;
-        for (uint32_t i = 0; i < hits->n_pub; ++i) p.pub_sinks[i] = hits->pub_sinks[i];
         p.sink_spec = hits->sink_spec;
         if (hits->published) *hits->published = false;
-        if (hits->n_sinks && p.fuse_merge && grid > 0 && n_queries == 1) {
+        if (hits->n_sinks && (p.stream || p.fuse_merge) && grid > 0 && n_queries == 1) {
             p.n_sinks = hits->n_sinks;
             p.sink_spec = hits->sink_spec;
             p.sink_seq = hits->sink_seq;
             for (uint32_t i = 0; i < hits->n_sinks; ++i) p.sinks[i] = hits->sinks[i];
-            p.done_counter = static_cast<unsigned long long *>(ix->d_barrier.p) + 16;
-            ix->done_target += (uint64_t)grid;
-            p.done_target = ix->done_target;
-            if (hits->published) *hits->published = true;
+            will_publish = true;
         }
         // stage 1 zeroes the hit counters; without a stage-1 launch do it here
         if (grid == 0) CK(cudaMemsetAsync(hits->n, 0, n_queries * sizeof(unsigned long long), stream));
     }
-    const uint64_t need = query_partial_bytes(p);
-    if (need > ix->partial.cap) {
-        CK(cudaStreamSynchronize(stream));
-        cudaError_t e = ix->partial.reserve(need);
-        if (e != cudaSuccess) return fail_cuda(e, "partial-plane workspace");
-    }
-    p.partial = static_cast<uint8_t *>(ix->partial.p);
-    if (p.solo) {
-        // [claim counter + padding: 256 B][ready flags: grid x u64][ids: grid x pool_share x h x i32]
+    if (p.stream) {
+        // ---- streamed launch: gather kernel + reduce kernel, ring-buffered scratch ------------------------------
+        const uint64_t seq = ix->stream_seq + 1;
+        const uint64_t slot = seq % kStreamRing;
+        const uint64_t need = round_up(query_partial_bytes(p), 256);
+        if (need > ix->stream_partial_slot) {
+            CK(cudaStreamSynchronize(stream));  // earlier queries may still use the old buffer
+            cudaError_t e = ix->stream_partial.reserve(kStreamRing * (need + need / 4));
+            if (e != cudaSuccess) return fail_cuda(e, "partial-plane workspace");
+            ix->stream_partial_slot = ix->stream_partial.cap / kStreamRing / 256 * 256;
+        }
+        p.partial = static_cast<uint8_t *>(ix->stream_partial.p) + slot * ix->stream_partial_slot;
+        // pool slot: [ready flags: grid x u64][ids: grid x pool_share x h x i32]
         const uint64_t flags_bytes = round_up((uint64_t)grid * 8, 256);
-        const uint64_t need_pool = 256 + flags_bytes + (uint64_t)grid * p.pool_share * h * 4 + 16;
-        if (need_pool > ix->d_pool.cap) {
+        const uint64_t need_pool = round_up(flags_bytes + (uint64_t)grid * p.pool_share * h * 4 + 16, 256);
+        if (need_pool > ix->pool_slot_bytes) {
             CK(cudaStreamSynchronize(stream));
-            cudaError_t e = ix->d_pool.reserve(need_pool);
+            cudaError_t e = ix->d_pool.reserve(kStreamRing * (need_pool + need_pool / 4));
             if (e != cudaSuccess) return fail_cuda(e, "pool workspace");
             CK(cudaMemsetAsync(ix->d_pool.p, 0, ix->d_pool.cap, stream));
-            ix->pool_epoch = 0;
+            ix->pool_slot_bytes = ix->d_pool.cap / kStreamRing / 256 * 256;
         }
-        uint8_t *pb = static_cast<uint8_t *>(ix->d_pool.p);
-        p.pool_counter = reinterpret_cast<unsigned int *>(pb);
-        p.pool_ready = reinterpret_cast<unsigned long long *>(pb + 256);
-        p.pool_ids = reinterpret_cast<int32_t *>(pb + 256 + flags_bytes);
-        p.pool_epoch = ++ix->pool_epoch;
-    }
-    if (p.fuse_merge) {
-        p.barrier = static_cast<unsigned long long *>(ix->d_barrier.p);
-        ix->barrier_target += (uint64_t)grid;
-        p.barrier_target = ix->barrier_target;
-    }
+        uint8_t *pb = static_cast<uint8_t *>(ix->d_pool.p) + slot * ix->pool_slot_bytes;
+        p.pool_ready = reinterpret_cast<unsigned long long *>(pb);
+        p.pool_ids = reinterpret_cast<int32_t *>(pb + flags_bytes);
+        p.pool_epoch = ix->pool_epoch + 1;
+        uint8_t *sb = static_cast<uint8_t *>(ix->d_stream.p);
+        QState *states = reinterpret_cast<QState *>(sb + 3 * 64);
+        p.stream_done = reinterpret_cast<unsigned long long *>(sb);
+        p.abort_word = reinterpret_cast<unsigned long long *>(sb + 64);
+        p.wait_ns_out = reinterpret_cast<unsigned long long *>(sb + 128);
+        void *hs = nullptr;
+        CK(cudaHostGetDevicePointer(&hs, ix->h_status.p, 0));
+        p.host_abort = static_cast<unsigned long long *>(hs);
+        p.spin_timeout_ns = (unsigned long long)ix->opt_spin_timeout_ms * 1000000ull;
+        p.stream_seq = seq;
+        p.qstate = states + seq % kStreamStates;
+        p.qstate_next = states + (seq + kStreamRing) % kStreamStates;
+        p.pool_counter = &p.qstate->pool_claims;
+        p.ll.abort_word = p.abort_word;
+        p.ll.host_abort = p.host_abort;
+        p.ll.timeout_ns = p.spin_timeout_ns;
+        p.ll.seq = seq;
+        // the kernel must wait for its predecessor in the stream when that may produce its input: always for a
+        // device-side k-mer count, and for caller-provided device k-mers unless the caller says otherwise
+        const bool ready = (hits && hits->inputs_ready) || ix->opt_inputs_ready != 0 || p.ll.in != nullptr;  // (a peer shard reads its inbox)
+        p.stream_wait_inputs = (ready && !p.total_dev) ? 0u : 1u;
 
-    TimedLaunch tl{};
-    if (ix->timing) {
-        if (ix->timed_free.empty()) {
-            CK(cudaEventCreate(&tl.e0));
-            CK(cudaEventCreate(&tl.e1));
-            CK(cudaEventCreate(&tl.e2));
-        } else {
-            tl = ix->timed_free.back();
-            ix->timed_free.pop_back();
+        TimedLaunch tl{};
+        if (ix->timing) {
+            if (ix->timed_free.empty()) {
+                CK(cudaEventCreate(&tl.e0));
+                CK(cudaEventCreate(&tl.e1));
+                CK(cudaEventCreate(&tl.e2));
+            } else {
+                tl = ix->timed_free.back();
+                ix->timed_free.pop_back();
+            }
+            CK(cudaEventRecord(tl.e0, stream));
         }
-        CK(cudaEventRecord(tl.e0, stream));
-    }
-    if (grid > 0) {
         cudaError_t e = launch_query(p, mode, grid, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "gather_solo launch");
+        ix->kernel_launches++;
+        if (ix->timing) CK(cudaEventRecord(tl.e1, stream));
+        QueryParams pr = p;
+        if (pr.debug_ts) pr.debug_ts += (uint64_t)grid * kDebugStamps;
+        e = launch_reduce(pr, mode, reduce_grid, stream);
+        // from here on the query counts as launched: the completion chain expects its reduce kernel
+        ix->stream_seq = seq;
+        ix->pool_epoch = p.pool_epoch;
         if (e != cudaSuccess) {
-            if (p.fuse_merge) ix->barrier_target -= (uint64_t)grid;  // nothing arrived
-            return fail_cuda(e, "fused_query launch");
+            // the gather kernel runs without its reduce kernel: the chain is broken for good
+            *static_cast<volatile unsigned long long *>(ix->h_status.p) = (seq << 8) | kAbortChain;
+            return fail_cuda(e, "reduce_kernel launch");
         }
         ix->kernel_launches++;
-    }
-    if (ix->timing) CK(cudaEventRecord(tl.e1, stream));
-    if (!p.fuse_merge) {
-        CK(launch_merge(p, mode, stream));
-        ix->kernel_launches++;
-    }
-    if (ix->timing) {
-        CK(cudaEventRecord(tl.e2, stream));
-        ix->timed_used.push_back(tl);
+        if (ix->timing) {
+            CK(cudaEventRecord(tl.e2, stream));
+            ix->timed_used.push_back(tl);
+        }
+        if (hits && hits->published) *hits->published = will_publish;
+    } else {
+        const uint64_t need = query_partial_bytes(p);
+        if (need > ix->partial.cap) {
+            CK(cudaStreamSynchronize(stream));
+            cudaError_t e = ix->partial.reserve(need);
+            if (e != cudaSuccess) return fail_cuda(e, "partial-plane workspace");
+        }
+        p.partial = static_cast<uint8_t *>(ix->partial.p);
+        TimedLaunch tl{};
+        if (ix->timing) {
+            if (ix->timed_free.empty()) {
+                CK(cudaEventCreate(&tl.e0));
+                CK(cudaEventCreate(&tl.e1));
+                CK(cudaEventCreate(&tl.e2));
+            } else {
+                tl = ix->timed_free.back();
+                ix->timed_free.pop_back();
+            }
+            CK(cudaEventRecord(tl.e0, stream));
+        }
+        if (grid > 0) {
+            // the host-side targets of the monotonic device counters advance only with a successful launch
+            if (p.fuse_merge) {
+                p.barrier = static_cast<unsigned long long *>(ix->d_barrier.p);
+                p.barrier_target = ix->barrier_target + (uint64_t)grid;
+            }
+            if (will_publish) {
+                p.done_counter = static_cast<unsigned long long *>(ix->d_barrier.p) + 16;
+                p.done_target = ix->done_target + (uint64_t)grid;
+            }
+            cudaError_t e = launch_query(p, mode, grid, stream);
+            if (e != cudaSuccess) return fail_cuda(e, "fused_query launch");
+            if (p.fuse_merge) ix->barrier_target = p.barrier_target;
+            if (will_publish) ix->done_target = p.done_target;
+            ix->kernel_launches++;
+        } else {
+            will_publish = false;
+        }
+        if (hits && hits->published) *hits->published = will_publish;
+        if (ix->timing) CK(cudaEventRecord(tl.e1, stream));
+        if (!p.fuse_merge) {
+            CK(launch_merge(p, mode, stream));
+            ix->kernel_launches++;
+        }
+        if (ix->timing) {
+            CK(cudaEventRecord(tl.e2, stream));
+            ix->timed_used.push_back(tl);
+        }
     }
 
     bigsi_b200_info &s = ix->stats;
@@ -548,7 +639,8 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
     s.last_kmers_per_stage = p.kmers_per_stage;
     s.last_n_stages = p.n_stages;
     s.last_n_slices = p.n_slices;
-    s.last_fused = (p.fuse_merge ? 1u : 0u) | (p.prehash ? 2u : 0u) | (p.solo ? 4u : 0u);
+    s.last_fused = (p.fuse_merge ? 1u : 0u) | (p.prehash ? 2u : 0u) | (p.solo ? 4u : 0u) | (p.stream ? 8u : 0u);
+    s.last_reduce_grid = (uint32_t)reduce_grid;
     return 0;
 }
 
@@ -661,11 +753,17 @@ int bigsi_b200_index_create(int device, uint64_t num_rows, uint64_t num_cols, ui
     e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = ix->d_barrier.reserve(256);
     if (e == cudaSuccess) e = cudaMemsetAsync(ix->d_barrier.p, 0, 256, ix->stream);
+    if (e == cudaSuccess) e = ix->d_stream.reserve(kStreamStateBytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ix->d_stream.p, 0, kStreamStateBytes, ix->stream);
+    if (e == cudaSuccess) e = ix->h_status.reserve(64);
+    if (e == cudaSuccess) memset(ix->h_status.p, 0, 64);
     if (e == cudaSuccess) e = cudaMemsetAsync(ix->matrix, 0, bytes, ix->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
     if (e != cudaSuccess) {
         cudaFree(ix->matrix);
         ix->d_barrier.release();
+        ix->d_stream.release();
+        ix->h_status.release();
         if (ix->stream) cudaStreamDestroy(ix->stream);
         delete ix;
         return fail_cuda(e, "index initialisation");
@@ -682,10 +780,11 @@ int bigsi_b200_index_destroy(bigsi_b200_index *ix)
     cudaDeviceSynchronize();
     for (auto &t : ix->timed_free) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
     for (auto &t : ix->timed_used) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
-    DevBuf *bufs[] = {&ix->d_seq, &ix->d_table, &ix->d_pool, &ix->d_barrier, &ix->debug_ts, &ix->partial, &ix->d_kmers, &ix->d_rows, &ix->d_qoff, &ix->d_out, &ix->d_min,
+    DevBuf *bufs[] = {&ix->stream_partial, &ix->d_stream, &ix->d_hits_ring, &ix->d_seq, &ix->d_table, &ix->d_pool, &ix->d_barrier, &ix->debug_ts, &ix->partial, &ix->d_kmers, &ix->d_rows, &ix->d_qoff, &ix->d_out, &ix->d_min,
                       &ix->d_nhits, &ix->d_bloom, &ix->d_planted};
     for (DevBuf *b : bufs) b->release();
     ix->h_small.release();
+    ix->h_status.release();
     ix->h_sink.release();
     ix->h_kmers.release();
     if (ix->matrix) cudaFree(ix->matrix);
@@ -731,6 +830,8 @@ int bigsi_b200_index_set_option(bigsi_b200_index *ix, const char *key, int64_t v
     else if (!strcmp(key, "solo")) ix->opt_solo = value;
     else if (!strcmp(key, "zero_copy")) ix->opt_zero_copy = value;
     else if (!strcmp(key, "cooperative")) ix->opt_cooperative = value;
+    else if (!strcmp(key, "inputs_ready")) ix->opt_inputs_ready = value;
+    else if (!strcmp(key, "spin_timeout_ms")) ix->opt_spin_timeout_ms = value < 1 ? 1 : value;
     else if (!strcmp(key, "pool_pct")) ix->opt_pool_pct = value > 100 ? 100 : value;
     else return fail(BIGSI_B200_ERR_INVALID, "unknown option '%s'", key);
     return 0;
@@ -1145,6 +1246,7 @@ static int search_one_published(bigsi_b200_index *ix, const char *d_kmers, uint6
     ho.total_dev = total_dev;
     ho.scrub = scrub;
     ho.scrub_words = scrub_words;
+    ho.inputs_ready = total_dev == nullptr;  // host-written (or staged before this call) k-mers: nothing in the stream produces them
     ho.n_sinks = 1;
     ho.sinks[0] = static_cast<unsigned long long *>(d_blk);
     ho.sink_spec = (uint32_t)spec;
@@ -1159,15 +1261,18 @@ static int search_one_published(bigsi_b200_index *ix, const char *d_kmers, uint6
     if (published) {
         // poll the sequence word; look at the stream now and then so that a failed launch cannot hang us
         uint64_t spins = 0;
-        while (blk[0] != ho.sink_seq) {
+        while (__atomic_load_n(&blk[0], __ATOMIC_ACQUIRE) != ho.sink_seq) {
             if ((++spins & 0x3fff) == 0) {
+                if (const unsigned long long av = abort_state(ix)) return fail_aborted(av);
                 e = cudaStreamQuery(ix->stream);
                 if (e != cudaErrorNotReady) {
                     if (e != cudaSuccess) return fail_cuda(e, "query kernel");
-                    if (blk[0] != ho.sink_seq) return fail(BIGSI_B200_ERR_CUDA, "query kernel finished without publishing its result");
+                    if (__atomic_load_n(&blk[0], __ATOMIC_ACQUIRE) != ho.sink_seq)
+                        return fail(BIGSI_B200_ERR_CUDA, "query kernel finished without publishing its result");
                 }
             }
         }
+        // (acquire load above: the payload behind the sequence word is read after it, also on weakly ordered hosts)
         n = blk[1];
         if (total_out) *total_out = total_dev ? blk[2 + spec] : total;
         const uint64_t m = n < cap ? n : cap;
@@ -1685,11 +1790,10 @@ int bigsi_b200_exchange_create(bigsi_b200_index *ix, int world, int rank, uint64
     ex.rank = rank;
     ex.spec = spec;
     ex.max_kmer_bytes = max_kmer_bytes;
-    ex.kmers_off = kExFlags * 8;
     ex.kmers_stride = round_up(max_kmer_bytes + 64, 256);
-    ex.ll_off = ex.kmers_off + kExInboxes * ex.kmers_stride;  // LL inboxes: every data byte takes two (hash.cuh:ll_store_line)
+    ex.ll_off = 0;  // LL inboxes: every data byte takes two (hash.cuh:ll_store_line)
     ex.sinks_off = ex.ll_off + kExInboxes * 2 * ex.kmers_stride;
-    ex.block_bytes = round_up(16 + 8ull * spec, 128);
+    ex.block_bytes = round_up(16 + 8ull * spec + 8, 128);
     ex.total_bytes = ex.sinks_off + kExGenerations * world * ex.block_bytes;
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ex.local), ex.total_bytes);
     if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(exchange)");
@@ -1765,28 +1869,43 @@ int bigsi_b200_exchange_destroy(bigsi_b200_index *ix)
     return 0;
 }
 
-// slot `rank` of generation seq % 3 in shard r's result blocks: where this shard's hits of query `seq` go
+// slot `rank` of generation seq % kExGenerations in shard r's result blocks: where this shard's hits of query `seq` go
 static unsigned long long *exchange_slot(const Exchange &ex, int r, uint64_t seq)
 {
     return reinterpret_cast<unsigned long long *>(ex.peer[r] + ex.sinks_off +
                                                   ((seq % kExGenerations) * ex.world + ex.rank) * ex.block_bytes);
 }
+static const uint8_t *exchange_blocks(const Exchange &ex, uint64_t seq)
+{
+    return ex.local + ex.sinks_off + (seq % kExGenerations) * ex.world * ex.block_bytes;
+}
 
+// One query of a column-sharded search: a streamed launch on every rank.  Rank 0's gather kernel pushes the k-mer
+// bytes into the peers' LL inboxes, the peers' gather kernels hash out of theirs; every rank's reduce kernel
+// publishes its hits into slot `rank` of every rank's result blocks and finishes when all slots of its own copy
+// carry this query's number.
 static int exchange_search(bigsi_b200_index *ix, const char *d_kmers, uint64_t n_kmers, int k, int h, uint32_t min_kmers,
-                           cudaStream_t stream, bool pipelined)
+                           cudaStream_t stream)
 {
     Exchange &ex = ix->ex;
     if (!ex.local || !ex.ready) return fail(BIGSI_B200_ERR_INVALID, "exchange not created / peers not opened");
     if (k < 1 || h < 1 || n_kmers == 0) return fail(BIGSI_B200_ERR_INVALID, "k, h and the number of k-mers must be positive");
     if (n_kmers * (uint64_t)k > ex.max_kmer_bytes) return fail(BIGSI_B200_ERR_RANGE, "query larger than the exchange inbox");
     if (ex.rank == 0 && (!d_kmers || (reinterpret_cast<uintptr_t>(d_kmers) & 15)))
-        return fail(BIGSI_B200_ERR_INVALID, "rank 0 needs the k-mers in a 16-byte aligned device buffer");
+        return fail(BIGSI_B200_ERR_INVALID, "rank 0 needs the k-mers in a 16-byte aligned device-addressable buffer");
     if (ix->num_cols == 0) return fail(BIGSI_B200_ERR_INVALID, "empty shard");
     cudaError_t e;
-    if ((e = ix->d_nhits.reserve(8 + 8ull * ex.spec + 16)) != cudaSuccess) return fail_cuda(e, "staging");
+    const uint64_t hit_slot = round_up(8 + 8ull * ex.spec + 16, 256);
+    if (hit_slot * kStreamStates > ix->d_hits_ring.cap) {
+        CK(cudaStreamSynchronize(stream));
+        if ((e = ix->d_hits_ring.reserve(hit_slot * kStreamStates)) != cudaSuccess) return fail_cuda(e, "staging");
+    }
+    // the exchange counts its own queries (the same number on every rank: it picks the inbox, the result generation
+    // and the LL flag); ring slots of the handle follow the handle's streamed launch number, which advances at least
+    // as fast, so the entry gate of the streamed path also covers the reuse of inboxes and generations
     const uint64_t seq = ex.seq + 1;
     const uint64_t inbox = seq % kExInboxes;
-    uint8_t *dev = static_cast<uint8_t *>(ix->d_nhits.p);
+    uint8_t *dev = static_cast<uint8_t *>(ix->d_hits_ring.p) + ((ix->stream_seq + 1) % kStreamStates) * hit_slot;
     HitsOut ho;
     ho.n = reinterpret_cast<unsigned long long *>(dev);
     ho.cols = reinterpret_cast<int32_t *>(dev + 8);
@@ -1794,57 +1913,36 @@ static int exchange_search(bigsi_b200_index *ix, const char *d_kmers, uint64_t n
     ho.cap = ex.spec;
     ho.by_value = true;
     ho.min_value = min_kmers;
-    ho.require_fused = true;
+    ho.require_stream = true;
+    ho.inputs_ready = ix->opt_inputs_ready != 0;
     ho.sink_spec = ex.spec;
     ho.sink_seq = seq;
-    ho.ll.flag = (uint32_t)seq ? (uint32_t)seq : 0x80000000u;  // an LL inbox is reused every second query: never 0, never the old value
+    ho.ll.flag = (uint32_t)seq ? (uint32_t)seq : 0x80000000u;  // an LL inbox is reused every kExInboxes queries: never 0, never the old value
     auto ll_inbox = [&](int r) { return reinterpret_cast<uint4 *>(ex.peer[r] + ex.ll_off + inbox * 2 * ex.kmers_stride); };
-    // lock-step: publish at the end of the kernel, then wait for this query's blocks.  Pipelined: no publication at
-    // the end (the NEXT kernel's prologue, or the drain, sends this query's hits); wait for the previous query's blocks
-    ho.n_sinks = pipelined ? 0u : (uint32_t)ex.world;
-    ho.gather_first = pipelined;
-    ho.gather_seq = pipelined ? seq - 1 : seq;
-    ho.n_gather = pipelined && seq == 1 ? 0u : (uint32_t)ex.world;
-    const uint64_t ggen = ho.gather_seq % kExGenerations;
+    ho.n_sinks = (uint32_t)ex.world;
+    ho.gather_seq = seq;
+    ho.n_gather = (uint32_t)ex.world;
+    const uint8_t *blocks = exchange_blocks(ex, seq);
     for (int r = 0; r < ex.world; ++r) {
         ho.sinks[r] = exchange_slot(ex, r, seq);
-        ho.gather_blocks[r] =
-            reinterpret_cast<const unsigned long long *>(ex.local + ex.sinks_off + (ggen * ex.world + r) * ex.block_bytes);
-    }
-    if (ex.published_seq < ex.seq) {  // the previous query was pipelined: this kernel's prologue publishes its hits
-        ho.n_pub = (uint32_t)ex.world;
-        ho.pub_seq = ex.seq;
-        for (int r = 0; r < ex.world; ++r) ho.pub_sinks[r] = exchange_slot(ex, r, ex.seq);
+        ho.gather_blocks[r] = reinterpret_cast<const unsigned long long *>(blocks + r * ex.block_bytes);
     }
     const char *kmers = d_kmers;
     if (ex.rank == 0) {
-        for (int r = 1; r < ex.world; ++r) {
-            ho.push_kmers[ho.n_push] = ex.peer[r] + ex.kmers_off + inbox * ex.kmers_stride;
-            ho.push_flags[ho.n_push] = reinterpret_cast<unsigned long long *>(ex.peer[r]);
-            ho.ll.out[ho.n_push] = ll_inbox(r);
-            ++ho.n_push;
-        }
-        ho.push_value = seq;
+        for (int r = 1; r < ex.world; ++r) ho.ll.out[ho.n_push++] = ll_inbox(r);
     } else {
-        ho.wait_flag = reinterpret_cast<const unsigned long long *>(ex.local);
-        ho.wait_value = seq;
-        ho.wait_per_cta = 1;
-        kmers = reinterpret_cast<const char *>(ex.local + ex.kmers_off + inbox * ex.kmers_stride);
+        kmers = nullptr;  // hashed out of the inbox; the address only fixes the line numbering (see below)
         ho.ll.in = ll_inbox(ex.rank);
     }
+    // a peer's "k-mer array" starts at line 0 of its inbox: any 16-byte aligned non-null base does (never dereferenced)
+    if (!kmers) kmers = reinterpret_cast<const char *>(ex.local);
     bool published = false;
     ho.published = &published;
     if (int rc = run_query(ix, BIGSI_B200_MODE_COUNTS, nullptr, kmers, k, nullptr, 1, n_kmers, n_kmers, h, nullptr, 0, stream, &ho))
         return rc;
-    if (!pipelined && !published) return fail(BIGSI_B200_ERR_INVALID, "the launch could not publish its result");
-    ex.published_seq = pipelined ? ex.seq : seq;  // everything up to the previous query (pipelined) / this one is out
+    if (!published) return fail(BIGSI_B200_ERR_INVALID, "the launch could not publish its result");
     ex.seq = seq;
     return 0;
-}
-
-static const void *exchange_blocks(const Exchange &ex, uint64_t seq)
-{
-    return ex.local + ex.sinks_off + (seq % kExGenerations) * ex.world * ex.block_bytes;
 }
 
 int bigsi_b200_exchange_search_dev(bigsi_b200_index *ix, const char *d_kmers, uint64_t n_kmers, int k, int h,
@@ -1852,54 +1950,30 @@ int bigsi_b200_exchange_search_dev(bigsi_b200_index *ix, const char *d_kmers, ui
 {
     if (int rc = check_index(ix)) return rc;
     DeviceGuard guard(ix->device);
-    if (int rc = exchange_search(ix, d_kmers, n_kmers, k, h, min_kmers, static_cast<cudaStream_t>(stream), false)) return rc;
+    if (int rc = exchange_search(ix, d_kmers, n_kmers, k, h, min_kmers, static_cast<cudaStream_t>(stream))) return rc;
     if (d_blocks_out) *d_blocks_out = exchange_blocks(ix->ex, ix->ex.seq);
     if (block_bytes_out) *block_bytes_out = ix->ex.block_bytes;
     return 0;
 }
 
-int bigsi_b200_exchange_search_pipelined_dev(bigsi_b200_index *ix, const char *d_kmers, uint64_t n_kmers, int k, int h,
-                                             uint32_t min_kmers, void *stream, const void **d_prev_blocks_out,
-                                             uint64_t *block_bytes_out)
+int bigsi_b200_exchange_wait_ns(bigsi_b200_index *ix, uint64_t *wait_ns_out, uint64_t *queries_out)
 {
     if (int rc = check_index(ix)) return rc;
+    if (!wait_ns_out) return fail(BIGSI_B200_ERR_INVALID, "null pointer");
     DeviceGuard guard(ix->device);
-    if (int rc = exchange_search(ix, d_kmers, n_kmers, k, h, min_kmers, static_cast<cudaStream_t>(stream), true)) return rc;
-    if (d_prev_blocks_out) *d_prev_blocks_out = ix->ex.seq >= 2 ? exchange_blocks(ix->ex, ix->ex.seq - 1) : nullptr;
-    if (block_bytes_out) *block_bytes_out = ix->ex.block_bytes;
+    CK(cudaDeviceSynchronize());
+    unsigned long long v = 0;
+    CK(cudaMemcpy(&v, static_cast<uint8_t *>(ix->d_stream.p) + 128, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemset(static_cast<uint8_t *>(ix->d_stream.p) + 128, 0, 8));
+    *wait_ns_out = v;
+    if (queries_out) *queries_out = ix->stream_seq;
     return 0;
 }
 
-int bigsi_b200_exchange_drain_dev(bigsi_b200_index *ix, void *stream, const void **d_blocks_out, uint64_t *block_bytes_out)
+int bigsi_b200_index_status(bigsi_b200_index *ix)
 {
     if (int rc = check_index(ix)) return rc;
-    Exchange &ex = ix->ex;
-    if (!ex.local || !ex.ready) return fail(BIGSI_B200_ERR_INVALID, "exchange not created / peers not opened");
-    if (d_blocks_out) *d_blocks_out = nullptr;
-    if (block_bytes_out) *block_bytes_out = ex.block_bytes;
-    if (ex.seq == 0) return 0;
-    DeviceGuard guard(ix->device);
-    const uint8_t *base = static_cast<const uint8_t *>(exchange_blocks(ex, ex.seq));
-    QueryParams p;
-    memset(&p, 0, sizeof p);
-    uint8_t *dev = static_cast<uint8_t *>(ix->d_nhits.p);  // the hit buffers every exchange search of this handle uses
-    p.n_hits = reinterpret_cast<unsigned long long *>(dev);
-    p.hit_cols = reinterpret_cast<int32_t *>(dev + 8);
-    p.hit_counts = reinterpret_cast<uint32_t *>(dev + 8 + 4ull * ex.spec);
-    p.hit_cap = ex.spec;
-    p.sink_spec = ex.spec;
-    if (ex.published_seq < ex.seq) {
-        p.n_pub = (uint32_t)ex.world;
-        p.pub_seq = ex.seq;
-        for (int r = 0; r < ex.world; ++r) p.pub_sinks[r] = exchange_slot(ex, r, ex.seq);
-    }
-    p.n_gather = (uint32_t)ex.world;
-    p.gather_seq = ex.seq;
-    for (int r = 0; r < ex.world; ++r) p.gather_blocks[r] = reinterpret_cast<const unsigned long long *>(base + r * ex.block_bytes);
-    CK(launch_exchange_drain(p, static_cast<cudaStream_t>(stream)));
-    ex.published_seq = ex.seq;
-    ix->kernel_launches++;
-    if (d_blocks_out) *d_blocks_out = base;
+    if (const unsigned long long av = abort_state(ix)) return fail_aborted(av);
     return 0;
 }
 

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ptx.cuh"
+
 namespace bigsi {
 
 __device__ __forceinline__ uint32_t comp_base(uint32_t b)
@@ -137,15 +139,8 @@ __device__ __forceinline__ void ll_store_line(uint4 *dst, const uint4 &v, uint32
     asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(v.x), "r"(flag), "r"(v.y), "r"(flag) : "memory");
     asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 1), "r"(v.z), "r"(flag), "r"(v.w), "r"(flag) : "memory");
 }
-__device__ __forceinline__ uint4 ll_load_line(const uint4 *src, uint32_t flag)
-{
-    uint4 p, q;
-    do {
-        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(p.x), "=r"(p.y), "=r"(p.z), "=r"(p.w) : "l"(src) : "memory");
-        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(src + 1) : "memory");
-    } while (p.y != flag || p.w != flag || q.y != flag || q.w != flag);
-    return make_uint4(p.x, p.z, q.x, q.z);
-}
+struct LlRoute;
+__device__ __forceinline__ uint4 ll_load_line(const uint4 *src, const LlRoute &route);
 
 // Route of a query's k-mer bytes in a column-sharded search: rank 0 stores every 16-byte line of the k-mer
 // array into every peer's LL inbox (out[0..n_push)); a peer reads its k-mers from its own inbox `in`.
@@ -157,7 +152,22 @@ struct LlRoute {
     const uint8_t *kmers_base; // address line 0 corresponds to (16-byte aligned)
     uint32_t flag;             // low 32 bits of the query's sequence number (never 0)
     uint4 *out[8];             // rank 0: the peers' LL inboxes
+    // the wait for a line is bounded (ptx.cuh:bounded_wait): a sender that never launches must not hang this GPU
+    unsigned long long *abort_word, *host_abort;
+    unsigned long long timeout_ns, seq;
 };
+// A line is re-read until all four flags match; gives up (abort word raised, data undefined) after timeout_ns.
+__device__ __forceinline__ uint4 ll_load_line(const uint4 *src, const LlRoute &route)
+{
+    uint4 p, q;
+    const uint32_t flag = route.flag;
+    bounded_wait(route.abort_word, route.host_abort, route.timeout_ns, /*kAbortInbox*/ 3u, route.seq, [&]() {
+        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(p.x), "=r"(p.y), "=r"(p.z), "=r"(p.w) : "l"(src) : "memory");
+        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(src + 1) : "memory");
+        return p.y == flag && p.w == flag && q.y == flag && q.w == flag;
+    });
+    return make_uint4(p.x, p.z, q.x, q.z);
+}
 
 // Synchronisation of a hashing group: the whole CTA (id 0), a subset of warps on a named barrier
 // (id > 0, nthreads a multiple of 32), or one warp (nthreads == 32).  A runtime choice on purpose: the
@@ -210,7 +220,7 @@ static __device__ __noinline__ void hash_kmers_group(const uint8_t *g0, uint32_t
         const uint64_t line0 = (uint64_t)(reinterpret_cast<const uint8_t *>(a0) - route->kmers_base) >> 4;
         for (uint32_t i = tid; i < nvec; i += nthreads) {
             const uint64_t line = line0 + i;
-            sv[i] = ll_load_line(route->in + 2 * line, route->flag);
+            sv[i] = ll_load_line(route->in + 2 * line, *route);
         }
     }
     sync();

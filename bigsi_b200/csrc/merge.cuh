@@ -99,6 +99,35 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, uint32_t lane)
     return x;
 }
 
+// The hit list of query 0 (n_hits, hit_cols, hit_counts) -> every sink block: payload, system-scope fence, then
+// {sequence word, number of hits} as ONE 16-byte release store, so the block header is never seen torn.
+// Every thread of the CTA must call it.
+__device__ __forceinline__ void publish_hits(const QueryParams &P, unsigned long long *const *sinks, uint32_t n_sinks,
+                                             unsigned long long seq)
+{
+    const unsigned long long n = *reinterpret_cast<volatile unsigned long long *>(P.n_hits);
+    unsigned long long m = n < P.hit_cap ? n : P.hit_cap;
+    if (m > P.sink_spec) m = P.sink_spec;
+    for (uint32_t sidx = 0; sidx < n_sinks; ++sidx) {
+        int32_t *dc = reinterpret_cast<int32_t *>(sinks[sidx] + 2);
+        uint32_t *dv = reinterpret_cast<uint32_t *>(dc + P.sink_spec);
+        for (uint32_t i = threadIdx.x; i < (uint32_t)m; i += blockDim.x) {
+            dc[i] = __ldcg(P.hit_cols + i);
+            dv[i] = __ldcg(P.hit_counts + i);
+        }
+    }
+    if (P.total_dev && threadIdx.x < n_sinks)  // the query's k-mer count was determined on the device: report it
+        sinks[threadIdx.x][2 + P.sink_spec] = __ldcg(P.total_dev);
+    // ONE system-scope fence per sink on the critical path: the CTA barrier orders every thread's payload
+    // stores before the publishing thread's fence (fences are cumulative -- the same pattern grid-wide barriers
+    // rely on), and the header store behind the fence can then be a plain one
+    __syncthreads();
+    if (threadIdx.x < n_sinks) {
+        __threadfence_system();
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(sinks[threadIdx.x]), "l"(seq), "l"(n) : "memory");
+    }
+}
+
 // Stage `bytes` (a multiple of 16) from global to shared memory with bulk async copies issued by warp 0
 // and wait for them.  Every thread of the CTA must call it; `phase` is the CTA-uniform parity of `mbar`.
 __device__ __forceinline__ void merge_stage_region(const QueryParams &P, uint8_t *dst, const uint8_t *src, uint32_t bytes,

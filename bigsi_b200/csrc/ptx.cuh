@@ -120,6 +120,58 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads)
 {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// Sticky error word of a handle: the first bounded wait that times out stores (query number << 8 | code) in the
+// device word and in its mapped host mirror; every later kernel of the handle exits at once when it sees it.
+__device__ __forceinline__ void raise_abort(unsigned long long *abort_word, unsigned long long *host_abort, uint32_t code,
+                                            unsigned long long seq)
+{
+    if (!abort_word) return;
+    const unsigned long long v = (seq << 8) | code;
+    if (atomicCAS(abort_word, 0ull, v) == 0ull && host_abort) {
+        *reinterpret_cast<volatile unsigned long long *>(host_abort) = v;
+        __threadfence_system();
+    }
+}
+// Spin until cond() holds, but never longer than timeout_ns and never past an abort raised by somebody else.
+// Returns false when it gave up (after raising the abort word with `code`): the caller carries on with whatever
+// it has -- results of an aborted handle are never reported, the host turns the abort word into an error code.
+template <typename Cond>
+__device__ __forceinline__ bool bounded_wait(unsigned long long *abort_word, unsigned long long *host_abort,
+                                             unsigned long long timeout_ns, uint32_t code, unsigned long long seq, Cond cond)
+{
+    if (cond()) return true;
+    unsigned long long t0 = 0;
+    for (uint32_t spins = 1;; ++spins) {
+        if (cond()) return true;
+        if ((spins & 255u) == 0) {
+            if (abort_word && ld_volatile_u64(abort_word) != 0ull) return false;
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > timeout_ns) {
+                raise_abort(abort_word, host_abort, code, seq);
+                return false;
+            }
+        }
+    }
+}
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p)
 {
     unsigned long long v;

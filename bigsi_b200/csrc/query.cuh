@@ -20,8 +20,29 @@ constexpr int kSegPlanes = 16;
 constexpr int kMaxH = 1024;
 constexpr int kPoolMaxH = 8;   // the solo path pools k-mers only for h <= 8 (row-id stash in the smem header)
 constexpr int kMaxSinks = 9;   // host + up to 8 GPUs of one box
+// "streamed" single-query launches: the gather kernel of query s+1 overlaps the reduce
+// kernel of query s, so everything a query owns rotates: big buffers (partial planes, pooled row ids, the
+// front-end's table) over kStreamRing queries, the small state blocks over kStreamStates
+constexpr int kStreamRing = 4;
+constexpr int kStreamStates = 8;
+constexpr int kReduceThreads = 128;           // threads of a reduce-kernel CTA (it shares its SM with a gather CTA)
+constexpr int kReduceSmemBytes = 32 * 1024;   // its dynamic shared memory
+constexpr int kSmBytes = 228 * 1024;          // shared memory of one SM; every resident CTA reserves 1 KB of it
 
 enum { kModeCounts = 0, kModeAnd = 1 };
+
+// Per-query state block of a streamed launch (64 bytes).  All zero when its query starts: the reduce kernel of
+// query s clears the block of query s + kStreamRing before it advances the completion word.
+struct QState {
+    unsigned int pool_claims;       // claim counter of the k-mer pool (gather kernel)
+    unsigned int reduce_arrivals;   // reduce-kernel CTAs that have finished their merge items
+    unsigned long long n_unique;    // sequence front-end: unique windows found by the gather kernel's CTAs
+    unsigned long long wait_ns;     // diagnostics: time the reduce kernel's last CTA waited for the other shards
+    unsigned long long pad[5];
+};
+static_assert(sizeof(QState) == 64, "QState is one 64-byte block");
+// error codes a kernel leaves in the abort word when a bounded wait times out (sticky; see bounded_wait)
+enum { kAbortGate = 1, kAbortPool = 2, kAbortInbox = 3, kAbortPeers = 4, kAbortChain = 5 };
 
 // Work space of one launch: items = (column tile, global k-mer index), k-mer fastest.  It is cut
 // into n_slices equal slices of items_per_slice (<= 65535); CTA b owns the contiguous slices
@@ -99,44 +120,45 @@ struct QueryParams {
     // single-query extras ------------------------------------------------------------------------
     uint32_t min_by_value;    // 1: threshold = min_kmers_value (no device array to read)
     uint32_t min_kmers_value;
-    // input gate: spin until *wait_flag >= wait_value before the k-mers are read (the query may live in
-    // a peer GPU's or the host's memory and be published there by somebody else)
-    const unsigned long long *wait_flag;
-    unsigned long long wait_value;
-    uint32_t wait_per_cta;    // 1: CTA b waits on wait_flag[b] (its own slice of the k-mers was pushed by a peer's CTA b)
-    // query broadcast fused into the prologue (rank 0 of a column-sharded search): CTA b copies ITS slice of
-    // the k-mer bytes into every peer's inbox (NVLink stores) and then raises the peer's flag b
-    uint32_t n_push;
-    uint8_t *push_kmers[kMaxSinks];            // peers' inbox k-mer bytes (same offsets as `kmers`)
-    unsigned long long *push_flags[kMaxSinks]; // peers' per-CTA inbox flags
-    unsigned long long push_value;
-    // solo path: the same broadcast without fences or flags ("low-latency" lines, hash.cuh:ll_store_line) --
-    // rank 0's consumer threads store their CTA's slice into every peer's LL inbox before they hash it; the
-    // peers' hashing reads its k-mer bytes from its own LL inbox and spins per 16-byte line on the embedded flag
-    LlRoute ll;                  // hash.cuh: who sends which segment of the k-mer bytes to whom
-    // result publication: after the merge phase the LAST CTA copies the hit list of query 0 to every
-    // sink -- a block [0] = sequence flag, [1] = number of hits, then int32 cols[sink_spec], uint32
-    // counts[sink_spec] -- in this GPU's, a peer GPU's (NVLink) or the host's (mapped pinned) memory
+    // query broadcast of a column-sharded search (streamed launches only): rank 0's producer warp stores its CTA's
+    // slice of the k-mer bytes into every peer's LL inbox ("low-latency" lines, hash.cuh:ll_store_line: no fence,
+    // no flag); the peers' hashing reads its k-mer bytes from its own LL inbox and spins per 16-byte line
+    uint32_t n_push;          // rank 0: number of peers (ll.out[0 .. n_push))
+    LlRoute ll;               // hash.cuh: who sends the k-mer bytes to whom
+    // result publication: after the merge the LAST CTA (of the reduce kernel, or of the generic kernel's merge
+    // phase) copies the hit list of query 0 to every sink -- a block [0] = sequence flag, [1] = number of hits,
+    // then int32 cols[sink_spec], uint32 counts[sink_spec] -- in this GPU's, a peer GPU's (NVLink) or the
+    // host's (mapped pinned) memory
     uint32_t n_sinks;
     uint32_t sink_spec;
     unsigned long long sink_seq;
     unsigned long long *sinks[kMaxSinks];
-    unsigned long long *done_counter;   // monotonic; the CTA that brings it to done_target is the last
+    unsigned long long *done_counter;   // generic kernel: monotonic; the CTA that brings it to done_target is the last
     unsigned long long done_target;
-    // all-gather completion: after publishing, the last CTA waits until these LOCAL blocks (the slots the
-    // peers publish into) carry sink_seq too, so that stream order implies "all shards have reported"
+    // all-gather completion: after publishing, the last CTA of the reduce kernel waits (bounded) until these LOCAL
+    // blocks (the slots the peers publish into) carry gather_seq too, so that stream order implies "all shards
+    // have reported".  The next query's gather kernel is already running by then: the wait costs no bandwidth.
     uint32_t n_gather;
-    const unsigned long long *gather_blocks[kMaxSinks];
-    // pipelined variant (gather_first): nothing is published at the end of the kernel.  The hit list of the
-    // PREVIOUS query (still in hit_cols / hit_counts / n_hits) is published from THIS kernel's prologue by its
-    // last CTA (pub_sinks, sequence pub_seq), where the NVLink latency overlaps the gather; the blocks waited
-    // for are those of the previous query (gather_seq), polled by CTA 0 behind the grid barrier while the
-    // other CTAs merge.  Kernel completion then implies "the previous query is complete on this shard".
-    uint32_t gather_first;
     unsigned long long gather_seq;
-    uint32_t n_pub;
-    unsigned long long pub_seq;
-    unsigned long long *pub_sinks[kMaxSinks];
+    const unsigned long long *gather_blocks[kMaxSinks];
+    // streamed launch (solo geometry, fuse_merge == 0): no grid barrier and no wait for the preceding kernel.  The
+    // gather kernel flushes its planes and exits; reduce_kernel (merge_kernels.cu) merges, thresholds and publishes
+    // while the NEXT query's gather kernel already runs on the same SMs.
+    uint32_t stream;
+    uint32_t stream_wait_inputs;         // 1: the k-mers may be produced by the preceding kernel of the stream: wait for it
+    unsigned long long stream_seq;       // number of this query among the handle's streamed launches (1-based)
+    unsigned long long *stream_done;     // device word: every streamed query <= *stream_done is completely reduced
+    QState *qstate;                      // this query's state block
+    QState *qstate_next;                 // the block of query stream_seq + kStreamRing (cleared by the reduce kernel)
+    unsigned long long *abort_word;      // device word, non-zero once a bounded wait has timed out (sticky)
+    unsigned long long *host_abort;      // its mirror in mapped host memory
+    unsigned long long spin_timeout_ns;  // bound of every device-side wait
+    unsigned long long *wait_ns_out;     // diagnostics: the reduce kernel adds the time it waited for the other shards
+    double seq_threshold;                // sequence front-end: min_kmers = ceil(n_unique * seq_threshold)
+    uint32_t seq_mode;                   // 1: `kmers` is a SEQUENCE of total_kmers + k - 1 bytes; windows are de-duplicated in the kernel
+    unsigned long long *seq_table;       // its open-addressing table (seq_table_entries x u64, a power of two)
+    uint64_t seq_table_entries;
+    uint32_t seq_epoch;                  // 16-bit epoch that marks live table entries (stale ones count as empty)
     uint32_t plain_launch;    // 1: launch WITHOUT the cooperative attribute (option "cooperative" = 0): the grid barrier
                               // then relies on grid <= resident CTA capacity alone; lets PDL start the next grid's CTAs early
     uint32_t debug_flags;     // bit 0: consumers skip the AND/count work (pure-gather ceiling measurement)
@@ -192,6 +214,8 @@ cudaError_t launch_query(const QueryParams &p, int mode, int grid, cudaStream_t 
 inline uint64_t prehash_bytes_per_kmer(uint32_t k) { return (uint64_t)k + 1 + 4ull * ((((uint64_t)k + 3) >> 2) | 1); }
 // Stage 2: sum (or AND) the partial planes of every (query, column), expand to integers -> p.out.
 cudaError_t launch_merge(const QueryParams &p, int mode, cudaStream_t stream);
+// Stage 2 of a streamed launch (p.stream): merge + threshold + publication + completion chain, `grid` CTAs.
+cudaError_t launch_reduce(const QueryParams &p, int mode, int grid, cudaStream_t stream);
 cudaError_t query_kernels_init();  // opt-in to large dynamic shared memory
 // drain of the pipelined exchange (uses n_hits/hit_*/sink_spec, n_pub/pub_*, n_gather/gather_* of p)
 cudaError_t launch_exchange_drain(const QueryParams &p, cudaStream_t stream);

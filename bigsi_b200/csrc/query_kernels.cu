@@ -101,9 +101,10 @@ struct SegIter {
 // ------------------------------------------------------------------------------------------
 // bit-sliced vertical counter: 128 columns x 16 bits per thread
 // ------------------------------------------------------------------------------------------
-constexpr int kHiPlanes = kSegPlanes - 3;  // planes of weight 8 .. 2^15
-
+// NP = most planes a segment may need (registers: 4 x (NP + 3) words of state per thread)
+template <int NP>
 struct VCounter {
+    static constexpr int kHiPlanes = NP - 3;  // planes of weight 8 .. 2^(NP-1)
     W4 ones, twos, fours;  // accumulators of weight 1, 2, 4
     W4 p0, p1, p2;         // pending operands waiting for a partner at each level
     W4 hi[kHiPlanes];
@@ -172,13 +173,14 @@ __device__ __forceinline__ void stg128(void *p, const W4 &x)
 // slot_unit + b * plane_stride (plane_stride = merge_cb, see partial_offset).  All planes_per_slot
 // planes are written (planes the segment cannot reach are zero in the counter), so the merge loads
 // them without looking at segment lengths.
-__device__ __forceinline__ void flush_planes(const VCounter &c, uint32_t pps, uint8_t *slot_unit, uint32_t plane_stride)
+template <int NP>
+__device__ __forceinline__ void flush_planes(const VCounter<NP> &c, uint32_t pps, uint8_t *slot_unit, uint32_t plane_stride)
 {
     stg128(slot_unit, c.ones);
     if (pps > 1) stg128(slot_unit + plane_stride, c.twos);
     if (pps > 2) stg128(slot_unit + 2 * (size_t)plane_stride, c.fours);
 #pragma unroll
-    for (int b = 0; b < kHiPlanes; ++b)
+    for (int b = 0; b < VCounter<NP>::kHiPlanes; ++b)
         if (b + 3 < (int)pps) stg128(slot_unit + (size_t)(b + 3) * plane_stride, c.hi[b]);
 }
 
@@ -268,7 +270,7 @@ __device__ __forceinline__ void tma_consumer(const QueryParams &P, const uint8_t
     const uint32_t stage_bytes = G * h * seg_stride;
     uint32_t stage = 0, parity = 0;
 
-    VCounter ctr;
+    VCounter<kSegPlanes> ctr;
     W4 acc;
     SegIter it(P, begin, end);
     Seg s;
@@ -336,12 +338,20 @@ __device__ __forceinline__ void tma_consumer(const QueryParams &P, const uint8_t
 }
 
 // ------------------------------------------------------------------------------------------
-// "solo" path: one query, one tile, one slice per CTA, k-mers hashed in the kernel (QueryParams::solo)
+// "solo" path = STREAMED single-query launch: one query, one tile, one slice per CTA, k-mers hashed in the
+// kernel.  gather_solo hashes, gathers, ANDs, counts, writes its CTA's bit planes and exits -- no grid barrier,
+// no merge phase.  reduce_kernel (merge_kernels.cu) follows in the stream and merges / thresholds / publishes;
+// both are launched with programmatic dependent launch and the gather kernel does NOT wait for its predecessor,
+// so the gather CTAs of query s+1 take over each SM the moment the gather CTA of query s leaves it, while the
+// reduce kernel of query s (128 threads, 32 KB of shared memory per CTA: it fits beside a gather CTA) runs
+// concurrently.  Everything a query owns rotates (query.cuh:kStreamRing); the gate at kernel entry makes query s
+// wait until query s - kStreamRing is completely reduced (normally long ago: one L2 read).
 // ------------------------------------------------------------------------------------------
 constexpr int kBarHashGroup = 1;   // named barrier of the consumer warps while they hash
 constexpr int kBarIdsReady = 2;    // consumers -> producer: the id table is complete
 constexpr uint32_t kStageCntOffset = 640;  // uint32 [kMaxStages] k-mers per ring slot, in the shared-memory header
 constexpr uint32_t kPoolStashOffset = 768; // int32 [kPoolBatch][kPoolMaxH] row ids of one claimed pool batch
+constexpr uint32_t kGateOffset = 528;      // int: 1 = the entry gate passed (behind the 2 x kMaxStages mbarriers)
 constexpr int kPoolBatch = 8;
 
 struct SoloGeom {
@@ -419,7 +429,8 @@ __device__ __forceinline__ void solo_producer(const QueryParams &P, const SoloGe
         // flight and the consumer warps are still hashing, so this warp has nothing else to do.  This CTA's slice
         // of the k-mer bytes (the 16-byte lines that cover it; neighbouring CTAs write identical lines at the
         // boundaries) goes into every peer's LL inbox over NVLink -- plain stores with the flag embedded: no fence
-        // (which would also wait for the bulk copies in flight), nothing to wait for
+        // (which would also wait for the bulk copies in flight), nothing to wait for.  The inbox was last used by
+        // query seq - kStreamRing, which every shard has finished (the entry gate).
         const uint64_t b0 = sg.begin * P.k, b1 = (sg.begin + sg.cnt) * P.k;
         const uint64_t l0 = b0 >> 4, nvec = ((b1 + 15) >> 4) - l0;
         const uint4 *src = reinterpret_cast<const uint4 *>(P.kmers) + l0;
@@ -466,8 +477,8 @@ __device__ __forceinline__ void solo_producer(const QueryParams &P, const SoloGe
         }
         if (base + n >= pool_total) exhausted = true;
         if (real)
-            while (ld_acquire_gpu_u64(P.pool_ready + owner) < P.pool_epoch) {
-            }
+            bounded_wait(P.abort_word, P.host_abort, P.spin_timeout_ns, kAbortPool, P.stream_seq,
+                         [&]() { return ld_acquire_gpu_u64(P.pool_ready + owner) >= P.pool_epoch; });
         const uint32_t real_mask = __ballot_sync(0xffffffffu, real);
         for (uint32_t t0 = 0; t0 < n * h; t0 += 32) {  // warp-uniform trip count (shuffles inside)
             const uint32_t t = t0 + lane;
@@ -494,7 +505,7 @@ __device__ __forceinline__ void solo_producer(const QueryParams &P, const SoloGe
     }
 }
 
-template <int MODE, int HC>
+template <int MODE, int HC, int NP>
 __device__ __forceinline__ void solo_consumer(const QueryParams &P, const SoloGeom &sg, uint8_t *smem, const uint8_t *ring,
                                               int32_t *ids, uint8_t *scratch, uint64_t *full, uint64_t *empty)
 {
@@ -527,7 +538,7 @@ __device__ __forceinline__ void solo_consumer(const QueryParams &P, const SoloGe
 
     const bool active = unit * 16 < tw;
     const uint32_t nhi = P.planes_per_slot > 3 ? P.planes_per_slot - 3 : 0;
-    VCounter ctr;
+    VCounter<NP> ctr;
     W4 acc;
     if (MODE == kModeCounts) ctr.reset();
     else acc = W4{{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}};
@@ -585,37 +596,55 @@ __device__ __forceinline__ void solo_consumer(const QueryParams &P, const SoloGe
     if (unit == 0) BIGSI_TS(4);
 }
 
-// The hit list of query 0 (n_hits, hit_cols, hit_counts) -> every sink block: payload, system-scope fence, then
-// {sequence word, number of hits} as ONE 16-byte release store, so the block header is never seen torn.
-// Every thread of the CTA must call it.
-__device__ __forceinline__ void publish_hits(const QueryParams &P, unsigned long long *const *sinks, uint32_t n_sinks,
-                                             unsigned long long seq)
+template <int MODE, int HC, int NP>
+__global__ void __launch_bounds__(kMaxBlockThreads, 1) gather_solo(const __grid_constant__ QueryParams P)
 {
-    const unsigned long long n = *reinterpret_cast<volatile unsigned long long *>(P.n_hits);
-    unsigned long long m = n < P.hit_cap ? n : P.hit_cap;
-    if (m > P.sink_spec) m = P.sink_spec;
-    for (uint32_t sidx = 0; sidx < n_sinks; ++sidx) {
-        int32_t *dc = reinterpret_cast<int32_t *>(sinks[sidx] + 2);
-        uint32_t *dv = reinterpret_cast<uint32_t *>(dc + P.sink_spec);
-        for (uint32_t i = threadIdx.x; i < (uint32_t)m; i += blockDim.x) {
-            dc[i] = __ldcg(P.hit_cols + i);
-            dv[i] = __ldcg(P.hit_counts + i);
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *empty = full + kMaxStages;
+    int32_t *ids = reinterpret_cast<int32_t *>(smem + kSmemHeaderBytes);
+    uint8_t *ring = smem + kSmemHeaderBytes + P.ids_bytes;
+    volatile int *s_gate = reinterpret_cast<volatile int *>(smem + kGateOffset);
+    const uint32_t consumer_warps = (blockDim.x >> 5) - 1;
+
+    // the dependents (this query's reduce kernel, the next query's gather kernel, ...) may be scheduled as soon
+    // as every CTA of this grid has started: they only become resident where resources are free
+    grid_launch_dependents();
+    if (threadIdx.x == 0) {
+        BIGSI_TS(0);
+        for (uint32_t s = 0; s < P.n_stages; ++s) {
+            mbar_init(&full[s], 1);                // one arrive.expect_tx by the producer + tx bytes
+            mbar_init(&empty[s], consumer_warps);  // one arrive per consumer warp
         }
+        fence_barrier_init();
     }
-    if (P.total_dev && threadIdx.x < n_sinks)  // the query's k-mer count was determined on the device: report it
-        sinks[threadIdx.x][2 + P.sink_spec] = __ldcg(P.total_dev);
-    // ONE system-scope fence per sink on the critical path: the CTA barrier orders every thread's payload
-    // stores before the publishing thread's fence (fences are cumulative -- the same pattern grid-wide barriers
-    // rely on), and the header store behind the fence can then be a plain one
+    if (threadIdx.x == 32) {
+        // entry gate: the buffers of this query's ring slot were last used by query seq - kStreamRing, whose
+        // reduce kernel must have finished (it also cleared our state block); a handle that has aborted stays dead
+        bool ok = ld_volatile_u64(P.abort_word) == 0ull;
+        if (ok && P.stream_seq > (unsigned long long)kStreamRing)
+            ok = bounded_wait(P.abort_word, P.host_abort, P.spin_timeout_ns, kAbortGate, P.stream_seq,
+                              [&]() { return ld_acquire_gpu_u64(P.stream_done) + kStreamRing >= P.stream_seq; });
+        *s_gate = ok ? 1 : 0;
+    }
     __syncthreads();
-    if (threadIdx.x < n_sinks) {
-        __threadfence_system();
-        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(sinks[threadIdx.x]), "l"(seq), "l"(n) : "memory");
-    }
+    if (!*s_gate) return;
+    // the k-mers may come out of the preceding kernel of the stream (query front-end, a caller's kernel): wait for
+    // it.  Otherwise nothing this kernel reads or writes depends on its predecessor.
+    if (P.stream_wait_inputs) grid_dependency_wait();
+    if (threadIdx.x == 0) BIGSI_TS(8);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && P.n_hits != nullptr) P.n_hits[0] = 0ull;  // the reduce kernel adds to it
+
+    const SoloGeom sg = solo_geometry(P);
+    uint8_t *scratch = smem + kSmemHeaderBytes + P.ids_table_bytes;
+    if ((threadIdx.x >> 5) == consumer_warps)
+        solo_producer(P, sg, smem, ring, ids, scratch, full, empty);
+    else
+        solo_consumer<MODE, HC, NP>(P, sg, smem, ring, ids, scratch, full, empty);
 }
 
-// grid-wide barrier over a monotonic arrival counter (all CTAs of the launch are co-resident: the
-// kernel is launched cooperatively with at most one CTA per SM)
+// grid-wide barrier over a monotonic arrival counter (all CTAs of the launch are co-resident: the generic kernel
+// is launched cooperatively with at most one CTA per SM whenever it merges in the kernel)
 __device__ __forceinline__ void grid_barrier(unsigned long long *counter, unsigned long long target)
 {
     __syncthreads();
@@ -631,7 +660,8 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *counter, unsign
     __syncthreads();
 }
 
-template <int MODE, int HC, bool SOLO>
+// generic path: any number of queries / tiles / slices; row ids or k-mers hashed in the prologue
+template <int MODE, int HC>
 __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_constant__ QueryParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -644,7 +674,6 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
 
     if (threadIdx.x == 0) {
         BIGSI_TS(0);
-        if (P.debug_ts) P.debug_ts[(size_t)blockIdx.x * kDebugStamps + 14] = (unsigned long long)clock64();
         for (uint32_t s = 0; s < P.n_stages; ++s) {
             mbar_init(&full[s], 1);                // one arrive.expect_tx by the producer + tx bytes
             mbar_init(&empty[s], consumer_warps);  // one arrive per consumer warp
@@ -659,26 +688,9 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
     grid_dependency_wait();
     if (threadIdx.x == 0) BIGSI_TS(8);
 
-    if (P.n_pub) {
-        // pipelined exchange: the previous query's hit list is still in the hit buffers; the LAST CTA (whose
-        // k-mer range is the short remainder) sends it to every shard now, then clears the counter
-        if (blockIdx.x == gridDim.x - 1) {
-            publish_hits(P, P.pub_sinks, P.n_pub, P.pub_seq);
-            if (threadIdx.x == 0) P.n_hits[0] = 0ull;
-        }
-    } else if (P.n_hits != nullptr) {  // hit counters of the fused threshold (stage 2 adds to them)
+    if (P.n_hits != nullptr) {  // hit counters of the fused threshold (stage 2 adds to them)
         for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < P.n_queries; q += gridDim.x * blockDim.x)
             P.n_hits[q] = 0ull;
-    }
-    if (P.gather_first && blockIdx.x == gridDim.x - 1 && threadIdx.x < P.n_gather) {
-        // pipelined exchange: every shard has published the PREVIOUS query's hits (from the prologue of its own
-        // kernel of THIS query, unconditionally and BEFORE it waits here itself, so this cannot deadlock).  Polled
-        // by the last CTA, whose k-mer range is the short remainder; kernel completion then implies "the
-        // previous query is complete on this shard".
-        unsigned long long seen;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(P.gather_blocks[threadIdx.x]) : "memory");
-        } while (seen != P.gather_seq);
     }
 
     const uint64_t span = (uint64_t)P.slices_per_cta * P.items_per_slice;
@@ -687,59 +699,18 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
     if (end > P.total_items) end = P.total_items;
     const bool have_work = begin < end;
 
-    // k-mers this CTA hashes itself (prehash geometry: one tile, one slice per CTA)
-    const uint64_t kb = (uint64_t)blockIdx.x * P.items_per_slice;
-    const uint32_t kcnt = (P.prehash && kb < P.total_kmers) ? (uint32_t)min((uint64_t)P.items_per_slice, P.total_kmers - kb) : 0u;
-    if (P.wait_flag != nullptr && (!P.wait_per_cta || kcnt) && !(SOLO && P.ll.in != nullptr)) {
-        // the query is published by another GPU / the host: wait for it (per CTA: for our own slice)
-        if (threadIdx.x == 0) {
-            const unsigned long long *flag = P.wait_flag + (P.wait_per_cta ? blockIdx.x : 0);
-            unsigned long long seen;
-            do {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
-            } while (seen < P.wait_value);
-        }
+    if (P.prehash && have_work) {
+        // n_tiles == 1 and one slice per CTA: this CTA's k-mers are [begin, end), contiguous in memory
+        hash_kmers_cooperative(P.kmers + begin * P.k, (uint32_t)(end - begin), (int)P.k, (int)P.h, P.num_rows, 1,
+                               smem + kSmemHeaderBytes + P.ids_table_bytes, ids, P.mod_magic);
         __syncthreads();
+        if (threadIdx.x == 0) BIGSI_TS(9);
     }
-    if (P.n_push && kcnt && !SOLO) {
-        // broadcast fused into the prologue (solo path: done by the producer warp, see solo_producer): push our slice of the k-mer bytes (16-byte lines that cover it;
-        // neighbouring CTAs write identical bytes into shared boundary lines) to every peer, then raise flag b
-        const uint64_t b0 = kb * P.k, b1 = (kb + kcnt) * P.k;
-        const uint64_t a0 = b0 & ~15ull, nvec = (((b1 + 15) & ~15ull) - a0) >> 4;
-        const uint4 *src = reinterpret_cast<const uint4 *>(P.kmers + a0);
-        for (uint64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
-            const uint4 v = __ldg(src + i);
-            for (uint32_t r = 0; r < P.n_push; ++r) reinterpret_cast<uint4 *>(P.push_kmers[r] + a0)[i] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence_system();
-            for (uint32_t r = 0; r < P.n_push; ++r)
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.push_flags[r] + blockIdx.x), "l"(P.push_value) : "memory");
-        }
-    }
-
-    if (SOLO) {
-        const SoloGeom sg = solo_geometry(P);
-        uint8_t *scratch = smem + kSmemHeaderBytes + P.ids_table_bytes;
+    if (have_work) {
         if ((threadIdx.x >> 5) == consumer_warps)
-            solo_producer(P, sg, smem, ring, ids, scratch, full, empty);
+            tma_producer(P, ring, ids, full, empty, begin, end);
         else
-            solo_consumer<MODE, HC>(P, sg, smem, ring, ids, scratch, full, empty);
-    } else {
-        if (P.prehash && have_work) {
-            // n_tiles == 1 and one slice per CTA: this CTA's k-mers are [begin, end), contiguous in memory
-            hash_kmers_cooperative(P.kmers + begin * P.k, (uint32_t)(end - begin), (int)P.k, (int)P.h, P.num_rows, 1,
-                                   smem + kSmemHeaderBytes + P.ids_table_bytes, ids, P.mod_magic);
-            __syncthreads();
-            if (threadIdx.x == 0) BIGSI_TS(9);
-        }
-        if (have_work) {
-            if ((threadIdx.x >> 5) == consumer_warps)
-                tma_producer(P, ring, ids, full, empty, begin, end);
-            else
-                tma_consumer<MODE, HC>(P, ring, full, empty, begin, end);
-        }
+            tma_consumer<MODE, HC>(P, ring, full, empty, begin, end);
     }
 
     if (P.fuse_merge) {
@@ -747,20 +718,10 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
         // merge work items; the drained ring is the scratch
         grid_barrier(P.barrier, P.barrier_target);
         if (threadIdx.x == 0) BIGSI_TS(6);
-        if (SOLO && blockIdx.x == 0 && threadIdx.x == 0) *P.pool_counter = 0u;  // every claim of this launch is done
-        if (P.scrub_words) {
-            // query front-end: its de-duplication table is dead once every CTA has read its k-mers; clear it for the
-            // next query here, where the stores overlap the merge (saves a memset node per query)
-            for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.scrub_words; i += (uint64_t)gridDim.x * blockDim.x)
-                P.scrub[i] = 0ull;
-        }
         uint32_t merge_phase = 0;
         for (uint64_t item = blockIdx.x; item < P.merge_items; item += gridDim.x)
             merge_item<MODE>(P, item, ring, merge_bar, merge_phase);
-        if (threadIdx.x == 0) {
-            BIGSI_TS(7);
-            if (P.debug_ts) P.debug_ts[(size_t)blockIdx.x * kDebugStamps + 15] = (unsigned long long)clock64();
-        }
+        if (threadIdx.x == 0) BIGSI_TS(7);
         if (P.n_sinks) {
             // the last CTA to finish its merge items publishes query 0's hit list to every sink
             int *s_last = reinterpret_cast<int *>(smem + 2 * kMaxStages * 8 + 64);  // header space behind the mbarriers
@@ -772,15 +733,6 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
             if (*s_last) {
                 __threadfence();
                 publish_hits(P, P.sinks, P.n_sinks, P.sink_seq);
-                // front-end words behind its table ({U}, {ticket, threshold}): every reader is done -- this CTA is
-                // the last one of the launch -- so they are re-armed here for the next query
-                if (P.scrub_words && threadIdx.x < 2) P.scrub[P.scrub_words + threadIdx.x] = 0ull;
-                if (!P.gather_first && threadIdx.x < P.n_gather) {  // all-gather: every shard's block has arrived here
-                    unsigned long long seen;
-                    do {
-                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(P.gather_blocks[threadIdx.x]) : "memory");
-                    } while (seen != P.gather_seq);
-                }
             }
         }
     }
@@ -792,10 +744,16 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
 template <int MODE, int HC>
 static cudaError_t launch_one(const QueryParams &p, int grid, cudaStream_t stream)
 {
-    if (p.solo)
-        return launch_ex(fused_query<MODE, HC, true>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream,
-                         /*pdl=*/true, /*cooperative=*/!p.plain_launch, p);
-    return launch_ex(fused_query<MODE, HC, false>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream,
+    if (p.solo) {
+        // streamed: plain launch with the programmatic-stream-serialization attribute (the kernel decides itself
+        // what it waits for); planes_per_slot <= 8 takes the variant with the small counter
+        if (MODE == kModeCounts && p.planes_per_slot > 8)
+            return launch_ex(gather_solo<MODE, HC, kSegPlanes>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream,
+                             /*pdl=*/true, /*cooperative=*/false, p);
+        return launch_ex(gather_solo<MODE, HC, 8>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream,
+                         /*pdl=*/true, /*cooperative=*/false, p);
+    }
+    return launch_ex(fused_query<MODE, HC>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream,
                      /*pdl=*/true, /*cooperative=*/p.fuse_merge != 0 && !p.plain_launch, p);
 }
 
@@ -806,39 +764,22 @@ cudaError_t launch_query(const QueryParams &p, int mode, int grid, cudaStream_t 
     return p.h == 3 ? launch_one<kModeAnd, 3>(p, grid, stream) : launch_one<kModeAnd, 0>(p, grid, stream);
 }
 
-// drain of the pipelined exchange: publishes the last query's hit list if no later kernel has done so, then
-// returns (in stream order) once every shard's block of that query has arrived (P.gather_blocks == P.gather_seq)
-__global__ void __launch_bounds__(256) exchange_drain_kernel(const __grid_constant__ QueryParams P)
-{
-    if (P.n_pub) publish_hits(P, P.pub_sinks, P.n_pub, P.pub_seq);
-    if (threadIdx.x < P.n_gather) {
-        unsigned long long seen;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(P.gather_blocks[threadIdx.x]) : "memory");
-        } while (seen != P.gather_seq);
-    }
-}
-
-cudaError_t launch_exchange_drain(const QueryParams &p, cudaStream_t stream)
-{
-    exchange_drain_kernel<<<1, 256, 0, stream>>>(p);
-    return cudaGetLastError();
-}
-
 cudaError_t query_kernels_init()
 {
     cudaError_t e;
 #define BIGSI_SET_SMEM(K)                                                                   \
     e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);  \
     if (e != cudaSuccess) return e;
-    BIGSI_SET_SMEM((fused_query<kModeCounts, 3, false>))
-    BIGSI_SET_SMEM((fused_query<kModeCounts, 3, true>))
-    BIGSI_SET_SMEM((fused_query<kModeCounts, 0, false>))
-    BIGSI_SET_SMEM((fused_query<kModeCounts, 0, true>))
-    BIGSI_SET_SMEM((fused_query<kModeAnd, 3, false>))
-    BIGSI_SET_SMEM((fused_query<kModeAnd, 3, true>))
-    BIGSI_SET_SMEM((fused_query<kModeAnd, 0, false>))
-    BIGSI_SET_SMEM((fused_query<kModeAnd, 0, true>))
+    BIGSI_SET_SMEM((fused_query<kModeCounts, 3>))
+    BIGSI_SET_SMEM((fused_query<kModeCounts, 0>))
+    BIGSI_SET_SMEM((fused_query<kModeAnd, 3>))
+    BIGSI_SET_SMEM((fused_query<kModeAnd, 0>))
+    BIGSI_SET_SMEM((gather_solo<kModeCounts, 3, 8>))
+    BIGSI_SET_SMEM((gather_solo<kModeCounts, 3, kSegPlanes>))
+    BIGSI_SET_SMEM((gather_solo<kModeCounts, 0, 8>))
+    BIGSI_SET_SMEM((gather_solo<kModeCounts, 0, kSegPlanes>))
+    BIGSI_SET_SMEM((gather_solo<kModeAnd, 3, 8>))
+    BIGSI_SET_SMEM((gather_solo<kModeAnd, 0, 8>))
 #undef BIGSI_SET_SMEM
     return merge_kernels_init();
 }

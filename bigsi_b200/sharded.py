@@ -58,6 +58,21 @@ class DeviceShard:
         self.device = torch.device("cuda", info["device"])
         self.cap = cap
         self._counts = None
+        # single-query searches are "streamed" (include/bigsi_b200.h): the gather kernel of the next query overlaps
+        # the reduce kernel of this one, so the output buffers of consecutive calls must differ -- a ring of 8
+        self._hit_ring = {}
+        self._hit_turn = 0
+
+    def _hit_buffer(self, n_queries):
+        t = self.torch
+        ring = self._hit_ring.get(n_queries)
+        if ring is None:
+            if len(self._hit_ring) > 4:
+                self._hit_ring.clear()
+            ring = [t.empty((n_queries * (2 + 2 * self.cap),), dtype=t.int32, device=self.device) for _ in range(8)]
+            self._hit_ring[n_queries] = ring
+        self._hit_turn = (self._hit_turn + 1) % 8
+        return ring[self._hit_turn]
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
@@ -98,10 +113,9 @@ class DeviceShard:
 
 
     def search_hits(self, rows, q_offsets, n_queries, min_kmers, max_query_kmers=0):
-        """Fused gather-AND-count + threshold (one C-ABI call, two kernels): same packed layout as
-        hits(); the full count vectors are never written."""
-        t = self.torch
-        buf = t.empty((n_queries * (2 + 2 * self.cap),), dtype=t.int32, device=self.device)
+        """Fused gather-AND-count + threshold (one C-ABI call): same packed layout as hits(); the full
+        count vectors are never written.  The returned buffer is one of a ring of 8."""
+        buf = self._hit_buffer(n_queries)
         base = buf.data_ptr()
         self.index.query_hits_dev(rows.data_ptr(), q_offsets.data_ptr(), n_queries, rows.shape[0], self.h,
                                   min_kmers.data_ptr(), base + 8 * n_queries,
@@ -111,11 +125,11 @@ class DeviceShard:
 
 
     def search_kmers_hits(self, kmers_u8, q_offsets, n_queries, min_kmers, max_query_kmers=0):
-        """The whole path in (normally) one kernel: raw k-mers uint8 [U, k] on the device ->
-        canonical + murmur3 in the kernel prologue -> gather-AND-count -> grid barrier -> merge +
-        threshold.  Same packed layout as hits()."""
-        t = self.torch
-        buf = t.empty((n_queries * (2 + 2 * self.cap),), dtype=t.int32, device=self.device)
+        """The whole path from raw k-mers uint8 [U, k] on the device: canonical + murmur3 in the kernel
+        prologue -> gather-AND-count -> merge + threshold (one query: gather kernel + overlapped reduce
+        kernel; a batch: one kernel with a grid barrier).  Same packed layout as hits(); the returned
+        buffer is one of a ring of 8 and stays valid for the next 7 calls."""
+        buf = self._hit_buffer(n_queries)
         base = buf.data_ptr()
         self.index.query_kmers_hits_dev(kmers_u8.data_ptr(), self.k, q_offsets.data_ptr(), n_queries, kmers_u8.shape[0],
                                         self.h, min_kmers.data_ptr(), base + 8 * n_queries,
@@ -132,11 +146,11 @@ class _DevArray:
 
 
 class FusedExchange:
-    """The two exchanges of a column-sharded single-query search done by the query kernel itself
-    (include/bigsi_b200.h "column-sharded search ... WITHOUT per-query collectives"): rank 0's kernel
-    pushes the k-mer bytes into the peers' inboxes over NVLink, every rank's kernel publishes its hits
-    into every rank's result blocks and waits for the others.  No NCCL call per query; torch.distributed
-    is only used once, to exchange the CUDA IPC handles."""
+    """The two exchanges of a column-sharded single-query search done by the query kernels themselves
+    (include/bigsi_b200.h "column-sharded search ... WITHOUT per-query collectives"): rank 0's gather kernel
+    pushes the k-mer bytes into the peers' inboxes over NVLink, every rank's reduce kernel publishes its hits
+    into every rank's result blocks and waits for the others while the next query's gather kernel already
+    runs.  No NCCL call per query; torch.distributed is only used once, to exchange the CUDA IPC handles."""
 
     def __init__(self, shard, world_size, rank, max_kmers, dist=None, peers=None):
         import ctypes
@@ -150,19 +164,16 @@ class FusedExchange:
         L = _lib.lib()
         handle = (ctypes.c_uint8 * 64)()
         _lib.check(L.bigsi_b200_exchange_create(shard.index.handle, world_size, rank, max_kmers * shard.k, self.spec, handle))
-        if world_size > 1:
-            if peers is not None:  # all shards live in this process (tests): plain peer access
-                self._pending_peers = peers
-            else:
-                gathered = [None] * world_size
-                dist.all_gather_object(gathered, bytes(handle))
-                blob = b"".join(gathered)
-                _lib.check(L.bigsi_b200_exchange_open(shard.index.handle, (ctypes.c_uint8 * len(blob)).from_buffer_copy(blob)))
-                dist.barrier()
+        if world_size > 1 and peers is None:
+            gathered = [None] * world_size
+            dist.all_gather_object(gathered, bytes(handle))
+            blob = b"".join(gathered)
+            _lib.check(L.bigsi_b200_exchange_open(shard.index.handle, (ctypes.c_uint8 * len(blob)).from_buffer_copy(blob)))
+            dist.barrier()
 
     @staticmethod
     def connect_local(exchanges):
-        """Same-process wiring of `world` FusedExchange objects (one per device)."""
+        """Same-process wiring of `world` FusedExchange objects (one per handle; the handles may share a device)."""
         import ctypes
 
         from . import _lib
@@ -175,35 +186,34 @@ class FusedExchange:
         if not ptr:
             return None
         view = self._views.get(ptr)
-        if view is None:  # three generations of result blocks rotate: build each torch view once
+        if view is None:  # eight generations of result blocks rotate: build each torch view once
             t = self.shard.torch
             blocks = t.as_tensor(_DevArray(ptr, (self.world, stride // 4), "<i4"), device=self.shard.device)
             view = blocks[:, 2 : 4 + 2 * self.spec]  # drop the sequence word: [n (2 x int32) | cols | counts]
             self._views[ptr] = view
         return view
 
-    def search(self, kmers_u8, n_kmers, min_kmers, pipelined=False):
-        """One query (rank 0's k-mers decide).  Returns int32 [world, 2 + 2*spec] (LOCAL colours), the
-        packed layout of DeviceShard.hits for one query; a view of library memory that stays valid until
-        the next-but-one search.  pipelined=True: the kernel does not wait for the other shards' hits of
-        THIS query; the return value is the complete result of the PREVIOUS query (None after the first
-        call) and drain() completes the last one."""
+    def search(self, kmers_u8, n_kmers, min_kmers, stream=None):
+        """One query (rank 0's k-mers decide; a device tensor, or any 16-byte aligned device-addressable
+        address as an int).  Returns int32 [world, 2 + 2*spec] (LOCAL colours), the packed layout of
+        DeviceShard.hits for one query: a view of library memory, complete in stream order, valid until four
+        more searches have been issued."""
         ct = self._ct
         ptr, stride = ct.c_void_p(0), ct.c_uint64(0)
-        d_k = kmers_u8.data_ptr() if (self.rank == 0 and kmers_u8 is not None) else 0
-        L = self._lib.lib()
-        fn = L.bigsi_b200_exchange_search_pipelined_dev if pipelined else L.bigsi_b200_exchange_search_dev
-        self._lib.check(fn(self.shard.index.handle, d_k, n_kmers, self.shard.k, self.shard.h, int(min_kmers),
-                           self.shard._stream(), ct.byref(ptr), ct.byref(stride)))
+        d_k = 0
+        if self.rank == 0 and kmers_u8 is not None:
+            d_k = kmers_u8 if isinstance(kmers_u8, int) else kmers_u8.data_ptr()
+        self._lib.check(self._lib.lib().bigsi_b200_exchange_search_dev(
+            self.shard.index.handle, d_k, n_kmers, self.shard.k, self.shard.h, int(min_kmers),
+            self.shard._stream() if stream is None else stream, ct.byref(ptr), ct.byref(stride)))
         return self._view(ptr.value, stride.value)
 
-    def drain(self):
-        """Completes the last pipelined query: its result view, valid in stream order."""
+    def wait_ns(self):
+        """(ns this rank's reduce kernels waited for the other shards since the last call, queries launched)."""
         ct = self._ct
-        ptr, stride = ct.c_void_p(0), ct.c_uint64(0)
-        self._lib.check(self._lib.lib().bigsi_b200_exchange_drain_dev(self.shard.index.handle, self.shard._stream(),
-                                                                       ct.byref(ptr), ct.byref(stride)))
-        return self._view(ptr.value, stride.value)
+        w, q = ct.c_uint64(0), ct.c_uint64(0)
+        self._lib.check(self._lib.lib().bigsi_b200_exchange_wait_ns(self.shard.index.handle, ct.byref(w), ct.byref(q)))
+        return w.value, q.value
 
     def close(self):
         self._lib.lib().bigsi_b200_exchange_destroy(self.shard.index.handle)
@@ -236,13 +246,10 @@ class ShardedSearcher:
             self.fused = FusedExchange(shard, world_size, rank, fused_max_kmers, dist=dist)
             self.fused_max_kmers = fused_max_kmers
 
-    def search_one_fused(self, kmers_u8, n_kmers, min_kmers, pipelined=False):
+    def search_one_fused(self, kmers_u8, n_kmers, min_kmers):
         """Single query through the in-kernel exchange; min_kmers is a host integer.  Same result layout
-        as search_step for one query.  pipelined=True returns the PREVIOUS query's result (FusedExchange.search)."""
-        return self.fused.search(kmers_u8, n_kmers, min_kmers, pipelined)
-
-    def drain_fused(self):
-        return self.fused.drain()
+        as search_step for one query (FusedExchange.search)."""
+        return self.fused.search(kmers_u8, n_kmers, min_kmers)
 
     def search_step(self, kmers_u8, q_offsets, min_kmers, n_queries, max_query_kmers=0):
         """One batched search: rank 0's k-mers decide; returns the packed hit buffers of all ranks,

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BIGSI_B200_ABI_VERSION 5
+#define BIGSI_B200_ABI_VERSION 6
 
 enum {
     BIGSI_B200_OK = 0,
@@ -35,7 +35,9 @@ enum {
     BIGSI_B200_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
     BIGSI_B200_ERR_OOM = -3,       /* device or pinned-host allocation failed */
     BIGSI_B200_ERR_NO_DEVICE = -4, /* no usable CUDA device */
-    BIGSI_B200_ERR_RANGE = -5      /* row / column / capacity out of range */
+    BIGSI_B200_ERR_RANGE = -5,     /* row / column / capacity out of range */
+    BIGSI_B200_ERR_TIMEOUT = -6    /* a bounded device-side wait timed out (a peer shard never launched, ...): the
+                                      handle is unusable afterwards; every later call on it returns this code */
 };
 
 /* query modes */
@@ -63,8 +65,9 @@ typedef struct {
     uint32_t last_tile_bytes, last_n_tiles, last_kmers_per_stage, last_n_stages, last_n_slices;
     uint64_t kernel_launches;        /* cumulative count of kernels this handle has launched          */
     uint64_t scratch_bytes;          /* partial-plane workspace currently allocated                   */
-    uint32_t last_fused;             /* bit 0: merge ran inside the fused kernel, bit 1: k-mers hashed in it */
-    uint32_t reserved;
+    uint32_t last_fused;             /* bit 0: merge ran inside the fused kernel, bit 1: k-mers hashed in it,
+                                        bit 3: streamed launch (gather kernel + reduce kernel)                */
+    uint32_t last_reduce_grid;       /* CTAs of the reduce kernel of a streamed launch (else 0)               */
 } bigsi_b200_info;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -87,17 +90,24 @@ int bigsi_b200_index_get_info(const bigsi_b200_index *index, bigsi_b200_info *in
  * "n_stages", "ctas_per_sm", "merge_chunk_bytes", "debug_flags"; "prehash" / "fuse_merge" / "solo" /
  * "zero_copy" (default 1; 0 forces the separate hash / merge kernels, the generic single-query
  * path, the staged host copies); "pool_pct" (default 12: share of a query's k-mers that the CTAs
- * claim dynamically); "cooperative" (default 0: the single-kernel path is launched WITHOUT the cooperative
- * attribute -- its grid barrier is safe because the plan keeps the grid within the resident-CTA capacity and a
- * stream's grids become resident in order, and programmatic dependent launch can then start the next query's
- * CTAs while the previous query's last CTAs finish, 2 us per query; 1 = cooperative launch, which makes the
- * driver verify co-residency); "timing" (1 = bracket the fused kernel and the merge kernel of every query
- * launch with CUDA events, read back with bigsi_b200_index_timing_collect). */
+ * claim dynamically); "cooperative" (default 1: a generic-path kernel that merges behind its own grid barrier is
+ * launched with the cooperative attribute, so the driver verifies that all its CTAs are co-resident; 0 = plain
+ * launch, only safe when nothing else runs on the device); "inputs_ready" (default 0; 1 = the k-mer buffers handed
+ * to the `_dev` single-query entry points are never produced by the kernel that precedes the call in the stream
+ * -- e.g. they are resident, or were copied in -- so a streamed query does not wait for its predecessor and
+ * consecutive queries overlap fully); "spin_timeout_ms" (default 10000: bound of every device-side wait, see
+ * BIGSI_B200_ERR_TIMEOUT); "timing" (1 = bracket the gather / fused kernel and the reduce / merge kernel of every
+ * query launch with CUDA events, read back with bigsi_b200_index_timing_collect; serialises the launches). */
 int bigsi_b200_index_set_option(bigsi_b200_index *index, const char *key, int64_t value);
 /* Synchronises, sums the event-timed durations recorded since the last collect and resets them.
  * fused_ms = fused gather-AND-count kernel, merge_ms = merge kernel, n = query launches timed. */
 int bigsi_b200_index_timing_collect(bigsi_b200_index *index, double *fused_ms_out, double *merge_ms_out,
                                     uint64_t *n_out);
+
+/* 0, or BIGSI_B200_ERR_TIMEOUT (with the reason in bigsi_b200_last_error) once a device-side wait of this handle
+ * has timed out.  Host calls that wait for a result check it themselves; callers of the stream-ordered `_dev`
+ * entry points use this after synchronising their stream. */
+int bigsi_b200_index_status(bigsi_b200_index *index);
 
 /* Debug aid: with option "debug_flags" bit 1 set, every CTA of the fused kernel records 8 uint64
  * globaltimer stamps (ns) of its last launch; this copies the first n_words of them to the host. */
@@ -153,10 +163,11 @@ int bigsi_b200_query_hits_dev(bigsi_b200_index *index, const int32_t *d_rows, co
                               uint64_t cap, uint64_t *d_n_out, uint32_t *d_counts_full, uint64_t counts_stride,
                               void *stream);
 
-/* The whole search path of a batch in (normally) ONE kernel: raw unique k-mers (n*k ASCII, device)
- * are canonicalised and hashed in the kernel prologue, rows gathered/ANDed/counted, and after a
- * grid-wide barrier the same kernel merges and thresholds.  Falls back to hash kernel + fused kernel
- * + merge kernel when the launch geometry does not allow it.  Outputs as bigsi_b200_query_hits_dev. */
+/* The whole search path from raw unique k-mers (n*k ASCII, device): canonicalised and hashed in the kernel
+ * prologue, rows gathered/ANDed/counted, merged and thresholded.  One query: a streamed launch (see "streamed
+ * single-query launches" below).  A batch: one kernel that merges behind a grid-wide barrier (cooperative
+ * launch), or hash kernel + fused kernel + merge kernel when the launch geometry does not allow that.
+ * Outputs as bigsi_b200_query_hits_dev. */
 int bigsi_b200_query_kmers_hits_dev(bigsi_b200_index *index, const char *d_kmers, int k, const int64_t *d_q_offsets,
                                     uint64_t n_queries, uint64_t total_kmers, uint64_t max_query_kmers, int h,
                                     const uint32_t *d_min_kmers, int32_t *d_cols_out, uint32_t *d_counts_out,
@@ -251,31 +262,46 @@ int bigsi_b200_file_info(const char *path, bigsi_b200_file_header *header_out, v
 int bigsi_b200_index_load_rows(bigsi_b200_index *index, const char *path, uint64_t file_offset, uint64_t file_stride,
                                uint64_t src_byte_offset, uint64_t row0, uint64_t n_rows);
 
-/* ---- column-sharded search over several GPUs WITHOUT per-query collectives ------------------
+/* ---- streamed single-query launches -----------------------------------------------------------
+ * A single query whose k-mers are hashed in the kernel (one column tile, up to ~200 000 k-mers) runs as TWO
+ * kernels: a gather kernel (hash, row gather, AND, vertical count; one CTA per SM) and a small reduce kernel
+ * (merge, threshold, publication).  Both carry the programmatic-dependent-launch attribute and the gather
+ * kernel does not wait for its predecessor, so the gather kernel of query s+1 runs while the reduce kernel of
+ * query s works on the same SMs; there is no grid-wide barrier and nothing needs a cooperative launch.  Scratch
+ * rotates over 4 queries.  Consequences for callers of the `_dev` entry points:
+ *   - output buffers (hit lists, counts) handed to one single-query call must not be handed to any of the next
+ *     3 single-query calls on the same handle unless another operation of the stream lies in between;
+ *   - results are complete in stream order after the call, as usual;
+ *   - see option "inputs_ready".
+ *
+ * ---- column-sharded search over several GPUs WITHOUT per-query collectives ------------------
  * The reference has no distributed path; sample columns are independent (graph/index.py:42-80,
  * graph/bigsi.py:192-230), so shard g holds all rows of its column range on its own GPU and a
  * query needs two exchanges: the query itself to every shard, the per-shard hits back.  Both are
- * fused into the query kernel: rank 0's kernel stores the k-mer bytes into its peers' inboxes over
+ * fused into the query kernels: rank 0's gather kernel stores the k-mer bytes into its peers' inboxes over
  * NVLink as "low-latency lines" (every 8 bytes carry 4 data bytes and the query's 32-bit sequence
- * number, so the receiving kernel spins per 16-byte line and no fence or separate flag is needed;
- * row tiles wider than one column tile use plain stores + per-CTA flags instead), every rank's
- * kernel publishes its hit list into slot `rank` of every rank's result blocks and finishes only
- * when all slots of its own copy have arrived (all-gather semantics in stream order).  Do not
- * interleave other searches on the same handle with a pipelined sequence before its drain (they
- * share the handle's hit buffers).  One handle per GPU; handles may live in
- * different processes (CUDA IPC) or in one (open_local).  Calls are SPMD: every rank calls
- * exchange_search_dev once per query with the same n_kmers / k / h / min_kmers.
+ * number, so the receiving kernel spins per 16-byte line and no fence or separate flag is needed);
+ * every rank's reduce kernel publishes its hit list into slot `rank` of every rank's result blocks and
+ * finishes only when all slots of its own copy have arrived (all-gather semantics in stream order) --
+ * while the next query's gather kernel is already streaming rows, so the shards do not wait for each
+ * other on the critical path.  Every device-side wait is bounded ("spin_timeout_ms"): a rank whose peers
+ * never launch gets BIGSI_B200_ERR_TIMEOUT instead of a hung GPU.  One handle per GPU; handles may live in
+ * different processes (CUDA IPC) or in one (open_local; they may even share a device).  Calls are SPMD:
+ * every rank calls exchange_search_dev once per query with the same n_kmers / k / h / min_kmers.
  *
  * create: allocates this rank's block; ipc_handle_out (64 bytes, may be NULL) is what the other
  *         processes pass to open.  spec = hits one result block holds (longer hit lists are cut,
  *         the count stays exact); max_kmer_bytes = largest query (n_kmers * k).
  * open / open_local: map the peers' blocks (handles: world x 64 bytes in rank order; peers: world
  *         handles of the same process).
- * search_dev: d_kmers = n_kmers * k raw unique k-mers on rank 0's device, 16-byte aligned (ignored
- *         on other ranks).  *d_blocks_out = device pointer to `world` result blocks of
- *         *block_bytes_out bytes each, block r = { u64 seq; u64 n_hits; int32 cols[spec]; uint32
- *         counts[spec] } with LOCAL column ids of shard r; valid in stream order after the call and
- *         until the next-but-one search on this handle (three generations of blocks rotate). */
+ * search_dev: d_kmers = n_kmers * k raw unique k-mers, 16-byte aligned, addressable by rank 0's device
+ *         (device memory or mapped pinned host memory; ignored on other ranks).  *d_blocks_out = device
+ *         pointer to `world` result blocks of *block_bytes_out bytes each, block r = { u64 seq; u64
+ *         n_hits; int32 cols[spec]; uint32 counts[spec] } with LOCAL column ids of shard r; valid in
+ *         stream order after the call and until 4 more searches have been issued on this handle (eight
+ *         generations of blocks rotate).
+ * wait_ns: synchronises the device; returns (and resets) the sum over the queries since the last call of
+ *         the time this rank's reduce kernel waited for the other shards' hit lists (diagnostics). */
 int bigsi_b200_exchange_create(bigsi_b200_index *index, int world, int rank, uint64_t max_kmer_bytes, uint32_t spec,
                                uint8_t *ipc_handle_out);
 int bigsi_b200_exchange_open(bigsi_b200_index *index, const uint8_t *ipc_handles);
@@ -283,19 +309,7 @@ int bigsi_b200_exchange_open_local(bigsi_b200_index *index, bigsi_b200_index *co
 int bigsi_b200_exchange_search_dev(bigsi_b200_index *index, const char *d_kmers, uint64_t n_kmers, int k, int h,
                                    uint32_t min_kmers, void *stream, const void **d_blocks_out,
                                    uint64_t *block_bytes_out);
-/* Pipelined variant: the kernel of query s does not publish at its end; the LAST CTA of the kernel of
- * query s+1 publishes query s's hit list from its prologue (where the NVLink latency overlaps the gather)
- * and then waits for every shard's publication of query s, so consecutive queries overlap across the
- * shards (a shard runs at the pace of its own kernel instead of kernel + two NVLink latencies).
- * *d_prev_blocks_out = the complete result blocks of the PREVIOUS query (NULL after the first call),
- * valid in stream order after this call and until the next-but-one call on this handle; consume them
- * (e.g. copy them out on the same stream) before that.  bigsi_b200_exchange_drain_dev completes the
- * LAST query: it returns its blocks once (in stream order) every shard has published them. */
-int bigsi_b200_exchange_search_pipelined_dev(bigsi_b200_index *index, const char *d_kmers, uint64_t n_kmers, int k,
-                                             int h, uint32_t min_kmers, void *stream, const void **d_prev_blocks_out,
-                                             uint64_t *block_bytes_out);
-int bigsi_b200_exchange_drain_dev(bigsi_b200_index *index, void *stream, const void **d_blocks_out,
-                                  uint64_t *block_bytes_out);
+int bigsi_b200_exchange_wait_ns(bigsi_b200_index *index, uint64_t *wait_ns_out, uint64_t *queries_out);
 int bigsi_b200_exchange_destroy(bigsi_b200_index *index);
 
 #ifdef __cplusplus

@@ -2,6 +2,7 @@
 oracle (oracle/) and the committed golden fixtures generated from the unmodified reference.
 Everything here is bit-exact (integer / byte work)."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -492,7 +493,7 @@ def test_single_query_zero_copy_path(B, pinned):
                 cols, vals, n = ix.search_kmers_hits(arr, k, h, [thr], cap=64)[0]
                 assert n == len(exp) and len(cols) == min(64, len(exp))
                 assert all(cnt[c] == v and v >= thr for c, v in zip(cols, vals))
-            assert ix.info()["last_fused"] & 1
+            assert ix.info()["last_fused"] & 8  # streamed launch: gather kernel + reduce kernel
             # same answers from the staged path
             ix.set_option("zero_copy", 0)
             thr = int(math.ceil(n_kmers * 0.7))
@@ -534,69 +535,41 @@ def test_solo_path_geometries(B, opts):
 
 
 # ---------------------------------------------------------------------------
-# multi-GPU: broadcast + all-gather fused into the query kernel (needs >= 2 GPUs)
+# column-sharded search: query broadcast + hit all-gather fused into the query kernels
 # ---------------------------------------------------------------------------
-def test_fused_exchange_two_shards_one_process(B):
+def _make_shards(B, world, m, part, k, h, cap, packed, max_kmers, opts=None):
+    """`world` column shards of `part` columns each, one handle per shard, wired through plain peer access
+    inside this process.  Shard g lives on device g % device_count: on a box with fewer GPUs than shards several
+    handles share a device (each with its own stream), which exercises the same protocol."""
     import torch
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    from bigsi_b200.sharded import DeviceShard, FusedExchange, merge_shard_hits, unpack_hits
+    from bigsi_b200.sharded import DeviceShard, FusedExchange
 
-    rng = np.random.default_rng(47)
-    m, N, k, h, cap = 10_007, 6000, 31, 3, 256
-    rb = (N + 7) // 8
-    rows = rng.random((m, rb * 8)) < 0.93
-    rows[:, N:] = False
-    packed = np.packbits(rows, axis=1)
-    oix = O.OracleIndex(k, m, h, N, rows=packed)
-    half = 3000  # multiple of 8
-    shards, exs = [], []
-    for g in range(2):
-        ix = B.DeviceIndex(m, half, col_offset=g * half, device=g)
-        ix.upload_rows(0, packed, src_byte_offset=g * half // 8)
+    ndev = torch.cuda.device_count()
+    shards, exs, streams = [], [], []
+    for g in range(world):
+        ix = B.DeviceIndex(m, part, col_offset=g * part, device=g % ndev)
+        ix.upload_rows(0, packed, src_byte_offset=g * part // 8)
+        for key, val in (opts or {}).items():
+            ix.set_option(key, val)
         shards.append(DeviceShard(ix, k, h, cap=cap))
-    for g in range(2):
-        exs.append(FusedExchange(shards[g], 2, g, 12_000, peers=True))
+        streams.append(torch.cuda.Stream(device=g % ndev))
+    for g in range(world):
+        exs.append(FusedExchange(shards[g], world, g, max_kmers, peers=True))
     FusedExchange.connect_local(exs)
-    try:
-        for step, n_kmers in enumerate((1, 60, 700, 5000, 9000, 333)):
-            arr = _rand_kmers(rng, n_kmers, k)
-            cnt = oix.counts(_kmer_strs(arr))
-            thr = int(math.ceil(n_kmers * 0.8))
-            d_k = torch.from_numpy(arr).to(shards[0].device)
-            # rank 1 first: its kernel waits for rank 0's push
-            with torch.cuda.device(1):
-                g1 = exs[1].search(None, n_kmers, thr)
-            with torch.cuda.device(0):
-                g0 = exs[0].search(d_k, n_kmers, thr)
-            torch.cuda.synchronize(0)
-            torch.cuda.synchronize(1)
-            exp = np.nonzero(cnt >= thr)[0]
-            for g in (g0, g1):  # both ranks hold both shards' hits (all-gather)
-                n, cols, vals = unpack_hits(g.cpu().numpy(), 1, cap)
-                assert int(n[:, 0].sum()) == len(exp), (step, n_kmers)
-                if (n[:, 0] <= cap).all():
-                    gc, gv = merge_shard_hits(n[:, 0], cols[:, 0], vals[:, 0], [0, half])
-                    assert np.array_equal(gc, exp) and np.array_equal(gv, cnt[exp])
-    finally:
-        for e in exs:
-            e.close()
-        for s in shards:
-            s.index.close()
+    return shards, exs, streams
 
 
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
-def test_fused_exchange_pipelined(B, world):
-    """Pipelined exchange over `world` shards in one process: query s returns the complete result of query
-    s-1, drain() the last one; lock-step searches mixed in on the same exchange.  world >= 3 exercises the
-    scatter + relay route of the k-mer bytes (rank 0 -> relay shard -> the other shards)."""
+def test_fused_exchange_shards_one_process(B, world):
+    """Streamed exchange over `world` shards in one process: a burst of back-to-back queries without any host
+    synchronisation in between (consecutive queries overlap on every shard, inboxes / generations / ring slots
+    rotate several times), every shard's copy of every query's all-gathered hits against the oracle."""
     import torch
 
-    if torch.cuda.device_count() < world:
-        pytest.skip("needs %d GPUs" % world)
-    from bigsi_b200.sharded import DeviceShard, FusedExchange, merge_shard_hits, unpack_hits
+    from bigsi_b200.sharded import merge_shard_hits, unpack_hits
 
+    ndev = torch.cuda.device_count()
     rng = np.random.default_rng(53 + world)
     part = 2000  # columns per shard, a multiple of 8
     m, N, k, h, cap = 20_011, part * world, 31, 3, 2048
@@ -606,71 +579,130 @@ def test_fused_exchange_pipelined(B, world):
     packed = np.packbits(rows, axis=1)
     oix = O.OracleIndex(k, m, h, N, rows=packed)
     offs = [g * part for g in range(world)]
-    shards, exs = [], []
-    for g in range(world):
-        ix = B.DeviceIndex(m, part, col_offset=offs[g], device=g)
-        ix.upload_rows(0, packed, src_byte_offset=offs[g] // 8)
-        shards.append(DeviceShard(ix, k, h, cap=cap))
-    for g in range(world):
-        exs.append(FusedExchange(shards[g], world, g, 8000, peers=True))
-    FusedExchange.connect_local(exs)
-
-    def expect(arr, thr):
-        cnt = oix.counts(_kmer_strs(arr))
-        e = np.nonzero(cnt >= thr)[0]
-        return e, cnt[e]
-
-    def check(views, want, tag):
-        for g in views:  # every shard holds every shard's hits (all-gather)
-            n, cols, vals = unpack_hits(g.cpu().numpy(), 1, cap)
-            assert (n[:, 0] <= cap).all()
-            gc, gv = merge_shard_hits(n[:, 0], cols[:, 0], vals[:, 0], offs)
-            assert np.array_equal(gc, want[0]) and np.array_equal(gv, want[1]), tag
-
-    def launch(arr, n_kmers, thr, pipelined):
-        d_k = torch.from_numpy(arr).to(shards[0].device)
-        out = [None] * world
-        for g in range(world - 1, -1, -1):  # the peers first: their kernels wait for rank 0's k-mers
-            with torch.cuda.device(g):
-                out[g] = exs[g].search(d_k if g == 0 else None, n_kmers, thr, pipelined=pipelined)
-        return out
-
+    shards, exs, streams = _make_shards(B, world, m, part, k, h, cap, packed, 8000, {"inputs_ready": 1})
+    # shards that share a device: rank 0 first (its CTAs must get SMs before the peers' CTAs spin on its k-mers);
+    # one shard per device: the peers first, so that their kernels really wait for rank 0's push
+    order = list(range(world)) if ndev < world else list(range(world - 1, -1, -1))
     try:
-        sizes = [40, 3000, 1, 7000, 512, 2500, 6000, 90, 4000, 4000, 333, 8000]
-        lockstep_steps = (5, 9)  # lock-step searches in between: generations and inboxes keep rotating
-        pending = None
-        for step, n_kmers in enumerate(sizes):
-            arr = _rand_kmers(rng, n_kmers, k)
-            thr = int(math.ceil(n_kmers * 0.85))
-            lockstep = step in lockstep_steps
-            views = launch(arr, n_kmers, thr, not lockstep)
-            if lockstep:
-                for g in range(world):
-                    torch.cuda.synchronize(g)
-                check(views, expect(arr, thr), ("lockstep", step))
-                pending = None
-                continue
-            if pending is not None:
-                # the PREVIOUS query's blocks: complete in stream order, no host synchronisation in between
-                assert all(v is not None for v in views)
-                copies = []
-                for g in range(world):
-                    with torch.cuda.device(g):
-                        copies.append(views[g].clone())  # consumed on each shard's own stream
-                check(copies, pending, ("pipelined", step - 1))
-            else:
-                assert all((v is None) == (step == 0) for v in views)
-            pending = expect(arr, thr)
-        last = []
-        for g in range(world - 1, -1, -1):
-            with torch.cuda.device(g):
-                last.append(exs[g].drain())
-        check(last, pending, "drain")
+        sizes = [40, 3000, 1, 7000, 512, 2500, 6000, 90, 4000, 4000, 333, 8000, 17, 5000]
+        queries = [_rand_kmers(rng, n, k) for n in sizes]
+        d_queries = [torch.from_numpy(a).to(shards[0].device) for a in queries]
+        torch.cuda.synchronize(shards[0].device)
+        for base, end in ((0, 1), (1, 7), (7, len(sizes))):  # 1, 6 and 7 queries in flight without a host sync
+            burst = sizes[base:end]
+            copies = []
+            for j, n_kmers in enumerate(burst):
+                thr = int(math.ceil(n_kmers * 0.85))
+                per_rank = [None] * world
+                for g in order:
+                    with torch.cuda.device(shards[g].device), torch.cuda.stream(streams[g]):
+                        view = exs[g].search(d_queries[base + j] if g == 0 else None, n_kmers, thr)
+                        per_rank[g] = view.clone()  # consumed on the shard's own stream, in stream order
+                copies.append(per_rank)
+            for d in range(ndev):
+                torch.cuda.synchronize(d)
+            for g in range(world):
+                assert shards[g].index.info()["last_fused"] & 8
+            for j, n_kmers in enumerate(burst):
+                thr = int(math.ceil(n_kmers * 0.85))
+                cnt = oix.counts(_kmer_strs(queries[base + j]))
+                exp = np.nonzero(cnt >= thr)[0]
+                for g in range(world):  # every shard holds every shard's hits (all-gather)
+                    n, cols, vals = unpack_hits(copies[j][g].cpu().numpy(), 1, cap)
+                    assert (n[:, 0] <= cap).all()
+                    gc, gv = merge_shard_hits(n[:, 0], cols[:, 0], vals[:, 0], offs)
+                    assert np.array_equal(gc, exp) and np.array_equal(gv, cnt[exp]), (world, base + j, g)
+        w, q = exs[0].wait_ns()
+        assert q == len(sizes)
     finally:
         for e in exs:
             e.close()
         for s in shards:
             s.index.close()
+
+
+def test_exchange_times_out_instead_of_hanging(B):
+    """A rank whose peer never launches its search gets an error code within a bounded time (no hung GPU):
+    rank 0's reduce kernel gives up waiting for rank 1's hit list, the handle reports BIGSI_B200_ERR_TIMEOUT
+    from then on; a peer that waits for k-mers nobody sends times out the same way."""
+    import time
+
+    import torch
+
+    from bigsi_b200 import _lib
+
+    rng = np.random.default_rng(59)
+    part, m, k, h, cap = 800, 5003, 31, 3, 256
+    rows = rng.random((m, 2 * part)) < 0.9
+    packed = np.packbits(rows, axis=1)
+    for silent in (1, 0):
+        shards, exs, streams = _make_shards(B, 2, m, part, k, h, cap, packed, 1000, {"spin_timeout_ms": 300, "inputs_ready": 1})
+        try:
+            arr = _rand_kmers(rng, 500, k)
+            d_k = torch.from_numpy(arr).to(shards[0].device)
+            talker = 1 - silent
+            t0 = time.perf_counter()
+            with torch.cuda.device(shards[talker].device), torch.cuda.stream(streams[talker]):
+                exs[talker].search(d_k if talker == 0 else None, 500, 400)
+                exs[talker].search(d_k if talker == 0 else None, 500, 400)  # a second query behind the stuck one
+            streams[talker].synchronize()
+            dt = time.perf_counter() - t0
+            assert dt < 5.0, "the stuck search took %.1f s to give up" % dt
+            rc = _lib.lib().bigsi_b200_index_status(shards[talker].index.handle)
+            assert rc == _lib.ERR_TIMEOUT
+            msg = _lib.lib().bigsi_b200_last_error().decode()
+            assert "timed out" in msg
+            with pytest.raises(_lib.BigsiB200Error) as ei:  # sticky: later calls fail instead of running
+                with torch.cuda.device(shards[talker].device), torch.cuda.stream(streams[talker]):
+                    exs[talker].search(d_k if talker == 0 else None, 500, 400)
+            assert ei.value.code == _lib.ERR_TIMEOUT
+            # the silent rank never launched anything: it is healthy
+            assert _lib.lib().bigsi_b200_index_status(shards[silent].index.handle) == 0
+        finally:
+            for e in exs:
+                e.close()
+            for s in shards:
+                s.index.close()
+
+
+def test_exchange_across_processes_ipc(B, tmp_path):
+    """The mode bench.py's multi-GPU runs use: one PROCESS per shard, result blocks and inboxes mapped through
+    CUDA IPC (bigsi_b200_exchange_create / open).  world = min(GPUs, 8) processes (two processes sharing the GPU
+    on a single-GPU box), >= 12 queries back to back, every rank's merged (colour, count) list against the oracle
+    (tests/exchange_worker.py does the checking and writes one verdict per rank)."""
+    import json
+    import socket
+    import subprocess
+    import sys
+
+    import torch
+
+    ndev = torch.cuda.device_count()
+    world = min(ndev, 8) if ndev >= 2 else 2
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r % ndev), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(os.path.dirname(__file__), "exchange_worker.py"),
+                                       str(tmp_path)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for pr in procs:
+        try:
+            out, _ = pr.communicate(timeout=600)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append(out)
+    for r, pr in enumerate(procs):
+        assert pr.returncode == 0, "rank %d failed:\n%s" % (r, outs[r][-3000:])
+    for r in range(world):
+        with open(os.path.join(str(tmp_path), "rank%d.json" % r)) as f:
+            verdict = json.load(f)
+        assert verdict["ok"] and verdict["queries"] >= 12 and verdict["world"] == world, verdict
 
 
 # ---------------------------------------------------------------------------
