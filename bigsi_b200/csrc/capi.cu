@@ -162,7 +162,7 @@ struct bigsi_b200_index {
     int64_t opt_tile_bytes = 0, opt_grid = 0, opt_kmers_per_stage = 0, opt_n_stages = 0, opt_ctas_per_sm = 0;
     bool timing = false;
     int64_t opt_debug_flags = 0;
-    int64_t opt_prehash = 1, opt_fuse_merge = 1, opt_merge_chunk_bytes = 0, opt_solo = 1, opt_pool_pct = 12, opt_zero_copy = 1, opt_cooperative = 1;
+    int64_t opt_prehash = 1, opt_fuse_merge = 1, opt_merge_chunk_bytes = 0, opt_solo = 1, opt_pool_pct = -1, opt_zero_copy = 1, opt_cooperative = 1;
     int64_t opt_inputs_ready = 0, opt_spin_timeout_ms = 10000;
     // streamed single-query launches (query.cuh:kStreamRing): ring-buffered scratch + the completion / abort words
     DevBuf d_pool;            // kStreamRing x [ready flags: grid x u64][ids: grid x pool_share x h x i32]
@@ -214,7 +214,7 @@ int ensure_kernels()
 // Launch plan of one query batch (DESIGN.md "Launch planning").  `have_kmers`: the caller holds
 // raw k-mers (length k), so the kernel may hash them itself when the geometry allows.
 int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t total_kmers, uint64_t max_query_kmers,
-               int h, bool have_kmers, int k, QueryParams &p, int &grid)
+               int h, bool have_kmers, int k, QueryParams &p, int &grid, bool isolated = false)
 {
     if (h < 1 || h > kMaxH) return fail(BIGSI_B200_ERR_INVALID, "h=%d out of range [1,%d]", h, kMaxH);
     if (n_queries > 0xffffffffull) return fail(BIGSI_B200_ERR_INVALID, "too many queries");
@@ -335,8 +335,13 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
         kSmemHeaderBytes + p.ids_bytes + (uint64_t)kMergeScratchBytes <= (uint64_t)kSmemBudget)
         p.fuse_merge = 1;
     if (p.solo) {
+        // The pool (a share of every CTA's k-mers claimed dynamically) evens out the CTAs' finish times when they all
+        // start together, i.e. for an ISOLATED query.  Back-to-back streamed queries never use it: their CTAs start
+        // whenever an SM becomes free, a claimer would wait for owners that have not even started, and there is no
+        // common finish line to balance for (the SM simply goes on with the next query).
         const uint64_t c = p.items_per_slice;
-        uint64_t pp = (c >= 16 && h <= kPoolMaxH) ? (c * (uint64_t)ix->opt_pool_pct + 50) / 100 : 0;
+        const uint64_t pct = ix->opt_pool_pct >= 0 ? (uint64_t)ix->opt_pool_pct : (isolated ? 12u : 0u);
+        uint64_t pp = (c >= 16 && h <= kPoolMaxH) ? (c * pct + 50) / 100 : 0;
         if (pp > c) pp = c;
         if (mode == BIGSI_B200_MODE_COUNTS && pp) {
             uint32_t pps = bits_of(c + 2 * pp);
@@ -377,6 +382,8 @@ struct HitsOut {
     unsigned long long sink_seq = 0;
     bool *published = nullptr;  // set when the launch will publish to the sinks
     // column-sharded exchange fused into the kernels (see Exchange above)
+    bool isolated = false;        // the caller waits for this query's result before it issues the next one: nothing overlaps
+                                  // it, so the CTAs start together and a pooled tail balances their finish times
     bool require_stream = false;  // fail before launching unless the plan is the streamed single-query one
     bool inputs_ready = false;    // the k-mers are not produced by the preceding kernel of the stream
     uint32_t n_push = 0;
@@ -430,7 +437,9 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
     if (int rc = ensure_kernels()) return rc;
     QueryParams p;
     int grid = 0;
-    if (int rc = plan_query(ix, mode, n_queries, total_kmers, max_query_kmers, h, d_kmers != nullptr, k, p, grid)) return rc;
+    if (int rc = plan_query(ix, mode, n_queries, total_kmers, max_query_kmers, h, d_kmers != nullptr, k, p, grid,
+                            hits != nullptr && hits->isolated))
+        return rc;
     if (d_kmers && p.prehash) {
         p.kmers = reinterpret_cast<const uint8_t *>(d_kmers);
     } else if (d_kmers && total_kmers) {
@@ -832,7 +841,7 @@ int bigsi_b200_index_set_option(bigsi_b200_index *ix, const char *key, int64_t v
     else if (!strcmp(key, "cooperative")) ix->opt_cooperative = value;
     else if (!strcmp(key, "inputs_ready")) ix->opt_inputs_ready = value;
     else if (!strcmp(key, "spin_timeout_ms")) ix->opt_spin_timeout_ms = value < 1 ? 1 : value;
-    else if (!strcmp(key, "pool_pct")) ix->opt_pool_pct = value > 100 ? 100 : value;
+    else if (!strcmp(key, "pool_pct")) ix->opt_pool_pct = value > 100 ? -1 : value;  // > 100 = automatic
     else return fail(BIGSI_B200_ERR_INVALID, "unknown option '%s'", key);
     return 0;
 }
@@ -1246,6 +1255,7 @@ static int search_one_published(bigsi_b200_index *ix, const char *d_kmers, uint6
     ho.total_dev = total_dev;
     ho.scrub = scrub;
     ho.scrub_words = scrub_words;
+    ho.isolated = true;
     ho.inputs_ready = total_dev == nullptr;  // host-written (or staged before this call) k-mers: nothing in the stream produces them
     ho.n_sinks = 1;
     ho.sinks[0] = static_cast<unsigned long long *>(d_blk);

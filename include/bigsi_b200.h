@@ -89,8 +89,9 @@ int bigsi_b200_index_get_info(const bigsi_b200_index *index, bigsi_b200_info *in
 /* Tuning / instrumentation knobs (value 0 = automatic): "tile_bytes", "grid", "kmers_per_stage",
  * "n_stages", "ctas_per_sm", "merge_chunk_bytes", "debug_flags"; "prehash" / "fuse_merge" / "solo" /
  * "zero_copy" (default 1; 0 forces the separate hash / merge kernels, the generic single-query
- * path, the staged host copies); "pool_pct" (default 12: share of a query's k-mers that the CTAs
- * claim dynamically); "cooperative" (default 1: a generic-path kernel that merges behind its own grid barrier is
+ * path, the staged host copies); "pool_pct" (0..100: share of a single query's k-mers that the CTAs claim
+ * dynamically; default / > 100 = automatic: 12 for an isolated query of the synchronous host calls, 0 for streamed
+ * back-to-back queries); "cooperative" (default 1: a generic-path kernel that merges behind its own grid barrier is
  * launched with the cooperative attribute, so the driver verifies that all its CTAs are co-resident; 0 = plain
  * launch, only safe when nothing else runs on the device); "inputs_ready" (default 0; 1 = the k-mer buffers handed
  * to the `_dev` single-query entry points are never produced by the kernel that precedes the call in the stream

@@ -579,11 +579,19 @@ def test_fused_exchange_shards_one_process(B, world):
     packed = np.packbits(rows, axis=1)
     oix = O.OracleIndex(k, m, h, N, rows=packed)
     offs = [g * part for g in range(world)]
-    shards, exs, streams = _make_shards(B, world, m, part, k, h, cap, packed, 8000, {"inputs_ready": 1})
-    # shards that share a device: rank 0 first (its CTAs must get SMs before the peers' CTAs spin on its k-mers);
-    # one shard per device: the peers first, so that their kernels really wait for rank 0's push
-    order = list(range(world)) if ndev < world else list(range(world - 1, -1, -1))
+    # shards that share a device: small rings (n_stages), so that the CTAs of all shards fit on the SMs together --
+    # a shard whose CTAs wait (for rank 0's k-mers, at the entry gate) must not keep the others off the device --
+    # and rank 0 first; one shard per device: the peers first, so that their kernels really wait for rank 0's push
+    shared = ndev < world
+    opts = {"inputs_ready": 1, "n_stages": 2} if shared else {"inputs_ready": 1}
+    shards, exs, streams = _make_shards(B, world, m, part, k, h, cap, packed, 8000, opts)
+    order = list(range(world)) if shared else list(range(world - 1, -1, -1))
     try:
+        for g in range(world):  # first use of torch's copy kernel / allocator must not fall between the ranks' launches
+            with torch.cuda.device(shards[g].device), torch.cuda.stream(streams[g]):
+                torch.zeros((world, 2 + 2 * cap), dtype=torch.int32, device=shards[g].device).clone()
+        for d in range(ndev):
+            torch.cuda.synchronize(d)
         sizes = [40, 3000, 1, 7000, 512, 2500, 6000, 90, 4000, 4000, 333, 8000, 17, 5000]
         queries = [_rand_kmers(rng, n, k) for n in sizes]
         d_queries = [torch.from_numpy(a).to(shards[0].device) for a in queries]
@@ -593,11 +601,13 @@ def test_fused_exchange_shards_one_process(B, world):
             copies = []
             for j, n_kmers in enumerate(burst):
                 thr = int(math.ceil(n_kmers * 0.85))
-                per_rank = [None] * world
+                views, per_rank = [None] * world, [None] * world
+                for g in order:  # every rank's launch first: nothing that may block the host in between
+                    with torch.cuda.device(shards[g].device), torch.cuda.stream(streams[g]):
+                        views[g] = exs[g].search(d_queries[base + j] if g == 0 else None, n_kmers, thr)
                 for g in order:
                     with torch.cuda.device(shards[g].device), torch.cuda.stream(streams[g]):
-                        view = exs[g].search(d_queries[base + j] if g == 0 else None, n_kmers, thr)
-                        per_rank[g] = view.clone()  # consumed on the shard's own stream, in stream order
+                        per_rank[g] = views[g].clone()  # consumed on the shard's own stream, in stream order
                 copies.append(per_rank)
             for d in range(ndev):
                 torch.cuda.synchronize(d)
