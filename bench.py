@@ -506,13 +506,43 @@ def run_e2e(args, index, searcher, shard, queries, h_queries, barrier, rank, wor
             assert uq == U and sorted(c.tolist()) == [0, 1, cols - 1] and set(v.tolist()) == {U}, (q, uq, c[:8], v[:8])
 
         def e2e_step(i):
-            for j in range(QPS):
-                res = index.search_sequence(h_seqs[(i * QPS + j) % N_DISTINCT], K, H, 1.0, cap=HIT_CAP)
+            # one step = ONE bulk call with the step's 64 host sequences (bulk_search, bigsi/__main__.py:261-314): 64 hit
+            # lists + 64 k-mer counts back in host memory
+            res = index.search_sequences(h_seqs, K, H, 1.0, cap=HIT_CAP)
+            assert len(res) == QPS and res[-1][3] == U and res[-1][2] == 3
             return res
 
         h2d, d2h = QPS * (U + K - 1), QPS * (24 + 3 * 8)
-        path = ("bigsi_b200_search_sequence (C ABI, host sequence in, hit list out: front-end kernel + gather kernel + "
-                "reduce kernel, no host round trip in between), %d synchronous calls per step" % QPS)
+        path = ("bigsi_b200_search_sequences (C ABI bulk call: %d host sequences in, %d hit lists out; per sequence the unique "
+                "windows are found inside the gather kernel, which reads the sequence out of pinned host memory, and the "
+                "reduce kernel writes the hits into mapped host memory; up to 7 searches in flight)" % (QPS, QPS))
+        # the same 64 sequences one synchronous call at a time (BIGSI.search's own call pattern)
+        for q in range(3):
+            index.search_sequence(h_seqs[q], K, H, 1.0, cap=HIT_CAP)
+        w0 = time.perf_counter()
+        for q in range(QPS):
+            index.search_sequence(h_seqs[q], K, H, 1.0, cap=HIT_CAP)
+        dt = time.perf_counter() - w0
+        extra["single_call"] = {"value": U * QPS / dt, "us_per_query": 1e6 * dt / QPS,
+                                "path": "bigsi_b200_search_sequence, one synchronous call per sequence (nothing in flight around it)"}
+        # ... and through the Python drop-in class: BIGSI(config).search(seq, 1.0) -> list of result dicts
+        from bigsi_b200 import bigsi as _bg
+
+        store = _bg._Store(index, args.m, H, K)
+        _bg.SampleMetadata(store.meta).add_samples(["s%d" % c for c in range(cols)])
+        _bg._STORES["bench-e2e"] = store
+        api = _bg.BIGSI({"k": K, "m": args.m, "h": H, "storage-engine": "b200", "storage-config": {"filename": "bench-e2e"}})
+        s_strs = [s.decode("ascii") for s in h_seqs]
+        for q in range(3):
+            r = api.search(s_strs[q], 1.0)
+        assert [d["sample_name"] for d in r] == ["s0", "s1", "s%d" % (cols - 1)] and r[0]["num_kmers"] == U
+        w0 = time.perf_counter()
+        for q in range(QPS):
+            api.search(s_strs[q], 1.0)
+        dt = time.perf_counter() - w0
+        del _bg._STORES["bench-e2e"]
+        extra["python_search"] = {"value": U * QPS / dt, "us_per_query": 1e6 * dt / QPS,
+                                  "path": "bigsi_b200.BIGSI(config).search(seq, threshold=1.0): str in, list of result dicts out"}
     else:
         h_out = [torch.empty((world, 2 + 2 * HIT_CAP), dtype=torch.int32).pin_memory() for _ in range(4)]
         d_qoff = torch.tensor([0, U], dtype=torch.int64, device=dev)
@@ -569,34 +599,46 @@ def run_e2e(args, index, searcher, shard, queries, h_queries, barrier, rank, wor
 
 
 def dump_timeline(index, dev_query, barrier, rank):
-    """Diagnostics: per-CTA globaltimer stamps of the last gather / reduce kernels of a short burst (stderr)."""
+    """Diagnostics: per-CTA globaltimer stamps of the gather / reduce kernels of the last 8 queries of a short burst:
+    a summary of the last query on stderr, the raw stamps in gpurun_out/timeline_rank<r>.npy."""
     import ctypes
 
     from bigsi_b200 import _lib as _L
 
     index.set_option("debug_flags", 2)
-    for i in range(24):
+    for i in range(32):
         dev_query(i)
     barrier()
     info = index.info()
     grid, rgrid = info["last_grid"], info["last_reduce_grid"]
-    buf = np.zeros((grid + rgrid) * 16, dtype=np.uint64)
+    per = grid + rgrid
+    buf = np.zeros(8 * per * 16, dtype=np.uint64)
     _L.check(_L.lib().bigsi_b200_index_debug_read(index.handle, ctypes.c_void_p(buf.ctypes.data), buf.size))
-    ts = buf.reshape(grid + rgrid, 16).astype(np.int64)
+    allts = buf.reshape(8, per, 16).astype(np.int64)
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        np.save(os.path.join(ROOT, "gpurun_out", "timeline_rank%d.npy" % rank), allts)
+    except OSError:
+        pass
+    last = int(np.argmax(allts[:, :grid, 0].min(axis=1)))  # the region with the latest gather entry = the last query
+    ts = allts[last]
     t0 = ts[:grid, 0].min()
     lines = ["rank %d timeline of the last query (us since its first gather CTA entered; min / median / max over CTAs)" % rank]
-    for title, block, names in (("gather kernel", ts[:grid], {0: "entry", 8: "past_gate", 1: "prod_first_issue", 9: "hash_done",
-                                                             2: "first_slot_landed", 5: "prod_last_issue", 3: "last_slot_consumed",
-                                                             4: "flushed"}),
+    for title, block, names in (("gather kernel", ts[:grid], {0: "entry", 8: "past_gate", 10: "front_end_done", 1: "prod_first_issue",
+                                                             9: "hash_done", 2: "first_slot_landed", 5: "prod_last_issue",
+                                                             3: "last_slot_consumed", 4: "flushed"}),
                                 ("reduce kernel", ts[grid:], {0: "entry", 8: "past_dependency_wait", 13: "stage_issue",
                                                              10: "planes_loaded", 11: "counters_in_smem", 12: "expanded",
-                                                             7: "items_done", 6: "last_cta_gathered"})):
+                                                             7: "items_done"})):
         lines.append(" " + title)
         for j, nm in names.items():
             col = block[:, j]
             col = (col[col > 0] - t0) / 1e3
             if col.size:
                 lines.append("  %-22s %8.2f %8.2f %8.2f   (n=%d)" % (nm, col.min(), np.median(col), col.max(), col.size))
+    firsts = np.sort(allts[:, :grid, 0].min(axis=1))
+    lines.append(" first gather-CTA entry of the last 8 queries, differences (us): %s"
+                 % np.round(np.diff(firsts) / 1e3, 2).tolist())
     sys.stderr.write("\n".join(lines) + "\n")
     index.set_option("debug_flags", 0)
 

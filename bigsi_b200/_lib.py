@@ -98,6 +98,9 @@ SIGNATURES = {
     "bigsi_b200_search_kmers_hits": (_int, [_vp, _vp, _vp, _u64, _int, _int, _vp, _vp, _vp, _u64, _vp]),
     "bigsi_b200_lookup_kmers": (_int, [_vp, _vp, _u64, _int, _int, _vp, _u64]),
     "bigsi_b200_search_sequence": (_int, [_vp, _vp, _u64, _int, _int, ctypes.c_double, _vp, _vp, _u64, _vp, _vp]),
+    "bigsi_b200_search_sequence_submit": (_int, [_vp, _vp, _u64, _int, _int, ctypes.c_double, _u64, ctypes.POINTER(_u64)]),
+    "bigsi_b200_search_sequence_wait": (_int, [_vp, _u64, _vp, _vp, _u64, _vp, _vp]),
+    "bigsi_b200_search_sequences": (_int, [_vp, _vp, _vp, _u64, _int, _int, ctypes.c_double, _vp, _vp, _u64, _vp, _vp]),
     "bigsi_b200_bloom_kmers": (_int, [_int, _vp, _u64, _int, _int, _u64, _int, _vp]),
     "bigsi_b200_index_build_columns": (_int, [_vp, _u64, _u64, _vp, _u64, _u64]),
     "bigsi_b200_index_build_columns_dev": (_int, [_vp, _u64, _u64, _vp, _u64, _u64, _vp]),

@@ -174,6 +174,26 @@ struct bigsi_b200_index {
     PinnedBuf h_status;       // mapped: word 0 = mirror of the abort word
     DevBuf d_hits_ring;       // host-buffer paths: kStreamStates x {n_hits, cols[cap], counts[cap]}
     uint64_t stream_seq = 0;  // streamed queries launched on this handle
+    // sequence searches (front-end inside the gather kernel): kStreamRing de-duplication tables with epoch-tagged
+    // entries, up to kSeqTickets searches in flight (submit / wait), each with its own pinned sequence buffer and
+    // its own result block in mapped host memory
+    DevBuf d_seq_tables;
+    uint64_t seq_table_entries = 0;               // entries of ONE table
+    uint64_t seq_table_uses[kStreamRing] = {};
+    struct SeqTicket {
+        uint64_t id = 0;
+        bool pending = false, deferred = false;
+        std::string seq;                          // deferred (not streamable): searched synchronously at wait()
+        int k = 0, h = 0;
+        double threshold = 0;
+        uint64_t cap = 0, spec = 0;
+        const uint8_t *d_hits = nullptr;          // device hit buffers of this search (long hit lists)
+    };
+    static constexpr int kSeqTickets = 8;
+    SeqTicket tickets[kSeqTickets];
+    PinnedBuf h_seq[kSeqTickets];
+    PinnedBuf h_tsink;
+    uint64_t next_ticket = 1;
     DevBuf d_barrier;                             // grid-barrier arrival counter of the fused kernel
     uint64_t barrier_target = 0, done_target = 0;
     PinnedBuf h_sink, h_kmers;   // mapped pinned: result block the kernel publishes to / staging of pageable k-mers
@@ -196,7 +216,8 @@ namespace {
 constexpr uint64_t kStreamStateBytes = 3 * 64 + (uint64_t)kStreamStates * sizeof(QState);
 // shared memory a streamed gather CTA may use so that a reduce CTA (kReduceSmemBytes + its static words) still
 // fits on the same SM; every resident CTA reserves 1 KB
-constexpr uint64_t kStreamGatherSmem = (uint64_t)kSmBytes - 2 * 1024 - kReduceSmemBytes - 512;
+constexpr uint64_t kStreamGatherSmem =
+    (uint64_t)kSmBytes - (1 + kReduceSlotsPerSm) * 1024 - (uint64_t)kReduceSlotsPerSm * (kReduceSmemBytes + 256);
 
 bool g_kernels_ready[64] = {};  // function attributes (dynamic shared memory opt-in) are per device
 
@@ -396,6 +417,10 @@ struct HitsOut {
     unsigned long long *scrub = nullptr;  // words the reduce kernel clears (front-end table)
     uint64_t scrub_words = 0;
     LlRoute ll = {};  // the k-mer bytes travel through the shards' low-latency inboxes
+    // sequence front-end inside the gather kernel: the "k-mers" are a SEQUENCE of total_kmers windows; unique windows
+    // and min_kmers = ceil(U * threshold) are determined on the device (needs the streamed plan, else run_query returns 1)
+    bool seq_mode = false;
+    double seq_threshold = 0;
 };
 
 // the sticky abort word of the handle (ptx.cuh:raise_abort), as the host sees it
@@ -463,10 +488,14 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
         reduce_grid = (int)std::min<uint64_t>(p.merge_items, (uint64_t)ix->sm_count);
         if (reduce_grid < 1) reduce_grid = 1;
     }
-    if (p.debug_flags & 2u) {  // timeline stamps of the LAST launch, fetched with bigsi_b200_index_debug_read
-        cudaError_t de = ix->debug_ts.reserve((uint64_t)((grid > 0 ? grid : 1) + reduce_grid) * kDebugStamps * 8);
+    if (p.debug_flags & 2u) {
+        // timeline stamps, fetched with bigsi_b200_index_debug_read: [gather grid + reduce grid][kDebugStamps] words per
+        // launch; streamed launches rotate over kStreamStates such regions (query seq uses region seq % kStreamStates),
+        // so the schedule of several consecutive queries can be read back
+        const uint64_t region = (uint64_t)((grid > 0 ? grid : 1) + reduce_grid) * kDebugStamps;
+        cudaError_t de = ix->debug_ts.reserve(region * 8 * kStreamStates);
         if (de != cudaSuccess) return fail_cuda(de, "debug buffer");
-        p.debug_ts = static_cast<unsigned long long *>(ix->debug_ts.p);
+        p.debug_ts = static_cast<unsigned long long *>(ix->debug_ts.p) + (p.stream ? ((ix->stream_seq + 1) % kStreamStates) * region : 0);
     }
     bool will_publish = false;
     if (hits) {
@@ -485,6 +514,7 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
             p.scrub = hits->scrub;
             p.scrub_words = hits->scrub_words;
         }
+        if (hits->seq_mode && !(p.stream && hits->n_sinks && k <= 32)) return 1;
         if (hits->require_stream && !p.stream)
             return fail(BIGSI_B200_ERR_INVALID, "this query cannot run as a streamed single-query launch (prehash=%u grid=%d)",
                         p.prehash, grid);
@@ -545,6 +575,23 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
         p.qstate = states + seq % kStreamStates;
         p.qstate_next = states + (seq + kStreamRing) % kStreamStates;
         p.pool_counter = &p.qstate->pool_claims;
+        if (hits && hits->seq_mode) {
+            // table `slot` of the ring; live entries carry this use's 16-bit epoch, so the table is only cleared when the
+            // epoch wraps (every 65 535 uses) -- stream-ordered, which serialises one query in a quarter of a million
+            uint64_t T = 1024;
+            while (T < 2 * total_kmers) T <<= 1;
+            if (T > ix->seq_table_entries) return fail(BIGSI_B200_ERR_INVALID, "internal: sequence table not reserved");
+            uint64_t &uses = ix->seq_table_uses[slot];
+            unsigned long long *table = static_cast<unsigned long long *>(ix->d_seq_tables.p) + slot * ix->seq_table_entries;
+            if (uses && uses % 65535 == 0) CK(cudaMemsetAsync(table, 0, ix->seq_table_entries * 8, stream));
+            p.seq_mode = 1;
+            p.seq_threshold = hits->seq_threshold;
+            p.seq_table = table;
+            p.seq_table_entries = T;
+            p.seq_epoch = (uint32_t)(uses % 65535) + 1;
+            ++uses;
+            p.total_dev = &p.qstate->n_unique;  // reported in the sink block by the reduce kernel
+        }
         p.ll.abort_word = p.abort_word;
         p.ll.host_abort = p.host_abort;
         p.ll.timeout_ns = p.spin_timeout_ns;
@@ -552,7 +599,7 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
         // the kernel must wait for its predecessor in the stream when that may produce its input: always for a
         // device-side k-mer count, and for caller-provided device k-mers unless the caller says otherwise
         const bool ready = (hits && hits->inputs_ready) || ix->opt_inputs_ready != 0 || p.ll.in != nullptr;  // (a peer shard reads its inbox)
-        p.stream_wait_inputs = (ready && !p.total_dev) ? 0u : 1u;
+        p.stream_wait_inputs = (ready && !(hits && hits->total_dev)) ? 0u : 1u;
 
         TimedLaunch tl{};
         if (ix->timing) {
@@ -789,7 +836,9 @@ int bigsi_b200_index_destroy(bigsi_b200_index *ix)
     cudaDeviceSynchronize();
     for (auto &t : ix->timed_free) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
     for (auto &t : ix->timed_used) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
-    DevBuf *bufs[] = {&ix->stream_partial, &ix->d_stream, &ix->d_hits_ring, &ix->d_seq, &ix->d_table, &ix->d_pool, &ix->d_barrier, &ix->debug_ts, &ix->partial, &ix->d_kmers, &ix->d_rows, &ix->d_qoff, &ix->d_out, &ix->d_min,
+    for (auto &b : ix->h_seq) b.release();
+    ix->h_tsink.release();
+    DevBuf *bufs[] = {&ix->d_seq_tables, &ix->stream_partial, &ix->d_stream, &ix->d_hits_ring, &ix->d_seq, &ix->d_table, &ix->d_pool, &ix->d_barrier, &ix->debug_ts, &ix->partial, &ix->d_kmers, &ix->d_rows, &ix->d_qoff, &ix->d_out, &ix->d_min,
                       &ix->d_nhits, &ix->d_bloom, &ix->d_planted};
     for (DevBuf *b : bufs) b->release();
     ix->h_small.release();
@@ -1413,20 +1462,14 @@ int bigsi_b200_lookup_kmers(bigsi_b200_index *ix, const char *kmers, uint64_t n,
 // ============================================================================================
 // query front-end + search: BIGSI.search's filter stage for one sequence (graph/bigsi.py:174-230)
 // ============================================================================================
-int bigsi_b200_search_sequence(bigsi_b200_index *ix, const char *seq, uint64_t len, int k, int h, double threshold,
-                               int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_hits_out,
-                               uint64_t *num_kmers_out)
+// The general path: a front-end kernel (aux_kernels.cu:dedup_windows_kernel) compacts the unique windows, the search
+// follows -- streamed without a host round trip when the plan allows, else after fetching U.  Used for k > 32, for
+// sequences too long for the streamed plan and for rows wider than one column tile.
+static int search_sequence_general(bigsi_b200_index *ix, const char *seq, uint64_t len, int k, int h, double threshold,
+                                   int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_hits_out,
+                                   uint64_t *num_kmers_out)
 {
-    if (int rc = check_index(ix)) return rc;
-    if (!n_hits_out || !num_kmers_out || (cap && (!cols_out || !counts_out))) return fail(BIGSI_B200_ERR_INVALID, "null pointer");
-    if (k < 1 || h < 1) return fail(BIGSI_B200_ERR_INVALID, "k and h must be >= 1");
-    if (len && !seq) return fail(BIGSI_B200_ERR_INVALID, "null sequence");
-    *n_hits_out = 0;
-    *num_kmers_out = 0;
-    if (len < (uint64_t)k) return 0;  // no window: the caller reproduces the reference's TypeError
     const uint64_t n = len - (uint64_t)k + 1;
-    if (n > 0xfffffff0ull) return fail(BIGSI_B200_ERR_RANGE, "sequence too long");
-    DeviceGuard guard(ix->device);
     cudaError_t e;
     uint64_t T = 1024;
     while (T < 2 * n) T <<= 1;
@@ -1483,6 +1526,212 @@ int bigsi_b200_search_sequence(bigsi_b200_index *ix, const char *seq, uint64_t l
     if (!scrubbed) CK(cudaMemsetAsync(ix->d_table.p, 0, clear_bytes, ix->stream));
     ix->table_clean_bytes = clear_bytes;
     return 0;
+}
+
+
+// --------------------------------------------------------------------------------------------
+// sequence searches with the front-end inside the gather kernel: submit / wait
+// --------------------------------------------------------------------------------------------
+static constexpr uint64_t kTicketSpec = 1024;  // hits one mapped host result block holds
+static constexpr uint64_t kTicketBlock = (16 + 8 * kTicketSpec + 8 + 127) / 128 * 128;
+
+static int seq_submit(bigsi_b200_index *ix, const char *seq, uint64_t len, int k, int h, double threshold, uint64_t cap,
+                      bool isolated, uint64_t *ticket_out)
+{
+    if (k < 1 || h < 1) return fail(BIGSI_B200_ERR_INVALID, "k and h must be >= 1");
+    if (len && !seq) return fail(BIGSI_B200_ERR_INVALID, "null sequence");
+    if (const unsigned long long av = abort_state(ix)) return fail_aborted(av);
+    const uint64_t id = ix->next_ticket;
+    const int slot = (int)(id % bigsi_b200_index::kSeqTickets);
+    bigsi_b200_index::SeqTicket &t = ix->tickets[slot];
+    if (t.pending) return fail(BIGSI_B200_ERR_INVALID, "too many sequence searches in flight (at most %d): wait for ticket %llu first",
+                               bigsi_b200_index::kSeqTickets, (unsigned long long)t.id);
+    t = bigsi_b200_index::SeqTicket();
+    t.id = id;
+    t.k = k;
+    t.h = h;
+    t.threshold = threshold;
+    t.cap = cap;
+    t.spec = cap < kTicketSpec ? cap : kTicketSpec;
+    auto defer = [&]() {  // not streamable: searched synchronously when the caller waits for it
+        t.deferred = true;
+        t.seq.assign(seq ? seq : "", len);
+        t.pending = true;
+        ++ix->next_ticket;
+        *ticket_out = id;
+        return 0;
+    };
+    if (len < (uint64_t)k || ix->num_cols == 0 || k > 32 || ix->opt_zero_copy == 0 || cap == 0) return defer();
+    const uint64_t n = len - (uint64_t)k + 1;
+    if (n > 0xfffffff0ull) return fail(BIGSI_B200_ERR_RANGE, "sequence too long");
+    cudaError_t e;
+    // tables: one per ring slot, 2 entries per window (a power of two), zeroed when (re)allocated
+    uint64_t T = 1024;
+    while (T < 2 * n) T <<= 1;
+    if (T > (1ull << 26)) return defer();  // (longer sequences never get the streamed plan anyway)
+    if (T > ix->seq_table_entries) {
+        CK(cudaStreamSynchronize(ix->stream));
+        if ((e = ix->d_seq_tables.reserve(kStreamRing * T * 8)) != cudaSuccess) return fail_cuda(e, "de-duplication tables");
+        CK(cudaMemsetAsync(ix->d_seq_tables.p, 0, kStreamRing * T * 8, ix->stream));
+        ix->seq_table_entries = T;
+        for (auto &u : ix->seq_table_uses) u = 0;
+    }
+    const uint64_t hit_slot = round_up(8 + 8ull * cap + 16, 256);
+    if (hit_slot * kStreamStates > ix->d_hits_ring.cap) {
+        CK(cudaStreamSynchronize(ix->stream));
+        if ((e = ix->d_hits_ring.reserve(hit_slot * kStreamStates)) != cudaSuccess) return fail_cuda(e, "staging");
+    }
+    if ((e = ix->h_tsink.reserve(kTicketBlock * bigsi_b200_index::kSeqTickets)) != cudaSuccess) return fail_cuda(e, "pinned result blocks");
+    if ((e = ix->h_seq[slot].reserve(len + 64)) != cudaSuccess) return fail_cuda(e, "pinned sequence staging");
+    // the sequence stays in (mapped, pinned) host memory: every gather CTA stages its own span (one PCIe round trip)
+    memcpy(ix->h_seq[slot].p, seq, len);
+    memset(static_cast<uint8_t *>(ix->h_seq[slot].p) + len, 0, 64);
+    void *d_seq = nullptr, *d_blk = nullptr;
+    CK(cudaHostGetDevicePointer(&d_seq, ix->h_seq[slot].p, 0));
+    CK(cudaHostGetDevicePointer(&d_blk, static_cast<uint8_t *>(ix->h_tsink.p) + (uint64_t)slot * kTicketBlock, 0));
+    uint8_t *dev = static_cast<uint8_t *>(ix->d_hits_ring.p) + ((ix->stream_seq + 1) % kStreamStates) * hit_slot;
+    bool published = false;
+    HitsOut ho;
+    ho.n = reinterpret_cast<unsigned long long *>(dev);
+    ho.cols = reinterpret_cast<int32_t *>(dev + 8);
+    ho.counts = reinterpret_cast<uint32_t *>(dev + 8 + cap * 4);
+    ho.cap = cap;
+    ho.seq_mode = true;
+    ho.seq_threshold = threshold;
+    ho.isolated = isolated;
+    ho.inputs_ready = true;
+    ho.n_sinks = 1;
+    ho.sinks[0] = static_cast<unsigned long long *>(d_blk);
+    ho.sink_spec = (uint32_t)t.spec;
+    ho.sink_seq = id;
+    ho.published = &published;
+    const int rc = run_query(ix, BIGSI_B200_MODE_COUNTS, nullptr, static_cast<const char *>(d_seq), k, nullptr, 1, n, n, h, nullptr, 0,
+                             ix->stream, &ho);
+    if (rc == 1) return defer();  // the launch plan is not the streamed one (wide rows, very long sequence)
+    if (rc) return rc;
+    if (!published) return fail(BIGSI_B200_ERR_CUDA, "internal: sequence search launched without publication");
+    t.d_hits = dev;
+    t.pending = true;
+    ++ix->next_ticket;
+    *ticket_out = id;
+    return 0;
+}
+
+static int seq_wait(bigsi_b200_index *ix, uint64_t ticket, int32_t *cols_out, uint32_t *counts_out, uint64_t cap,
+                    uint64_t *n_hits_out, uint64_t *num_kmers_out)
+{
+    const int slot = (int)(ticket % bigsi_b200_index::kSeqTickets);
+    bigsi_b200_index::SeqTicket &t = ix->tickets[slot];
+    if (!t.pending || t.id != ticket) return fail(BIGSI_B200_ERR_INVALID, "unknown or already collected ticket %llu", (unsigned long long)ticket);
+    if (cap < t.cap) return fail(BIGSI_B200_ERR_INVALID, "output capacity %llu smaller than the one submitted (%llu)",
+                                 (unsigned long long)cap, (unsigned long long)t.cap);
+    t.pending = false;
+    *n_hits_out = 0;
+    *num_kmers_out = 0;
+    if (t.deferred) {
+        if (t.seq.size() < (size_t)t.k) return 0;  // no window: the caller reproduces the reference's TypeError
+        std::string seq;
+        seq.swap(t.seq);
+        return search_sequence_general(ix, seq.data(), seq.size(), t.k, t.h, t.threshold, cols_out, counts_out, t.cap, n_hits_out,
+                                       num_kmers_out);
+    }
+    volatile unsigned long long *blk =
+        reinterpret_cast<volatile unsigned long long *>(static_cast<uint8_t *>(ix->h_tsink.p) + (uint64_t)slot * kTicketBlock);
+    uint64_t spins = 0;
+    while (__atomic_load_n(&blk[0], __ATOMIC_ACQUIRE) != ticket) {
+        if ((++spins & 0x3fff) == 0) {
+            if (const unsigned long long av = abort_state(ix)) return fail_aborted(av);
+            cudaError_t e = cudaStreamQuery(ix->stream);
+            if (e != cudaErrorNotReady) {
+                if (e != cudaSuccess) return fail_cuda(e, "query kernel");
+                if (__atomic_load_n(&blk[0], __ATOMIC_ACQUIRE) != ticket)
+                    return fail(BIGSI_B200_ERR_CUDA, "query kernels finished without publishing their result");
+            }
+        }
+    }
+    const uint64_t n = blk[1];
+    *num_kmers_out = blk[2 + t.spec];
+    const uint64_t m = n < t.cap ? n : t.cap;
+    const uint64_t ms = m < t.spec ? m : t.spec;
+    const int32_t *hc = reinterpret_cast<const int32_t *>(const_cast<unsigned long long *>(blk) + 2);
+    memcpy(cols_out, hc, ms * 4);
+    memcpy(counts_out, hc + t.spec, ms * 4);
+    if (m > t.spec) {  // a long hit list: the device buffers are complete once the block was published
+        CK(cudaMemcpyAsync(cols_out, t.d_hits + 8, m * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CK(cudaMemcpyAsync(counts_out, t.d_hits + 8 + t.cap * 4, m * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CK(cudaStreamSynchronize(ix->stream));
+    }
+    *n_hits_out = n;
+    return 0;
+}
+
+int bigsi_b200_search_sequence_submit(bigsi_b200_index *ix, const char *seq, uint64_t len, int k, int h, double threshold,
+                                      uint64_t cap, uint64_t *ticket_out)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (!ticket_out) return fail(BIGSI_B200_ERR_INVALID, "null pointer");
+    DeviceGuard guard(ix->device);
+    return seq_submit(ix, seq, len, k, h, threshold, cap, false, ticket_out);
+}
+
+int bigsi_b200_search_sequence_wait(bigsi_b200_index *ix, uint64_t ticket, int32_t *cols_out, uint32_t *counts_out, uint64_t cap,
+                                    uint64_t *n_hits_out, uint64_t *num_kmers_out)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (!n_hits_out || !num_kmers_out || (cap && (!cols_out || !counts_out))) return fail(BIGSI_B200_ERR_INVALID, "null pointer");
+    DeviceGuard guard(ix->device);
+    return seq_wait(ix, ticket, cols_out, counts_out, cap, n_hits_out, num_kmers_out);
+}
+
+int bigsi_b200_search_sequence(bigsi_b200_index *ix, const char *seq, uint64_t len, int k, int h, double threshold,
+                               int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_hits_out,
+                               uint64_t *num_kmers_out)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (!n_hits_out || !num_kmers_out || (cap && (!cols_out || !counts_out))) return fail(BIGSI_B200_ERR_INVALID, "null pointer");
+    DeviceGuard guard(ix->device);
+    uint64_t ticket = 0;
+    if (int rc = seq_submit(ix, seq, len, k, h, threshold, cap, /*isolated=*/true, &ticket)) return rc;
+    return seq_wait(ix, ticket, cols_out, counts_out, cap, n_hits_out, num_kmers_out);
+}
+
+// bulk_search (bigsi/__main__.py:261-314: every record of a FASTA file through BIGSI.search): n_seqs sequences in one
+// call, up to kSeqTickets - 1 searches in flight -- the gather kernel of one sequence overlaps the reduce kernel of
+// the one before, the host stages the next sequence meanwhile.
+int bigsi_b200_search_sequences(bigsi_b200_index *ix, const char *seqs, const uint64_t *offsets, uint64_t n_seqs, int k, int h,
+                                double threshold, int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_hits_out,
+                                uint64_t *num_kmers_out)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (n_seqs == 0) return 0;
+    if (!offsets || !n_hits_out || !num_kmers_out || (cap && (!cols_out || !counts_out))) return fail(BIGSI_B200_ERR_INVALID, "null pointer");
+    for (uint64_t q = 0; q < n_seqs; ++q)
+        if (offsets[q + 1] < offsets[q]) return fail(BIGSI_B200_ERR_INVALID, "offsets must be non-decreasing");
+    if (offsets[n_seqs] > offsets[0] && !seqs) return fail(BIGSI_B200_ERR_INVALID, "null sequences");
+    DeviceGuard guard(ix->device);
+    const uint64_t window = bigsi_b200_index::kSeqTickets - 1;
+    std::vector<uint64_t> tickets(n_seqs, 0);
+    uint64_t submitted = 0, collected = 0;
+    int rc = 0;
+    while (collected < n_seqs && !rc) {
+        while (submitted < n_seqs && submitted - collected < window && !rc) {
+            rc = seq_submit(ix, seqs + offsets[submitted], offsets[submitted + 1] - offsets[submitted], k, h, threshold, cap, false,
+                            &tickets[submitted]);
+            if (!rc) ++submitted;
+        }
+        if (rc) break;
+        rc = seq_wait(ix, tickets[collected], cols_out + collected * cap, counts_out + collected * cap, cap, n_hits_out + collected,
+                      num_kmers_out + collected);
+        ++collected;
+    }
+    // on an error the searches still in flight are abandoned: their tickets are released once the stream is idle
+    if (rc) {
+        const std::string msg = g_err;
+        cudaStreamSynchronize(ix->stream);
+        for (auto &t : ix->tickets) t.pending = false;
+        g_err = msg;
+    }
+    return rc;
 }
 
 // ============================================================================================

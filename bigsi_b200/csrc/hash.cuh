@@ -268,6 +268,103 @@ static __device__ __noinline__ void hash_kmers_group(const uint8_t *g0, uint32_t
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Sequence front-end inside the query kernel (k <= 32): BIGSI.search's `set(kmers)` over RAW window strings
+// (bigsi/utils/fncts.py:63-65, graph/index.py:45, graph/bigsi.py:177-179) without a separate kernel.  Every CTA
+// stages its span of the sequence, every window is inserted into a global open-addressing table with atomicCAS;
+// the window that wins its entry represents its string (any representative will do for a set), equal tags are
+// confirmed by comparing the k bytes, so the set is exact.  Entries carry a 16-bit epoch: entries of other epochs
+// count as empty, the table is never cleared between queries.
+//   entry = epoch (16) | tag (16) | window index (32)
+// ------------------------------------------------------------------------------------------------
+struct SeqTable {
+    unsigned long long *entries;
+    uint64_t mask;        // entries - 1 (a power of two minus one)
+    uint32_t epoch;       // 1 .. 65535
+    const uint8_t *seq;   // the whole sequence (device-addressable; may be mapped host memory)
+};
+
+// 8 bytes of a window held in shared memory (unaligned), zero padded past k
+__device__ __forceinline__ unsigned long long window_word(const uint8_t *s, int k, int j)
+{
+    unsigned long long v = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+        if (j * 8 + b < k) v |= (unsigned long long)s[j * 8 + b] << (8 * b);
+    return v;
+}
+__device__ __forceinline__ unsigned long long window_fingerprint(const uint8_t *s, int k)
+{
+    unsigned long long fp = 0x9e3779b97f4a7c15ull ^ (unsigned long long)k;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j * 8 < k) {
+            fp = (fp ^ window_word(s, k, j)) * 0xff51afd7ed558ccdull;
+            fp ^= fp >> 29;
+        }
+    }
+    fp *= 0xc4ceb9fe1a85ec53ull;
+    return fp ^ (fp >> 32);
+}
+// window `s` (shared memory) == window `other` of the sequence?  The other window is read from the CTA's own span
+// when it lies inside it, else from the sequence in global memory as aligned 8-byte words (one round trip).
+__device__ __forceinline__ bool window_equals(const SeqTable &T, const uint8_t *s, int k, uint64_t other, const uint8_t *span,
+                                              uint64_t span_w0, uint32_t span_cnt)
+{
+    if (other >= span_w0 && other < span_w0 + span_cnt) {
+        const uint8_t *o = span + (other - span_w0);
+        bool eq = true;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j * 8 < k) eq = eq && window_word(s, k, j) == window_word(o, k, j);
+        return eq;
+    }
+    const uint8_t *g = T.seq + other;
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 7) * 8;
+    const unsigned long long *a = reinterpret_cast<const unsigned long long *>(g - (sh >> 3));
+    unsigned long long w[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) w[j] = (j * 8 < k + 8) ? __ldg(a + j) : 0ull;  // the staging buffer is padded: never out of bounds
+    bool eq = true;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j * 8 < k) {
+            unsigned long long v = sh ? (w[j] >> sh) | (w[j + 1] << (64 - sh)) : w[j];
+            const int rem = k - j * 8;
+            if (rem < 8) v &= (1ull << (8 * rem)) - 1ull;
+            eq = eq && v == window_word(s, k, j);
+        }
+    }
+    return eq;
+}
+// true: this window is the representative of its string (first to claim the entry)
+__device__ __forceinline__ bool seq_table_insert(const SeqTable &T, const uint8_t *s, int k, uint64_t widx, const uint8_t *span,
+                                                 uint64_t span_w0, uint32_t span_cnt)
+{
+    const unsigned long long fp = window_fingerprint(s, k);
+    const unsigned long long tag = (fp >> 44) & 0xffffull;
+    const unsigned long long mine = ((unsigned long long)T.epoch << 48) | (tag << 32) | (unsigned long long)(uint32_t)widx;
+    uint64_t slot = fp & T.mask;
+    for (;;) {
+        unsigned long long cur = ld_volatile_u64(T.entries + slot);
+        if ((cur >> 48) != T.epoch) {
+            const unsigned long long old = atomicCAS(T.entries + slot, cur, mine);
+            if (old == cur) return true;
+            cur = old;
+            if ((cur >> 48) != T.epoch) continue;  // (cannot happen: only this query writes this table) look again
+        }
+        if (((cur >> 32) & 0xffffull) == tag && window_equals(T, s, k, cur & 0xffffffffull, span, span_w0, span_cnt)) return false;
+        slot = (slot + 1) & T.mask;
+    }
+}
+
+// Hash `cnt` windows of a staged span: window j starts at span + list[j]; one thread per window (k <= 32).
+__device__ __forceinline__ void hash_window_list(const uint8_t *span, const uint16_t *list, uint32_t cnt, int k, int h, uint32_t m,
+                                                 uint64_t magic, int32_t *ids, uint32_t tid, uint32_t nthreads)
+{
+    for (uint32_t j = tid; j < cnt; j += nthreads) hash_one_kmer_regs(span + list[j], k, h, m, magic, 1, ids + (size_t)j * h);
+}
+
 // the whole CTA as one group
 __device__ __forceinline__ void hash_kmers_cooperative(const uint8_t *g0, uint32_t cnt, int k, int h, uint32_t m,
                                                        int canonical, uint8_t *scratch, int32_t *ids, uint64_t magic)

@@ -314,8 +314,14 @@ __device__ __forceinline__ void merge_item(const QueryParams &P, uint64_t item, 
 
     if (MODE == kModeCounts) {
         uint32_t *out = P.out ? reinterpret_cast<uint32_t *>(P.out) + (uint64_t)G.q * P.out_stride : nullptr;
-        const bool thresholding = P.min_kmers != nullptr || P.min_by_value;
-        const uint32_t thr = P.min_by_value ? P.min_kmers_value : (thresholding ? __ldg(P.min_kmers + G.q) : 0u);
+        const bool thresholding = P.min_kmers != nullptr || P.min_by_value || P.seq_mode;
+        uint32_t thr = P.min_by_value ? P.min_kmers_value : (P.min_kmers != nullptr ? __ldg(P.min_kmers + G.q) : 0u);
+        if (P.seq_mode) {
+            // min_kmers = math.ceil(U * threshold) in IEEE double (graph/bigsi.py:179) with the U the gather kernel's
+            // front-end counted; <= 0 keeps every column
+            const double need = ceil(__dmul_rn((double)__ldcg(&P.qstate->n_unique), P.seq_threshold));
+            thr = need <= 0.0 ? 0u : need >= 4294967295.0 ? 0xffffffffu : (uint32_t)need;
+        }
         for (uint32_t w = warp; w < G.vw; w += nwarps) {
             uint32_t total = 0;
             const uint32_t *cw = cnt + (size_t)w * pps * J;

@@ -22,9 +22,10 @@ __global__ void __launch_bounds__(kMergeKernelThreads) merge_kernel(const __grid
     merge_item<MODE>(P, blockIdx.x, merge_smem, &bar, phase);
 }
 
-// Stage 2 of a STREAMED query (query_kernels.cu:gather_solo): merge + threshold + publication.  128 threads and
-// 32 KB of shared memory per CTA, so that its CTAs fit beside the gather CTAs: it becomes resident while "its"
-// gather kernel runs, sleeps in the dependency wait, and works while the NEXT query's gather kernel streams rows.
+// Stage 2 of a STREAMED query (query_kernels.cu:gather_solo): merge + threshold + publication.  64 threads and
+// 16 KB of shared memory per CTA, so that TWO of its CTAs fit beside a gather CTA (query.cuh:kReduceSlotsPerSm): it
+// becomes resident while "its" gather kernel runs, sleeps in the dependency wait, and works while the NEXT query's
+// gather kernel streams rows.
 // The last CTA to finish publishes the hit list (host block and / or every shard's result blocks), waits -- bounded
 // -- for the other shards' blocks of the same query, clears the state block of query seq + kStreamRing and advances
 // the handle's completion word in query order.
@@ -37,6 +38,11 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_kernel(const __grid_con
     grid_launch_dependents();
     if (threadIdx.x == 0) {
         BIGSI_TS(0);
+        if (P.debug_ts) {
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            P.debug_ts[(size_t)blockIdx.x * kDebugStamps + 15] = smid;
+        }
         mbar_init(&bar, 1);
         fence_barrier_init();
         s_flag = ld_volatile_u64(P.abort_word) != 0ull;

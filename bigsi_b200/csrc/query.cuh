@@ -25,8 +25,14 @@ constexpr int kMaxSinks = 9;   // host + up to 8 GPUs of one box
 // front-end's table) over kStreamRing queries, the small state blocks over kStreamStates
 constexpr int kStreamRing = 4;
 constexpr int kStreamStates = 8;
-constexpr int kReduceThreads = 128;           // threads of a reduce-kernel CTA (it shares its SM with a gather CTA)
-constexpr int kReduceSmemBytes = 32 * 1024;   // its dynamic shared memory
+// A reduce CTA is resident from the moment the last gather CTA of its query STARTS until the merge is done (about
+// one gather-kernel duration asleep in the dependency wait + the merge), i.e. longer than the cadence of
+// back-to-back queries: TWO reduce CTAs (of consecutive queries) must fit on an SM beside one gather CTA, or the
+// next query's reduce kernel cannot become resident, cannot signal its dependents, and the gather kernels stall
+// (measured: 43 us per query with one reduce slot per SM).  64 threads x 128 registers and 16 KB each.
+constexpr int kReduceThreads = 64;
+constexpr int kReduceSmemBytes = 16 * 1024;   // its dynamic shared memory
+constexpr int kReduceSlotsPerSm = 2;
 constexpr int kSmBytes = 228 * 1024;          // shared memory of one SM; every resident CTA reserves 1 KB of it
 
 enum { kModeCounts = 0, kModeAnd = 1 };

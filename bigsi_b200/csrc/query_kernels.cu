@@ -351,6 +351,7 @@ constexpr int kBarHashGroup = 1;   // named barrier of the consumer warps while 
 constexpr int kBarIdsReady = 2;    // consumers -> producer: the id table is complete
 constexpr uint32_t kStageCntOffset = 640;  // uint32 [kMaxStages] k-mers per ring slot, in the shared-memory header
 constexpr uint32_t kPoolStashOffset = 768; // int32 [kPoolBatch][kPoolMaxH] row ids of one claimed pool batch
+constexpr uint32_t kSeqCountOffset = 536;  // uint32: unique windows of this CTA (sequence front-end)
 constexpr uint32_t kGateOffset = 528;      // int: 1 = the entry gate passed (behind the 2 x kMaxStages mbarriers)
 constexpr int kPoolBatch = 8;
 
@@ -361,20 +362,24 @@ struct SoloGeom {
     uint32_t n_pool;    // the last n_pool go to the shared pool
     uint32_t n_first;   // static k-mers the producer warp hashes itself (one ring-full)
     uint64_t total;     // k-mers of the query: P.total_kmers, or *P.total_dev when a preceding kernel determines it
+    // sequence front-end: the CTA's staged span of the sequence and the list of its unique windows (offsets into it)
+    const uint8_t *span;
+    const uint16_t *ulist;
 };
 __device__ __forceinline__ uint32_t solo_range_cnt(const QueryParams &P, uint32_t cta, uint64_t total)
 {
     const uint64_t b = (uint64_t)cta * P.items_per_slice;
     return b >= total ? 0u : (uint32_t)min((uint64_t)P.items_per_slice, total - b);
 }
-__device__ __forceinline__ SoloGeom solo_geometry(const QueryParams &P)
+// seq_cnt: sequence front-end -- the number of unique windows this CTA represents (its k-mers are listed in shared memory)
+__device__ __forceinline__ SoloGeom solo_geometry(const QueryParams &P, uint32_t seq_cnt)
 {
     SoloGeom g;
     // the geometry was planned for P.total_kmers (an upper bound when total_dev is set): fewer k-mers only
     // leave the ranges of the last CTAs short or empty
-    g.total = P.total_dev ? min((uint64_t)__ldcg(P.total_dev), P.total_kmers) : P.total_kmers;
+    g.total = (P.total_dev && !P.seq_mode) ? min((uint64_t)__ldcg(P.total_dev), P.total_kmers) : P.total_kmers;
     g.begin = (uint64_t)blockIdx.x * P.items_per_slice;
-    g.cnt = solo_range_cnt(P, blockIdx.x, g.total);
+    g.cnt = P.seq_mode ? seq_cnt : solo_range_cnt(P, blockIdx.x, g.total);
     g.n_pool = min(P.pool_share, g.cnt);
     g.n_static = g.cnt - g.n_pool;
     g.n_first = min(g.n_static, P.n_stages * P.kmers_per_stage);
@@ -415,8 +420,11 @@ __device__ __forceinline__ void solo_producer(const QueryParams &P, const SoloGe
     };
 
     // the first ring-full of k-mers is hashed by this warp alone, so the gather starts at once
-    hash_kmers_group(P.kmers + sg.begin * P.k, sg.n_first, (int)P.k, (int)h, P.num_rows, 1, scratch, ids, lane, 32u,
-                     SyncWarp(), P.mod_magic, &P.ll);
+    if (P.seq_mode)
+        hash_window_list(sg.span, sg.ulist, sg.n_first, (int)P.k, (int)h, P.num_rows, P.mod_magic, ids, lane, 32u);
+    else
+        hash_kmers_group(P.kmers + sg.begin * P.k, sg.n_first, (int)P.k, (int)h, P.num_rows, 1, scratch, ids, lane, 32u,
+                         SyncWarp(), P.mod_magic, &P.ll);
     __syncwarp();
     if (lane == 0) BIGSI_TS(1);
     uint32_t k0 = 0;
@@ -473,12 +481,15 @@ __device__ __forceinline__ void solo_producer(const QueryParams &P, const SoloGe
         if (lane < n && idx < pool_total) {
             owner = idx % gridDim.x;
             j = idx / gridDim.x;
-            real = j < min(P.pool_share, solo_range_cnt(P, owner, sg.total));  // short ranges pool fewer k-mers
+            // the owner's ready word = launch epoch (high half) | number of k-mers it pooled (short ranges pool fewer)
+            unsigned long long word = 0;
+            bounded_wait(P.abort_word, P.host_abort, P.spin_timeout_ns, kAbortPool, P.stream_seq, [&]() {
+                word = ld_acquire_gpu_u64(P.pool_ready + owner);
+                return (uint32_t)(word >> 32) == (uint32_t)P.pool_epoch;
+            });
+            real = j < (uint32_t)word;
         }
         if (base + n >= pool_total) exhausted = true;
-        if (real)
-            bounded_wait(P.abort_word, P.host_abort, P.spin_timeout_ns, kAbortPool, P.stream_seq,
-                         [&]() { return ld_acquire_gpu_u64(P.pool_ready + owner) >= P.pool_epoch; });
         const uint32_t real_mask = __ballot_sync(0xffffffffu, real);
         for (uint32_t t0 = 0; t0 < n * h; t0 += 32) {  // warp-uniform trip count (shuffles inside)
             const uint32_t t = t0 + lane;
@@ -519,9 +530,13 @@ __device__ __forceinline__ void solo_consumer(const QueryParams &P, const SoloGe
 
     // hash the part of the range the producer did not take, publish the pooled ids, release the producer
     const uint32_t rest = sg.cnt - sg.n_first;
-    hash_kmers_group(P.kmers + (sg.begin + sg.n_first) * P.k, rest, (int)P.k, (int)P.h, P.num_rows, 1,
-                     scratch + ((hash_scratch_bytes(sg.n_first, P.k) + 127) & ~127ull), ids + (size_t)sg.n_first * P.h, unit,
-                     consumer_threads, GroupSync{kBarHashGroup, (int)consumer_threads}, P.mod_magic, &P.ll);
+    if (P.seq_mode)
+        hash_window_list(sg.span, sg.ulist + sg.n_first, rest, (int)P.k, (int)P.h, P.num_rows, P.mod_magic,
+                         ids + (size_t)sg.n_first * P.h, unit, consumer_threads);
+    else
+        hash_kmers_group(P.kmers + (sg.begin + sg.n_first) * P.k, rest, (int)P.k, (int)P.h, P.num_rows, 1,
+                         scratch + ((hash_scratch_bytes(sg.n_first, P.k) + 127) & ~127ull), ids + (size_t)sg.n_first * P.h, unit,
+                         consumer_threads, GroupSync{kBarHashGroup, (int)consumer_threads}, P.mod_magic, &P.ll);
     named_bar_sync(kBarHashGroup, consumer_threads);
     if (P.pool_share) {
         int32_t *dst = P.pool_ids + (size_t)blockIdx.x * P.pool_share * P.h;
@@ -530,7 +545,7 @@ __device__ __forceinline__ void solo_consumer(const QueryParams &P, const SoloGe
         named_bar_sync(kBarHashGroup, consumer_threads);
         if (unit == 0) {  // one cumulative fence behind the barrier publishes every thread's ids
             __threadfence();
-            st_release_gpu_u64(P.pool_ready + blockIdx.x, P.pool_epoch);
+            st_release_gpu_u64(P.pool_ready + blockIdx.x, (P.pool_epoch << 32) | (unsigned long long)sg.n_pool);
         }
     }
     named_bar_arrive(kBarIdsReady, blockDim.x);
@@ -612,6 +627,11 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) gather_solo(const __grid_
     grid_launch_dependents();
     if (threadIdx.x == 0) {
         BIGSI_TS(0);
+        if (P.debug_ts) {
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            P.debug_ts[(size_t)blockIdx.x * kDebugStamps + 15] = smid;
+        }
         for (uint32_t s = 0; s < P.n_stages; ++s) {
             mbar_init(&full[s], 1);                // one arrive.expect_tx by the producer + tx bytes
             mbar_init(&empty[s], consumer_warps);  // one arrive per consumer warp
@@ -635,8 +655,52 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) gather_solo(const __grid_
     if (threadIdx.x == 0) BIGSI_TS(8);
     if (blockIdx.x == 0 && threadIdx.x == 0 && P.n_hits != nullptr) P.n_hits[0] = 0ull;  // the reduce kernel adds to it
 
-    const SoloGeom sg = solo_geometry(P);
     uint8_t *scratch = smem + kSmemHeaderBytes + P.ids_table_bytes;
+    uint32_t seq_cnt = 0;
+    const uint8_t *span = nullptr;
+    const uint16_t *ulist = nullptr;
+    if (P.seq_mode) {
+        // sequence front-end (hash.cuh): this CTA's windows [w0, w0 + cw) of the sequence; the whole CTA stages the
+        // span with one round trip of 16-byte loads (the sequence may live in mapped host memory), every window
+        // tries to claim its string in the table, the winners are listed -- they are this CTA's k-mers
+        volatile uint32_t *s_cnt = reinterpret_cast<volatile uint32_t *>(smem + kSeqCountOffset);
+        const uint64_t n = P.total_kmers;
+        const uint64_t w0 = (uint64_t)blockIdx.x * P.items_per_slice;
+        const uint32_t cw = w0 >= n ? 0u : (uint32_t)min((uint64_t)P.items_per_slice, n - w0);
+        if (threadIdx.x == 0) *s_cnt = 0;
+        const uint8_t *g0 = P.kmers + w0;
+        const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15);
+        const uint32_t nvec = cw ? (skew + cw + P.k - 1 + 15) >> 4 : 0u;
+        const uint4 *a0 = reinterpret_cast<const uint4 *>(g0 - skew);
+        uint4 *sv = reinterpret_cast<uint4 *>(scratch);
+        for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) sv[i] = __ldg(a0 + i);
+        __syncthreads();
+        span = scratch + skew;
+        uint16_t *list = reinterpret_cast<uint16_t *>(scratch + ((P.items_per_slice + P.k + 47u) & ~15u));
+        ulist = list;
+        const SeqTable T{P.seq_table, P.seq_table_entries - 1, P.seq_epoch, P.kmers};
+        const uint32_t lane = threadIdx.x & 31;
+        for (uint32_t base = 0; base < cw; base += blockDim.x) {  // block-uniform trip count (ballots inside)
+            const uint32_t w = base + threadIdx.x;
+            const bool win = w < cw && seq_table_insert(T, span + w, (int)P.k, w0 + w, span, w0, cw);
+            const uint32_t mask = __ballot_sync(0xffffffffu, win);
+            uint32_t pos = 0;
+            if (mask) {
+                if (lane == 0) pos = atomicAdd(const_cast<uint32_t *>(s_cnt), (uint32_t)__popc(mask));
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+            }
+            if (win) list[pos + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)w;
+        }
+        __syncthreads();
+        seq_cnt = *s_cnt;
+        if (threadIdx.x == 0) {
+            if (seq_cnt) atomicAdd(&P.qstate->n_unique, (unsigned long long)seq_cnt);
+            BIGSI_TS(10);
+        }
+    }
+    SoloGeom sg = solo_geometry(P, seq_cnt);
+    sg.span = span;
+    sg.ulist = ulist;
     if ((threadIdx.x >> 5) == consumer_warps)
         solo_producer(P, sg, smem, ring, ids, scratch, full, empty);
     else

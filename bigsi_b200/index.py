@@ -277,6 +277,58 @@ class DeviceIndex:
         order = np.argsort(c, kind="stable")
         return c[order], v[order], ni, int(u[0])
 
+    @staticmethod
+    def _seq_array(seq):
+        if isinstance(seq, (bytes, bytearray)):
+            return np.frombuffer(seq, dtype=np.uint8)
+        return np.ascontiguousarray(seq, dtype=np.uint8)
+
+    def search_sequence_submit(self, seq, k, h, threshold, cap=None):
+        """First half of search_sequence: stage the sequence and launch; returns a ticket for search_sequence_wait.
+        Up to 8 tickets may be outstanding; one host thread can so keep several handles (column shards) busy."""
+        arr = self._seq_array(seq)
+        cap = self.num_cols if cap is None else int(cap)
+        ticket = ctypes.c_uint64(0)
+        check(self._L.bigsi_b200_search_sequence_submit(self.handle, arr.ctypes.data if arr.size else 0, arr.size, k, h,
+                                                        float(threshold), cap, ctypes.byref(ticket)))
+        return ticket.value, cap
+
+    def search_sequence_wait(self, ticket):
+        """(colours int32 ascending, counts uint32, n_hits, num_kmers U) of a submitted search."""
+        ticket, cap = ticket
+        cols = np.empty(max(cap, 1), dtype=np.int32)
+        cnts = np.empty(max(cap, 1), dtype=np.uint32)
+        n, u = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        check(self._L.bigsi_b200_search_sequence_wait(self.handle, ticket, cols.ctypes.data, cnts.ctypes.data, cap,
+                                                      ctypes.byref(n), ctypes.byref(u)))
+        m = min(n.value, cap)
+        order = np.argsort(cols[:m], kind="stable")
+        return cols[:m][order], cnts[:m][order], n.value, u.value
+
+    def search_sequences(self, seqs, k, h, threshold, cap=1024):
+        """bulk_search: a list of sequences (bytes) through one C-ABI call, pipelined on the device.  Returns a list of
+        (colours int32 ascending, counts uint32, n_hits, num_kmers U), one per sequence; hit lists longer than `cap`
+        are cut (n_hits stays exact)."""
+        nq = len(seqs)
+        if nq == 0:
+            return []
+        offsets = np.zeros(nq + 1, dtype=np.uint64)
+        np.cumsum([len(s) for s in seqs], out=offsets[1:])
+        blob = np.frombuffer(b"".join(bytes(s) for s in seqs), dtype=np.uint8) if offsets[-1] else np.zeros(1, dtype=np.uint8)
+        cap = int(cap)
+        cols = np.empty((nq, max(cap, 1)), dtype=np.int32)
+        cnts = np.empty((nq, max(cap, 1)), dtype=np.uint32)
+        n = np.zeros(nq, dtype=np.uint64)
+        u = np.zeros(nq, dtype=np.uint64)
+        check(self._L.bigsi_b200_search_sequences(self.handle, blob.ctypes.data, offsets.ctypes.data, nq, k, h, float(threshold),
+                                                  cols.ctypes.data, cnts.ctypes.data, cap, n.ctypes.data, u.ctypes.data))
+        out = []
+        for q in range(nq):
+            m = min(int(n[q]), cap)
+            order = np.argsort(cols[q, :m], kind="stable")
+            out.append((cols[q, :m][order], cnts[q, :m][order], int(n[q]), int(u[q])))
+        return out
+
     def lookup_kmers(self, kmers, k, h):
         """Per-k-mer AND vectors: uint8 [n, ceil(N/8)] (graph/index.py:42-49)."""
         arr = kmers if isinstance(kmers, np.ndarray) else kmers_to_array(list(kmers), k)

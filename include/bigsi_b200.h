@@ -204,7 +204,9 @@ int bigsi_b200_search_kmers_hits(bigsi_b200_index *index, const char *kmers, con
                                  uint64_t n_queries, int k, int h, const uint32_t *min_kmers,
                                  int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_out);
 /* BIGSI.search's whole filter stage for ONE sequence (graph/bigsi.py:174-230) on the device: every
- * window of length k (utils/fncts.py:63-65), de-duplicated as RAW byte strings (graph/index.py:45),
+ * window of length k (utils/fncts.py:63-65), de-duplicated as RAW byte strings (graph/index.py:45) -- for k <= 32
+ * inside the gather kernel itself: every CTA stages its span of the sequence (read straight out of pinned host
+ * memory) and claims its windows in an exact hash table; else by a front-end kernel --,
  * *num_kmers_out = U = number of unique k-mers, min_kmers = ceil(U * threshold) in IEEE double
  * (<= 0 keeps every column), then canonical + hash + gather-AND-count + threshold.  Hits as in
  * bigsi_b200_search_kmers_hits for one query (order unspecified, *n_hits_out may exceed cap).
@@ -212,6 +214,21 @@ int bigsi_b200_search_kmers_hits(bigsi_b200_index *index, const char *kmers, con
 int bigsi_b200_search_sequence(bigsi_b200_index *index, const char *seq, uint64_t len, int k, int h, double threshold,
                                int32_t *cols_out, uint32_t *counts_out, uint64_t cap, uint64_t *n_hits_out,
                                uint64_t *num_kmers_out);
+/* The same search split in two halves, so that several searches are in flight on one handle (and one host thread
+ * can drive several handles, i.e. several column shards, at once): submit stages the sequence and launches the
+ * kernels, wait returns the result of that ticket.  Up to 8 tickets may be outstanding per handle; tickets are
+ * collected in any order.  Consecutive searches overlap on the device (see "streamed single-query launches"). */
+int bigsi_b200_search_sequence_submit(bigsi_b200_index *index, const char *seq, uint64_t len, int k, int h, double threshold,
+                                      uint64_t cap, uint64_t *ticket_out);
+int bigsi_b200_search_sequence_wait(bigsi_b200_index *index, uint64_t ticket, int32_t *cols_out, uint32_t *counts_out,
+                                    uint64_t cap, uint64_t *n_hits_out, uint64_t *num_kmers_out);
+/* bulk_search (bigsi/__main__.py:261-314: every record of a FASTA file through BIGSI.search with one threshold):
+ * sequence q = seqs[offsets[q] .. offsets[q+1]); outputs of sequence q at cols_out / counts_out + q*cap,
+ * n_hits_out[q], num_kmers_out[q], each exactly as bigsi_b200_search_sequence would return them.  The searches are
+ * pipelined (up to 7 in flight). */
+int bigsi_b200_search_sequences(bigsi_b200_index *index, const char *seqs, const uint64_t *offsets, uint64_t n_seqs, int k,
+                                int h, double threshold, int32_t *cols_out, uint32_t *counts_out, uint64_t cap,
+                                uint64_t *n_hits_out, uint64_t *num_kmers_out);
 /* lookup(): per-k-mer AND vectors to host, out = uint8 [n][out_stride]. */
 int bigsi_b200_lookup_kmers(bigsi_b200_index *index, const char *kmers, uint64_t n, int k, int h,
                             uint8_t *out, uint64_t out_stride);

@@ -865,3 +865,50 @@ def test_search_sequence_front_end(B):
         assert U == len(uk) and n_hits == len(exp) and np.array_equal(cols, exp) and np.array_equal(vals, cnt[exp])
     finally:
         ix.close()
+
+
+def test_search_sequences_bulk_and_tickets(B):
+    """bulk_search (one C-ABI call, pipelined searches with the front-end inside the gather kernel) and the
+    submit / wait halves: every result identical to the oracle's search of the same sequence, whatever is in flight
+    around it -- sequences with heavy repeats (many windows lose their table entry to another CTA's window),
+    non-ACGT bytes, one window, no window, and a sequence too long for the streamed plan in the middle."""
+    rng = np.random.default_rng(71)
+    m, N, h, k = 20_011, 5000, 3, 31
+    ix, packed = _random_index(B, rng, m, N, density=0.9)
+    oix = O.OracleIndex(k, m, h, N, rows=packed)
+    try:
+        base = "".join(rng.choice(list("ACGT"), size=12_000))
+        unit = base[:31]
+        seqs = [base[:9000], base[100:400] * 20, unit * 28 + unit[:5], "ACGT" * 500, base[:k], base[: k - 1], "",
+                base[2000:5000].lower() + "N" + base[:3000], base[:6000] + base[:6000], "A" * 5000,
+                "".join(rng.choice(list("ACGT"), size=230_000)), base[500:9500], base[:4000] + "T" + base[:4000]]
+        seqs = seqs + [base[i * 37 : i * 37 + 3000 + 13 * i] for i in range(30)]
+        for thr in (1.0, 0.6, 0.0):
+            res = ix.search_sequences([s.encode() for s in seqs], k, h, thr, cap=N)
+            assert len(res) == len(seqs)
+            for q, (seq, (cols, vals, n_hits, U)) in enumerate(zip(seqs, res)):
+                uk = O.unique_kmers(seq, k)
+                assert U == len(uk), (q, thr, U, len(uk))
+                if not uk:
+                    assert n_hits == 0
+                    continue
+                cnt = oix.counts(uk)
+                exp = np.nonzero(cnt >= max(math.ceil(len(uk) * thr), 0))[0]
+                assert n_hits == len(exp) and np.array_equal(cols, exp) and np.array_equal(vals, cnt[exp]), (q, thr)
+        # a small capacity cuts the list, the count stays exact
+        res = ix.search_sequences([s.encode() for s in seqs[:4]], k, h, 0.0, cap=16)
+        assert all(n == N and len(c) == 16 for c, v, n, u in res)
+        # tickets collected out of order, eight in flight
+        tickets = [ix.search_sequence_submit(s.encode(), k, h, 0.7) for s in seqs[13:21]]
+        with pytest.raises(B.BigsiB200Error):
+            ix.search_sequence_submit(seqs[0].encode(), k, h, 0.7)  # a ninth
+        for j in (3, 0, 7, 1, 2, 6, 5, 4):
+            cols, vals, n_hits, U = ix.search_sequence_wait(tickets[j])
+            uk = O.unique_kmers(seqs[13 + j], k)
+            cnt = oix.counts(uk)
+            exp = np.nonzero(cnt >= math.ceil(len(uk) * 0.7))[0]
+            assert U == len(uk) and n_hits == len(exp) and np.array_equal(cols, exp) and np.array_equal(vals, cnt[exp]), j
+        with pytest.raises(B.BigsiB200Error):
+            ix.search_sequence_wait(tickets[0])  # collected already
+    finally:
+        ix.close()

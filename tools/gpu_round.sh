@@ -2,7 +2,7 @@
 # One gpurun call of the development loop: smoke, targeted parity tests, bench (+ timeline), full GPU suite.
 # usage: tools/gpu_round.sh <tag> [pytest -k expression for the targeted pass]
 TAG=${1:-dev}
-KEXPR=${2:-"exchange or solo_path or zero_copy or device_pointer or search_sequence"}
+KEXPR=${2:-"exchange or solo_path or zero_copy or device_pointer or search_sequence or golden or config1"}
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1
