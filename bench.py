@@ -530,8 +530,9 @@ def run_e2e(args, index, searcher, shard, queries, h_queries, barrier, rank, wor
 
         store = _bg._Store(index, args.m, H, K)
         _bg.SampleMetadata(store.meta).add_samples(["s%d" % c for c in range(cols)])
-        _bg._STORES["bench-e2e"] = store
-        api = _bg.BIGSI({"k": K, "m": args.m, "h": H, "storage-engine": "b200", "storage-config": {"filename": "bench-e2e"}})
+        api_cfg = {"k": K, "m": args.m, "h": H, "storage-engine": "b200", "storage-config": {"filename": "bench-e2e", "device": index.info()["device"]}}
+        _bg._STORES[_bg._store_key(api_cfg)] = store
+        api = _bg.BIGSI(api_cfg)
         s_strs = [s.decode("ascii") for s in h_seqs]
         for q in range(3):
             r = api.search(s_strs[q], 1.0)
@@ -540,7 +541,7 @@ def run_e2e(args, index, searcher, shard, queries, h_queries, barrier, rank, wor
         for q in range(QPS):
             api.search(s_strs[q], 1.0)
         dt = time.perf_counter() - w0
-        del _bg._STORES["bench-e2e"]
+        del _bg._STORES[_bg._store_key(api_cfg)]
         extra["python_search"] = {"value": U * QPS / dt, "us_per_query": 1e6 * dt / QPS,
                                   "path": "bigsi_b200.BIGSI(config).search(seq, threshold=1.0): str in, list of result dicts out"}
     else:

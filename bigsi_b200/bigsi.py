@@ -17,6 +17,7 @@ index is therefore cached per process, keyed by the storage name, and never re-u
 import json
 import logging
 import math
+import threading
 
 import numpy as np
 
@@ -24,6 +25,7 @@ from . import bits as _bits
 from ._lib import MODE_AND, MODE_COUNTS
 from .bloom import BloomFilter
 from .index import DeviceIndex, bloom_kmers, file_info, hash_kmers, kmers_to_array
+from .sharded_index import make_index
 from .metadata import DELETION_SPECIAL_SAMPLE_NAME, SampleMetadata
 from .scoring import Scorer
 from .utils import convert_query_kmers, seq_to_kmers, unique_kmers
@@ -35,12 +37,14 @@ DEFAULT_CONFIG = {  # bigsi/constants.py:13-19 with the HBM engine in place of a
     "k": 31,
     "m": 25 * 10 ** 6,
     "storage-engine": "b200",
+    # "device": one GPU; "devices": [0, 1, ...] column-shards the matrix over several GPUs of the box (sharded_index.py)
     "storage-config": {"filename": "bigsi-b200-default", "device": 0},
 }
 DEFAULT_NPROC = 4
 MIN_UNIQUE_KMERS_IN_QUERY = 0
 
-_STORES = {}  # storage name -> _Store (the process-resident replacement of the KV store)
+_STORES = {}  # (storage name, devices) -> _Store (the process-resident replacement of the KV store)
+_STORES_LOCK = threading.RLock()
 
 
 class _Store:
@@ -62,8 +66,36 @@ def _store_name(config):
     return str(sc.get("filename", sc.get("name", "bigsi-b200-default")))
 
 
+def _devices(config):
+    """storage-config.devices (a list: column shards over several GPUs) or storage-config.device (one GPU)."""
+    sc = config.get("storage-config", {}) or {}
+    devs = sc.get("devices")
+    if devs is None:
+        return [int(sc.get("device", 0))]
+    if isinstance(devs, int):
+        devs = [devs]
+    devs = [int(d) for d in devs]  # (an ordinal may repeat: several shards on one GPU -- pointless in production, handy for tests)
+    if not devs:
+        raise ValueError("storage-config.devices must be a non-empty list of device ordinals")
+    return devs
+
+
 def _device(config):
-    return int((config.get("storage-config", {}) or {}).get("device", 0))
+    return _devices(config)[0]
+
+
+def _store_key(config):
+    return (_store_name(config), tuple(_devices(config)))
+
+
+def _register(config, store):
+    """Put `store` under config's key; a store it replaces is closed (objects that still hold it get 'index has been
+    destroyed' from their next call, as with a reference store deleted under its users)."""
+    with _STORES_LOCK:
+        old = _STORES.pop(_store_key(config), None)
+        _STORES[_store_key(config)] = store
+    if old is not None and old is not store:
+        old.close()
 
 
 def merge_packed_rows(a, n1, b, n2):
@@ -121,12 +153,13 @@ class BIGSI(SampleMetadata):
         if config is None:
             config = DEFAULT_CONFIG
         self.config = config
-        name = _store_name(config)
-        if name not in _STORES:
-            # the reference raises KeyError from storage.get_integer on an empty store
-            # (graph/index.py:24, matrix/bitmatrix.py:16-17)
-            raise KeyError("no index has been built for storage '%s'" % name)
-        self._store = _STORES[name]
+        key = _store_key(config)
+        with _STORES_LOCK:
+            if key not in _STORES:
+                # the reference raises KeyError from storage.get_integer on an empty store
+                # (graph/index.py:24, matrix/bitmatrix.py:16-17)
+                raise KeyError("no index has been built for storage '%s' on devices %s" % key)
+            self._store = _STORES[key]
         SampleMetadata.__init__(self, self._store.meta)
         self.min_unique_kmers_in_query = MIN_UNIQUE_KMERS_IN_QUERY
         self.scorer = Scorer(self.num_samples)  # graph/bigsi.py:140 (DB size fixed at construction)
@@ -166,13 +199,14 @@ class BIGSI(SampleMetadata):
         """graph/bigsi.py:157-172: N Bloom filters become the N columns of the m x N matrix."""
         validate_build_params(bloomfilters, samples)
         m, h, k = config["m"], config["h"], config["k"]
-        name = _store_name(config)
-        if name in _STORES:
-            _STORES.pop(name).close()
+        with _STORES_LOCK:
+            old = _STORES.pop(_store_key(config), None)
+        if old is not None:
+            old.close()
         n = len(bloomfilters)
         sc = config.get("storage-config", {}) or {}
         capacity = int(sc.get("col_capacity", 0)) or max(n, 1)
-        index = DeviceIndex(m, n, col_capacity=capacity, col_offset=0, device=_device(config))
+        index = make_index(m, n, col_capacity=capacity, devices=_devices(config))
         store = _Store(index, m, h, k)
         try:
             SampleMetadata(store.meta).add_samples(samples)
@@ -193,7 +227,7 @@ class BIGSI(SampleMetadata):
         except Exception:
             store.close()
             raise
-        _STORES[name] = store
+        _register(config, store)
         return cls(config)
 
     def insert(self, bloomfilter, sample):
@@ -211,26 +245,14 @@ class BIGSI(SampleMetadata):
         nbits = m if nbits is None else min(nbits, m)
         info = self.index.info()
         if column_index >= info["col_capacity"]:
-            self._grow(max(column_index + 1, 2 * info["col_capacity"]))
+            # re-pitch when an insert exceeds the column capacity (a sharded index grows its last shard itself)
+            self._store.index = self.index.grown(max(column_index + 1, 2 * info["col_capacity"]))
         self.index.set_column(column_index, p, nbits)
-
-    def _grow(self, new_capacity):
-        """Re-pitch the matrix when an insert exceeds the column capacity (host round trip)."""
-        old = self.index
-        info = old.info()
-        new = DeviceIndex(info["num_rows"], info["num_cols"], col_capacity=new_capacity,
-                          col_offset=info["col_offset"], device=info["device"])
-        step = max(1, (1 << 26) // max(info["row_bytes"], 1))
-        for r0 in range(0, info["num_rows"], step):
-            n = min(step, info["num_rows"] - r0)
-            new.upload_rows(r0, old.download_rows(r0, n))
-        self._store.index = new
-        old.close()
 
     def delete(self):
         """graph/bigsi.py:249-250: storage.delete_all()."""
-        name = _store_name(self.config)
-        st = _STORES.pop(name, None)
+        with _STORES_LOCK:
+            st = _STORES.pop(_store_key(self.config), None)
         if st is not None:
             st.close()
 
@@ -246,8 +268,8 @@ class BIGSI(SampleMetadata):
         old, other = self.index, bigsi.index
         info = old.info()
         n1, n2 = info["num_cols"], other.num_cols
-        new = DeviceIndex(info["num_rows"], n1 + n2, col_capacity=max(info["col_capacity"], n1 + n2),
-                          col_offset=info["col_offset"], device=info["device"])
+        new = make_index(info["num_rows"], n1 + n2, col_capacity=max(info["col_capacity"], n1 + n2),
+                         col_offset=info["col_offset"], devices=_devices(self.config))
         try:
             step = max(1, (1 << 24) // max((n1 + n2 + 7) // 8, 1))
             for r0 in range(0, info["num_rows"], step):
@@ -289,7 +311,10 @@ class BIGSI(SampleMetadata):
         dictionaries."""
         assert threshold <= 1
         if not (isinstance(seq, str) and seq.isascii()):
-            return self._search_host_kmers(seq, threshold, score)
+            # The reference hashes the UTF-8 bytes of each k-character window (bloom/bloomfilter.py:5-6), so a window
+            # with a non-ASCII character is longer than k bytes; this engine works on fixed k-byte windows.  DNA
+            # queries are ASCII: anything else is rejected instead of being answered differently (DESIGN.md section 5).
+            raise ValueError("BIGSI.search takes an ASCII str sequence")
         n = self.num_samples
         colours, found, n_hits, num_kmers = self.index.search_sequence(seq.encode("ascii"), self.kmer_size, self.num_hashes,
                                                                        threshold, cap=max(self.index.num_cols, 1))
@@ -310,24 +335,6 @@ class BIGSI(SampleMetadata):
             order = np.argsort(-found.astype(np.int64), kind="stable")
             results = [BigsiQueryResult(colour=int(colours[i]), sample_name=self.colour_to_sample(int(colours[i])),
                                         num_kmers_found=int(found[i]), num_kmers=num_kmers) for i in order]
-        if score:
-            self.score(seq, results)
-        return [r.todict() for r in results if not r.sample_name == DELETION_SPECIAL_SAMPLE_NAME]
-
-    def _search_host_kmers(self, seq, threshold, score):
-        """The same search with the k-mer set built in Python (non-ASCII sequences, score=True)."""
-        self.__validate_search_query(seq)
-        kmers = list(self.seq_to_kmers(seq))
-        uk = unique_kmers(kmers)
-        num_kmers = len(uk)
-        if num_kmers == 0:
-            raise TypeError("reduce() of empty iterable with no initial value")
-        min_kmers = math.ceil(num_kmers * threshold)
-        arr = kmers_to_array(uk, self.kmer_size)
-        if threshold == 1.0:
-            results = self.exact_filter(arr, num_kmers)
-        else:
-            results = self.inexact_filter(arr, num_kmers, min_kmers)
         if score:
             self.score(seq, results)
         return [r.todict() for r in results if not r.sample_name == DELETION_SPECIAL_SAMPLE_NAME]
@@ -388,12 +395,13 @@ class BIGSI(SampleMetadata):
     def load(cls, config, path):
         """Open an index file written by save() into HBM (file -> pinned double buffer -> device) and
         register it under config's storage name.  config["k"/"m"/"h"] are taken from the file."""
+        config = dict(config)  # k / m / h below come from the file: the caller's dict is not touched
         hd, meta_bytes = file_info(path)
         meta = json.loads(meta_bytes.decode("utf-8"))
         sc = config.get("storage-config", {}) or {}
         capacity = max(int(sc.get("col_capacity", 0)), hd["num_cols"], 1)
-        index = DeviceIndex(hd["num_rows"], hd["num_cols"], col_capacity=capacity, col_offset=hd["col_offset"],
-                            device=_device(config))
+        index = make_index(hd["num_rows"], hd["num_cols"], col_capacity=capacity, col_offset=hd["col_offset"],
+                           devices=_devices(config))
         try:
             index.load_rows(path, hd["rows_offset"], hd["row_bytes"], 0, 0, hd["num_rows"])
         except Exception:
@@ -403,10 +411,7 @@ class BIGSI(SampleMetadata):
         for key, value in meta["metadata"]:
             store.meta[("metadata", key)] = value
         config["k"], config["m"], config["h"] = meta["k"], meta["m"], meta["h"]
-        name = _store_name(config)
-        if name in _STORES:
-            _STORES.pop(name).close()
-        _STORES[name] = store
+        _register(config, store)
         return cls(config)
 
     def to_kv(self, rows_per_chunk=4096):
@@ -441,13 +446,14 @@ class BIGSI(SampleMetadata):
         def get_int(key):
             return int(bytes(kv[("%s:int" % key).encode("utf-8")]).decode("utf-8"))
 
+        config = dict(config)  # m / h below come from the store: the caller's dict is not touched
         m, h = get_int("ksi:bloomfilter_size"), get_int("ksi:num_hashes")
         n_rows, n_cols = get_int("number_of_rows"), get_int("number_of_cols")
         if n_rows != m:
             raise ValueError("number_of_rows=%d differs from ksi:bloomfilter_size=%d" % (n_rows, m))
         sc = config.get("storage-config", {}) or {}
         capacity = max(int(sc.get("col_capacity", 0)), n_cols, 1)
-        index = DeviceIndex(m, n_cols, col_capacity=capacity, col_offset=0, device=_device(config))
+        index = make_index(m, n_cols, col_capacity=capacity, devices=_devices(config))
         store = _Store(index, m, h, config["k"])
         try:
             row_bytes = (n_cols + 7) // 8
@@ -472,10 +478,7 @@ class BIGSI(SampleMetadata):
             store.close()
             raise
         config["m"], config["h"] = m, h
-        name = _store_name(config)
-        if name in _STORES:
-            _STORES.pop(name).close()
-        _STORES[name] = store
+        _register(config, store)
         return cls(config)
 
     def __warn_few_kmers(self, n):

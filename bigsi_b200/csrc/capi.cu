@@ -163,7 +163,7 @@ struct bigsi_b200_index {
     bool timing = false;
     int64_t opt_debug_flags = 0;
     int64_t opt_prehash = 1, opt_fuse_merge = 1, opt_merge_chunk_bytes = 0, opt_solo = 1, opt_pool_pct = -1, opt_zero_copy = 1, opt_cooperative = 1;
-    int64_t opt_inputs_ready = 0, opt_spin_timeout_ms = 10000;
+    int64_t opt_inputs_ready = 0, opt_spin_timeout_ms = 10000, opt_exit_gate = 1;
     // streamed single-query launches (query.cuh:kStreamRing): ring-buffered scratch + the completion / abort words
     DevBuf d_pool;            // kStreamRing x [ready flags: grid x u64][ids: grid x pool_share x h x i32]
     uint64_t pool_slot_bytes = 0;
@@ -213,6 +213,7 @@ struct bigsi_b200_index {
 
 namespace {
 
+constexpr uint64_t kPoolFlagEntries = 16384, kPoolFlagBytes = kPoolFlagEntries * 8;
 constexpr uint64_t kStreamStateBytes = 3 * 64 + (uint64_t)kStreamStates * sizeof(QState);
 // shared memory a streamed gather CTA may use so that a reduce CTA (kReduceSmemBytes + its static words) still
 // fits on the same SM; every resident CTA reserves 1 KB
@@ -362,7 +363,7 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
         // common finish line to balance for (the SM simply goes on with the next query).
         const uint64_t c = p.items_per_slice;
         const uint64_t pct = ix->opt_pool_pct >= 0 ? (uint64_t)ix->opt_pool_pct : (isolated ? 12u : 0u);
-        uint64_t pp = (c >= 16 && h <= kPoolMaxH) ? (c * pct + 50) / 100 : 0;
+        uint64_t pp = (c >= 16 && h <= kPoolMaxH && (uint64_t)grid <= kPoolFlagEntries) ? (c * pct + 50) / 100 : 0;
         if (pp > c) pp = c;
         if (mode == BIGSI_B200_MODE_COUNTS && pp) {
             uint32_t pps = bits_of(c + 2 * pp);
@@ -381,7 +382,10 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
         const uint32_t scratch = query_smem_bytes(p) - kSmemHeaderBytes - p.ids_bytes;  // the drained ring
         plan_merge(p, mode, scratch, (uint64_t)grid, (uint32_t)ix->opt_merge_chunk_bytes);
     } else if (p.stream) {
-        plan_merge(p, mode, kReduceSmemBytes, (uint64_t)ix->sm_count, (uint32_t)ix->opt_merge_chunk_bytes);
+        // back-to-back queries: the slim reduce CTA that fits beside a gather CTA; an isolated query: the fat one,
+        // and its gather kernel may use the whole SM
+        plan_merge(p, mode, isolated ? kReduceFatSmemBytes : kReduceSmemBytes, (uint64_t)ix->sm_count,
+                   (uint32_t)ix->opt_merge_chunk_bytes);
     } else {
         plan_merge(p, mode, kMergeKernelSmem, (uint64_t)ix->sm_count * 3, (uint32_t)ix->opt_merge_chunk_bytes);
     }
@@ -434,10 +438,38 @@ int fail_aborted(unsigned long long v)
                                  "a CTA waited for another CTA's pooled row ids",
                                  "a shard waited for the query bytes of rank 0 (was rank 0's search launched?)",
                                  "a shard waited for another shard's hit list (was the search launched on every rank?)",
-                                 "a reduce kernel waited for its predecessor (completion chain)"};
+                                 "a reduce kernel waited for its predecessor (completion chain)",
+                                 "a gather kernel waited for its reduce kernel to become resident (exit gate)"};
     const unsigned code = (unsigned)(v & 0xff);
     return fail(BIGSI_B200_ERR_TIMEOUT, "device-side wait timed out in query %llu: %s; the handle is unusable (destroy it)",
-                (unsigned long long)(v >> 8), what[code < 6 ? code : 0]);
+                (unsigned long long)(v >> 8), what[code < 7 ? code : 0]);
+}
+
+// Ring-buffered scratch of a streamed launch planned as `p` (partial planes, pool slots).  Growing a buffer
+// synchronises `stream` first (earlier queries may still use the old one) and frees device memory, which waits for
+// the WHOLE device -- callers that must not block there (column shards of one process sharing a GPU) reserve for
+// their largest query up front (bigsi_b200_exchange_reserve).
+int reserve_stream_scratch(bigsi_b200_index *ix, const QueryParams &p, int grid, cudaStream_t stream)
+{
+    const uint64_t need = round_up(query_partial_bytes(p), 256);
+    if (need > ix->stream_partial_slot) {
+        CK(cudaStreamSynchronize(stream));
+        cudaError_t e = ix->stream_partial.reserve(kStreamRing * (need + need / 4));
+        if (e != cudaSuccess) return fail_cuda(e, "partial-plane workspace");
+        ix->stream_partial_slot = ix->stream_partial.cap / kStreamRing / 256 * 256;
+    }
+    // pool slot: [ready flags: kPoolFlagEntries x u64][ids: grid x pool_share x h x i32].  The flag region has a FIXED
+    // size: a ready word is compared with the launch epoch, so it must never alias bytes that an earlier query
+    // with another grid used for row ids
+    const uint64_t need_pool = round_up(kPoolFlagBytes + (uint64_t)grid * p.pool_share * p.h * 4 + 16, 256);
+    if (need_pool > ix->pool_slot_bytes) {
+        CK(cudaStreamSynchronize(stream));
+        cudaError_t e = ix->d_pool.reserve(kStreamRing * (need_pool + need_pool / 4));
+        if (e != cudaSuccess) return fail_cuda(e, "pool workspace");
+        CK(cudaMemsetAsync(ix->d_pool.p, 0, ix->d_pool.cap, stream));
+        ix->pool_slot_bytes = ix->d_pool.cap / kStreamRing / 256 * 256;
+    }
+    return 0;
 }
 
 // One query batch on `stream`.  Exactly one of d_rows / d_kmers is given; with k-mers the kernel
@@ -540,27 +572,11 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
         // ---- streamed launch: gather kernel + reduce kernel, ring-buffered scratch ------------------------------
         const uint64_t seq = ix->stream_seq + 1;
         const uint64_t slot = seq % kStreamRing;
-        const uint64_t need = round_up(query_partial_bytes(p), 256);
-        if (need > ix->stream_partial_slot) {
-            CK(cudaStreamSynchronize(stream));  // earlier queries may still use the old buffer
-            cudaError_t e = ix->stream_partial.reserve(kStreamRing * (need + need / 4));
-            if (e != cudaSuccess) return fail_cuda(e, "partial-plane workspace");
-            ix->stream_partial_slot = ix->stream_partial.cap / kStreamRing / 256 * 256;
-        }
+        if (int rc = reserve_stream_scratch(ix, p, grid, stream)) return rc;
         p.partial = static_cast<uint8_t *>(ix->stream_partial.p) + slot * ix->stream_partial_slot;
-        // pool slot: [ready flags: grid x u64][ids: grid x pool_share x h x i32]
-        const uint64_t flags_bytes = round_up((uint64_t)grid * 8, 256);
-        const uint64_t need_pool = round_up(flags_bytes + (uint64_t)grid * p.pool_share * h * 4 + 16, 256);
-        if (need_pool > ix->pool_slot_bytes) {
-            CK(cudaStreamSynchronize(stream));
-            cudaError_t e = ix->d_pool.reserve(kStreamRing * (need_pool + need_pool / 4));
-            if (e != cudaSuccess) return fail_cuda(e, "pool workspace");
-            CK(cudaMemsetAsync(ix->d_pool.p, 0, ix->d_pool.cap, stream));
-            ix->pool_slot_bytes = ix->d_pool.cap / kStreamRing / 256 * 256;
-        }
         uint8_t *pb = static_cast<uint8_t *>(ix->d_pool.p) + slot * ix->pool_slot_bytes;
         p.pool_ready = reinterpret_cast<unsigned long long *>(pb);
-        p.pool_ids = reinterpret_cast<int32_t *>(pb + flags_bytes);
+        p.pool_ids = reinterpret_cast<int32_t *>(pb + kPoolFlagBytes);
         p.pool_epoch = ix->pool_epoch + 1;
         uint8_t *sb = static_cast<uint8_t *>(ix->d_stream.p);
         QState *states = reinterpret_cast<QState *>(sb + 3 * 64);
@@ -575,6 +591,7 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
         p.qstate = states + seq % kStreamStates;
         p.qstate_next = states + (seq + kStreamRing) % kStreamStates;
         p.pool_counter = &p.qstate->pool_claims;
+        p.reduce_grid = (hits && hits->isolated) || ix->timing || ix->opt_exit_gate == 0 ? 0u : (uint32_t)reduce_grid;  // exit gate
         if (hits && hits->seq_mode) {
             // table `slot` of the ring; live entries carry this use's 16-bit epoch, so the table is only cleared when the
             // epoch wraps (every 65 535 uses) -- stream-ordered, which serialises one query in a quarter of a million
@@ -889,6 +906,7 @@ int bigsi_b200_index_set_option(bigsi_b200_index *ix, const char *key, int64_t v
     else if (!strcmp(key, "zero_copy")) ix->opt_zero_copy = value;
     else if (!strcmp(key, "cooperative")) ix->opt_cooperative = value;
     else if (!strcmp(key, "inputs_ready")) ix->opt_inputs_ready = value;
+    else if (!strcmp(key, "exit_gate")) ix->opt_exit_gate = value;
     else if (!strcmp(key, "spin_timeout_ms")) ix->opt_spin_timeout_ms = value < 1 ? 1 : value;
     else if (!strcmp(key, "pool_pct")) ix->opt_pool_pct = value > 100 ? -1 : value;  // > 100 = automatic
     else return fail(BIGSI_B200_ERR_INVALID, "unknown option '%s'", key);
@@ -2201,6 +2219,33 @@ static int exchange_search(bigsi_b200_index *ix, const char *d_kmers, uint64_t n
         return rc;
     if (!published) return fail(BIGSI_B200_ERR_INVALID, "the launch could not publish its result");
     ex.seq = seq;
+    return 0;
+}
+
+int bigsi_b200_exchange_reserve(bigsi_b200_index *ix, uint64_t max_kmers, int k, int h)
+{
+    if (int rc = check_index(ix)) return rc;
+    Exchange &ex = ix->ex;
+    if (!ex.local) return fail(BIGSI_B200_ERR_INVALID, "exchange not created");
+    if (k < 1 || h < 1 || max_kmers == 0) return fail(BIGSI_B200_ERR_INVALID, "k, h and max_kmers must be positive");
+    if (ix->num_cols == 0) return 0;
+    DeviceGuard guard(ix->device);
+    if (int rc = ensure_kernels()) return rc;
+    // scratch of a streamed query grows with the number of k-mers per CTA (partial planes) and with the grid (pool,
+    // none for back-to-back queries): the largest query and the first one that fills the grid cover both
+    for (uint64_t n : {max_kmers, std::min<uint64_t>(max_kmers, (uint64_t)ix->sm_count)}) {
+        QueryParams p;
+        int grid = 0;
+        if (int rc = plan_query(ix, BIGSI_B200_MODE_COUNTS, 1, n, n, h, true, k, p, grid)) return rc;
+        if (!p.stream) return fail(BIGSI_B200_ERR_INVALID, "a query of %llu k-mers cannot run as a streamed launch", (unsigned long long)n);
+        if (int rc = reserve_stream_scratch(ix, p, grid, ix->stream)) return rc;
+    }
+    const uint64_t hit_slot = round_up(8 + 8ull * ex.spec + 16, 256);
+    if (hit_slot * kStreamStates > ix->d_hits_ring.cap) {
+        cudaError_t e = ix->d_hits_ring.reserve(hit_slot * kStreamStates);
+        if (e != cudaSuccess) return fail_cuda(e, "staging");
+    }
+    CK(cudaStreamSynchronize(ix->stream));
     return 0;
 }
 

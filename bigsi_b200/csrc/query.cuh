@@ -33,6 +33,8 @@ constexpr int kStreamStates = 8;
 constexpr int kReduceThreads = 64;
 constexpr int kReduceSmemBytes = 16 * 1024;   // its dynamic shared memory
 constexpr int kReduceSlotsPerSm = 2;
+constexpr int kReduceFatThreads = 256;        // isolated queries: nothing shares the SMs, the merge is on the critical path
+constexpr int kReduceFatSmemBytes = 64 * 1024;
 constexpr int kSmBytes = 228 * 1024;          // shared memory of one SM; every resident CTA reserves 1 KB of it
 
 enum { kModeCounts = 0, kModeAnd = 1 };
@@ -44,11 +46,13 @@ struct QState {
     unsigned int reduce_arrivals;   // reduce-kernel CTAs that have finished their merge items
     unsigned long long n_unique;    // sequence front-end: unique windows found by the gather kernel's CTAs
     unsigned long long wait_ns;     // diagnostics: time the reduce kernel's last CTA waited for the other shards
-    unsigned long long pad[5];
+    unsigned int reduce_started;    // reduce-kernel CTAs that have become resident (see gather_solo's exit gate)
+    unsigned int pad0;
+    unsigned long long pad[4];
 };
 static_assert(sizeof(QState) == 64, "QState is one 64-byte block");
 // error codes a kernel leaves in the abort word when a bounded wait times out (sticky; see bounded_wait)
-enum { kAbortGate = 1, kAbortPool = 2, kAbortInbox = 3, kAbortPeers = 4, kAbortChain = 5 };
+enum { kAbortGate = 1, kAbortPool = 2, kAbortInbox = 3, kAbortPeers = 4, kAbortChain = 5, kAbortExit = 6 };
 
 // Work space of one launch: items = (column tile, global k-mer index), k-mer fastest.  It is cut
 // into n_slices equal slices of items_per_slice (<= 65535); CTA b owns the contiguous slices
@@ -151,6 +155,7 @@ struct QueryParams {
     // gather kernel flushes its planes and exits; reduce_kernel (merge_kernels.cu) merges, thresholds and publishes
     // while the NEXT query's gather kernel already runs on the same SMs.
     uint32_t stream;
+    uint32_t reduce_grid;                // CTAs of this query's reduce kernel
     uint32_t stream_wait_inputs;         // 1: the k-mers may be produced by the preceding kernel of the stream: wait for it
     unsigned long long stream_seq;       // number of this query among the handle's streamed launches (1-based)
     unsigned long long *stream_done;     // device word: every streamed query <= *stream_done is completely reduced

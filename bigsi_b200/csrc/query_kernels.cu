@@ -705,6 +705,21 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) gather_solo(const __grid_
         solo_producer(P, sg, smem, ring, ids, scratch, full, empty);
     else
         solo_consumer<MODE, HC, NP>(P, sg, smem, ring, ids, scratch, full, empty);
+    // Exit gate.  The reduce kernel becomes resident when the LAST gather CTA of this query has started, and the
+    // hardware puts its CTAs wherever most resources are free.  An SM whose gather CTA has already left would be
+    // filled with sleeping reduce CTAs (4-5 of them: no gather CTA fits beside those) and is lost to the gather for
+    // good, because the next query's reduce CTAs arrive before these leave -- measured: 40 of 148 SMs, 43 us per
+    // query instead of 32.  So no gather CTA leaves before every reduce CTA of its query is resident: they then
+    // always land BESIDE gather CTAs (at most two fit there), and the next query's gather kernel is eligible the
+    // moment this CTA exits.  Normally true long before (CTA lifetimes differ by ~1 us): one L2 read.  It is a
+    // scheduling hint, not a correctness condition: after 200 us the CTA leaves anyway (a profiler or
+    // CUDA_LAUNCH_BLOCKING that serialises kernels never lets the reduce kernel in while this one runs).
+    if (threadIdx.x == 0 && P.reduce_grid) {
+        const unsigned long long t0 = globaltimer_ns();
+        while (*reinterpret_cast<volatile unsigned int *>(&P.qstate->reduce_started) < P.reduce_grid &&
+               globaltimer_ns() - t0 < 200000ull) {
+        }
+    }
 }
 
 // grid-wide barrier over a monotonic arrival counter (all CTAs of the launch are co-resident: the generic kernel

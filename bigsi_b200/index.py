@@ -149,6 +149,24 @@ class DeviceIndex:
     def build_columns_dev(self, col0, n_blooms, d_blooms, bloom_stride, n_bits, stream=0):
         check(self._L.bigsi_b200_index_build_columns_dev(self.handle, col0, n_blooms, d_blooms, bloom_stride, n_bits, stream))
 
+    def grown(self, new_capacity):
+        """A re-pitched copy of this shard that holds `new_capacity` columns (host round trip in chunks); closes self.
+        BitMatrix.insert_column appends to rows of any length (matrix/bitmatrix.py:67-75, storage/base.py:113-116);
+        here the pitch is fixed at creation, so an insert beyond it moves the matrix once (capacity doubles)."""
+        info = self.info()
+        new = DeviceIndex(info["num_rows"], info["num_cols"], col_capacity=new_capacity, col_offset=info["col_offset"],
+                          device=info["device"])
+        try:
+            step = max(1, (1 << 26) // max(info["row_bytes"], 1))
+            for r0 in range(0, info["num_rows"], step):
+                n = min(step, info["num_rows"] - r0)
+                new.upload_rows(r0, self.download_rows(r0, n))
+        except Exception:
+            new.close()
+            raise
+        self.close()
+        return new
+
     def save(self, path, meta=b""):
         """Write the shard to a flat index file (include/bigsi_b200.h "persistence")."""
         meta = bytes(meta)

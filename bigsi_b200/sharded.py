@@ -164,6 +164,8 @@ class FusedExchange:
         L = _lib.lib()
         handle = (ctypes.c_uint8 * 64)()
         _lib.check(L.bigsi_b200_exchange_create(shard.index.handle, world_size, rank, max_kmers * shard.k, self.spec, handle))
+        # all scratch now: a search must never have to grow (and free) a buffer while other shards' kernels wait for it
+        _lib.check(L.bigsi_b200_exchange_reserve(shard.index.handle, max_kmers, shard.k, shard.h))
         if world_size > 1 and peers is None:
             gathered = [None] * world_size
             dist.all_gather_object(gathered, bytes(handle))

@@ -318,6 +318,7 @@ int bigsi_b200_index_load_rows(bigsi_b200_index *index, const char *path, uint64
  *         n_hits; int32 cols[spec]; uint32 counts[spec] } with LOCAL column ids of shard r; valid in
  *         stream order after the call and until 4 more searches have been issued on this handle (eight
  *         generations of blocks rotate).
+ * reserve: optional; see below.
  * wait_ns: synchronises the device; returns (and resets) the sum over the queries since the last call of
  *         the time this rank's reduce kernel waited for the other shards' hit lists (diagnostics). */
 int bigsi_b200_exchange_create(bigsi_b200_index *index, int world, int rank, uint64_t max_kmer_bytes, uint32_t spec,
@@ -327,6 +328,10 @@ int bigsi_b200_exchange_open_local(bigsi_b200_index *index, bigsi_b200_index *co
 int bigsi_b200_exchange_search_dev(bigsi_b200_index *index, const char *d_kmers, uint64_t n_kmers, int k, int h,
                                    uint32_t min_kmers, void *stream, const void **d_blocks_out,
                                    uint64_t *block_bytes_out);
+/* Allocates the scratch a search of up to max_kmers k-mers needs now, so that no later search has to grow a buffer
+ * (growing frees device memory, which waits for every kernel on the device -- also for a kernel of ANOTHER shard of
+ * this process on the same GPU that is itself waiting for this shard's launch). */
+int bigsi_b200_exchange_reserve(bigsi_b200_index *index, uint64_t max_kmers, int k, int h);
 int bigsi_b200_exchange_wait_ns(bigsi_b200_index *index, uint64_t *wait_ns_out, uint64_t *queries_out);
 int bigsi_b200_exchange_destroy(bigsi_b200_index *index);
 

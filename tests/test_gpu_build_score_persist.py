@@ -257,3 +257,93 @@ def test_reference_kv_schema_import_export(B):
     bigsi = B.BIGSI.build(cfg, [B.BIGSI.bloom(cfg, B.seq_to_kmers(s, case["k"])) for s in case["sample_seqs"]], case["samples"])
     assert bigsi.to_kv() == kv_of(case)
     bigsi.delete()
+
+
+# ---------------------------------------------------------------------------
+# BIGSI(config) column-sharded over several GPUs (storage-config.devices, bigsi_b200/sharded_index.py)
+# ---------------------------------------------------------------------------
+def test_sharded_bigsi_matches_single_gpu(B, tmp_path):
+    """build / insert / search (exact, inexact, score=True) / lookup / delete_sample / to_kv / save / load through a
+    column-sharded index give what the single-GPU index gives, bit for bit: three shards (distinct GPUs where the box
+    has them), appends that land in the last shard and grow it, a file written sharded and loaded on one GPU and on two
+    shards."""
+    import torch
+
+    ndev = max(torch.cuda.device_count(), 1)
+    devs = [0, 1 % ndev, 2 % ndev]
+    rng = np.random.default_rng(77)
+    k, m, h, n = 15, 30_011, 3, 45
+    genomes = ["".join(rng.choice(list("ACGT"), size=500)) for _ in range(n + 4)]
+    for i in range(2, n, 4):
+        genomes[i] = genomes[i - 1][:300] + genomes[i][300:]
+    names = ["g%d" % i for i in range(n + 4)]
+    one_cfg = {"k": k, "m": m, "h": h, "storage-config": {"filename": "sh-one", "device": 0}}
+    sh_cfg = {"k": k, "m": m, "h": h, "storage-config": {"filename": "sh-three", "devices": devs}}
+    blooms = [B.BIGSI.bloom(one_cfg, B.seq_to_kmers(g, k)) for g in genomes]
+    one = B.BIGSI.build(one_cfg, blooms[:n], names[:n])
+    sh = B.BIGSI.build(sh_cfg, blooms[:n], names[:n])
+    info = sh.index.info()
+    assert [i["num_cols"] for i in info["shards"]] == [16, 16, 13] and [i["col_offset"] for i in info["shards"]] == [0, 16, 32]
+    queries = [(genomes[0][:150], 1.0), (genomes[1][200:420], 0.8), (genomes[17][:80] + "N" + genomes[40][:80], 0.3),
+               (genomes[44][:k], 1.0), (genomes[3][:200], 0.0), ("ACGT" * 30, 1.0)]
+
+    def same(a, b):
+        assert np.array_equal(a.index.download_rows(0, m), b.index.download_rows(0, m))
+        for q, t in queries:
+            assert a.search(q, t) == b.search(q, t), (q[:20], t)
+            if t < 1.0:
+                assert a.search(q, t, score=True) == b.search(q, t, score=True)
+        kms = list(B.seq_to_kmers(genomes[2][:60], k))
+        la, lb = a.lookup(kms), b.lookup(kms)
+        assert {x: v.to01() for x, v in la.items()} == {x: v.to01() for x, v in lb.items()}
+        assert a.to_kv() == b.to_kv()
+
+    same(one, sh)
+    for j in range(n, n + 4):  # appends: the last shard takes them
+        one.insert(blooms[j], names[j])
+        sh.insert(blooms[j], names[j])
+    assert sh.index.num_cols == n + 4 and sh.num_samples == n + 4
+    one.delete_sample("g7")
+    sh.delete_sample("g7")
+    queries.append((genomes[n + 2][:140], 1.0))
+    same(one, sh)
+    path = str(tmp_path / "sharded.bigsib2")
+    sh.save(path)
+    single_path = str(tmp_path / "single.bigsib2")
+    one.save(single_path)
+    with open(path, "rb") as f1, open(single_path, "rb") as f2:  # one file format, whatever wrote it
+        assert f1.read() == f2.read()
+    re1 = B.BIGSI.load({"storage-config": {"filename": "sh-re1", "device": 0}}, path)
+    re2 = B.BIGSI.load({"storage-config": {"filename": "sh-re2", "devices": devs[:2]}}, path)
+    same(one, re1)
+    same(one, re2)
+    for b in (one, sh, re1, re2):
+        b.delete()
+    with pytest.raises(BaseException):
+        B.BIGSI(sh_cfg)
+
+
+def test_sharded_append_crosses_shards(B):
+    """Fewer samples than shards: the later shards start empty; appends fill the first shard's pitch (1 024 columns),
+    then open the next shard exactly there."""
+    rng = np.random.default_rng(79)
+    k, m, h = 9, 997, 2
+    cfg = {"k": k, "m": m, "h": h, "storage-config": {"filename": "sh-append", "devices": [0, 0]}}
+    one_cfg = {"k": k, "m": m, "h": h, "storage-config": {"filename": "sh-append-one", "device": 0}}
+    seqs = ["".join(rng.choice(list("ACGT"), size=40)) for _ in range(6)]
+    blooms = [B.BIGSI.bloom(cfg, B.seq_to_kmers(s, k)) for s in seqs]
+    sh = B.BIGSI.build(cfg, blooms[:3], ["a", "b", "c"])
+    one = B.BIGSI.build(one_cfg, blooms[:3], ["a", "b", "c"])
+    assert [i["num_cols"] for i in sh.index.info()["shards"]] == [3, 0]
+    filler = B.BIGSI.bloom(cfg, B.seq_to_kmers(seqs[3], k))
+    for j in range(3, 1027):
+        b = blooms[4] if j == 1025 else filler
+        sh.insert(b, "x%d" % j)
+        one.insert(b, "x%d" % j)
+    info = sh.index.info()
+    assert [i["num_cols"] for i in info["shards"]] == [1024, 3] and info["shards"][1]["col_offset"] == 1024
+    for q, t in ((seqs[4][:30], 1.0), (seqs[0], 1.0), (seqs[3][:20], 0.5)):
+        assert sh.search(q, t) == one.search(q, t)
+    assert np.array_equal(sh.index.download_rows(0, m), one.index.download_rows(0, m))
+    sh.delete()
+    one.delete()

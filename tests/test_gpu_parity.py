@@ -241,9 +241,24 @@ def test_fill_synthetic_matches_oracle(B, col_offset, N):
 # ---------------------------------------------------------------------------
 # reference API: golden vectors from the unmodified reference
 # ---------------------------------------------------------------------------
-def _config(case, name):
-    return {"k": case["k"], "m": case["m"], "h": case["h"], "storage-engine": "b200",
-            "storage-config": {"filename": name, "device": 0}}
+def _config(case, name, devices=None):
+    sc = {"filename": name, "device": 0} if devices is None else {"filename": name, "devices": list(devices)}
+    return {"k": case["k"], "m": case["m"], "h": case["h"], "storage-engine": "b200", "storage-config": sc}
+
+
+# BIGSI(config) over one GPU, and column-sharded (storage-config.devices, bigsi_b200/sharded_index.py) over two and three
+# shards -- on distinct GPUs where the box has them, else on the same one (the shard logic is the same)
+def _device_sets():
+    try:
+        import torch
+
+        n = torch.cuda.device_count()
+    except Exception:
+        n = 0
+    return [None, [0, 1 % max(n, 1)], [0, 1 % max(n, 1), 2 % max(n, 1)]]
+
+
+DEVICE_SETS = _device_sets()
 
 
 def _check_queries(bigsi, queries):
@@ -256,11 +271,12 @@ def _check_queries(bigsi, queries):
             assert bigsi.search(q["seq"], q["threshold"]) == q["result"], (q["seq"][:40], q["threshold"])
 
 
-def test_reference_golden_search_cases(B):
+@pytest.mark.parametrize("devices", DEVICE_SETS, ids=lambda d: "1gpu" if d is None else "shards" + "".join(map(str, d)))
+def test_reference_golden_search_cases(B, devices):
     g = load("search_cases.json")
     for ci, case in enumerate(g["cases"]):
         k, m, h = case["k"], case["m"], case["h"]
-        cfg = _config(case, "golden-%d" % ci)
+        cfg = _config(case, "golden-%d" % ci, devices)
         blooms = []
         for seq, ref_b64 in zip(case["sample_seqs"], case["blooms_b64"]):
             b = B.BIGSI.bloom(cfg, B.seq_to_kmers(seq, k))
@@ -316,9 +332,10 @@ def test_reference_end_to_end_kat(B):
     bigsi.delete()
 
 
-def test_config1_golden(B):
+@pytest.mark.parametrize("devices", DEVICE_SETS, ids=lambda d: "1gpu" if d is None else "shards" + "".join(map(str, d)))
+def test_config1_golden(B, devices):
     c = load("config1.json")
-    cfg = _config(c, "config1")
+    cfg = _config(c, "config1", devices)
     blooms = [B.BIGSI.bloom(cfg, km) for km in c["sample_kmers"]]
     assert [b.count() for b in blooms] == c["bloom_popcounts"]
     bigsi = B.BIGSI.build(cfg, blooms, c["samples"])
@@ -327,12 +344,13 @@ def test_config1_golden(B):
     bigsi.delete()
 
 
-def test_random_api_parity_vs_oracle(B):
+@pytest.mark.parametrize("devices", DEVICE_SETS, ids=lambda d: "1gpu" if d is None else "shards" + "".join(map(str, d)))
+def test_random_api_parity_vs_oracle(B, devices):
     """Randomised BIGSI.search vs the oracle restatement, incl. non-ACGT bases and reverse
     complements in one query, thresholds 0..1, N not a multiple of 8."""
     rng = np.random.default_rng(101)
     k, m, h, n = 11, 20_011, 3, 37
-    cfg = {"k": k, "m": m, "h": h, "storage-config": {"filename": "rand-api"}}
+    cfg = _config({"k": k, "m": m, "h": h}, "rand-api", devices)
     genomes = ["".join(rng.choice(list("ACGT"), size=600)) for _ in range(n)]
     for i in range(1, n, 3):  # related samples: shared prefixes
         genomes[i] = genomes[i - 1][:400] + genomes[i][400:]
