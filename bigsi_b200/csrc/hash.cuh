@@ -173,11 +173,12 @@ __device__ __forceinline__ uint4 ll_load_line(const uint4 *src, const LlRoute &r
 // (id > 0, nthreads a multiple of 32), or one warp (nthreads == 32).  A runtime choice on purpose: the
 // hashing code exists ONCE per kernel (it runs once per launch, so its cost is instruction fetch).
 struct GroupSync {
-    int id, nthreads;
+    int id, nthreads;  // id 0 = the CTA barrier, any other id = hardware barrier 1 (ids are immediates: see ptx.cuh:named_bar_sync)
     __device__ __forceinline__ void operator()() const
     {
         if (nthreads == 32) __syncwarp();
-        else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+        else if (id == 0) asm volatile("bar.sync 0, %0;" ::"r"(nthreads) : "memory");
+        else asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
     }
 };
 typedef GroupSync SyncNamed;

@@ -111,14 +111,19 @@ __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) { r
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return lop3<0xE8>(a, b, c); }
 __device__ __forceinline__ uint32_t and3(uint32_t a, uint32_t b, uint32_t c) { return lop3<0x80>(a, b, c); }
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+// Named barriers with COMPILE-TIME ids: with a register operand ptxas reserves all 16 hardware barriers of the SM
+// for the kernel ("used 16 barriers"), and no other CTA that needs even one barrier can become resident beside it --
+// which is exactly what the streamed path needs (a reduce CTA beside every gather CTA).
+template <int ID>
+__device__ __forceinline__ void named_bar_sync(int nthreads)
 {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(nthreads) : "memory");
 }
 // signal a named barrier without waiting on it (the waiting side uses named_bar_sync with the same count)
-__device__ __forceinline__ void named_bar_arrive(int id, int nthreads)
+template <int ID>
+__device__ __forceinline__ void named_bar_arrive(int nthreads)
 {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+    asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {

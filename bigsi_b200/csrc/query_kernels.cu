@@ -347,7 +347,7 @@ __device__ __forceinline__ void tma_consumer(const QueryParams &P, const uint8_t
 // concurrently.  Everything a query owns rotates (query.cuh:kStreamRing); the gate at kernel entry makes query s
 // wait until query s - kStreamRing is completely reduced (normally long ago: one L2 read).
 // ------------------------------------------------------------------------------------------
-constexpr int kBarHashGroup = 1;   // named barrier of the consumer warps while they hash
+constexpr int kBarHashGroup = 1;   // named barrier of the consumer warps while they hash (== the id GroupSync uses)
 constexpr int kBarIdsReady = 2;    // consumers -> producer: the id table is complete
 constexpr uint32_t kStageCntOffset = 640;  // uint32 [kMaxStages] k-mers per ring slot, in the shared-memory header
 constexpr uint32_t kPoolStashOffset = 768; // int32 [kPoolBatch][kPoolMaxH] row ids of one claimed pool batch
@@ -454,7 +454,7 @@ __device__ __forceinline__ void solo_producer(const QueryParams &P, const SoloGe
                     for (uint32_t r = 0; r < P.n_push; ++r) ll_store_line(P.ll.out[r] + 2 * (l0 + i0 + 32 * u), v[u], P.ll.flag);
         }
     }
-    named_bar_sync(kBarIdsReady, blockDim.x);  // the consumer warps have hashed the rest of the range
+    named_bar_sync<kBarIdsReady>(blockDim.x);  // the consumer warps have hashed the rest of the range
     for (; k0 < sg.n_static; k0 += G) {
         const int32_t *id = ids + (size_t)k0 * h;
         issue(min(G, sg.n_static - k0), [&](uint32_t i) { return id[i]; });
@@ -537,18 +537,18 @@ __device__ __forceinline__ void solo_consumer(const QueryParams &P, const SoloGe
         hash_kmers_group(P.kmers + (sg.begin + sg.n_first) * P.k, rest, (int)P.k, (int)P.h, P.num_rows, 1,
                          scratch + ((hash_scratch_bytes(sg.n_first, P.k) + 127) & ~127ull), ids + (size_t)sg.n_first * P.h, unit,
                          consumer_threads, GroupSync{kBarHashGroup, (int)consumer_threads}, P.mod_magic, &P.ll);
-    named_bar_sync(kBarHashGroup, consumer_threads);
+    named_bar_sync<kBarHashGroup>(consumer_threads);
     if (P.pool_share) {
         int32_t *dst = P.pool_ids + (size_t)blockIdx.x * P.pool_share * P.h;
         const int32_t *src = ids + (size_t)sg.n_static * P.h;
         for (uint32_t i = unit; i < sg.n_pool * P.h; i += consumer_threads) dst[i] = src[i];
-        named_bar_sync(kBarHashGroup, consumer_threads);
+        named_bar_sync<kBarHashGroup>(consumer_threads);
         if (unit == 0) {  // one cumulative fence behind the barrier publishes every thread's ids
             __threadfence();
             st_release_gpu_u64(P.pool_ready + blockIdx.x, (P.pool_epoch << 32) | (unsigned long long)sg.n_pool);
         }
     }
-    named_bar_arrive(kBarIdsReady, blockDim.x);
+    named_bar_arrive<kBarIdsReady>(blockDim.x);
     if (unit == 0) BIGSI_TS(9);
 
     const bool active = unit * 16 < tw;
