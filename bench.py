@@ -290,21 +290,31 @@ def run_b200(args):
             torch.cuda.synchronize()
 
     def dev_query(q, min_kmers=U):
-        if fused:  # 2 kernels per rank and query, no collective: rank 0's k-mers are pushed by its gather kernel
+        """One query, DEFERRED launch: ONE kernel per rank (gather of this query + merge/threshold/publication of the
+        previous one by its merge team); the returned buffer is complete after the next dev_query or dev_flush."""
+        if fused:  # no collective: rank 0's k-mers are pushed by its gather kernel, the merge teams all-gather the hits
             return searcher.search_one_fused(d_queries[q] if rank == 0 else None, U, min_kmers)
+        if world == 1:
+            return shard.search_kmers_hits_stream(d_queries[q], min_kmers)[None]
         if min_kmers != U:
             return searcher.search_step(d_queries[q], d_qoff, torch.tensor([min_kmers], dtype=torch.int32, device=dev), 1, U)
         return searcher.search_step(d_queries[q], d_qoff, d_min, 1, U)
 
+    def dev_flush():
+        if fused or world == 1:
+            index.flush()  # stage 2 of the last query as a kernel of its own
+
     def dev_step(i):
         for j in range(QPS):
             g = dev_query((i * QPS + j) % N_DISTINCT)
+        dev_flush()  # every hit list of the step is complete in stream order when the step ends
         return g
 
     # ---- correctness gate (the parity tests proper are tests/, this guards the bench's own wiring): query 0
     # exact -> exactly the planted all-ones columns on every shard; query 1 at score >= 0.4 -> those plus the graded
     # column of density 0.95, whose count must be the same through the batch path (generic kernel) of the same shard
     g = dev_query(0)
+    dev_flush()
     torch.cuda.synchronize()
     n, hc, hv = unpack_hits(g.cpu().numpy(), 1, HIT_CAP)
     for r in range(world):
@@ -312,6 +322,7 @@ def run_b200(args):
         assert got == [0, 1, cols - 1], "rank %d: unexpected exact hits %r" % (r, got[:10])
     thr04 = int(math.ceil(U * 0.4))
     g = dev_query(1, thr04)
+    dev_flush()
     torch.cuda.synchronize()
     n, hc, hv = unpack_hits(g.cpu().numpy(), 1, HIT_CAP)
     d_cnt = torch.zeros((1, cols + 8), dtype=torch.int32, device=dev)
@@ -337,6 +348,7 @@ def run_b200(args):
     sampler.start()
     barrier()
     dev_query(0)  # device-side rendezvous: one untimed query through the exchange right before the clock starts
+    dev_flush()
     barrier()
     if fused:
         searcher.fused.wait_ns()  # reset the wait counter
@@ -371,7 +383,7 @@ def run_b200(args):
         dump_timeline(index, dev_query, barrier, rank)
 
     # ---- isolated pass: one CUDA-event pair per launch (serialises the launches, no overlap between queries)
-    index.set_option("timing", 1)
+    index.set_option("timing", 1)  # (no deferral under timing: gather kernel, then its flush kernel)
     for j in range(QPS):
         dev_query(j)
     barrier()
@@ -550,15 +562,23 @@ def run_e2e(args, index, searcher, shard, queries, h_queries, barrier, rank, wor
         d_min = torch.tensor([U], dtype=torch.int32, device=dev)
 
         def e2e_step(i):
+            prev = None
             for j in range(QPS):
                 q = (i * QPS + j) % N_DISTINCT
                 if fused:
                     g = searcher.search_one_fused(h_queries[q].data_ptr() if rank == 0 else None, U, U)
+                    if prev is not None and rank == 0:  # deferred: query j-1 is complete behind the launch of query j
+                        h_out[(j - 1) % 4].copy_(prev, non_blocking=True)
+                    prev = g
                 else:
                     d_k = h_queries[q].to(dev, non_blocking=True)
                     g = searcher.search_step(d_k, d_qoff, d_min, 1, U)
+                    if rank == 0:
+                        h_out[j % 4].copy_(g, non_blocking=True)
+            if fused:
+                searcher.flush()
                 if rank == 0:
-                    h_out[j % 4].copy_(g, non_blocking=True)
+                    h_out[(QPS - 1) % 4].copy_(prev, non_blocking=True)
             torch.cuda.synchronize()
             return h_out[(QPS - 1) % 4]
 
@@ -609,9 +629,10 @@ def dump_timeline(index, dev_query, barrier, rank):
     index.set_option("debug_flags", 2)
     for i in range(32):
         dev_query(i)
+    index.flush()
     barrier()
     info = index.info()
-    grid, rgrid = info["last_grid"], info["last_reduce_grid"]
+    grid, rgrid = info["last_grid"], max(info["last_reduce_grid"], info["sm_count"])
     per = grid + rgrid
     buf = np.zeros(8 * per * 16, dtype=np.uint64)
     _L.check(_L.lib().bigsi_b200_index_debug_read(index.handle, ctypes.c_void_p(buf.ctypes.data), buf.size))

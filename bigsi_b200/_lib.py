@@ -91,6 +91,8 @@ SIGNATURES = {
     "bigsi_b200_query_hits_dev": (_int, [_vp, _vp, _vp, _u64, _u64, _u64, _int, _vp, _vp, _vp, _u64, _vp, _vp, _u64, _vp]),
     "bigsi_b200_query_kmers_hits_dev": (_int, [_vp, _vp, _int, _vp, _u64, _u64, _u64, _int, _vp, _vp, _vp, _u64, _vp, _vp,
                                                _u64, _vp]),
+    "bigsi_b200_query_kmers_hits_stream_dev": (_int, [_vp, _vp, _int, _u64, _int, ctypes.c_uint32, _vp, _vp, _u64, _vp, _vp]),
+    "bigsi_b200_index_flush": (_int, [_vp]),
     "bigsi_b200_lookup_dev": (_int, [_vp, _vp, _u64, _int, _vp, _u64, _vp]),
     "bigsi_b200_threshold_dev": (_int, [_vp, _u64, _u64, _u64, _vp, _vp, _vp, _u64, _vp, _vp]),
     "bigsi_b200_search_kmers": (_int, [_vp, _int, _vp, _vp, _u64, _int, _int, _vp, _u64]),

@@ -98,7 +98,12 @@ struct PinnedBuf {
         p = nullptr;
         cap = 0;
         cudaError_t e = cudaHostAlloc(&p, round_up(bytes, 4096), cudaHostAllocMapped | cudaHostAllocPortable);
-        if (e == cudaSuccess) cap = round_up(bytes, 4096);
+        if (e == cudaSuccess) {
+            cap = round_up(bytes, 4096);
+            // result blocks live here and are recognised by a per-handle sequence number in their first word: a
+            // recycled allocation must not carry a block some earlier handle published (same numbers, other index)
+            memset(p, 0, cap);
+        }
         return e;
     }
     void release()
@@ -163,7 +168,7 @@ struct bigsi_b200_index {
     bool timing = false;
     int64_t opt_debug_flags = 0;
     int64_t opt_prehash = 1, opt_fuse_merge = 1, opt_merge_chunk_bytes = 0, opt_solo = 1, opt_pool_pct = -1, opt_zero_copy = 1, opt_cooperative = 1;
-    int64_t opt_inputs_ready = 0, opt_spin_timeout_ms = 10000, opt_exit_gate = 1;
+    int64_t opt_inputs_ready = 0, opt_spin_timeout_ms = 10000, opt_defer = 1;
     // streamed single-query launches (query.cuh:kStreamRing): ring-buffered scratch + the completion / abort words
     DevBuf d_pool;            // kStreamRing x [ready flags: grid x u64][ids: grid x pool_share x h x i32]
     uint64_t pool_slot_bytes = 0;
@@ -174,6 +179,15 @@ struct bigsi_b200_index {
     PinnedBuf h_status;       // mapped: word 0 = mirror of the abort word
     DevBuf d_hits_ring;       // host-buffer paths: kStreamStates x {n_hits, cols[cap], counts[cap]}
     uint64_t stream_seq = 0;  // streamed queries launched on this handle
+    // the last streamed query when its stage 2 has not been launched yet (deferred launches): the next streamed
+    // launch hands it to its merge team, flush_pending() launches reduce_kernel for it
+    struct PendingQuery {
+        bool have = false;
+        QueryParams p;
+        int mode = 0, reduce_grid = 0;
+        cudaStream_t stream = nullptr;
+        uint64_t ticket = 0;  // sequence searches: the ticket waiting for it
+    } pending;
     // sequence searches (front-end inside the gather kernel): kStreamRing de-duplication tables with epoch-tagged
     // entries, up to kSeqTickets searches in flight (submit / wait), each with its own pinned sequence buffer and
     // its own result block in mapped host memory
@@ -215,10 +229,8 @@ namespace {
 
 constexpr uint64_t kPoolFlagEntries = 16384, kPoolFlagBytes = kPoolFlagEntries * 8;
 constexpr uint64_t kStreamStateBytes = 3 * 64 + (uint64_t)kStreamStates * sizeof(QState);
-// shared memory a streamed gather CTA may use so that a reduce CTA (kReduceSmemBytes + its static words) still
-// fits on the same SM; every resident CTA reserves 1 KB
-constexpr uint64_t kStreamGatherSmem =
-    (uint64_t)kSmBytes - (1 + kReduceSlotsPerSm) * 1024 - (uint64_t)kReduceSlotsPerSm * (kReduceSmemBytes + 256);
+// shared memory of a streamed gather CTA in COUNTS mode: the merge team's scratch lies behind the ring
+constexpr uint64_t kStreamTeamSmem = kReduceSmemBytes;
 
 bool g_kernels_ready[64] = {};  // function attributes (dynamic shared memory opt-in) are per device
 
@@ -325,12 +337,13 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
     p.solo = p.stream = 0;
     p.pool_share = 0;
     p.solo_max_kmers = 0xffffffffu;
+    const uint64_t team_smem = mode == BIGSI_B200_MODE_COUNTS ? kStreamTeamSmem : 0;
     if (p.prehash && n_queries == 1 && ix->opt_solo != 0 && grid > 0 &&
-        kSmemHeaderBytes + p.ids_bytes + 3ull * h * tile <= kStreamGatherSmem)
+        kSmemHeaderBytes + p.ids_bytes + 3ull * h * tile + team_smem <= (uint64_t)kSmemBudget)
         p.solo = p.stream = 1;
 
     // ring geometry
-    const uint64_t ring_avail = (p.solo ? kStreamGatherSmem - kSmemHeaderBytes : smem_avail) - p.ids_bytes;
+    const uint64_t ring_avail = smem_avail - p.ids_bytes - (p.solo ? team_smem : 0);
     const uint64_t kmer_bytes = (uint64_t)h * tile;
     uint32_t G = 1;
     if (ix->opt_kmers_per_stage > 0) {
@@ -375,6 +388,7 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
             }
         }
         p.pool_share = (uint32_t)pp;
+        p.merge_team = query_has_merge_team(p, mode) ? (uint32_t)kMergeTeamThreads : 0u;
     }
     // merge geometry; it fixes the chunk-major layout of the partial planes, so stage 1 needs it as well
     p.n_slots_total = query_n_slots(p);
@@ -382,8 +396,8 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
         const uint32_t scratch = query_smem_bytes(p) - kSmemHeaderBytes - p.ids_bytes;  // the drained ring
         plan_merge(p, mode, scratch, (uint64_t)grid, (uint32_t)ix->opt_merge_chunk_bytes);
     } else if (p.stream) {
-        // back-to-back queries: the slim reduce CTA that fits beside a gather CTA; an isolated query: the fat one,
-        // and its gather kernel may use the whole SM
+        // back-to-back queries: the scratch of a gather CTA's merge team; an isolated query is always merged by the
+        // flush kernel, with more scratch (fewer, larger slot batches)
         plan_merge(p, mode, isolated ? kReduceFatSmemBytes : kReduceSmemBytes, (uint64_t)ix->sm_count,
                    (uint32_t)ix->opt_merge_chunk_bytes);
     } else {
@@ -409,6 +423,9 @@ struct HitsOut {
     // column-sharded exchange fused into the kernels (see Exchange above)
     bool isolated = false;        // the caller waits for this query's result before it issues the next one: nothing overlaps
                                   // it, so the CTAs start together and a pooled tail balances their finish times
+    bool deferred = false;        // stage 2 may be left to the NEXT streamed launch of the handle (its merge team) or to
+                                  // flush_pending(): the caller does not read the result before one of the two
+    uint64_t ticket = 0;          // deferred sequence searches: the ticket that waits for this query
     bool require_stream = false;  // fail before launching unless the plan is the streamed single-query one
     bool inputs_ready = false;    // the k-mers are not produced by the preceding kernel of the stream
     uint32_t n_push = 0;
@@ -449,10 +466,12 @@ int fail_aborted(unsigned long long v)
 // synchronises `stream` first (earlier queries may still use the old one) and frees device memory, which waits for
 // the WHOLE device -- callers that must not block there (column shards of one process sharing a GPU) reserve for
 // their largest query up front (bigsi_b200_exchange_reserve).
+int flush_pending(bigsi_b200_index *ix);
 int reserve_stream_scratch(bigsi_b200_index *ix, const QueryParams &p, int grid, cudaStream_t stream)
 {
     const uint64_t need = round_up(query_partial_bytes(p), 256);
     if (need > ix->stream_partial_slot) {
+        if (int rc = flush_pending(ix)) return rc;  // its planes live in the buffer that is about to go
         CK(cudaStreamSynchronize(stream));
         cudaError_t e = ix->stream_partial.reserve(kStreamRing * (need + need / 4));
         if (e != cudaSuccess) return fail_cuda(e, "partial-plane workspace");
@@ -463,12 +482,29 @@ int reserve_stream_scratch(bigsi_b200_index *ix, const QueryParams &p, int grid,
     // with another grid used for row ids
     const uint64_t need_pool = round_up(kPoolFlagBytes + (uint64_t)grid * p.pool_share * p.h * 4 + 16, 256);
     if (need_pool > ix->pool_slot_bytes) {
+        if (int rc = flush_pending(ix)) return rc;
         CK(cudaStreamSynchronize(stream));
         cudaError_t e = ix->d_pool.reserve(kStreamRing * (need_pool + need_pool / 4));
         if (e != cudaSuccess) return fail_cuda(e, "pool workspace");
         CK(cudaMemsetAsync(ix->d_pool.p, 0, ix->d_pool.cap, stream));
         ix->pool_slot_bytes = ix->d_pool.cap / kStreamRing / 256 * 256;
     }
+    return 0;
+}
+
+// Stage 2 of the pending streamed query (if any) as a kernel of its own, on the stream it was launched on.
+int flush_pending(bigsi_b200_index *ix)
+{
+    if (!ix->pending.have) return 0;
+    bigsi_b200_index::PendingQuery &pq = ix->pending;
+    pq.have = false;
+    const cudaError_t e = launch_reduce(pq.p, pq.mode, pq.reduce_grid, pq.stream);
+    if (e != cudaSuccess) {
+        // the gather kernel ran without its stage 2: the completion chain is broken for good
+        *static_cast<volatile unsigned long long *>(ix->h_status.p) = ((unsigned long long)pq.p.stream_seq << 8) | kAbortChain;
+        return fail_cuda(e, "reduce_kernel launch");
+    }
+    ix->kernel_launches++;
     return 0;
 }
 
@@ -524,7 +560,8 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
         // timeline stamps, fetched with bigsi_b200_index_debug_read: [gather grid + reduce grid][kDebugStamps] words per
         // launch; streamed launches rotate over kStreamStates such regions (query seq uses region seq % kStreamStates),
         // so the schedule of several consecutive queries can be read back
-        const uint64_t region = (uint64_t)((grid > 0 ? grid : 1) + reduce_grid) * kDebugStamps;
+        // (stage 2's stamps are written by whoever executes it: at most sm_count CTAs)
+        const uint64_t region = (uint64_t)((grid > 0 ? grid : 1) + std::max(reduce_grid, ix->sm_count)) * kDebugStamps;
         cudaError_t de = ix->debug_ts.reserve(region * 8 * kStreamStates);
         if (de != cudaSuccess) return fail_cuda(de, "debug buffer");
         p.debug_ts = static_cast<unsigned long long *>(ix->debug_ts.p) + (p.stream ? ((ix->stream_seq + 1) % kStreamStates) * region : 0);
@@ -591,7 +628,6 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
         p.qstate = states + seq % kStreamStates;
         p.qstate_next = states + (seq + kStreamRing) % kStreamStates;
         p.pool_counter = &p.qstate->pool_claims;
-        p.reduce_grid = (hits && hits->isolated) || ix->timing || ix->opt_exit_gate == 0 ? 0u : (uint32_t)reduce_grid;  // exit gate
         if (hits && hits->seq_mode) {
             // table `slot` of the ring; live entries carry this use's 16-bit epoch, so the table is only cleared when the
             // epoch wraps (every 65 535 uses) -- stream-ordered, which serialises one query in a quarter of a million
@@ -618,6 +654,15 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
         const bool ready = (hits && hits->inputs_ready) || ix->opt_inputs_ready != 0 || p.ll.in != nullptr;  // (a peer shard reads its inbox)
         p.stream_wait_inputs = (ready && !(hits && hits->total_dev)) ? 0u : 1u;
 
+        // the previous streamed query, if its stage 2 is still pending: this launch's merge team takes it when it can
+        // (same stream, COUNTS, scratch within the team's), otherwise it is flushed first
+        bigsi_b200_index::PendingQuery &pq = ix->pending;
+        const bool take_prev = pq.have && p.merge_team != 0 && pq.stream == stream && pq.mode == BIGSI_B200_MODE_COUNTS &&
+                               pq.p.merge_smem <= (uint32_t)kReduceSmemBytes && !ix->timing;
+        if (pq.have && !take_prev)
+            if (int rc = flush_pending(ix)) return rc;
+        p.merge_prev = take_prev ? 1u : 0u;
+
         TimedLaunch tl{};
         if (ix->timing) {
             if (ix->timed_free.empty()) {
@@ -630,28 +675,31 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
             }
             CK(cudaEventRecord(tl.e0, stream));
         }
-        cudaError_t e = launch_query(p, mode, grid, stream);
-        if (e != cudaSuccess) return fail_cuda(e, "gather_solo launch");
+        cudaError_t e = launch_query(p, mode, grid, stream, take_prev ? &pq.p : nullptr);
+        if (e != cudaSuccess) return fail_cuda(e, "gather_solo launch");  // (a pending query stays pending)
         ix->kernel_launches++;
         if (ix->timing) CK(cudaEventRecord(tl.e1, stream));
-        QueryParams pr = p;
-        if (pr.debug_ts) pr.debug_ts += (uint64_t)grid * kDebugStamps;
-        e = launch_reduce(pr, mode, reduce_grid, stream);
-        // from here on the query counts as launched: the completion chain expects its reduce kernel
+        // from here on the query counts as launched: the completion chain expects its stage 2
         ix->stream_seq = seq;
         ix->pool_epoch = p.pool_epoch;
-        if (e != cudaSuccess) {
-            // the gather kernel runs without its reduce kernel: the chain is broken for good
-            *static_cast<volatile unsigned long long *>(ix->h_status.p) = (seq << 8) | kAbortChain;
-            return fail_cuda(e, "reduce_kernel launch");
-        }
-        ix->kernel_launches++;
+        pq.have = true;
+        pq.p = p;
+        if (pq.p.debug_ts) pq.p.debug_ts += (uint64_t)grid * kDebugStamps;
+        pq.mode = mode;
+        pq.reduce_grid = reduce_grid;
+        pq.stream = stream;
+        pq.ticket = hits ? hits->ticket : 0;
+        const bool defer = hits && hits->deferred && mode == BIGSI_B200_MODE_COUNTS && !ix->timing && ix->opt_defer != 0 &&
+                           p.merge_smem <= (uint32_t)kReduceSmemBytes;
+        if (!defer)
+            if (int rc = flush_pending(ix)) return rc;
         if (ix->timing) {
             CK(cudaEventRecord(tl.e2, stream));
             ix->timed_used.push_back(tl);
         }
         if (hits && hits->published) *hits->published = will_publish;
     } else {
+        if (int rc = flush_pending(ix)) return rc;
         const uint64_t need = query_partial_bytes(p);
         if (need > ix->partial.cap) {
             CK(cudaStreamSynchronize(stream));
@@ -906,7 +954,7 @@ int bigsi_b200_index_set_option(bigsi_b200_index *ix, const char *key, int64_t v
     else if (!strcmp(key, "zero_copy")) ix->opt_zero_copy = value;
     else if (!strcmp(key, "cooperative")) ix->opt_cooperative = value;
     else if (!strcmp(key, "inputs_ready")) ix->opt_inputs_ready = value;
-    else if (!strcmp(key, "exit_gate")) ix->opt_exit_gate = value;
+    else if (!strcmp(key, "defer")) ix->opt_defer = value;  // 0: every streamed query is flushed at once (diagnostics)
     else if (!strcmp(key, "spin_timeout_ms")) ix->opt_spin_timeout_ms = value < 1 ? 1 : value;
     else if (!strcmp(key, "pool_pct")) ix->opt_pool_pct = value > 100 ? -1 : value;  // > 100 = automatic
     else return fail(BIGSI_B200_ERR_INVALID, "unknown option '%s'", key);
@@ -1149,6 +1197,34 @@ int bigsi_b200_query_kmers_hits_dev(bigsi_b200_index *ix, const char *d_kmers, i
     return run_query(ix, BIGSI_B200_MODE_COUNTS, nullptr, total_kmers ? d_kmers : nullptr, k, d_q_offsets, n_queries,
                      total_kmers, max_query_kmers, h, d_counts_full, counts_stride, static_cast<cudaStream_t>(stream),
                      &ho);
+}
+
+int bigsi_b200_query_kmers_hits_stream_dev(bigsi_b200_index *ix, const char *d_kmers, int k, uint64_t n_kmers, int h,
+                                           uint32_t min_kmers, int32_t *d_cols_out, uint32_t *d_counts_out, uint64_t cap,
+                                           uint64_t *d_n_out, void *stream)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (!d_n_out || (cap && (!d_cols_out || !d_counts_out))) return fail(BIGSI_B200_ERR_INVALID, "null device pointer");
+    if (n_kmers == 0 || !d_kmers) return fail(BIGSI_B200_ERR_INVALID, "a streamed query needs at least one k-mer");
+    DeviceGuard guard(ix->device);
+    HitsOut ho;
+    ho.by_value = true;
+    ho.min_value = min_kmers;
+    ho.cols = d_cols_out;
+    ho.counts = d_counts_out;
+    ho.n = reinterpret_cast<unsigned long long *>(d_n_out);
+    ho.cap = cap;
+    ho.deferred = true;
+    // (a plan that is not the streamed one runs to completion in stream order like bigsi_b200_query_kmers_hits_dev)
+    return run_query(ix, BIGSI_B200_MODE_COUNTS, nullptr, d_kmers, k, nullptr, 1, n_kmers, n_kmers, h, nullptr, 0,
+                     static_cast<cudaStream_t>(stream), &ho);
+}
+
+int bigsi_b200_index_flush(bigsi_b200_index *ix)
+{
+    if (int rc = check_index(ix)) return rc;
+    DeviceGuard guard(ix->device);
+    return flush_pending(ix);
 }
 
 int bigsi_b200_lookup_dev(bigsi_b200_index *ix, const int32_t *d_rows, uint64_t n_kmers, int h, uint8_t *d_out,
@@ -1596,6 +1672,7 @@ static int seq_submit(bigsi_b200_index *ix, const char *seq, uint64_t len, int k
     }
     const uint64_t hit_slot = round_up(8 + 8ull * cap + 16, 256);
     if (hit_slot * kStreamStates > ix->d_hits_ring.cap) {
+        if (int rc = flush_pending(ix)) return rc;  // its hit buffers live in the ring that is about to go
         CK(cudaStreamSynchronize(ix->stream));
         if ((e = ix->d_hits_ring.reserve(hit_slot * kStreamStates)) != cudaSuccess) return fail_cuda(e, "staging");
     }
@@ -1617,6 +1694,8 @@ static int seq_submit(bigsi_b200_index *ix, const char *seq, uint64_t len, int k
     ho.seq_mode = true;
     ho.seq_threshold = threshold;
     ho.isolated = isolated;
+    ho.deferred = !isolated;  // bulk searches: stage 2 rides in the next sequence's gather kernel; seq_wait flushes the last one
+    ho.ticket = id;
     ho.inputs_ready = true;
     ho.n_sinks = 1;
     ho.sinks[0] = static_cast<unsigned long long *>(d_blk);
@@ -1653,6 +1732,9 @@ static int seq_wait(bigsi_b200_index *ix, uint64_t ticket, int32_t *cols_out, ui
         return search_sequence_general(ix, seq.data(), seq.size(), t.k, t.h, t.threshold, cols_out, counts_out, t.cap, n_hits_out,
                                        num_kmers_out);
     }
+    // the newest search has nobody behind it to run its stage 2: flush it
+    if (ix->pending.have && ix->pending.ticket == ticket)
+        if (int rc = flush_pending(ix)) return rc;
     volatile unsigned long long *blk =
         reinterpret_cast<volatile unsigned long long *>(static_cast<uint8_t *>(ix->h_tsink.p) + (uint64_t)slot * kTicketBlock);
     uint64_t spins = 0;
@@ -2174,6 +2256,7 @@ static int exchange_search(bigsi_b200_index *ix, const char *d_kmers, uint64_t n
     cudaError_t e;
     const uint64_t hit_slot = round_up(8 + 8ull * ex.spec + 16, 256);
     if (hit_slot * kStreamStates > ix->d_hits_ring.cap) {
+        if (int rc = flush_pending(ix)) return rc;
         CK(cudaStreamSynchronize(stream));
         if ((e = ix->d_hits_ring.reserve(hit_slot * kStreamStates)) != cudaSuccess) return fail_cuda(e, "staging");
     }
@@ -2191,6 +2274,7 @@ static int exchange_search(bigsi_b200_index *ix, const char *d_kmers, uint64_t n
     ho.by_value = true;
     ho.min_value = min_kmers;
     ho.require_stream = true;
+    ho.deferred = true;  // published by the next search's merge team, or by bigsi_b200_index_flush
     ho.inputs_ready = ix->opt_inputs_ready != 0;
     ho.sink_spec = ex.spec;
     ho.sink_seq = seq;

@@ -99,11 +99,28 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, uint32_t lane)
     return x;
 }
 
+// The threads that execute the merge together: a whole CTA (stand-alone merge / reduce kernels, the merge phase of the
+// generic kernel), or a group of warps of a gather CTA on a named barrier (the deferred merge of the previous query,
+// query_kernels.cu:gather_solo).  tid() / size() replace threadIdx.x / blockDim.x, sync() replaces __syncthreads().
+struct CtaTeam {
+    __device__ __forceinline__ uint32_t tid() const { return threadIdx.x; }
+    __device__ __forceinline__ uint32_t size() const { return blockDim.x; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+template <int BAR>
+struct WarpGroupTeam {
+    uint32_t first_thread, n;  // the group = threads [first_thread, first_thread + n), n a multiple of 32
+    __device__ __forceinline__ uint32_t tid() const { return threadIdx.x - first_thread; }
+    __device__ __forceinline__ uint32_t size() const { return n; }
+    __device__ __forceinline__ void sync() const { named_bar_sync<BAR>((int)n); }
+};
+
 // The hit list of query 0 (n_hits, hit_cols, hit_counts) -> every sink block: payload, system-scope fence, then
 // {sequence word, number of hits} as ONE 16-byte release store, so the block header is never seen torn.
-// Every thread of the CTA must call it.
+// Every thread of the team must call it.
+template <class Team>
 __device__ __forceinline__ void publish_hits(const QueryParams &P, unsigned long long *const *sinks, uint32_t n_sinks,
-                                             unsigned long long seq)
+                                             unsigned long long seq, const Team &T)
 {
     const unsigned long long n = *reinterpret_cast<volatile unsigned long long *>(P.n_hits);
     unsigned long long m = n < P.hit_cap ? n : P.hit_cap;
@@ -111,31 +128,32 @@ __device__ __forceinline__ void publish_hits(const QueryParams &P, unsigned long
     for (uint32_t sidx = 0; sidx < n_sinks; ++sidx) {
         int32_t *dc = reinterpret_cast<int32_t *>(sinks[sidx] + 2);
         uint32_t *dv = reinterpret_cast<uint32_t *>(dc + P.sink_spec);
-        for (uint32_t i = threadIdx.x; i < (uint32_t)m; i += blockDim.x) {
+        for (uint32_t i = T.tid(); i < (uint32_t)m; i += T.size()) {
             dc[i] = __ldcg(P.hit_cols + i);
             dv[i] = __ldcg(P.hit_counts + i);
         }
     }
-    if (P.total_dev && threadIdx.x < n_sinks)  // the query's k-mer count was determined on the device: report it
-        sinks[threadIdx.x][2 + P.sink_spec] = __ldcg(P.total_dev);
+    if (P.total_dev && T.tid() < n_sinks)  // the query's k-mer count was determined on the device: report it
+        sinks[T.tid()][2 + P.sink_spec] = __ldcg(P.total_dev);
     // ONE system-scope fence per sink on the critical path: the CTA barrier orders every thread's payload
     // stores before the publishing thread's fence (fences are cumulative -- the same pattern grid-wide barriers
     // rely on), and the header store behind the fence can then be a plain one
-    __syncthreads();
-    if (threadIdx.x < n_sinks) {
+    T.sync();
+    if (T.tid() < n_sinks) {
         __threadfence_system();
-        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(sinks[threadIdx.x]), "l"(seq), "l"(n) : "memory");
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(sinks[T.tid()]), "l"(seq), "l"(n) : "memory");
     }
 }
 
 // Stage `bytes` (a multiple of 16) from global to shared memory with bulk async copies issued by warp 0
 // and wait for them.  Every thread of the CTA must call it; `phase` is the CTA-uniform parity of `mbar`.
+template <class Team>
 __device__ __forceinline__ void merge_stage_region(const QueryParams &P, uint8_t *dst, const uint8_t *src, uint32_t bytes,
-                                                   uint64_t *mbar, uint32_t &phase)
+                                                   uint64_t *mbar, uint32_t &phase, const Team &T)
 {
-    __syncthreads();  // every reader of the previous contents is done
-    if (threadIdx.x < 32) {
-        const uint32_t lane = threadIdx.x;
+    T.sync();  // every reader of the previous contents is done
+    if (T.tid() < 32) {
+        const uint32_t lane = T.tid();
         if (lane == 0) BIGSI_TS(13);
         if (!(P.debug_flags & 8u)) fence_proxy_async_all();  // partial planes were written through the generic proxy (by other SMs)
         if (lane == 0) mbar_arrive_expect_tx(mbar, bytes);
@@ -152,12 +170,13 @@ __device__ __forceinline__ void merge_stage_region(const QueryParams &P, uint8_t
 // One merge work item, executed by the whole CTA (all threads must call it: it contains
 // __syncthreads).  smem: 128-byte aligned scratch of P.merge_smem bytes; mbar: an initialised
 // (count 1) mbarrier owned by the merge phase; phase: its CTA-uniform parity.
-template <int MODE>
-__device__ __forceinline__ void merge_item(const QueryParams &P, uint64_t item, uint8_t *smem, uint64_t *mbar, uint32_t &phase)
+template <int MODE, class Team>
+__device__ __forceinline__ void merge_item(const QueryParams &P, uint64_t item, uint8_t *smem, uint64_t *mbar, uint32_t &phase,
+                                           const Team &T)
 {
     MergeGeom G;
     if (!merge_geometry(P, item, G)) return;  // block-uniform
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t lane = T.tid() & 31, warp = T.tid() >> 5, nwarps = T.size() >> 5;
     const uint32_t pps = MODE == kModeCounts ? P.planes_per_slot : 1;
     const uint32_t cb = P.merge_cb;
     const uint32_t wpi = cb >> 2;
@@ -176,20 +195,20 @@ __device__ __forceinline__ void merge_item(const QueryParams &P, uint64_t item, 
     uint32_t Gs = 1;
     {
         const uint32_t lim = (uint32_t)min((uint64_t)SB, G.n_slots);
-        while (Gs < kMaxSlotGroups && Gs < lim && pairs * (Gs * 2) <= blockDim.x) Gs <<= 1;
+        while (Gs < kMaxSlotGroups && Gs < lim && pairs * (Gs * 2) <= T.size()) Gs <<= 1;
     }
     const uint32_t g = lane & (Gs - 1);
-    const uint32_t pairs_per_pass = blockDim.x / Gs;
+    const uint32_t pairs_per_pass = T.size() / Gs;
     const uint32_t stage_s = smem_u32(stage);
 
-    __syncthreads();  // the previous item's expansion is done with `cnt`
+    T.sync();  // the previous item's expansion is done with `cnt`
     if (MODE == kModeAnd && G.n_slots == 0)  // an empty query is all-ones (reduce over nothing is the identity)
-        for (uint32_t w = threadIdx.x; w < G.vw; w += blockDim.x) cnt[w] = 0xffffffffu;
+        for (uint32_t w = T.tid(); w < G.vw; w += T.size()) cnt[w] = 0xffffffffu;
 
     for (uint64_t s0 = 0; s0 < G.n_slots; s0 += SB) {
         const uint32_t nb = (uint32_t)min((uint64_t)SB, G.n_slots - s0);
-        merge_stage_region(P, stage, region + s0 * slot_bytes, nb * slot_bytes, mbar, phase);
-        if (threadIdx.x == 0 && s0 == 0) BIGSI_TS(10);
+        merge_stage_region(P, stage, region + s0 * slot_bytes, nb * slot_bytes, mbar, phase, T);
+        if (T.tid() == 0 && s0 == 0) BIGSI_TS(10);
         const bool first = s0 == 0;
         for (uint32_t p0 = (warp * 32) / Gs; p0 < pairs; p0 += pairs_per_pass) {  // warp-uniform trip count
             const uint32_t p = p0 + lane / Gs;
@@ -309,8 +328,8 @@ __device__ __forceinline__ void merge_item(const QueryParams &P, uint64_t item, 
             }
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) BIGSI_TS(11);
+    T.sync();
+    if (T.tid() == 0) BIGSI_TS(11);
 
     if (MODE == kModeCounts) {
         uint32_t *out = P.out ? reinterpret_cast<uint32_t *>(P.out) + (uint64_t)G.q * P.out_stride : nullptr;
@@ -360,7 +379,7 @@ __device__ __forceinline__ void merge_item(const QueryParams &P, uint64_t item, 
         uint8_t *out = reinterpret_cast<uint8_t *>(P.out) + (uint64_t)G.q * P.out_stride;
         const uint32_t row_bytes = (P.num_cols + 7) >> 3;
         const uint32_t byte0 = G.col0 >> 3;
-        for (uint32_t c = threadIdx.x; c < G.vw * 4; c += blockDim.x) {
+        for (uint32_t c = T.tid(); c < G.vw * 4; c += T.size()) {
             const uint32_t byte = byte0 + c;
             if (byte >= row_bytes) break;
             uint32_t v = (cnt[c >> 2] >> (8 * (c & 3))) & 0xffu;
@@ -368,8 +387,65 @@ __device__ __forceinline__ void merge_item(const QueryParams &P, uint64_t item, 
             out[byte] = (uint8_t)v;
         }
     }
-    if (threadIdx.x == 0) BIGSI_TS(12);
+    if (T.tid() == 0) BIGSI_TS(12);
     // the next item's staging starts with __syncthreads, which also protects `cnt`
+}
+
+// Stage 2 of a STREAMED query (query_kernels.cu:gather_solo wrote its planes and is complete): merge + threshold +
+// publication + completion chain, executed by `n_ctas` teams (one per CTA of the executing grid; `cta` = this team's
+// index).  Two executors: the merge warps of the NEXT query's gather kernel (the normal case for back-to-back
+// queries: the merge of query s overlaps the gather of query s+1 inside the same CTAs, so nothing has to become
+// co-resident with anything) and reduce_kernel (merge_kernels.cu: the flush behind the last query of a burst and
+// behind every synchronous call).
+// The last team to finish publishes the hit list (host block and / or every shard's result blocks), waits -- bounded
+// -- for the other shards' blocks of the same query, clears the state block of query seq + kStreamRing and advances
+// the handle's completion word in query order.  s_flag: a shared-memory word owned by the team.
+template <int MODE, class Team>
+__device__ __forceinline__ void reduce_query(const QueryParams &P, uint8_t *merge_smem, uint64_t *bar, volatile int *s_flag,
+                                             const Team &T, uint32_t cta, uint32_t n_ctas)
+{
+    uint32_t phase = 0;
+    for (uint64_t item = cta; item < P.merge_items; item += n_ctas) merge_item<MODE>(P, item, merge_smem, bar, phase, T);
+    if (P.scrub_words) {
+        // query front-end (general path): its de-duplication table is dead once the gather kernel has read the
+        // k-mers; clear it for the next query here, off every critical path
+        for (uint64_t i = (uint64_t)cta * T.size() + T.tid(); i < P.scrub_words; i += (uint64_t)n_ctas * T.size()) P.scrub[i] = 0ull;
+    }
+    T.sync();
+    if (T.tid() == 0) {
+        BIGSI_TS(7);
+        __threadfence();
+        *s_flag = atomicAdd(&P.qstate->reduce_arrivals, 1u) + 1u == n_ctas;
+    }
+    T.sync();
+    if (!*s_flag) return;
+    // ---- the last team of the query ------------------------------------------------------------------------
+    __threadfence();
+    if (P.n_sinks) publish_hits(P, P.sinks, P.n_sinks, P.sink_seq, T);
+    // front-end words behind its table ({U}, {ticket, threshold}): every reader is done, re-arm them
+    if (P.scrub_words && T.tid() < 2) P.scrub[P.scrub_words + T.tid()] = 0ull;
+    if (T.tid() < P.n_gather) {  // all-gather: every shard's block of this query has arrived here
+        const unsigned long long t0 = globaltimer_ns();
+        const unsigned long long *blk = P.gather_blocks[T.tid()];
+        bounded_wait(P.abort_word, P.host_abort, P.spin_timeout_ns, kAbortPeers, P.stream_seq,
+                     [&]() { return ld_acquire_sys_u64(blk) == P.gather_seq; });
+        atomicMax(&P.qstate->wait_ns, globaltimer_ns() - t0);
+    }
+    T.sync();
+    if (T.tid() == 0) {
+        BIGSI_TS(6);
+        if (P.wait_ns_out) atomicAdd(P.wait_ns_out, P.qstate->wait_ns);
+    }
+    T.sync();
+    if (T.tid() < sizeof(QState) / 8) reinterpret_cast<unsigned long long *>(P.qstate_next)[T.tid()] = 0ull;
+    T.sync();
+    if (T.tid() == 0) {
+        // completion in query order: "done >= s" implies every query <= s is reduced and its ring slots are free
+        bounded_wait(P.abort_word, P.host_abort, P.spin_timeout_ns, kAbortChain, P.stream_seq,
+                     [&]() { return ld_acquire_gpu_u64(P.stream_done) + 1ull >= P.stream_seq; });
+        __threadfence();
+        st_release_gpu_u64(P.stream_done, P.stream_seq);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

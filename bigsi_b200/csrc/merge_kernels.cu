@@ -19,20 +19,15 @@ __global__ void __launch_bounds__(kMergeKernelThreads) merge_kernel(const __grid
     __syncthreads();
     grid_dependency_wait();  // stage 1 must have completed (PDL launch)
     uint32_t phase = 0;
-    merge_item<MODE>(P, blockIdx.x, merge_smem, &bar, phase);
+    merge_item<MODE>(P, blockIdx.x, merge_smem, &bar, phase, CtaTeam());
 }
 
-// Stage 2 of a STREAMED query (query_kernels.cu:gather_solo): merge + threshold + publication.  64 threads and
-// 16 KB of shared memory per CTA, so that TWO of its CTAs fit beside a gather CTA (query.cuh:kReduceSlotsPerSm): it
-// becomes resident while "its" gather kernel runs, sleeps in the dependency wait, and works while the NEXT query's
-// gather kernel streams rows.
-// The last CTA to finish publishes the hit list (host block and / or every shard's result blocks), waits -- bounded
-// -- for the other shards' blocks of the same query, clears the state block of query seq + kStreamRing and advances
-// the handle's completion word in query order.
-// THREADS = kReduceThreads for back-to-back queries; an ISOLATED query (synchronous host call: nothing runs beside it)
-// takes the fat variant, 256 threads and 64 KB, which merges in a quarter of the time.
-template <int MODE, int THREADS>
-__global__ void __launch_bounds__(THREADS) reduce_kernel(const __grid_constant__ QueryParams P)
+// Stage 2 of a STREAMED query as a kernel of its own (merge.cuh:reduce_query): the FLUSH.  Back-to-back queries are
+// merged by the merge warps of their successor's gather kernel; this kernel runs behind the last query of a burst
+// and behind every synchronous (isolated) call.  kReduceThreads threads; shared memory = the scratch the query's
+// merge was planned for (P.merge_smem).
+template <int MODE>
+__global__ void __launch_bounds__(kReduceThreads) reduce_kernel(const __grid_constant__ QueryParams P)
 {
     extern __shared__ __align__(128) uint8_t merge_smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -40,94 +35,44 @@ __global__ void __launch_bounds__(THREADS) reduce_kernel(const __grid_constant__
     grid_launch_dependents();
     if (threadIdx.x == 0) {
         BIGSI_TS(0);
-        if (P.debug_ts) {
-            unsigned int smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            P.debug_ts[(size_t)blockIdx.x * kDebugStamps + 15] = smid;
-        }
         mbar_init(&bar, 1);
         fence_barrier_init();
         s_flag = ld_volatile_u64(P.abort_word) != 0ull;
-        atomicAdd(&P.qstate->reduce_started, 1u);  // gather_solo's exit gate counts the resident reduce CTAs
     }
     __syncthreads();
     if (s_flag) return;      // the handle has aborted: nothing is reported any more
     grid_dependency_wait();  // the gather kernel has completed, its planes are visible
     if (threadIdx.x == 0) BIGSI_TS(8);
-    uint32_t phase = 0;
-    for (uint64_t item = blockIdx.x; item < P.merge_items; item += gridDim.x) merge_item<MODE>(P, item, merge_smem, &bar, phase);
-    if (P.scrub_words) {
-        // query front-end: its de-duplication table is dead once the gather kernel has read the k-mers; clear it
-        // for the next query here, off every critical path
-        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.scrub_words; i += (uint64_t)gridDim.x * blockDim.x)
-            P.scrub[i] = 0ull;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        BIGSI_TS(7);
-        __threadfence();
-        s_flag = atomicAdd(&P.qstate->reduce_arrivals, 1u) + 1u == gridDim.x;
-    }
-    __syncthreads();
-    if (!s_flag) return;
-    // ---- the last CTA of the query -------------------------------------------------------------------------
-    __threadfence();
-    if (P.n_sinks) publish_hits(P, P.sinks, P.n_sinks, P.sink_seq);
-    // front-end words behind its table ({U}, {ticket, threshold}): every reader is done, re-arm them
-    if (P.scrub_words && threadIdx.x < 2) P.scrub[P.scrub_words + threadIdx.x] = 0ull;
-    if (threadIdx.x < P.n_gather) {  // all-gather: every shard's block of this query has arrived here
-        const unsigned long long t0 = globaltimer_ns();
-        const unsigned long long *blk = P.gather_blocks[threadIdx.x];
-        bounded_wait(P.abort_word, P.host_abort, P.spin_timeout_ns, kAbortPeers, P.stream_seq,
-                     [&]() { return ld_acquire_sys_u64(blk) == P.gather_seq; });
-        atomicMax(&P.qstate->wait_ns, globaltimer_ns() - t0);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        BIGSI_TS(6);
-        if (P.wait_ns_out) atomicAdd(P.wait_ns_out, P.qstate->wait_ns);
-    }
-    __syncthreads();
-    if (threadIdx.x < sizeof(QState) / 8) reinterpret_cast<unsigned long long *>(P.qstate_next)[threadIdx.x] = 0ull;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // completion in query order: "done >= s" implies every query <= s is reduced and its ring slots are free
-        bounded_wait(P.abort_word, P.host_abort, P.spin_timeout_ns, kAbortChain, P.stream_seq,
-                     [&]() { return ld_acquire_gpu_u64(P.stream_done) + 1ull >= P.stream_seq; });
-        __threadfence();
-        st_release_gpu_u64(P.stream_done, P.stream_seq);
-    }
+    reduce_query<MODE>(P, merge_smem, &bar, &s_flag, CtaTeam(), blockIdx.x, gridDim.x);
 }
 
 cudaError_t merge_kernels_init()
 {
-    cudaError_t e = cudaFuncSetAttribute(merge_kernel<kModeCounts>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kMergeKernelSmem);
+    cudaError_t e;
+    // Every kernel asks for the LARGEST shared-memory carve-out: the driver otherwise sizes an SM's carve-out for the
+    // kernel that gets there first, and the carve-out only changes when the SM is empty -- a small merge CTA on an SM
+    // must not keep a 227 KB gather CTA of the next launch waiting for a reconfiguration.
+#define BIGSI_SET_SMEM(K, BYTES)                                                                                   \
+    e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES));                       \
+    if (e != cudaSuccess) return e;                                                                                \
+    e = cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);  \
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(merge_kernel<kModeAnd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMergeKernelSmem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(reduce_kernel<kModeCounts, kReduceThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReduceSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(reduce_kernel<kModeAnd, kReduceThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReduceSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(reduce_kernel<kModeCounts, kReduceFatThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReduceFatSmemBytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(reduce_kernel<kModeAnd, kReduceFatThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReduceFatSmemBytes);
+    BIGSI_SET_SMEM((merge_kernel<kModeCounts>), kMergeKernelSmem)
+    BIGSI_SET_SMEM((merge_kernel<kModeAnd>), kMergeKernelSmem)
+    BIGSI_SET_SMEM((reduce_kernel<kModeCounts>), kReduceFatSmemBytes)
+    BIGSI_SET_SMEM((reduce_kernel<kModeAnd>), kReduceFatSmemBytes)
+#undef BIGSI_SET_SMEM
+    return cudaSuccess;
 }
 
-// Streamed launch: the reduce kernel of a gather_solo launch.  debug_ts (if any) points behind the gather grid's stamps.
+// The flush of a streamed query: `grid` CTAs share the merge items.  debug_ts (if any) points behind the gather grid's stamps.
 cudaError_t launch_reduce(const QueryParams &p, int mode, int grid, cudaStream_t stream)
 {
     if (grid <= 0) return cudaErrorInvalidConfiguration;
-    const dim3 g((unsigned)grid);
-    if (p.merge_smem > (uint32_t)kReduceSmemBytes) {  // planned for the fat variant (isolated query)
-        const dim3 block(kReduceFatThreads);
-        if (mode == kModeAnd) return launch_pdl(reduce_kernel<kModeAnd, kReduceFatThreads>, g, block, p.merge_smem, stream, p);
-        return launch_pdl(reduce_kernel<kModeCounts, kReduceFatThreads>, g, block, p.merge_smem, stream, p);
-    }
-    const dim3 block(kReduceThreads);
-    if (mode == kModeAnd) return launch_pdl(reduce_kernel<kModeAnd, kReduceThreads>, g, block, p.merge_smem, stream, p);
-    return launch_pdl(reduce_kernel<kModeCounts, kReduceThreads>, g, block, p.merge_smem, stream, p);
+    if (p.merge_smem > (uint32_t)kReduceFatSmemBytes) return cudaErrorInvalidConfiguration;
+    const dim3 g((unsigned)grid), block(kReduceThreads);
+    if (mode == kModeAnd) return launch_pdl(reduce_kernel<kModeAnd>, g, block, p.merge_smem, stream, p);
+    return launch_pdl(reduce_kernel<kModeCounts>, g, block, p.merge_smem, stream, p);
 }
 
 cudaError_t launch_merge(const QueryParams &p_in, int mode, cudaStream_t stream)

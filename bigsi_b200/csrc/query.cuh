@@ -25,17 +25,16 @@ constexpr int kMaxSinks = 9;   // host + up to 8 GPUs of one box
 // front-end's table) over kStreamRing queries, the small state blocks over kStreamStates
 constexpr int kStreamRing = 4;
 constexpr int kStreamStates = 8;
-// A reduce CTA is resident from the moment the last gather CTA of its query STARTS until the merge is done (about
-// one gather-kernel duration asleep in the dependency wait + the merge), i.e. longer than the cadence of
-// back-to-back queries: TWO reduce CTAs (of consecutive queries) must fit on an SM beside one gather CTA, or the
-// next query's reduce kernel cannot become resident, cannot signal its dependents, and the gather kernels stall
-// (measured: 43 us per query with one reduce slot per SM).  64 threads x 128 registers and 16 KB each.
-constexpr int kReduceThreads = 64;
-constexpr int kReduceSmemBytes = 16 * 1024;   // its dynamic shared memory
-constexpr int kReduceSlotsPerSm = 2;
-constexpr int kReduceFatThreads = 256;        // isolated queries: nothing shares the SMs, the merge is on the critical path
-constexpr int kReduceFatSmemBytes = 64 * 1024;
-constexpr int kSmBytes = 228 * 1024;          // shared memory of one SM; every resident CTA reserves 1 KB of it
+// Stage 2 (merge + threshold + publication) of a streamed query s normally runs INSIDE the gather kernel of query
+// s + 1: kMergeTeamWarps extra warps per gather CTA (the "merge team") wait for the preceding grid to complete and
+// then share the merge items of query s, while the other warps of the same CTA stream the rows of query s + 1.  One
+// CTA per SM as before -- nothing has to become co-resident with anything.  The last query of a burst (and every
+// synchronous call) is flushed by reduce_kernel (merge_kernels.cu), kReduceThreads threads per CTA.
+constexpr int kMergeTeamWarps = 4;
+constexpr int kMergeTeamThreads = kMergeTeamWarps * 32;
+constexpr int kReduceThreads = 256;
+constexpr int kReduceSmemBytes = 16 * 1024;      // merge scratch of a streamed query (team and flush kernel alike)
+constexpr int kReduceFatSmemBytes = 64 * 1024;   // isolated queries: the flush is on the critical path, bigger batches
 
 enum { kModeCounts = 0, kModeAnd = 1 };
 
@@ -46,8 +45,7 @@ struct QState {
     unsigned int reduce_arrivals;   // reduce-kernel CTAs that have finished their merge items
     unsigned long long n_unique;    // sequence front-end: unique windows found by the gather kernel's CTAs
     unsigned long long wait_ns;     // diagnostics: time the reduce kernel's last CTA waited for the other shards
-    unsigned int reduce_started;    // reduce-kernel CTAs that have become resident (see gather_solo's exit gate)
-    unsigned int pad0;
+    unsigned int pad0[2];
     unsigned long long pad[4];
 };
 static_assert(sizeof(QState) == 64, "QState is one 64-byte block");
@@ -155,7 +153,8 @@ struct QueryParams {
     // gather kernel flushes its planes and exits; reduce_kernel (merge_kernels.cu) merges, thresholds and publishes
     // while the NEXT query's gather kernel already runs on the same SMs.
     uint32_t stream;
-    uint32_t reduce_grid;                // CTAs of this query's reduce kernel
+    uint32_t merge_team;                 // threads of the gather CTA's merge team (kMergeTeamThreads, or 0: a variant without)
+    uint32_t merge_prev;                 // 1: the kernel's second argument describes the previous query, to be merged by the team
     uint32_t stream_wait_inputs;         // 1: the k-mers may be produced by the preceding kernel of the stream: wait for it
     unsigned long long stream_seq;       // number of this query among the handle's streamed launches (1-based)
     unsigned long long *stream_done;     // device word: every streamed query <= *stream_done is completely reduced
@@ -195,14 +194,14 @@ __device__ __forceinline__ unsigned long long debug_gtime()
 #endif
 
 inline uint32_t query_consumer_warps(const QueryParams &p) { return (p.tile_bytes + 511) / 512; }
-inline uint32_t query_block_threads(const QueryParams &p) { return (query_consumer_warps(p) + 1) * 32; }
+inline uint32_t query_block_threads(const QueryParams &p) { return (query_consumer_warps(p) + 1) * 32 + p.merge_team; }
 constexpr int kMergeScratchBytes = 16 * 16 * 32 * 4 + 256;  // == kMergeSmemBytes (merge.cuh)
 inline uint32_t query_ring_bytes(const QueryParams &p) { return p.n_stages * p.kmers_per_stage * p.h * p.tile_bytes; }
 inline uint32_t query_smem_bytes(const QueryParams &p)
 {
     uint32_t ring = query_ring_bytes(p);
     if (p.fuse_merge && ring < (uint32_t)kMergeScratchBytes) ring = kMergeScratchBytes;  // the merge phase reuses the ring
-    return kSmemHeaderBytes + p.ids_bytes + ring;
+    return kSmemHeaderBytes + p.ids_bytes + ring + (p.merge_team ? (uint32_t)kReduceSmemBytes : 0u);  // + the team's scratch
 }
 inline uint64_t query_n_slots(const QueryParams &p)
 {
@@ -219,13 +218,16 @@ inline uint64_t query_partial_bytes(const QueryParams &p)
     return (uint64_t)p.merge_cpt * p.n_slots_total * p.planes_per_slot * p.merge_cb + 256;
 }
 
-// Stage 1: gather + AND + vertical count, per-segment bit planes -> p.partial.
-cudaError_t launch_query(const QueryParams &p, int mode, int grid, cudaStream_t stream);
+// Stage 1: gather + AND + vertical count, per-segment bit planes -> p.partial.  prev (streamed launches with
+// p.merge_prev only): the previous streamed query of the handle, merged by this launch's merge team.
+cudaError_t launch_query(const QueryParams &p, int mode, int grid, cudaStream_t stream, const QueryParams *prev = nullptr);
+// true when the streamed launch of p runs the kernel variant that carries a merge team
+inline bool query_has_merge_team(const QueryParams &p, int mode) { return p.stream && mode == kModeCounts && p.planes_per_slot <= 8; }
 // shared-memory scratch the in-kernel hashing needs per k-mer (raw bytes + flag + canonical words)
 inline uint64_t prehash_bytes_per_kmer(uint32_t k) { return (uint64_t)k + 1 + 4ull * ((((uint64_t)k + 3) >> 2) | 1); }
 // Stage 2: sum (or AND) the partial planes of every (query, column), expand to integers -> p.out.
 cudaError_t launch_merge(const QueryParams &p, int mode, cudaStream_t stream);
-// Stage 2 of a streamed launch (p.stream): merge + threshold + publication + completion chain, `grid` CTAs.
+// Stage 2 of a streamed launch (p.stream) as its own kernel (the flush): merge + threshold + publication + completion chain, `grid` CTAs.
 cudaError_t launch_reduce(const QueryParams &p, int mode, int grid, cudaStream_t stream);
 cudaError_t query_kernels_init();  // opt-in to large dynamic shared memory
 // drain of the pipelined exchange (uses n_hits/hit_*/sink_spec, n_pub/pub_*, n_gather/gather_* of p)

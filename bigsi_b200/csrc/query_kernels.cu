@@ -338,22 +338,32 @@ __device__ __forceinline__ void tma_consumer(const QueryParams &P, const uint8_t
 }
 
 // ------------------------------------------------------------------------------------------
-// "solo" path = STREAMED single-query launch: one query, one tile, one slice per CTA, k-mers hashed in the
-// kernel.  gather_solo hashes, gathers, ANDs, counts, writes its CTA's bit planes and exits -- no grid barrier,
-// no merge phase.  reduce_kernel (merge_kernels.cu) follows in the stream and merges / thresholds / publishes;
-// both are launched with programmatic dependent launch and the gather kernel does NOT wait for its predecessor,
-// so the gather CTAs of query s+1 take over each SM the moment the gather CTA of query s leaves it, while the
-// reduce kernel of query s (128 threads, 32 KB of shared memory per CTA: it fits beside a gather CTA) runs
-// concurrently.  Everything a query owns rotates (query.cuh:kStreamRing); the gate at kernel entry makes query s
-// wait until query s - kStreamRing is completely reduced (normally long ago: one L2 read).
+// "solo" path = STREAMED single-query launch: one query, one tile, one slice per CTA, k-mers hashed in the kernel.
+// gather_solo hashes, gathers, ANDs, counts, writes its CTA's bit planes and exits -- no grid barrier, no merge phase
+// of its own.  It is launched with programmatic dependent launch and its gather warps do NOT wait for the preceding
+// kernel, so the gather CTA of query s+1 takes over each SM the moment the gather CTA of query s leaves it.  Stage 2
+// of query s (merge.cuh:reduce_query) is executed by the MERGE TEAM of the gather kernel of query s+1: four extra
+// warps per CTA that wait for the preceding grid (query s's gather kernel) to complete and then share the merge
+// items, in the shadow of the row stream of query s+1.  Behind the last query of a burst, reduce_kernel
+// (merge_kernels.cu) does the same as a kernel of its own.  Everything a query owns rotates (query.cuh:kStreamRing);
+// the gate at kernel entry makes query s wait until query s - kStreamRing is completely reduced (normally long ago:
+// one L2 read).
 // ------------------------------------------------------------------------------------------
 constexpr int kBarHashGroup = 1;   // named barrier of the consumer warps while they hash (== the id GroupSync uses)
 constexpr int kBarIdsReady = 2;    // consumers -> producer: the id table is complete
+constexpr int kBarGather = 3;      // consumer warps + producer warp (the sequence front-end)
+constexpr int kBarMergeTeam = 4;   // the merge team
+constexpr uint32_t kTeamBarOffset = 544;   // uint64: staging mbarrier of the merge team
+constexpr uint32_t kTeamFlagOffset = 552;  // int: the team's "last CTA" flag
 constexpr uint32_t kStageCntOffset = 640;  // uint32 [kMaxStages] k-mers per ring slot, in the shared-memory header
 constexpr uint32_t kPoolStashOffset = 768; // int32 [kPoolBatch][kPoolMaxH] row ids of one claimed pool batch
 constexpr uint32_t kSeqCountOffset = 536;  // uint32: unique windows of this CTA (sequence front-end)
 constexpr uint32_t kGateOffset = 528;      // int: 1 = the entry gate passed (behind the 2 x kMaxStages mbarriers)
 constexpr int kPoolBatch = 8;
+
+// threads of a streamed gather CTA that gather: the consumer warps (one 16-byte unit of the tile per thread) + the
+// producer warp; the merge team (if the variant has one) follows them
+__device__ __forceinline__ uint32_t gather_threads(const QueryParams &P) { return (((P.tile_bytes + 511u) >> 9) + 1u) * 32u; }
 
 struct SoloGeom {
     uint64_t begin;     // first k-mer of this CTA's contiguous range
@@ -454,7 +464,7 @@ __device__ __forceinline__ void solo_producer(const QueryParams &P, const SoloGe
                     for (uint32_t r = 0; r < P.n_push; ++r) ll_store_line(P.ll.out[r] + 2 * (l0 + i0 + 32 * u), v[u], P.ll.flag);
         }
     }
-    named_bar_sync<kBarIdsReady>(blockDim.x);  // the consumer warps have hashed the rest of the range
+    named_bar_sync<kBarIdsReady>(gather_threads(P));  // the consumer warps have hashed the rest of the range
     for (; k0 < sg.n_static; k0 += G) {
         const int32_t *id = ids + (size_t)k0 * h;
         issue(min(G, sg.n_static - k0), [&](uint32_t i) { return id[i]; });
@@ -521,7 +531,7 @@ __device__ __forceinline__ void solo_consumer(const QueryParams &P, const SoloGe
                                               int32_t *ids, uint8_t *scratch, uint64_t *full, uint64_t *empty)
 {
     const uint32_t unit = threadIdx.x, lane = threadIdx.x & 31;
-    const uint32_t consumer_threads = blockDim.x - 32;
+    const uint32_t consumer_threads = gather_threads(P) - 32;
     const uint32_t h = HC ? HC : P.h, G = P.kmers_per_stage;
     const uint32_t seg_stride = P.tile_bytes;
     const uint32_t stage_bytes = G * h * seg_stride;
@@ -548,7 +558,7 @@ __device__ __forceinline__ void solo_consumer(const QueryParams &P, const SoloGe
             st_release_gpu_u64(P.pool_ready + blockIdx.x, (P.pool_epoch << 32) | (unsigned long long)sg.n_pool);
         }
     }
-    named_bar_arrive<kBarIdsReady>(blockDim.x);
+    named_bar_arrive<kBarIdsReady>(gather_threads(P));
     if (unit == 0) BIGSI_TS(9);
 
     const bool active = unit * 16 < tw;
@@ -611,8 +621,9 @@ __device__ __forceinline__ void solo_consumer(const QueryParams &P, const SoloGe
     if (unit == 0) BIGSI_TS(4);
 }
 
-template <int MODE, int HC, int NP>
-__global__ void __launch_bounds__(kMaxBlockThreads, 1) gather_solo(const __grid_constant__ QueryParams P)
+template <int MODE, int HC, int NP, bool TEAM>
+__global__ void __launch_bounds__(kMaxBlockThreads + (TEAM ? kMergeTeamThreads : 0), 1)
+gather_solo(const __grid_constant__ QueryParams P, const __grid_constant__ QueryParams PV)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
@@ -620,10 +631,11 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) gather_solo(const __grid_
     int32_t *ids = reinterpret_cast<int32_t *>(smem + kSmemHeaderBytes);
     uint8_t *ring = smem + kSmemHeaderBytes + P.ids_bytes;
     volatile int *s_gate = reinterpret_cast<volatile int *>(smem + kGateOffset);
-    const uint32_t consumer_warps = (blockDim.x >> 5) - 1;
+    const uint32_t n_gather = gather_threads(P);
+    const uint32_t consumer_warps = (n_gather >> 5) - 1;
 
-    // the dependents (this query's reduce kernel, the next query's gather kernel, ...) may be scheduled as soon
-    // as every CTA of this grid has started: they only become resident where resources are free
+    // the dependents (the next query's gather kernel, or the flush) may be scheduled as soon as every CTA of this grid
+    // has started: they only become resident where an SM is free
     grid_launch_dependents();
     if (threadIdx.x == 0) {
         BIGSI_TS(0);
@@ -636,11 +648,12 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) gather_solo(const __grid_
             mbar_init(&full[s], 1);                // one arrive.expect_tx by the producer + tx bytes
             mbar_init(&empty[s], consumer_warps);  // one arrive per consumer warp
         }
+        if (TEAM) mbar_init(reinterpret_cast<uint64_t *>(smem + kTeamBarOffset), 1);
         fence_barrier_init();
     }
     if (threadIdx.x == 32) {
         // entry gate: the buffers of this query's ring slot were last used by query seq - kStreamRing, whose
-        // reduce kernel must have finished (it also cleared our state block); a handle that has aborted stays dead
+        // stage 2 must have finished (it also cleared our state block); a handle that has aborted stays dead
         bool ok = ld_volatile_u64(P.abort_word) == 0ull;
         if (ok && P.stream_seq > (unsigned long long)kStreamRing)
             ok = bounded_wait(P.abort_word, P.host_abort, P.spin_timeout_ns, kAbortGate, P.stream_seq,
@@ -649,18 +662,32 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) gather_solo(const __grid_
     }
     __syncthreads();
     if (!*s_gate) return;
+
+    if (TEAM && threadIdx.x >= n_gather) {
+        // ---- merge team: stage 2 of the PREVIOUS streamed query, once its gather kernel (the preceding grid) is
+        // complete and its planes are visible.  Its scratch lies behind the ring.
+        if (!P.merge_prev) return;
+        grid_dependency_wait();
+        const WarpGroupTeam<kBarMergeTeam> T{n_gather, (uint32_t)kMergeTeamThreads};
+        if (T.tid() == 0 && PV.debug_ts) PV.debug_ts[(size_t)blockIdx.x * kDebugStamps + 8] = debug_gtime();
+        uint8_t *team_smem = ring + (size_t)P.n_stages * P.kmers_per_stage * P.h * P.tile_bytes;
+        reduce_query<kModeCounts>(PV, team_smem, reinterpret_cast<uint64_t *>(smem + kTeamBarOffset),
+                                  reinterpret_cast<volatile int *>(smem + kTeamFlagOffset), T, blockIdx.x, gridDim.x);
+        return;
+    }
+
     // the k-mers may come out of the preceding kernel of the stream (query front-end, a caller's kernel): wait for
-    // it.  Otherwise nothing this kernel reads or writes depends on its predecessor.
+    // it.  Otherwise nothing the gather warps read or write depends on their predecessor.
     if (P.stream_wait_inputs) grid_dependency_wait();
     if (threadIdx.x == 0) BIGSI_TS(8);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && P.n_hits != nullptr) P.n_hits[0] = 0ull;  // the reduce kernel adds to it
+    if (blockIdx.x == 0 && threadIdx.x == 0 && P.n_hits != nullptr) P.n_hits[0] = 0ull;  // stage 2 adds to it
 
     uint8_t *scratch = smem + kSmemHeaderBytes + P.ids_table_bytes;
     uint32_t seq_cnt = 0;
     const uint8_t *span = nullptr;
     const uint16_t *ulist = nullptr;
     if (P.seq_mode) {
-        // sequence front-end (hash.cuh): this CTA's windows [w0, w0 + cw) of the sequence; the whole CTA stages the
+        // sequence front-end (hash.cuh): this CTA's windows [w0, w0 + cw) of the sequence; all gather threads stage the
         // span with one round trip of 16-byte loads (the sequence may live in mapped host memory), every window
         // tries to claim its string in the table, the winners are listed -- they are this CTA's k-mers
         volatile uint32_t *s_cnt = reinterpret_cast<volatile uint32_t *>(smem + kSeqCountOffset);
@@ -673,14 +700,14 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) gather_solo(const __grid_
         const uint32_t nvec = cw ? (skew + cw + P.k - 1 + 15) >> 4 : 0u;
         const uint4 *a0 = reinterpret_cast<const uint4 *>(g0 - skew);
         uint4 *sv = reinterpret_cast<uint4 *>(scratch);
-        for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) sv[i] = __ldg(a0 + i);
-        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nvec; i += n_gather) sv[i] = __ldg(a0 + i);
+        named_bar_sync<kBarGather>(n_gather);
         span = scratch + skew;
         uint16_t *list = reinterpret_cast<uint16_t *>(scratch + ((P.items_per_slice + P.k + 47u) & ~15u));
         ulist = list;
         const SeqTable T{P.seq_table, P.seq_table_entries - 1, P.seq_epoch, P.kmers};
         const uint32_t lane = threadIdx.x & 31;
-        for (uint32_t base = 0; base < cw; base += blockDim.x) {  // block-uniform trip count (ballots inside)
+        for (uint32_t base = 0; base < cw; base += n_gather) {  // uniform trip count (ballots inside)
             const uint32_t w = base + threadIdx.x;
             const bool win = w < cw && seq_table_insert(T, span + w, (int)P.k, w0 + w, span, w0, cw);
             const uint32_t mask = __ballot_sync(0xffffffffu, win);
@@ -691,7 +718,7 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) gather_solo(const __grid_
             }
             if (win) list[pos + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)w;
         }
-        __syncthreads();
+        named_bar_sync<kBarGather>(n_gather);
         seq_cnt = *s_cnt;
         if (threadIdx.x == 0) {
             if (seq_cnt) atomicAdd(&P.qstate->n_unique, (unsigned long long)seq_cnt);
@@ -705,21 +732,6 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) gather_solo(const __grid_
         solo_producer(P, sg, smem, ring, ids, scratch, full, empty);
     else
         solo_consumer<MODE, HC, NP>(P, sg, smem, ring, ids, scratch, full, empty);
-    // Exit gate.  The reduce kernel becomes resident when the LAST gather CTA of this query has started, and the
-    // hardware puts its CTAs wherever most resources are free.  An SM whose gather CTA has already left would be
-    // filled with sleeping reduce CTAs (4-5 of them: no gather CTA fits beside those) and is lost to the gather for
-    // good, because the next query's reduce CTAs arrive before these leave -- measured: 40 of 148 SMs, 43 us per
-    // query instead of 32.  So no gather CTA leaves before every reduce CTA of its query is resident: they then
-    // always land BESIDE gather CTAs (at most two fit there), and the next query's gather kernel is eligible the
-    // moment this CTA exits.  Normally true long before (CTA lifetimes differ by ~1 us): one L2 read.  It is a
-    // scheduling hint, not a correctness condition: after 200 us the CTA leaves anyway (a profiler or
-    // CUDA_LAUNCH_BLOCKING that serialises kernels never lets the reduce kernel in while this one runs).
-    if (threadIdx.x == 0 && P.reduce_grid) {
-        const unsigned long long t0 = globaltimer_ns();
-        while (*reinterpret_cast<volatile unsigned int *>(&P.qstate->reduce_started) < P.reduce_grid &&
-               globaltimer_ns() - t0 < 200000ull) {
-        }
-    }
 }
 
 // grid-wide barrier over a monotonic arrival counter (all CTAs of the launch are co-resident: the generic kernel
@@ -799,7 +811,7 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
         if (threadIdx.x == 0) BIGSI_TS(6);
         uint32_t merge_phase = 0;
         for (uint64_t item = blockIdx.x; item < P.merge_items; item += gridDim.x)
-            merge_item<MODE>(P, item, ring, merge_bar, merge_phase);
+            merge_item<MODE>(P, item, ring, merge_bar, merge_phase, CtaTeam());
         if (threadIdx.x == 0) BIGSI_TS(7);
         if (P.n_sinks) {
             // the last CTA to finish its merge items publishes query 0's hit list to every sink
@@ -811,7 +823,7 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
             __syncthreads();
             if (*s_last) {
                 __threadfence();
-                publish_hits(P, P.sinks, P.n_sinks, P.sink_seq);
+                publish_hits(P, P.sinks, P.n_sinks, P.sink_seq, CtaTeam());
             }
         }
     }
@@ -821,26 +833,32 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
 // host side
 // ------------------------------------------------------------------------------------------
 template <int MODE, int HC>
-static cudaError_t launch_one(const QueryParams &p, int grid, cudaStream_t stream)
+static cudaError_t launch_one(const QueryParams &p, int grid, cudaStream_t stream, const QueryParams *prev)
 {
     if (p.solo) {
         // streamed: plain launch with the programmatic-stream-serialization attribute (the kernel decides itself
-        // what it waits for); planes_per_slot <= 8 takes the variant with the small counter
+        // what it waits for).  COUNTS with planes_per_slot <= 8 (up to 255 k-mers per CTA) takes the variant with
+        // the small counter and the merge team; the others leave stage 2 to the flush kernel.
+        const dim3 g(grid), b(query_block_threads(p));
+        const QueryParams &pv = prev ? *prev : p;
         if (MODE == kModeCounts && p.planes_per_slot > 8)
-            return launch_ex(gather_solo<MODE, HC, kSegPlanes>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream,
-                             /*pdl=*/true, /*cooperative=*/false, p);
-        return launch_ex(gather_solo<MODE, HC, 8>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream,
-                         /*pdl=*/true, /*cooperative=*/false, p);
+            return launch_ex(gather_solo<MODE, HC, kSegPlanes, false>, g, b, query_smem_bytes(p), stream, /*pdl=*/true,
+                             /*cooperative=*/false, p, pv);
+        if (MODE == kModeCounts)
+            return launch_ex(gather_solo<MODE, HC, 8, true>, g, b, query_smem_bytes(p), stream, true, false, p, pv);
+        return launch_ex(gather_solo<MODE, HC, 8, false>, g, b, query_smem_bytes(p), stream, true, false, p, pv);
     }
     return launch_ex(fused_query<MODE, HC>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream,
                      /*pdl=*/true, /*cooperative=*/p.fuse_merge != 0 && !p.plain_launch, p);
 }
 
-cudaError_t launch_query(const QueryParams &p, int mode, int grid, cudaStream_t stream)
+cudaError_t launch_query(const QueryParams &p, int mode, int grid, cudaStream_t stream, const QueryParams *prev)
 {
+    if (p.merge_prev && !(prev && query_has_merge_team(p, mode))) return cudaErrorInvalidValue;
+    if ((p.merge_team != 0) != (p.solo && query_has_merge_team(p, mode))) return cudaErrorInvalidValue;
     if (mode == kModeCounts)
-        return p.h == 3 ? launch_one<kModeCounts, 3>(p, grid, stream) : launch_one<kModeCounts, 0>(p, grid, stream);
-    return p.h == 3 ? launch_one<kModeAnd, 3>(p, grid, stream) : launch_one<kModeAnd, 0>(p, grid, stream);
+        return p.h == 3 ? launch_one<kModeCounts, 3>(p, grid, stream, prev) : launch_one<kModeCounts, 0>(p, grid, stream, prev);
+    return p.h == 3 ? launch_one<kModeAnd, 3>(p, grid, stream, prev) : launch_one<kModeAnd, 0>(p, grid, stream, prev);
 }
 
 cudaError_t query_kernels_init()
@@ -848,17 +866,19 @@ cudaError_t query_kernels_init()
     cudaError_t e;
 #define BIGSI_SET_SMEM(K)                                                                   \
     e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);  \
+    if (e != cudaSuccess) return e;                                                         \
+    e = cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
     if (e != cudaSuccess) return e;
     BIGSI_SET_SMEM((fused_query<kModeCounts, 3>))
     BIGSI_SET_SMEM((fused_query<kModeCounts, 0>))
     BIGSI_SET_SMEM((fused_query<kModeAnd, 3>))
     BIGSI_SET_SMEM((fused_query<kModeAnd, 0>))
-    BIGSI_SET_SMEM((gather_solo<kModeCounts, 3, 8>))
-    BIGSI_SET_SMEM((gather_solo<kModeCounts, 3, kSegPlanes>))
-    BIGSI_SET_SMEM((gather_solo<kModeCounts, 0, 8>))
-    BIGSI_SET_SMEM((gather_solo<kModeCounts, 0, kSegPlanes>))
-    BIGSI_SET_SMEM((gather_solo<kModeAnd, 3, 8>))
-    BIGSI_SET_SMEM((gather_solo<kModeAnd, 0, 8>))
+    BIGSI_SET_SMEM((gather_solo<kModeCounts, 3, 8, true>))
+    BIGSI_SET_SMEM((gather_solo<kModeCounts, 3, kSegPlanes, false>))
+    BIGSI_SET_SMEM((gather_solo<kModeCounts, 0, 8, true>))
+    BIGSI_SET_SMEM((gather_solo<kModeCounts, 0, kSegPlanes, false>))
+    BIGSI_SET_SMEM((gather_solo<kModeAnd, 3, 8, false>))
+    BIGSI_SET_SMEM((gather_solo<kModeAnd, 0, 8, false>))
 #undef BIGSI_SET_SMEM
     return merge_kernels_init();
 }

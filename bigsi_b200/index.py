@@ -374,6 +374,16 @@ class DeviceIndex:
                                                       max_query_kmers, h, d_min_kmers, d_cols_out, d_counts_out, cap,
                                                       d_n_out, d_counts_full, counts_stride, stream))
 
+    def query_kmers_hits_stream_dev(self, d_kmers, k, n_kmers, h, min_kmers, d_cols_out, d_counts_out, cap, d_n_out, stream=0):
+        """ONE query, DEFERRED (include/bigsi_b200.h "streamed single-query launches"): the result is complete in stream
+        order after the next streamed query on this handle or after flush()."""
+        check(self._L.bigsi_b200_query_kmers_hits_stream_dev(self.handle, d_kmers, k, n_kmers, h, int(min_kmers), d_cols_out,
+                                                             d_counts_out, cap, d_n_out, stream))
+
+    def flush(self):
+        """Launch stage 2 of the pending deferred query, if any (no host synchronisation)."""
+        check(self._L.bigsi_b200_index_flush(self.handle))
+
     def lookup_dev(self, d_rows, n_kmers, h, d_out, out_stride, stream=0):
         check(self._L.bigsi_b200_lookup_dev(self.handle, d_rows, n_kmers, h, d_out, out_stride, stream))
 

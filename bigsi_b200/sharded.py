@@ -138,6 +138,20 @@ class DeviceShard:
         return buf
 
 
+    def search_kmers_hits_stream(self, kmers_u8, min_kmers):
+        """ONE query from raw k-mers uint8 [U, k] on the device, DEFERRED: same packed layout as hits() for one query,
+        but the returned buffer (one of a ring of 8) is complete in stream order only after the NEXT streamed
+        search on this shard or after flush() -- stage 2 of a query rides in the gather kernel of its successor."""
+        buf = self._hit_buffer(1)
+        base = buf.data_ptr()
+        self.index.query_kmers_hits_stream_dev(kmers_u8.data_ptr(), self.k, kmers_u8.shape[0], self.h, int(min_kmers), base + 8,
+                                               base + 8 + 4 * self.cap, self.cap, base, self._stream())
+        return buf
+
+    def flush(self):
+        self.index.flush()
+
+
 class _DevArray:
     """Minimal __cuda_array_interface__ carrier so torch can view library-owned device memory."""
 
@@ -198,8 +212,8 @@ class FusedExchange:
     def search(self, kmers_u8, n_kmers, min_kmers, stream=None):
         """One query (rank 0's k-mers decide; a device tensor, or any 16-byte aligned device-addressable
         address as an int).  Returns int32 [world, 2 + 2*spec] (LOCAL colours), the packed layout of
-        DeviceShard.hits for one query: a view of library memory, complete in stream order, valid until four
-        more searches have been issued."""
+        DeviceShard.hits for one query: a view of library memory, DEFERRED -- complete in stream order after the
+        next search() or after flush() (on every rank) -- and valid until four more searches have been issued."""
         ct = self._ct
         ptr, stride = ct.c_void_p(0), ct.c_uint64(0)
         d_k = 0
@@ -209,6 +223,10 @@ class FusedExchange:
             self.shard.index.handle, d_k, n_kmers, self.shard.k, self.shard.h, int(min_kmers),
             self.shard._stream() if stream is None else stream, ct.byref(ptr), ct.byref(stride)))
         return self._view(ptr.value, stride.value)
+
+    def flush(self):
+        """Stage 2 of the last search as a kernel of its own (SPMD: every rank calls it)."""
+        self.shard.index.flush()
 
     def wait_ns(self):
         """(ns this rank's reduce kernels waited for the other shards since the last call, queries launched)."""
@@ -250,8 +268,12 @@ class ShardedSearcher:
 
     def search_one_fused(self, kmers_u8, n_kmers, min_kmers):
         """Single query through the in-kernel exchange; min_kmers is a host integer.  Same result layout
-        as search_step for one query (FusedExchange.search)."""
+        as search_step for one query (FusedExchange.search): DEFERRED, see flush()."""
         return self.fused.search(kmers_u8, n_kmers, min_kmers)
+
+    def flush(self):
+        """Completes the last deferred search of this rank in stream order (every rank calls it)."""
+        self.shard.index.flush()
 
     def search_step(self, kmers_u8, q_offsets, min_kmers, n_queries, max_query_kmers=0):
         """One batched search: rank 0's k-mers decide; returns the packed hit buffers of all ranks,

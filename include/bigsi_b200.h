@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BIGSI_B200_ABI_VERSION 6
+#define BIGSI_B200_ABI_VERSION 7
 
 enum {
     BIGSI_B200_OK = 0,
@@ -66,8 +66,8 @@ typedef struct {
     uint64_t kernel_launches;        /* cumulative count of kernels this handle has launched          */
     uint64_t scratch_bytes;          /* partial-plane workspace currently allocated                   */
     uint32_t last_fused;             /* bit 0: merge ran inside the fused kernel, bit 1: k-mers hashed in it,
-                                        bit 3: streamed launch (gather kernel + reduce kernel)                */
-    uint32_t last_reduce_grid;       /* CTAs of the reduce kernel of a streamed launch (else 0)               */
+                                        bit 3: streamed launch (gather kernel; stage 2 deferred)                */
+    uint32_t last_reduce_grid;       /* CTAs of the flush kernel of a streamed launch (else 0)                */
 } bigsi_b200_info;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -281,17 +281,35 @@ int bigsi_b200_index_load_rows(bigsi_b200_index *index, const char *path, uint64
                                uint64_t src_byte_offset, uint64_t row0, uint64_t n_rows);
 
 /* ---- streamed single-query launches -----------------------------------------------------------
- * A single query whose k-mers are hashed in the kernel (one column tile, up to ~200 000 k-mers) runs as TWO
- * kernels: a gather kernel (hash, row gather, AND, vertical count; one CTA per SM) and a small reduce kernel
- * (merge, threshold, publication).  Both carry the programmatic-dependent-launch attribute and the gather
- * kernel does not wait for its predecessor, so the gather kernel of query s+1 runs while the reduce kernel of
- * query s works on the same SMs; there is no grid-wide barrier and nothing needs a cooperative launch.  Scratch
- * rotates over 4 queries.  Consequences for callers of the `_dev` entry points:
- *   - output buffers (hit lists, counts) handed to one single-query call must not be handed to any of the next
- *     3 single-query calls on the same handle unless another operation of the stream lies in between;
- *   - results are complete in stream order after the call, as usual;
- *   - see option "inputs_ready".
+ * A single query whose k-mers are hashed in the kernel (one column tile, up to ~200 000 k-mers) runs in two
+ * stages.  Stage 1, the gather kernel: hash, row gather, AND, vertical count; one CTA per SM; it carries the
+ * programmatic-dependent-launch attribute and its gather warps do not wait for the preceding kernel, so the gather
+ * CTA of query s+1 takes over an SM the moment the gather CTA of query s leaves it.  Stage 2 (merge of the CTAs'
+ * bit planes, threshold, publication) of query s is executed by the MERGE TEAM of the gather kernel of query s+1 --
+ * four extra warps per CTA that wait for query s's kernel to complete and work in the shadow of the row stream --
+ * or, when nothing follows, by a flush kernel.  No grid-wide barrier, no cooperative launch, one CTA per SM at all
+ * times.  Scratch rotates over 4 queries.
+ *   - The ordinary entry points (bigsi_b200_query_kmers_hits_dev, the host-buffer calls) launch the flush kernel
+ *     right behind the gather kernel: results are complete in stream order after the call, as usual.
+ *   - The DEFERRED entry points (bigsi_b200_query_kmers_hits_stream_dev, bigsi_b200_exchange_search_dev,
+ *     bigsi_b200_search_sequence_submit, bigsi_b200_search_sequences) leave stage 2 of a query to the next streamed
+ *     query of the handle: the result of call s is complete in stream order after call s+1 (any streamed query on
+ *     the same stream) or after bigsi_b200_index_flush.  Any other query call on the handle flushes first.
+ *   - Output buffers handed to one single-query call must not be handed to any of the next 3 single-query calls
+ *     on the same handle.
+ *   - See option "inputs_ready".
  *
+ * query_kmers_hits_stream_dev: ONE query of n_kmers raw unique k-mers (device), threshold by value; outputs as
+ * bigsi_b200_query_hits_dev for one query (d_n_out: one u64).  Falls back to an ordinary, complete-in-stream-order
+ * launch when the launch plan is not the streamed one (rows wider than one tile, very long queries).
+ * index_flush: launches stage 2 of the handle's pending deferred query, if any, on the stream that query was
+ * launched on (no host synchronisation). */
+int bigsi_b200_query_kmers_hits_stream_dev(bigsi_b200_index *index, const char *d_kmers, int k, uint64_t n_kmers, int h,
+                                           uint32_t min_kmers, int32_t *d_cols_out, uint32_t *d_counts_out, uint64_t cap,
+                                           uint64_t *d_n_out, void *stream);
+int bigsi_b200_index_flush(bigsi_b200_index *index);
+
+/*
  * ---- column-sharded search over several GPUs WITHOUT per-query collectives ------------------
  * The reference has no distributed path; sample columns are independent (graph/index.py:42-80,
  * graph/bigsi.py:192-230), so shard g holds all rows of its column range on its own GPU and a
@@ -299,10 +317,10 @@ int bigsi_b200_index_load_rows(bigsi_b200_index *index, const char *path, uint64
  * fused into the query kernels: rank 0's gather kernel stores the k-mer bytes into its peers' inboxes over
  * NVLink as "low-latency lines" (every 8 bytes carry 4 data bytes and the query's 32-bit sequence
  * number, so the receiving kernel spins per 16-byte line and no fence or separate flag is needed);
- * every rank's reduce kernel publishes its hit list into slot `rank` of every rank's result blocks and
- * finishes only when all slots of its own copy have arrived (all-gather semantics in stream order) --
- * while the next query's gather kernel is already streaming rows, so the shards do not wait for each
- * other on the critical path.  Every device-side wait is bounded ("spin_timeout_ms"): a rank whose peers
+ * every rank's stage 2 (the merge team of the next query's gather kernel, or the flush kernel) publishes its
+ * hit list into slot `rank` of every rank's result blocks and finishes only when all slots of its own copy have
+ * arrived (all-gather semantics in stream order) -- while the next query's rows are already streaming, so
+ * the shards do not wait for each other on the critical path.  Every device-side wait is bounded ("spin_timeout_ms"): a rank whose peers
  * never launch gets BIGSI_B200_ERR_TIMEOUT instead of a hung GPU.  One handle per GPU; handles may live in
  * different processes (CUDA IPC) or in one (open_local; they may even share a device).  Calls are SPMD:
  * every rank calls exchange_search_dev once per query with the same n_kmers / k / h / min_kmers.
@@ -315,12 +333,13 @@ int bigsi_b200_index_load_rows(bigsi_b200_index *index, const char *path, uint64
  * search_dev: d_kmers = n_kmers * k raw unique k-mers, 16-byte aligned, addressable by rank 0's device
  *         (device memory or mapped pinned host memory; ignored on other ranks).  *d_blocks_out = device
  *         pointer to `world` result blocks of *block_bytes_out bytes each, block r = { u64 seq; u64
- *         n_hits; int32 cols[spec]; uint32 counts[spec] } with LOCAL column ids of shard r; valid in
- *         stream order after the call and until 4 more searches have been issued on this handle (eight
- *         generations of blocks rotate).
+ *         n_hits; int32 cols[spec]; uint32 counts[spec] } with LOCAL column ids of shard r; a DEFERRED
+ *         call (see above): complete in stream order after the NEXT search_dev call or bigsi_b200_index_flush
+ *         (every rank flushes), valid until 4 more searches have been issued on this handle (eight generations
+ *         of blocks rotate).
  * reserve: optional; see below.
  * wait_ns: synchronises the device; returns (and resets) the sum over the queries since the last call of
- *         the time this rank's reduce kernel waited for the other shards' hit lists (diagnostics). */
+ *         the time this rank's stage 2 waited for the other shards' hit lists (diagnostics). */
 int bigsi_b200_exchange_create(bigsi_b200_index *index, int world, int rank, uint64_t max_kmer_bytes, uint32_t spec,
                                uint8_t *ipc_handle_out);
 int bigsi_b200_exchange_open(bigsi_b200_index *index, const uint8_t *ipc_handles);

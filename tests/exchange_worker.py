@@ -45,10 +45,15 @@ def main():
     dist.barrier()
     ok, detail = True, ""
     try:
-        copies = []
+        copies, prev = [], None
         for j, n in enumerate(sizes):  # back to back: no host synchronisation between the queries
             thr = int(math.ceil(n * (0.85 if j % 3 else 0.4)))
-            copies.append(ex.search(d_queries[j], n, thr).clone())
+            view = ex.search(d_queries[j], n, thr)
+            if prev is not None:  # deferred: the result of query j-1 is complete behind the launch of query j
+                copies.append(prev.clone())
+            prev = view
+        ex.flush()  # the last one: stage 2 as a kernel of its own (every rank)
+        copies.append(prev.clone())
         torch.cuda.synchronize()
         _lib = B._lib
         _lib.check(_lib.lib().bigsi_b200_index_status(ix.handle))

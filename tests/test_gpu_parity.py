@@ -617,16 +617,27 @@ def test_fused_exchange_shards_one_process(B, world):
         for base, end in ((0, 1), (1, 7), (7, len(sizes))):  # 1, 6 and 7 queries in flight without a host sync
             burst = sizes[base:end]
             copies = []
+            prev = None
+
+            def consume(views):  # on each shard's own stream, in stream order
+                per_rank = [None] * world
+                for g in order:
+                    with torch.cuda.device(shards[g].device), torch.cuda.stream(streams[g]):
+                        per_rank[g] = views[g].clone()
+                copies.append(per_rank)
+
             for j, n_kmers in enumerate(burst):
                 thr = int(math.ceil(n_kmers * 0.85))
-                views, per_rank = [None] * world, [None] * world
+                views = [None] * world
                 for g in order:  # every rank's launch first: nothing that may block the host in between
                     with torch.cuda.device(shards[g].device), torch.cuda.stream(streams[g]):
                         views[g] = exs[g].search(d_queries[base + j] if g == 0 else None, n_kmers, thr)
-                for g in order:
-                    with torch.cuda.device(shards[g].device), torch.cuda.stream(streams[g]):
-                        per_rank[g] = views[g].clone()  # consumed on the shard's own stream, in stream order
-                copies.append(per_rank)
+                if prev is not None:  # deferred: query j-1 is complete behind the launch of query j
+                    consume(prev)
+                prev = views
+            for g in order:  # the last query of the burst: stage 2 as a kernel of its own, on every shard
+                exs[g].flush()
+            consume(prev)
             for d in range(ndev):
                 torch.cuda.synchronize(d)
             for g in range(world):
