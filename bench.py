@@ -3,14 +3,15 @@
 
 Workload (config.workload): synthetic m=25 000 000, h=3, k=31 index with 50 000 sample columns
 PER GPU resident in HBM (156.8 GB/GPU); one STEP = a block of 64 distinct 10 000-k-mer queries, each
-run through the hot path on its own: canonical+murmur3 hashing, gather-AND-popcount (gather kernel),
-merge + threshold at min_kmers = U (reduce kernel; an exact query through the count path), i.e. 2 kernel
-launches per query, no batching across queries.  The 64 queries of a step are all different
-(187.5 MB of rows per query > 126 MB L2), every query's hit list is produced separately.
+run through the hot path on its own: canonical+murmur3 hashing, gather-AND-popcount (the gather warps of
+its kernel), merge + threshold at min_kmers = U (an exact query through the count path; done by the merge
+team of the NEXT query's kernel, by a flush kernel behind the 64th), i.e. one kernel launch per query,
+no batching across queries.  The 64 queries of a step are all different (187.5 MB of rows per query >
+126 MB L2), every query's hit list is produced separately and is complete when the step ends.
 
 Metric: k-mer row-AND lookups/s, one lookup = gather h rows of one 50 000-column shard and AND
 them (18 750 algorithmic bytes).  At N GPUs every rank looks the same k-mers up in its own
-column shard (rank 0's gather kernel pushes the k-mers to the peers, the reduce kernels all-gather
+column shard (rank 0's gather kernel pushes the k-mers to the peers, the merge teams all-gather
 the hits), so the whole-job value is N * U * 64 * steps / time.
 
 `--impl reference` times the CPU oracle port of the reference's algorithm (oracle/, OpenMP on all
@@ -222,13 +223,14 @@ def workload_config(args, n_gpus):
     return {
         "workload": "BASELINE configs[1]: synthetic m=%d h=%d k=%d, N=%d columns per GPU (x%d GPUs, column-sharded), "
                     "%d-k-mer exact queries (min_kmers=U), each on its own: canonical+murmur3 hash + gather-AND-popcount "
-                    "(gather kernel), merge + threshold (reduce kernel); one step = %d distinct queries back to back"
+                    "(one kernel per query), merge + threshold by the merge team of the next query's kernel (flush kernel behind "
+                    "the last); one step = %d distinct queries back to back, all hit lists complete at its end"
                     % (args.m, H, K, args.cols, n_gpus, args.kmers, QUERIES_PER_STEP),
         "m": args.m, "h": H, "k": K, "cols_per_gpu": args.cols, "kmers_per_query": args.kmers,
         "distinct_queries": N_DISTINCT, "queries_per_step": QUERIES_PER_STEP,
         "exchange": ("none (one shard)" if n_gpus == 1 else
-                     "in-kernel: rank 0's gather kernel pushes the query to the peers, every rank's reduce kernel publishes its hits "
-                     "to every rank and waits for the others' (while the next query's gather kernel runs) -- NVLink peer memory, "
+                     "in-kernel: rank 0's gather kernel pushes the query to the peers, every rank's merge team publishes its hits "
+                     "to every rank and waits for the others' (while the next query's rows stream) -- NVLink peer memory, "
                      "no collective call"
                      if getattr(args, "exchange", "fused") == "fused" else "NCCL broadcast + all-gather per query"),
         "l2_policy": "inputs larger than L2: each query gathers %.1f MB of distinct rows, %d distinct queries rotate"
@@ -394,8 +396,9 @@ def run_b200(args):
     merge_avg_ms = merge_ms / max(n_timed, 1)
     algo_bytes = info["last_algorithmic_bytes"]
     # The timed region is steps x 64 back-to-back queries, bracketed by ONE CUDA-event pair on their stream.  A query =
-    # one gather kernel (all the row traffic) + one small reduce kernel that runs concurrently with the NEXT query's
-    # gather kernel; the gather kernel's average launch duration in the stream is therefore region / queries.
+    # one gather_solo launch (all the row traffic; its merge team finishes the previous query in the shadow of the row
+    # stream) and consecutive launches overlap CTA by CTA, so the kernel's average launch duration in the stream is
+    # region / queries (the one flush kernel per step is inside the region too).
     kernel_ms = ms_max / n_queries
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     achieved_isolated = algo_bytes / (fused_avg_ms * 1e-3) / 1e9
@@ -465,13 +468,14 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "gather_solo<COUNTS,h=3> (in-kernel hash prologue + TMA row gather + AND + bit-sliced count; its "
-                                   "reduce_kernel runs concurrently with the next query's gather)" if streamed else "fused_query<COUNTS,h=3>",
+                         "kernel": "gather_solo<COUNTS,h=3,team> (in-kernel hash prologue + TMA row gather + AND + bit-sliced count; merge + "
+                                   "threshold of the previous query by its merge team)" if streamed else "fused_query<COUNTS,h=3>",
                          "kernel_ms": kernel_ms,
                          "timing": "one CUDA-event pair around the timed region of back-to-back queries, / queries",
                          "kernel_ms_isolated": fused_avg_ms, "achieved_isolated": achieved_isolated,
                          "frac_isolated": achieved_isolated / peak,
-                         "timing_isolated": "one CUDA-event pair per launch (serialises the launches: no overlap between queries, includes the launch gap)",
+                         "timing_isolated": "one CUDA-event pair per launch (serialises the launches: no overlap between queries, includes the "
+                                            "launch gap; the query's flush kernel is timed separately as reduce_kernel_ms_isolated)",
                          "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
                          "frac_of_8TBps_nominal": achieved / 8000.0, "reduce_kernel_ms_isolated": merge_avg_ms,
                          "launches_timed": int(n_timed)},
@@ -526,8 +530,8 @@ def run_e2e(args, index, searcher, shard, queries, h_queries, barrier, rank, wor
 
         h2d, d2h = QPS * (U + K - 1), QPS * (24 + 3 * 8)
         path = ("bigsi_b200_search_sequences (C ABI bulk call: %d host sequences in, %d hit lists out; per sequence the unique "
-                "windows are found inside the gather kernel, which reads the sequence out of pinned host memory, and the "
-                "reduce kernel writes the hits into mapped host memory; up to 7 searches in flight)" % (QPS, QPS))
+                "windows are found inside the gather kernel, which reads the sequence out of pinned host memory; the merge team "
+                "of the next sequence's kernel writes the hits into mapped host memory; up to 7 searches in flight)" % (QPS, QPS))
         # the same 64 sequences one synchronous call at a time (BIGSI.search's own call pattern)
         for q in range(3):
             index.search_sequence(h_seqs[q], K, H, 1.0, cap=HIT_CAP)
@@ -583,7 +587,7 @@ def run_e2e(args, index, searcher, shard, queries, h_queries, barrier, rank, wor
             return h_out[(QPS - 1) % 4]
 
         h2d, d2h = QPS * U * K, QPS * world * (2 + 2 * HIT_CAP) * 4
-        path = ("rank 0: pinned host k-mers read zero-copy by the gather kernel and pushed to the peers over NVLink; 2 kernels "
+        path = ("rank 0: pinned host k-mers read zero-copy by the gather kernel and pushed to the peers over NVLink; 1 kernel "
                 "per rank and query; all-gathered hit blocks -> pinned host memory (cudaMemcpyAsync) behind every query"
                 if fused else "pinned host k-mers -> H2D -> NCCL broadcast -> query -> NCCL all-gather -> D2H")
     for i in range(2):

@@ -315,6 +315,9 @@ def test_sharded_bigsi_matches_single_gpu(B, tmp_path):
         assert f1.read() == f2.read()
     re1 = B.BIGSI.load({"storage-config": {"filename": "sh-re1", "device": 0}}, path)
     re2 = B.BIGSI.load({"storage-config": {"filename": "sh-re2", "devices": devs[:2]}}, path)
+    # a BIGSI object fixes its Scorer's database size at construction (graph/bigsi.py:140), so `one` (45 samples when it
+    # was built, 49 now) is compared through a fresh handle on the same resident store, like the freshly loaded ones
+    one = B.BIGSI(one_cfg)
     same(one, re1)
     same(one, re2)
     for b in (one, sh, re1, re2):
