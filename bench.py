@@ -652,8 +652,10 @@ def dump_timeline(index, dev_query, barrier, rank):
     lines = ["rank %d timeline of the last query (us since its first gather CTA entered; min / median / max over CTAs)" % rank]
     for title, block, names in (("gather kernel", ts[:grid], {0: "entry", 8: "past_gate", 10: "front_end_done", 1: "prod_first_issue",
                                                              9: "hash_done", 2: "first_slot_landed", 5: "prod_last_issue",
-                                                             3: "last_slot_consumed", 4: "flushed"}),
-                                ("reduce kernel", ts[grid:], {0: "entry", 8: "past_dependency_wait", 13: "stage_issue",
+                                                             3: "last_slot_consumed", 4: "flushed", 6: "team_push_done",
+                                                             7: "team_done (merge of the previous query)"}),
+                                ("stage 2 of this query (merge team of the next kernel / flush kernel)", ts[grid:],
+                                 {0: "entry (flush kernel only)", 8: "past_dependency_wait", 13: "stage_issue",
                                                              10: "planes_loaded", 11: "counters_in_smem", 12: "expanded",
                                                              7: "items_done"})):
         lines.append(" " + title)

@@ -33,7 +33,11 @@ constexpr int kStreamStates = 8;
 constexpr int kMergeTeamWarps = 4;
 constexpr int kMergeTeamThreads = kMergeTeamWarps * 32;
 constexpr int kReduceThreads = 256;
-constexpr int kReduceSmemBytes = 16 * 1024;      // merge scratch of a streamed query (team and flush kernel alike)
+// merge scratch of a streamed query (team and flush kernel alike): large enough to stage all 148 slots of a
+// 10 000-k-mer query's merge item (7 planes x 48 B each) in ONE batch -- staging is latency bound (one bulk-copy
+// round trip per batch), and with five batches the team was still merging when its CTA's gather ended.  The ring
+// keeps 8 stages beside it, which is as fast as 11 (measured).
+constexpr int kReduceSmemBytes = 56 * 1024;
 constexpr int kReduceFatSmemBytes = 64 * 1024;   // isolated queries: the flush is on the critical path, bigger batches
 
 enum { kModeCounts = 0, kModeAnd = 1 };

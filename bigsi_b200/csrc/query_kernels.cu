@@ -396,6 +396,32 @@ __device__ __forceinline__ SoloGeom solo_geometry(const QueryParams &P, uint32_t
     return g;
 }
 
+// Query broadcast (rank 0 of a column-sharded search): this CTA's slice of the k-mer bytes (the 16-byte lines that cover
+// it; neighbouring CTAs write identical lines at the boundaries) goes into every peer's LL inbox over NVLink -- plain
+// stores with the flag embedded: no fence (which would also wait for the bulk copies in flight), nothing to wait
+// for.  The inbox was last used by query seq - kStreamRing, which every shard has finished (the entry gate).
+// Executed by `nthreads` threads (tid = 0 .. nthreads-1): the merge team, which is idle at this point of the
+// CTA's life, or -- in the kernel variants without one -- the producer warp once its first ring-full is in flight.
+__device__ __forceinline__ void push_query_slice(const QueryParams &P, uint64_t begin, uint32_t cnt, uint32_t tid, uint32_t nthreads)
+{
+    const uint64_t b0 = begin * P.k, b1 = (begin + cnt) * P.k;
+    const uint64_t l0 = b0 >> 4, nvec = ((b1 + 15) >> 4) - l0;
+    const uint4 *src = reinterpret_cast<const uint4 *>(P.kmers) + l0;
+    constexpr int kBatch = 6;  // loads in flight per thread: a 68-k-mer slice (133 lines) is one batch of a warp
+    for (uint64_t i0 = tid; i0 < nvec; i0 += (uint64_t)nthreads * kBatch) {
+        uint4 v[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u)
+            if (i0 + (uint64_t)nthreads * u < nvec) v[u] = __ldg(src + i0 + (uint64_t)nthreads * u);
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u)
+            if (i0 + (uint64_t)nthreads * u < nvec)
+                for (uint32_t r = 0; r < P.n_push; ++r)
+                    ll_store_line(P.ll.out[r] + 2 * (l0 + i0 + (uint64_t)nthreads * u), v[u], P.ll.flag);
+    }
+}
+
+template <bool PUSH>
 __device__ __forceinline__ void solo_producer(const QueryParams &P, const SoloGeom &sg, uint8_t *smem, uint8_t *ring,
                                               int32_t *ids, uint8_t *scratch, uint64_t *full, uint64_t *empty)
 {
@@ -442,28 +468,7 @@ __device__ __forceinline__ void solo_producer(const QueryParams &P, const SoloGe
         const int32_t *id = ids + (size_t)k0 * h;
         issue(min(G, sg.n_first - k0), [&](uint32_t i) { return id[i]; });
     }
-    if (P.n_push && sg.cnt) {
-        // query broadcast (rank 0 of a column-sharded search), off the critical path: the first ring-full is in
-        // flight and the consumer warps are still hashing, so this warp has nothing else to do.  This CTA's slice
-        // of the k-mer bytes (the 16-byte lines that cover it; neighbouring CTAs write identical lines at the
-        // boundaries) goes into every peer's LL inbox over NVLink -- plain stores with the flag embedded: no fence
-        // (which would also wait for the bulk copies in flight), nothing to wait for.  The inbox was last used by
-        // query seq - kStreamRing, which every shard has finished (the entry gate).
-        const uint64_t b0 = sg.begin * P.k, b1 = (sg.begin + sg.cnt) * P.k;
-        const uint64_t l0 = b0 >> 4, nvec = ((b1 + 15) >> 4) - l0;
-        const uint4 *src = reinterpret_cast<const uint4 *>(P.kmers) + l0;
-        constexpr int kBatch = 6;  // loads in flight per lane: a 68-k-mer slice (133 lines) is one batch
-        for (uint64_t i0 = lane; i0 < nvec; i0 += 32 * kBatch) {
-            uint4 v[kBatch];
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u)
-                if (i0 + 32 * u < nvec) v[u] = __ldg(src + i0 + 32 * u);
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u)
-                if (i0 + 32 * u < nvec)
-                    for (uint32_t r = 0; r < P.n_push; ++r) ll_store_line(P.ll.out[r] + 2 * (l0 + i0 + 32 * u), v[u], P.ll.flag);
-        }
-    }
+    if (PUSH && P.n_push && sg.cnt) push_query_slice(P, sg.begin, sg.cnt, lane, 32u);  // (variants without a merge team)
     named_bar_sync<kBarIdsReady>(gather_threads(P));  // the consumer warps have hashed the rest of the range
     for (; k0 < sg.n_static; k0 += G) {
         const int32_t *id = ids + (size_t)k0 * h;
@@ -664,8 +669,15 @@ gather_solo(const __grid_constant__ QueryParams P, const __grid_constant__ Query
     if (!*s_gate) return;
 
     if (TEAM && threadIdx.x >= n_gather) {
-        // ---- merge team: stage 2 of the PREVIOUS streamed query, once its gather kernel (the preceding grid) is
-        // complete and its planes are visible.  Its scratch lies behind the ring.
+        // ---- merge team.  First the query broadcast of a column-sharded search (rank 0): the team has nothing else to
+        // do yet, and the peers' hashing waits for these lines.  Then stage 2 of the PREVIOUS streamed query, once its
+        // gather kernel (the preceding grid) is complete and its planes are visible.  Its scratch lies behind the ring.
+        if (P.n_push) {
+            if (P.stream_wait_inputs) grid_dependency_wait();
+            const uint32_t cnt = solo_range_cnt(P, blockIdx.x, P.total_kmers);
+            if (cnt) push_query_slice(P, (uint64_t)blockIdx.x * P.items_per_slice, cnt, threadIdx.x - n_gather, (uint32_t)kMergeTeamThreads);
+            if (threadIdx.x == n_gather) BIGSI_TS(6);
+        }
         if (!P.merge_prev) return;
         grid_dependency_wait();
         const WarpGroupTeam<kBarMergeTeam> T{n_gather, (uint32_t)kMergeTeamThreads};
@@ -673,6 +685,7 @@ gather_solo(const __grid_constant__ QueryParams P, const __grid_constant__ Query
         uint8_t *team_smem = ring + (size_t)P.n_stages * P.kmers_per_stage * P.h * P.tile_bytes;
         reduce_query<kModeCounts>(PV, team_smem, reinterpret_cast<uint64_t *>(smem + kTeamBarOffset),
                                   reinterpret_cast<volatile int *>(smem + kTeamFlagOffset), T, blockIdx.x, gridDim.x);
+        if (threadIdx.x == n_gather) BIGSI_TS(7);
         return;
     }
 
@@ -729,7 +742,7 @@ gather_solo(const __grid_constant__ QueryParams P, const __grid_constant__ Query
     sg.span = span;
     sg.ulist = ulist;
     if ((threadIdx.x >> 5) == consumer_warps)
-        solo_producer(P, sg, smem, ring, ids, scratch, full, empty);
+        solo_producer<!TEAM>(P, sg, smem, ring, ids, scratch, full, empty);
     else
         solo_consumer<MODE, HC, NP>(P, sg, smem, ring, ids, scratch, full, empty);
 }
