@@ -153,6 +153,10 @@ struct Exchange {
     bool ipc_opened[kMaxSinks] = {};
     bool ready = false;
     uint64_t seq = 0;            // queries launched on this shard
+    // optional host results (bigsi_b200_exchange_host_results): kStreamStates blocks of mapped host memory, query s ->
+    // block s % kStreamStates = [u64 seq][u64 pad][world x block_bytes]
+    PinnedBuf h_gather;
+    uint64_t h_gather_block = 0;
 };
 constexpr uint64_t kExInboxes = kStreamRing, kExGenerations = 2 * kStreamRing;
 
@@ -432,6 +436,8 @@ struct HitsOut {
     uint32_t n_gather = 0;
     const unsigned long long *gather_blocks[kMaxSinks] = {};
     unsigned long long gather_seq = 0;
+    unsigned long long *host_gather = nullptr;  // device address of the mapped host block the gathered hits are copied into
+    uint32_t host_block_words = 0;
     // the number of k-mers comes from a preceding kernel (query front-end): only the streamed path can follow it;
     // run_query returns 1 without launching anything when the plan is a different one
     const unsigned long long *total_dev = nullptr;
@@ -591,6 +597,8 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
         p.n_gather = hits->n_gather;
         for (uint32_t i = 0; i < hits->n_gather; ++i) p.gather_blocks[i] = hits->gather_blocks[i];
         p.gather_seq = hits->gather_seq;
+        p.host_gather = hits->host_gather;
+        p.host_block_words = hits->host_block_words;
         p.ll = hits->ll;
         p.ll.kmers_base = reinterpret_cast<const uint8_t *>(d_kmers);
         p.sink_spec = hits->sink_spec;
@@ -2224,6 +2232,7 @@ int bigsi_b200_exchange_destroy(bigsi_b200_index *ix)
     for (int r = 0; r < ex.world; ++r)
         if (ex.ipc_opened[r] && ex.peer[r]) cudaIpcCloseMemHandle(ex.peer[r]);
     cudaFree(ex.local);
+    ex.h_gather.release();
     ex = Exchange();
     return 0;
 }
@@ -2288,6 +2297,12 @@ static int exchange_search(bigsi_b200_index *ix, const char *d_kmers, uint64_t n
         ho.sinks[r] = exchange_slot(ex, r, seq);
         ho.gather_blocks[r] = reinterpret_cast<const unsigned long long *>(blocks + r * ex.block_bytes);
     }
+    if (ex.h_gather.p) {
+        void *dp = nullptr;
+        CK(cudaHostGetDevicePointer(&dp, static_cast<uint8_t *>(ex.h_gather.p) + (seq % kStreamStates) * ex.h_gather_block, 0));
+        ho.host_gather = static_cast<unsigned long long *>(dp);
+        ho.host_block_words = (uint32_t)(ex.block_bytes / 8);
+    }
     const char *kmers = d_kmers;
     if (ex.rank == 0) {
         for (int r = 1; r < ex.world; ++r) ho.ll.out[ho.n_push++] = ll_inbox(r);
@@ -2341,6 +2356,53 @@ int bigsi_b200_exchange_search_dev(bigsi_b200_index *ix, const char *d_kmers, ui
     if (int rc = exchange_search(ix, d_kmers, n_kmers, k, h, min_kmers, static_cast<cudaStream_t>(stream))) return rc;
     if (d_blocks_out) *d_blocks_out = exchange_blocks(ix->ex, ix->ex.seq);
     if (block_bytes_out) *block_bytes_out = ix->ex.block_bytes;
+    return 0;
+}
+
+int bigsi_b200_exchange_last_seq(bigsi_b200_index *ix, uint64_t *seq_out)
+{
+    if (int rc = check_index(ix)) return rc;
+    if (!seq_out) return fail(BIGSI_B200_ERR_INVALID, "null pointer");
+    *seq_out = ix->ex.seq;
+    return 0;
+}
+
+int bigsi_b200_exchange_host_results(bigsi_b200_index *ix)
+{
+    if (int rc = check_index(ix)) return rc;
+    Exchange &ex = ix->ex;
+    if (!ex.local) return fail(BIGSI_B200_ERR_INVALID, "exchange not created");
+    if (ex.seq) return fail(BIGSI_B200_ERR_INVALID, "enable host results before the first search");
+    DeviceGuard guard(ix->device);
+    ex.h_gather_block = round_up(16 + (uint64_t)ex.world * ex.block_bytes, 128);
+    cudaError_t e = ex.h_gather.reserve(ex.h_gather_block * kStreamStates);
+    if (e != cudaSuccess) return fail_cuda(e, "pinned result blocks");
+    return 0;
+}
+
+int bigsi_b200_exchange_wait_host(bigsi_b200_index *ix, uint64_t seq, const void **blocks_out, uint64_t *block_bytes_out)
+{
+    if (int rc = check_index(ix)) return rc;
+    Exchange &ex = ix->ex;
+    if (!ex.h_gather.p) return fail(BIGSI_B200_ERR_INVALID, "host results are not enabled on this exchange");
+    if (seq == 0 || seq > ex.seq || seq + kStreamStates <= ex.seq)
+        return fail(BIGSI_B200_ERR_INVALID, "query %llu is not among the last %d searches (last: %llu)", (unsigned long long)seq,
+                    kStreamStates, (unsigned long long)ex.seq);
+    DeviceGuard guard(ix->device);
+    // the newest search has nobody behind it to run its stage 2: flush it (SPMD: every rank does, or searches on)
+    if (ix->pending.have && ix->pending.p.gather_seq == seq && ix->pending.p.host_gather)
+        if (int rc = flush_pending(ix)) return rc;
+    volatile unsigned long long *blk = reinterpret_cast<volatile unsigned long long *>(static_cast<uint8_t *>(ex.h_gather.p) +
+                                                                                    (seq % kStreamStates) * ex.h_gather_block);
+    uint64_t spins = 0;
+    while (__atomic_load_n(&blk[0], __ATOMIC_ACQUIRE) != seq) {
+        if ((++spins & 0x3fff) == 0) {
+            // (every device-side wait is bounded: a search that cannot complete raises the abort word)
+            if (const unsigned long long av = abort_state(ix)) return fail_aborted(av);
+        }
+    }
+    if (blocks_out) *blocks_out = const_cast<unsigned long long *>(blk) + 2;
+    if (block_bytes_out) *block_bytes_out = ex.block_bytes;
     return 0;
 }
 

@@ -432,6 +432,31 @@ __device__ __forceinline__ void reduce_query(const QueryParams &P, uint8_t *merg
         atomicMax(&P.qstate->wait_ns, globaltimer_ns() - t0);
     }
     T.sync();
+    if (P.host_gather && P.n_gather) {
+        // every shard's hit list -> mapped host memory (the waiting threads' acquire loads + the barrier above order
+        // these reads behind the peers' publications; volatile loads: nothing stale from L1)
+        for (uint32_t r = 0; r < P.n_gather; ++r) {
+            const unsigned long long *src = P.gather_blocks[r];
+            unsigned long long *dst = P.host_gather + 2 + (size_t)r * P.host_block_words;
+            const unsigned long long n = ld_volatile_u64(src + 1);
+            const uint32_t m = (uint32_t)(n < P.sink_spec ? n : P.sink_spec);
+            if (T.tid() == 0) {
+                dst[0] = P.gather_seq;
+                dst[1] = n;
+            }
+            const volatile uint32_t *sc = reinterpret_cast<const volatile uint32_t *>(src + 2);
+            uint32_t *dc = reinterpret_cast<uint32_t *>(dst + 2);
+            for (uint32_t i = T.tid(); i < m; i += T.size()) {
+                dc[i] = sc[i];
+                dc[P.sink_spec + i] = sc[P.sink_spec + i];
+            }
+        }
+        T.sync();
+        if (T.tid() == 0) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(P.host_gather) = P.gather_seq;
+        }
+    }
     if (T.tid() == 0) {
         BIGSI_TS(6);
         if (P.wait_ns_out) atomicAdd(P.wait_ns_out, P.qstate->wait_ns);

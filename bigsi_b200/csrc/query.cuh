@@ -152,6 +152,12 @@ struct QueryParams {
     // have reported".  The next query's gather kernel is already running by then: the wait costs no bandwidth.
     uint32_t n_gather;
     unsigned long long gather_seq;
+    // optional: once all blocks are here, copy them (header + the hits each one holds) into a block of mapped HOST
+    // memory, [0] = gather_seq (written last, behind a system fence), [1] unused, then n_gather blocks of
+    // host_block_words words in the layout of the device blocks -- the host reads every shard's hits without a copy
+    // operation in the stream
+    unsigned long long *host_gather;
+    uint32_t host_block_words;
     const unsigned long long *gather_blocks[kMaxSinks];
     // streamed launch (solo geometry, fuse_merge == 0): no grid barrier and no wait for the preceding kernel.  The
     // gather kernel flushes its planes and exits; reduce_kernel (merge_kernels.cu) merges, thresholds and publishes

@@ -228,6 +228,27 @@ class FusedExchange:
         """Stage 2 of the last search as a kernel of its own (SPMD: every rank calls it)."""
         self.shard.index.flush()
 
+    def enable_host_results(self):
+        """Before the first search: every search's all-gathered hit lists are also written into mapped host memory by
+        the kernels themselves (no copy in the stream); see wait_host."""
+        self._lib.check(self._lib.lib().bigsi_b200_exchange_host_results(self.shard.index.handle))
+
+    def last_seq(self):
+        s = self._ct.c_uint64(0)
+        self._lib.check(self._lib.lib().bigsi_b200_exchange_last_seq(self.shard.index.handle, self._ct.byref(s)))
+        return s.value
+
+    def wait_host(self, seq):
+        """Blocks until search number `seq` (last_seq() right after its search()) is complete on this rank and returns
+        its result as a numpy int32 view [world, 2 + 2*spec] of HOST memory (the packed layout of search()), valid
+        until 8 more searches.  Flushes the search when it is the newest one (then every rank must flush too)."""
+        ct = self._ct
+        ptr, stride = ct.c_void_p(0), ct.c_uint64(0)
+        self._lib.check(self._lib.lib().bigsi_b200_exchange_wait_host(self.shard.index.handle, seq, ct.byref(ptr), ct.byref(stride)))
+        n = self.world * stride.value // 4
+        arr = np.ctypeslib.as_array((ct.c_int32 * n).from_address(ptr.value)).reshape(self.world, stride.value // 4)
+        return arr[:, 2: 4 + 2 * self.spec]
+
     def wait_ns(self):
         """(ns this rank's reduce kernels waited for the other shards since the last call, queries launched)."""
         ct = self._ct

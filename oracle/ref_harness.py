@@ -2,8 +2,10 @@
 /root/reference (read-only, only present in the build container) through the
 stand-ins in oracle/ref_shims, so golden vectors can be generated from the real
 reference code (tests/golden/make_golden.py) and the restatements in oracle/ can
-be cross-checked against it.  Never imported by bigsi_b200/ and never used on the
-GPU box (the reference does not travel).
+be cross-checked against it.  Never imported by bigsi_b200/.  On the GPU box the
+tree is absent; the unmodified package installed into the git-ignored baseline/_ref/
+(oracle/install_reference.py) is imported instead -- by the reference-suite injection
+test and by the "reference" CPU timing of bench.py only.
 
 Recipe:
   * `mmh3`, `bitarray`, `redis` stand-ins ahead of the reference on sys.path;
@@ -14,7 +16,11 @@ Recipe:
 import os
 import sys
 
+_INSTALLED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
 REFERENCE_ROOT = os.environ.get("BIGSI_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "bigsi")) and os.path.isdir(os.path.join(_INSTALLED, "bigsi")):
+    # the GPU box: no /root/reference, but the unmodified package installed by oracle/install_reference.py travels
+    REFERENCE_ROOT = _INSTALLED
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shims")
 
 _DICT_STORES = {}

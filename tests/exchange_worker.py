@@ -37,6 +37,7 @@ def main():
     ix.set_option("inputs_ready", 1)
     shard = DeviceShard(ix, k, h, cap=cap)
     ex = FusedExchange(shard, world, rank, 8000, dist=dist)
+    ex.enable_host_results()  # the kernels also write every query's gathered hits into mapped host memory
     sizes = [25, 3000, 1, 7000, 640, 2500, 6000, 77, 4000, 4000, 333, 8000, 5, 1234]
     acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
     queries = [acgt[rng.integers(0, 4, size=(n, k))] for n in sizes]
@@ -45,15 +46,20 @@ def main():
     dist.barrier()
     ok, detail = True, ""
     try:
-        copies, prev = [], None
+        copies, prev, seqs, host = [], None, [], {}
         for j, n in enumerate(sizes):  # back to back: no host synchronisation between the queries
             thr = int(math.ceil(n * (0.85 if j % 3 else 0.4)))
             view = ex.search(d_queries[j], n, thr)
+            seqs.append(ex.last_seq())
             if prev is not None:  # deferred: the result of query j-1 is complete behind the launch of query j
                 copies.append(prev.clone())
             prev = view
+            if j >= 3 and rank % 2 == 0:  # host results consumed while later searches are in flight (some ranks only)
+                host[j - 3] = np.array(ex.wait_host(seqs[j - 3]))
         ex.flush()  # the last one: stage 2 as a kernel of its own (every rank)
         copies.append(prev.clone())
+        for j in range(max(0, len(sizes) - 6), len(sizes)):
+            host[j] = np.array(ex.wait_host(seqs[j]))
         torch.cuda.synchronize()
         _lib = B._lib
         _lib.check(_lib.lib().bigsi_b200_index_status(ix.handle))
@@ -63,6 +69,14 @@ def main():
             cnt = oix.counts([bytes(r).decode() for r in queries[j]])
             exp = np.nonzero(cnt >= thr)[0]
             nh, cols, vals = unpack_hits(copies[j].cpu().numpy(), 1, cap)
+            if j in host:  # the host copy carries the same hit counts and the same hits (up to what a block holds)
+                hn, hc_, hv_ = unpack_hits(host[j], 1, cap)
+                same = np.array_equal(hn, nh) and all(
+                    np.array_equal(hc_[g, 0, : min(int(nh[g, 0]), cap)], cols[g, 0, : min(int(nh[g, 0]), cap)]) and
+                    np.array_equal(hv_[g, 0, : min(int(nh[g, 0]), cap)], vals[g, 0, : min(int(nh[g, 0]), cap)]) for g in range(world))
+                if not same:
+                    ok, detail = False, "query %d: host result block differs from the device blocks on rank %d" % (j, rank)
+                    break
             if (nh[:, 0] > cap).any():
                 if int(nh[:, 0].sum()) != len(exp):
                     ok, detail = False, "query %d: %d hits, expected %d" % (j, int(nh[:, 0].sum()), len(exp))
