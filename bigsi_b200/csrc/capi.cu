@@ -172,7 +172,7 @@ struct bigsi_b200_index {
     bool timing = false;
     int64_t opt_debug_flags = 0;
     int64_t opt_prehash = 1, opt_fuse_merge = 1, opt_merge_chunk_bytes = 0, opt_solo = 1, opt_pool_pct = -1, opt_zero_copy = 1, opt_cooperative = 1;
-    int64_t opt_inputs_ready = 0, opt_spin_timeout_ms = 10000, opt_defer = 1;
+    int64_t opt_inputs_ready = 0, opt_spin_timeout_ms = 10000, opt_defer = 1, opt_direct = 1;
     // streamed single-query launches (query.cuh:kStreamRing): ring-buffered scratch + the completion / abort words
     DevBuf d_pool;            // kStreamRing x [ready flags: grid x u64][ids: grid x pool_share x h x i32]
     uint64_t pool_slot_bytes = 0;
@@ -708,6 +708,12 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
         if (hits && hits->published) *hits->published = will_publish;
     } else {
         if (int rc = flush_pending(ix)) return rc;
+        // batches in COUNTS mode: queries that lie inside one slice are finished by the CTA that counts them; the hit
+        // counters are zeroed here (the kernel's CTAs start at different times, so it cannot do that itself)
+        if (mode == BIGSI_B200_MODE_COUNTS && n_queries > 1 && grid > 0 && ix->opt_direct != 0) {
+            p.direct_complete = 1;
+            if (hits) CK(cudaMemsetAsync(hits->n, 0, n_queries * sizeof(unsigned long long), stream));
+        }
         const uint64_t need = query_partial_bytes(p);
         if (need > ix->partial.cap) {
             CK(cudaStreamSynchronize(stream));
@@ -962,6 +968,7 @@ int bigsi_b200_index_set_option(bigsi_b200_index *ix, const char *key, int64_t v
     else if (!strcmp(key, "zero_copy")) ix->opt_zero_copy = value;
     else if (!strcmp(key, "cooperative")) ix->opt_cooperative = value;
     else if (!strcmp(key, "inputs_ready")) ix->opt_inputs_ready = value;
+    else if (!strcmp(key, "direct")) ix->opt_direct = value;  // 0: batches merge every query (no direct finish)
     else if (!strcmp(key, "defer")) ix->opt_defer = value;  // 0: every streamed query is flushed at once (diagnostics)
     else if (!strcmp(key, "spin_timeout_ms")) ix->opt_spin_timeout_ms = value < 1 ? 1 : value;
     else if (!strcmp(key, "pool_pct")) ix->opt_pool_pct = value > 100 ? -1 : value;  // > 100 = automatic

@@ -176,6 +176,8 @@ __device__ __forceinline__ void merge_item(const QueryParams &P, uint64_t item, 
 {
     MergeGeom G;
     if (!merge_geometry(P, item, G)) return;  // block-uniform
+    // a query inside one slice was finished by the CTA that counted it (query_kernels.cu:direct_output)
+    if (MODE == kModeCounts && P.direct_complete && G.n_slots == 1) return;
     const uint32_t lane = T.tid() & 31, warp = T.tid() >> 5, nwarps = T.size() >> 5;
     const uint32_t pps = MODE == kModeCounts ? P.planes_per_slot : 1;
     const uint32_t cb = P.merge_cb;
@@ -341,6 +343,88 @@ __device__ __forceinline__ void merge_item(const QueryParams &P, uint64_t item, 
             const double need = ceil(__dmul_rn((double)__ldcg(&P.qstate->n_unique), P.seq_threshold));
             thr = need <= 0.0 ? 0u : need >= 4294967295.0 ? 0xffffffffu : (uint32_t)need;
         }
+        // Word-parallel expansion: thread = one 32-column word.  Its pps x J planes (plane (b, j) has weight 2^(b+j))
+        // are added into a BINARY bit-sliced accumulator of np = bits(longest query) planes -- a ripple-carry add per
+        // plane, 32 columns at a time -- kept in the (now free) staging area, plane-major so that the warp's accesses
+        // never conflict.  The threshold is a bit-sliced >= comparison against the constant; only hits (and, with a
+        // count buffer, all columns) are turned into integers.  ~20 instructions per word and warp instead of ~130
+        // for the column-per-lane expansion below, which remains for scratch areas too small for the accumulators.
+        const uint32_t np = P.total_planes < 1 ? 1 : P.total_planes;
+        const uint32_t stage_bytes_avail = P.merge_smem - cnt_bytes;
+        if ((uint64_t)T.size() * np * 4 <= stage_bytes_avail) {
+            uint32_t *acc = reinterpret_cast<uint32_t *>(stage) + T.tid();
+            const uint32_t ts = T.size();
+            for (uint32_t w0 = 0; w0 < G.vw; w0 += ts) {  // team-uniform trip count (warp shuffles inside)
+                const uint32_t w = w0 + T.tid();
+                const bool have = w < G.vw;
+                uint32_t ge = 0, valid = 0;
+                const uint32_t wcol0 = G.col0 + w * 32;
+                if (have) {
+                    for (uint32_t p = 0; p < np; ++p) acc[p * ts] = 0u;
+                    const uint32_t *cw = cnt + (size_t)w * pps * J;
+                    for (uint32_t b = 0; b < pps; ++b)
+                        for (uint32_t j = 0; j < J; ++j) {
+                            uint32_t x = cw[b * J + j];
+                            for (uint32_t p = b + j; x && p < np; ++p) {
+                                const uint32_t a = acc[p * ts];
+                                acc[p * ts] = a ^ x;
+                                x &= a;
+                            }
+                        }
+                    if (wcol0 < P.num_cols) {  // columns of this word that exist (bit i <-> column wcol0 + (i ^ 7))
+                        const uint32_t rem = P.num_cols - wcol0;
+                        if (rem >= 32) valid = 0xffffffffu;
+                        else
+                            for (uint32_t k8 = 0; k8 < 4; ++k8) {
+                                const uint32_t r = rem > 8 * k8 ? rem - 8 * k8 : 0;
+                                valid |= (r >= 8 ? 0xffu : r ? ((0xffu << (8 - r)) & 0xffu) : 0u) << (8 * k8);
+                            }
+                    }
+                    if (out)
+                        for (uint32_t i = 0; i < 32; ++i)
+                            if ((valid >> i) & 1u) {
+                                uint32_t v = 0;
+                                for (uint32_t p = 0; p < np; ++p) v |= ((acc[p * ts] >> i) & 1u) << p;
+                                out[wcol0 + (i ^ 7u)] = v;
+                            }
+                    if (thresholding) {
+                        uint32_t g = 0xffffffffu;  // "equal so far" counts as >=
+                        for (uint32_t p = 0; p < np; ++p) {
+                            const uint32_t a = acc[p * ts];
+                            g = ((thr >> p) & 1u) ? (a & g) : (a | g);
+                        }
+                        ge = (np < 32 && (thr >> np)) ? 0u : (g & valid);  // beyond the counters' range: never reached
+                    }
+                }
+                if (thresholding) {  // counts >= min_kmers (graph/bigsi.py:241-242), warp-level compaction
+                    const uint32_t mine = __popc(ge);
+                    uint32_t incl = mine;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= (uint32_t)d) incl += o;
+                    }
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total) {  // warp-uniform
+                        unsigned long long base = 0;
+                        if (lane == 31) base = atomicAdd(P.n_hits + G.q, (unsigned long long)total);
+                        base = __shfl_sync(0xffffffffu, base, 31);
+                        uint64_t pos = base + (incl - mine);
+                        while (ge) {
+                            const uint32_t i = __ffs(ge) - 1;
+                            ge &= ge - 1;
+                            if (pos < P.hit_cap) {
+                                uint32_t v = 0;
+                                for (uint32_t p = 0; p < np; ++p) v |= ((acc[p * ts] >> i) & 1u) << p;
+                                P.hit_cols[(uint64_t)G.q * P.hit_cap + pos] = (int32_t)(wcol0 + (i ^ 7u));
+                                P.hit_counts[(uint64_t)G.q * P.hit_cap + pos] = v;
+                            }
+                            ++pos;
+                        }
+                    }
+                }
+            }
+        } else
         for (uint32_t w = warp; w < G.vw; w += nwarps) {
             uint32_t total = 0;
             const uint32_t *cw = cnt + (size_t)w * pps * J;

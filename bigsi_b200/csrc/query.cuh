@@ -179,6 +179,12 @@ struct QueryParams {
     unsigned long long *seq_table;       // its open-addressing table (seq_table_entries x u64, a power of two)
     uint64_t seq_table_entries;
     uint32_t seq_epoch;                  // 16-bit epoch that marks live table entries (stale ones count as empty)
+    // batches (generic path, COUNTS): a segment that covers a WHOLE query (the query lies inside one slice) is finished
+    // by the CTA that counted it, straight from its registers -- threshold by a bit-sliced comparison, the few hits
+    // extracted individually, optionally the full count vector -- and neither writes partial planes nor takes part in
+    // the merge phase (merge_item skips queries with a single slot).  Only queries cut by a slice boundary are merged.
+    // The hit counters are then zeroed by the host before the launch (the kernel's CTAs start at different times).
+    uint32_t direct_complete;
     uint32_t plain_launch;    // 1: launch WITHOUT the cooperative attribute (option "cooperative" = 0): the grid barrier
                               // then relies on grid <= resident CTA capacity alone; lets PDL start the next grid's CTAs early
     uint32_t debug_flags;     // bit 0: consumers skip the AND/count work (pure-gather ceiling measurement)

@@ -184,6 +184,86 @@ __device__ __forceinline__ void flush_planes(const VCounter<NP> &c, uint32_t pps
         if (b + 3 < (int)pps) stg128(slot_unit + (size_t)(b + 3) * plane_stride, c.hi[b]);
 }
 
+// A segment that covers a whole query: its counters ARE the query's counts.  Every thread holds the bit planes of
+// its 128 columns (word j of the unit, bit i <-> column 128*unit + 32*j + (i ^ 7): MSB-first bytes in little-endian
+// words).  Threshold by a bit-sliced >= comparison against the constant (2 operations per plane and word), hits
+// compacted per warp with one atomic, their counts extracted bit by bit; with a count buffer every column is
+// extracted.  Called by all threads of the consumer warps (warp shuffles inside); `active` = the unit lies in the tile.
+template <int NP>
+__device__ __forceinline__ void direct_output(const QueryParams &P, const VCounter<NP> &c, uint32_t q, uint32_t unit_col0, bool active)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    auto plane = [&](int b, int j) -> uint32_t {
+        return b == 0 ? c.ones.v[j] : b == 1 ? c.twos.v[j] : b == 2 ? c.fours.v[j] : c.hi[b - 3].v[j];
+    };
+    auto count_of = [&](int j, uint32_t i) -> uint32_t {
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < NP; ++b) v |= ((plane(b, j) >> i) & 1u) << b;
+        return v;
+    };
+    // columns of word j that exist: padding bits of the last byte(s) never count
+    uint32_t valid[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t w0 = unit_col0 + 32u * j;
+        uint32_t m = 0;
+        if (active && w0 < P.num_cols) {
+            const uint32_t rem = P.num_cols - w0;
+            if (rem >= 32) m = 0xffffffffu;
+            else
+                for (uint32_t k8 = 0; k8 < 4; ++k8) {
+                    const uint32_t r = rem > 8 * k8 ? rem - 8 * k8 : 0;
+                    m |= (r >= 8 ? 0xffu : r ? ((0xffu << (8 - r)) & 0xffu) : 0u) << (8 * k8);
+                }
+        }
+        valid[j] = m;
+    }
+    if (P.out) {
+        uint32_t *out = reinterpret_cast<uint32_t *>(P.out) + (uint64_t)q * P.out_stride;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            for (uint32_t i = 0; i < 32; ++i)
+                if ((valid[j] >> i) & 1u) out[unit_col0 + 32u * j + (i ^ 7u)] = count_of(j, i);
+    }
+    if (P.min_kmers == nullptr && !P.min_by_value) return;
+    const uint32_t thr = P.min_by_value ? P.min_kmers_value : __ldg(P.min_kmers + q);
+    uint32_t ge[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t g = 0xffffffffu;  // "equal so far" counts as >=
+#pragma unroll
+        for (int b = 0; b < NP; ++b) g = ((thr >> b) & 1u) ? (plane(b, j) & g) : (plane(b, j) | g);
+        ge[j] = (thr >> NP) ? 0u : (g & valid[j]);  // a threshold beyond the counter's range is never reached
+    }
+    const uint32_t mine = __popc(ge[0]) + __popc(ge[1]) + __popc(ge[2]) + __popc(ge[3]);
+    uint32_t incl = mine;  // inclusive prefix sum over the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += o;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;  // warp-uniform
+    unsigned long long base = 0;
+    if (lane == 31) base = atomicAdd(P.n_hits + q, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    uint64_t pos = base + (incl - mine);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t g = ge[j];
+        while (g) {
+            const uint32_t i = __ffs(g) - 1;
+            g &= g - 1;
+            if (pos < P.hit_cap) {
+                P.hit_cols[(uint64_t)q * P.hit_cap + pos] = (int32_t)(unit_col0 + 32u * j + (i ^ 7u));
+                P.hit_counts[(uint64_t)q * P.hit_cap + pos] = count_of(j, i);
+            }
+            ++pos;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // stage 1: producer warp
 // ------------------------------------------------------------------------------------------
@@ -322,7 +402,13 @@ __device__ __forceinline__ void tma_consumer(const QueryParams &P, const uint8_t
             }
         }
         if (threadIdx.x == 0) BIGSI_TS(3);
-        if (active) {
+        // the whole query in this one segment: finished here, no partial planes, no merge (QueryParams::direct_complete)
+        const bool complete = MODE == kModeCounts && P.direct_complete &&
+                              (uint64_t)s.nk == it.qend(s.q) - (P.n_queries == 1 ? 0ull : (uint64_t)__ldg(P.qoff + s.q));
+        if (complete) {
+            ctr.finish(nhi);
+            direct_output(P, ctr, s.q, (tb0 + unit * 16) * 8, active);
+        } else if (active) {
             const uint64_t slot = (uint64_t)s.slice + (uint64_t)s.tile * P.n_queries + s.q;
             const uint32_t chunk = unit * 16 / P.merge_cb;  // merge chunk this unit's columns belong to
             uint8_t *dst = P.partial + partial_offset(P, chunk, slot, 0) + (unit * 16 - chunk * P.merge_cb);
@@ -792,7 +878,7 @@ __global__ void __launch_bounds__(kMaxBlockThreads, 1) fused_query(const __grid_
     grid_dependency_wait();
     if (threadIdx.x == 0) BIGSI_TS(8);
 
-    if (P.n_hits != nullptr) {  // hit counters of the fused threshold (stage 2 adds to them)
+    if (P.n_hits != nullptr && !P.direct_complete) {  // hit counters of the fused threshold (stage 2 adds to them)
         for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < P.n_queries; q += gridDim.x * blockDim.x)
             P.n_hits[q] = 0ull;
     }

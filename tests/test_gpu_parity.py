@@ -137,6 +137,45 @@ def test_ragged_batch_with_empty_queries(B):
     ix.close()
 
 
+@pytest.mark.parametrize("opts", [{}, {"grid": 7}, {"tile_bytes": 64, "grid": 5}, {"grid": 1}, {"fuse_merge": 0, "grid": 9}])
+def test_batch_whole_query_segments_finished_directly(B, opts):
+    """Batches: a query that lies inside one slice is finished by the CTA that counted it (no partial planes, no merge);
+    queries cut by a slice boundary are merged.  Counts, thresholded hits (thresholds 0, mid, len, beyond len; a hit
+    capacity smaller than the hit list) against the oracle, and identical to the all-merged path (option direct = 0).
+    N is not a multiple of 8: the padding bits of the last byte must never become hits at threshold 0."""
+    rng = np.random.default_rng(101)
+    m, N, k, h, cap = 6007, 1003, 31, 3, 300
+    ix, packed = _random_index(B, rng, m, N, density=0.8)
+    oix = O.OracleIndex(k, m, h, N, rows=packed)
+    lens = [40, 0, 1, 333, 7, 64, 0, 250, 19, 8, 100, 55, 2, 129, 31]
+    qoff = np.concatenate([[0], np.cumsum(lens)])
+    arr = _rand_kmers(rng, int(qoff[-1]), k)
+    kmers = _kmer_strs(arr)
+    mins = np.array([int(np.ceil(n * f)) for n, f in zip(lens, [0.5, 0.0, 1.0, 0.6, 0.0, 0.4, 1.0, 0.55, 1.0, 2.0, 0.5, 0.0, 0.5, 0.45, 0.5])],
+                    dtype=np.uint32)
+    results = {}
+    for direct in (1, 0):
+        ix.set_option("direct", direct)
+        for key, v in opts.items():
+            ix.set_option(key, v)
+        counts = ix.search_kmers(arr, k, h, q_offsets=qoff)
+        hits = ix.search_kmers_hits(arr, k, h, mins, q_offsets=qoff, cap=cap)
+        results[direct] = (counts, hits)
+        for q, n in enumerate(lens):
+            cnt = oix.counts(kmers[qoff[q]: qoff[q + 1]]) if n else np.zeros(N, dtype=np.int64)
+            assert np.array_equal(counts[q].astype(np.int64), cnt.astype(np.int64)), (direct, q)
+            exp = np.nonzero(cnt >= mins[q])[0]
+            cols, vals, nh = hits[q]
+            assert nh == len(exp), (direct, q, nh, len(exp))
+            if len(exp) <= cap:
+                assert np.array_equal(cols, exp) and np.array_equal(vals.astype(np.int64), cnt[exp]), (direct, q)
+            else:  # more hits than the list holds: any `cap` of them, each with its exact count
+                assert len(cols) == cap and len(set(cols.tolist())) == cap
+                assert all(cnt[c] == v and cnt[c] >= mins[q] for c, v in zip(cols.tolist(), vals.tolist())), (direct, q)
+    assert np.array_equal(results[0][0], results[1][0])
+    ix.close()
+
+
 @pytest.mark.parametrize("opts", [
     {"tile_bytes": 16}, {"tile_bytes": 48, "kmers_per_stage": 1}, {"tile_bytes": 512, "kmers_per_stage": 4, "n_stages": 2},
     {"grid": 1}, {"grid": 3, "tile_bytes": 128}, {"grid": 1000}, {"kmers_per_stage": 8, "n_stages": 3},
