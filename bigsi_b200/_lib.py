@@ -43,6 +43,7 @@ class Info(ctypes.Structure):
         ("scratch_bytes", ctypes.c_uint64),
         ("last_fused", ctypes.c_uint32),
         ("last_reduce_grid", ctypes.c_uint32),
+        ("last_unique_kmers", ctypes.c_uint64),
     ]
 
     def asdict(self):

@@ -120,6 +120,99 @@ cudaError_t launch_lookup(const uint8_t *matrix, uint64_t pitch, uint32_t row_by
 }
 
 // ------------------------------------------------------------------------------------------
+// K12: shared row-gather reuse for batches (BASELINE configs[4]; the reference gathers every distinct row of ONE
+// query once, graph/index.py:45-48 -- here across the queries of a batch).  Two k-mers gather the same bytes iff
+// their h row ids agree, so the batch's k-mers are de-duplicated by their row-id tuples: an open-addressing table
+// keyed by a fingerprint of the tuple (equal tags are confirmed by comparing the ids, so the classes are exact),
+// the first k-mer to claim an entry represents its class and takes the next free unique id.  Pass 2 gives every
+// k-mer the id of its class and copies the representatives' row ids.  Table entry: tag (32) | k-mer index + 1 (32).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t row_tuple_fingerprint(const int32_t *r, int h)
+{
+    uint64_t fp = 0x9e3779b97f4a7c15ull ^ (uint64_t)h;
+    for (int j = 0; j < h; ++j) {
+        fp = (fp ^ (uint64_t)(uint32_t)__ldg(r + j)) * 0xff51afd7ed558ccdull;
+        fp ^= fp >> 29;
+    }
+    fp *= 0xc4ceb9fe1a85ec53ull;
+    return fp ^ (fp >> 32);
+}
+
+__global__ void __launch_bounds__(256) dedup_rows_claim_kernel(const int32_t *__restrict__ rows, uint64_t n, int h,
+                                                              unsigned long long *__restrict__ table, uint64_t mask,
+                                                              uint32_t *__restrict__ rep, uint32_t *__restrict__ uid_of,
+                                                              unsigned int *__restrict__ counter)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool claimed = false;
+    if (t < n) {
+        const int32_t *mine = rows + t * (uint64_t)h;
+        const uint64_t fp = row_tuple_fingerprint(mine, h);
+        const unsigned long long entry = ((fp >> 32) << 32) | (unsigned long long)(uint32_t)(t + 1);
+        uint64_t slot = fp & mask;
+        for (;;) {
+            unsigned long long cur = ld_volatile_u64(table + slot);
+            if (cur == 0ull) {
+                const unsigned long long old = atomicCAS(table + slot, 0ull, entry);
+                if (old == 0ull) {  // this k-mer represents its class
+                    rep[t] = (uint32_t)t;
+                    claimed = true;
+                    break;
+                }
+                cur = old;
+            }
+            if ((cur >> 32) == (fp >> 32)) {
+                const uint64_t o = (cur & 0xffffffffull) - 1;
+                const int32_t *other = rows + o * (uint64_t)h;
+                bool eq = true;
+                for (int j = 0; j < h && eq; ++j) eq = __ldg(other + j) == __ldg(mine + j);
+                if (eq) {
+                    rep[t] = (uint32_t)o;
+                    break;
+                }
+            }
+            slot = (slot + 1) & mask;
+        }
+    }
+    // unique ids: one atomic per warp (a batch of all-distinct k-mers would otherwise serialise a million atomics on one word)
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t m = __ballot_sync(0xffffffffu, claimed);
+    if (m) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned int)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (claimed) uid_of[t] = base + __popc(m & ((1u << lane) - 1u));
+    }
+}
+
+__global__ void __launch_bounds__(256) dedup_rows_assign_kernel(const int32_t *__restrict__ rows, uint64_t n, int h,
+                                                               const uint32_t *__restrict__ rep, const uint32_t *__restrict__ uid_of,
+                                                               int32_t *__restrict__ ids_out, int32_t *__restrict__ unique_rows)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t r = rep[t];
+    const uint32_t u = uid_of[r];
+    ids_out[t] = (int32_t)u;
+    if (r == (uint32_t)t)
+        for (int j = 0; j < h; ++j) unique_rows[(uint64_t)u * h + j] = __ldg(rows + t * (uint64_t)h + j);
+}
+
+cudaError_t launch_dedup_rows(const int32_t *d_rows, uint64_t n, int h, unsigned long long *d_table, uint64_t table_entries,
+                              uint32_t *d_rep, uint32_t *d_uid_of, unsigned int *d_counter, int32_t *d_ids_out,
+                              int32_t *d_unique_rows, cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    if (n > 0xfffffff0ull) return cudaErrorInvalidConfiguration;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    dedup_rows_claim_kernel<<<blocks, 256, 0, stream>>>(d_rows, n, h, d_table, table_entries - 1, d_rep, d_uid_of, d_counter);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    dedup_rows_assign_kernel<<<blocks, 256, 0, stream>>>(d_rows, n, h, d_rep, d_uid_of, d_ids_out, d_unique_rows);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // counts >= min_kmers -> compact (colour, count) pairs (bigsi/graph/bigsi.py:241-242).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) threshold_kernel(const uint32_t *__restrict__ counts, uint64_t counts_stride,

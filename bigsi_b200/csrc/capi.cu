@@ -172,7 +172,7 @@ struct bigsi_b200_index {
     bool timing = false;
     int64_t opt_debug_flags = 0;
     int64_t opt_prehash = 1, opt_fuse_merge = 1, opt_merge_chunk_bytes = 0, opt_solo = 1, opt_pool_pct = -1, opt_zero_copy = 1, opt_cooperative = 1;
-    int64_t opt_inputs_ready = 0, opt_spin_timeout_ms = 10000, opt_defer = 1, opt_direct = 1;
+    int64_t opt_inputs_ready = 0, opt_spin_timeout_ms = 10000, opt_defer = 1, opt_direct = 1, opt_batch_reuse = 1;
     // streamed single-query launches (query.cuh:kStreamRing): ring-buffered scratch + the completion / abort words
     DevBuf d_pool;            // kStreamRing x [ready flags: grid x u64][ids: grid x pool_share x h x i32]
     uint64_t pool_slot_bytes = 0;
@@ -221,6 +221,7 @@ struct bigsi_b200_index {
     DevBuf d_seq, d_table;   // query front-end: sequence bytes, de-duplication table (+ counter, ticket, threshold)
     uint64_t table_clean_bytes = 0;  // leading bytes of d_table known to be zero
     DevBuf partial, d_kmers, d_rows, d_qoff, d_out, d_min, d_nhits, d_bloom, d_planted;
+    DevBuf d_reuse, d_reuse_rows;  // batch reuse: de-duplication workspace, the gathered AND vectors of the distinct k-mers
     PinnedBuf h_small;
     // timing
     std::vector<TimedLaunch> timed_free, timed_used;
@@ -231,6 +232,7 @@ struct bigsi_b200_index {
 
 namespace {
 
+constexpr uint64_t kReuseMinKmers = 16384;  // smaller batches are not worth the de-duplication pass and its host round trip
 constexpr uint64_t kPoolFlagEntries = 16384, kPoolFlagBytes = kPoolFlagEntries * 8;
 constexpr uint64_t kStreamStateBytes = 3 * 64 + (uint64_t)kStreamStates * sizeof(QState);
 // shared memory of a streamed gather CTA in COUNTS mode: the merge team's scratch lies behind the ring
@@ -353,8 +355,10 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
     if (ix->opt_kmers_per_stage > 0) {
         G = (uint32_t)ix->opt_kmers_per_stage;
     } else {
+        // (a ring slot costs the producer warp ~0.4 us whatever it holds: below ~16 KB per slot the slot rate, not HBM,
+        // bounds the gather -- measured with h = 1 rows of 6 KB: 2 per slot 3.6 TB/s, 4 per slot 6 TB/s)
         for (uint32_t g = 8; g > 1; g >>= 1)
-            if (g * kmer_bytes <= 16384) {
+            if (g * kmer_bytes <= 28672) {
                 G = g;
                 break;
             }
@@ -539,6 +543,73 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
     if (int rc = plan_query(ix, mode, n_queries, total_kmers, max_query_kmers, h, d_kmers != nullptr, k, p, grid,
                             hits != nullptr && hits->isolated))
         return rc;
+    // ---- shared row-gather reuse (batches): de-duplicate the batch's k-mers by row-id tuple; when at most half of them
+    // are distinct, gather the distinct tuples' AND vectors ONCE (lookup kernel -> scratch matrix A, one row per class)
+    // and let the queries count over A with h = 1.  Bytes moved: (h + 1) * U' + T rows instead of h * T.
+    uint64_t reuse_unique = 0;
+    const bool reuse_candidate = n_queries > 1 && total_kmers >= kReuseMinKmers && total_kmers < 0xfffffff0ull && grid > 0 &&
+                                 ix->opt_batch_reuse != 0 && !(hits && (hits->seq_mode || hits->total_dev));
+    if (reuse_candidate) {
+        if (int rc = flush_pending(ix)) return rc;
+        const uint64_t T = total_kmers;
+        cudaError_t e;
+        if (d_kmers) {  // the row ids are needed up front: hash kernel (the plan below never hashes in the kernel)
+            if (T * (uint64_t)h * 4 > ix->d_rows.cap) {
+                CK(cudaStreamSynchronize(stream));
+                if ((e = ix->d_rows.reserve(T * (uint64_t)h * 4)) != cudaSuccess) return fail_cuda(e, "row-id workspace");
+            }
+            CK(launch_hash_kmers(d_kmers, T, k, h, ix->num_rows, 1, static_cast<int32_t *>(ix->d_rows.p), stream));
+            ix->kernel_launches++;
+            d_rows = static_cast<const int32_t *>(ix->d_rows.p);
+            d_kmers = nullptr;
+        }
+        uint64_t entries = 1024;
+        while (entries < 2 * T) entries <<= 1;
+        // scratch: [table: entries x u64][counter: 256 B][rep: T x u32][uid_of: T x u32][ids: T x i32][unique rows: T x h x i32]
+        const uint64_t off_counter = entries * 8, off_rep = off_counter + 256, off_uid = off_rep + round_up(T * 4, 256),
+                       off_ids = off_uid + round_up(T * 4, 256), off_urows = off_ids + round_up(T * 4, 256),
+                       need = off_urows + round_up(T * (uint64_t)h * 4, 256);
+        if (need > ix->d_reuse.cap) {
+            CK(cudaStreamSynchronize(stream));
+            if ((e = ix->d_reuse.reserve(need)) != cudaSuccess) return fail_cuda(e, "batch de-duplication workspace");
+        }
+        uint8_t *rb = static_cast<uint8_t *>(ix->d_reuse.p);
+        CK(cudaMemsetAsync(rb, 0, off_counter + 256, stream));
+        CK(launch_dedup_rows(d_rows, T, h, reinterpret_cast<unsigned long long *>(rb), entries, reinterpret_cast<uint32_t *>(rb + off_rep),
+                             reinterpret_cast<uint32_t *>(rb + off_uid), reinterpret_cast<unsigned int *>(rb + off_counter),
+                             reinterpret_cast<int32_t *>(rb + off_ids), reinterpret_cast<int32_t *>(rb + off_urows), stream));
+        ix->kernel_launches += 2;
+        if ((e = ix->h_small.reserve(64)) != cudaSuccess) return fail_cuda(e, "pinned staging");
+        CK(cudaMemcpyAsync(ix->h_small.p, rb + off_counter, 4, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        const uint64_t U = *static_cast<const unsigned int *>(ix->h_small.p);
+        const uint64_t pitch_a = round_up(row_bytes, 128);
+        bool use = U > 0 && 2 * U <= T;
+        if (use && U * pitch_a > ix->d_reuse_rows.cap) {
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            if (U * pitch_a + (1ull << 30) > (uint64_t)free_b + ix->d_reuse_rows.cap) use = false;  // not worth evicting anything
+            else if ((e = ix->d_reuse_rows.reserve(U * pitch_a)) != cudaSuccess) {
+                (void)cudaGetLastError();
+                use = false;
+            }
+        }
+        int h_run = h;
+        if (use) {
+            CK(launch_lookup(ix->matrix, ix->pitch, (uint32_t)row_bytes, reinterpret_cast<const int32_t *>(rb + off_urows), U, h,
+                             static_cast<uint8_t *>(ix->d_reuse_rows.p), pitch_a, stream));
+            ix->kernel_launches++;
+            d_rows = reinterpret_cast<const int32_t *>(rb + off_ids);
+            h_run = 1;
+            reuse_unique = U;
+        }
+        // re-plan for row ids (no in-kernel hashing) and, with reuse, one "row" per k-mer
+        if (int rc = plan_query(ix, mode, n_queries, total_kmers, max_query_kmers, h_run, false, k, p, grid, false)) return rc;
+        if (use) {
+            p.matrix = static_cast<const uint8_t *>(ix->d_reuse_rows.p);
+            p.pitch = pitch_a;
+        }
+    }
     if (d_kmers && p.prehash) {
         p.kmers = reinterpret_cast<const uint8_t *>(d_kmers);
     } else if (d_kmers && total_kmers) {
@@ -776,6 +847,7 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
     s.last_n_slices = p.n_slices;
     s.last_fused = (p.fuse_merge ? 1u : 0u) | (p.prehash ? 2u : 0u) | (p.solo ? 4u : 0u) | (p.stream ? 8u : 0u);
     s.last_reduce_grid = (uint32_t)reduce_grid;
+    s.last_unique_kmers = reuse_unique;
     return 0;
 }
 
@@ -918,7 +990,7 @@ int bigsi_b200_index_destroy(bigsi_b200_index *ix)
     for (auto &b : ix->h_seq) b.release();
     ix->h_tsink.release();
     DevBuf *bufs[] = {&ix->d_seq_tables, &ix->stream_partial, &ix->d_stream, &ix->d_hits_ring, &ix->d_seq, &ix->d_table, &ix->d_pool, &ix->d_barrier, &ix->debug_ts, &ix->partial, &ix->d_kmers, &ix->d_rows, &ix->d_qoff, &ix->d_out, &ix->d_min,
-                      &ix->d_nhits, &ix->d_bloom, &ix->d_planted};
+                      &ix->d_nhits, &ix->d_bloom, &ix->d_planted, &ix->d_reuse, &ix->d_reuse_rows};
     for (DevBuf *b : bufs) b->release();
     ix->h_small.release();
     ix->h_status.release();
@@ -968,6 +1040,7 @@ int bigsi_b200_index_set_option(bigsi_b200_index *ix, const char *key, int64_t v
     else if (!strcmp(key, "zero_copy")) ix->opt_zero_copy = value;
     else if (!strcmp(key, "cooperative")) ix->opt_cooperative = value;
     else if (!strcmp(key, "inputs_ready")) ix->opt_inputs_ready = value;
+    else if (!strcmp(key, "batch_reuse")) ix->opt_batch_reuse = value;
     else if (!strcmp(key, "direct")) ix->opt_direct = value;  // 0: batches merge every query (no direct finish)
     else if (!strcmp(key, "defer")) ix->opt_defer = value;  // 0: every streamed query is flushed at once (diagnostics)
     else if (!strcmp(key, "spin_timeout_ms")) ix->opt_spin_timeout_ms = value < 1 ? 1 : value;

@@ -255,6 +255,11 @@ cudaError_t launch_hash_kmers(const char *d_kmers, uint64_t n, int k, int h, uin
                               int32_t *d_rows_out, cudaStream_t stream);
 cudaError_t launch_lookup(const uint8_t *matrix, uint64_t pitch, uint32_t row_bytes, const int32_t *d_rows,
                           uint64_t n_kmers, int h, uint8_t *d_out, uint64_t out_stride, cudaStream_t stream);
+// batch reuse: classes of equal row-id tuples (table: a power of two >= 2 n entries, zeroed; *d_counter zeroed, receives
+// the number of classes U'); d_ids_out[t] = class of k-mer t, d_unique_rows[u] = the row ids of class u
+cudaError_t launch_dedup_rows(const int32_t *d_rows, uint64_t n, int h, unsigned long long *d_table, uint64_t table_entries,
+                              uint32_t *d_rep, uint32_t *d_uid_of, unsigned int *d_counter, int32_t *d_ids_out,
+                              int32_t *d_unique_rows, cudaStream_t stream);
 cudaError_t launch_threshold(const uint32_t *d_counts, uint64_t counts_stride, uint64_t n_queries,
                              uint64_t num_cols, const uint32_t *d_min_kmers, int32_t *d_cols_out,
                              uint32_t *d_counts_out, uint64_t cap, unsigned long long *d_n_out,

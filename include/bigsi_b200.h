@@ -68,6 +68,8 @@ typedef struct {
     uint32_t last_fused;             /* bit 0: merge ran inside the fused kernel, bit 1: k-mers hashed in it,
                                         bit 3: streamed launch (gather kernel; stage 2 deferred)                */
     uint32_t last_reduce_grid;       /* CTAs of the flush kernel of a streamed launch (else 0)                */
+    uint64_t last_unique_kmers;      /* batches with shared row-gather reuse: classes of equal row-id tuples whose rows
+                                        were gathered once (0: the launch gathered every k-mer's rows itself)   */
 } bigsi_b200_info;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -89,7 +91,9 @@ int bigsi_b200_index_get_info(const bigsi_b200_index *index, bigsi_b200_info *in
 /* Tuning / instrumentation knobs (value 0 = automatic): "tile_bytes", "grid", "kmers_per_stage",
  * "n_stages", "ctas_per_sm", "merge_chunk_bytes", "debug_flags"; "prehash" / "fuse_merge" / "solo" /
  * "zero_copy" (default 1; 0 forces the separate hash / merge kernels, the generic single-query
- * path, the staged host copies); "pool_pct" (0..100: share of a single query's k-mers that the CTAs claim
+ * path, the staged host copies); "batch_reuse" (default 1: a batch of >= 2 queries and >= 16 384 k-mers is
+ * de-duplicated by row-id tuple first; when at most half of its k-mers are distinct, the distinct ones' AND vectors
+ * are gathered ONCE into scratch and the queries count over those -- shared row-gather reuse; 0 = never); "pool_pct" (0..100: share of a single query's k-mers that the CTAs claim
  * dynamically; default / > 100 = automatic: 12 for an isolated query of the synchronous host calls, 0 for streamed
  * back-to-back queries); "cooperative" (default 1: a generic-path kernel that merges behind its own grid barrier is
  * launched with the cooperative attribute, so the driver verifies that all its CTAs are co-resident; 0 = plain

@@ -137,6 +137,58 @@ def test_ragged_batch_with_empty_queries(B):
     ix.close()
 
 
+@pytest.mark.parametrize("h", [3, 1, 5])
+def test_batch_shared_row_gather_reuse(B, h):
+    """Batches whose queries share k-mers (BASELINE configs[4] "shared row-gather reuse"): the batch is de-duplicated by
+    row-id tuple, the distinct tuples' AND vectors are gathered once and the queries count over those.  Counts, presence
+    (AND mode) and thresholded hits against the oracle, identical to the path without reuse, through the k-mer and the
+    row-id entry points; a batch of all-distinct k-mers does not take the reuse path."""
+    rng = np.random.default_rng(211 + h)
+    m, N, k = 7001, 1201, 31
+    ix, packed = _random_index(B, rng, m, N, density=0.85)
+    oix = O.OracleIndex(k, m, h, N, rows=packed)
+    pool = _rand_kmers(rng, 2500, k)
+    pool[1] = np.frombuffer(B.reverse_comp(bytes(pool[0]).decode()).encode(), dtype=np.uint8)  # same canonical k-mer, other string
+    lens = [int(x) for x in rng.integers(300, 700, size=40)]
+    lens[3] = 0
+    qoff = np.concatenate([[0], np.cumsum(lens)])
+    pick = np.concatenate([rng.choice(2500, size=n, replace=False) for n in lens if n] + [np.zeros(0, dtype=np.int64)])
+    arr = np.ascontiguousarray(pool[pick.astype(np.int64)])
+    assert arr.shape[0] == qoff[-1] >= 16384
+    kmers = _kmer_strs(arr)
+    mins = np.array([int(np.ceil(n * 0.6)) for n in lens], dtype=np.uint32)
+    got = {}
+    for reuse in (1, 0):
+        ix.set_option("batch_reuse", reuse)
+        counts = ix.search_kmers(arr, k, h, q_offsets=qoff)
+        uniq = ix.info()["last_unique_kmers"]
+        assert (0 < uniq <= 2500) if reuse else uniq == 0, uniq
+        pres = ix.search_kmers(arr, k, h, q_offsets=qoff, mode=1)
+        hits = ix.search_kmers_hits(arr, k, h, mins, q_offsets=qoff, cap=N)
+        rows = O.hash_kmers(arr, k, h, m)
+        counts_r = ix.search_rows(rows, h, q_offsets=qoff, mode=0)
+        got[reuse] = (counts, pres)
+        assert np.array_equal(counts, counts_r)
+        for q, n in enumerate(lens):
+            part = kmers[qoff[q]: qoff[q + 1]]
+            cnt = oix.counts(part) if n else np.zeros(N, dtype=np.int64)
+            assert np.array_equal(counts[q].astype(np.int64), cnt.astype(np.int64)), (reuse, q)
+            if n:
+                assert np.array_equal(pres[q], oix.presence(part)), (reuse, q)
+            exp = np.nonzero(cnt >= mins[q])[0]
+            cols, vals, nh = hits[q]
+            assert nh == len(exp) and np.array_equal(cols, exp) and np.array_equal(vals.astype(np.int64), cnt[exp]), (reuse, q)
+    assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1])
+    ix.set_option("batch_reuse", 1)
+    distinct = _rand_kmers(rng, 17_000, k)
+    ix.search_kmers(distinct, k, h, q_offsets=[0, 9000, 17_000])
+    if h >= 3:  # nothing to share: the ordinary batch path (with h = 1 the 7 001 rows ARE shared between 17 000 k-mers)
+        assert ix.info()["last_unique_kmers"] == 0
+    else:
+        assert 0 < ix.info()["last_unique_kmers"] <= m
+    ix.close()
+
+
 @pytest.mark.parametrize("opts", [{}, {"grid": 7}, {"tile_bytes": 64, "grid": 5}, {"grid": 1}, {"fuse_merge": 0, "grid": 9}])
 def test_batch_whole_query_segments_finished_directly(B, opts):
     """Batches: a query that lies inside one slice is finished by the CTA that counted it (no partial planes, no merge);

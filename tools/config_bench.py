@@ -60,6 +60,9 @@ def run(name, batches, qoff, mins, nq):
                       "lookups_per_s": U / (ms * 1e-3), "algorithmic_GBps": gbs, "frac_of_measured_copy_peak": gbs / peak,
                       "kernels_per_launch": 1 if info["last_fused"] & 1 else 2, "grid": info["last_grid"],
                       "n_slices": info["last_n_slices"], "stages": info["last_n_stages"],
+                      "distinct_row_tuples_gathered_once": info["last_unique_kmers"],
+                      "dram_bytes_moved_estimate_GB": (((H + 1) * info["last_unique_kmers"] + U) * row_bytes / 1e9
+                                                       if info["last_unique_kmers"] else U * H * row_bytes / 1e9),
                       "first_query_hits": int(out[0].item())}))
 
 
@@ -82,6 +85,9 @@ qoff = list(range(0, Q * L + 1, L))
 rng = np.random.default_rng(5)
 indep = [torch.from_numpy(acgt[rng.integers(0, 4, size=(Q * L, K))]).to(dev) for _ in range(3)]
 run("config5: 1 000 x 1 000 k-mers, independent queries", indep, qoff, [L] * Q, Q)
+ix.set_option("batch_reuse", 0)
+run("config5: 1 000 x 1 000 k-mers, independent queries, option batch_reuse = 0 (no de-duplication pass)", indep, qoff, [L] * Q, Q)
+ix.set_option("batch_reuse", 1)
 del indep
 shared = []
 for i in range(3):
@@ -90,5 +96,8 @@ for i in range(3):
     starts = rng.integers(0, 100_000 - L, size=Q)
     shared.append(torch.from_numpy(np.ascontiguousarray(np.concatenate([win[s : s + L] for s in starts]))).to(dev))
 run("config5: 1 000 x 1 000 k-mers, windows of one 100 kbp sequence (rows shared between queries)", shared, qoff,
+    [math.ceil(L * 0.4)] * Q, Q)
+ix.set_option("batch_reuse", 0)
+run("config5: 1 000 x 1 000 k-mers, windows of one 100 kbp sequence, option batch_reuse = 0", shared, qoff,
     [math.ceil(L * 0.4)] * Q, Q)
 ix.close()
