@@ -543,6 +543,10 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
     if (int rc = plan_query(ix, mode, n_queries, total_kmers, max_query_kmers, h, d_kmers != nullptr, k, p, grid,
                             hits != nullptr && hits->isolated))
         return rc;
+    // a sequence (front-end inside the gather kernel) or a device-side k-mer count can only be followed by the streamed
+    // plan: say so BEFORE anything is launched (the "k-mers" of a sequence search are not n x k bytes)
+    if (hits && hits->seq_mode && !(p.stream && hits->n_sinks && k <= 32)) return 1;
+    if (hits && hits->total_dev && !(p.stream && hits->n_sinks)) return 1;
     // ---- shared row-gather reuse (batches): de-duplicate the batch's k-mers by row-id tuple; when at most half of them
     // are distinct, gather the distinct tuples' AND vectors ONCE (lookup kernel -> scratch matrix A, one row per class)
     // and let the queries count over A with h = 1.  Bytes moved: (h + 1) * U' + T rows instead of h * T.

@@ -744,12 +744,21 @@ gather_solo(const __grid_constant__ QueryParams P, const __grid_constant__ Query
     }
     if (threadIdx.x == 32) {
         // entry gate: the buffers of this query's ring slot were last used by query seq - kStreamRing, whose
-        // stage 2 must have finished (it also cleared our state block); a handle that has aborted stays dead
+        // stage 2 must have finished (it also cleared our state block); a handle that has aborted stays dead.
+        // Both words are requested before either is looked at: one L2 round trip, not two.
+        const bool gated = P.stream_seq > (unsigned long long)kStreamRing;
+        const unsigned long long done = gated ? ld_acquire_gpu_u64(P.stream_done) : 0ull;
         bool ok = ld_volatile_u64(P.abort_word) == 0ull;
-        if (ok && P.stream_seq > (unsigned long long)kStreamRing)
+        if (ok && gated && done + kStreamRing < P.stream_seq)
             ok = bounded_wait(P.abort_word, P.host_abort, P.spin_timeout_ns, kAbortGate, P.stream_seq,
                               [&]() { return ld_acquire_gpu_u64(P.stream_done) + kStreamRing >= P.stream_seq; });
         *s_gate = ok ? 1 : 0;
+    } else if (threadIdx.x >= 64 && threadIdx.x < 96 && !P.stream_wait_inputs && !P.seq_mode && P.ll.in == nullptr) {
+        // this CTA's k-mer bytes on their way into L2 while the gate is read (they are host- or copy-written: in HBM)
+        const uint32_t cnt = solo_range_cnt(P, blockIdx.x, P.total_kmers);
+        const uint8_t *b0 = P.kmers + (uint64_t)blockIdx.x * P.items_per_slice * P.k;
+        for (uint32_t off = (threadIdx.x - 64) * 128u; off < cnt * P.k; off += 32u * 128u)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + off));
     }
     __syncthreads();
     if (!*s_gate) return;
@@ -940,12 +949,13 @@ static cudaError_t launch_one(const QueryParams &p, int grid, cudaStream_t strea
         // the small counter and the merge team; the others leave stage 2 to the flush kernel.
         const dim3 g(grid), b(query_block_threads(p));
         const QueryParams &pv = prev ? *prev : p;
+        constexpr int SHC = HC == 3 ? 3 : 0;  // (the streamed kernels exist for h = 3 and for any h)
         if (MODE == kModeCounts && p.planes_per_slot > 8)
-            return launch_ex(gather_solo<MODE, HC, kSegPlanes, false>, g, b, query_smem_bytes(p), stream, /*pdl=*/true,
+            return launch_ex(gather_solo<MODE, SHC, kSegPlanes, false>, g, b, query_smem_bytes(p), stream, /*pdl=*/true,
                              /*cooperative=*/false, p, pv);
         if (MODE == kModeCounts)
-            return launch_ex(gather_solo<MODE, HC, 8, true>, g, b, query_smem_bytes(p), stream, true, false, p, pv);
-        return launch_ex(gather_solo<MODE, HC, 8, false>, g, b, query_smem_bytes(p), stream, true, false, p, pv);
+            return launch_ex(gather_solo<MODE, SHC, 8, true>, g, b, query_smem_bytes(p), stream, true, false, p, pv);
+        return launch_ex(gather_solo<MODE, SHC, 8, false>, g, b, query_smem_bytes(p), stream, true, false, p, pv);
     }
     return launch_ex(fused_query<MODE, HC>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream,
                      /*pdl=*/true, /*cooperative=*/p.fuse_merge != 0 && !p.plain_launch, p);
@@ -955,9 +965,14 @@ cudaError_t launch_query(const QueryParams &p, int mode, int grid, cudaStream_t 
 {
     if (p.merge_prev && !(prev && query_has_merge_team(p, mode))) return cudaErrorInvalidValue;
     if ((p.merge_team != 0) != (p.solo && query_has_merge_team(p, mode))) return cudaErrorInvalidValue;
+    // h = 3 (the reference's default) and h = 1 (batches counting over once-gathered AND vectors) are compiled in
     if (mode == kModeCounts)
-        return p.h == 3 ? launch_one<kModeCounts, 3>(p, grid, stream, prev) : launch_one<kModeCounts, 0>(p, grid, stream, prev);
-    return p.h == 3 ? launch_one<kModeAnd, 3>(p, grid, stream, prev) : launch_one<kModeAnd, 0>(p, grid, stream, prev);
+        return p.h == 3   ? launch_one<kModeCounts, 3>(p, grid, stream, prev)
+               : p.h == 1 ? launch_one<kModeCounts, 1>(p, grid, stream, prev)
+                          : launch_one<kModeCounts, 0>(p, grid, stream, prev);
+    return p.h == 3   ? launch_one<kModeAnd, 3>(p, grid, stream, prev)
+           : p.h == 1 ? launch_one<kModeAnd, 1>(p, grid, stream, prev)
+                      : launch_one<kModeAnd, 0>(p, grid, stream, prev);
 }
 
 cudaError_t query_kernels_init()
@@ -972,6 +987,8 @@ cudaError_t query_kernels_init()
     BIGSI_SET_SMEM((fused_query<kModeCounts, 0>))
     BIGSI_SET_SMEM((fused_query<kModeAnd, 3>))
     BIGSI_SET_SMEM((fused_query<kModeAnd, 0>))
+    BIGSI_SET_SMEM((fused_query<kModeCounts, 1>))
+    BIGSI_SET_SMEM((fused_query<kModeAnd, 1>))
     BIGSI_SET_SMEM((gather_solo<kModeCounts, 3, 8, true>))
     BIGSI_SET_SMEM((gather_solo<kModeCounts, 3, kSegPlanes, false>))
     BIGSI_SET_SMEM((gather_solo<kModeCounts, 0, 8, true>))
