@@ -172,7 +172,7 @@ struct bigsi_b200_index {
     bool timing = false;
     int64_t opt_debug_flags = 0;
     int64_t opt_prehash = 1, opt_fuse_merge = 1, opt_merge_chunk_bytes = 0, opt_solo = 1, opt_pool_pct = -1, opt_zero_copy = 1, opt_cooperative = 1;
-    int64_t opt_inputs_ready = 0, opt_spin_timeout_ms = 10000, opt_defer = 1, opt_direct = 1, opt_batch_reuse = 1;
+    int64_t opt_inputs_ready = 0, opt_spin_timeout_ms = 10000, opt_defer = 1, opt_direct = 1, opt_batch_reuse = 1, opt_self_merge = 0;
     // streamed single-query launches (query.cuh:kStreamRing): ring-buffered scratch + the completion / abort words
     DevBuf d_pool;            // kStreamRing x [ready flags: grid x u64][ids: grid x pool_share x h x i32]
     uint64_t pool_slot_bytes = 0;
@@ -406,7 +406,7 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
     } else if (p.stream) {
         // back-to-back queries: the scratch of a gather CTA's merge team; an isolated query is always merged by the
         // flush kernel, with more scratch (fewer, larger slot batches)
-        plan_merge(p, mode, isolated ? kReduceFatSmemBytes : kReduceSmemBytes, (uint64_t)ix->sm_count,
+        plan_merge(p, mode, (isolated && !p.merge_team) ? kReduceFatSmemBytes : kReduceSmemBytes, (uint64_t)ix->sm_count,
                    (uint32_t)ix->opt_merge_chunk_bytes);
     } else {
         plan_merge(p, mode, kMergeKernelSmem, (uint64_t)ix->sm_count * 3, (uint32_t)ix->opt_merge_chunk_bytes);
@@ -466,7 +466,7 @@ int fail_aborted(unsigned long long v)
                                  "a shard waited for the query bytes of rank 0 (was rank 0's search launched?)",
                                  "a shard waited for another shard's hit list (was the search launched on every rank?)",
                                  "a reduce kernel waited for its predecessor (completion chain)",
-                                 "a gather kernel waited for its reduce kernel to become resident (exit gate)"};
+                                 "a merge team waited for the gather CTAs of its own query (self-merging launch)"};
     const unsigned code = (unsigned)(v & 0xff);
     return fail(BIGSI_B200_ERR_TIMEOUT, "device-side wait timed out in query %llu: %s; the handle is unusable (destroy it)",
                 (unsigned long long)(v >> 8), what[code < 7 ? code : 0]);
@@ -745,6 +745,14 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
         if (pq.have && !take_prev)
             if (int rc = flush_pending(ix)) return rc;
         p.merge_prev = take_prev ? 1u : 0u;
+        const bool defer = hits && hits->deferred && mode == BIGSI_B200_MODE_COUNTS && !ix->timing && ix->opt_defer != 0 &&
+                           p.merge_smem <= (uint32_t)kReduceSmemBytes;
+        // option "self_merge": a query nobody follows (synchronous calls) is merged by its OWN kernel's team once every
+        // gather CTA has flushed -- needs all CTAs co-resident, so the launch is cooperative (the driver checks).  Off by
+        // default: measured no faster than the flush kernel, which is already queued behind the gather kernel (PDL)
+        bool self_merge = !defer && p.merge_team != 0 && !ix->timing && ix->opt_self_merge != 0 && grid <= ix->sm_count &&
+                          p.merge_smem <= (uint32_t)kReduceSmemBytes;
+        p.self_merge = self_merge ? 1u : 0u;
 
         TimedLaunch tl{};
         if (ix->timing) {
@@ -759,23 +767,30 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
             CK(cudaEventRecord(tl.e0, stream));
         }
         cudaError_t e = launch_query(p, mode, grid, stream, take_prev ? &pq.p : nullptr);
+        if (e != cudaSuccess && self_merge) {  // the cooperative launch was refused (SMs held by something else): two kernels
+            (void)cudaGetLastError();
+            self_merge = false;
+            p.self_merge = 0;
+            e = launch_query(p, mode, grid, stream, take_prev ? &pq.p : nullptr);
+        }
         if (e != cudaSuccess) return fail_cuda(e, "gather_solo launch");  // (a pending query stays pending)
         ix->kernel_launches++;
         if (ix->timing) CK(cudaEventRecord(tl.e1, stream));
         // from here on the query counts as launched: the completion chain expects its stage 2
         ix->stream_seq = seq;
         ix->pool_epoch = p.pool_epoch;
-        pq.have = true;
-        pq.p = p;
-        if (pq.p.debug_ts) pq.p.debug_ts += (uint64_t)grid * kDebugStamps;
-        pq.mode = mode;
-        pq.reduce_grid = reduce_grid;
-        pq.stream = stream;
-        pq.ticket = hits ? hits->ticket : 0;
-        const bool defer = hits && hits->deferred && mode == BIGSI_B200_MODE_COUNTS && !ix->timing && ix->opt_defer != 0 &&
-                           p.merge_smem <= (uint32_t)kReduceSmemBytes;
-        if (!defer)
-            if (int rc = flush_pending(ix)) return rc;
+        if (take_prev) pq.have = false;  // (merged by this launch's team)
+        if (!self_merge) {
+            pq.have = true;
+            pq.p = p;
+            if (pq.p.debug_ts) pq.p.debug_ts += (uint64_t)grid * kDebugStamps;
+            pq.mode = mode;
+            pq.reduce_grid = reduce_grid;
+            pq.stream = stream;
+            pq.ticket = hits ? hits->ticket : 0;
+            if (!defer)
+                if (int rc = flush_pending(ix)) return rc;
+        }
         if (ix->timing) {
             CK(cudaEventRecord(tl.e2, stream));
             ix->timed_used.push_back(tl);
@@ -1044,6 +1059,8 @@ int bigsi_b200_index_set_option(bigsi_b200_index *ix, const char *key, int64_t v
     else if (!strcmp(key, "zero_copy")) ix->opt_zero_copy = value;
     else if (!strcmp(key, "cooperative")) ix->opt_cooperative = value;
     else if (!strcmp(key, "inputs_ready")) ix->opt_inputs_ready = value;
+    else if (!strcmp(key, "self_merge")) ix->opt_self_merge = value;  // 1: a synchronous single query is merged by its own
+                                                                      // kernel's team (cooperative launch) instead of the flush kernel
     else if (!strcmp(key, "batch_reuse")) ix->opt_batch_reuse = value;
     else if (!strcmp(key, "direct")) ix->opt_direct = value;  // 0: batches merge every query (no direct finish)
     else if (!strcmp(key, "defer")) ix->opt_defer = value;  // 0: every streamed query is flushed at once (diagnostics)

@@ -177,6 +177,12 @@ __device__ __forceinline__ bool bounded_wait(unsigned long long *abort_word, uns
         }
     }
 }
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p)
 {
     unsigned long long v;

@@ -49,7 +49,8 @@ struct QState {
     unsigned int reduce_arrivals;   // reduce-kernel CTAs that have finished their merge items
     unsigned long long n_unique;    // sequence front-end: unique windows found by the gather kernel's CTAs
     unsigned long long wait_ns;     // diagnostics: time the reduce kernel's last CTA waited for the other shards
-    unsigned int pad0[2];
+    unsigned int gather_arrivals;   // self-merging launches: gather CTAs of this query that have flushed their planes
+    unsigned int pad0;
     unsigned long long pad[4];
 };
 static_assert(sizeof(QState) == 64, "QState is one 64-byte block");
@@ -165,6 +166,8 @@ struct QueryParams {
     uint32_t stream;
     uint32_t merge_team;                 // threads of the gather CTA's merge team (kMergeTeamThreads, or 0: a variant without)
     uint32_t merge_prev;                 // 1: the kernel's second argument describes the previous query, to be merged by the team
+    uint32_t self_merge;                 // 1 (isolated query, COOPERATIVE launch: all CTAs co-resident): the team merges THIS
+                                         // query once every gather CTA of the grid has flushed (arrival counter) -- no flush kernel
     uint32_t stream_wait_inputs;         // 1: the k-mers may be produced by the preceding kernel of the stream: wait for it
     unsigned long long stream_seq;       // number of this query among the handle's streamed launches (1-based)
     unsigned long long *stream_done;     // device word: every streamed query <= *stream_done is completely reduced

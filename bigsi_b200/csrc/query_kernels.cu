@@ -773,14 +773,29 @@ gather_solo(const __grid_constant__ QueryParams P, const __grid_constant__ Query
             if (cnt) push_query_slice(P, (uint64_t)blockIdx.x * P.items_per_slice, cnt, threadIdx.x - n_gather, (uint32_t)kMergeTeamThreads);
             if (threadIdx.x == n_gather) BIGSI_TS(6);
         }
-        if (!P.merge_prev) return;
-        grid_dependency_wait();
         const WarpGroupTeam<kBarMergeTeam> T{n_gather, (uint32_t)kMergeTeamThreads};
-        if (T.tid() == 0 && PV.debug_ts) PV.debug_ts[(size_t)blockIdx.x * kDebugStamps + 8] = debug_gtime();
         uint8_t *team_smem = ring + (size_t)P.n_stages * P.kmers_per_stage * P.h * P.tile_bytes;
-        reduce_query<kModeCounts>(PV, team_smem, reinterpret_cast<uint64_t *>(smem + kTeamBarOffset),
-                                  reinterpret_cast<volatile int *>(smem + kTeamFlagOffset), T, blockIdx.x, gridDim.x);
-        if (threadIdx.x == n_gather) BIGSI_TS(7);
+        uint64_t *team_bar = reinterpret_cast<uint64_t *>(smem + kTeamBarOffset);
+        volatile int *team_flag = reinterpret_cast<volatile int *>(smem + kTeamFlagOffset);
+        if (P.merge_prev) {
+            grid_dependency_wait();
+            if (T.tid() == 0 && PV.debug_ts) PV.debug_ts[(size_t)blockIdx.x * kDebugStamps + 8] = debug_gtime();
+            reduce_query<kModeCounts>(PV, team_smem, team_bar, team_flag, T, blockIdx.x, gridDim.x);
+            if (threadIdx.x == n_gather) BIGSI_TS(7);
+        }
+        if (P.self_merge) {
+            // isolated query, cooperative launch (every CTA of the grid is resident): stage 2 of THIS query as soon as all
+            // gather CTAs have flushed their planes -- no flush kernel, no second launch on the critical path
+            if (T.tid() == 0)
+                *team_flag = bounded_wait(P.abort_word, P.host_abort, P.spin_timeout_ns, kAbortExit, P.stream_seq,
+                                          [&]() { return ld_acquire_gpu_u32(&P.qstate->gather_arrivals) >= gridDim.x; })
+                                 ? 1 : 0;
+            T.sync();
+            if (!*team_flag) return;
+            __threadfence();
+            T.sync();
+            reduce_query<kModeCounts>(P, team_smem, team_bar, team_flag, T, blockIdx.x, gridDim.x);
+        }
         return;
     }
 
@@ -840,6 +855,14 @@ gather_solo(const __grid_constant__ QueryParams P, const __grid_constant__ Query
         solo_producer<!TEAM>(P, sg, smem, ring, ids, scratch, full, empty);
     else
         solo_consumer<MODE, HC, NP>(P, sg, smem, ring, ids, scratch, full, empty);
+    if (TEAM && P.self_merge) {
+        // every plane store of this CTA before its arrival: barrier over the gather threads, then one release
+        named_bar_sync<kBarGather>(n_gather);
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&P.qstate->gather_arrivals, 1u);
+        }
+    }
 }
 
 // grid-wide barrier over a monotonic arrival counter (all CTAs of the launch are co-resident: the generic kernel
@@ -954,7 +977,7 @@ static cudaError_t launch_one(const QueryParams &p, int grid, cudaStream_t strea
             return launch_ex(gather_solo<MODE, SHC, kSegPlanes, false>, g, b, query_smem_bytes(p), stream, /*pdl=*/true,
                              /*cooperative=*/false, p, pv);
         if (MODE == kModeCounts)
-            return launch_ex(gather_solo<MODE, SHC, 8, true>, g, b, query_smem_bytes(p), stream, true, false, p, pv);
+            return launch_ex(gather_solo<MODE, SHC, 8, true>, g, b, query_smem_bytes(p), stream, true, /*cooperative=*/p.self_merge != 0, p, pv);
         return launch_ex(gather_solo<MODE, SHC, 8, false>, g, b, query_smem_bytes(p), stream, true, false, p, pv);
     }
     return launch_ex(fused_query<MODE, HC>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream,

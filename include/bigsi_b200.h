@@ -93,7 +93,10 @@ int bigsi_b200_index_get_info(const bigsi_b200_index *index, bigsi_b200_info *in
  * "zero_copy" (default 1; 0 forces the separate hash / merge kernels, the generic single-query
  * path, the staged host copies); "batch_reuse" (default 1: a batch of >= 2 queries and >= 16 384 k-mers is
  * de-duplicated by row-id tuple first; when at most half of its k-mers are distinct, the distinct ones' AND vectors
- * are gathered ONCE into scratch and the queries count over those -- shared row-gather reuse; 0 = never); "pool_pct" (0..100: share of a single query's k-mers that the CTAs claim
+ * are gathered ONCE into scratch and the queries count over those -- shared row-gather reuse; 0 = never);
+ * "direct" (default 1: batch queries that lie inside one slice are finished by the CTA that counted them; 0 = every
+ * query goes through the merge); "defer" (default 1; 0 = deferred entry points flush at once); "self_merge" (default 0;
+ * 1 = a synchronous single query is merged by its own kernel's team, cooperative launch, instead of the flush kernel); "pool_pct" (0..100: share of a single query's k-mers that the CTAs claim
  * dynamically; default / > 100 = automatic: 12 for an isolated query of the synchronous host calls, 0 for streamed
  * back-to-back queries); "cooperative" (default 1: a generic-path kernel that merges behind its own grid barrier is
  * launched with the cooperative attribute, so the driver verifies that all its CTAs are co-resident; 0 = plain

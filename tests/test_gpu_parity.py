@@ -619,6 +619,7 @@ def test_single_query_zero_copy_path(B, pinned):
 @pytest.mark.parametrize("opts", [
     {"pool_pct": 0}, {"pool_pct": 50}, {"pool_pct": 100}, {"solo": 0}, {"n_stages": 2}, {"grid": 3},
     {"merge_chunk_bytes": 16}, {"merge_chunk_bytes": 1024}, {"kmers_per_stage": 4, "pool_pct": 30},
+    {"self_merge": 1}, {"self_merge": 1, "pool_pct": 0, "n_stages": 3}, {"defer": 0},
 ])
 def test_solo_path_geometries(B, opts):
     """The single-query in-kernel path (producer-warp hashing, pooled tail k-mers, chunk-major merge)
