@@ -137,11 +137,11 @@ struct TimedLaunch {
 // Column-sharded search without per-query collectives: every rank owns one device block
 //   [kExInboxes low-latency inboxes][result blocks: kExGenerations generations x world x block]
 // that its peers map (CUDA IPC across processes, plain peer access inside one process).  Rank 0's gather
-// kernel pushes the query into the peers' inboxes (LL lines); every rank's reduce kernel publishes its hit
+// kernel pushes the query into the peers' inboxes (LL lines); every rank's stage 2 (merge team / flush) publishes its hit
 // list into slot `rank` of every rank's result blocks and waits (bounded) for the others' slots of the same
 // query while the next query's gather kernel already runs.  Query s uses inbox s % kExInboxes and result
 // generation s % kExGenerations.  Reuse is safe because of the streamed path's entry gate: the gather kernel of
-// query s starts only after THIS rank's reduce kernel of query s - kStreamRing has seen every shard's block of
+// query s starts only after THIS rank's stage 2 of query s - kStreamRing has seen every shard's block of
 // that query, i.e. after every shard has finished reading the inbox of s - kStreamRing and has launched past
 // its consumers of generations <= s - kExGenerations.
 struct Exchange {
@@ -337,9 +337,9 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
         }
     }
 
-    // solo = STREAMED path: one query, hashed in the kernel, one slice per CTA; the merge runs as a separate
-    // reduce kernel that overlaps the next query's gather (no grid barrier).  Its shared memory leaves room for
-    // a reduce CTA on the same SM; a share of every CTA's k-mers goes to a pool that is drained dynamically.
+    // solo = STREAMED path: one query, hashed in the kernel, one slice per CTA; stage 2 (merge, threshold, publication)
+    // is left to the merge team of the next streamed launch or to the flush kernel (no grid barrier).  In COUNTS mode
+    // the team's scratch lies behind the ring; an isolated query pools a share of every CTA's k-mers (tail balance).
     p.solo = p.stream = 0;
     p.pool_share = 0;
     p.solo_max_kmers = 0xffffffffu;
@@ -461,11 +461,11 @@ unsigned long long abort_state(const bigsi_b200_index *ix)
 }
 int fail_aborted(unsigned long long v)
 {
-    static const char *what[] = {"?", "a query waited for the reduce kernel of an earlier query (entry gate)",
+    static const char *what[] = {"?", "a query waited for stage 2 of an earlier query (entry gate)",
                                  "a CTA waited for another CTA's pooled row ids",
                                  "a shard waited for the query bytes of rank 0 (was rank 0's search launched?)",
                                  "a shard waited for another shard's hit list (was the search launched on every rank?)",
-                                 "a reduce kernel waited for its predecessor (completion chain)",
+                                 "stage 2 of a query waited for its predecessor's (completion chain)",
                                  "a merge team waited for the gather CTAs of its own query (self-merging launch)"};
     const unsigned code = (unsigned)(v & 0xff);
     return fail(BIGSI_B200_ERR_TIMEOUT, "device-side wait timed out in query %llu: %s; the handle is unusable (destroy it)",
@@ -689,7 +689,7 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
         if (grid == 0) CK(cudaMemsetAsync(hits->n, 0, n_queries * sizeof(unsigned long long), stream));
     }
     if (p.stream) {
-        // ---- streamed launch: gather kernel + reduce kernel, ring-buffered scratch ------------------------------
+        // ---- streamed launch: gather kernel (+ merge team / flush kernel), ring-buffered scratch ------------------
         const uint64_t seq = ix->stream_seq + 1;
         const uint64_t slot = seq % kStreamRing;
         if (int rc = reserve_stream_scratch(ix, p, grid, stream)) return rc;

@@ -42,7 +42,7 @@ constexpr int kReduceFatSmemBytes = 64 * 1024;   // isolated queries: the flush 
 
 enum { kModeCounts = 0, kModeAnd = 1 };
 
-// Per-query state block of a streamed launch (64 bytes).  All zero when its query starts: the reduce kernel of
+// Per-query state block of a streamed launch (64 bytes).  All zero when its query starts: stage 2 of
 // query s clears the block of query s + kStreamRing before it advances the completion word.
 struct QState {
     unsigned int pool_claims;       // claim counter of the k-mer pool (gather kernel)
@@ -161,7 +161,7 @@ struct QueryParams {
     uint32_t host_block_words;
     const unsigned long long *gather_blocks[kMaxSinks];
     // streamed launch (solo geometry, fuse_merge == 0): no grid barrier and no wait for the preceding kernel.  The
-    // gather kernel flushes its planes and exits; reduce_kernel (merge_kernels.cu) merges, thresholds and publishes
+    // gather kernel flushes its planes and exits; stage 2 (merge team of the next launch / reduce_kernel) merges, thresholds and publishes
     // while the NEXT query's gather kernel already runs on the same SMs.
     uint32_t stream;
     uint32_t merge_team;                 // threads of the gather CTA's merge team (kMergeTeamThreads, or 0: a variant without)

@@ -58,8 +58,8 @@ class DeviceShard:
         self.device = torch.device("cuda", info["device"])
         self.cap = cap
         self._counts = None
-        # single-query searches are "streamed" (include/bigsi_b200.h): the gather kernel of the next query overlaps
-        # the reduce kernel of this one, so the output buffers of consecutive calls must differ -- a ring of 8
+        # single-query searches are "streamed" (include/bigsi_b200.h): stage 2 of a query runs while the next query's rows
+        # stream, so the output buffers of consecutive calls must differ -- a ring of 8
         self._hit_ring = {}
         self._hit_turn = 0
 
@@ -162,7 +162,7 @@ class _DevArray:
 class FusedExchange:
     """The two exchanges of a column-sharded single-query search done by the query kernels themselves
     (include/bigsi_b200.h "column-sharded search ... WITHOUT per-query collectives"): rank 0's gather kernel
-    pushes the k-mer bytes into the peers' inboxes over NVLink, every rank's reduce kernel publishes its hits
+    pushes the k-mer bytes into the peers' inboxes over NVLink, every rank's stage 2 (merge team / flush kernel) publishes its hits
     into every rank's result blocks and waits for the others while the next query's gather kernel already
     runs.  No NCCL call per query; torch.distributed is only used once, to exchange the CUDA IPC handles."""
 
@@ -250,7 +250,7 @@ class FusedExchange:
         return arr[:, 2: 4 + 2 * self.spec]
 
     def wait_ns(self):
-        """(ns this rank's reduce kernels waited for the other shards since the last call, queries launched)."""
+        """(ns this rank's stage-2 code waited for the other shards since the last call, queries launched)."""
         ct = self._ct
         w, q = ct.c_uint64(0), ct.c_uint64(0)
         self._lib.check(self._lib.lib().bigsi_b200_exchange_wait_ns(self.shard.index.handle, ct.byref(w), ct.byref(q)))

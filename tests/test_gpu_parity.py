@@ -602,7 +602,7 @@ def test_single_query_zero_copy_path(B, pinned):
                 cols, vals, n = ix.search_kmers_hits(arr, k, h, [thr], cap=64)[0]
                 assert n == len(exp) and len(cols) == min(64, len(exp))
                 assert all(cnt[c] == v and v >= thr for c, v in zip(cols, vals))
-            assert ix.info()["last_fused"] & 8  # streamed launch: gather kernel + reduce kernel
+            assert ix.info()["last_fused"] & 8  # streamed launch: gather kernel + flush kernel
             # same answers from the staged path
             ix.set_option("zero_copy", 0)
             thr = int(math.ceil(n_kmers * 0.7))
@@ -640,6 +640,81 @@ def test_solo_path_geometries(B, opts):
             assert n == len(exp) and np.array_equal(cols, exp) and np.array_equal(vals, cnt[exp]), (opts, n_kmers)
             assert np.array_equal(ix.search_kmers(arr, k, h)[0].astype(np.int64), cnt.astype(np.int64))
             assert np.array_equal(ix.search_kmers(arr, k, h, mode=1)[0], oix.presence(_kmer_strs(arr)))
+    finally:
+        ix.close()
+
+
+def test_deferred_stream_of_single_queries(B):
+    """The deferred entry point (bigsi_b200_query_kmers_hits_stream_dev + bigsi_b200_index_flush): stage 2 of query s is
+    executed by the merge team of query s+1's kernel, or by the flush kernel.  A burst of queries of very different
+    sizes without any host synchronisation -- tiny grids (several kernels resident at once), queries too long for the
+    team variant (flushed by the next launch), an AND-mode call and a batch in between (both flush first), ring slots
+    and state blocks rotating several times -- every hit list against the oracle, and identical with option defer = 0."""
+    import torch
+
+    from bigsi_b200.sharded import DeviceShard, unpack_hits
+
+    rng = np.random.default_rng(307)
+    m, N, k, h, cap = 20_011, 6000, 31, 3, 4096
+    ix, packed = _random_index(B, rng, m, N, density=0.9)
+    oix = O.OracleIndex(k, m, h, N, rows=packed)
+    shard = DeviceShard(ix, k, h, cap=cap)
+    dev = shard.device
+    sizes = [3000, 1, 40, 9000, 148, 60_000, 5, 7000, 2500, 149, 33, 45_000, 4000, 4000, 1, 6000, 800, 12_000, 7, 3000, 3000, 90]
+    queries = [_rand_kmers(rng, n, k) for n in sizes]
+    d_queries = [torch.from_numpy(a).to(dev) for a in queries]
+    expected = []
+    for a, n in zip(queries, sizes):
+        cnt = oix.counts(_kmer_strs(a))
+        thr = int(math.ceil(n * 0.8))
+        expected.append((thr, cnt, np.nonzero(cnt >= thr)[0]))
+    d_and = torch.empty((1, (N + 7) // 8 + 16), dtype=torch.uint8, device=dev)
+    d_qoff1 = torch.tensor([0, sizes[0]], dtype=torch.int64, device=dev)
+    ix.set_option("inputs_ready", 1)
+    try:
+        for defer in (1, 0):
+            ix.set_option("defer", defer)
+            bufs = []
+            for j, n in enumerate(sizes):
+                bufs.append(shard.search_kmers_hits_stream(d_queries[j], expected[j][0]))
+                if j % 8 == 7:
+                    # the ring of output buffers has 8 entries: consume before they come round again.  The NEWEST result
+                    # is only complete after the next streamed query or a flush; the seven before it are complete now
+                    # (in stream order), which is what this copy relies on -- then flush for the eighth.
+                    done = [b.clone() for b in bufs[-8:-1]]
+                    shard.flush()
+                    done.append(bufs[-1].clone())
+                    bufs[-8:] = done
+                if j == 4:  # an AND-mode query on the same handle: flushes the pending query first
+                    rows = shard.hash(d_queries[0])
+                    ix.query_dev(1, rows.data_ptr(), d_qoff1.data_ptr(), 1, sizes[0], h, d_and.data_ptr(), d_and.shape[1],
+                                 torch.cuda.current_stream().cuda_stream, sizes[0])
+                if j == 10:  # a batch (generic kernel) in between
+                    both = torch.cat([d_queries[2], d_queries[4]])
+                    qo = torch.tensor([0, sizes[2], sizes[2] + sizes[4]], dtype=torch.int64, device=dev)
+                    mn = torch.tensor([expected[2][0], expected[4][0]], dtype=torch.int32, device=dev)
+                    batch = shard.search_kmers_hits(both, qo, 2, mn, max(sizes[2], sizes[4])).clone()
+            shard.flush()
+            tail = [b.clone() for b in bufs[len(sizes) - len(sizes) % 8:]]
+            bufs[len(sizes) - len(sizes) % 8:] = tail
+            torch.cuda.synchronize()
+            assert B._lib.lib().bigsi_b200_index_status(ix.handle) == 0
+            for j, n in enumerate(sizes):
+                thr, cnt, exp = expected[j]
+                nh, cols, vals = unpack_hits(bufs[j].cpu().numpy(), 1, cap)
+                assert int(nh[0, 0]) == len(exp), (defer, j, n, int(nh[0, 0]), len(exp))
+                got = min(int(nh[0, 0]), cap)
+                order = np.argsort(cols[0, 0, :got])
+                if len(exp) <= cap:
+                    assert np.array_equal(cols[0, 0, :got][order], exp) and np.array_equal(vals[0, 0, :got][order], cnt[exp]), (defer, j)
+                else:  # more hits than the list holds (a 1-k-mer query): any `cap` distinct hits with their exact counts
+                    c = cols[0, 0, :got]
+                    assert len(set(c.tolist())) == cap and np.array_equal(vals[0, 0, :got], cnt[c]) and (cnt[c] >= thr).all(), (defer, j)
+            assert np.array_equal(d_and[0, : (N + 7) // 8].cpu().numpy(), oix.presence(_kmer_strs(queries[0])))
+            nb, cb, vb = unpack_hits(batch.cpu().numpy(), 2, cap)
+            for q, j in enumerate((2, 4)):
+                got = int(nb[0, q])
+                assert got == len(expected[j][2]) and np.array_equal(np.sort(cb[0, q, :got]), expected[j][2]), (defer, "batch", q)
     finally:
         ix.close()
 
@@ -754,7 +829,7 @@ def test_fused_exchange_shards_one_process(B, world):
 
 def test_exchange_times_out_instead_of_hanging(B):
     """A rank whose peer never launches its search gets an error code within a bounded time (no hung GPU):
-    rank 0's reduce kernel gives up waiting for rank 1's hit list, the handle reports BIGSI_B200_ERR_TIMEOUT
+    rank 0's stage 2 gives up waiting for rank 1's hit list, the handle reports BIGSI_B200_ERR_TIMEOUT
     from then on; a peer that waits for k-mers nobody sends times out the same way."""
     import time
 
