@@ -84,23 +84,55 @@ __global__ void __launch_bounds__(256) transpose_blooms_kernel(uint8_t *__restri
     }
 }
 
-// Wide variant: one warp = 256 rows x FOUR aligned 32-column words (128 columns), one CTA = 256 rows x 1 024
-// columns.  Lane l holds 32 bytes of the four filters l, l+32, l+64, l+96 of its warp's column range; per 32-row
-// block the four 32x32 transposes leave lane j with the 128 columns of row j, written as ONE 16-byte store
-// (the pitch is a multiple of 128 bytes and the first word a multiple of 4, so the address is 16-byte
-// aligned).  Words only partly inside [col0, col0 + n) fall back to the per-word read-modify-write.
-__global__ void __launch_bounds__(256) transpose_blooms_wide_kernel(uint8_t *__restrict__ matrix, uint64_t pitch,
+// Wide variant: one warp = 256 rows x EIGHT aligned 32-column words (256 columns), one CTA = 256 rows x 2 048
+// columns.  Lane l holds 32 bytes (one 256-bit load: a whole sector) of the eight filters l, l+32, ..., l+224 of its
+// warp's column range; per 32-row block the eight 32x32 transposes leave lane j with the 256 columns of row j,
+// written as ONE 32-byte store: a full sector.  (With four words per warp the 16-byte stores were partial-sector
+// writes and L2 filled every sector from DRAM first: ncu showed 3.4 GB read for 1.28 GB of filters.)  The pitch is a
+// multiple of 128 bytes and the first word a multiple of 8, so the address is 32-byte aligned; the filters' stride
+// is a multiple of 32.  Words only partly inside [col0, col0 + n) fall back to the per-word read-modify-write.
+constexpr int kTWords = 8;
+
+// 32x32 bit-matrix transpose across a warp in 3 instructions per step (rotate, shuffle, select): the SENDER rotates its
+// word so that the bits its partner wants sit where they will be stored (partner = lane ^ s: a lane with bit s clear
+// sends its word rotated right by s, the other one rotated left), the receiver selects with a per-lane mask.  Rotate
+// amounts and masks are per-lane constants of the five steps.  Same result as merge.cuh:warp_transpose32.
+struct Transpose32 {
+    uint32_t rot[5], msk[5];
+    __device__ __forceinline__ explicit Transpose32(uint32_t lane)
+    {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const uint32_t s = 16u >> i;
+            const uint32_t m = i == 0 ? 0x0000ffffu : i == 1 ? 0x00ff00ffu : i == 2 ? 0x0f0f0f0fu : i == 3 ? 0x33333333u : 0x55555555u;
+            const bool hi = (lane & s) != 0;
+            rot[i] = hi ? s : 32u - s;  // rotate-left amount of what this lane SENDS
+            msk[i] = hi ? m : ~m;       // bits this lane TAKES from what it receives
+        }
+    }
+    __device__ __forceinline__ uint32_t operator()(uint32_t x) const
+    {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const uint32_t z = __shfl_xor_sync(0xffffffffu, __funnelshift_l(x, x, rot[i]), 16 >> i);
+            x = lop3<0xCA>(msk[i], z, x);  // msk ? z : x
+        }
+        return x;
+    }
+};
+__global__ void __launch_bounds__(256, 3) transpose_blooms_wide_kernel(uint8_t *__restrict__ matrix, uint64_t pitch,
                                                                     uint64_t num_rows, uint64_t col0, uint64_t n_blooms,
                                                                     const uint8_t *__restrict__ blooms, uint64_t bloom_stride,
                                                                     uint64_t n_bits)
 {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t word0 = ((col0 >> 5) & ~3ull) + ((uint64_t)blockIdx.y * 8 + warp) * 4;  // first of this warp's 4 words
+    const uint64_t word0 = ((col0 >> 5) & ~(uint64_t)(kTWords - 1)) + ((uint64_t)blockIdx.y * 8 + warp) * kTWords;  // first of this warp's words
     const uint64_t r0 = (uint64_t)blockIdx.x * 256;
-    uint32_t w[4][8], vmask[4];
+    const Transpose32 transpose(lane);
+    uint32_t w[kTWords][8], vmask[kTWords];
     bool any = false, all = true;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < kTWords; ++g) {
         const uint64_t col = (word0 + g) * 32 + lane;
         const bool valid = col >= col0 && col < col0 + n_blooms;
         vmask[g] = __ballot_sync(0xffffffffu, valid);
@@ -108,31 +140,27 @@ __global__ void __launch_bounds__(256) transpose_blooms_wide_kernel(uint8_t *__r
         all &= vmask[g] == 0xffffffffu;
 #pragma unroll
         for (int s = 0; s < 8; ++s) w[g][s] = 0;
-        if (valid) {
-            const uint8_t *src = blooms + (col - col0) * bloom_stride + (r0 >> 3);
-            const uint4 a = ldg128_stream(src), b = ldg128_stream(src + 16);
-            w[g][0] = a.x; w[g][1] = a.y; w[g][2] = a.z; w[g][3] = a.w;
-            w[g][4] = b.x; w[g][5] = b.y; w[g][6] = b.z; w[g][7] = b.w;
-        }
+        if (valid) ldg256_stream(blooms + (col - col0) * bloom_stride + (r0 >> 3), w[g]);
     }
     if (!any) return;  // warp-uniform
+    const bool aligned = all && ((reinterpret_cast<uintptr_t>(matrix) + word0 * 4) & 31) == 0 && (pitch & 31) == 0;
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
         const uint64_t rb = r0 + 32 * s;
         uint32_t rowmask = 0xffffffffu;  // rows of this block below n_bits
         if (rb >= n_bits) rowmask = 0;
         else if (n_bits - rb < 32) rowmask = (1u << (uint32_t)(n_bits - rb)) - 1u;
-        uint32_t y[4];
+        uint32_t y[kTWords];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) y[g] = msb_first_swizzle(warp_transpose32(msb_first_swizzle(w[g][s]) & rowmask, lane));
+        for (int g = 0; g < kTWords; ++g) y[g] = msb_first_swizzle(transpose(msb_first_swizzle(w[g][s]) & rowmask));
         const uint64_t row = rb + lane;
         if (row < num_rows) {
             uint32_t *dst = reinterpret_cast<uint32_t *>(matrix + row * pitch + word0 * 4);
-            if (all) {
-                *reinterpret_cast<uint4 *>(dst) = make_uint4(y[0], y[1], y[2], y[3]);
+            if (aligned) {
+                stg256(dst, y);
             } else {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
+                for (int g = 0; g < kTWords; ++g) {
                     if (vmask[g] == 0) continue;
                     const uint32_t smask = msb_first_swizzle(vmask[g]);
                     dst[g] = vmask[g] == 0xffffffffu ? y[g] : ((dst[g] & ~smask) | (y[g] & smask));
@@ -150,9 +178,9 @@ cudaError_t launch_transpose_blooms(uint8_t *matrix, uint64_t pitch, uint64_t nu
     if (n_blooms == 0 || num_rows == 0) return cudaSuccess;
     const uint64_t row_blocks = (num_rows + 255) / 256;
     if ((bloom_stride & 31) || bloom_stride < row_blocks * 32) return cudaErrorInvalidValue;
-    if (kTransposeWide) {
-        const uint64_t w_first = (col0 >> 5) & ~3ull, w_end = (col0 + n_blooms + 31) >> 5;  // words [w_first, w_end)
-        const uint64_t gy = (w_end - w_first + 31) / 32;  // 8 warps x 4 words per CTA
+    if (kTransposeWide && (reinterpret_cast<uintptr_t>(d_blooms) & 31) == 0) {  // (256-bit loads need 32-byte aligned filters)
+        const uint64_t w_first = (col0 >> 5) & ~(uint64_t)(kTWords - 1), w_end = (col0 + n_blooms + 31) >> 5;  // words [w_first, w_end)
+        const uint64_t gy = (w_end - w_first + 8 * kTWords - 1) / (8 * kTWords);  // 8 warps x kTWords words per CTA
         if (row_blocks > 0x7fffffffull || gy > 65535) return cudaErrorInvalidConfiguration;
         transpose_blooms_wide_kernel<<<dim3((unsigned)row_blocks, (unsigned)gy), 256, 0, stream>>>(
             matrix, pitch, num_rows, col0, n_blooms, d_blooms, bloom_stride, n_bits);

@@ -90,6 +90,20 @@ __device__ __forceinline__ uint4 lds128(const void *p)
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
     return v;
 }
+// streaming 256-bit global load (sm_100: LDG.256), no L1 allocation; p 32-byte aligned
+__device__ __forceinline__ void ldg256_stream(const void *p, uint32_t (&v)[8])
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
+// 256-bit global store (STG.256): one full 32-byte sector per lane -- no partial-sector write, no fill read
+__device__ __forceinline__ void stg256(void *p, const uint32_t (&v)[8])
+{
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+                 "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
 // streaming 128-bit global load, no L1 allocation
 __device__ __forceinline__ uint4 ldg128_stream(const void *p)
 {

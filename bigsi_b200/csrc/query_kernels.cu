@@ -973,12 +973,14 @@ static cudaError_t launch_one(const QueryParams &p, int grid, cudaStream_t strea
         const dim3 g(grid), b(query_block_threads(p));
         const QueryParams &pv = prev ? *prev : p;
         constexpr int SHC = HC == 3 ? 3 : 0;  // (the streamed kernels exist for h = 3 and for any h)
-        if (MODE == kModeCounts && p.planes_per_slot > 8)
-            return launch_ex(gather_solo<MODE, SHC, kSegPlanes, false>, g, b, query_smem_bytes(p), stream, /*pdl=*/true,
-                             /*cooperative=*/false, p, pv);
-        if (MODE == kModeCounts)
+        if constexpr (MODE == kModeCounts) {
+            if (p.planes_per_slot > 8)
+                return launch_ex(gather_solo<MODE, SHC, kSegPlanes, false>, g, b, query_smem_bytes(p), stream, /*pdl=*/true,
+                                 /*cooperative=*/false, p, pv);
             return launch_ex(gather_solo<MODE, SHC, 8, true>, g, b, query_smem_bytes(p), stream, true, /*cooperative=*/p.self_merge != 0, p, pv);
-        return launch_ex(gather_solo<MODE, SHC, 8, false>, g, b, query_smem_bytes(p), stream, true, false, p, pv);
+        } else {
+            return launch_ex(gather_solo<MODE, SHC, 8, false>, g, b, query_smem_bytes(p), stream, true, false, p, pv);
+        }
     }
     return launch_ex(fused_query<MODE, HC>, dim3(grid), dim3(query_block_threads(p)), query_smem_bytes(p), stream,
                      /*pdl=*/true, /*cooperative=*/p.fuse_merge != 0 && !p.plain_launch, p);
