@@ -5,7 +5,7 @@ TAG=${1:-multi}; NS=${2:-"2"}
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-echo "== exchange / sharded tests"; timeout 900 python -m pytest tests -m gpu -q -k "exchange or sharded" > gpurun_out/${TAG}_pytest_multi.log 2>&1; tail -6 gpurun_out/${TAG}_pytest_multi.log
+echo "== exchange / sharded tests"; timeout 900 python -m pytest tests -m gpu -q -rA -k "exchange or sharded or golden or config1" 2>&1 | grep -v WARNING > gpurun_out/${TAG}_pytest_multi.log; tail -4 gpurun_out/${TAG}_pytest_multi.log
 for N in $NS; do
   echo "== bench N=$N"
   if [ "$N" = "1" ]; then
