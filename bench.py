@@ -274,8 +274,6 @@ def run_b200(args):
     shard = DeviceShard(index, K, H, cap=HIT_CAP)
     fused = world > 1 and args.exchange == "fused"
     searcher = ShardedSearcher(shard, dist if world > 1 else None, world, rank, fused_max_kmers=U if fused else 0)
-    if fused:
-        searcher.fused.enable_host_results()
 
     queries = make_queries(N_DISTINCT, U)
     d_queries = torch.from_numpy(queries).to(dev)  # resident k-mer bytes (value arm)
@@ -569,10 +567,11 @@ def run_e2e(args, index, searcher, shard, queries, h_queries, barrier, rank, wor
 
         def e2e_step(i):
             if fused:
-                # rank 0: the gather kernel reads the pinned host k-mers itself (zero copy) and pushes them to the peers; every
-                # rank's stage-2 code writes the all-gathered hit lists into mapped host memory; rank 0 consumes them with up
-                # to 6 searches in flight -- no copy operation in the stream, consecutive queries keep overlapping
+                # rank 0: the gather kernel reads the pinned host k-mers itself (zero copy) and pushes them to the peers; rank
+                # 0's stage-2 code writes the all-gathered hit lists into mapped host memory, where rank 0 consumes them with
+                # up to 6 searches in flight -- no copy operation in the stream, consecutive queries keep overlapping
                 ex = searcher.fused
+                ex.enable_host_results(rank == 0)
                 seqs = []
                 last = None
                 for j in range(QPS):
@@ -587,6 +586,7 @@ def run_e2e(args, index, searcher, shard, queries, h_queries, barrier, rank, wor
                         last = ex.wait_host(s_)
                     assert int(last[0, 0]) == 3 and int(last[world - 1, 0]) == 3  # 3 exact hits per shard, low word of n_hits
                 torch.cuda.synchronize()
+                ex.enable_host_results(False)
                 return last
             for j in range(QPS):
                 q = (i * QPS + j) % N_DISTINCT

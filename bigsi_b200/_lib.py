@@ -117,7 +117,7 @@ SIGNATURES = {
     "bigsi_b200_exchange_search_dev": (_int, [_vp, _vp, _u64, _int, _int, ctypes.c_uint32, _vp, c_void_pp,
                                               ctypes.POINTER(_u64)]),
     "bigsi_b200_exchange_reserve": (_int, [_vp, _u64, _int, _int]),
-    "bigsi_b200_exchange_host_results": (_int, [_vp]),
+    "bigsi_b200_exchange_host_results": (_int, [_vp, _int]),
     "bigsi_b200_exchange_last_seq": (_int, [_vp, ctypes.POINTER(_u64)]),
     "bigsi_b200_exchange_wait_host": (_int, [_vp, _u64, c_void_pp, ctypes.POINTER(_u64)]),
     "bigsi_b200_exchange_wait_ns": (_int, [_vp, ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),

@@ -157,6 +157,8 @@ struct Exchange {
     // block s % kStreamStates = [u64 seq][u64 pad][world x block_bytes]
     PinnedBuf h_gather;
     uint64_t h_gather_block = 0;
+    bool h_gather_on = false;    // searches launched while it is on also land in the host blocks
+    uint64_t h_gather_seq[kStreamStates] = {};  // host block b holds (or will hold) the result of this search number
 };
 constexpr uint64_t kExInboxes = kStreamRing, kExGenerations = 2 * kStreamRing;
 
@@ -2398,11 +2400,12 @@ static int exchange_search(bigsi_b200_index *ix, const char *d_kmers, uint64_t n
         ho.sinks[r] = exchange_slot(ex, r, seq);
         ho.gather_blocks[r] = reinterpret_cast<const unsigned long long *>(blocks + r * ex.block_bytes);
     }
-    if (ex.h_gather.p) {
+    if (ex.h_gather.p && ex.h_gather_on) {
         void *dp = nullptr;
         CK(cudaHostGetDevicePointer(&dp, static_cast<uint8_t *>(ex.h_gather.p) + (seq % kStreamStates) * ex.h_gather_block, 0));
         ho.host_gather = static_cast<unsigned long long *>(dp);
         ho.host_block_words = (uint32_t)(ex.block_bytes / 8);
+        ex.h_gather_seq[seq % kStreamStates] = seq;
     }
     const char *kmers = d_kmers;
     if (ex.rank == 0) {
@@ -2468,16 +2471,18 @@ int bigsi_b200_exchange_last_seq(bigsi_b200_index *ix, uint64_t *seq_out)
     return 0;
 }
 
-int bigsi_b200_exchange_host_results(bigsi_b200_index *ix)
+int bigsi_b200_exchange_host_results(bigsi_b200_index *ix, int enable)
 {
     if (int rc = check_index(ix)) return rc;
     Exchange &ex = ix->ex;
     if (!ex.local) return fail(BIGSI_B200_ERR_INVALID, "exchange not created");
-    if (ex.seq) return fail(BIGSI_B200_ERR_INVALID, "enable host results before the first search");
     DeviceGuard guard(ix->device);
-    ex.h_gather_block = round_up(16 + (uint64_t)ex.world * ex.block_bytes, 128);
-    cudaError_t e = ex.h_gather.reserve(ex.h_gather_block * kStreamStates);
-    if (e != cudaSuccess) return fail_cuda(e, "pinned result blocks");
+    if (enable && !ex.h_gather.p) {
+        ex.h_gather_block = round_up(16 + (uint64_t)ex.world * ex.block_bytes, 128);
+        cudaError_t e = ex.h_gather.reserve(ex.h_gather_block * kStreamStates);
+        if (e != cudaSuccess) return fail_cuda(e, "pinned result blocks");
+    }
+    ex.h_gather_on = enable != 0;
     return 0;
 }
 
@@ -2489,6 +2494,8 @@ int bigsi_b200_exchange_wait_host(bigsi_b200_index *ix, uint64_t seq, const void
     if (seq == 0 || seq > ex.seq || seq + kStreamStates <= ex.seq)
         return fail(BIGSI_B200_ERR_INVALID, "query %llu is not among the last %d searches (last: %llu)", (unsigned long long)seq,
                     kStreamStates, (unsigned long long)ex.seq);
+    if (ex.h_gather_seq[seq % kStreamStates] != seq)
+        return fail(BIGSI_B200_ERR_INVALID, "search %llu was launched with host results off", (unsigned long long)seq);
     DeviceGuard guard(ix->device);
     // the newest search has nobody behind it to run its stage 2: flush it (SPMD: every rank does, or searches on)
     if (ix->pending.have && ix->pending.p.gather_seq == seq && ix->pending.p.host_gather)

@@ -228,10 +228,11 @@ class FusedExchange:
         """Stage 2 of the last search as a kernel of its own (SPMD: every rank calls it)."""
         self.shard.index.flush()
 
-    def enable_host_results(self):
-        """Before the first search: every search's all-gathered hit lists are also written into mapped host memory by
-        the kernels themselves (no copy in the stream); see wait_host."""
-        self._lib.check(self._lib.lib().bigsi_b200_exchange_host_results(self.shard.index.handle))
+    def enable_host_results(self, on=True):
+        """The all-gathered hit lists of the searches launched while this is on are also written into mapped host
+        memory by the kernels themselves (no copy in the stream); see wait_host.  Per rank; costs the query's last
+        stage-2 CTA a system fence over PCIe, so ranks that do not read results on the host leave it off."""
+        self._lib.check(self._lib.lib().bigsi_b200_exchange_host_results(self.shard.index.handle, 1 if on else 0))
 
     def last_seq(self):
         s = self._ct.c_uint64(0)

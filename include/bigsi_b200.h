@@ -358,13 +358,14 @@ int bigsi_b200_exchange_search_dev(bigsi_b200_index *index, const char *d_kmers,
  * (growing frees device memory, which waits for every kernel on the device -- also for a kernel of ANOTHER shard of
  * this process on the same GPU that is itself waiting for this shard's launch). */
 int bigsi_b200_exchange_reserve(bigsi_b200_index *index, uint64_t max_kmers, int k, int h);
-/* Host results (optional, before the first search): every search's all-gathered hit lists are ALSO written by the
- * stage-2 code into mapped host memory -- no copy operation in the stream, so back-to-back searches keep overlapping
- * while the host consumes earlier results.  last_seq: the number of the latest search_dev call on this handle
+/* Host results (optional; enable = 1 / 0 at any time, per rank): the all-gathered hit lists of the searches launched
+ * while it is on are ALSO written by the stage-2 code into mapped host memory -- no copy operation in the stream, so
+ * back-to-back searches keep overlapping while the host consumes earlier results.  It costs the last stage-2 CTA of
+ * every query a system-scope fence over PCIe (~3 us): leave it off on ranks that do not consume results on the host.  last_seq: the number of the latest search_dev call on this handle
  * (1, 2, ...).  wait_host(seq): flushes the search if it is the newest one (SPMD: then every rank must flush or
  * search on), polls until its block is complete and returns a HOST pointer to `world` blocks in the layout
  * search_dev documents; valid until 8 more searches have been issued. */
-int bigsi_b200_exchange_host_results(bigsi_b200_index *index);
+int bigsi_b200_exchange_host_results(bigsi_b200_index *index, int enable);
 int bigsi_b200_exchange_last_seq(bigsi_b200_index *index, uint64_t *seq_out);
 int bigsi_b200_exchange_wait_host(bigsi_b200_index *index, uint64_t seq, const void **blocks_out, uint64_t *block_bytes_out);
 int bigsi_b200_exchange_wait_ns(bigsi_b200_index *index, uint64_t *wait_ns_out, uint64_t *queries_out);
