@@ -357,10 +357,13 @@ int plan_query(bigsi_b200_index *ix, int mode, uint64_t n_queries, uint64_t tota
     if (ix->opt_kmers_per_stage > 0) {
         G = (uint32_t)ix->opt_kmers_per_stage;
     } else {
-        // (a ring slot costs the producer warp ~0.4 us whatever it holds: below ~16 KB per slot the slot rate, not HBM,
-        // bounds the gather -- measured with h = 1 rows of 6 KB: 2 per slot 3.6 TB/s, 4 per slot 6 TB/s)
+        // A ring slot costs the producer warp ~0.4 us whatever it holds (empty-barrier wait, expect_tx, the serialised
+        // bulk-copy issue), which caps an SM at slot bytes / 0.4 us: 18.7 KB slots (one k-mer at h = 3, N = 50 000) = 47 GB/s
+        // per SM -- enough when all 148 SMs gather all the time (6.3 TB/s), but a streamed query's SMs spend 20 % of their
+        // time in prologue / flush / hand-over and the others could not make up for it: 34.4 us per query; two k-mers per
+        // slot (37.5 KB, 4 stages): 29.9 us = 6.27 TB/s.  (h = 1 rows of 6 KB: 2 per slot 3.6 TB/s, 4 per slot 6 TB/s.)
         for (uint32_t g = 8; g > 1; g >>= 1)
-            if (g * kmer_bytes <= 28672) {
+            if (g * kmer_bytes <= 40960) {
                 G = g;
                 break;
             }

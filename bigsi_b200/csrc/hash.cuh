@@ -88,15 +88,45 @@ __device__ __forceinline__ uint32_t comp_base4(uint32_t w)
 __device__ __forceinline__ void hash_one_kmer_regs(const uint8_t *s, int k, int h, uint32_t m, uint64_t magic, int canonical,
                                                    int32_t *ids)
 {
+    // The k bytes as eight little-endian words, zero padded: nine aligned 32-bit loads around s (the staging buffers
+    // are padded, so the words before / behind the k-mer exist) and one funnel shift per word, instead of k byte
+    // loads -- this code runs once per CTA on the critical path of the first bulk copy.
     uint32_t F[8], R[8];
+    {
+        const uint32_t addr = smem_u32(s);
+        const uint32_t base = addr & ~3u, sh = (addr & 3u) * 8u;
+        uint32_t W[9];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) F[j] = R[j] = 0;
+        for (int j = 0; j < 9; ++j) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(W[j]) : "r"(base + 4u * j));
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        if (i < k) {
-            F[i >> 2] |= (uint32_t)s[i] << (8 * (i & 3));
-            R[i >> 2] |= (uint32_t)s[k - 1 - i] << (8 * (i & 3));
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t w = __funnelshift_r(W[j], W[j + 1], sh);
+            const int nv = k - 4 * j;  // valid bytes of this word
+            F[j] = nv >= 4 ? w : nv <= 0 ? 0u : (w & ((1u << (8 * nv)) - 1u));
         }
+    }
+    // reverse string: byte i = s[k-1-i] = the fully reversed 32-byte block shifted down by 32-k bytes
+    {
+        uint32_t V[9];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) V[j] = __byte_perm(F[7 - j], 0, 0x0123);
+        V[8] = 0;
+        const uint32_t d = 32u - (uint32_t)k;  // 0 .. 31 bytes
+        if (d & 16u) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) V[j] = j + 4 < 8 ? V[j + 4] : 0u;
+        }
+        if (d & 8u) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) V[j] = j + 2 < 8 ? V[j + 2] : 0u;
+        }
+        if (d & 4u) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) V[j] = j + 1 < 8 ? V[j + 1] : 0u;
+        }
+        const uint32_t db = (d & 3u) * 8u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) R[j] = __funnelshift_r(V[j], V[j + 1], db);
     }
     bool fwd = true;
     if (canonical) {
@@ -115,19 +145,28 @@ __device__ __forceinline__ void hash_one_kmer_regs(const uint8_t *s, int k, int 
         k1 = rotl32(k1, 15);
         F[j] = k1 * 0x1b873593u;
     }
-    for (int seed = 0; seed < h; ++seed) {
-        uint32_t h1 = (uint32_t)seed;
+    // four seeds at a time: the block chain of one seed is 8 dependent steps, four independent chains fill the pipeline
+    for (int seed0 = 0; seed0 < h; seed0 += 4) {
+        uint32_t h1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) h1[u] = (uint32_t)(seed0 + u);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (j < nblocks) {
-                h1 ^= F[j];
-                h1 = rotl32(h1, 13);
-                h1 = h1 * 5u + 0xe6546b64u;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    h1[u] ^= F[j];
+                    h1[u] = rotl32(h1[u], 13);
+                    h1[u] = h1[u] * 5u + 0xe6546b64u;
+                }
             } else if (j == nblocks && rem) {
-                h1 ^= F[j];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) h1[u] ^= F[j];
             }
         }
-        ids[seed] = murmur_finish_fastmod(h1, (uint32_t)k, m, magic);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (seed0 + u < h) ids[seed0 + u] = murmur_finish_fastmod(h1[u], (uint32_t)k, m, magic);
     }
 }
 
