@@ -22,8 +22,9 @@ _STORES = {}  # name -> _HbmRows: a named store persists for the life of the pro
 class _HbmRows:
     """Mapping bytes -> bytes.  Keys b"<int>:bitarray" -> rows of a DeviceIndex (grown on demand), others -> dict."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, index_factory=None):
         self.device = device
+        self._make = index_factory or (lambda rows, cols, dev: DeviceIndex(rows, cols, device=dev))  # (tests inject a host stand-in)
         self.other = {}
         self.index = None
         self.rows_cap = 0       # rows the DeviceIndex holds
@@ -48,7 +49,7 @@ class _HbmRows:
         bytes_cap = max(self.bytes_cap, 16)
         while bytes_cap < nbytes:
             bytes_cap *= 2
-        new = DeviceIndex(rows_cap, bytes_cap * 8, device=self.device)
+        new = self._make(rows_cap, bytes_cap * 8, self.device)
         if self.index is not None:
             if self.row_len:
                 top = max(self.row_len) + 1
