@@ -174,7 +174,7 @@ struct bigsi_b200_index {
     bool timing = false;
     int64_t opt_debug_flags = 0;
     int64_t opt_prehash = 1, opt_fuse_merge = 1, opt_merge_chunk_bytes = 0, opt_solo = 1, opt_pool_pct = -1, opt_zero_copy = 1, opt_cooperative = 1;
-    int64_t opt_inputs_ready = 0, opt_spin_timeout_ms = 10000, opt_defer = 1, opt_direct = 1, opt_batch_reuse = 1, opt_self_merge = 0;
+    int64_t opt_inputs_ready = 0, opt_spin_timeout_ms = 10000, opt_defer = 1, opt_direct = 1, opt_batch_reuse = 1, opt_self_merge = 0, opt_push_repeat = 0, opt_push_all_warps = 0;
     // streamed single-query launches (query.cuh:kStreamRing): ring-buffered scratch + the completion / abort words
     DevBuf d_pool;            // kStreamRing x [ready flags: grid x u64][ids: grid x pool_share x h x i32]
     uint64_t pool_slot_bytes = 0;
@@ -674,6 +674,8 @@ int run_query(bigsi_b200_index *ix, int mode, const int32_t *d_rows, const char 
             return fail(BIGSI_B200_ERR_INVALID, "this query cannot run as a streamed single-query launch (prehash=%u grid=%d)",
                         p.prehash, grid);
         p.n_push = hits->n_push;
+        p.push_repeat = (uint32_t)ix->opt_push_repeat;
+        p.push_all_warps = (uint32_t)ix->opt_push_all_warps;
         p.n_gather = hits->n_gather;
         for (uint32_t i = 0; i < hits->n_gather; ++i) p.gather_blocks[i] = hits->gather_blocks[i];
         p.gather_seq = hits->gather_seq;
@@ -1066,6 +1068,8 @@ int bigsi_b200_index_set_option(bigsi_b200_index *ix, const char *key, int64_t v
     else if (!strcmp(key, "inputs_ready")) ix->opt_inputs_ready = value;
     else if (!strcmp(key, "self_merge")) ix->opt_self_merge = value;  // 1: a synchronous single query is merged by its own
                                                                       // kernel's team (cooperative launch) instead of the flush kernel
+    else if (!strcmp(key, "push_repeat")) ix->opt_push_repeat = value > 16 ? 16 : value;  // diagnostics
+    else if (!strcmp(key, "push_all_warps")) ix->opt_push_all_warps = value;             // diagnostics
     else if (!strcmp(key, "batch_reuse")) ix->opt_batch_reuse = value;
     else if (!strcmp(key, "direct")) ix->opt_direct = value;  // 0: batches merge every query (no direct finish)
     else if (!strcmp(key, "defer")) ix->opt_defer = value;  // 0: every streamed query is flushed at once (diagnostics)

@@ -137,6 +137,8 @@ struct QueryParams {
     // slice of the k-mer bytes into every peer's LL inbox ("low-latency" lines, hash.cuh:ll_store_line: no fence,
     // no flag); the peers' hashing reads its k-mer bytes from its own LL inbox and spins per 16-byte line
     uint32_t n_push;          // rank 0: number of peers (ll.out[0 .. n_push))
+    uint32_t push_repeat;     // diagnostics (option "push_repeat"): every line is stored this many times (emulates more peers)
+    uint32_t push_all_warps;  // diagnostics (option "push_all_warps"): 1 = the team's warp 0 pushes too (see gather_solo)
     LlRoute ll;               // hash.cuh: who sends the k-mer bytes to whom
     // result publication: after the merge the LAST CTA (of the reduce kernel, or of the generic kernel's merge
     // phase) copies the hit list of query 0 to every sink -- a block [0] = sequence flag, [1] = number of hits,

@@ -502,8 +502,9 @@ __device__ __forceinline__ void push_query_slice(const QueryParams &P, uint64_t 
 #pragma unroll
         for (int u = 0; u < kBatch; ++u)
             if (i0 + (uint64_t)nthreads * u < nvec)
-                for (uint32_t r = 0; r < P.n_push; ++r)
-                    ll_store_line(P.ll.out[r] + 2 * (l0 + i0 + (uint64_t)nthreads * u), v[u], P.ll.flag);
+                for (uint32_t rep = 0; rep <= P.push_repeat; ++rep)  // (push_repeat = 0 outside diagnostics)
+                    for (uint32_t r = 0; r < P.n_push; ++r)
+                        ll_store_line(P.ll.out[r] + 2 * (l0 + i0 + (uint64_t)nthreads * u), v[u], P.ll.flag);
     }
 }
 
@@ -769,9 +770,16 @@ gather_solo(const __grid_constant__ QueryParams P, const __grid_constant__ Query
         // gather kernel (the preceding grid) is complete and its planes are visible.  Its scratch lies behind the ring.
         if (P.n_push) {
             if (P.stream_wait_inputs) grid_dependency_wait();
+            // The team's warp 0 does NOT push: it executes the fences of the merge (staging, arrival, publication), and a
+            // fence waits for the warp's outstanding stores -- with 7 peers ~500 remote stores per warp over NVLink, which
+            // held rank 0's teams back by 8 us per query on 8 GPUs.  Warps 1-3 carry the push; they never fence.
             const uint32_t cnt = solo_range_cnt(P, blockIdx.x, P.total_kmers);
-            if (cnt) push_query_slice(P, (uint64_t)blockIdx.x * P.items_per_slice, cnt, threadIdx.x - n_gather, (uint32_t)kMergeTeamThreads);
-            if (threadIdx.x == n_gather) BIGSI_TS(6);
+            const uint32_t tt = threadIdx.x - n_gather;
+            if (cnt) {
+                if (P.push_all_warps) push_query_slice(P, (uint64_t)blockIdx.x * P.items_per_slice, cnt, tt, (uint32_t)kMergeTeamThreads);
+                else if (tt >= 32) push_query_slice(P, (uint64_t)blockIdx.x * P.items_per_slice, cnt, tt - 32, (uint32_t)kMergeTeamThreads - 32);
+            }
+            if (threadIdx.x == n_gather + 32) BIGSI_TS(6);
         }
         const WarpGroupTeam<kBarMergeTeam> T{n_gather, (uint32_t)kMergeTeamThreads};
         uint8_t *team_smem = ring + (size_t)P.n_stages * P.kmers_per_stage * P.h * P.tile_bytes;
