@@ -96,7 +96,8 @@ int bigsi_b200_index_get_info(const bigsi_b200_index *index, bigsi_b200_info *in
  * are gathered ONCE into scratch and the queries count over those -- shared row-gather reuse; 0 = never);
  * "direct" (default 1: batch queries that lie inside one slice are finished by the CTA that counted them; 0 = every
  * query goes through the merge); "defer" (default 1; 0 = deferred entry points flush at once); "self_merge" (default 0;
- * 1 = a synchronous single query is merged by its own kernel's team, cooperative launch, instead of the flush kernel); "pool_pct" (0..100: share of a single query's k-mers that the CTAs claim
+ * 1 = a synchronous single query is merged by its own kernel's team, cooperative launch, instead of the flush kernel);
+ * diagnostics of the multi-GPU query broadcast: "push_repeat" (every line stored 1 + value times), "push_all_warps"; "pool_pct" (0..100: share of a single query's k-mers that the CTAs claim
  * dynamically; default / > 100 = automatic: 12 for an isolated query of the synchronous host calls, 0 for streamed
  * back-to-back queries); "cooperative" (default 1: a generic-path kernel that merges behind its own grid barrier is
  * launched with the cooperative attribute, so the driver verifies that all its CTAs are co-resident; 0 = plain
