@@ -65,3 +65,26 @@ def test_shard_columns_and_merge():
     buf[1, 2 * Q + Q * cap : 2 * Q + Q * cap + 2] = [5, 6]
     n, c, v = unpack_hits(buf, Q, cap)
     assert n.tolist() == [[0, 0], [2, 0]] and c[1, 0].tolist() == [11, 12, 0] and v[1, 0].tolist() == [5, 6, 0]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside the GPU arm) on a small workload: one JSON line with
+    the keys of the bench contract; under a multi-rank launch only rank 0 prints."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--m", "100003",
+           "--cols", "1000", "--kmers", "300", "--gpus", "2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="0", WORLD_SIZE="2"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config",
+                "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["cols_per_gpu"] == 1000
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
